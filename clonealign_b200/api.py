@@ -1,0 +1,127 @@
+"""`clonealign()` / `run_clonealign()` host mirrors (R/clonealign.R:35-75, 184-305).
+
+Only what sits directly on either side of the hot path is mirrored here: input parsing into the
+cell x gene matrix, the call into `inference_tflow`, clone calling, the post-hoc correlations and the
+best-of-restarts selection.  Plotting, preprocessing and printing are out of scope.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from .inference import clone_assignment, inference_tflow
+
+
+class CloneAlignFit(dict):
+    """The reference's `clonealign_fit` list (R/clonealign.R:303): dict with attribute access."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __repr__(self):   # print.clonealign_fit, R/clonealign.R:348-357
+        N = len(self["clone"])
+        G = len(self["ml_params"]["mu"])
+        C = self["ml_params"]["clone_probs"].shape[1]
+        return (f"A clonealign_fit for {N} cells, {G} genes, and {C} clones\n"
+                "To access clone assignments, call x['clone']\n"
+                "To access ML parameter estimates, call x['ml_params']")
+
+
+def compute_correlations(Y, L, clones, clone_names):
+    """R/clonealign.R:318-334 — per-gene Pearson correlation of scaled expression with assigned copy number."""
+    clones = np.asarray(clones, dtype=object)
+    keep = clones != "unassigned"
+    Y = np.asarray(Y, dtype=np.float64)[keep]
+    idx = np.array([clone_names.index(c) for c in clones[keep]], dtype=int)
+    out = np.full(Y.shape[1], np.nan)
+    if Y.shape[0] < 2:
+        return out
+    with np.errstate(invalid="ignore", divide="ignore"):
+        Ys = (Y - Y.mean(axis=0)) / Y.std(axis=0, ddof=1)
+        for i in range(Y.shape[1]):
+            xv = np.asarray(L, dtype=np.float64)[i, idx]
+            yv = Ys[:, i]
+            if np.std(xv) == 0 or not np.all(np.isfinite(yv)) or np.std(yv) == 0:
+                continue
+            out[i] = np.corrcoef(xv, yv)[0, 1]
+    return out
+
+
+def clonealign(gene_expression_data, copy_number_data, max_iter=200, rel_tol=1e-6, gene_filter_threshold=0,
+               learning_rate=0.1, x=None, clone_allele=None, cov=None, ref=None, fix_alpha=False, dtype="float32",
+               saturate=True, saturation_threshold=6, K=None, mc_samples=1, verbose=True, initial_shrink=5,
+               clone_call_probability=0.95, data_init_mu=True, clone_names=None, gene_names=None, seed=None,
+               device=0, fix_ref_bug=False, **backend):
+    """Assign cells to clones (R/clonealign.R:184-305).
+
+    gene_expression_data: cell x gene count matrix (an R user passes a SingleCellExperiment whose
+    counts assay is transposed to this, :212-222).  copy_number_data: gene x clone matrix.
+    `fix_ref_bug=False` keeps the reference's `ref = cov` forwarding (:271) which makes the
+    alternate-allele count identically zero; pass True to forward `ref` as documented.
+    """
+    Y = np.asarray(gene_expression_data)
+    if Y.ndim != 2:
+        raise ValueError("Input gene_expression_data must be SingleCellExperiment, SummarizedExperiment, or matrix")
+    N, G = Y.shape
+    if K is None:
+        K = 1                                                                           # :226-232
+    L = np.asarray(copy_number_data, dtype=np.float64)
+    if L.ndim != 2:
+        raise ValueError("copy_number_data must be a matrix, data.frame or DataFrame.")
+    if L.shape[0] != G:
+        raise ValueError("copy_number_data must have same number of genes (rows) as gene_expression_data")
+    C = L.shape[1]
+    if clone_names is None:
+        clone_names = [f"clone_{chr(ord('a') + i)}" for i in range(C)]                  # :251-253
+    clone_names = list(clone_names)
+    if gene_names is None:
+        gene_names = [f"gene_{i + 1}" for i in range(G)]
+
+    res = inference_tflow(Y, L, max_iter=max_iter, rel_tol=rel_tol, learning_rate=learning_rate,
+                          gene_filter_threshold=gene_filter_threshold, x=x, clone_allele=clone_allele, cov=cov,
+                          ref=(ref if fix_ref_bug else cov), fix_alpha=fix_alpha, dtype=dtype, saturate_=saturate,
+                          saturation_threshold=saturation_threshold, K=K, mc_samples=mc_samples, verbose=verbose,
+                          initial_shrink=initial_shrink, data_init_mu=data_init_mu, seed=seed, device=device,
+                          gene_names=gene_names, **backend)                             # :262-280
+    fit = CloneAlignFit(res)
+    fit["clone"] = clone_assignment(res["ml_params"]["clone_probs"], clone_names, clone_call_probability)   # :283
+    fit["clone_names"] = clone_names
+    ridx = [gene_names.index(g) for g in res["retained_genes"]]
+    fit["correlations"] = compute_correlations(Y[:, ridx], L[ridx, :], fit["clone"], clone_names)          # :292-294
+    cor = fit["correlations"]
+    if np.any(~np.isnan(cor)) and np.nanquantile(cor, 0.25) < 0:                        # :296-300
+        warnings.warn("Less than 75% of genes positively correlated with expression - assignment may have failed")
+    return fit
+
+
+def run_clonealign(gene_expression_data, copy_number_data, initial_shrinks=(0, 5, 10), n_repeats=3,
+                   print_elbos=True, seed=None, devices=None, **kwargs):
+    """Best-of-restarts wrapper (R/clonealign.R:35-75).  Restarts are independent fits; `devices`
+    (list of CUDA ordinals) spreads them round-robin over GPUs (replicas only, no communication)."""
+    rng = np.random.default_rng(seed)
+    fits = []
+    i = 0
+    for is_ in initial_shrinks:
+        for _ in range(n_repeats):
+            dev = devices[i % len(devices)] if devices else kwargs.get("device", 0)
+            kw = dict(kwargs)
+            kw.update(initial_shrink=is_, seed=int(rng.integers(0, 2 ** 31 - 1)), device=dev)
+            fits.append(clonealign(gene_expression_data, copy_number_data, **kw))
+            i += 1
+    final_elbos = np.array([f["convergence_info"]["final_elbo"] for f in fits])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        median_correlations = np.array([np.nanmedian(f["correlations"]) for f in fits])
+    if print_elbos:
+        print("ELBOs:  " + " ".join(str(e) for e in final_elbos))
+    best = fits[int(np.argmax(final_elbos))]
+    best["multirun_info"] = {
+        "clone_prevalences_at_different_shrinks": [dict(zip(*np.unique(f["clone"], return_counts=True))) for f in fits],
+        "elbos": final_elbos,
+        "median_correlations": median_correlations,
+    }
+    return best

@@ -1,0 +1,1044 @@
+// clonealign_b200 core: device state + the C-ABI declared in include/clonealign_b200.h.
+//
+// One ca_handle == one TensorFlow session of the reference (R/inference-tflow.R:351-457) for one
+// cell shard on one GPU.  No CPU fallback exists: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <stdexcept>
+#include <type_traits>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/clonealign_b200.h"
+#include "common.cuh"
+#include "kernels_expgemm.cuh"
+#include "kernels_small.cuh"
+#include "kernels_tc.cuh"
+#include "kernels_ypass.cuh"
+
+using namespace ca;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct CaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+[[noreturn]] void fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw CaError(buf);
+}
+
+#define CUDA_OK(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) fail("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, \
+                                __LINE__, cudaGetErrorString(_e));                            \
+  } while (0)
+
+int report(const std::exception& e, char* err, size_t errlen) {
+  if (err && errlen) {
+    strncpy(err, e.what(), errlen - 1);
+    err[errlen - 1] = 0;
+  }
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (no link-time dependency; a single-GPU fit never touches it)
+// ------------------------------------------------------------------------------------------------
+struct Uid { char internal[128]; };   // ncclUniqueId (passed by value)
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Uid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+NcclApi& nccl() {
+  static NcclApi api;
+  if (api.lib) return api;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) fail("NCCL is required for world > 1 but libnccl.so.2 could not be loaded: %s", dlerror());
+  auto sym = [&](const char* s) {
+    void* p = dlsym(api.lib, s);
+    if (!p) fail("NCCL symbol %s not found", s);
+    return p;
+  };
+  api.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void**, int, Uid, int))sym("ncclCommInitRank");
+  api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+  api.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+  api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+  return api;
+}
+constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;
+#define NCCL_OK(expr)                                                              \
+  do {                                                                             \
+    int _r = (expr);                                                               \
+    if (_r != 0) fail("NCCL error %d at %s:%d: %s", _r, __FILE__, __LINE__, nccl().GetErrorString(_r)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// conversion kernels (ingest)
+// ------------------------------------------------------------------------------------------------
+template <typename Tin>
+__global__ void k_ingest_colmajor(const Tin* __restrict__ in, int64_t ld_in, int64_t N, int g0, int gcount,
+                                  float* __restrict__ out, int64_t ldY) {
+  // in: column-major chunk, element (n, gg) at in[gg*ld_in + n]; out[n][g0+gg]
+  __shared__ float tile[32][33];
+  int64_t nb = (int64_t)blockIdx.x * 32;
+  int gb = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int gg = gb + i;
+    int64_t n = nb + threadIdx.x;
+    tile[i][threadIdx.x] = (gg < gcount && n < N) ? (float)in[(int64_t)gg * ld_in + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int64_t n = nb + i;
+    int gg = gb + threadIdx.x;
+    if (n < N && gg < gcount) out[n * ldY + g0 + gg] = tile[threadIdx.x][i];
+  }
+}
+template <typename Tin>
+__global__ void k_ingest_rowmajor(const Tin* __restrict__ in, int64_t ld_in, int64_t rows, int G,
+                                  float* __restrict__ out, int64_t ldY) {
+  int64_t r = blockIdx.y;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x)
+    if (r < rows) out[r * ldY + g] = (float)in[r * ld_in + g];
+}
+// flags: bit0 non-integer or negative, bit1 value > 255, bit2 value > 65535
+__global__ void k_scan_y(const float* __restrict__ Y, int64_t ldY, int64_t N, int G, int* __restrict__ flags) {
+  int64_t r = blockIdx.y;
+  int f = 0;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+    float y = Y[r * ldY + g];
+    if (!(y >= 0.f) || y != floorf(y)) f |= 1;
+    if (y > 255.f) f |= 2;
+    if (y > 65535.f) f |= 4;
+  }
+  if (f) atomicOr(flags, f);
+}
+template <typename Tout>
+__global__ void k_narrow_y(const float* __restrict__ Y, int64_t ldY, int64_t N, Tout* __restrict__ out) {
+  int64_t r = blockIdx.y;
+  for (int64_t g = blockIdx.x * blockDim.x + threadIdx.x; g < ldY; g += (int64_t)gridDim.x * blockDim.x)
+    out[r * ldY + g] = (Tout)Y[r * ldY + g];
+}
+__global__ void k_colmajor_to_rowmajor_f(const double* __restrict__ in, int64_t rows, int cols, float* __restrict__ out,
+                                         int ld_out, int col_off) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  int64_t r = i % rows;
+  int c = (int)(i / rows);
+  out[r * ld_out + col_off + c] = (float)in[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct Prof {
+  std::string name;
+  cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct ca_handle {
+  ca_config cfg{};
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  int64_t N = 0, Ntot = 0, ldY = 0, Gld = 0, Nld = 0;
+  int G = 0, C = 0, S = 0, K = 0, P = 0, KP = 0, SC = 0, SCp = 0, J = 0, V = 0;
+  bool tc = false;
+  int ystore = CA_STORE_F32;
+  int poison = 0;
+  std::vector<void*> allocs;
+
+  void* Y = nullptr;
+  float *L = nullptr, *Bm = nullptr, *vA = nullptr, *s = nullptr, *colsum = nullptr, *snv = nullptr;
+  double const_sum = 0.0;
+  // trainable + Adam state + gradients
+  float *U = nullptr, *Vm = nullptr, *chi_raw = nullptr, *u = nullptr, *loc = nullptr, *lsd = nullptr, *t = nullptr;
+  float *m_U = nullptr, *v_U = nullptr, *m_V = nullptr, *v_V = nullptr, *m_chi = nullptr, *v_chi = nullptr;
+  float *m_u = nullptr, *v_u = nullptr, *m_loc = nullptr, *v_loc = nullptr, *m_lsd = nullptr, *v_lsd = nullptr;
+  float *m_t = nullptr, *v_t = nullptr;
+  float *g_U = nullptr, *g_V = nullptr, *g_chi = nullptr, *g_u = nullptr, *g_loc = nullptr, *g_lsd = nullptr, *g_t = nullptr;
+  // per-iteration scratch
+  float *eps_in = nullptr, *eps = nullptr, *mu = nullptr, *logmu = nullptr, *sig = nullptr;
+  float *Mx = nullptr, *shift = nullptr, *mm = nullptr, *Zx = nullptr, *Rx = nullptr, *dMx = nullptr, *dM_sum = nullptr;
+  __nv_bfloat16 *MxT_hi = nullptr, *MxT_lo = nullptr, *RxT = nullptr;
+  float *rowpart = nullptr, *colpart = nullptr, *YV = nullptr, *YtU = nullptr, *Fout = nullptr, *log_alpha = nullptr;
+  float* ar = nullptr;
+  double *gsum_part = nullptr, *elbo_part = nullptr, *gene_part = nullptr, *scal_elbo = nullptr, *cell_sum = nullptr,
+         *wsq = nullptr, *elbo_dev = nullptr;
+  int nCB = 1, nRB = 1, RB = 512, n_gene_blocks = 0, nsplit = 1;
+  int64_t n_epi_blocks = 0;
+  bool ydirty = true;
+  TcPlan tcplan;
+
+  std::vector<float> eps_queue;   // host-fed draws, S*G floats each
+  int64_t eps_q_head = 0;         // next draw to consume
+  uint64_t draw = 0;
+  int adam_t = 0;
+
+  void* comm = nullptr;
+  bool prof_on = false;
+  std::vector<Prof> prof;
+  int launches_last_step = 0;
+
+  template <typename T> T* alloc(size_t n, bool zero = true) {
+    void* p = nullptr;
+    size_t bytes = (n ? n : 1) * sizeof(T);
+    CUDA_OK(cudaMalloc(&p, bytes));
+    allocs.push_back(p);
+    if (zero) CUDA_OK(cudaMemsetAsync(p, 0, bytes, stream));
+    return (T*)p;
+  }
+  void release(void* p) {
+    for (auto& q : allocs)
+      if (q == p) { cudaFree(p); q = nullptr; }
+  }
+};
+
+namespace {
+
+struct LaunchScope {
+  ca_handle* h;
+  bool on;
+  size_t idx = 0;
+  LaunchScope(ca_handle* h_, const char* name) : h(h_), on(h_->prof_on) {
+    h->launches_last_step++;
+    if (on) {
+      Prof p;
+      p.name = name;
+      CUDA_OK(cudaEventCreate(&p.a));
+      CUDA_OK(cudaEventCreate(&p.b));
+      CUDA_OK(cudaEventRecord(p.a, h->stream));
+      h->prof.push_back(p);
+      idx = h->prof.size() - 1;
+    }
+  }
+  ~LaunchScope() {
+    if (on) cudaEventRecord(h->prof[idx].b, h->stream);
+  }
+};
+#define KCHECK() CUDA_OK(cudaGetLastError())
+
+template <typename F>
+void dispatch_y(ca_handle* h, F&& f) {
+  switch (h->ystore) {
+    case CA_STORE_F32: f((const float*)h->Y); break;
+    case CA_STORE_U16: f((const uint16_t*)h->Y); break;
+    case CA_STORE_U8: f((const uint8_t*)h->Y); break;
+    default: fail("bad y_store");
+  }
+}
+
+AdamHyper adam_hyper(ca_handle* h, bool apply) {
+  AdamHyper a;
+  int t = h->adam_t + 1;
+  double b1 = 0.9, b2 = 0.999;
+  a.lr_t = (float)(h->cfg.learning_rate * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t)));
+  a.b1 = 0.9f;
+  a.b2 = 0.999f;
+  a.eps = 1e-8f;
+  a.apply = apply ? 1 : 0;
+  return a;
+}
+
+// ---- the Y pass (K3) ---------------------------------------------------------------------------
+void run_ypass(ca_handle* h) {
+  if (h->KP == 0 || !h->ydirty) return;
+  dispatch_y(h, [&](auto* Yp) {
+    using T = typename std::remove_const<typename std::remove_pointer<decltype(Yp)>::type>::type;
+    if (h->KP == 1) {
+      LaunchScope ls(h, "ypass");
+      dim3 grid(h->nCB, h->nRB);
+      k_ypass_k1<T><<<grid, 256, 0, h->stream>>>(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
+      KCHECK();
+    } else {
+      {
+        LaunchScope ls(h, "ypass_rows");
+        k_ypass_rows_generic<T><<<(unsigned)ceil_div64(h->N, 8), 256, 0, h->stream>>>(Yp, h->ldY, h->N, h->G, h->KP, h->Vm,
+                                                                                 h->rowpart);
+        KCHECK();
+      }
+      {
+        LaunchScope ls(h, "ypass_cols");
+        dim3 grid((h->G + 127) / 128, h->nRB);
+        k_ypass_cols_generic<T><<<grid, 128, 0, h->stream>>>(Yp, h->ldY, h->N, h->G, h->KP, h->RB, h->U, h->colpart);
+        KCHECK();
+      }
+    }
+  });
+  h->ydirty = false;
+}
+
+// ---- forward: eps -> mu, Mx -> shift -> Zx -> (Y pass) -> epilogue -------------------------------
+void stage_eps(ca_handle* h, const float** eps_in) {
+  *eps_in = nullptr;
+  size_t per = (size_t)h->S * h->G;
+  if ((size_t)h->eps_q_head * per < h->eps_queue.size()) {
+    CUDA_OK(cudaMemcpyAsync(h->eps_in, h->eps_queue.data() + (size_t)h->eps_q_head * per, per * sizeof(float),
+                            cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));   // source is pageable host memory owned by the queue
+    h->eps_q_head++;
+    if ((size_t)h->eps_q_head * per >= h->eps_queue.size()) {
+      h->eps_queue.clear();
+      h->eps_q_head = 0;
+    }
+    *eps_in = h->eps_in;
+  }
+}
+
+void run_forward(ca_handle* h, int mode) {
+  const float* eps_in;
+  stage_eps(h, &eps_in);
+  {
+    LaunchScope ls(h, "alpha");
+    k_alpha<<<1, 32, 0, h->stream>>>(h->u, h->C, h->chi_raw, h->K, h->log_alpha, h->scal_elbo);
+    KCHECK();
+  }
+  {
+    LaunchScope ls(h, "sample_mu");
+    SampleMuArgs a;
+    a.G = h->G; a.C = h->C; a.S = h->S; a.K = h->K; a.KP = h->KP; a.SCp = h->SCp; a.J = h->J; a.Gld = h->Gld;
+    a.loc = h->loc; a.lsd = h->lsd; a.Vm = h->Vm; a.L = h->L; a.colsum = h->colsum; a.chi_raw = h->chi_raw;
+    a.eps_in = eps_in; a.seed = h->cfg.seed; a.draw = h->draw++;
+    a.eps_out = h->eps; a.mu = h->mu; a.logmu = h->logmu; a.sig = h->sig;
+    a.Mx = h->tc ? nullptr : h->Mx; a.MxT_hi = h->tc ? h->MxT_hi : nullptr; a.MxT_lo = h->tc ? h->MxT_lo : nullptr;
+    a.gene_part = h->gene_part;
+    k_sample_mu<<<h->n_gene_blocks, 256, 0, h->stream>>>(a);
+    KCHECK();
+  }
+  if (h->KP == 0) {
+    CUDA_OK(cudaMemsetAsync(h->shift, 0, sizeof(float) * h->N, h->stream));
+  } else if (h->K == 1 && h->P == 0) {
+    LaunchScope ls(h, "shift");
+    k_minmax<<<1, 1024, 0, h->stream>>>(h->Vm, h->G, h->mm);
+    KCHECK();
+    k_shift_k1<<<(unsigned)ceil_div64(h->N, 256), 256, 0, h->stream>>>(h->U, h->mm, h->N, h->shift);
+    KCHECK();
+  } else {
+    LaunchScope ls(h, "shift");
+    k_shift_general<<<(unsigned)ceil_div64(h->N, 8), 256, 0, h->stream>>>(h->U, h->Vm, h->N, h->G, h->KP, h->shift);
+    KCHECK();
+  }
+  {
+    LaunchScope ls(h, "lse_fwd");
+    if (h->tc) {
+      tc_launch_fwd(h->tcplan, h->U, h->Vm, h->shift, h->Zx, h->stream);
+    } else {
+      int Jc = (mode == EPI_TRAIN) ? h->J : h->SC;   // ELBO-only passes need just Z
+      dim3 grid((Jc + 63) / 64, (unsigned)ceil_div64(h->N, 64));
+      k_expgemm<true><<<grid, 256, 0, h->stream>>>(h->U, h->Vm, h->shift, h->Mx, h->Zx, h->N, h->G, Jc, h->J, h->KP);
+    }
+    KCHECK();
+  }
+  if (mode != EPI_INIT) run_ypass(h);
+  {
+    LaunchScope ls(h, mode == EPI_TRAIN ? "cell_epilogue" : (mode == EPI_EVAL ? "cell_epilogue_eval" : "gamma_init"));
+    EpiArgs a;
+    a.N = h->N; a.Nld = h->Nld; a.C = h->C; a.S = h->S; a.SCp = h->SCp; a.J = h->J; a.K = h->K; a.KP = h->KP; a.nCB = h->nCB;
+    a.fsplit = h->tc ? h->tcplan.fsplit : 1;
+    a.Zx = h->Zx; a.Bm = h->Bm; a.vA = h->vA; a.s = h->s; a.shift = h->shift; a.log_alpha = h->log_alpha; a.U = h->U;
+    a.rowpart = h->rowpart; a.t = h->t; a.gT = h->g_t; a.Rx = h->tc ? nullptr : h->Rx; a.gU = h->g_U; a.YV = h->YV;
+    a.Fout = h->Fout; a.RxT = h->tc ? h->RxT : nullptr; a.elbo_part = h->elbo_part; a.gsum_part = h->gsum_part;
+    size_t smem = epi_smem_bytes(h->SCp, h->C, h->J, h->tc);
+    unsigned grid = (unsigned)h->n_epi_blocks;
+    if (mode == EPI_TRAIN) k_cell_epilogue<EPI_TRAIN><<<grid, kEpiWarps * 32, smem, h->stream>>>(a);
+    else if (mode == EPI_EVAL) k_cell_epilogue<EPI_EVAL><<<grid, kEpiWarps * 32, smem, h->stream>>>(a);
+    else k_cell_epilogue<EPI_INIT><<<grid, kEpiWarps * 32, smem, h->stream>>>(a);
+    KCHECK();
+  }
+}
+
+void run_train(ca_handle* h, bool apply) {
+  h->launches_last_step = 0;
+  run_forward(h, EPI_TRAIN);
+  {
+    LaunchScope ls(h, "lse_bwd");
+    if (h->tc) {
+      tc_launch_bwd(h->tcplan, h->U, h->Vm, h->shift, h->dMx, h->stream);
+    } else {
+      dim3 grid((h->J + 63) / 64, (h->G + 63) / 64);
+      k_expgemm<false><<<grid, 256, 0, h->stream>>>(h->Vm, h->U, h->shift, h->Rx, h->dMx, h->G, h->N, h->J, h->J, h->KP);
+    }
+    KCHECK();
+  }
+  {
+    LaunchScope ls(h, "gene_grads");
+    GeneGradArgs a;
+    a.G = h->G; a.C = h->C; a.S = h->S; a.K = h->K; a.KP = h->KP; a.SCp = h->SCp; a.J = h->J; a.nsplit = h->nsplit; a.nRB = h->nRB;
+    a.dMx = h->dMx; a.colpart = h->colpart; a.mu = h->mu; a.sig = h->sig; a.eps = h->eps; a.lsd = h->lsd; a.L = h->L;
+    a.ar = h->ar; a.YtU = h->YtU; a.dM_out = h->dM_sum;
+    k_gene_grads<<<(h->G + 127) / 128, 128, 0, h->stream>>>(a);
+    KCHECK();
+    k_reduce_gsum<<<1, 1024, 0, h->stream>>>(h->gsum_part, h->n_epi_blocks, h->C, h->ar + (int64_t)h->G * (2 + h->KP));
+    KCHECK();
+  }
+  if (h->cfg.world > 1) {
+    LaunchScope ls(h, "allreduce");
+    size_t cnt = (size_t)h->G * (2 + h->KP) + h->C;
+    NCCL_OK(nccl().AllReduce(h->ar, h->ar, cnt, kNcclFloat32, kNcclSum, h->comm, h->stream));
+  }
+  {
+    LaunchScope ls(h, "adam");
+    AdamHyper hy = adam_hyper(h, apply);
+    k_wsq<<<1, 1024, 0, h->stream>>>(h->Vm, h->G, h->K, h->KP, h->wsq);
+    KCHECK();
+    ScalarAdamArgs sa;
+    sa.G = h->G; sa.C = h->C; sa.K = h->K; sa.n_total = (double)h->Ntot; sa.wsq = h->wsq;
+    sa.gsum = h->ar + (int64_t)h->G * (2 + h->KP);
+    sa.chi_raw = h->chi_raw; sa.m_chi = h->m_chi; sa.v_chi = h->v_chi; sa.g_chi = h->g_chi;
+    sa.u = h->u; sa.m_u = h->m_u; sa.v_u = h->v_u; sa.g_u = h->g_u; sa.h = hy;
+    GeneAdamArgs ga;
+    ga.G = h->G; ga.S = h->S; ga.K = h->K; ga.KP = h->KP; ga.ar = h->ar; ga.mu = h->mu; ga.logmu = h->logmu; ga.sig = h->sig;
+    ga.eps = h->eps; ga.colsum = h->colsum; ga.chi_raw = h->chi_raw; ga.loc = h->loc; ga.lsd = h->lsd; ga.Vm = h->Vm;
+    ga.m_loc = h->m_loc; ga.v_loc = h->v_loc; ga.m_lsd = h->m_lsd; ga.v_lsd = h->v_lsd; ga.m_V = h->m_V; ga.v_V = h->v_V;
+    ga.g_loc = h->g_loc; ga.g_lsd = h->g_lsd; ga.g_V = h->g_V; ga.h = hy;
+    // gene kernel reads chi_raw (old) -> must precede the scalar update
+    k_gene_adam<<<(h->G + 127) / 128, 128, 0, h->stream>>>(ga);
+    KCHECK();
+    k_scalar_adam<<<1, 32, 0, h->stream>>>(sa);
+    KCHECK();
+    if (apply) {
+      int64_t tot = h->N * h->C + h->N * h->KP;
+      k_cell_adam<<<(unsigned)ceil_div64(tot, 256), 256, 0, h->stream>>>(h->N, h->C, h->K, h->KP, h->t, h->m_t, h->v_t, h->g_t,
+                                                                       h->U, h->m_U, h->v_U, h->g_U, hy);
+      KCHECK();
+    }
+  }
+  if (apply) {
+    h->adam_t++;
+    h->ydirty = true;
+  }
+}
+
+void run_elbo_async(ca_handle* h) {
+  h->launches_last_step = 0;
+  run_forward(h, EPI_EVAL);
+  LaunchScope ls(h, "elbo_reduce");
+  k_reduce_partials<<<1, 1024, 0, h->stream>>>(h->elbo_part, h->n_epi_blocks, 1, h->cell_sum, h->const_sum);
+  KCHECK();
+  if (h->cfg.world > 1) NCCL_OK(nccl().AllReduce(h->cell_sum, h->cell_sum, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
+  k_elbo_final<<<1, 256, 0, h->stream>>>(h->cell_sum, h->gene_part, h->n_gene_blocks, h->scal_elbo, h->poison, h->elbo_dev);
+  KCHECK();
+}
+
+// ---- host <-> device helpers ---------------------------------------------------------------------
+void upload_colmajor(ca_handle* h, const double* src, int64_t rows, int cols, float* dst, int ld_dst, int col_off) {
+  if (!src || rows * cols == 0) return;
+  double* tmp = nullptr;
+  CUDA_OK(cudaMalloc(&tmp, sizeof(double) * rows * cols));
+  CUDA_OK(cudaMemcpyAsync(tmp, src, sizeof(double) * rows * cols, cudaMemcpyHostToDevice, h->stream));
+  k_colmajor_to_rowmajor_f<<<(unsigned)ceil_div64(rows * cols, 256), 256, 0, h->stream>>>(tmp, rows, cols, dst, ld_dst, col_off);
+  KCHECK();
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaFree(tmp));
+}
+
+// device row-major float [rows][ld] (columns col_off..col_off+cols) -> host column-major double
+void download_colmajor(ca_handle* h, const float* src, int64_t rows, int cols, int ld, int col_off, double* out) {
+  if (!out || rows * cols == 0) return;
+  std::vector<float> tmp((size_t)rows * ld);
+  CUDA_OK(cudaMemcpyAsync(tmp.data(), src, sizeof(float) * rows * ld, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < cols; ++c)
+    for (int64_t r = 0; r < rows; ++r) out[(int64_t)c * rows + r] = (double)tmp[(size_t)r * ld + col_off + c];
+}
+
+template <typename Tin>
+void ingest_y(ca_handle* h, const Tin* Ysrc, float* Yf) {
+  const ca_config& c = h->cfg;
+  const int64_t N = h->N;
+  const int G = h->G;
+  const bool on_dev = c.y_mem == CA_Y_DEVICE;
+  if (c.y_layout == CA_Y_COLMAJOR) {
+    int64_t ld = c.y_ld ? c.y_ld : N;
+    int gchunk = (int)std::max<int64_t>(1, std::min<int64_t>(G, (int64_t)(256ll << 20) / (int64_t)(sizeof(Tin) * N)));
+    Tin* stage = nullptr;
+    if (!on_dev) CUDA_OK(cudaMalloc(&stage, sizeof(Tin) * (size_t)gchunk * N));
+    for (int g0 = 0; g0 < G; g0 += gchunk) {
+      int gc = std::min(gchunk, G - g0);
+      const Tin* src;
+      int64_t ld_in;
+      if (on_dev) {
+        src = Ysrc + (int64_t)g0 * ld;
+        ld_in = ld;
+      } else {
+        CUDA_OK(cudaMemcpy2DAsync(stage, sizeof(Tin) * N, Ysrc + (int64_t)g0 * ld, sizeof(Tin) * ld, sizeof(Tin) * N, gc,
+                                  cudaMemcpyHostToDevice, h->stream));
+        src = stage;
+        ld_in = N;
+      }
+      dim3 grid((unsigned)ceil_div64(N, 32), (gc + 31) / 32), blk(32, 8);
+      k_ingest_colmajor<Tin><<<grid, blk, 0, h->stream>>>(src, ld_in, N, g0, gc, Yf, h->ldY);
+      KCHECK();
+      CUDA_OK(cudaStreamSynchronize(h->stream));
+    }
+    if (stage) CUDA_OK(cudaFree(stage));
+  } else {
+    int64_t ld = c.y_ld ? c.y_ld : G;
+    int64_t rchunk = std::max<int64_t>(1, std::min<int64_t>(N, (int64_t)(256ll << 20) / (int64_t)(sizeof(Tin) * ld)));
+    rchunk = std::min<int64_t>(rchunk, 65535);
+    Tin* stage = nullptr;
+    if (!on_dev) CUDA_OK(cudaMalloc(&stage, sizeof(Tin) * (size_t)rchunk * ld));
+    for (int64_t r0 = 0; r0 < N; r0 += rchunk) {
+      int64_t rc = std::min(rchunk, N - r0);
+      const Tin* src;
+      if (on_dev) {
+        src = Ysrc + r0 * ld;
+      } else {
+        CUDA_OK(cudaMemcpyAsync(stage, Ysrc + r0 * ld, sizeof(Tin) * (size_t)rc * ld, cudaMemcpyHostToDevice, h->stream));
+        src = stage;
+      }
+      dim3 grid(std::min((G + 255) / 256, 64), (unsigned)rc);
+      k_ingest_rowmajor<Tin><<<grid, 256, 0, h->stream>>>(src, ld, rc, G, Yf + r0 * h->ldY, h->ldY);
+      KCHECK();
+      CUDA_OK(cudaStreamSynchronize(h->stream));
+    }
+    if (stage) CUDA_OK(cudaFree(stage));
+  }
+}
+
+void destroy(ca_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->dev);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm) nccl().CommDestroy(h->comm);
+  tc_plan_destroy(h->tcplan);
+  for (auto& p : h->prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (void* p : h->allocs)
+    if (p) cudaFree(p);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+void build(ca_handle* h, const void* Y, const double* L, const double* psi_init, const double* loc_init, const double* X,
+           const double* colsum_total, const double* clone_allele, const double* alt, const double* cov) {
+  const ca_config& c = h->cfg;
+  if (c.N <= 0 || c.G <= 0 || c.C <= 0 || c.S <= 0 || c.K < 0 || c.P < 0) fail("bad dimensions");
+  if (c.K + c.P > kMaxKP) fail("K + P = %d exceeds the supported maximum of %d", c.K + c.P, kMaxKP);
+  if (c.world < 1 || c.rank < 0 || c.rank >= c.world) fail("bad rank/world");
+  if (c.world > 1 && !c.nccl_id) fail("world > 1 requires cfg.nccl_id");
+  if (c.world > 1 && !colsum_total) fail("world > 1 requires colsum_total (global column sums of Y)");
+  if (!Y || !L || !loc_init || (c.K > 0 && !psi_init) || (c.P > 0 && !X)) fail("missing input pointer");
+  if (c.V > 0 && (!clone_allele || !alt || !cov)) fail("V > 0 requires clone_allele, alt and cov");
+  int ndev = 0;
+  CUDA_OK(cudaGetDeviceCount(&ndev));
+  if (c.device < 0 || c.device >= ndev) fail("CUDA device %d not available (%d devices)", c.device, ndev);
+  h->dev = c.device;
+  CUDA_OK(cudaSetDevice(h->dev));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, h->dev));
+  if (prop.major != 10) fail("clonealign_b200 kernels are built for sm_100a only; device %d is sm_%d%d", h->dev, prop.major, prop.minor);
+  CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+
+  h->N = c.N; h->Ntot = c.N_total > 0 ? c.N_total : c.N; h->G = c.G; h->C = c.C; h->S = c.S; h->K = c.K; h->P = c.P;
+  h->KP = c.K + c.P; h->SC = c.S * c.C; h->V = c.V;
+  bool tc_ok = (c.K == 1 && c.P == 0 && round_up64(h->SC, 16) <= 128);
+  if (c.path == CA_PATH_TENSOR && !tc_ok) fail("tensor path needs K == 1, P == 0 and S*C <= 128");
+  h->tc = (c.path == CA_PATH_TENSOR) || (c.path == CA_PATH_AUTO && tc_ok);
+  h->SCp = h->tc ? (int)round_up64(h->SC, 16) : h->SC;
+  h->J = h->SCp * (1 + h->KP);
+  h->ldY = round_up64(h->G, 16);
+  h->Gld = round_up64(h->G, 64);
+  h->Nld = round_up64(h->N, 64);
+  const int64_t N = h->N;
+  const int G = h->G, C = h->C, S = h->S, K = h->K, KP = h->KP, J = h->J;
+
+  // ---- Y -> device fp32 [N][ldY] ----
+  float* Yf = h->alloc<float>((size_t)N * h->ldY);
+  switch (c.y_dtype) {
+    case CA_Y_F64: ingest_y<double>(h, (const double*)Y, Yf); break;
+    case CA_Y_F32: ingest_y<float>(h, (const float*)Y, Yf); break;
+    case CA_Y_I32: ingest_y<int>(h, (const int*)Y, Yf); break;
+    default: fail("bad y_dtype");
+  }
+  // ---- narrow storage if exact ----
+  int* flags = h->alloc<int>(1);
+  {
+    dim3 grid(std::min((G + 255) / 256, 64), 1);
+    // grid.y is limited to 65535: loop over row chunks
+    for (int64_t r0 = 0; r0 < N; r0 += 65535) {
+      grid.y = (unsigned)std::min<int64_t>(65535, N - r0);
+      k_scan_y<<<grid, 256, 0, h->stream>>>(Yf + r0 * h->ldY, h->ldY, grid.y, G, flags);
+      KCHECK();
+    }
+  }
+  int hflags = 0;
+  CUDA_OK(cudaMemcpyAsync(&hflags, flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  int want = c.y_store;
+  if (want == CA_STORE_AUTO) want = (hflags & 1) ? CA_STORE_F32 : ((hflags & 2) ? ((hflags & 4) ? CA_STORE_F32 : CA_STORE_U16) : CA_STORE_U8);
+  if (want == CA_STORE_U8 && (hflags & 3)) fail("y_store = u8 requested but Y has non-integer, negative or > 255 entries");
+  if (want == CA_STORE_U16 && (hflags & 5)) fail("y_store = u16 requested but Y has non-integer, negative or > 65535 entries");
+  h->ystore = want;
+  h->Y = Yf;
+
+  // ---- small inputs ----
+  h->L = h->alloc<float>((size_t)G * C);
+  upload_colmajor(h, L, G, C, h->L, C, 0);
+  std::vector<float> logL((size_t)G * C);
+  for (int g = 0; g < G; ++g)
+    for (int cc = 0; cc < C; ++cc) {
+      double l = L[(size_t)cc * G + g];
+      if (!(l > 0.0)) h->poison = 1;   // copy number 0 => 0*log(0) = NaN in the reference
+      logL[(size_t)g * C + cc] = l > 0.0 ? (float)log(l) : 0.f;
+    }
+  float* d_logL = h->alloc<float>((size_t)G * C);
+  CUDA_OK(cudaMemcpyAsync(d_logL, logL.data(), sizeof(float) * G * C, cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+
+  h->Bm = h->alloc<float>((size_t)N * C);
+  h->vA = h->alloc<float>((size_t)N * C);
+  h->s = h->alloc<float>(N);
+  h->colsum = h->alloc<float>(G);
+  double* cst = h->alloc<double>(N);
+  k_setup_rows<float><<<(unsigned)N, 256, 0, h->stream>>>(Yf, h->ldY, N, G, C, d_logL, h->s, cst, h->Bm);
+  KCHECK();
+  {
+    double* csum = h->alloc<double>(1);
+    k_reduce_partials<<<1, 1024, 0, h->stream>>>(cst, N, 1, csum, 0.0);
+    KCHECK();
+    CUDA_OK(cudaMemcpyAsync(&h->const_sum, csum, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->release(csum);
+  }
+  h->release(cst);
+  h->release(d_logL);
+  if (colsum_total) {
+    std::vector<float> cs(G);
+    for (int g = 0; g < G; ++g) cs[g] = (float)colsum_total[g];
+    CUDA_OK(cudaMemcpyAsync(h->colsum, cs.data(), sizeof(float) * G, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+  } else {
+    const int RS = 64;
+    double* part = h->alloc<double>((size_t)RS * G);
+    dim3 grid((G + 127) / 128, RS);
+    k_colsum_part<float><<<grid, 128, 0, h->stream>>>(Yf, h->ldY, N, G, RS, part);
+    KCHECK();
+    k_colsum_final<<<(G + 127) / 128, 128, 0, h->stream>>>(part, RS, G, h->colsum);
+    KCHECK();
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->release(part);
+  }
+  if (c.V > 0) {
+    int V = c.V;
+    float* d_alt = h->alloc<float>((size_t)N * V);
+    float* d_cov = h->alloc<float>((size_t)N * V);
+    float* d_cn = h->alloc<float>((size_t)V * C);
+    upload_colmajor(h, alt, N, V, d_alt, V, 0);
+    upload_colmajor(h, cov, N, V, d_cov, V, 0);
+    upload_colmajor(h, clone_allele, V, C, d_cn, C, 0);
+    k_allele<<<(unsigned)N, 128, 0, h->stream>>>(d_alt, d_cov, d_cn, N, V, C, h->vA);
+    KCHECK();
+    h->snv = h->alloc<float>((size_t)N * C);
+    k_softmax_rows<<<(unsigned)ceil_div64(N, 128), 128, 0, h->stream>>>(h->vA, N, C, h->snv);
+    KCHECK();
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->release(d_alt);
+    h->release(d_cov);
+    h->release(d_cn);
+  }
+  // narrow Y after the setup passes that read it as fp32
+  if (h->ystore != CA_STORE_F32) {
+    dim3 grid(std::min<int64_t>((h->ldY + 255) / 256, 64), 1);
+    void* Yn = nullptr;
+    if (h->ystore == CA_STORE_U16) Yn = h->alloc<uint16_t>((size_t)N * h->ldY, false);
+    else Yn = h->alloc<uint8_t>((size_t)N * h->ldY, false);
+    for (int64_t r0 = 0; r0 < N; r0 += 65535) {
+      grid.y = (unsigned)std::min<int64_t>(65535, N - r0);
+      if (h->ystore == CA_STORE_U16) k_narrow_y<uint16_t><<<grid, 256, 0, h->stream>>>(Yf + r0 * h->ldY, h->ldY, grid.y, (uint16_t*)Yn + r0 * h->ldY);
+      else k_narrow_y<uint8_t><<<grid, 256, 0, h->stream>>>(Yf + r0 * h->ldY, h->ldY, grid.y, (uint8_t*)Yn + r0 * h->ldY);
+      KCHECK();
+    }
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->release(Yf);
+    h->Y = Yn;
+  }
+
+  // ---- parameters (R/inference-tflow.R:240-272) ----
+  auto z = [&](size_t n) { return h->alloc<float>(n); };
+  h->U = z((size_t)N * KP); h->m_U = z((size_t)N * KP); h->v_U = z((size_t)N * KP); h->g_U = z((size_t)N * KP);
+  h->Vm = z((size_t)G * KP); h->m_V = z((size_t)G * KP); h->v_V = z((size_t)G * KP); h->g_V = z((size_t)G * KP);
+  h->chi_raw = z(K); h->m_chi = z(K); h->v_chi = z(K); h->g_chi = z(K);
+  h->u = z(C); h->m_u = z(C); h->v_u = z(C); h->g_u = z(C);
+  h->loc = z(G); h->m_loc = z(G); h->v_loc = z(G); h->g_loc = z(G);
+  h->lsd = z(G); h->m_lsd = z(G); h->v_lsd = z(G); h->g_lsd = z(G);
+  h->t = z((size_t)N * C); h->m_t = z((size_t)N * C); h->v_t = z((size_t)N * C); h->g_t = z((size_t)N * C);
+  if (K > 0) upload_colmajor(h, psi_init, N, K, h->U, KP, 0);
+  if (c.P > 0) upload_colmajor(h, X, N, c.P, h->U, KP, K);
+  {
+    std::vector<float> lf(G);
+    for (int g = 0; g < G; ++g) lf[g] = (float)loc_init[g];
+    CUDA_OK(cudaMemcpyAsync(h->loc, lf.data(), sizeof(float) * G, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+  }
+
+  // ---- scratch ----
+  h->eps_in = z((size_t)S * G); h->eps = z((size_t)S * G); h->mu = z((size_t)S * G); h->logmu = z((size_t)S * G); h->sig = z((size_t)S * G);
+  h->shift = z(N); h->mm = z(2); h->log_alpha = z(C);
+  h->YV = z((size_t)N * std::max(KP, 1)); h->YtU = z((size_t)G * std::max(KP, 1)); h->Fout = z((size_t)N * C);
+  h->dM_sum = z((size_t)G * J);
+  h->n_gene_blocks = (G + 255) / 256;
+  h->n_epi_blocks = ceil_div64(N, kEpiWarps);
+  h->gene_part = h->alloc<double>(h->n_gene_blocks);
+  h->elbo_part = h->alloc<double>(h->n_epi_blocks);
+  h->gsum_part = h->alloc<double>((size_t)h->n_epi_blocks * C);
+  h->scal_elbo = h->alloc<double>(1); h->cell_sum = h->alloc<double>(1); h->wsq = h->alloc<double>(std::max(K, 1));
+  h->elbo_dev = h->alloc<double>(1);
+  h->ar = z((size_t)G * (2 + KP) + C + 4);
+  if (KP == 1) {
+    h->nCB = (int)ceil_div64(h->ldY, kYCB);
+    h->RB = 512;
+  } else {
+    h->nCB = 1;
+    h->RB = 1024;
+  }
+  h->nRB = (int)ceil_div64(N, h->RB);
+  h->rowpart = z((size_t)h->nCB * N * std::max(KP, 1));
+  h->colpart = z((size_t)h->nRB * G * std::max(KP, 1));
+  if (h->tc) {
+    h->MxT_hi = h->alloc<__nv_bfloat16>((size_t)J * h->Gld);
+    h->MxT_lo = h->alloc<__nv_bfloat16>((size_t)h->SCp * h->Gld);
+    h->RxT = h->alloc<__nv_bfloat16>((size_t)J * h->Nld);
+    tc_plan_create(h->tcplan, h->dev, N, h->Nld, G, h->Gld, h->SCp, J, h->MxT_hi, h->MxT_lo, h->RxT);
+    h->nsplit = h->tcplan.nsplit;
+    h->Zx = z((size_t)h->tcplan.fsplit * N * J);
+    h->dMx = z((size_t)h->nsplit * G * J);
+  } else {
+    h->Mx = z((size_t)G * J);
+    h->Zx = z((size_t)N * J);
+    h->Rx = z((size_t)N * J);
+    h->dMx = z((size_t)G * J);
+    h->nsplit = 1;
+  }
+  size_t smem = epi_smem_bytes(h->SCp, C, J, h->tc);
+  if (smem > 48 * 1024) {
+    if (smem > 200 * 1024) fail("S*C too large for the per-cell epilogue (%zu bytes of shared memory)", smem);
+    CUDA_OK(cudaFuncSetAttribute(k_cell_epilogue<EPI_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(k_cell_epilogue<EPI_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(k_cell_epilogue<EPI_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  if (c.world > 1) {
+    Uid id;
+    memcpy(&id, c.nccl_id, sizeof id);
+    NCCL_OK(nccl().CommInitRank(&h->comm, c.world, id, c.rank));
+  }
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+}
+
+struct ArrayRef {
+  const float* p;
+  int64_t rows;
+  int cols, ld, off;
+  bool writable;
+};
+
+bool lookup(ca_handle* h, const std::string& n, ArrayRef& r) {
+  const int64_t N = h->N;
+  const int G = h->G, C = h->C, K = h->K, P = h->P, KP = h->KP, SC = h->SC, J = h->J;
+  auto set = [&](const float* p, int64_t rows, int cols, int ld, int off, bool w) { r = {p, rows, cols, ld, off, w}; return true; };
+  if (n == "W") return set(h->Vm, G, K, KP, 0, true);
+  if (n == "beta") return set(h->Vm, G, P, KP, K, true);
+  if (n == "psi") return set(h->U, N, K, KP, 0, true);
+  if (n == "chi_raw") return set(h->chi_raw, K, 1, 1, 0, true);
+  if (n == "alpha_unconstr") return set(h->u, C, 1, 1, 0, true);
+  if (n == "loc") return set(h->loc, G, 1, 1, 0, true);
+  if (n == "lsd") return set(h->lsd, G, 1, 1, 0, true);
+  if (n == "gamma_logits") return set(h->t, N, C, C, 0, true);
+  if (n == "grad_W") return set(h->g_V, G, K, KP, 0, false);
+  if (n == "grad_beta") return set(h->g_V, G, P, KP, K, false);
+  if (n == "grad_psi") return set(h->g_U, N, K, KP, 0, false);
+  if (n == "grad_chi_raw") return set(h->g_chi, K, 1, 1, 0, false);
+  if (n == "grad_alpha_unconstr") return set(h->g_u, C, 1, 1, 0, false);
+  if (n == "grad_loc") return set(h->g_loc, G, 1, 1, 0, false);
+  if (n == "grad_lsd") return set(h->g_lsd, G, 1, 1, 0, false);
+  if (n == "grad_gamma_logits") return set(h->g_t, N, C, C, 0, false);
+  if (n == "Z") return set(h->Zx, N, SC, J, 0, false);
+  if (n == "Zx") return set(h->Zx, N, J, J, 0, false);
+  if (n == "R" && h->Rx) return set(h->Rx, N, SC, J, 0, false);
+  if (n == "dM") return set(h->dM_sum, G, SC, J, 0, false);
+  if (n == "dMx") return set(h->dM_sum, G, J, J, 0, false);
+  if (n == "F") return set(h->Fout, N, C, C, 0, false);
+  if (n == "YV") return set(h->YV, N, KP, KP, 0, false);
+  if (n == "YtU") return set(h->YtU, G, KP, KP, 0, false);
+  if (n == "B") return set(h->Bm, N, C, C, 0, false);
+  if (n == "v") return set(h->vA, N, C, C, 0, false);
+  if (n == "s") return set(h->s, N, 1, 1, 0, false);
+  if (n == "colsum") return set(h->colsum, G, 1, 1, 0, false);
+  if (n == "shift") return set(h->shift, N, 1, 1, 0, false);
+  if (n == "mu_samples") return set(h->mu, h->S, G, G, 0, false);   // NOTE: returned as S x G column-major
+  return false;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int ca_core_abi_version(void) { return CA_ABI_VERSION; }
+
+int ca_core_device_count(int* count, char* err, size_t errlen) {
+  try {
+    int n = 0;
+    CUDA_OK(cudaGetDeviceCount(&n));
+    if (count) *count = n;
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_nccl_unique_id(void* out128, char* err, size_t errlen) {
+  try {
+    if (!out128) fail("null output");
+    NCCL_OK(nccl().GetUniqueId(out128));
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_create(ca_handle** out, const ca_config* cfg, const void* Y, const double* L, const double* psi_init,
+                   const double* loc_init, const double* X, const double* colsum_total, const double* clone_allele,
+                   const double* alt, const double* cov, char* err, size_t errlen) {
+  ca_handle* h = nullptr;
+  try {
+    if (!out || !cfg) fail("null argument");
+    h = new ca_handle();
+    h->cfg = *cfg;
+    build(h, Y, L, psi_init, loc_init, X, colsum_total, clone_allele, alt, cov);
+    h->cfg.nccl_id = nullptr;   // never retain caller pointers
+    *out = h;
+    return 0;
+  } catch (const std::exception& e) {
+    destroy(h);
+    return report(e, err, errlen);
+  }
+}
+
+int ca_core_destroy(ca_handle* h) {
+  destroy(h);
+  return 0;
+}
+
+int ca_core_init_gamma(ca_handle* h, char* err, size_t errlen) {
+  try {
+    if (!h) fail("null handle");
+    CUDA_OK(cudaSetDevice(h->dev));
+    run_forward(h, EPI_INIT);
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_step(ca_handle* h, char* err, size_t errlen) {
+  try {
+    if (!h) fail("null handle");
+    CUDA_OK(cudaSetDevice(h->dev));
+    run_train(h, true);
+    return 0;   // asynchronous: the next call on this handle is stream-ordered behind it
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_grads(ca_handle* h, char* err, size_t errlen) {
+  try {
+    if (!h) fail("null handle");
+    CUDA_OK(cudaSetDevice(h->dev));
+    run_train(h, false);
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_elbo(ca_handle* h, double* elbo, char* err, size_t errlen) {
+  try {
+    if (!h || !elbo) fail("null argument");
+    CUDA_OK(cudaSetDevice(h->dev));
+    run_elbo_async(h);
+    CUDA_OK(cudaMemcpyAsync(elbo, h->elbo_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_params(ca_handle* h, double* mu, double* clone_probs, double* s, double* alpha, double* psi, double* W,
+                   double* chi, double* beta, double* clone_probs_from_snv, char* err, size_t errlen) {
+  try {
+    if (!h) fail("null handle");
+    CUDA_OK(cudaSetDevice(h->dev));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    const int64_t N = h->N;
+    const int G = h->G, C = h->C, K = h->K, KP = h->KP;
+    if (mu) {   // tf$nn$softplus(qmu$distribution$loc), R/inference-tflow.R:424
+      std::vector<double> tmp(G);
+      download_colmajor(h, h->loc, G, 1, 1, 0, tmp.data());
+      for (int g = 0; g < G; ++g) { double x = tmp[g]; mu[g] = x > 0 ? x + log1p(exp(-x)) : log1p(exp(x)); }
+    }
+    if (clone_probs) {   // softmax(gamma_logits), :273,424
+      std::vector<double> tmp((size_t)N * C);
+      download_colmajor(h, h->t, N, C, C, 0, tmp.data());
+      for (int64_t n = 0; n < N; ++n) {
+        double mx = -1e300, z = 0;
+        for (int c = 0; c < C; ++c) mx = std::max(mx, tmp[(size_t)c * N + n]);
+        for (int c = 0; c < C; ++c) z += exp(tmp[(size_t)c * N + n] - mx);
+        for (int c = 0; c < C; ++c) clone_probs[(size_t)c * N + n] = exp(tmp[(size_t)c * N + n] - mx) / z;
+      }
+    }
+    if (s) download_colmajor(h, h->s, N, 1, 1, 0, s);
+    if (alpha) {   // exp(log_softmax(alpha_unconstr))
+      std::vector<double> tmp(C);
+      download_colmajor(h, h->u, C, 1, 1, 0, tmp.data());
+      double mx = -1e300, z = 0;
+      for (int c = 0; c < C; ++c) mx = std::max(mx, tmp[c]);
+      for (int c = 0; c < C; ++c) z += exp(tmp[c] - mx);
+      for (int c = 0; c < C; ++c) alpha[c] = exp(tmp[c] - mx) / z;
+    }
+    if (psi && K > 0) download_colmajor(h, h->U, N, K, KP, 0, psi);
+    if (W && K > 0) download_colmajor(h, h->Vm, G, K, KP, 0, W);
+    if (beta && h->P > 0) download_colmajor(h, h->Vm, G, h->P, KP, K, beta);
+    if (chi && K > 0) {
+      std::vector<double> tmp(K);
+      download_colmajor(h, h->chi_raw, K, 1, 1, 0, tmp.data());
+      for (int k = 0; k < K; ++k) chi[k] = exp(tmp[k]);
+    }
+    if (clone_probs_from_snv) {
+      if (!h->snv) fail("clone_probs_from_snv requested but the allele-specific likelihood is not in use");
+      download_colmajor(h, h->snv, N, C, C, 0, clone_probs_from_snv);
+    }
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_set_eps(ca_handle* h, const float* eps, int64_t n_draws, char* err, size_t errlen) {
+  try {
+    if (!h || !eps || n_draws < 0) fail("bad argument");
+    size_t per = (size_t)h->S * h->G;
+    h->eps_queue.insert(h->eps_queue.end(), eps, eps + per * (size_t)n_draws);
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_get_eps(ca_handle* h, float* eps, char* err, size_t errlen) {
+  try {
+    if (!h || !eps) fail("bad argument");
+    CUDA_OK(cudaSetDevice(h->dev));
+    CUDA_OK(cudaMemcpyAsync(eps, h->eps, sizeof(float) * h->S * h->G, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_get_array(ca_handle* h, const char* name, double* out, int64_t n, char* err, size_t errlen) {
+  try {
+    if (!h || !name || !out) fail("bad argument");
+    CUDA_OK(cudaSetDevice(h->dev));
+    ArrayRef r;
+    if (!lookup(h, name, r)) fail("unknown array '%s'", name);
+    if (n < r.rows * r.cols) fail("buffer too small for '%s': need %lld", name, (long long)(r.rows * r.cols));
+    download_colmajor(h, r.p, r.rows, r.cols, r.ld, r.off, out);
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_set_array(ca_handle* h, const char* name, const double* in, int64_t n, char* err, size_t errlen) {
+  try {
+    if (!h || !name || !in) fail("bad argument");
+    CUDA_OK(cudaSetDevice(h->dev));
+    ArrayRef r;
+    if (!lookup(h, name, r) || !r.writable) fail("array '%s' is not writable", name);
+    if (n != r.rows * r.cols) fail("size mismatch for '%s': expected %lld", name, (long long)(r.rows * r.cols));
+    upload_colmajor(h, in, r.rows, r.cols, const_cast<float*>(r.p), r.ld, r.off);
+    h->ydirty = true;
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_time_steps(ca_handle* h, int32_t n_steps, int32_t with_eval, double* ms, char* err, size_t errlen) {
+  try {
+    if (!h || !ms || n_steps < 0) fail("bad argument");
+    CUDA_OK(cudaSetDevice(h->dev));
+    cudaEvent_t a, b;
+    CUDA_OK(cudaEventCreate(&a));
+    CUDA_OK(cudaEventCreate(&b));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaEventRecord(a, h->stream));
+    for (int i = 0; i < n_steps; ++i) {
+      run_train(h, true);
+      if (with_eval) run_elbo_async(h);
+    }
+    CUDA_OK(cudaEventRecord(b, h->stream));
+    CUDA_OK(cudaEventSynchronize(b));
+    float f = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&f, a, b));
+    *ms = (double)f;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_profile_step(ca_handle* h, char* names, size_t names_len, double* ms, int32_t cap, int32_t* n_k, char* err,
+                         size_t errlen) {
+  try {
+    if (!h || !names || !ms || !n_k) fail("bad argument");
+    CUDA_OK(cudaSetDevice(h->dev));
+    for (auto& p : h->prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    h->prof.clear();
+    h->prof_on = true;
+    run_train(h, true);
+    h->prof_on = false;
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    std::string all;
+    int k = 0;
+    for (auto& p : h->prof) {
+      if (k >= cap) break;
+      float f = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&f, p.a, p.b));
+      ms[k++] = (double)f;
+      if (!all.empty()) all += ";";
+      all += p.name;
+    }
+    *n_k = k;
+    strncpy(names, all.c_str(), names_len - 1);
+    names[names_len - 1] = 0;
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_describe(ca_handle* h, char* json, size_t json_len) {
+  if (!h || !json || !json_len) return 1;
+  const char* st = h->ystore == CA_STORE_F32 ? "f32" : (h->ystore == CA_STORE_U16 ? "u16" : "u8");
+  int bpe = h->ystore == CA_STORE_F32 ? 4 : (h->ystore == CA_STORE_U16 ? 2 : 1);
+  snprintf(json, json_len,
+           "{\"N\": %lld, \"G\": %d, \"C\": %d, \"S\": %d, \"K\": %d, \"P\": %d, \"path\": \"%s\", \"y_store\": \"%s\", "
+           "\"y_bytes_per_entry\": %d, \"ldY\": %lld, \"launches_last_step\": %d, \"nsplit\": %d, \"world\": %d, \"rank\": %d}",
+           (long long)h->N, h->G, h->C, h->S, h->K, h->P, h->tc ? "tcgen05" : "cudacore", st, bpe, (long long)h->ldY,
+           h->launches_last_step, h->nsplit, h->cfg.world, h->cfg.rank);
+  return 0;
+}
+
+}  // extern "C"

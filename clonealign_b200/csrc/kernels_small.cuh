@@ -1,0 +1,670 @@
+// Setup, gene-level, per-cell epilogue and optimiser kernels (everything except the two
+// contractions and the Y stream).  Math: SURVEY.md Appendix A.2/A.3; reference graph nodes are
+// cited per kernel (paths relative to the reference repository).
+#pragma once
+#include "common.cuh"
+
+namespace ca {
+
+// =============================================================================================
+// setup (once per fit)
+// =============================================================================================
+
+// per cell: s_n = rowSums(Y) (R/inference-tflow.R:210), const_n = lgamma(s_n+1) - sum_g lgamma(y+1)
+// (Multinomial log_combinations, :294-296) and B_nc = sum_g y_ng log L_gc (the Y-linear part of
+// sum_g y log pi that does not depend on any trainable parameter).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_setup_rows(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int C,
+             const float* __restrict__ logL, float* __restrict__ s_out, double* __restrict__ cst,
+             float* __restrict__ Bm) {
+  __shared__ double scratch[32];
+  const int64_t n = blockIdx.x;
+  const T* row = Y + n * ldY;
+  for (int c0 = 0; c0 < C; c0 += 8) {
+    double acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+    double ssum = 0.0, lg = 0.0;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      float y = (float)row[g];
+      if (y != 0.f) {
+        if (c0 == 0) {
+          ssum += (double)y;
+          lg += lgamma((double)y + 1.0);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < C) acc[j] += (double)y * (double)logL[(int64_t)g * C + c0 + j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (c0 + j < C) {
+        double t = block_sum(acc[j], scratch);
+        if (threadIdx.x == 0) Bm[n * C + c0 + j] = (float)t;
+      }
+    }
+    if (c0 == 0) {
+      double st = block_sum(ssum, scratch);
+      double lt = block_sum(lg, scratch);
+      if (threadIdx.x == 0) {
+        s_out[n] = (float)st;
+        cst[n] = lgamma(st + 1.0) - lt;
+      }
+    }
+  }
+}
+
+// deterministic column sums of Y (two stages)
+template <typename T>
+__global__ void k_colsum_part(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RS,
+                              double* __restrict__ part) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  int rs = blockIdx.y;
+  int64_t rps = ceil_div64(N, RS);
+  int64_t r0 = rs * rps, r1 = r0 + rps < N ? r0 + rps : N;
+  if (g >= G) return;
+  double a = 0.0;
+  for (int64_t r = r0; r < r1; ++r) a += (double)(float)Y[r * ldY + g];
+  part[(int64_t)rs * G + g] = a;
+}
+__global__ void k_colsum_final(const double* __restrict__ part, int RS, int G, float* __restrict__ colsum) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  double a = 0.0;
+  for (int r = 0; r < RS; ++r) a += part[(int64_t)r * G + g];
+  colsum[g] = (float)a;
+}
+
+// allele-specific (beta-binomial) cell x clone log-likelihood, R/allele-specific.R:17-58.
+// One block per cell; alt/cov are [N][V] floats, cn is [V][C].  cov == 0 contributes exactly 0.
+__device__ __forceinline__ double bb_lp(double k, double n, double a, double b) {
+  return lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(n - k + 1.0) + lgamma(k + a) + lgamma(n - k + b) -
+         lgamma(a + b + n) - lgamma(a) - lgamma(b) + lgamma(a + b);
+}
+__global__ void __launch_bounds__(128)
+k_allele(const float* __restrict__ alt, const float* __restrict__ cov, const float* __restrict__ cn,
+         int64_t N, int V, int C, float* __restrict__ vA) {
+  __shared__ double scratch[32];
+  const int64_t n = blockIdx.x;
+  const double lh = -0.69314718055994530942;  // log(0.5)
+  for (int c0 = 0; c0 < C; c0 += 16) {
+    double acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      double cv = (double)cov[n * V + v];
+      if (cv == 0.0) continue;
+      double k = (double)alt[n * V + v];
+      double lo = lh + bb_lp(k, cv, 0.1, 1.9), hi = lh + bb_lp(k, cv, 1.9, 0.1);
+      double mx = lo > hi ? lo : hi;
+      double p1 = mx + log(exp(lo - mx) + exp(hi - mx));
+      double p2 = bb_lp(k, cv, 2.0, 2.0);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (c0 + j < C) acc[j] += (cn[(int64_t)v * C + c0 + j] == 2.0f) ? p2 : p1;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (c0 + j < C) {
+        double t = block_sum(acc[j], scratch);
+        if (threadIdx.x == 0) vA[n * C + c0 + j] = (float)t;
+      }
+    }
+  }
+}
+
+// softmax_c(v_n.) = clone_probs_from_snv, R/inference-tflow.R:438-439
+__global__ void k_softmax_rows(const float* __restrict__ in, int64_t N, int C, float* __restrict__ out) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double mx = -1e300;
+  for (int c = 0; c < C; ++c) mx = fmax(mx, (double)in[n * C + c]);
+  double z = 0.0;
+  for (int c = 0; c < C; ++c) z += exp((double)in[n * C + c] - mx);
+  for (int c = 0; c < C; ++c) out[n * C + c] = (float)(exp((double)in[n * C + c] - mx) / z);
+}
+
+// =============================================================================================
+// per-iteration gene-level kernels
+// =============================================================================================
+
+// K1: draw eps, mu = softplus(loc + exp(lsd) eps) (qmu$sample, R/inference-tflow.R:260-269), build the
+// contraction operand Mx[g][j] = mu_sg L_gc (j = s*C+c) and its W/beta-weighted copies
+// (j = SCp*(1+kp) + s*C+c) and the gene-level ELBO terms (prior on log mu :323, -E_q log q(mu) :332,
+// colsum_g * log mu_sg, prior on W :312).  One thread per gene.
+struct SampleMuArgs {
+  int G, C, S, K, KP, SCp, J;
+  int64_t Gld;
+  const float *loc, *lsd, *Vm, *L, *colsum, *chi_raw;
+  const float* eps_in;   // S x G host-fed draw or nullptr
+  uint64_t seed, draw;
+  float *eps_out, *mu, *logmu, *sig;
+  float* Mx;                       // [G][J] fp32 (CUDA-core path) or nullptr
+  __nv_bfloat16 *MxT_hi, *MxT_lo;  // [J][Gld] / [SCp][Gld] bf16 split (tensor path) or nullptr
+  double* gene_part;               // one partial per block
+};
+
+__global__ void __launch_bounds__(256) k_sample_mu(SampleMuArgs a) {
+  __shared__ double scratch[32];
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0;
+  if (g < a.G) {
+    float loc = a.loc[g], lsd = a.lsd[g], sd = expf(lsd);
+    double cs = (double)a.colsum[g];
+    float vk[kMaxKP];
+#pragma unroll
+    for (int kp = 0; kp < kMaxKP; ++kp) vk[kp] = kp < a.KP ? a.Vm[(int64_t)g * a.KP + kp] : 0.f;
+    for (int s = 0; s < a.S; ++s) {
+      float eps = a.eps_in ? a.eps_in[(int64_t)s * a.G + g] : normal_draw(a.seed, a.draw, (uint32_t)s, (uint32_t)g);
+      float x = loc + sd * eps;
+      float mu = softplusf(x);
+      float lm = logf(mu);
+      float sg = sigmoidf_(x);
+      int64_t o = (int64_t)s * a.G + g;
+      a.eps_out[o] = eps;
+      a.mu[o] = mu;
+      a.logmu[o] = lm;
+      a.sig[o] = sg;
+      double lsg = -(double)softplusf(-x);   // log sigmoid(x)
+      e += cs * (double)lm - 0.5 * (double)lm * (double)lm - (-0.5 * (double)eps * (double)eps - (double)lsd - lsg);
+      for (int c = 0; c < a.C; ++c) {
+        float m = mu * a.L[(int64_t)g * a.C + c];
+        int j = s * a.C + c;
+        if (a.Mx) {
+          a.Mx[(int64_t)g * a.J + j] = m;
+          for (int kp = 0; kp < a.KP; ++kp) a.Mx[(int64_t)g * a.J + a.SCp * (1 + kp) + j] = vk[kp] * m;
+        }
+        if (a.MxT_hi) {
+          __nv_bfloat16 hi = __float2bfloat16_rn(m);
+          a.MxT_hi[(int64_t)j * a.Gld + g] = hi;
+          a.MxT_lo[(int64_t)j * a.Gld + g] = __float2bfloat16_rn(m - __bfloat162float(hi));
+          a.MxT_hi[(int64_t)(a.SCp + j) * a.Gld + g] = __float2bfloat16_rn(vk[0] * m);
+        }
+      }
+    }
+    e /= (double)a.S;
+    for (int k = 0; k < a.K; ++k) {   // Normal(0, chi^-1/2) prior on W, R/inference-tflow.R:312-313
+      double cr = (double)a.chi_raw[k], w = (double)vk[k];
+      e += -0.5 * exp(cr) * w * w + 0.5 * cr - 0.5 * kLog2Pi;
+    }
+  }
+  double t = block_sum(e, scratch);
+  if (threadIdx.x == 0) a.gene_part[blockIdx.x] = t;
+}
+
+// min / max of the single latent loading column (K == 1, P == 0): gives the exact row maximum of
+// eta_ng = psi_n w_g without touching the N x G index space.  One block.
+__global__ void k_minmax(const float* __restrict__ w, int G, float* __restrict__ out2) {
+  __shared__ float smin[32], smax[32];
+  float mn = 3.4e38f, mx = -3.4e38f;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float v = w[g];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { smin[wid] = mn; smax[wid] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nw = blockDim.x >> 5;
+    for (int i = 1; i < nw; ++i) { mn = fminf(mn, smin[i]); mx = fmaxf(mx, smax[i]); }
+    out2[0] = mn;
+    out2[1] = mx;
+  }
+}
+__global__ void k_shift_k1(const float* __restrict__ psi, const float* __restrict__ mm, int64_t N,
+                           float* __restrict__ shift) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float p = psi[n];
+  shift[n] = fmaxf(p * mm[0], p * mm[1]);
+}
+// general K+P: exact row max of eta, one warp per cell
+__global__ void k_shift_general(const float* __restrict__ U, const float* __restrict__ Vm, int64_t N, int G,
+                                int KP, float* __restrict__ shift) {
+  int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float u[kMaxKP];
+#pragma unroll
+  for (int kp = 0; kp < kMaxKP; ++kp) u[kp] = kp < KP ? U[n * KP + kp] : 0.f;
+  float mx = -3.4e38f;
+  for (int g = lane; g < G; g += 32) {
+    float e = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < kMaxKP; ++kp)
+      if (kp < KP) e = fmaf(u[kp], Vm[(int64_t)g * KP + kp], e);
+    mx = fmaxf(mx, e);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) shift[n] = mx;
+}
+
+// log_softmax(alpha_unconstr) (R/inference-tflow.R:255), chi = exp(chi_raw) (:241), and the scalar ELBO
+// terms: Dirichlet(1/C) prior on alpha + 1e-3 (:324) and Gamma(2,1) prior on chi (:315).  One thread.
+__global__ void k_alpha(const float* __restrict__ u, int C, const float* __restrict__ chi_raw, int K,
+                        float* __restrict__ log_alpha, double* __restrict__ scal_elbo) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double mx = -1e300;
+  for (int c = 0; c < C; ++c) mx = fmax(mx, (double)u[c]);
+  double z = 0.0;
+  for (int c = 0; c < C; ++c) z += exp((double)u[c] - mx);
+  double lz = mx + log(z);
+  double e = 0.0;
+  for (int c = 0; c < C; ++c) {
+    double la = (double)u[c] - lz;
+    log_alpha[c] = (float)la;
+    e += (1.0 / C - 1.0) * log(exp(la) + 1e-3);
+  }
+  e -= (double)C * lgamma(1.0 / C) - lgamma(1.0);
+  for (int k = 0; k < K; ++k) e += (double)chi_raw[k] - exp((double)chi_raw[k]);
+  scal_elbo[0] = e;
+}
+
+// =============================================================================================
+// K5: per-cell epilogue.  One warp per cell.
+//   logZ_scn = log Z~_scn + m_n;  F_nc = B_nc - s_n mean_s logZ_scn + v_nc        (:294-306)
+//   gamma = softmax(t) (:273);  ELBO_n = sum_c gamma (F + log alpha - log gamma) + U_n.(YV)_n + psi prior
+//   d t = gamma (H - sum gamma H);  R_scn = gamma_nc s_n / (S Z~_scn);  d U_n = (YV)_n - sum_sc R Z'~ - psi
+//   INIT mode: t_nc <- sum_s l_scn - logsumexp_c (gamma_init, :338-340; SUM over s, not mean)
+// =============================================================================================
+enum { EPI_TRAIN = 0, EPI_EVAL = 1, EPI_INIT = 2 };
+
+struct EpiArgs {
+  int64_t N, Nld;
+  int C, S, SCp, J, K, KP, nCB, fsplit;
+  float* Zx;
+  const float *Bm, *vA, *s, *shift, *log_alpha, *U, *rowpart;
+  float* t;            // gamma_logits (written in INIT mode)
+  float *gT, *Rx, *gU, *YV, *Fout;
+  __nv_bfloat16* RxT;  // [J][Nld] transposed bf16 copy for the tensor path, or nullptr
+  double *elbo_part, *gsum_part;
+};
+
+constexpr int kEpiWarps = 16;
+
+template <int MODE>
+__global__ void __launch_bounds__(kEpiWarps * 32) k_cell_epilogue(EpiArgs a) {
+  extern __shared__ double sm[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int SC = a.S * a.C;
+  // per-warp scratch: lz[SCp] | F[C] | gam[C] ; block scratch after that
+  double* lz = sm + (size_t)wid * (a.SCp + 2 * a.C);
+  double* Fc = lz + a.SCp;
+  double* gam = Fc + a.C;
+  double* blk = sm + (size_t)kEpiWarps * (a.SCp + 2 * a.C);   // [kEpiWarps] elbo, then [kEpiWarps][C] gamma
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(blk + kEpiWarps + (size_t)kEpiWarps * a.C);  // [J][kEpiWarps]
+
+  const int64_t n = (int64_t)blockIdx.x * kEpiWarps + wid;
+  const bool live = n < a.N;
+  double elbo_n = 0.0;
+
+  if (live) {
+    float* zrow = a.Zx + n * a.J;
+    if (a.fsplit > 1) {   // tensor path: sum the K-split partials in a fixed order, keep the sum in split 0
+      const int jn = (MODE == EPI_TRAIN) ? a.J : a.SCp;
+      for (int j = lane; j < jn; j += 32) {
+        float z = zrow[j];
+        for (int f = 1; f < a.fsplit; ++f) z += a.Zx[((int64_t)f * a.N + n) * a.J + j];
+        zrow[j] = z;
+      }
+      __syncwarp();
+    }
+    const double m = (double)a.shift[n];
+    const double sn = (double)a.s[n];
+    for (int j = lane; j < SC; j += 32) lz[j] = log((double)zrow[j]) + m;
+    __syncwarp();
+    for (int c = lane; c < a.C; c += 32) {
+      double acc = 0.0;
+      for (int s = 0; s < a.S; ++s) acc += lz[s * a.C + c];
+      double b = (double)a.Bm[n * a.C + c], v = (double)a.vA[n * a.C + c];
+      if (MODE == EPI_INIT) Fc[c] = (double)a.S * (b + v) - sn * acc;
+      else Fc[c] = b + v - sn * acc / (double)a.S;
+    }
+    __syncwarp();
+    if (MODE == EPI_INIT) {
+      double mx = -1e300;
+      for (int c = lane; c < a.C; c += 32) mx = fmax(mx, Fc[c]);
+      mx = warp_max(mx);
+      double z = 0.0;
+      for (int c = lane; c < a.C; c += 32) z += exp(Fc[c] - mx);
+      z = warp_sum(z);
+      double lse = mx + log(z);
+      for (int c = lane; c < a.C; c += 32) a.t[n * a.C + c] = (float)(Fc[c] - lse);
+    } else {
+      // gamma = softmax(t)
+      double mx = -1e300;
+      for (int c = lane; c < a.C; c += 32) mx = fmax(mx, (double)a.t[n * a.C + c]);
+      mx = warp_max(mx);
+      double z = 0.0;
+      for (int c = lane; c < a.C; c += 32) z += exp((double)a.t[n * a.C + c] - mx);
+      z = warp_sum(z);
+      double lse = mx + log(z);
+      double sumGH = 0.0, e = 0.0;
+      for (int c = lane; c < a.C; c += 32) {
+        double lg = (double)a.t[n * a.C + c] - lse;
+        double g = exp(lg);
+        gam[c] = g;
+        double H = Fc[c] + (double)a.log_alpha[c] - lg;
+        double gh = (g == 0.0) ? 0.0 : g * H;   // tf$where(gamma == 0, 0, gamma*log gamma), :333
+        sumGH += gh;
+        e += gh;
+        if (a.Fout) a.Fout[n * a.C + c] = (float)Fc[c];
+      }
+      sumGH = warp_sum(sumGH);
+      e = sumGH;
+      // Y-linear term sum_g y eta = U_n . (YV)_n and the N(0,1) prior on psi (:318-319)
+      double yv[kMaxKP];
+      for (int kp = 0; kp < a.KP; ++kp) {
+        double acc = 0.0;
+        for (int cb = 0; cb < a.nCB; ++cb) acc += (double)a.rowpart[((int64_t)cb * a.N + n) * a.KP + kp];
+        yv[kp] = acc;
+        double u = (double)a.U[n * a.KP + kp];
+        e += u * acc;
+        if (kp < a.K) e += -0.5 * u * u - 0.5 * kLog2Pi;
+        if (lane == 0 && a.YV) a.YV[n * a.KP + kp] = (float)acc;
+      }
+      elbo_n = e;
+      __syncwarp();
+      if (MODE == EPI_TRAIN) {
+        for (int c = lane; c < a.C; c += 32) {
+          double lg = (double)a.t[n * a.C + c] - lse;
+          double g = gam[c];
+          double H = Fc[c] + (double)a.log_alpha[c] - lg;
+          a.gT[n * a.C + c] = (g == 0.0) ? 0.f : (float)(g * (H - sumGH));
+        }
+        // R and the psi / covariate-side gradient
+        double gu[kMaxKP];
+#pragma unroll
+        for (int kp = 0; kp < kMaxKP; ++kp) gu[kp] = 0.0;
+        for (int j = lane; j < a.SCp; j += 32) {
+          float r = 0.f;
+          if (j < SC) {
+            int c = j % a.C;
+            r = (float)(gam[c] * sn / ((double)a.S * (double)zrow[j]));
+          }
+          if (a.Rx) a.Rx[n * a.J + j] = r;
+          if (a.RxT) tile[(size_t)j * kEpiWarps + wid] = __float2bfloat16_rn(r);
+          for (int kp = 0; kp < a.KP; ++kp) {
+            float u = a.U[n * a.KP + kp];
+            float ru = u * r;
+            int jj = a.SCp * (1 + kp) + j;
+            if (a.Rx) a.Rx[n * a.J + jj] = ru;
+            if (a.RxT) tile[(size_t)jj * kEpiWarps + wid] = __float2bfloat16_rn(ru);
+            if (j < SC) gu[kp] += (double)r * (double)zrow[jj];
+          }
+        }
+        for (int kp = 0; kp < a.KP; ++kp) {
+          double tot = warp_sum(gu[kp]);
+          if (lane == 0) {
+            double g = yv[kp] - tot;
+            if (kp < a.K) g -= (double)a.U[n * a.KP + kp];
+            a.gU[n * a.KP + kp] = (float)g;
+          }
+        }
+      }
+    }
+  } else if (MODE == EPI_TRAIN && a.RxT) {
+    for (int j = lane; j < a.J; j += 32) tile[(size_t)j * kEpiWarps + wid] = __float2bfloat16_rn(0.f);
+  }
+
+  if (MODE == EPI_INIT) return;
+  // block-level fixed-order partials
+  if (lane == 0) blk[wid] = live ? elbo_n : 0.0;
+  if (MODE == EPI_TRAIN) {
+    double* bg = blk + kEpiWarps + (size_t)wid * a.C;
+    for (int c = lane; c < a.C; c += 32) bg[c] = live ? gam[c] : 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double e = 0.0;
+    for (int w = 0; w < kEpiWarps; ++w) e += blk[w];
+    a.elbo_part[blockIdx.x] = e;
+  }
+  if (MODE == EPI_TRAIN) {
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      double g = 0.0;
+      for (int w = 0; w < kEpiWarps; ++w) g += blk[kEpiWarps + (size_t)w * a.C + c];
+      a.gsum_part[(int64_t)blockIdx.x * a.C + c] = g;
+    }
+    if (a.RxT) {
+      // transposed store: row j of RxT gets this block's kEpiWarps consecutive cells (32 bytes)
+      const int64_t n0 = (int64_t)blockIdx.x * kEpiWarps;
+      constexpr int kVec = 8;                               // bf16 per 16-byte store
+      constexpr int kPer = kEpiWarps / kVec;                // stores per row
+      for (int i = threadIdx.x; i < a.J * kPer; i += blockDim.x) {
+        int j = i / kPer, h = i % kPer;
+        if (n0 + h * kVec < a.Nld) {
+          uint4 val = *reinterpret_cast<const uint4*>(tile + (size_t)j * kEpiWarps + h * kVec);
+          *reinterpret_cast<uint4*>(a.RxT + (int64_t)j * a.Nld + n0 + h * kVec) = val;
+        }
+      }
+    }
+  }
+}
+
+inline size_t epi_smem_bytes(int SCp, int C, int J, bool tc) {
+  size_t b = (size_t)kEpiWarps * (SCp + 2 * C) * 8 + (size_t)kEpiWarps * 8 + (size_t)kEpiWarps * C * 8;
+  if (tc) b += (size_t)J * kEpiWarps * 2;
+  return b + 16;
+}
+
+// sum of per-block partials in block order (one block)
+__global__ void k_reduce_partials(const double* __restrict__ part, int64_t nblk, int ncol,
+                                  double* __restrict__ out, double add0) {
+  __shared__ double scratch[32];
+  for (int c = 0; c < ncol; ++c) {
+    double a = 0.0;
+    for (int64_t i = threadIdx.x; i < nblk; i += blockDim.x) a += part[i * ncol + c];
+    double t = block_sum(a, scratch);
+    if (threadIdx.x == 0) out[c] = t + (c == 0 ? add0 : 0.0);
+  }
+}
+// sum_n gamma_nc partials -> float slots of the allreduce buffer
+__global__ void k_reduce_gsum(const double* __restrict__ part, int64_t nblk, int C, float* __restrict__ out) {
+  __shared__ double scratch[32];
+  for (int c = 0; c < C; ++c) {
+    double a = 0.0;
+    for (int64_t i = threadIdx.x; i < nblk; i += blockDim.x) a += part[i * C + c];
+    double t = block_sum(a, scratch);
+    if (threadIdx.x == 0) out[c] = (float)t;
+  }
+}
+
+// ELBO = (all-rank sum of cell partials) + gene-level terms + scalar priors.  One block.
+__global__ void k_elbo_final(const double* __restrict__ cell_sum, const double* __restrict__ gene_part, int n_gene_part,
+                             const double* __restrict__ scal_elbo, int poison, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n_gene_part; i += blockDim.x) a += gene_part[i];
+  double t = block_sum(a, scratch);
+  if (threadIdx.x == 0) {
+    double e = cell_sum[0] + t + scal_elbo[0];
+    out[0] = poison ? __longlong_as_double(0x7ff8000000000000LL) : e;
+  }
+}
+
+// =============================================================================================
+// gene-level gradients (K6/K7) and optimiser
+// =============================================================================================
+struct GeneGradArgs {
+  int G, C, S, K, KP, SCp, J, nsplit, nRB;
+  const float* dMx;       // [nsplit][G][J] partial contraction outputs (nsplit = 1 on the CUDA-core path)
+  const float* colpart;   // [nRB][G][KP] partial Y^T U
+  const float *mu, *sig, *eps, *lsd, *L;
+  float* ar;              // allreduce buffer: [G] d loc | [G] d lsd | [G][KP] d V | [C] sum gamma
+  float* YtU;             // [G][KP] (kept for inspection)
+  float* dM_out;          // [G][J] summed over splits (inspection), may be nullptr
+};
+
+// rank-local (linear in the cell sums) parts of the gene gradients -> allreduce buffer
+__global__ void __launch_bounds__(128) k_gene_grads(GeneGradArgs a) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.G) return;
+  const int SC = a.S * a.C;
+  float sd = expf(a.lsd[g]);
+  double aloc = 0.0, alsd = 0.0;
+  double gv[kMaxKP];
+#pragma unroll
+  for (int kp = 0; kp < kMaxKP; ++kp) gv[kp] = 0.0;
+  for (int kp = 0; kp < a.KP; ++kp) {
+    double acc = 0.0;
+    for (int rb = 0; rb < a.nRB; ++rb) acc += (double)a.colpart[((int64_t)rb * a.G + g) * a.KP + kp];
+    gv[kp] = acc;
+    a.YtU[(int64_t)g * a.KP + kp] = (float)acc;
+  }
+  for (int s = 0; s < a.S; ++s) {
+    int64_t o = (int64_t)s * a.G + g;
+    float mu = a.mu[o];
+    double dmu = 0.0;
+    for (int c = 0; c < a.C; ++c) {
+      int j = s * a.C + c;
+      float l = a.L[(int64_t)g * a.C + c];
+      double d = 0.0;
+      for (int sp = 0; sp < a.nsplit; ++sp) d += (double)a.dMx[((int64_t)sp * a.G + g) * a.J + j];
+      if (a.dM_out) a.dM_out[(int64_t)g * a.J + j] = (float)d;
+      dmu -= (double)l * d;
+      for (int kp = 0; kp < a.KP; ++kp) {
+        int jj = a.SCp * (1 + kp) + j;
+        double d2 = 0.0;
+        for (int sp = 0; sp < a.nsplit; ++sp) d2 += (double)a.dMx[((int64_t)sp * a.G + g) * a.J + jj];
+        if (a.dM_out) a.dM_out[(int64_t)g * a.J + jj] = (float)d2;
+        gv[kp] -= (double)(mu * l) * d2;
+      }
+    }
+    double dx = (double)a.sig[o] * dmu;
+    aloc += dx;
+    alsd += dx * (double)sd * (double)a.eps[o];
+  }
+  (void)SC;
+  a.ar[g] = (float)aloc;
+  a.ar[a.G + g] = (float)alsd;
+  for (int kp = 0; kp < a.KP; ++kp) a.ar[2 * (int64_t)a.G + (int64_t)g * a.KP + kp] = (float)gv[kp];
+}
+
+struct AdamHyper {
+  float lr_t, b1, b2, eps;
+  int apply;   // 0: gradients only
+};
+__device__ __forceinline__ void adam_update(float& th, float& m, float& v, float g_elbo, const AdamHyper& h) {
+  // TF1 AdamOptimizer on loss = -ELBO: epsilon outside the bias correction
+  float g = -g_elbo;
+  m = m + (1.f - h.b1) * (g - m);
+  v = v + (1.f - h.b2) * (g * g - v);
+  th = th - h.lr_t * m / (sqrtf(v) + h.eps);
+}
+
+struct GeneAdamArgs {
+  int G, S, K, KP;
+  const float* ar;   // after allreduce
+  const float *mu, *logmu, *sig, *eps, *colsum, *chi_raw;
+  float *loc, *lsd, *Vm;
+  float *m_loc, *v_loc, *m_lsd, *v_lsd, *m_V, *v_V;
+  float *g_loc, *g_lsd, *g_V;
+  AdamHyper h;
+};
+// finish d loc, d lsd, d W / d beta with the replicated (rank-independent) terms, then Adam
+__global__ void __launch_bounds__(128) k_gene_adam(GeneAdamArgs a) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.G) return;
+  float lsd = a.lsd[g];
+  double sd = exp((double)lsd), cs = (double)a.colsum[g];
+  double gl = (double)a.ar[g], gs = (double)a.ar[a.G + g];
+  for (int s = 0; s < a.S; ++s) {
+    int64_t o = (int64_t)s * a.G + g;
+    double mu = (double)a.mu[o], sg = (double)a.sig[o];
+    double dmu = (cs - (double)a.logmu[o]) / ((double)a.S * mu);
+    double dx = sg * dmu + (1.0 - sg) / (double)a.S;
+    gl += dx;
+    gs += dx * sd * (double)a.eps[o];
+  }
+  gs += 1.0;
+  float gloc = (float)gl, glsd = (float)gs;
+  a.g_loc[g] = gloc;
+  a.g_lsd[g] = glsd;
+  for (int kp = 0; kp < a.KP; ++kp) {
+    int64_t o = (int64_t)g * a.KP + kp;
+    double gv = (double)a.ar[2 * (int64_t)a.G + o];
+    if (kp < a.K) gv -= exp((double)a.chi_raw[kp]) * (double)a.Vm[o];
+    a.g_V[o] = (float)gv;
+  }
+  if (a.h.apply) {
+    adam_update(a.loc[g], a.m_loc[g], a.v_loc[g], gloc, a.h);
+    adam_update(a.lsd[g], a.m_lsd[g], a.v_lsd[g], glsd, a.h);
+    for (int kp = 0; kp < a.KP; ++kp) {
+      int64_t o = (int64_t)g * a.KP + kp;
+      adam_update(a.Vm[o], a.m_V[o], a.v_V[o], a.g_V[o], a.h);
+    }
+  }
+}
+
+// sum_g W_gk^2 with the OLD W (must run before k_gene_adam); one block
+__global__ void k_wsq(const float* __restrict__ Vm, int G, int K, int KP, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  for (int k = 0; k < K; ++k) {
+    double a = 0.0;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      double w = (double)Vm[(int64_t)g * KP + k];
+      a += w * w;
+    }
+    double t = block_sum(a, scratch);
+    if (threadIdx.x == 0) out[k] = t;
+  }
+}
+
+// d chi_raw and d alpha_unconstr (closed forms) + Adam; one thread
+struct ScalarAdamArgs {
+  int G, C, K;
+  double n_total;
+  const double* wsq;
+  const float* gsum;   // allreduced sum_n gamma_nc
+  float *chi_raw, *m_chi, *v_chi, *g_chi;
+  float *u, *m_u, *v_u, *g_u;
+  AdamHyper h;
+};
+__global__ void k_scalar_adam(ScalarAdamArgs a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int k = 0; k < a.K; ++k) {
+    double chi = exp((double)a.chi_raw[k]);
+    a.g_chi[k] = (float)(-0.5 * chi * a.wsq[k] + 0.5 * (double)a.G + 1.0 - chi);
+  }
+  double mx = -1e300;
+  for (int c = 0; c < a.C; ++c) mx = fmax(mx, (double)a.u[c]);
+  double z = 0.0;
+  for (int c = 0; c < a.C; ++c) z += exp((double)a.u[c] - mx);
+  double rsum = 0.0;
+  for (int c = 0; c < a.C; ++c) {
+    double al = exp((double)a.u[c] - mx) / z;
+    rsum += al / (al + 1e-3);
+  }
+  for (int c = 0; c < a.C; ++c) {
+    double al = exp((double)a.u[c] - mx) / z;
+    double r = al / (al + 1e-3);
+    a.g_u[c] = (float)((double)a.gsum[c] - a.n_total * al + (1.0 / a.C - 1.0) * (r - al * rsum));
+  }
+  if (a.h.apply) {
+    for (int k = 0; k < a.K; ++k) adam_update(a.chi_raw[k], a.m_chi[k], a.v_chi[k], a.g_chi[k], a.h);
+    for (int c = 0; c < a.C; ++c) adam_update(a.u[c], a.m_u[c], a.v_u[c], a.g_u[c], a.h);
+  }
+}
+
+// Adam on the per-cell variables: gamma_logits [N][C] and the psi columns of U [N][KP]
+__global__ void k_cell_adam(int64_t N, int C, int K, int KP, float* __restrict__ t, float* __restrict__ m_t,
+                            float* __restrict__ v_t, const float* __restrict__ gT, float* __restrict__ U,
+                            float* __restrict__ m_U, float* __restrict__ v_U, const float* __restrict__ gU,
+                            AdamHyper h) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t nt = N * C;
+  if (i < nt) {
+    adam_update(t[i], m_t[i], v_t[i], gT[i], h);
+  } else {
+    int64_t j = i - nt;
+    if (j < N * KP && (j % KP) < K) adam_update(U[j], m_U[j], v_U[j], gU[j], h);
+  }
+}
+
+}  // namespace ca

@@ -1,0 +1,427 @@
+// tcgen05 (5th-gen tensor core) contraction kernels for the reference's default model (K = 1, P = 0).
+//
+//   FWD  Zx[n][j]  = sum_g E_ng * Mx[g][j]     M-dim = 128 cells, N-dim = J = 2*SCp, K-dim = genes
+//   BWD  dMx[g][j] = sum_n E_ng * Rx[n][j]     M-dim = 128 genes, N-dim = J,          K-dim = cells
+//   E_ng = exp(psi_n w_g - m_n)   (random_fixed_effects, R/inference-tflow.R:243,280; never materialised)
+//
+// The A operand (E) is GENERATED on chip: 8 generator warps evaluate exp2 on the fly and store the
+// bf16 tile straight into shared memory in the canonical K-major SWIZZLE_128B UMMA layout; the B
+// operand (Mx^T / Rx^T, bf16, K-major) arrives by TMA; one elected thread issues tcgen05.mma with the
+// fp32 accumulator in TMEM; the same 8 warps drain TMEM with tcgen05.ld in the epilogue.
+//
+// Precision: log Z is multiplied by the library size s_n ~ 1e3..1e4 before the clone
+// softmax, so the Z columns of FWD use a 3-term bf16 split (E_hi*M_hi + E_hi*M_lo + E_lo*M_hi, error
+// ~2^-17 relative, fp32-equivalent); the gradient-only columns (Z' = sum E w M) and BWD use plain bf16.
+//
+// Column layout of Mx / Zx / Rx / dMx (J = 2*SCp, SCp = S*C rounded up to 16):
+//   [0, SCp)      : (s,c) -> mu_sg L_gc            | Z      | R            | dM
+//   [SCp, 2*SCp)  : (s,c) -> w_g mu_sg L_gc        | Z'     | psi_n R      | dM'
+#pragma once
+#include <cuda.h>
+
+#include <algorithm>
+#include <stdexcept>
+
+#include "common.cuh"
+
+namespace ca {
+
+constexpr int kTcGenWarps = 8;                       // generator / epilogue warps
+constexpr int kTcThreads = (kTcGenWarps + 2) * 32;   // + TMA warp + MMA warp
+constexpr int kTcBM = 128;                           // UMMA M
+constexpr int kTcBK = 64;                            // K elements per stage (one 128-byte swizzle row of bf16)
+constexpr int kTcTmemCols = 256;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct TcPlan {
+  bool ok = false;
+  int dev = 0, num_sms = 0;
+  int64_t N = 0, Nld = 0, Gld = 0;
+  int G = 0, SCp = 0, J = 0;
+  int fsplit = 1, nsplit = 1;          // K-dim splits of FWD (genes) and BWD (cells)
+  int64_t genes_per_fsplit = 0, cells_per_split = 0;
+  int fwd_stages = 0, bwd_stages = 0;
+  size_t fwd_smem = 0, bwd_smem = 0;
+  alignas(64) CUtensorMap tm_mhi, tm_mlo, tm_rx;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, single CTA
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tm, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
+      "l"(tm), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+}  // namespace ptx
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1, layout type 2).
+// Rows are 128 bytes (64 bf16); 8-row groups are 1024 bytes apart (SBO); LBO is unused for swizzled K-major.
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+}
+
+// pack two floats to bf16x2 (lo half = a) with round-to-nearest-even
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel.  FWD: rows = cells (row scalar psi_n, shift m_n per row), K index = genes (w_g).
+//              BWD: rows = genes (row scalar w_g), K index = cells (psi_n and shift m_n per K index).
+// ------------------------------------------------------------------------------------------------
+struct TcArgs {
+  const float* rowv;     // FWD: psi [N]   BWD: w [G]
+  const float* kv;       // FWD: w [G]     BWD: psi [N]
+  const float* shift;    // m [N]
+  float* out;            // FWD: Zx [fsplit][N][J]   BWD: dMx [nsplit][G][J]
+  int64_t rows;          // valid rows (N or G)
+  int64_t kdim;          // valid K extent (G or N)
+  int64_t k_per_split;   // K elements handled per blockIdx.y (multiple of 64)
+  int J, SCp;
+  int stages;
+};
+
+template <bool FWD>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_expgemm_tc(const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ CUtensorMap tm_b1, TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages] x { A_hi 16K | (FWD) A_lo 16K | B0 J*128 | (FWD) B1 SCp*128 } then barriers
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = kTcBM * 128;
+  const uint32_t b0_bytes = (uint32_t)a.J * 128, b1_bytes = FWD ? (uint32_t)a.SCp * 128 : 0;
+  const uint32_t stage_bytes = a_bytes * (FWD ? 2 : 1) + b0_bytes + b1_bytes;
+  const int stages = a.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)stages * stage_bytes);
+  // bars: full_a[stages] | full_b[stages] | empty[stages] | acc_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base_u32 = ptx::smem_u32(base);
+  const uint32_t bar_u32 = ptx::smem_u32(bars);
+  auto full_a = [&](int s) { return bar_u32 + 8u * s; };
+  auto full_b = [&](int s) { return bar_u32 + 8u * (stages + s); };
+  auto empty = [&](int s) { return bar_u32 + 8u * (2 * stages + s); };
+  const uint32_t acc_full = bar_u32 + 8u * (3 * stages);
+
+  const int64_t row0 = (int64_t)blockIdx.x * kTcBM;
+  const int64_t kbeg = (int64_t)blockIdx.y * a.k_per_split;
+  int64_t kend = kbeg + a.k_per_split;
+  if (kend > a.kdim) kend = a.kdim;
+  const int nkb = kend > kbeg ? (int)((kend - kbeg + kTcBK - 1) / kTcBK) : 0;
+
+  if (warp == kTcGenWarps + 1) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) {
+        ptx::mbar_init(full_a(s), kTcGenWarps * 32);
+        ptx::mbar_init(full_b(s), 1);
+        ptx::mbar_init(empty(s), 1);
+      }
+      ptx::mbar_init(acc_full, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), kTcTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kTcGenWarps) {
+    // ===================== A-operand generators =====================
+    const int r = tid & (kTcBM - 1);        // row of the tile owned by this thread
+    const int cpar = tid >> 7;              // 0/1: which 16-byte chunks (cpar, cpar+2, cpar+4, cpar+6)
+    const int64_t grow = row0 + r;
+    float rv = 0.f, rsh = 0.f;
+    if (grow < a.rows) {
+      rv = a.rowv[grow] * kLog2e;
+      if (FWD) rsh = a.shift[grow] * kLog2e;
+    }
+    const uint32_t row_off = (uint32_t)r * 128u;
+    const uint32_t sw = (uint32_t)(r & 7);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int st = kb % stages;
+      const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+      ptx::mbar_wait(empty(st), ph ^ 1u);
+      const uint32_t sA = base_u32 + (uint32_t)st * stage_bytes;
+      const int64_t k0 = kbeg + (int64_t)kb * kTcBK;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = cpar + 2 * i;
+        const int64_t kk = k0 + c * 8;
+        float kvv[8], ksh[8];
+        if (kk + 8 <= kend) {
+          float4 v0 = __ldg(reinterpret_cast<const float4*>(a.kv + kk));
+          float4 v1 = __ldg(reinterpret_cast<const float4*>(a.kv + kk) + 1);
+          kvv[0] = v0.x; kvv[1] = v0.y; kvv[2] = v0.z; kvv[3] = v0.w; kvv[4] = v1.x; kvv[5] = v1.y; kvv[6] = v1.z; kvv[7] = v1.w;
+          if (!FWD) {
+            float4 s0 = __ldg(reinterpret_cast<const float4*>(a.shift + kk));
+            float4 s1 = __ldg(reinterpret_cast<const float4*>(a.shift + kk) + 1);
+            ksh[0] = s0.x; ksh[1] = s0.y; ksh[2] = s0.z; ksh[3] = s0.w; ksh[4] = s1.x; ksh[5] = s1.y; ksh[6] = s1.z; ksh[7] = s1.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            bool ok = kk + j < kend;
+            kvv[j] = ok ? a.kv[kk + j] : 0.f;
+            ksh[j] = (!FWD && ok) ? a.shift[kk + j] : 0.f;
+          }
+        }
+        float e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float arg = FWD ? fmaf(rv, kvv[j], -rsh) : fmaf(rv, kvv[j], -ksh[j] * kLog2e);
+          e[j] = ptx::ex2(arg);
+        }
+        uint32_t hi[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hi[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+        const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3])
+                     : "memory");
+        if (FWD) {
+          uint32_t lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float h0 = __uint_as_float(hi[j] << 16), h1 = __uint_as_float(hi[j] & 0xffff0000u);
+            lo[j] = pack_bf16x2(e[2 * j] - h0, e[2 * j + 1] - h1);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + a_bytes + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]),
+                       "r"(lo[3])
+                       : "memory");
+        }
+      }
+      ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+      ptx::mbar_arrive(full_a(st));
+    }
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    if (nkb > 0) {
+      ptx::mbar_wait(acc_full, 0);
+      ptx::tc_fence_after();
+    }
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = warp >> 2;        // column half
+    const int64_t orow = row0 + q * 32 + lane;
+    float* obase = a.out + ((int64_t)blockIdx.y * a.rows + orow) * a.J;
+    const int ncol_half = a.J / 2;     // = SCp, multiple of 16
+    for (int c0 = 0; c0 < ncol_half; c0 += 16) {
+      const int col = half * ncol_half + c0;
+      uint32_t v[16];
+      if (nkb > 0) {
+        ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+      if (orow < a.rows) {
+        float4* o4 = reinterpret_cast<float4*>(obase + col);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          o4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                              __uint_as_float(v[4 * j + 3]));
+      }
+    }
+  } else if (warp == kTcGenWarps) {
+    // ===================== TMA producer for the B operand =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % stages;
+        const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+        ptx::mbar_wait(empty(st), ph ^ 1u);
+        const uint32_t sB0 = base_u32 + (uint32_t)st * stage_bytes + a_bytes * (FWD ? 2 : 1);
+        const int kx = (int)(kbeg + (int64_t)kb * kTcBK);
+        ptx::mbar_expect_tx(full_b(st), b0_bytes + b1_bytes);
+        ptx::tma_load_2d(sB0, &tm_b0, kx, 0, full_b(st));
+        if (FWD) ptx::tma_load_2d(sB0 + b0_bytes, &tm_b1, kx, 0, full_b(st));
+      }
+    }
+  } else {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idJ = umma_idesc_bf16(a.J), idS = umma_idesc_bf16(a.SCp);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % stages;
+        const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+        ptx::mbar_wait(full_a(st), ph);
+        ptx::mbar_wait(full_b(st), ph);
+        ptx::tc_fence_after();
+        const uint32_t sA = base_u32 + (uint32_t)st * stage_bytes;
+        const uint32_t sB0 = sA + a_bytes * (FWD ? 2 : 1);
+        const uint64_t dA = umma_desc_k128(sA), dAlo = umma_desc_k128(sA + a_bytes);
+        const uint64_t dB0 = umma_desc_k128(sB0), dB1 = umma_desc_k128(sB0 + b0_bytes);
+#pragma unroll
+        for (int k = 0; k < kTcBK / 16; ++k) {
+          const uint64_t adv = (uint64_t)(k * 32 >> 4);   // +32 bytes along K inside the swizzle atom
+          ptx::umma_bf16(tmem_base, dA + adv, dB0 + adv, idJ, (kb | k) != 0 ? 1u : 0u);
+          if (FWD) {
+            ptx::umma_bf16(tmem_base, dA + adv, dB1 + adv, idS, 1u);     // E_hi * M_lo  -> Z columns
+            ptx::umma_bf16(tmem_base, dAlo + adv, dB0 + adv, idS, 1u);   // E_lo * M_hi  -> Z columns
+          }
+        }
+        ptx::umma_commit(empty(st));   // frees the stage once these MMAs have read it
+      }
+      if (nkb > 0) ptx::umma_commit(acc_full);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kTcGenWarps + 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTcTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline void tc_make_map(CUtensorMap* tm, void* gptr, uint64_t inner, uint64_t outer, uint32_t box_outer) {
+  static tc_encode_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+      throw std::runtime_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    fn = (tc_encode_fn)p;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * 2};   // bytes, row pitch
+  cuuint32_t box[2] = {kTcBK, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, gptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+}
+
+inline int tc_pick_split(int64_t tiles, int64_t kchunks, int num_sms, int max_split) {
+  // choose the K-split that minimises tail-wave waste; prefer fewer splits on ties
+  int best = 1;
+  double best_eff = 0.0;
+  for (int ns = 1; ns <= max_split; ++ns) {
+    if (kchunks / ns < 8 && ns > 1) break;
+    int64_t total = tiles * ns;
+    int64_t waves = (total + num_sms - 1) / num_sms;
+    double eff = (double)total / (double)(waves * num_sms);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = ns; }
+  }
+  return best;
+}
+
+inline void tc_plan_create(TcPlan& p, int dev, int64_t N, int64_t Nld, int G, int64_t Gld, int SCp, int J, __nv_bfloat16* MxT_hi,
+                           __nv_bfloat16* MxT_lo, __nv_bfloat16* RxT) {
+  p.dev = dev; p.N = N; p.Nld = Nld; p.G = G; p.Gld = Gld; p.SCp = SCp; p.J = J;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) throw std::runtime_error("cudaGetDeviceProperties failed");
+  p.num_sms = prop.multiProcessorCount;
+  tc_make_map(&p.tm_mhi, MxT_hi, (uint64_t)Gld, (uint64_t)J, (uint32_t)J);
+  tc_make_map(&p.tm_mlo, MxT_lo, (uint64_t)Gld, (uint64_t)SCp, (uint32_t)SCp);
+  tc_make_map(&p.tm_rx, RxT, (uint64_t)Nld, (uint64_t)J, (uint32_t)J);
+  const size_t budget = 220 * 1024;
+  size_t fstage = 2 * kTcBM * 128 + (size_t)(J + SCp) * 128, bstage = kTcBM * 128 + (size_t)J * 128;
+  p.fwd_stages = (int)std::min<size_t>(4, (budget - 2048) / fstage);
+  p.bwd_stages = (int)std::min<size_t>(6, (budget - 2048) / bstage);
+  if (p.fwd_stages < 2 || p.bwd_stages < 2) throw std::runtime_error("tensor path: tile does not fit in shared memory");
+  p.fwd_smem = p.fwd_stages * fstage + 1024 + 512;
+  p.bwd_smem = p.bwd_stages * bstage + 1024 + 512;
+  int64_t ftiles = (N + kTcBM - 1) / kTcBM, btiles = (G + kTcBM - 1) / kTcBM;
+  p.fsplit = tc_pick_split(ftiles, Gld / kTcBK, p.num_sms, 4);
+  p.nsplit = tc_pick_split(btiles, Nld / kTcBK, p.num_sms, 16);
+  p.genes_per_fsplit = ((Gld / kTcBK + p.fsplit - 1) / p.fsplit) * kTcBK;
+  p.cells_per_split = ((Nld / kTcBK + p.nsplit - 1) / p.nsplit) * kTcBK;
+  if (cudaFuncSetAttribute(k_expgemm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.fwd_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(k_expgemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.bwd_smem) != cudaSuccess)
+    throw std::runtime_error("tensor path: cannot raise the dynamic shared memory limit");
+  p.ok = true;
+}
+inline void tc_plan_destroy(TcPlan& p) { p.ok = false; }
+
+// FWD: psi = U [N] (K == 1), w = V [G]; out Zx [fsplit][N][J]
+inline void tc_launch_fwd(const TcPlan& p, const float* psi, const float* w, const float* shift, float* Zx, cudaStream_t st) {
+  TcArgs a;
+  a.rowv = psi; a.kv = w; a.shift = shift; a.out = Zx; a.rows = p.N; a.kdim = p.G; a.k_per_split = p.genes_per_fsplit;
+  a.J = p.J; a.SCp = p.SCp; a.stages = p.fwd_stages;
+  dim3 grid((unsigned)((p.N + kTcBM - 1) / kTcBM), p.fsplit);
+  k_expgemm_tc<true><<<grid, kTcThreads, p.fwd_smem, st>>>(p.tm_mhi, p.tm_mlo, a);
+}
+// BWD: out dMx [nsplit][G][J]
+inline void tc_launch_bwd(const TcPlan& p, const float* psi, const float* w, const float* shift, float* dMx, cudaStream_t st) {
+  TcArgs a;
+  a.rowv = w; a.kv = psi; a.shift = shift; a.out = dMx; a.rows = p.G; a.kdim = p.N; a.k_per_split = p.cells_per_split;
+  a.J = p.J; a.SCp = p.SCp; a.stages = p.bwd_stages;
+  dim3 grid((unsigned)((p.G + kTcBM - 1) / kTcBM), p.nsplit);
+  k_expgemm_tc<false><<<grid, kTcThreads, p.bwd_smem, st>>>(p.tm_rx, p.tm_rx, a);
+}
+
+}  // namespace ca

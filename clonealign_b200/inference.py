@@ -1,0 +1,181 @@
+"""Host-side mirror of the reference's `inference_tflow()` (R/inference-tflow.R:71-481).
+
+Same arguments, same order of operations, same return structure; the TensorFlow session is
+replaced by `clonealign_b200.session.Session` (CUDA).  The optimisation loop, convergence test and
+messages stay on the host exactly as in the reference (:378-417) so interrupt / progress semantics
+do not change.  All randomness derives from one host RNG (`seed`), as the reference derives it from
+R's RNG (tests/testthat/test_clonealign.R:42-66).
+"""
+from __future__ import annotations
+
+import sys
+
+import numpy as np
+
+from .session import Session
+
+
+def inverse_softplus(x):
+    """R/inference-tflow.R:2-4."""
+    return np.log(np.exp(x) - 1.0)
+
+
+def safe_inverse_softplus(x):
+    """R/inference-tflow.R:6-11."""
+    x = np.asarray(x, dtype=np.float64)
+    if np.any(x < 0):
+        raise ValueError("Inverse softplus only takes positive values")
+    return np.log(1.0 - np.exp(-np.abs(x))) + np.maximum(x, 0.0)
+
+
+def softplus(x):
+    """R/inference-tflow.R:13-15."""
+    return np.logaddexp(0.0, x)
+
+
+def saturate(x, threshold=4):
+    """R/clonealign.R:394-397."""
+    x = np.array(x, dtype=np.float64, copy=True)
+    x[x > threshold] = threshold
+    return x
+
+
+def clone_assignment(gamma, clone_names, clone_assignment_probability=0.95):
+    """R/inference-tflow.R:22-29."""
+    gamma = np.asarray(gamma)
+    mx = gamma.max(axis=1)
+    am = gamma.argmax(axis=1)
+    return [("unassigned" if mx[i] < clone_assignment_probability else clone_names[am[i]]) for i in range(len(mx))]
+
+
+def get_next_seed(rng):
+    """R/inference-tflow.R:49-51 — sample(.Machine$integer.max - 1, 1)."""
+    return int(rng.integers(1, 2 ** 31 - 1))
+
+
+def _message(verbose, msg):
+    if verbose:
+        print(msg, file=sys.stderr)
+
+
+def pca_init(Y, K, rng):
+    """psi initialisation, R/inference-tflow.R:204-208: prcomp(log2(Y+1), center, scale)$x[,1:K], scale(), + N(0,.05^2)."""
+    X = np.log2(np.asarray(Y, dtype=np.float64) + 1.0)
+    X = X - X.mean(axis=0)
+    sd = X.std(axis=0, ddof=1)
+    if np.any(sd == 0):
+        raise ValueError("cannot rescale a constant/zero column to unit variance")
+    X = X / sd
+    U, S, _ = np.linalg.svd(X, full_matrices=False)
+    pcs = (U * S)[:, :K]
+    pcs = (pcs - pcs.mean(axis=0)) / pcs.std(axis=0, ddof=1)
+    return pcs + rng.normal(0.0, 0.05, size=pcs.shape)
+
+
+def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1, gene_filter_threshold=0,
+                    x=None, clone_allele=None, cov=None, ref=None, fix_alpha=False, dtype="float32",
+                    saturate_=True, saturation_threshold=6, K=1, mc_samples=1, verbose=True, initial_shrink=5,
+                    data_init_mu=True, seed=None, device=0, psi_init=None, y_store="auto", path="auto",
+                    gene_names=None):
+    """CUDA-backed equivalent of the reference's `inference_tflow`.
+
+    Y_dat: cell x gene counts; L_dat: gene x clone copy number.  Returns the reference's list as a dict:
+    ml_params {mu, clone_probs, s, alpha [, beta] [, psi, W, chi]}, convergence_info {final_elbo,
+    sd_final_elbo, elbo}, retained_genes, clone_probs_from_snv (R/inference-tflow.R:475-480).
+    `fix_alpha` and `initial_shrink` are accepted and ignored, as in the reference (:81,:88).
+    `psi_init` (N x K) skips the PCA; it exists for callers that compute the initialisation elsewhere.
+    """
+    if dtype not in ("float32", "float64"):
+        raise ValueError("'arg' should be one of 'float32', 'float64'")
+    if dtype == "float64":
+        raise ValueError("dtype='float64' is broken in the reference graph (tf$to_float, "
+                         "R/inference-tflow.R:323); only float32 is supported")
+    rng = np.random.default_rng(seed)
+    _message(verbose, "Constructing CUDA session")
+
+    Y_dat = np.asarray(Y_dat)
+    L_dat = np.asarray(L_dat, dtype=np.float64)
+    zero_gene_means = Y_dat.sum(axis=0) <= gene_filter_threshold                      # :117
+    _message(verbose, f"Removing {int(zero_gene_means.sum())} genes with low counts")  # :120
+    Y = Y_dat[:, ~zero_gene_means]
+    L = L_dat[~zero_gene_means, :]
+    if gene_names is not None:
+        retained_genes = [g for g, z in zip(gene_names, zero_gene_means) if not z]    # :127-128
+    else:
+        retained_genes = (np.nonzero(~zero_gene_means)[0] + 1).tolist()               # which(), 1-based :130
+    N, G = Y.shape
+    if L.shape[0] != G:
+        raise ValueError("nrow(L_dat) == G is not TRUE")                              # :139
+    K = int(K)
+    if saturate_:
+        L = saturate(L, saturation_threshold)                                         # :142-144
+    if x is not None:                                                                 # :147-153
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 1:
+            x = x[:, None]
+        if x.shape[0] != N:
+            raise ValueError("nrow(x) == N is not TRUE")
+
+    use_allele = clone_allele is not None and ref is not None and cov is not None     # :167
+    alt = None
+    if use_allele:
+        _message(verbose, "Using allelic imbalance info")
+        clone_allele = np.asarray(clone_allele, dtype=np.float64)
+        cov = np.asarray(cov, dtype=np.float64)
+        ref = np.asarray(ref, dtype=np.float64)
+        V = clone_allele.shape[0]
+        # sanitize_allele_info, R/allele-specific.R:61-71
+        if clone_allele.shape[1] != L.shape[1] or cov.shape != (N, V) or ref.shape != (N, V):
+            raise ValueError("allele inputs have inconsistent dimensions")
+        alt = cov - ref                                                               # :180
+
+    if psi_init is None:
+        psi_init = pca_init(Y, K, rng) if K > 0 else np.zeros((N, 0))                 # :204-208
+    s_init = np.asarray(Y, dtype=np.float64).sum(axis=1)                              # :210
+    if np.any(s_init == 0):
+        raise ValueError("Some cells have no counts mapping")                         # :212-214
+    if isinstance(data_init_mu, (bool, np.bool_)):                                    # :220-235
+        if data_init_mu:
+            Yd = np.asarray(Y, dtype=np.float64)
+            mu_guess = (Yd / Yd.mean(axis=1, keepdims=True)).mean(axis=0)
+        else:
+            mu_guess = np.ones(G)
+    else:
+        _message(verbose, "Using user-provided mu values to start")
+        d = np.asarray(data_init_mu, dtype=np.float64)
+        mu_guess = d / d.mean()
+
+    op_seed = get_next_seed(rng)                                                      # :269
+    sess = Session(Y, L, psi_init, safe_inverse_softplus(mu_guess), mc_samples=int(mc_samples), K=K, x=x,
+                   learning_rate=learning_rate, seed=op_seed, device=device,
+                   clone_allele=clone_allele if use_allele else None, alt=alt, cov=cov if use_allele else None,
+                   y_store=y_store, path=path)
+    try:
+        sess.init_gamma()                                                             # :368-369
+        elbo_val = sess.elbo()                                                        # :372
+        if np.isnan(elbo_val):
+            raise ValueError("Initial elbo is NA")                                    # :374-376
+        elbo_diffs = [1e3] * 10                                                       # :379
+        elbos = [elbo_val]
+        _message(verbose, "Optimizing ELBO")
+        for _ in range(int(max_iter)):                                                # :394
+            sess.step()                                                               # :401
+            elbo_new = sess.elbo()                                                    # :403
+            elbo_diff = (elbo_new - elbo_val) / abs(elbo_val)
+            elbo_diffs = elbo_diffs[1:] + [elbo_diff]
+            elbos.append(elbo_new)
+            elbo_val = elbo_new
+            if np.mean(np.abs(elbo_diffs)) < rel_tol:                                 # :414
+                break
+        _message(verbose, "\nELBO converged or reached max iterations")
+        rlist = sess.params()                                                         # :424-434
+        clone_probs_from_snv = rlist.pop("clone_probs_from_snv", None)                # :436-440
+        _message(verbose, "Computing final ELBO")
+        final_elbo = [sess.elbo() for _ in range(20)]                                 # :447-449
+    finally:
+        sess.close()                                                                  # :457
+    convergence_info = {"final_elbo": float(np.mean(final_elbo)),
+                        "sd_final_elbo": float(np.std(final_elbo, ddof=1)),
+                        "elbo": np.array(elbos)}
+    return {"ml_params": rlist, "convergence_info": convergence_info, "retained_genes": retained_genes,
+            "clone_probs_from_snv": clone_probs_from_snv}

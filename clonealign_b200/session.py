@@ -1,0 +1,263 @@
+"""`Session`: the CUDA replacement for the TensorFlow session used by `inference_tflow()`.
+
+Lifecycle mirrors R/inference-tflow.R:351-457 of the reference:
+
+    sess <- tf$Session(); sess$run(init)          -> Session(...)
+    sess$run(gamma_init) / sess$run(init_gamma)   -> Session.init_gamma()
+    sess$run(train)                               -> Session.step()
+    sess$run(elbo)                                -> Session.elbo()
+    sess$run(list(softplus(loc), gamma, ...))     -> Session.params()
+    sess$close()                                  -> Session.close()
+
+Everything numeric happens in libclonealign_b200.so (hand-written sm_100a kernels) through the
+C-ABI of include/clonealign_b200.h; this file only marshals buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+
+import numpy as np
+
+from . import _lib
+
+_STORE = {"auto": _lib.STORE_AUTO, "f32": _lib.STORE_F32, "u16": _lib.STORE_U16, "u8": _lib.STORE_U8}
+_PATH = {"auto": _lib.PATH_AUTO, "cudacore": _lib.PATH_CUDACORE, "tensor": _lib.PATH_TENSOR}
+
+_SHAPES = {  # name -> lambda(session) -> (rows, cols)
+    "W": lambda s: (s.G, s.K), "beta": lambda s: (s.G, s.P), "psi": lambda s: (s.N, s.K),
+    "chi_raw": lambda s: (s.K, 1), "alpha_unconstr": lambda s: (s.C, 1), "loc": lambda s: (s.G, 1),
+    "lsd": lambda s: (s.G, 1), "gamma_logits": lambda s: (s.N, s.C),
+    "Z": lambda s: (s.N, s.S * s.C), "R": lambda s: (s.N, s.S * s.C), "dM": lambda s: (s.G, s.S * s.C),
+    "F": lambda s: (s.N, s.C), "YV": lambda s: (s.N, s.K + s.P), "YtU": lambda s: (s.G, s.K + s.P),
+    "B": lambda s: (s.N, s.C), "v": lambda s: (s.N, s.C), "s": lambda s: (s.N, 1), "colsum": lambda s: (s.G, 1),
+    "shift": lambda s: (s.N, 1), "mu_samples": lambda s: (s.S, s.G),
+}
+
+
+def _f64_colmajor(a, shape=None):
+    if a is None:
+        return None
+    a = np.asarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return np.asfortranarray(a)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Session:
+    """One cell shard of one fit on one GPU."""
+
+    def __init__(self, Y, L, psi_init, loc_init, *, mc_samples=1, K=1, x=None, learning_rate=0.1, seed=0,
+                 device=0, clone_allele=None, alt=None, cov=None, rank=0, world=1, nccl_id=None, n_total=None,
+                 colsum_total=None, y_store="auto", path="auto"):
+        self._h = None
+        lib = _lib.load()
+        self._lib = lib
+        self._err = C.create_string_buffer(1024)
+
+        cfg = _lib.CaConfig()
+        keep = []
+        if hasattr(Y, "data_ptr") and getattr(Y, "is_cuda", False):      # a CUDA tensor already in HBM
+            if Y.dim() != 2 or not Y.is_contiguous() or str(Y.dtype) != "torch.float32":
+                raise ValueError("device Y must be a contiguous 2-D float32 tensor (cells x genes)")
+            N, G = int(Y.shape[0]), int(Y.shape[1])
+            yptr = C.c_void_p(Y.data_ptr())
+            cfg.y_dtype, cfg.y_layout, cfg.y_mem = _lib.Y_F32, _lib.Y_ROWMAJOR, _lib.Y_DEVICE
+            keep.append(Y)
+        else:
+            Y = np.asarray(Y)
+            if Y.ndim != 2:
+                raise ValueError("Y must be cells x genes")
+            if Y.dtype == np.float64:
+                cfg.y_dtype = _lib.Y_F64
+            elif Y.dtype == np.float32:
+                cfg.y_dtype = _lib.Y_F32
+            elif Y.dtype == np.int32:
+                cfg.y_dtype = _lib.Y_I32
+            else:
+                Y = Y.astype(np.float64)
+                cfg.y_dtype = _lib.Y_F64
+            if Y.flags.f_contiguous and not Y.flags.c_contiguous:
+                cfg.y_layout = _lib.Y_COLMAJOR                            # an R matrix
+            else:
+                Y = np.ascontiguousarray(Y)
+                cfg.y_layout = _lib.Y_ROWMAJOR
+            cfg.y_mem = _lib.Y_HOST
+            N, G = Y.shape
+            yptr = _ptr(Y)
+            keep.append(Y)
+        Lm = _f64_colmajor(L)
+        if Lm.ndim != 2 or Lm.shape[0] != G:
+            raise ValueError("copy_number_data must have same number of genes (rows) as gene_expression_data")
+        Cn = Lm.shape[1]
+        K = int(K)
+        psi = _f64_colmajor(psi_init, (N, K)) if K > 0 else None
+        loc = _f64_colmajor(loc_init, (G,))
+        X = None
+        P = 0
+        if x is not None:
+            X = np.asarray(x, dtype=np.float64)
+            if X.ndim == 1:
+                X = X[:, None]
+            if X.shape[0] != N:
+                raise ValueError("x must have one row per cell")
+            P = X.shape[1]
+            X = np.asfortranarray(X)
+        V = 0
+        ca = al = cv = None
+        if clone_allele is not None:
+            ca = _f64_colmajor(clone_allele)
+            V = ca.shape[0]
+            if ca.shape[1] != Cn:
+                raise ValueError("clone_allele must be variants x clones")
+            al = _f64_colmajor(alt, (N, V))
+            cv = _f64_colmajor(cov, (N, V))
+        cs = _f64_colmajor(colsum_total, (G,)) if colsum_total is not None else None
+        idbuf = None
+        if world > 1:
+            if nccl_id is None or len(nccl_id) != 128:
+                raise ValueError("world > 1 needs the 128-byte nccl_id from Session.nccl_unique_id()")
+            idbuf = C.create_string_buffer(bytes(nccl_id), 128)
+
+        cfg.N, cfg.N_total = N, int(n_total) if n_total is not None else N
+        cfg.G, cfg.C, cfg.S, cfg.K, cfg.P, cfg.V = G, Cn, int(mc_samples), K, P, V
+        cfg.learning_rate, cfg.seed = float(learning_rate), int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.device, cfg.rank, cfg.world = int(device), int(rank), int(world)
+        cfg.y_store, cfg.path, cfg.y_ld = _STORE[y_store], _PATH[path], 0
+        cfg.nccl_id = C.cast(idbuf, C.c_void_p) if idbuf is not None else None
+
+        self.N, self.G, self.C, self.S, self.K, self.P, self.V = N, G, Cn, int(mc_samples), K, P, V
+        h = C.c_void_p()
+        st = lib.ca_core_create(C.byref(h), C.byref(cfg), yptr, _ptr(Lm), _ptr(psi), _ptr(loc), _ptr(X), _ptr(cs),
+                                _ptr(ca), _ptr(al), _ptr(cv), self._err, len(self._err))
+        _lib.check(st, self._err)
+        self._h = h
+        del keep
+
+    # -- discovery --------------------------------------------------------------------------------
+    @staticmethod
+    def device_count() -> int:
+        lib = _lib.load()
+        n = C.c_int(0)
+        err = C.create_string_buffer(512)
+        _lib.check(lib.ca_core_device_count(C.byref(n), err, len(err)), err)
+        return n.value
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        lib = _lib.load()
+        buf = C.create_string_buffer(128)
+        err = C.create_string_buffer(512)
+        _lib.check(lib.ca_core_nccl_unique_id(buf, err, len(err)), err)
+        return buf.raw
+
+    # -- the session operations ---------------------------------------------------------------------
+    def _chk(self, st):
+        _lib.check(st, self._err)
+
+    def init_gamma(self):
+        self._chk(self._lib.ca_core_init_gamma(self._h, self._err, len(self._err)))
+
+    def step(self):
+        self._chk(self._lib.ca_core_step(self._h, self._err, len(self._err)))
+
+    def grads(self):
+        self._chk(self._lib.ca_core_grads(self._h, self._err, len(self._err)))
+
+    def elbo(self) -> float:
+        out = C.c_double(0.0)
+        self._chk(self._lib.ca_core_elbo(self._h, C.byref(out), self._err, len(self._err)))
+        return out.value
+
+    def params(self) -> dict:
+        """mu, clone_probs, s, alpha [, beta] [, psi, W, chi] [, clone_probs_from_snv] (R/inference-tflow.R:424-440)."""
+        N, G, Cn, K, P = self.N, self.G, self.C, self.K, self.P
+        f = lambda *shape: np.zeros(shape, dtype=np.float64, order="F")
+        mu, cp, s, alpha = f(G), f(N, Cn), f(N), f(Cn)
+        psi = f(N, K) if K > 0 else None
+        W = f(G, K) if K > 0 else None
+        chi = f(K) if K > 0 else None
+        beta = f(G, P) if P > 0 else None
+        snv = f(N, Cn) if self.V > 0 else None
+        self._chk(self._lib.ca_core_params(self._h, _ptr(mu), _ptr(cp), _ptr(s), _ptr(alpha), _ptr(psi), _ptr(W),
+                                           _ptr(chi), _ptr(beta), _ptr(snv), self._err, len(self._err)))
+        out = {"mu": mu, "clone_probs": cp, "s": s, "alpha": alpha}
+        if P > 0:
+            out["beta"] = beta
+        if K > 0:
+            out.update(psi=psi, W=W, chi=chi)
+        if snv is not None:
+            out["clone_probs_from_snv"] = snv
+        return out
+
+    # -- parity / test hooks ------------------------------------------------------------------------
+    def set_eps(self, eps):
+        """Queue host-fed N(0,1) draws, shape (n_draws, S, G) or (S, G)."""
+        e = np.ascontiguousarray(eps, dtype=np.float32)
+        if e.ndim == 2:
+            e = e[None]
+        if e.shape[1:] != (self.S, self.G):
+            raise ValueError(f"eps must have shape (n, {self.S}, {self.G})")
+        self._chk(self._lib.ca_core_set_eps(self._h, _ptr(e), e.shape[0], self._err, len(self._err)))
+
+    def get_eps(self):
+        e = np.zeros((self.S, self.G), dtype=np.float32)
+        self._chk(self._lib.ca_core_get_eps(self._h, _ptr(e), self._err, len(self._err)))
+        return e
+
+    def get_array(self, name: str):
+        base = name[5:] if name.startswith("grad_") else name
+        rows, cols = _SHAPES[base](self)
+        out = np.zeros((rows, cols), dtype=np.float64, order="F")
+        if out.size:
+            self._chk(self._lib.ca_core_get_array(self._h, name.encode(), _ptr(out), out.size, self._err, len(self._err)))
+        return np.ascontiguousarray(out)
+
+    def set_array(self, name: str, value):
+        rows, cols = _SHAPES[name](self)
+        v = _f64_colmajor(value, (rows, cols))
+        if v.size:
+            self._chk(self._lib.ca_core_set_array(self._h, name.encode(), _ptr(v), v.size, self._err, len(self._err)))
+
+    # -- measurement hooks --------------------------------------------------------------------------
+    def time_steps(self, n_steps: int, with_eval: bool = False) -> float:
+        """Milliseconds (CUDA events on the library's stream) for n_steps train steps [+ ELBO evals]."""
+        ms = C.c_double(0.0)
+        self._chk(self._lib.ca_core_time_steps(self._h, int(n_steps), int(bool(with_eval)), C.byref(ms), self._err,
+                                               len(self._err)))
+        return ms.value
+
+    def profile_step(self) -> list:
+        names = C.create_string_buffer(4096)
+        ms = (C.c_double * 64)()
+        nk = C.c_int32(0)
+        self._chk(self._lib.ca_core_profile_step(self._h, names, len(names), ms, 64, C.byref(nk), self._err,
+                                                 len(self._err)))
+        labels = names.value.decode().split(";") if names.value else []
+        return [(labels[i], ms[i]) for i in range(nk.value)]
+
+    def describe(self) -> dict:
+        buf = C.create_string_buffer(1024)
+        self._lib.ca_core_describe(self._h, buf, len(buf))
+        return json.loads(buf.value.decode())
+
+    def close(self):
+        if self._h is not None:
+            self._lib.ca_core_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,136 @@
+/* clonealign_b200 — C-ABI of the B200 backend for clonealign's variational hot path.
+ *
+ * This is the drop-in boundary.  The reference (kieranrcampbell/clonealign, R) runs the path as a
+ * TensorFlow-1 session inside `inference_tflow()` (R/inference-tflow.R:71-481); each entry point
+ * below replaces one use of that session and is what an R `.Call` shim (r/src/ca_shim.c,
+ * INTEGRATION.md) or the Python host mirror (clonealign_b200/session.py, ctypes) binds:
+ *
+ *   ca_core_create      graph build + sess$run(init)            R/inference-tflow.R:240-353
+ *   ca_core_init_gamma  sess$run(gamma_init) + assign           R/inference-tflow.R:338-342,368-369
+ *   ca_core_step        sess$run(train)                         R/inference-tflow.R:345-346,401
+ *   ca_core_elbo        sess$run(elbo)                          R/inference-tflow.R:336,372,403,448
+ *   ca_core_params      sess$run(list(softplus(loc),gamma,...)) R/inference-tflow.R:424-440
+ *   ca_core_destroy     sess$close()                            R/inference-tflow.R:457
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no C++/torch types.  Every call returns 0 on success and a
+ *     non-zero status with a message in `err` (NUL-terminated, truncated to errlen) otherwise.
+ *     Nothing throws or longjmps across this boundary.
+ *   - Small dense matrices cross the ABI as COLUMN-MAJOR doubles, exactly as R stores them
+ *     (L: G x C, psi: N x K, X: N x P, clone_allele: V x C, alt/cov: N x V, outputs likewise).
+ *   - The count matrix Y (cells x genes) is the one large operand; its element type, layout and
+ *     memory space are described by ca_config so that R (column-major double / integer on the
+ *     host) and a CUDA-aware caller (row-major float already in HBM) both avoid extra copies.
+ *   - The caller owns every input buffer; the library copies what it needs during ca_core_create
+ *     and never retains caller pointers.
+ *   - There is NO CPU fallback: without a usable CUDA device every call fails with a message.
+ */
+#ifndef CLONEALIGN_B200_H
+#define CLONEALIGN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CA_ABI_VERSION 1
+#if defined(__GNUC__)
+#define CA_API __attribute__((visibility("default")))
+#else
+#define CA_API
+#endif
+
+typedef struct ca_handle ca_handle;
+
+enum ca_y_dtype  { CA_Y_F64 = 0, CA_Y_F32 = 1, CA_Y_I32 = 2 };
+enum ca_y_layout { CA_Y_COLMAJOR = 0 /* R matrix: cell index fastest */, CA_Y_ROWMAJOR = 1 /* gene index fastest */ };
+enum ca_y_mem    { CA_Y_HOST = 0, CA_Y_DEVICE = 1 };
+/* how Y is kept in HBM: fp32 (the reference's tensor dtype) or, when every count is an integer that
+ * fits, a narrower unsigned type.  AUTO picks the narrowest exact representation. */
+enum ca_y_store  { CA_STORE_AUTO = 0, CA_STORE_F32 = 1, CA_STORE_U16 = 2, CA_STORE_U8 = 3 };
+/* which contraction kernels run: AUTO = tcgen05 path when K == 1 and P == 0 (the reference's default
+ * model), CUDA-core fp32 path otherwise. */
+enum ca_path     { CA_PATH_AUTO = 0, CA_PATH_CUDACORE = 1, CA_PATH_TENSOR = 2 };
+
+typedef struct ca_config {
+  int64_t N;            /* cells held by this handle (this rank's shard)                       */
+  int64_t N_total;      /* cells over all ranks (== N when world == 1)                         */
+  int32_t G;            /* genes (after the host-side gene filter)                             */
+  int32_t C;            /* clones                                                              */
+  int32_t S;            /* Monte-Carlo samples (mc_samples)                                    */
+  int32_t K;            /* latent dimensions of psi / W                                        */
+  int32_t P;            /* covariates (columns of x)                                           */
+  int32_t V;            /* variants for the allele-specific likelihood; 0 = not used           */
+  double  learning_rate;
+  uint64_t seed;        /* seeds the counter-based N(0,1) generator (get_next_seed() in R)     */
+  int32_t device;       /* CUDA device ordinal                                                 */
+  int32_t rank;         /* 0..world-1                                                          */
+  int32_t world;        /* number of cell shards / GPUs                                        */
+  int32_t y_dtype;      /* enum ca_y_dtype                                                     */
+  int32_t y_layout;     /* enum ca_y_layout                                                    */
+  int32_t y_mem;        /* enum ca_y_mem                                                       */
+  int32_t y_store;      /* enum ca_y_store                                                     */
+  int32_t path;         /* enum ca_path                                                        */
+  int64_t y_ld;         /* leading dimension of Y in elements (0 = tight)                      */
+  const void* nccl_id;  /* 128-byte ncclUniqueId shared by all ranks when world > 1, else NULL */
+} ca_config;
+
+/* library / device discovery */
+CA_API int ca_core_abi_version(void);
+CA_API int ca_core_device_count(int* count, char* err, size_t errlen);
+/* writes a fresh 128-byte ncclUniqueId (rank 0 calls this and ships it to the other ranks) */
+CA_API int ca_core_nccl_unique_id(void* out128, char* err, size_t errlen);
+
+/* Build the device state.  Y: N x G counts as described by cfg.  L: G x C copy number (already
+ * saturated, R/clonealign.R:394-397).  psi_init: N x K.  loc_init: G values of
+ * safe_inverse_softplus(mu_guess) (R/inference-tflow.R:262).  X: N x P or NULL.
+ * colsum_total: G global column sums of Y over ALL ranks, or NULL when world == 1.
+ * Allele inputs (V > 0): clone_allele V x C, alt and cov N x V (R/allele-specific.R:17-48). */
+CA_API int ca_core_create(ca_handle** out, const ca_config* cfg, const void* Y, const double* L,
+                   const double* psi_init, const double* loc_init, const double* X,
+                   const double* colsum_total, const double* clone_allele, const double* alt,
+                   const double* cov, char* err, size_t errlen);
+CA_API int ca_core_destroy(ca_handle* h);
+
+/* the session operations */
+CA_API int ca_core_init_gamma(ca_handle* h, char* err, size_t errlen);
+CA_API int ca_core_step(ca_handle* h, char* err, size_t errlen);
+CA_API int ca_core_elbo(ca_handle* h, double* elbo, char* err, size_t errlen);
+/* any output pointer may be NULL.  mu: G, clone_probs: N x C, s: N, alpha: C, psi: N x K,
+ * W: G x K, chi: K, beta: G x P, clone_probs_from_snv: N x C (only when V > 0). */
+CA_API int ca_core_params(ca_handle* h, double* mu, double* clone_probs, double* s, double* alpha,
+                   double* psi, double* W, double* chi, double* beta, double* clone_probs_from_snv,
+                   char* err, size_t errlen);
+
+/* Test / parity hooks ("fixed MC draws"): feed the next eps draws from the host (S x G floats,
+ * sample-major: eps[s*G + g]); n_draws consecutive draws are queued and consumed one per
+ * init_gamma / step / elbo call; when the queue is empty the device generator is used. */
+CA_API int ca_core_set_eps(ca_handle* h, const float* eps, int64_t n_draws, char* err, size_t errlen);
+/* eps used by the most recent init_gamma / step / elbo call (S x G floats) */
+CA_API int ca_core_get_eps(ca_handle* h, float* eps, char* err, size_t errlen);
+/* gradients of the ELBO without the Adam update (same draw consumption as ca_core_step) */
+CA_API int ca_core_grads(ca_handle* h, char* err, size_t errlen);
+/* read / write a named device array as column-major doubles.  Names: W chi_raw psi beta
+ * alpha_unconstr loc lsd gamma_logits (trainable); grad_<name>; mu_samples(S x G, sample-major)
+ * Z(N x S*C) R(N x S*C) dM(G x S*C) F(N x C) YV(N x (K+P)) YtU(G x (K+P)) B(N x C) v(N x C)
+ * const(N) colsum(G) shift(N).  `n` is the capacity / length in elements. */
+CA_API int ca_core_get_array(ca_handle* h, const char* name, double* out, int64_t n, char* err, size_t errlen);
+CA_API int ca_core_set_array(ca_handle* h, const char* name, const double* in, int64_t n, char* err, size_t errlen);
+
+/* Measurement hooks (bench.py): run n_steps train steps (and, if with_eval != 0, one ELBO
+ * evaluation after each, as the reference loop does) back to back on the handle's stream,
+ * bracketed by CUDA events on that stream; *ms = elapsed milliseconds. */
+CA_API int ca_core_time_steps(ca_handle* h, int32_t n_steps, int32_t with_eval, double* ms, char* err, size_t errlen);
+/* per-kernel device time of ONE train step, measured with events around every launch.
+ * names: buffer for a ';'-separated list of kernel labels; ms[i] their durations; *n_k count. */
+CA_API int ca_core_profile_step(ca_handle* h, char* names, size_t names_len, double* ms, int32_t cap, int32_t* n_k,
+                         char* err, size_t errlen);
+/* static facts for the roofline: bytes of Y as stored, kernels per step, path in use ... as a JSON string */
+CA_API int ca_core_describe(ca_handle* h, char* json, size_t json_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLONEALIGN_B200_H */
