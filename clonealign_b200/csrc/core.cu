@@ -228,8 +228,8 @@ struct LaunchScope {
   ca_handle* h;
   bool on;
   size_t idx = 0;
-  LaunchScope(ca_handle* h_, const char* name) : h(h_), on(h_->prof_on) {
-    h->launches_last_step++;
+  LaunchScope(ca_handle* h_, const char* name, int n_kernels = 1) : h(h_), on(h_->prof_on) {
+    h->launches_last_step += n_kernels;
     if (on) {
       Prof p;
       p.name = name;
@@ -336,7 +336,7 @@ void run_forward(ca_handle* h, int mode) {
   if (h->KP == 0) {
     CUDA_OK(cudaMemsetAsync(h->shift, 0, sizeof(float) * h->N, h->stream));
   } else if (h->K == 1 && h->P == 0) {
-    LaunchScope ls(h, "shift");
+    LaunchScope ls(h, "shift", 2);
     k_minmax<<<1, 1024, 0, h->stream>>>(h->Vm, h->G, h->mm);
     KCHECK();
     k_shift_k1<<<(unsigned)ceil_div64(h->N, 256), 256, 0, h->stream>>>(h->U, h->mm, h->N, h->shift);
@@ -389,7 +389,7 @@ void run_train(ca_handle* h, bool apply) {
     KCHECK();
   }
   {
-    LaunchScope ls(h, "gene_grads");
+    LaunchScope ls(h, "gene_grads", 2);
     GeneGradArgs a;
     a.G = h->G; a.C = h->C; a.S = h->S; a.K = h->K; a.KP = h->KP; a.SCp = h->SCp; a.J = h->J; a.nsplit = h->nsplit; a.nRB = h->nRB;
     a.dMx = h->dMx; a.colpart = h->colpart; a.mu = h->mu; a.sig = h->sig; a.eps = h->eps; a.lsd = h->lsd; a.L = h->L;
@@ -405,7 +405,7 @@ void run_train(ca_handle* h, bool apply) {
     NCCL_OK(nccl().AllReduce(h->ar, h->ar, cnt, kNcclFloat32, kNcclSum, h->comm, h->stream));
   }
   {
-    LaunchScope ls(h, "adam");
+    LaunchScope ls(h, "adam", apply ? 4 : 3);
     AdamHyper hy = adam_hyper(h, apply);
     k_wsq<<<1, 1024, 0, h->stream>>>(h->Vm, h->G, h->K, h->KP, h->wsq);
     KCHECK();
@@ -440,7 +440,7 @@ void run_train(ca_handle* h, bool apply) {
 void run_elbo_async(ca_handle* h) {
   h->launches_last_step = 0;
   run_forward(h, EPI_EVAL);
-  LaunchScope ls(h, "elbo_reduce");
+  LaunchScope ls(h, "elbo_reduce", 2);
   k_reduce_partials<<<1, 1024, 0, h->stream>>>(h->elbo_part, h->n_epi_blocks, 1, h->cell_sum, h->const_sum);
   KCHECK();
   if (h->cfg.world > 1) NCCL_OK(nccl().AllReduce(h->cell_sum, h->cell_sum, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
@@ -1035,9 +1035,10 @@ int ca_core_describe(ca_handle* h, char* json, size_t json_len) {
   int bpe = h->ystore == CA_STORE_F32 ? 4 : (h->ystore == CA_STORE_U16 ? 2 : 1);
   snprintf(json, json_len,
            "{\"N\": %lld, \"G\": %d, \"C\": %d, \"S\": %d, \"K\": %d, \"P\": %d, \"path\": \"%s\", \"y_store\": \"%s\", "
-           "\"y_bytes_per_entry\": %d, \"ldY\": %lld, \"launches_last_step\": %d, \"nsplit\": %d, \"world\": %d, \"rank\": %d}",
+           "\"y_bytes_per_entry\": %d, \"ldY\": %lld, \"launches_last_step\": %d, \"nsplit\": %d, \"fsplit\": %d, "
+           "\"SCp\": %d, \"J\": %d, \"world\": %d, \"rank\": %d}",
            (long long)h->N, h->G, h->C, h->S, h->K, h->P, h->tc ? "tcgen05" : "cudacore", st, bpe, (long long)h->ldY,
-           h->launches_last_step, h->nsplit, h->cfg.world, h->cfg.rank);
+           h->launches_last_step, h->nsplit, h->tc ? h->tcplan.fsplit : 1, h->SCp, h->J, h->cfg.world, h->cfg.rank);
   return 0;
 }
 

@@ -116,6 +116,8 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
         if x.shape[0] != N:
             raise ValueError("nrow(x) == N is not TRUE")
 
+    if K == 0:
+        x = None   # reference quirk (:279-285): without latent dimensions the covariates never enter the graph
     use_allele = clone_allele is not None and ref is not None and cov is not None     # :167
     alt = None
     if use_allele:

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
+import os
 
 import numpy as np
 
@@ -55,6 +56,8 @@ class Session:
                  device=0, clone_allele=None, alt=None, cov=None, rank=0, world=1, nccl_id=None, n_total=None,
                  colsum_total=None, y_store="auto", path="auto"):
         self._h = None
+        if path == "auto":   # operator override, e.g. CLONEALIGN_B200_PATH=cudacore
+            path = os.environ.get("CLONEALIGN_B200_PATH", "auto")
         lib = _lib.load()
         self._lib = lib
         self._err = C.create_string_buffer(1024)
