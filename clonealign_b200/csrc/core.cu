@@ -188,7 +188,9 @@ struct ca_handle {
   // per-iteration scratch
   float *eps_in = nullptr, *eps = nullptr, *mu = nullptr, *logmu = nullptr, *sig = nullptr;
   float *Mx = nullptr, *shift = nullptr, *mm = nullptr, *Zx = nullptr, *Rx = nullptr, *dMx = nullptr, *dM_sum = nullptr;
-  __nv_bfloat16 *MxT_hi = nullptr, *MxT_lo = nullptr, *RxT = nullptr;
+  __nv_bfloat16 *MxT_hi = nullptr, *MxT_lo = nullptr;
+  __half* RxT = nullptr;
+  float* shift_bwd = nullptr;
   float *rowpart = nullptr, *colpart = nullptr, *YV = nullptr, *YtU = nullptr, *Fout = nullptr, *log_alpha = nullptr;
   float* ar = nullptr;
   double *gsum_part = nullptr, *elbo_part = nullptr, *gene_part = nullptr, *scal_elbo = nullptr, *cell_sum = nullptr,
@@ -365,7 +367,7 @@ void run_forward(ca_handle* h, int mode) {
     a.fsplit = h->tc ? h->tcplan.fsplit : 1;
     a.Zx = h->Zx; a.Bm = h->Bm; a.vA = h->vA; a.s = h->s; a.shift = h->shift; a.log_alpha = h->log_alpha; a.U = h->U;
     a.rowpart = h->rowpart; a.t = h->t; a.gT = h->g_t; a.Rx = h->tc ? nullptr : h->Rx; a.gU = h->g_U; a.YV = h->YV;
-    a.Fout = h->Fout; a.RxT = h->tc ? h->RxT : nullptr; a.elbo_part = h->elbo_part; a.gsum_part = h->gsum_part;
+    a.Fout = h->Fout; a.RxT = h->tc ? h->RxT : nullptr; a.shift_bwd = h->shift_bwd; a.elbo_part = h->elbo_part; a.gsum_part = h->gsum_part;
     size_t smem = epi_smem_bytes(h->SCp, h->C, h->J, h->tc);
     unsigned grid = (unsigned)h->n_epi_blocks;
     if (mode == EPI_TRAIN) k_cell_epilogue<EPI_TRAIN><<<grid, kEpiWarps * 32, smem, h->stream>>>(a);
@@ -381,7 +383,7 @@ void run_train(ca_handle* h, bool apply) {
   {
     LaunchScope ls(h, "lse_bwd");
     if (h->tc) {
-      tc_launch_bwd(h->tcplan, h->U, h->Vm, h->shift, h->dMx, h->stream);
+      tc_launch_bwd(h->tcplan, h->U, h->Vm, h->shift_bwd, h->dMx, h->stream);
     } else {
       dim3 grid((h->J + 63) / 64, (h->G + 63) / 64);
       k_expgemm<false><<<grid, 256, 0, h->stream>>>(h->Vm, h->U, h->shift, h->Rx, h->dMx, h->G, h->N, h->J, h->J, h->KP);
@@ -394,7 +396,7 @@ void run_train(ca_handle* h, bool apply) {
     a.G = h->G; a.C = h->C; a.S = h->S; a.K = h->K; a.KP = h->KP; a.SCp = h->SCp; a.J = h->J; a.nsplit = h->nsplit; a.nRB = h->nRB;
     a.dMx = h->dMx; a.colpart = h->colpart; a.mu = h->mu; a.sig = h->sig; a.eps = h->eps; a.lsd = h->lsd; a.L = h->L;
     a.ar = h->ar; a.YtU = h->YtU; a.dM_out = h->dM_sum;
-    k_gene_grads<<<(h->G + 127) / 128, 128, 0, h->stream>>>(a);
+    k_gene_grads_warp<<<(h->G + 7) / 8, 256, 0, h->stream>>>(a);
     KCHECK();
     k_reduce_gsum<<<1, 1024, 0, h->stream>>>(h->gsum_part, h->n_epi_blocks, h->C, h->ar + (int64_t)h->G * (2 + h->KP));
     KCHECK();
@@ -683,8 +685,8 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
 
   // ---- parameters (R/inference-tflow.R:240-272) ----
   auto z = [&](size_t n) { return h->alloc<float>(n); };
-  h->U = z((size_t)N * KP); h->m_U = z((size_t)N * KP); h->v_U = z((size_t)N * KP); h->g_U = z((size_t)N * KP);
-  h->Vm = z((size_t)G * KP); h->m_V = z((size_t)G * KP); h->v_V = z((size_t)G * KP); h->g_V = z((size_t)G * KP);
+  h->U = z((size_t)N * KP + 64); h->m_U = z((size_t)N * KP); h->v_U = z((size_t)N * KP); h->g_U = z((size_t)N * KP);
+  h->Vm = z((size_t)G * KP + 64); h->m_V = z((size_t)G * KP); h->v_V = z((size_t)G * KP); h->g_V = z((size_t)G * KP);
   h->chi_raw = z(K); h->m_chi = z(K); h->v_chi = z(K); h->g_chi = z(K);
   h->u = z(C); h->m_u = z(C); h->v_u = z(C); h->g_u = z(C);
   h->loc = z(G); h->m_loc = z(G); h->v_loc = z(G); h->g_loc = z(G);
@@ -701,7 +703,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
 
   // ---- scratch ----
   h->eps_in = z((size_t)S * G); h->eps = z((size_t)S * G); h->mu = z((size_t)S * G); h->logmu = z((size_t)S * G); h->sig = z((size_t)S * G);
-  h->shift = z(N); h->mm = z(2); h->log_alpha = z(C);
+  h->shift = z(N + 64); h->mm = z(2); h->log_alpha = z(C);
   h->YV = z((size_t)N * std::max(KP, 1)); h->YtU = z((size_t)G * std::max(KP, 1)); h->Fout = z((size_t)N * C);
   h->dM_sum = z((size_t)G * J);
   h->n_gene_blocks = (G + 255) / 256;
@@ -724,8 +726,9 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   h->colpart = z((size_t)h->nRB * G * std::max(KP, 1));
   if (h->tc) {
     h->MxT_hi = h->alloc<__nv_bfloat16>((size_t)J * h->Gld);
-    h->MxT_lo = h->alloc<__nv_bfloat16>((size_t)h->SCp * h->Gld);
-    h->RxT = h->alloc<__nv_bfloat16>((size_t)J * h->Nld);
+    h->MxT_lo = h->alloc<__nv_bfloat16>((size_t)J * h->Gld);
+    h->RxT = h->alloc<__half>((size_t)J * h->Nld);
+    h->shift_bwd = z((size_t)h->Nld);
     tc_plan_create(h->tcplan, h->dev, N, h->Nld, G, h->Gld, h->SCp, J, h->MxT_hi, h->MxT_lo, h->RxT);
     h->nsplit = h->tcplan.nsplit;
     h->Zx = z((size_t)h->tcplan.fsplit * N * J);

@@ -142,7 +142,7 @@ struct SampleMuArgs {
   uint64_t seed, draw;
   float *eps_out, *mu, *logmu, *sig;
   float* Mx;                       // [G][J] fp32 (CUDA-core path) or nullptr
-  __nv_bfloat16 *MxT_hi, *MxT_lo;  // [J][Gld] / [SCp][Gld] bf16 split (tensor path) or nullptr
+  __nv_bfloat16 *MxT_hi, *MxT_lo;  // [J][Gld] bf16 hi / lo split (tensor path) or nullptr
   double* gene_part;               // one partial per block
 };
 
@@ -180,7 +180,10 @@ __global__ void __launch_bounds__(256) k_sample_mu(SampleMuArgs a) {
           __nv_bfloat16 hi = __float2bfloat16_rn(m);
           a.MxT_hi[(int64_t)j * a.Gld + g] = hi;
           a.MxT_lo[(int64_t)j * a.Gld + g] = __float2bfloat16_rn(m - __bfloat162float(hi));
-          a.MxT_hi[(int64_t)(a.SCp + j) * a.Gld + g] = __float2bfloat16_rn(vk[0] * m);
+          const float wm = vk[0] * m;
+          __nv_bfloat16 whi = __float2bfloat16_rn(wm);
+          a.MxT_hi[(int64_t)(a.SCp + j) * a.Gld + g] = whi;
+          a.MxT_lo[(int64_t)(a.SCp + j) * a.Gld + g] = __float2bfloat16_rn(wm - __bfloat162float(whi));
         }
       }
     }
@@ -281,7 +284,8 @@ struct EpiArgs {
   const float *Bm, *vA, *s, *shift, *log_alpha, *U, *rowpart;
   float* t;            // gamma_logits (written in INIT mode)
   float *gT, *Rx, *gU, *YV, *Fout;
-  __nv_bfloat16* RxT;  // [J][Nld] transposed bf16 copy for the tensor path, or nullptr
+  __half* RxT;         // [J][Nld] transposed, per-cell power-of-two scaled fp16 copy for the tensor path, or nullptr
+  float* shift_bwd;    // [Nld] m_n*log2(e) - a_n: the BWD generator's per-cell exponent offset (tensor path)
   double *elbo_part, *gsum_part;
 };
 
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(kEpiWarps * 32) k_cell_epilogue(EpiArgs a) {
   double* Fc = lz + a.SCp;
   double* gam = Fc + a.C;
   double* blk = sm + (size_t)kEpiWarps * (a.SCp + 2 * a.C);   // [kEpiWarps] elbo, then [kEpiWarps][C] gamma
-  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(blk + kEpiWarps + (size_t)kEpiWarps * a.C);  // [J][kEpiWarps]
+  __half* tile = reinterpret_cast<__half*>(blk + kEpiWarps + (size_t)kEpiWarps * a.C);  // [J][kEpiWarps]
 
   const int64_t n = (int64_t)blockIdx.x * kEpiWarps + wid;
   const bool live = n < a.N;
@@ -381,20 +385,40 @@ __global__ void __launch_bounds__(kEpiWarps * 32) k_cell_epilogue(EpiArgs a) {
         double gu[kMaxKP];
 #pragma unroll
         for (int kp = 0; kp < kMaxKP; ++kp) gu[kp] = 0.0;
+        const float inv_S = 1.0f / (float)a.S;
+        // tensor path: the fp16 B operand of BWD is scaled per cell by a power of two that is folded back into
+        // the generated A operand through the per-cell shift (E 2^a_n)(R 2^-a_n) = E R, so |R^| stays in fp16 range
+        float bscale = 1.f;
+        if (a.RxT) {
+          float rmax = 0.f;
+          for (int j = lane; j < SC; j += 32) {
+            const int c = j % a.C;
+            rmax = fmaxf(rmax, (float)(gam[c] * sn) * inv_S / zrow[j]);
+          }
+          rmax = warp_max(rmax);
+          float umax = 1.f;
+          for (int kp = 0; kp < a.KP; ++kp) umax = fmaxf(umax, fabsf(a.U[n * a.KP + kp]));
+          int ex = 0;
+          if (rmax > 0.f && rmax < 3.0e38f) frexpf(rmax * umax, &ex);
+          int an = ex + 7;
+          an = an < -8 ? -8 : (an > 8 ? 8 : an);
+          bscale = exp2f((float)-an);
+          if (lane == 0) a.shift_bwd[n] = (float)(m * 1.4426950408889634) - (float)an;
+        }
         for (int j = lane; j < a.SCp; j += 32) {
           float r = 0.f;
           if (j < SC) {
-            int c = j % a.C;
-            r = (float)(gam[c] * sn / ((double)a.S * (double)zrow[j]));
+            const int c = j % a.C;
+            r = (float)(gam[c] * sn) * inv_S / zrow[j];
           }
           if (a.Rx) a.Rx[n * a.J + j] = r;
-          if (a.RxT) tile[(size_t)j * kEpiWarps + wid] = __float2bfloat16_rn(r);
+          if (a.RxT) tile[(size_t)j * kEpiWarps + wid] = __float2half_rn(r * bscale);
           for (int kp = 0; kp < a.KP; ++kp) {
             float u = a.U[n * a.KP + kp];
             float ru = u * r;
             int jj = a.SCp * (1 + kp) + j;
             if (a.Rx) a.Rx[n * a.J + jj] = ru;
-            if (a.RxT) tile[(size_t)jj * kEpiWarps + wid] = __float2bfloat16_rn(ru);
+            if (a.RxT) tile[(size_t)jj * kEpiWarps + wid] = __float2half_rn(ru * bscale);
             if (j < SC) gu[kp] += (double)r * (double)zrow[jj];
           }
         }
@@ -409,7 +433,8 @@ __global__ void __launch_bounds__(kEpiWarps * 32) k_cell_epilogue(EpiArgs a) {
       }
     }
   } else if (MODE == EPI_TRAIN && a.RxT) {
-    for (int j = lane; j < a.J; j += 32) tile[(size_t)j * kEpiWarps + wid] = __float2bfloat16_rn(0.f);
+    for (int j = lane; j < a.J; j += 32) tile[(size_t)j * kEpiWarps + wid] = __float2half_rn(0.f);
+    if (lane == 0 && n < a.Nld) a.shift_bwd[n] = 0.f;
   }
 
   if (MODE == EPI_INIT) return;
@@ -544,6 +569,56 @@ __global__ void __launch_bounds__(128) k_gene_grads(GeneGradArgs a) {
   a.ar[g] = (float)aloc;
   a.ar[a.G + g] = (float)alsd;
   for (int kp = 0; kp < a.KP; ++kp) a.ar[2 * (int64_t)a.G + (int64_t)g * a.KP + kp] = (float)gv[kp];
+}
+
+// Same contract as k_gene_grads, one WARP per gene: lanes stride over the J columns so every read of the
+// K-split partials is a coalesced 128-byte line; the three weighted column sums are reduced with a
+// fixed-pattern warp shuffle (deterministic).
+__global__ void __launch_bounds__(256) k_gene_grads_warp(GeneGradArgs a) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g >= a.G) return;
+  const int SC = a.S * a.C;
+  const float sd = expf(a.lsd[g]);
+  double aloc = 0.0, alsd = 0.0;
+  double gv[kMaxKP];
+#pragma unroll
+  for (int kp = 0; kp < kMaxKP; ++kp) gv[kp] = 0.0;
+  for (int j = lane; j < SC; j += 32) {
+    const int s = j / a.C, c = j - s * a.C;
+    const int64_t o = (int64_t)s * a.G + g;
+    const float l = a.L[(int64_t)g * a.C + c];
+    float d = 0.f;
+    for (int sp = 0; sp < a.nsplit; ++sp) d += a.dMx[((int64_t)sp * a.G + g) * a.J + j];
+    if (a.dM_out) a.dM_out[(int64_t)g * a.J + j] = d;
+    const double dx = -(double)a.sig[o] * (double)l * (double)d;
+    aloc += dx;
+    alsd += dx * (double)sd * (double)a.eps[o];
+    const float m = a.mu[o] * l;
+    for (int kp = 0; kp < a.KP; ++kp) {
+      const int jj = a.SCp * (1 + kp) + j;
+      float d2 = 0.f;
+      for (int sp = 0; sp < a.nsplit; ++sp) d2 += a.dMx[((int64_t)sp * a.G + g) * a.J + jj];
+      if (a.dM_out) a.dM_out[(int64_t)g * a.J + jj] = d2;
+      gv[kp] -= (double)m * (double)d2;
+    }
+  }
+  aloc = warp_sum(aloc);
+  alsd = warp_sum(alsd);
+  for (int kp = 0; kp < a.KP; ++kp) {
+    double t = warp_sum(gv[kp]);
+    double acc = 0.0;
+    for (int rb = lane; rb < a.nRB; rb += 32) acc += (double)a.colpart[((int64_t)rb * a.G + g) * a.KP + kp];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      a.YtU[(int64_t)g * a.KP + kp] = (float)acc;
+      a.ar[2 * (int64_t)a.G + (int64_t)g * a.KP + kp] = (float)(acc + t);
+    }
+  }
+  if (lane == 0) {
+    a.ar[g] = (float)aloc;
+    a.ar[a.G + g] = (float)alsd;
+  }
 }
 
 struct AdamHyper {

