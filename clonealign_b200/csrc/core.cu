@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -167,8 +168,10 @@ struct Prof {
 
 struct ca_handle {
   ca_config cfg{};
-  int dev = 0;
-  cudaStream_t stream = nullptr;
+  int dev = 0, num_sms = 148;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap = true;
   int64_t N = 0, Ntot = 0, ldY = 0, Gld = 0, Nld = 0;
   int G = 0, C = 0, S = 0, K = 0, P = 0, KP = 0, SC = 0, SCp = 0, J = 0, V = 0;
   bool tc = false;
@@ -271,26 +274,33 @@ AdamHyper adam_hyper(ca_handle* h, bool apply) {
 }
 
 // ---- the Y pass (K3) ---------------------------------------------------------------------------
-void run_ypass(ca_handle* h) {
+void run_ypass(ca_handle* h, cudaStream_t st) {
   if (h->KP == 0 || !h->ydirty) return;
   dispatch_y(h, [&](auto* Yp) {
     using T = typename std::remove_const<typename std::remove_pointer<decltype(Yp)>::type>::type;
     if (h->KP == 1) {
       LaunchScope ls(h, "ypass");
       dim3 grid(h->nCB, h->nRB);
-      k_ypass_k1<T><<<grid, 256, 0, h->stream>>>(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
+      if (st == h->stream && !getenv("CLONEALIGN_B200_YPASS_LIGHT")) {
+        k_ypass_k1<T><<<grid, 256, 0, st>>>(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
+      } else {
+        int64_t tiles = (int64_t)h->nCB * h->nRB;
+        unsigned g = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)h->num_sms);
+        k_ypass_k1_persistent<T><<<g, 256, 0, st>>>(Yp, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm, h->rowpart,
+                                                    h->colpart);
+      }
       KCHECK();
     } else {
       {
         LaunchScope ls(h, "ypass_rows");
-        k_ypass_rows_generic<T><<<(unsigned)ceil_div64(h->N, 8), 256, 0, h->stream>>>(Yp, h->ldY, h->N, h->G, h->KP, h->Vm,
+        k_ypass_rows_generic<T><<<(unsigned)ceil_div64(h->N, 8), 256, 0, st>>>(Yp, h->ldY, h->N, h->G, h->KP, h->Vm,
                                                                                  h->rowpart);
         KCHECK();
       }
       {
         LaunchScope ls(h, "ypass_cols");
         dim3 grid((h->G + 127) / 128, h->nRB);
-        k_ypass_cols_generic<T><<<grid, 128, 0, h->stream>>>(Yp, h->ldY, h->N, h->G, h->KP, h->RB, h->U, h->colpart);
+        k_ypass_cols_generic<T><<<grid, 128, 0, st>>>(Yp, h->ldY, h->N, h->G, h->KP, h->RB, h->U, h->colpart);
         KCHECK();
       }
     }
@@ -318,6 +328,16 @@ void stage_eps(ca_handle* h, const float** eps_in) {
 void run_forward(ca_handle* h, int mode) {
   const float* eps_in;
   stage_eps(h, &eps_in);
+  // The Y stream (HBM-bound, touches only Y, psi, W) is independent of the forward contraction (tensor / MUFU
+  // bound): fork it onto a second stream so both run on the SMs at once; joined before the per-cell epilogue.
+  bool joined_later = false;
+  if (mode != EPI_INIT && h->overlap && !h->prof_on && h->ydirty && h->KP > 0) {
+    CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
+    CUDA_OK(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    run_ypass(h, h->stream2);
+    CUDA_OK(cudaEventRecord(h->ev_join, h->stream2));
+    joined_later = true;
+  }
   {
     LaunchScope ls(h, "alpha");
     k_alpha<<<1, 32, 0, h->stream>>>(h->u, h->C, h->chi_raw, h->K, h->log_alpha, h->scal_elbo);
@@ -359,7 +379,8 @@ void run_forward(ca_handle* h, int mode) {
     }
     KCHECK();
   }
-  if (mode != EPI_INIT) run_ypass(h);
+  if (joined_later) CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+  else if (mode != EPI_INIT) run_ypass(h, h->stream);
   {
     LaunchScope ls(h, mode == EPI_TRAIN ? "cell_epilogue" : (mode == EPI_EVAL ? "cell_epilogue_eval" : "gamma_init"));
     EpiArgs a;
@@ -535,6 +556,9 @@ void destroy(ca_handle* h) {
   for (auto& p : h->prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (void* p : h->allocs)
     if (p) cudaFree(p);
+  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -557,7 +581,12 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, h->dev));
   if (prop.major != 10) fail("clonealign_b200 kernels are built for sm_100a only; device %d is sm_%d%d", h->dev, prop.major, prop.minor);
+  h->num_sms = prop.multiProcessorCount;
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  h->overlap = getenv("CLONEALIGN_B200_NO_OVERLAP") == nullptr;
 
   h->N = c.N; h->Ntot = c.N_total > 0 ? c.N_total : c.N; h->G = c.G; h->C = c.C; h->S = c.S; h->K = c.K; h->P = c.P;
   h->KP = c.K + c.P; h->SC = c.S * c.C; h->V = c.V;
@@ -730,6 +759,11 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     h->RxT = h->alloc<__half>((size_t)J * h->Nld);
     h->shift_bwd = z((size_t)h->Nld);
     tc_plan_create(h->tcplan, h->dev, N, h->Nld, G, h->Gld, h->SCp, J, h->MxT_hi, h->MxT_lo, h->RxT);
+    // The overlapped Y pass must be able to share an SM with a contraction CTA (211 KB of shared memory): give it
+    // the same (maximum) shared-memory carveout, otherwise the SM has to drain before it can be reconfigured.
+    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_persistent<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_persistent<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_persistent<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     h->nsplit = h->tcplan.nsplit;
     h->Zx = z((size_t)h->tcplan.fsplit * N * J);
     h->dMx = z((size_t)h->nsplit * G * J);

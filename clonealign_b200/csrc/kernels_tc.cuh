@@ -25,6 +25,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <stdexcept>
 #include <string>
@@ -33,12 +35,11 @@
 
 namespace ca {
 
-constexpr int kTcGenWarps = 16;                      // generator / epilogue warps (multiple of 4, divides 32)
-constexpr int kTcTasks = 32 / kTcGenWarps;           // 16-byte chunk-tasks per generator thread and K block
+constexpr int kTcGenWarps = 16;                      // generator / epilogue warps: two groups of 8
+constexpr int kTcGroupThreads = kTcGenWarps / 2 * 32; // threads per generator group (one group per 128-row sub-tile)
 constexpr int kTcThreads = (kTcGenWarps + 2) * 32;   // + TMA warp + MMA warp
 constexpr int kTcBM = 128;                           // UMMA M
 constexpr int kTcBK = 64;                            // K elements per stage (one 128-byte swizzle row of 16-bit)
-constexpr int kTcTmemCols = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct TcPlan {
@@ -50,6 +51,8 @@ struct TcPlan {
   int64_t genes_per_fsplit = 0, cells_per_split = 0;
   int fwd_na = 0, fwd_nb = 0, bwd_na = 0, bwd_nb = 0;   // ring depths
   size_t fwd_smem = 0, bwd_smem = 0;
+  int tmem_cols = 256;
+  int dbg = 0;
   alignas(64) CUtensorMap tm_mhi, tm_mlo, tm_rx;
 };
 
@@ -160,7 +163,12 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
 
 // ------------------------------------------------------------------------------------------------
 // the kernel.  FWD: rows = cells (row scalar psi_n, shift m_n per row), K index = genes (w_g).
-//              BWD: rows = genes (row scalar w_g), K index = cells (psi_n and shift m_n per K index).
+//              BWD: rows = genes (row scalar w_g), K index = cells (psi_n and shift_bwd_n per K index).
+//
+// CTA tile = 256 rows = two 128-row sub-tiles that share every B stage (halves the L2 -> SM traffic of B and
+// doubles the time a B stage lives, i.e. the latency the TMA ring can hide).  Generator warps form two groups of
+// 8, one per sub-tile, each with its own A ring and its own barriers: the groups run out of phase, so while one
+// group sits in its barrier / fence phase the other keeps the MUFU (ex2) pipe busy.
 // ------------------------------------------------------------------------------------------------
 struct TcArgs {
   const float* rowv;     // FWD: psi [N]   BWD: w [G]
@@ -171,16 +179,18 @@ struct TcArgs {
   int64_t kdim;          // valid K extent (G or N)
   int64_t k_per_split;   // K elements handled per blockIdx.y (multiple of 64)
   int J, SCp;
-  int na, nb;            // A / B ring depths
+  int na, nb;            // A ring depth PER GROUP / B ring depth
+  int tmem_cols;         // 256 or 512
+  int dbg;               // timing experiments only (CLONEALIGN_B200_TC_DBG): 1 = no ex2, 2 = no B loads, 4 = 1/4 MMA, 8 = no proxy fence
 };
 
 template <bool FWD>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_expgemm_tc(const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ CUtensorMap tm_b1, TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: A ring [na] x { hi 16K | (FWD) lo 16K }, B ring [nb] x { B0 J*128 | (FWD) B1 J*128 | K-side scalars 1K },
-  // then barriers.  The K-side scalars of a block (FWD: w_g; BWD: psi_n and shift_bwd_n; 64 floats each) ride in the
-  // B ring: one bulk copy per block by the TMA warp instead of redundant global loads in every generator thread.
+  // carve: A rings [2 groups][na] x { hi 16K | (FWD) lo 16K }, B ring [nb] x { B0 J*128 | (FWD) B1 J*128 | K-side
+  // scalars 1K }, then barriers.  The K-side scalars of a block (FWD: w_g; BWD: psi_n and shift_bwd_n; 64 floats each)
+  // ride in the B ring: one bulk copy per block by the TMA warp instead of redundant global loads per thread.
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr uint32_t a_tile = kTcBM * 128;
   constexpr uint32_t a_stage = a_tile * (FWD ? 2 : 1);
@@ -188,20 +198,20 @@ k_expgemm_tc(const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ 
   const uint32_t b_stage = b_tile * (FWD ? 2 : 1) + 1024;
   const uint32_t ks_off = b_tile * (FWD ? 2 : 1);   // offset of the K-side scalars inside a B stage
   const int na = a.na, nb = a.nb;
-  uint8_t* b_base = base + (size_t)na * a_stage;
+  uint8_t* b_base = base + (size_t)2 * na * a_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)nb * b_stage);
-  // bars: full_a[na] | empty_a[na] | full_b[nb] | empty_b[nb] | acc_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * na + 2 * nb + 1);
+  // bars: full_a[2][na] | empty_a[2][na] | full_b[nb] | empty_b[nb] | acc_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * na + 2 * nb + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_u32 = ptx::smem_u32(base), b_u32 = ptx::smem_u32(b_base), bar_u32 = ptx::smem_u32(bars);
-  auto full_a = [&](int s) { return bar_u32 + 8u * s; };
-  auto empty_a = [&](int s) { return bar_u32 + 8u * (na + s); };
-  auto full_b = [&](int s) { return bar_u32 + 8u * (2 * na + s); };
-  auto empty_b = [&](int s) { return bar_u32 + 8u * (2 * na + nb + s); };
-  const uint32_t acc_full = bar_u32 + 8u * (2 * na + 2 * nb);
+  auto full_a = [&](int t, int s) { return bar_u32 + 8u * (t * na + s); };
+  auto empty_a = [&](int t, int s) { return bar_u32 + 8u * (2 * na + t * na + s); };
+  auto full_b = [&](int s) { return bar_u32 + 8u * (4 * na + s); };
+  auto empty_b = [&](int s) { return bar_u32 + 8u * (4 * na + nb + s); };
+  const uint32_t acc_full = bar_u32 + 8u * (4 * na + 2 * nb);
 
-  const int64_t row0 = (int64_t)blockIdx.x * kTcBM;
+  const int64_t row0 = (int64_t)blockIdx.x * (2 * kTcBM);
   const int64_t kbeg = (int64_t)blockIdx.y * a.k_per_split;
   int64_t kend = kbeg + a.k_per_split;
   if (kend > a.kdim) kend = a.kdim;
@@ -209,9 +219,9 @@ k_expgemm_tc(const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ 
 
   if (warp == kTcGenWarps + 1) {
     if (lane == 0) {
-      for (int s = 0; s < na; ++s) {
-        ptx::mbar_init(full_a(s), kTcGenWarps * 32);
-        ptx::mbar_init(empty_a(s), 1);
+      for (int s = 0; s < 2 * na; ++s) {
+        ptx::mbar_init(bar_u32 + 8u * s, kTcGenWarps / 2);    // full_a: one arrival per warp of the group
+        ptx::mbar_init(bar_u32 + 8u * (2 * na + s), 1);      // empty_a
       }
       for (int s = 0; s < nb; ++s) {
         ptx::mbar_init(full_b(s), 1);
@@ -221,7 +231,7 @@ k_expgemm_tc(const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ 
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), kTcTmemCols);
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -230,74 +240,86 @@ k_expgemm_tc(const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < kTcGenWarps) {
-    // ===================== A-operand generators =====================
-    const int r = tid & (kTcBM - 1);        // row of the tile owned by this thread
-    const int cpar = tid >> 7;              // which 16-byte chunks of the row: cpar, cpar + kTcGenWarps/4, ...
-    const int64_t grow = row0 + r;
+    // ===================== A-operand generators: group t = sub-tile t =====================
+    const int t = warp / (kTcGenWarps / 2);
+    const int gt = tid - t * kTcGroupThreads;   // thread index inside the group, 0..255
+    const int r = gt & (kTcBM - 1);             // row of the sub-tile owned by this thread
+    const int cpar = gt >> 7;                   // 0/1: 16-byte chunks cpar, cpar+2, cpar+4, cpar+6 of the row
+    const int64_t grow = row0 + t * kTcBM + r;
     float rv = 0.f, rsh = 0.f;
     if (grow < a.rows) {
       rv = a.rowv[grow] * kLog2e;
       if (FWD) rsh = a.shift[grow] * kLog2e;
     }
-    const uint32_t a_row = a_u32 + (uint32_t)r * 128u;
+    const uint32_t a_row = a_u32 + (uint32_t)(t * na) * a_stage + (uint32_t)r * 128u;
     const uint32_t sw = (uint32_t)(r & 7);
+    // ring positions and phases are carried incrementally (runtime '%' and '/' cost ~40 instructions each)
+    int st = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
     for (int kb = 0; kb < nkb; ++kb) {
-      const int st = kb % na, sb = kb % nb;
-      ptx::mbar_wait(full_b(sb), (uint32_t)(kb / nb) & 1u);           // K-side scalars of this block have landed
-      ptx::mbar_wait(empty_a(st), ((uint32_t)(kb / na) & 1u) ^ 1u);   // A slot free
-      const uint32_t sA = a_row + (uint32_t)st * a_stage;
+      ptx::mbar_wait(full_b(sb), pb);                                    // K-side scalars of this block have landed
       const uint32_t ks = b_u32 + (uint32_t)sb * b_stage + ks_off;
+      // all exponentials of this thread's 4 chunk-tasks are evaluated BEFORE waiting for the A slot: the MUFU work of
+      // block kb overlaps the tensor core still reading block kb - na; only the pack + store needs the slot
+      float e[4][8];
 #pragma unroll
-      for (int i = 0; i < kTcTasks; ++i) {
-        const uint32_t c = (uint32_t)(cpar + (kTcGenWarps / 4) * i);
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t c = (uint32_t)(cpar + 2 * i);
         const float4 k0 = ptx::ld_shared_v4f(ks + c * 32);
         const float4 k1 = ptx::ld_shared_v4f(ks + c * 32 + 16);
         const float kvv[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-        float e[8];
         if (FWD) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) e[j] = ptx::ex2(fmaf(rv, kvv[j], -rsh));
+          for (int j = 0; j < 8; ++j) e[i][j] = (a.dbg & 1) ? fmaf(rv, kvv[j], -rsh) : ptx::ex2(fmaf(rv, kvv[j], -rsh));
         } else {
           const float4 s0 = ptx::ld_shared_v4f(ks + 256 + c * 32);
           const float4 s1 = ptx::ld_shared_v4f(ks + 256 + c * 32 + 16);
           const float shv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) e[j] = ptx::ex2(fmaf(rv, kvv[j], -shv[j]));
+          for (int j = 0; j < 8; ++j) e[i][j] = (a.dbg & 1) ? fmaf(rv, kvv[j], -shv[j]) : ptx::ex2(fmaf(rv, kvv[j], -shv[j]));
         }
-        const uint32_t off = (c ^ sw) << 4;
+      }
+      ptx::mbar_wait(empty_a(t, st), pa ^ 1u);                           // A slot free
+      const uint32_t sA = a_row + (uint32_t)st * a_stage;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t off = ((uint32_t)(cpar + 2 * i) ^ sw) << 4;
         if (FWD) {
           uint4 hi, lo;
-          hi.x = pack_bf16x2(e[0], e[1]); hi.y = pack_bf16x2(e[2], e[3]);
-          hi.z = pack_bf16x2(e[4], e[5]); hi.w = pack_bf16x2(e[6], e[7]);
-          lo.x = pack_bf16x2(e[0] - __uint_as_float(hi.x << 16), e[1] - __uint_as_float(hi.x & 0xffff0000u));
-          lo.y = pack_bf16x2(e[2] - __uint_as_float(hi.y << 16), e[3] - __uint_as_float(hi.y & 0xffff0000u));
-          lo.z = pack_bf16x2(e[4] - __uint_as_float(hi.z << 16), e[5] - __uint_as_float(hi.z & 0xffff0000u));
-          lo.w = pack_bf16x2(e[6] - __uint_as_float(hi.w << 16), e[7] - __uint_as_float(hi.w & 0xffff0000u));
+          hi.x = pack_bf16x2(e[i][0], e[i][1]); hi.y = pack_bf16x2(e[i][2], e[i][3]);
+          hi.z = pack_bf16x2(e[i][4], e[i][5]); hi.w = pack_bf16x2(e[i][6], e[i][7]);
+          lo.x = pack_bf16x2(e[i][0] - __uint_as_float(hi.x << 16), e[i][1] - __uint_as_float(hi.x & 0xffff0000u));
+          lo.y = pack_bf16x2(e[i][2] - __uint_as_float(hi.y << 16), e[i][3] - __uint_as_float(hi.y & 0xffff0000u));
+          lo.z = pack_bf16x2(e[i][4] - __uint_as_float(hi.z << 16), e[i][5] - __uint_as_float(hi.z & 0xffff0000u));
+          lo.w = pack_bf16x2(e[i][6] - __uint_as_float(hi.w << 16), e[i][7] - __uint_as_float(hi.w & 0xffff0000u));
           ptx::st_shared_v4(sA + off, hi);
           ptx::st_shared_v4(sA + a_tile + off, lo);
         } else {
           uint4 h;
-          h.x = pack_f16x2(e[0], e[1]); h.y = pack_f16x2(e[2], e[3]);
-          h.z = pack_f16x2(e[4], e[5]); h.w = pack_f16x2(e[6], e[7]);
+          h.x = pack_f16x2(e[i][0], e[i][1]); h.y = pack_f16x2(e[i][2], e[i][3]);
+          h.z = pack_f16x2(e[i][4], e[i][5]); h.w = pack_f16x2(e[i][6], e[i][7]);
           ptx::st_shared_v4(sA + off, h);
         }
       }
-      ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
-      ptx::mbar_arrive(full_a(st));
+      if (!(a.dbg & 8)) ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(full_a(t, st));    // one arrival per warp (256 same-address arrivals would serialise)
+      if (++st == na) { st = 0; pa ^= 1u; }
+      if (++sb == nb) { sb = 0; pb ^= 1u; }
     }
     // ===================== epilogue: TMEM -> registers -> global =====================
     if (nkb > 0) {
       ptx::mbar_wait(acc_full, 0);
       ptx::tc_fence_after();
     }
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int wg = warp >> 2;          // warps sharing a lane quarter take 16-column chunks round-robin
-    const int64_t orow = row0 + q * 32 + lane;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int wg = (warp >> 2) & 1;         // the two warps sharing (sub-tile, quarter) alternate 16-column chunks
+    const int64_t orow = row0 + t * kTcBM + q * 32 + lane;
     float* obase = a.out + ((int64_t)blockIdx.y * a.rows + orow) * a.J;
-    for (int col = wg * 16; col < a.J; col += (kTcGenWarps / 4) * 16) {
+    for (int col = wg * 16; col < a.J; col += 32) {
       uint32_t v[16];
       if (nkb > 0) {
-        ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
+        ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * a.J + col), v);
         ptx::tmem_ld_wait();
       } else {
 #pragma unroll
@@ -312,19 +334,24 @@ k_expgemm_tc(const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ 
       }
     }
   } else if (warp == kTcGenWarps) {
-    // ===================== TMA producer for the B operand =====================
+    // ===================== TMA producer for the B operand + K-side scalars =====================
     if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb % nb;
-        const uint32_t ph = (uint32_t)(kb / nb) & 1u;
         ptx::mbar_wait(empty_b(st), ph ^ 1u);
         const uint32_t sB = b_u32 + (uint32_t)st * b_stage;
         const int kx = (int)(kbeg + (int64_t)kb * kTcBK);
-        ptx::mbar_expect_tx(full_b(st), ks_off + (FWD ? 256u : 512u));
-        ptx::tma_load_2d(sB, &tm_b0, kx, 0, full_b(st));
-        if (FWD) ptx::tma_load_2d(sB + b_tile, &tm_b1, kx, 0, full_b(st));
+        if (a.dbg & 2) {
+          ptx::mbar_expect_tx(full_b(st), FWD ? 256u : 512u);
+        } else {
+          ptx::mbar_expect_tx(full_b(st), ks_off + (FWD ? 256u : 512u));
+          ptx::tma_load_2d(sB, &tm_b0, kx, 0, full_b(st));
+          if (FWD) ptx::tma_load_2d(sB + b_tile, &tm_b1, kx, 0, full_b(st));
+        }
         ptx::bulk_load_1d(sB + ks_off, a.kv + kx, 256u, full_b(st));
         if (!FWD) ptx::bulk_load_1d(sB + ks_off + 256u, a.shift + kx, 256u, full_b(st));
+        if (++st == nb) { st = 0; ph ^= 1u; }
       }
     }
   } else {
@@ -332,26 +359,33 @@ k_expgemm_tc(const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ 
     if (lane == 0) {
       // FWD: A bf16 (hi, lo), B bf16 (hi, lo).  BWD: A fp16, B fp16 (mixed f16/bf16 operands trap as illegal).
       const uint32_t idesc = FWD ? umma_idesc(a.J, 1u, 1u) : umma_idesc(a.J, 0u, 0u);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int sa = kb % na, sb = kb % nb;
-        ptx::mbar_wait(full_a(sa), (uint32_t)(kb / na) & 1u);
-        ptx::mbar_wait(full_b(sb), (uint32_t)(kb / nb) & 1u);
-        ptx::tc_fence_after();
-        const uint32_t sA = a_u32 + (uint32_t)sa * a_stage;
+        ptx::mbar_wait(full_b(sb), pb);
         const uint32_t sB = b_u32 + (uint32_t)sb * b_stage;
-        const uint64_t dA = umma_desc_k128(sA), dAlo = umma_desc_k128(sA + a_tile);
         const uint64_t dB = umma_desc_k128(sB), dBlo = umma_desc_k128(sB + b_tile);
 #pragma unroll
-        for (int k = 0; k < kTcBK / 16; ++k) {
-          const uint64_t adv = (uint64_t)(k * 32 >> 4);   // +32 bytes along K inside the swizzle atom
-          ptx::umma_f16(tmem_base, dA + adv, dB + adv, idesc, (kb | k) != 0 ? 1u : 0u);
-          if (FWD) {
-            ptx::umma_f16(tmem_base, dA + adv, dBlo + adv, idesc, 1u);   // E_hi * M_lo
-            ptx::umma_f16(tmem_base, dAlo + adv, dB + adv, idesc, 1u);   // E_lo * M_hi
+        for (int t = 0; t < 2; ++t) {
+          ptx::mbar_wait(full_a(t, sa), pa);
+          ptx::tc_fence_after();
+          const uint32_t sA = a_u32 + (uint32_t)(t * na + sa) * a_stage;
+          const uint64_t dA = umma_desc_k128(sA), dAlo = umma_desc_k128(sA + a_tile);
+          const uint32_t acc = tmem_base + (uint32_t)(t * a.J);
+#pragma unroll
+          for (int k = 0; k < ((a.dbg & 4) ? 1 : kTcBK / 16); ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);   // +32 bytes along K inside the swizzle atom
+            ptx::umma_f16(acc, dA + adv, dB + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (FWD) {
+              ptx::umma_f16(acc, dA + adv, dBlo + adv, idesc, 1u);   // E_hi * M_lo
+              ptx::umma_f16(acc, dAlo + adv, dB + adv, idesc, 1u);   // E_lo * M_hi
+            }
           }
+          ptx::umma_commit(empty_a(t, sa));   // A slot of this group is free once these MMAs have read it
         }
-        ptx::umma_commit(empty_a(sa));   // both rings are released once these MMAs have read them
-        ptx::umma_commit(empty_b(sb));
+        ptx::umma_commit(empty_b(sb));        // B stage is free once both sub-tiles have consumed it
+        if (++sa == na) { sa = 0; pa ^= 1u; }
+        if (++sb == nb) { sb = 0; pb ^= 1u; }
       }
       if (nkb > 0) ptx::umma_commit(acc_full);
     }
@@ -360,7 +394,7 @@ k_expgemm_tc(const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ 
   __syncthreads();
   if (warp == kTcGenWarps + 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTcTmemCols);
+    ptx::tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
   }
 }
 
@@ -385,8 +419,9 @@ inline void tc_make_map(CUtensorMap* tm, void* gptr, uint64_t inner, uint64_t ou
   cuuint64_t strides[1] = {inner * 2};   // bytes, row pitch
   cuuint32_t box[2] = {kTcBK, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, gptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, gptr, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
 }
 
@@ -404,13 +439,14 @@ inline int tc_pick_split(int64_t tiles, int64_t kchunks, int num_sms, int max_sp
   return best;
 }
 
+// ring depths: `na` A stages per generator group (two groups), `nb` B stages, inside ~220 KB
 inline void tc_pick_rings(size_t a_stage, size_t b_stage, int& na, int& nb) {
   const size_t budget = 220 * 1024;
-  na = 3;
-  nb = (int)std::min<size_t>(6, (budget - na * a_stage) / b_stage);
+  na = 2;
+  nb = (2 * na * a_stage < budget) ? (int)std::min<size_t>(6, (budget - 2 * na * a_stage) / b_stage) : 0;
   if (nb < 3) {
-    na = 2;
-    nb = (int)std::min<size_t>(6, (budget - na * a_stage) / b_stage);
+    na = 1;
+    nb = (int)std::min<size_t>(6, (budget - 2 * na * a_stage) / b_stage);
   }
   if (nb < 2) throw std::runtime_error("tensor path: tile does not fit in shared memory");
 }
@@ -427,9 +463,11 @@ inline void tc_plan_create(TcPlan& p, int dev, int64_t N, int64_t Nld, int G, in
   const size_t fa = 2 * kTcBM * 128, fb = 2 * (size_t)J * 128 + 1024, ba = kTcBM * 128, bb = (size_t)J * 128 + 1024;
   tc_pick_rings(fa, fb, p.fwd_na, p.fwd_nb);
   tc_pick_rings(ba, bb, p.bwd_na, p.bwd_nb);
-  p.fwd_smem = p.fwd_na * fa + p.fwd_nb * fb + 1024 + 512;
-  p.bwd_smem = p.bwd_na * ba + p.bwd_nb * bb + 1024 + 512;
-  int64_t ftiles = (N + kTcBM - 1) / kTcBM, btiles = (G + kTcBM - 1) / kTcBM;
+  p.fwd_smem = 2 * p.fwd_na * fa + p.fwd_nb * fb + 1024 + 512;
+  p.bwd_smem = 2 * p.bwd_na * ba + p.bwd_nb * bb + 1024 + 512;
+  p.tmem_cols = (2 * J > 256) ? 512 : 256;
+  const int64_t rows_per_cta = 2 * kTcBM;
+  int64_t ftiles = (N + rows_per_cta - 1) / rows_per_cta, btiles = (G + rows_per_cta - 1) / rows_per_cta;
   p.fsplit = tc_pick_split(ftiles, Gld / kTcBK, p.num_sms, 4);
   p.nsplit = tc_pick_split(btiles, Nld / kTcBK, p.num_sms, 16);
   p.genes_per_fsplit = ((Gld / kTcBK + p.fsplit - 1) / p.fsplit) * kTcBK;
@@ -437,6 +475,8 @@ inline void tc_plan_create(TcPlan& p, int dev, int64_t N, int64_t Nld, int G, in
   if (cudaFuncSetAttribute(k_expgemm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.fwd_smem) != cudaSuccess ||
       cudaFuncSetAttribute(k_expgemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.bwd_smem) != cudaSuccess)
     throw std::runtime_error("tensor path: cannot raise the dynamic shared memory limit");
+  const char* dbg = getenv("CLONEALIGN_B200_TC_DBG");
+  p.dbg = dbg ? atoi(dbg) : 0;
   p.ok = true;
 }
 inline void tc_plan_destroy(TcPlan& p) { p.ok = false; }
@@ -445,16 +485,16 @@ inline void tc_plan_destroy(TcPlan& p) { p.ok = false; }
 inline void tc_launch_fwd(const TcPlan& p, const float* psi, const float* w, const float* shift, float* Zx, cudaStream_t st) {
   TcArgs a;
   a.rowv = psi; a.kv = w; a.shift = shift; a.out = Zx; a.rows = p.N; a.kdim = p.G; a.k_per_split = p.genes_per_fsplit;
-  a.J = p.J; a.SCp = p.SCp; a.na = p.fwd_na; a.nb = p.fwd_nb;
-  dim3 grid((unsigned)((p.N + kTcBM - 1) / kTcBM), p.fsplit);
+  a.J = p.J; a.SCp = p.SCp; a.na = p.fwd_na; a.nb = p.fwd_nb; a.tmem_cols = p.tmem_cols; a.dbg = p.dbg;
+  dim3 grid((unsigned)((p.N + 2 * kTcBM - 1) / (2 * kTcBM)), p.fsplit);
   k_expgemm_tc<true><<<grid, kTcThreads, p.fwd_smem, st>>>(p.tm_mhi, p.tm_mlo, a);
 }
 // BWD: out dMx [nsplit][G][J]; shift_bwd is written by the per-cell epilogue together with the scaled fp16 R^T
 inline void tc_launch_bwd(const TcPlan& p, const float* psi, const float* w, const float* shift, float* dMx, cudaStream_t st) {
   TcArgs a;
   a.rowv = w; a.kv = psi; a.shift = shift; a.out = dMx; a.rows = p.G; a.kdim = p.N; a.k_per_split = p.cells_per_split;
-  a.J = p.J; a.SCp = p.SCp; a.na = p.bwd_na; a.nb = p.bwd_nb;
-  dim3 grid((unsigned)((p.G + kTcBM - 1) / kTcBM), p.nsplit);
+  a.J = p.J; a.SCp = p.SCp; a.na = p.bwd_na; a.nb = p.bwd_nb; a.tmem_cols = p.tmem_cols; a.dbg = p.dbg;
+  dim3 grid((unsigned)((p.G + 2 * kTcBM - 1) / (2 * kTcBM)), p.nsplit);
   k_expgemm_tc<false><<<grid, kTcThreads, p.bwd_smem, st>>>(p.tm_rx, p.tm_rx, a);
 }
 

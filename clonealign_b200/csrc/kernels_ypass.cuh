@@ -18,7 +18,7 @@
 namespace ca {
 
 constexpr int kYCB = 2048;   // columns per CTA tile
-constexpr int kYRI = 8;      // rows in flight per thread
+constexpr int kYRI = 8;      // rows reduced together by one butterfly
 
 template <typename T> struct YLoad;
 template <> struct YLoad<float> {
@@ -74,14 +74,15 @@ __device__ __forceinline__ float butterfly8(float (&v)[8], int lane) {
 }
 
 // KP == 1 (the reference's default model: K = 1 latent dimension, no covariates)
-template <typename T>
-__global__ void __launch_bounds__(256, 2)
-k_ypass_k1(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, const float* __restrict__ U,
-           const float* __restrict__ Vm, float* __restrict__ rowpart, float* __restrict__ colpart) {
-  __shared__ float red[2][8][kYRI];
+// LIGHT = true halves the rows in flight per thread (4 instead of 8) so that the kernel needs <= 80 registers:
+// two of its CTAs then fit on an SM NEXT TO one tcgen05 contraction CTA (27.6k registers, 211 KB smem), which is
+// what lets the Y stream (HBM-bound) overlap the forward contraction (tensor-bound) on a second stream.
+template <typename T, bool LIGHT>
+__device__ __forceinline__ void ypass_tile(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB,
+                                           const float* __restrict__ U, const float* __restrict__ Vm,
+                                           float* __restrict__ rowpart, float* __restrict__ colpart, int cb, int64_t rb,
+                                           float (*red)[8][kYRI]) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int cb = blockIdx.x;
-  const int64_t rb = blockIdx.y;
   const int64_t col0 = (int64_t)cb * kYCB + tid * 8;
   const bool colok = col0 < ldY;
   float vr[8], cacc[8];
@@ -93,30 +94,34 @@ k_ypass_k1(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, const
   const int64_t rbeg = rb * RB, rend = (rbeg + RB < N) ? rbeg + RB : N;
   const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   int buf = 0;
+  constexpr int kInFlight = LIGHT ? 4 : 8;
   for (int64_t r0 = rbeg; r0 < rend; r0 += kYRI) {
-    float y[kYRI][8];
-    float u[kYRI];
-#pragma unroll
-    for (int i = 0; i < kYRI; ++i) {
-      const bool ok = colok && (r0 + i < rend);
-      if (ok) {
-        YLoad<T>::ld8(Y + (r0 + i) * ldY + col0, y[i]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[i][j] = 0.f;
-      }
-      u[i] = (r0 + i < rend) ? __ldg(U + r0 + i) : 0.f;
-    }
     float rp[kYRI];
 #pragma unroll
-    for (int i = 0; i < kYRI; ++i) {
-      float a = 0.f;
+    for (int h = 0; h < kYRI / kInFlight; ++h) {
+      float y[kInFlight][8];
+      float u[kInFlight];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a = fmaf(y[i][j], vr[j], a);
-        cacc[j] = fmaf(y[i][j], u[i], cacc[j]);
+      for (int i = 0; i < kInFlight; ++i) {
+        const int64_t r = r0 + h * kInFlight + i;
+        if (colok && r < rend) {
+          YLoad<T>::ld8(Y + r * ldY + col0, y[i]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[i][j] = 0.f;
+        }
+        u[i] = (r < rend) ? __ldg(U + r) : 0.f;
       }
-      rp[i] = a;
+#pragma unroll
+      for (int i = 0; i < kInFlight; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a = fmaf(y[i][j], vr[j], a);
+          cacc[j] = fmaf(y[i][j], u[i], cacc[j]);
+        }
+        rp[h * kInFlight + i] = a;
+      }
     }
     float tot = butterfly8(rp, lane);
     if ((lane & 3) == 0) red[buf][wid][ridx] = tot;
@@ -132,6 +137,29 @@ k_ypass_k1(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, const
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     if (col0 + j < G) colpart[rb * G + col0 + j] = cacc[j];
+  __syncthreads();   // `red` is reused by the next tile of a persistent CTA
+}
+
+// one CTA per tile (used when the Y pass runs alone on the GPU)
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+k_ypass_k1(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, const float* __restrict__ U,
+           const float* __restrict__ Vm, float* __restrict__ rowpart, float* __restrict__ colpart) {
+  __shared__ float red[2][8][kYRI];
+  ypass_tile<T, false>(Y, ldY, N, G, RB, U, Vm, rowpart, colpart, blockIdx.x, blockIdx.y, red);
+}
+
+// persistent, register-light variant for overlap with the contraction kernels: exactly two CTAs per SM
+// (grid = 2 x #SM), 72 registers per thread, tiles taken round-robin in a fixed assignment (deterministic)
+template <typename T>
+__global__ void __maxnreg__(72)
+k_ypass_k1_persistent(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, int nCB, int nRB,
+                      const float* __restrict__ U, const float* __restrict__ Vm, float* __restrict__ rowpart,
+                      float* __restrict__ colpart) {
+  __shared__ float red[2][8][kYRI];
+  const int64_t ntiles = (int64_t)nCB * nRB;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+    ypass_tile<T, true>(Y, ldY, N, G, RB, U, Vm, rowpart, colpart, (int)(t % nCB), t / nCB, red);
 }
 
 // generic K + P (slow path, reads Y twice): rows then columns
