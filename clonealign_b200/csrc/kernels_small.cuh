@@ -311,16 +311,23 @@ __global__ void __launch_bounds__(kEpiWarps * 32) k_cell_epilogue(EpiArgs a) {
     float* zrow = a.Zx + n * a.J;
     if (a.fsplit > 1) {   // tensor path: sum the K-split partials in a fixed order, keep the sum in split 0
       const int jn = (MODE == EPI_TRAIN) ? a.J : a.SCp;
+      const int64_t fstride = a.N * (int64_t)a.J;
       for (int j = lane; j < jn; j += 32) {
-        float z = zrow[j];
-        for (int f = 1; f < a.fsplit; ++f) z += a.Zx[((int64_t)f * a.N + n) * a.J + j];
+        const float* pz = zrow + j;
+        float z = *pz;
+        for (int f = 1; f < a.fsplit; ++f) {
+          pz += fstride;
+          z += *pz;
+        }
         zrow[j] = z;
       }
       __syncwarp();
     }
     const double m = (double)a.shift[n];
     const double sn = (double)a.s[n];
-    for (int j = lane; j < SC; j += 32) lz[j] = log((double)zrow[j]) + m;
+    // single-precision log (<= 1 ulp: ~7e-7 absolute on log Z ~ 10), promoted: with s_n ~ 1e4 that is ~1e-3 nats per
+    // (s, c), an order of magnitude below what the tensor core's fp32 accumulation already leaves in Z
+    for (int j = lane; j < SC; j += 32) lz[j] = (double)logf(zrow[j]) + m;
     __syncwarp();
     for (int c = lane; c < a.C; c += 32) {
       double acc = 0.0;
@@ -385,16 +392,29 @@ __global__ void __launch_bounds__(kEpiWarps * 32) k_cell_epilogue(EpiArgs a) {
         double gu[kMaxKP];
 #pragma unroll
         for (int kp = 0; kp < kMaxKP; ++kp) gu[kp] = 0.0;
-        const float inv_S = 1.0f / (float)a.S;
+        const float sn_over_S = (float)(sn / (double)a.S);
+        float* gamf = reinterpret_cast<float*>(Fc);   // F is dead from here on: reuse as float gamma[C]
+        float* rbuf = reinterpret_cast<float*>(lz);   // log Z is dead: reuse as float R[SCp]
+        __syncwarp();
+        for (int c = lane; c < a.C; c += 32) gamf[c] = (float)gam[c];
+        __syncwarp();
+        const int c_first = lane % a.C, c_step = 32 % a.C;   // column j = lane + 32 i  ->  clone (c_first + i c_step) mod C
         // tensor path: the fp16 B operand of BWD is scaled per cell by a power of two that is folded back into
         // the generated A operand through the per-cell shift (E 2^a_n)(R 2^-a_n) = E R, so |R^| stays in fp16 range
         float bscale = 1.f;
-        if (a.RxT) {
-          float rmax = 0.f;
+        float rmax = 0.f;
+        {
+          int c = c_first;
           for (int j = lane; j < SC; j += 32) {
-            const int c = j % a.C;
-            rmax = fmaxf(rmax, (float)(gam[c] * sn) * inv_S / zrow[j]);
+            const float r = __fdividef(gamf[c] * sn_over_S, zrow[j]);
+            rbuf[j] = r;
+            rmax = fmaxf(rmax, r);
+            c += c_step;
+            if (c >= a.C) c -= a.C;
           }
+        }
+        __syncwarp();
+        if (a.RxT) {
           rmax = warp_max(rmax);
           float umax = 1.f;
           for (int kp = 0; kp < a.KP; ++kp) umax = fmaxf(umax, fabsf(a.U[n * a.KP + kp]));
@@ -406,11 +426,7 @@ __global__ void __launch_bounds__(kEpiWarps * 32) k_cell_epilogue(EpiArgs a) {
           if (lane == 0) a.shift_bwd[n] = (float)(m * 1.4426950408889634) - (float)an;
         }
         for (int j = lane; j < a.SCp; j += 32) {
-          float r = 0.f;
-          if (j < SC) {
-            const int c = j % a.C;
-            r = (float)(gam[c] * sn) * inv_S / zrow[j];
-          }
+          const float r = (j < SC) ? rbuf[j] : 0.f;
           if (a.Rx) a.Rx[n * a.J + j] = r;
           if (a.RxT) tile[(size_t)j * kEpiWarps + wid] = __float2half_rn(r * bscale);
           for (int kp = 0; kp < a.KP; ++kp) {

@@ -18,32 +18,51 @@
 namespace ca {
 
 constexpr int kYCB = 2048;   // columns per CTA tile
-constexpr int kYRI = 8;      // rows reduced together by one butterfly
 
+// Per storage type: Raw = the 8 consecutive counts a thread owns in one row, exactly as loaded (kept packed in
+// registers until use), kRows = rows in flight per thread so that every type keeps 128-256 bytes per thread in flight.
+// Narrow integer counts are widened without the (slow, XU-pipe) I2F conversion: a byte permute drops the value
+// into the mantissa of 2^23 (0x4B000000) and one FADD removes the 2^23: exact for values < 2^23.
+__device__ __forceinline__ float magic_to_float(uint32_t x, uint32_t sel) {
+  return __uint_as_float(__byte_perm(x, 0x4B000000u, sel)) - 8388608.0f;
+}
 template <typename T> struct YLoad;
 template <> struct YLoad<float> {
-  static __device__ __forceinline__ void ld8(const float* p, float (&o)[8]) {
-    float4 a = __ldcs(reinterpret_cast<const float4*>(p));
-    float4 b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
-    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  struct Raw { float4 a, b; };
+  static constexpr int kRows = 8;
+  static __device__ __forceinline__ Raw ld(const float* p) {
+    Raw r;
+    r.a = __ldcs(reinterpret_cast<const float4*>(p));
+    r.b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
+    return r;
+  }
+  static __device__ __forceinline__ Raw zero() { Raw r; r.a = make_float4(0.f, 0.f, 0.f, 0.f); r.b = r.a; return r; }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&o)[8]) {
+    o[0] = r.a.x; o[1] = r.a.y; o[2] = r.a.z; o[3] = r.a.w; o[4] = r.b.x; o[5] = r.b.y; o[6] = r.b.z; o[7] = r.b.w;
   }
 };
 template <> struct YLoad<uint16_t> {
-  static __device__ __forceinline__ void ld8(const uint16_t* p, float (&o)[8]) {
-    uint4 a = __ldcs(reinterpret_cast<const uint4*>(p));
-    o[0] = (float)(a.x & 0xffffu); o[1] = (float)(a.x >> 16);
-    o[2] = (float)(a.y & 0xffffu); o[3] = (float)(a.y >> 16);
-    o[4] = (float)(a.z & 0xffffu); o[5] = (float)(a.z >> 16);
-    o[6] = (float)(a.w & 0xffffu); o[7] = (float)(a.w >> 16);
+  typedef uint4 Raw;
+  static constexpr int kRows = 16;
+  static __device__ __forceinline__ Raw ld(const uint16_t* p) { return __ldcs(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  static __device__ __forceinline__ void unpack(const Raw& a, float (&o)[8]) {
+    o[0] = magic_to_float(a.x, 0x7510u); o[1] = magic_to_float(a.x, 0x7532u);
+    o[2] = magic_to_float(a.y, 0x7510u); o[3] = magic_to_float(a.y, 0x7532u);
+    o[4] = magic_to_float(a.z, 0x7510u); o[5] = magic_to_float(a.z, 0x7532u);
+    o[6] = magic_to_float(a.w, 0x7510u); o[7] = magic_to_float(a.w, 0x7532u);
   }
 };
 template <> struct YLoad<uint8_t> {
-  static __device__ __forceinline__ void ld8(const uint8_t* p, float (&o)[8]) {
-    uint2 a = __ldcs(reinterpret_cast<const uint2*>(p));
-    o[0] = (float)(a.x & 0xffu); o[1] = (float)((a.x >> 8) & 0xffu);
-    o[2] = (float)((a.x >> 16) & 0xffu); o[3] = (float)(a.x >> 24);
-    o[4] = (float)(a.y & 0xffu); o[5] = (float)((a.y >> 8) & 0xffu);
-    o[6] = (float)((a.y >> 16) & 0xffu); o[7] = (float)(a.y >> 24);
+  typedef uint2 Raw;
+  static constexpr int kRows = 16;
+  static __device__ __forceinline__ Raw ld(const uint8_t* p) { return __ldcs(reinterpret_cast<const uint2*>(p)); }
+  static __device__ __forceinline__ Raw zero() { return make_uint2(0u, 0u); }
+  static __device__ __forceinline__ void unpack(const Raw& a, float (&o)[8]) {
+    o[0] = magic_to_float(a.x, 0x7540u); o[1] = magic_to_float(a.x, 0x7541u);
+    o[2] = magic_to_float(a.x, 0x7542u); o[3] = magic_to_float(a.x, 0x7543u);
+    o[4] = magic_to_float(a.y, 0x7540u); o[5] = magic_to_float(a.y, 0x7541u);
+    o[6] = magic_to_float(a.y, 0x7542u); o[7] = magic_to_float(a.y, 0x7543u);
   }
 };
 
@@ -74,14 +93,17 @@ __device__ __forceinline__ float butterfly8(float (&v)[8], int lane) {
 }
 
 // KP == 1 (the reference's default model: K = 1 latent dimension, no covariates)
-// LIGHT = true halves the rows in flight per thread (4 instead of 8) so that the kernel needs <= 80 registers:
-// two of its CTAs then fit on an SM NEXT TO one tcgen05 contraction CTA (27.6k registers, 211 KB smem), which is
-// what lets the Y stream (HBM-bound) overlap the forward contraction (tensor-bound) on a second stream.
+// LIGHT = true halves the rows in flight per thread so that the kernel fits in 72 registers: two of its CTAs then
+// fit on an SM NEXT TO one tcgen05 contraction CTA (27.6k registers, 211 KB smem) when the Y stream is overlapped
+// with the forward contraction on a second stream.
+constexpr int kYMaxRows = 16;
 template <typename T, bool LIGHT>
 __device__ __forceinline__ void ypass_tile(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB,
                                            const float* __restrict__ U, const float* __restrict__ Vm,
                                            float* __restrict__ rowpart, float* __restrict__ colpart, int cb, int64_t rb,
-                                           float (*red)[8][kYRI]) {
+                                           float (*red)[8][kYMaxRows]) {
+  using L = YLoad<T>;
+  constexpr int kRows = LIGHT ? L::kRows / 2 : L::kRows;   // rows per iteration (multiple of 4)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t col0 = (int64_t)cb * kYCB + tid * 8;
   const bool colok = col0 < ldY;
@@ -94,43 +116,45 @@ __device__ __forceinline__ void ypass_tile(const T* __restrict__ Y, int64_t ldY,
   const int64_t rbeg = rb * RB, rend = (rbeg + RB < N) ? rbeg + RB : N;
   const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   int buf = 0;
-  constexpr int kInFlight = LIGHT ? 4 : 8;
-  for (int64_t r0 = rbeg; r0 < rend; r0 += kYRI) {
-    float rp[kYRI];
+  for (int64_t r0 = rbeg; r0 < rend; r0 += kRows) {
+    typename L::Raw raw[kRows];
 #pragma unroll
-    for (int h = 0; h < kYRI / kInFlight; ++h) {
-      float y[kInFlight][8];
-      float u[kInFlight];
+    for (int i = 0; i < kRows; ++i) raw[i] = (colok && r0 + i < rend) ? L::ld(Y + (r0 + i) * ldY + col0) : L::zero();
+    float u[kRows];   // U is allocated with 64 elements of slack, r0 is a multiple of 4: vector loads stay in bounds
 #pragma unroll
-      for (int i = 0; i < kInFlight; ++i) {
-        const int64_t r = r0 + h * kInFlight + i;
-        if (colok && r < rend) {
-          YLoad<T>::ld8(Y + r * ldY + col0, y[i]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) y[i][j] = 0.f;
-        }
-        u[i] = (r < rend) ? __ldg(U + r) : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < kInFlight; ++i) {
-        float a = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          a = fmaf(y[i][j], vr[j], a);
-          cacc[j] = fmaf(y[i][j], u[i], cacc[j]);
-        }
-        rp[h * kInFlight + i] = a;
-      }
+    for (int i = 0; i < kRows; i += 4) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(U + r0 + i));
+      u[i] = t4.x; u[i + 1] = t4.y; u[i + 2] = t4.z; u[i + 3] = t4.w;
     }
-    float tot = butterfly8(rp, lane);
-    if ((lane & 3) == 0) red[buf][wid][ridx] = tot;
-    __syncthreads();
-    if (tid < kYRI && r0 + tid < rend) {
-      float a = 0.f;
+    float rp[(kRows + 7) / 8 * 8];
 #pragma unroll
-      for (int w = 0; w < 8; ++w) a += red[buf][w][tid];
-      rowpart[(int64_t)cb * N + r0 + tid] = a;
+    for (int i = 0; i < (kRows + 7) / 8 * 8; ++i) rp[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+      float y[8];
+      L::unpack(raw[i], y);
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc = fmaf(y[j], vr[j], acc);
+        cacc[j] = fmaf(y[j], u[i], cacc[j]);
+      }
+      rp[i] = acc;
+    }
+#pragma unroll
+    for (int h = 0; h < (kRows + 7) / 8; ++h) {
+      float v8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v8[i] = rp[h * 8 + i];
+      float tot = butterfly8(v8, lane);
+      if ((lane & 3) == 0) red[buf][wid][h * 8 + ridx] = tot;
+    }
+    __syncthreads();
+    if (tid < kRows && r0 + tid < rend) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) acc += red[buf][w][tid];
+      rowpart[(int64_t)cb * N + r0 + tid] = acc;
     }
     buf ^= 1;
   }
@@ -145,7 +169,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 2)
 k_ypass_k1(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, const float* __restrict__ U,
            const float* __restrict__ Vm, float* __restrict__ rowpart, float* __restrict__ colpart) {
-  __shared__ float red[2][8][kYRI];
+  __shared__ float red[2][8][kYMaxRows];
   ypass_tile<T, false>(Y, ldY, N, G, RB, U, Vm, rowpart, colpart, blockIdx.x, blockIdx.y, red);
 }
 
@@ -156,7 +180,7 @@ __global__ void __maxnreg__(72)
 k_ypass_k1_persistent(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, int nCB, int nRB,
                       const float* __restrict__ U, const float* __restrict__ Vm, float* __restrict__ rowpart,
                       float* __restrict__ colpart) {
-  __shared__ float red[2][8][kYRI];
+  __shared__ float red[2][8][kYMaxRows];
   const int64_t ntiles = (int64_t)nCB * nRB;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
     ypass_tile<T, true>(Y, ldY, N, G, RB, U, Vm, rowpart, colpart, (int)(t % nCB), t / nCB, red);
