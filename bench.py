@@ -219,9 +219,11 @@ def run_ours(args, cfg):
     torch.cuda.synchronize()
     with ClockSampler(dev) as cs:
         ms = sess.time_steps(args.steps)
-        # keep the sampler alive for very short timed regions
-        if ms < 400:
-            sess.time_steps(max(1, int(args.steps * 400 / max(ms, 1e-3))))
+        # keep the sampler alive for very short timed regions.  Every step contains a collective, so the number of
+        # extra (untimed) steps MUST be identical on all ranks: derive it from the max over ranks, not the local time.
+        ms_all = D.max_over_ranks(ms)
+        if ms_all < 400:
+            sess.time_steps(max(1, int(args.steps * 400 / max(ms_all, 1e-3))))
     clocks = cs.summary()
     D.barrier()
     torch.cuda.synchronize()
@@ -252,9 +254,16 @@ def run_ours(args, cfg):
     if top:
         k = kern[top]
         peak = pk["hbm"] if k["bound"] == "hbm" else pk["bf16"]
-        ach = k["alg"] / (k["t"] / 1e3) * (1.0 if k["bound"] == "hbm" else 1.0)
+        ach = k["alg"] / (k["t"] / 1e3)
+        traffic = None                      # DRAM bytes per launch from the committed `ncu --set full` capture (same config only)
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if world == 1 and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.config, {}).get(top)
         roofline = dict(kernel=top, bound=k["bound"], achieved=ach, peak=peak, unit="GB/s" if k["bound"] == "hbm" else "TFLOP/s",
-                        frac=ach / peak, traffic=None, peak_source=pk["which"], ms_per_launch=k["t"],
+                        frac=ach / peak, traffic=traffic, peak_source=pk["which"], ms_per_launch=k["t"],
+                        note=("algorithmic flops 2*N*G*J (J = 2*S*C: Z and Z' columns); the forward kernel ISSUES 3x that "
+                              "(bf16 3-term split for fp32-grade log Z / d psi), so its tensor-pipe utilisation is ~3x frac"
+                              if top == "lse_fwd" else None),
                         all_kernels_ms={n: round(t, 4) for n, t in prof.items()},
                         per_kernel={n: dict(bound=v["bound"], achieved=v["alg"] / (v["t"] / 1e3),
                                             frac=v["alg"] / (v["t"] / 1e3) / (pk["hbm"] if v["bound"] == "hbm" else pk["bf16"]))
@@ -311,7 +320,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
-    ap.add_argument("--y-store", default="f32", choices=["auto", "f32", "u16", "u8"])
+    ap.add_argument("--y-store", default="auto", choices=["auto", "f32", "u16", "u8"])
     ap.add_argument("--path", default="auto", choices=["auto", "cudacore", "tensor"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

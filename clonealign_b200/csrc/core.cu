@@ -586,7 +586,9 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-  h->overlap = getenv("CLONEALIGN_B200_NO_OVERLAP") == nullptr;
+  // Measured on B200 (profiles/r01_notes.md): co-scheduling the Y stream with the forward contraction does not pay
+  // yet (the register-light Y kernel is slower than the saved time), so the fork is opt-in.
+  h->overlap = getenv("CLONEALIGN_B200_OVERLAP") != nullptr;
 
   h->N = c.N; h->Ntot = c.N_total > 0 ? c.N_total : c.N; h->G = c.G; h->C = c.C; h->S = c.S; h->K = c.K; h->P = c.P;
   h->KP = c.K + c.P; h->SC = c.S * c.C; h->V = c.V;

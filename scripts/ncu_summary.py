@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Turn an .ncu-rep (ncu --set full) into a compact markdown table: python scripts/ncu_summary.py rep.ncu-rep"""
+import csv
+import io
+import subprocess
+import sys
+
+METRICS = [
+    ("gpu__time_duration.sum", "time"),
+    ("dram__bytes_read.sum", "dram rd"),
+    ("dram__bytes_write.sum", "dram wr"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU %"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps %"),
+    ("launch__registers_per_thread", "regs"),
+    ("launch__grid_size", "grid"),
+    ("sm__cycles_elapsed.max.per_second", "SM clk"),
+]
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    print("| kernel | " + " | ".join(n for _, n in METRICS) + " |")
+    print("|---|" + "---|" * len(METRICS))
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "")[:44]
+        cells = []
+        for m, _ in METRICS:
+            if m in idx:
+                v = r[idx[m]]
+                try:
+                    v = f"{float(v.replace(',', '')):.4g}"
+                except ValueError:
+                    pass
+                cells.append(f"{v} {units[idx[m]]}".strip())
+            else:
+                cells.append("-")
+        print(f"| {name} | " + " | ".join(cells) + " |")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
