@@ -103,15 +103,27 @@ def run_clonealign(gene_expression_data, copy_number_data, initial_shrinks=(0, 5
     """Best-of-restarts wrapper (R/clonealign.R:35-75).  Restarts are independent fits; `devices`
     (list of CUDA ordinals) spreads them round-robin over GPUs (replicas only, no communication)."""
     rng = np.random.default_rng(seed)
-    fits = []
-    i = 0
+    jobs = []
     for is_ in initial_shrinks:
         for _ in range(n_repeats):
-            dev = devices[i % len(devices)] if devices else kwargs.get("device", 0)
+            dev = devices[len(jobs) % len(devices)] if devices else kwargs.get("device", 0)
             kw = dict(kwargs)
-            kw.update(initial_shrink=is_, seed=int(rng.integers(0, 2 ** 31 - 1)), device=dev)
-            fits.append(clonealign(gene_expression_data, copy_number_data, **kw))
-            i += 1
+            kw.update(initial_shrink=is_, seed=int(rng.integers(0, 2 ** 31 - 1)), device=dev)   # seeds fixed up front
+            jobs.append(kw)
+    if devices and len(devices) > 1:
+        # replicas only: one host thread per GPU, each running its share of the restarts one after another
+        # (the C-ABI calls release the GIL); results keep the serial order, so the selection below is unchanged
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run_on(dev):
+            return [(i, clonealign(gene_expression_data, copy_number_data, **kw))
+                    for i, kw in enumerate(jobs) if kw["device"] == dev]
+
+        with ThreadPoolExecutor(max_workers=len(devices)) as pool:
+            done = [r for part in pool.map(run_on, list(dict.fromkeys(devices))) for r in part]
+        fits = [f for _, f in sorted(done, key=lambda t: t[0])]
+    else:
+        fits = [clonealign(gene_expression_data, copy_number_data, **kw) for kw in jobs]
     final_elbos = np.array([f["convergence_info"]["final_elbo"] for f in fits])
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")

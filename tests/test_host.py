@@ -114,6 +114,34 @@ def test_synthetic_generator():
     assert 0.5 < np.corrcoef(rs, a["s"])[0, 1]            # s_n is the library size in the benchmark variant
 
 
+def test_run_clonealign_spreads_restarts_over_devices(monkeypatch):
+    """run_clonealign (R/clonealign.R:35-75): restarts pinned round-robin to `devices`, run from one host thread per
+    GPU, results kept in the serial order and the max-ELBO fit returned.  The fit itself is faked (no GPU here)."""
+    import threading
+    from clonealign_b200 import api
+    seen = []
+    lock = threading.Lock()
+
+    def fake_clonealign(gex, cnv, **kw):
+        import time
+        time.sleep(0.05)          # a real fit takes seconds: keeps the per-device workers alive side by side
+        with lock:
+            seen.append((kw["device"], kw["initial_shrink"], kw["seed"], threading.get_ident()))
+        return api.CloneAlignFit(convergence_info={"final_elbo": -1000.0 + kw["seed"] % 97}, clone=["A", "B"],
+                                 correlations=np.array([0.1, 0.2]), ml_params={}, seed=kw["seed"], device=kw["device"])
+
+    monkeypatch.setattr(api, "clonealign", fake_clonealign)
+    Y, L = np.ones((2, 3)), np.ones((3, 2))
+    a = api.run_clonealign(Y, L, initial_shrinks=(0, 5, 10), n_repeats=2, print_elbos=False, seed=7, devices=[0, 1, 2])
+    b = api.run_clonealign(Y, L, initial_shrinks=(0, 5, 10), n_repeats=2, print_elbos=False, seed=7)
+    assert len(a["multirun_info"]["elbos"]) == 6
+    np.testing.assert_array_equal(a["multirun_info"]["elbos"], b["multirun_info"]["elbos"])   # same seeds, same order
+    assert a["convergence_info"]["final_elbo"] == a["multirun_info"]["elbos"].max()
+    par = seen[:6]
+    assert sorted(d for d, *_ in par) == [0, 0, 1, 1, 2, 2]                                   # round-robin pinning
+    assert len({t for *_, t in par}) >= 2                                                       # more than one host thread
+
+
 def test_shard_bounds_cover_exactly():
     from clonealign_b200.dist import shard_bounds
     for n, w in [(10, 3), (100000, 8), (7, 8), (64, 2)]:
