@@ -324,7 +324,14 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "cudacore", "tensor"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--watchdog", type=int, default=1500,
+                    help="abort the process after this many seconds (a hung collective must not hold the GPU box)")
     args = ap.parse_args()
+    if args.watchdog > 0:
+        # a thread, not signal.alarm: the main thread may be blocked inside a C call (stream sync, NCCL) for ever
+        wd = threading.Timer(args.watchdog, lambda: (sys.stderr.write("bench.py: watchdog expired\n"), os._exit(124)))
+        wd.daemon = True
+        wd.start()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
         run_reference(args, cfg)

@@ -36,7 +36,9 @@ def init_process_group(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        import datetime
+        # short collective timeout: a rank that dies or diverges must take the job down in minutes, not hang the box
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, timeout=datetime.timedelta(seconds=300))
     return rank, local_rank, world
 
 

@@ -142,6 +142,19 @@ def test_run_clonealign_spreads_restarts_over_devices(monkeypatch):
     assert len({t for *_, t in par}) >= 2                                                       # more than one host thread
 
 
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU, oracle port) prints one JSON line with the contract's keys."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c1",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "iterations/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert "workload" in line["config"]
+
+
 def test_shard_bounds_cover_exactly():
     from clonealign_b200.dist import shard_bounds
     for n, w in [(10, 3), (100000, 8), (7, 8), (64, 2)]:
