@@ -40,14 +40,14 @@ def compute_correlations(Y, L, clones, clone_names):
     out = np.full(Y.shape[1], np.nan)
     if Y.shape[0] < 2:
         return out
-    with np.errstate(invalid="ignore", divide="ignore"):
-        Ys = (Y - Y.mean(axis=0)) / Y.std(axis=0, ddof=1)
-        for i in range(Y.shape[1]):
-            xv = np.asarray(L, dtype=np.float64)[i, idx]
-            yv = Ys[:, i]
-            if np.std(xv) == 0 or not np.all(np.isfinite(yv)) or np.std(yv) == 0:
-                continue
-            out[i] = np.corrcoef(xv, yv)[0, 1]
+    # cor(x, scale(y)) == cor(x, y); constant x or y gives NA (R's cor warns and returns NA), all genes at once
+    X = np.asarray(L, dtype=np.float64)[:, idx].T                  # cells x genes: copy number of the assigned clone
+    Yc = Y - Y.mean(axis=0)
+    Xc = X - X.mean(axis=0)
+    sy = np.sqrt((Yc * Yc).sum(axis=0))
+    sx = np.sqrt((Xc * Xc).sum(axis=0))
+    ok = (sy > 0) & (sx > 0)
+    out[ok] = (Xc[:, ok] * Yc[:, ok]).sum(axis=0) / (sx[ok] * sy[ok])
     return out
 
 

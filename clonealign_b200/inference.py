@@ -58,16 +58,29 @@ def _message(verbose, msg):
         print(msg, file=sys.stderr)
 
 
-def pca_init(Y, K, rng):
-    """psi initialisation, R/inference-tflow.R:204-208: prcomp(log2(Y+1), center, scale)$x[,1:K], scale(), + N(0,.05^2)."""
-    X = np.log2(np.asarray(Y, dtype=np.float64) + 1.0)
-    X = X - X.mean(axis=0)
+def pca_init(Y, K, rng, truncated=None):
+    """psi initialisation, R/inference-tflow.R:204-208: prcomp(log2(Y+1), center, scale)$x[,1:K], scale(), + N(0,.05^2).
+
+    The reference runs a full `prcomp` (O(N G^2)); only the K leading components are used, so large inputs go through
+    a truncated Lanczos SVD (same components up to sign, which the model does not see: W starts at 0)."""
+    Y = np.asarray(Y)
+    big = (Y.shape[0] * Y.shape[1] > (1 << 24)) if truncated is None else bool(truncated)
+    X = np.log2(np.asarray(Y, dtype=np.float32 if big else np.float64) + 1.0)
+    X -= X.mean(axis=0)
     sd = X.std(axis=0, ddof=1)
     if np.any(sd == 0):
         raise ValueError("cannot rescale a constant/zero column to unit variance")
-    X = X / sd
-    U, S, _ = np.linalg.svd(X, full_matrices=False)
-    pcs = (U * S)[:, :K]
+    X /= sd
+    if big:
+        # only the K leading principal components are used (:205): Lanczos on the standardised matrix
+        from scipy.sparse.linalg import svds
+        k = max(1, K)
+        U, S, _ = svds(X, k=k, which="LM", random_state=np.random.RandomState(0))
+        order = np.argsort(-S)
+        pcs = (U[:, order] * S[order]).astype(np.float64)[:, :K]
+    else:
+        U, S, _ = np.linalg.svd(X, full_matrices=False)
+        pcs = (U * S)[:, :K]
     pcs = (pcs - pcs.mean(axis=0)) / pcs.std(axis=0, ddof=1)
     return pcs + rng.normal(0.0, 0.05, size=pcs.shape)
 

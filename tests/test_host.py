@@ -94,6 +94,45 @@ def test_pca_init_properties(example_sce):
     assert np.allclose(np.abs(np.corrcoef(p[:, 0], q[:, 0])[0, 1]), 1.0, atol=1e-3)
 
 
+def test_pca_init_truncated_matches_full():
+    """Large inputs use a truncated SVD for the K leading PCs; same components as the full prcomp up to sign."""
+    from clonealign_b200.inference import pca_init
+    from clonealign_b200.synthetic import make_synthetic
+    Y = make_synthetic(400, 300, 3, seed=5)["Y"]
+    class NoNoise:                                         # the N(0, .05^2) jitter (:208) is not what is compared
+        def normal(self, loc, scale, size):
+            return np.zeros(size)
+    for K in (1, 2):
+        a = pca_init(Y, K, NoNoise(), truncated=False)
+        b = pca_init(Y, K, NoNoise(), truncated=True)
+        assert a.shape == b.shape == (400, K)
+        for k in range(K):
+            assert abs(np.corrcoef(a[:, k], b[:, k])[0, 1]) > 0.999
+
+
+def test_compute_correlations_matches_per_gene_pearson():
+    """compute_correlations (R/clonealign.R:318-334) against an explicit per-gene loop."""
+    from clonealign_b200.api import compute_correlations
+    rng = np.random.default_rng(0)
+    N, G = 60, 25
+    Y = rng.poisson(3.0, size=(N, G)).astype(float)
+    Y[:, 4] = 2.0                                         # constant expression -> NA
+    L = rng.integers(1, 4, size=(G, 3)).astype(float)
+    L[7] = 2.0                                            # same copy number in every clone -> NA
+    names = ["A", "B", "C"]
+    clones = [names[i] for i in rng.integers(0, 3, size=N)]
+    clones[3] = clones[10] = "unassigned"
+    got = compute_correlations(Y, L, clones, names)
+    keep = np.array([c != "unassigned" for c in clones])
+    idx = np.array([names.index(c) for c in np.array(clones)[keep]])
+    for g in range(G):
+        x, y = L[g, idx], Y[keep, g]
+        if x.std() == 0 or y.std() == 0:
+            assert np.isnan(got[g])
+        else:
+            assert abs(got[g] - np.corrcoef(x, y)[0, 1]) < 1e-12
+
+
 def test_preprocess_matches_vignette(example_sce):
     from clonealign_b200.preprocess import preprocess_for_clonealign
     Y, L = example_sce
