@@ -108,6 +108,8 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
 
     Y_dat = np.asarray(Y_dat)
     L_dat = np.asarray(L_dat, dtype=np.float64)
+    if Y_dat.ndim != 2 or L_dat.ndim != 2 or L_dat.shape[0] != Y_dat.shape[1]:
+        raise ValueError("nrow(L_dat) == G is not TRUE")                              # :139 (R fails in the subset at :124)
     zero_gene_means = Y_dat.sum(axis=0) <= gene_filter_threshold                      # :117
     _message(verbose, f"Removing {int(zero_gene_means.sum())} genes with low counts")  # :120
     Y = Y_dat[:, ~zero_gene_means]
