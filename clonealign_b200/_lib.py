@@ -15,7 +15,7 @@ Y_F64, Y_F32, Y_I32 = 0, 1, 2
 Y_COLMAJOR, Y_ROWMAJOR = 0, 1
 Y_HOST, Y_DEVICE = 0, 1
 STORE_AUTO, STORE_F32, STORE_U16, STORE_U8 = 0, 1, 2, 3
-PATH_AUTO, PATH_CUDACORE, PATH_TENSOR = 0, 1, 2
+PATH_AUTO, PATH_CUDACORE, PATH_TENSOR, PATH_INTERP = 0, 1, 2, 3
 ABI_VERSION = 1
 
 EXPORTS = (

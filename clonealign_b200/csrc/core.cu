@@ -20,6 +20,7 @@
 #include "../../include/clonealign_b200.h"
 #include "common.cuh"
 #include "kernels_expgemm.cuh"
+#include "kernels_interp.cuh"
 #include "kernels_small.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_ypass.cuh"
@@ -175,6 +176,12 @@ struct ca_handle {
   int64_t N = 0, Ntot = 0, ldY = 0, Gld = 0, Nld = 0;
   int G = 0, C = 0, S = 0, K = 0, P = 0, KP = 0, SC = 0, SCp = 0, J = 0, V = 0;
   bool tc = false;
+  bool interp = false;             // K = 1 univariate-interpolation path (kernels_interp.cuh)
+  InterpPlan* iplan = nullptr;
+  float* mm_psi = nullptr;
+  double *ivals = nullptr, *icoef = nullptr;
+  size_t ieval_smem = 0;
+  int ieval_panels = 0;
   int ystore = CA_STORE_F32;
   int poison = 0;
   std::vector<void*> allocs;
@@ -369,8 +376,18 @@ void run_forward(ca_handle* h, int mode) {
     KCHECK();
   }
   {
-    LaunchScope ls(h, "lse_fwd");
-    if (h->tc) {
+    LaunchScope ls(h, "lse_fwd", h->interp ? 5 : 1);
+    if (h->interp) {
+      // K = 1: Zx[n][j] = F_j(psi_n) by piecewise Chebyshev interpolation (kernels_interp.cuh)
+      k_minmax<<<1, 1024, 0, h->stream>>>(h->U, (int)h->N, h->mm_psi);
+      k_interp_plan<<<1, 32, 0, h->stream>>>(h->mm, h->mm_psi, h->iplan);
+      dim3 gn((h->J + 31) / 32, kIMaxPanF * kIP / 8);
+      k_interp_nodes<true><<<gn, 256, 0, h->stream>>>(h->iplan, h->Vm, nullptr, h->Mx, h->G, h->J, h->ivals);
+      int64_t tot = (int64_t)kIMaxPanF * kIP * h->J;
+      k_interp_coeffs<<<(unsigned)ceil_div64(tot, 256), 256, 0, h->stream>>>(h->iplan, h->ivals, 1, kIMaxPanF, h->J, 1, h->icoef);
+      k_interp_eval<true><<<h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream>>>(h->iplan, h->icoef, h->U, h->N, h->J, h->Zx,
+                                                                                  h->ieval_panels);
+    } else if (h->tc) {
       tc_launch_fwd(h->tcplan, h->U, h->Vm, h->shift, h->Zx, h->stream);
     } else {
       int Jc = (mode == EPI_TRAIN) ? h->J : h->SC;   // ELBO-only passes need just Z
@@ -402,8 +419,16 @@ void run_train(ca_handle* h, bool apply) {
   h->launches_last_step = 0;
   run_forward(h, EPI_TRAIN);
   {
-    LaunchScope ls(h, "lse_bwd");
-    if (h->tc) {
+    LaunchScope ls(h, "lse_bwd", h->interp ? 3 : 1);
+    if (h->interp) {
+      // K = 1: dMx[g][j] = H_j(w_g); the plan of this step's forward pass is still valid (psi, W unchanged)
+      dim3 gn((h->J + 31) / 32, kIMaxPanB * kIP / 8, kISplitB);
+      k_interp_nodes<false><<<gn, 256, 0, h->stream>>>(h->iplan, h->U, h->shift, h->Rx, h->N, h->J, h->ivals);
+      int64_t tot = (int64_t)kIMaxPanB * kIP * h->J;
+      k_interp_coeffs<<<(unsigned)ceil_div64(tot, 256), 256, 0, h->stream>>>(h->iplan, h->ivals, kISplitB, kIMaxPanB, h->J, 0, h->icoef);
+      k_interp_eval<false><<<h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream>>>(h->iplan, h->icoef, h->Vm, h->G, h->J, h->dMx,
+                                                                                   h->ieval_panels);
+    } else if (h->tc) {
       tc_launch_bwd(h->tcplan, h->U, h->Vm, h->shift_bwd, h->dMx, h->stream);
     } else {
       dim3 grid((h->J + 63) / 64, (h->G + 63) / 64);
@@ -594,7 +619,9 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   h->KP = c.K + c.P; h->SC = c.S * c.C; h->V = c.V;
   bool tc_ok = (c.K == 1 && c.P == 0 && round_up64(h->SC, 16) <= 128);
   if (c.path == CA_PATH_TENSOR && !tc_ok) fail("tensor path needs K == 1, P == 0 and S*C <= 128");
-  h->tc = (c.path == CA_PATH_TENSOR) || (c.path == CA_PATH_AUTO && tc_ok);
+  if (c.path == CA_PATH_INTERP && !(c.K == 1 && c.P == 0)) fail("interp path needs K == 1 and P == 0");
+  h->interp = (c.path == CA_PATH_INTERP);
+  h->tc = !h->interp && ((c.path == CA_PATH_TENSOR) || (c.path == CA_PATH_AUTO && tc_ok));
   h->SCp = h->tc ? (int)round_up64(h->SC, 16) : h->SC;
   h->J = h->SCp * (1 + h->KP);
   h->ldY = round_up64(h->G, 16);
@@ -775,6 +802,20 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     h->Rx = z((size_t)N * J);
     h->dMx = z((size_t)G * J);
     h->nsplit = 1;
+  }
+  if (h->interp) {
+    h->iplan = h->alloc<InterpPlan>(1);
+    h->mm_psi = z(2);
+    const size_t nodes_f = (size_t)kIMaxPanF * kIP, nodes_b = (size_t)kISplitB * kIMaxPanB * kIP;
+    h->ivals = h->alloc<double>(std::max(nodes_f, nodes_b) * J);
+    h->icoef = h->alloc<double>((size_t)std::max(kIMaxPanF, kIMaxPanB) * kIP * J);
+    const size_t per_panel = (size_t)kIP * J * sizeof(double);
+    h->ieval_panels = (int)std::min<size_t>(16, (200 * 1024) / per_panel);
+    h->ieval_smem = (size_t)h->ieval_panels * per_panel;
+    if (h->ieval_smem > 48 * 1024) {
+      CUDA_OK(cudaFuncSetAttribute(k_interp_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ieval_smem));
+      CUDA_OK(cudaFuncSetAttribute(k_interp_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ieval_smem));
+    }
   }
   size_t smem = epi_smem_bytes(h->SCp, C, J, h->tc);
   if (smem > 48 * 1024) {
@@ -1076,7 +1117,7 @@ int ca_core_describe(ca_handle* h, char* json, size_t json_len) {
            "{\"N\": %lld, \"G\": %d, \"C\": %d, \"S\": %d, \"K\": %d, \"P\": %d, \"path\": \"%s\", \"y_store\": \"%s\", "
            "\"y_bytes_per_entry\": %d, \"ldY\": %lld, \"launches_last_step\": %d, \"nsplit\": %d, \"fsplit\": %d, "
            "\"SCp\": %d, \"J\": %d, \"world\": %d, \"rank\": %d}",
-           (long long)h->N, h->G, h->C, h->S, h->K, h->P, h->tc ? "tcgen05" : "cudacore", st, bpe, (long long)h->ldY,
+           (long long)h->N, h->G, h->C, h->S, h->K, h->P, h->interp ? "interp" : (h->tc ? "tcgen05" : "cudacore"), st, bpe, (long long)h->ldY,
            h->launches_last_step, h->nsplit, h->tc ? h->tcplan.fsplit : 1, h->SCp, h->J, h->cfg.world, h->cfg.rank);
   return 0;
 }

@@ -1,0 +1,232 @@
+// "interp" path (K = 1, P = 0): both contractions collapse to UNIVARIATE functions.
+//
+// With a single latent dimension eta_ng = psi_n w_g, so
+//     Zx[n][j]  = sum_g Mx[g][j] exp(psi_n w_g - m(psi_n)) = F_j(psi_n)     (normaliser, R/inference-tflow.R:288-290)
+//     dMx[g][j] = sum_n Rx[n][j] exp(psi_n w_g - m_n)       = H_j(w_g)       (its reverse-mode gradient)
+// where F_j, H_j are sums of exponentials: entire functions of ONE real variable.  Piecewise Chebyshev
+// interpolation on panels whose exponent half-range is <= kAmax converges spectrally (24 nodes: ~1e-14 relative,
+// scripts/interp_prototype.py, tests/test_interp_model.py), so the (N x G) x (G x J) contraction is replaced by
+//     nodes:  (n_nodes x G) x (G x J)   with n_nodes ~ 50..200 instead of N = 100 000        (k_interp_nodes<FWD>)
+//     DCT  :  node values -> Chebyshev coefficients per panel                                  (k_interp_coeffs)
+//     eval :  one Clenshaw recurrence per (cell, column)                                       (k_interp_eval)
+// and symmetrically for the backward pass (nodes over w, reduction over cells, evaluation per gene).
+// Everything is fp64 (node exponentials, accumulation, recurrence); inputs/outputs keep the fp32 layouts of the
+// CUDA-core path (Mx [G][J], Zx [N][J], Rx [N][J], dMx [G][J]), so the per-cell epilogue and the gene-gradient
+// kernels are shared.  All reductions run in a fixed order (deterministic).
+//
+// The shift convention is the one used everywhere else: m(x) = max(x w_max, x w_min), i.e. the exponent is
+// x (w_g - w_max) <= 0 for x >= 0 and x (w_g - w_min) <= 0 for x < 0: two smooth pieces, panelled separately.
+#pragma once
+#include "common.cuh"
+
+namespace ca {
+
+constexpr int kIP = 24;            // Chebyshev nodes per panel (multiple of 8)
+constexpr int kIMaxPanF = 64;      // forward panels (both signs of psi together)
+constexpr int kIMaxPanB = 64;      // backward panels over [w_min, w_max]
+constexpr int kISplitB = 16;       // fixed split of the cell reduction in the backward node kernel
+constexpr double kIAmax = 4.0;     // exponent half-range per panel
+constexpr double kPi = 3.14159265358979323846;
+
+struct InterpPlan {
+  double wmin, wmax, pmin, pmax;
+  int nf_neg, nf_pos;              // forward panels on [pmin, 0) and [0, pmax]
+  double f_neg_w, f_pos_w;         // panel widths (0 when the side is empty)
+  int nb;                          // backward panels on [wmin, wmax]
+  double b_w;
+};
+
+// panel -> (mid, half) helpers
+__device__ __forceinline__ void fwd_panel(const InterpPlan& pl, int pf, double& mid, double& half, double& wref) {
+  if (pf < pl.nf_neg) {
+    double lo = pl.pmin + pf * pl.f_neg_w;
+    half = 0.5 * pl.f_neg_w;
+    mid = lo + half;
+    wref = pl.wmin;
+  } else {
+    double lo = (pf - pl.nf_neg) * pl.f_pos_w;
+    half = 0.5 * pl.f_pos_w;
+    mid = lo + half;
+    wref = pl.wmax;
+  }
+}
+__device__ __forceinline__ void bwd_panel(const InterpPlan& pl, int pb, double& mid, double& half) {
+  half = 0.5 * pl.b_w;
+  mid = pl.wmin + pb * pl.b_w + half;
+}
+__device__ __forceinline__ double cheb_node(int p) { return cos(kPi * (p + 0.5) / kIP); }
+
+// one thread: panel structure from the current ranges of psi and w
+__global__ void k_interp_plan(const float* __restrict__ mm_w, const float* __restrict__ mm_psi, InterpPlan* __restrict__ plan) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  InterpPlan pl;
+  pl.wmin = (double)mm_w[0]; pl.wmax = (double)mm_w[1];
+  pl.pmin = (double)mm_psi[0]; pl.pmax = (double)mm_psi[1];
+  const double D = pl.wmax - pl.wmin;
+  auto count = [](double width, double scale, int cap) {
+    int n = (int)ceil(scale * width / 2.0 / kIAmax);
+    return n < 1 ? 1 : (n > cap ? cap : n);
+  };
+  if (pl.pmin < 0.0) {
+    pl.nf_neg = count(-pl.pmin, D, kIMaxPanF / 2);
+    pl.f_neg_w = -pl.pmin / pl.nf_neg;
+  } else {
+    pl.nf_neg = 0; pl.f_neg_w = 0.0;
+  }
+  if (pl.pmax >= 0.0) {
+    pl.nf_pos = count(pl.pmax, D, kIMaxPanF / 2);
+    pl.f_pos_w = pl.pmax / pl.nf_pos;
+  } else {
+    pl.nf_pos = 0; pl.f_pos_w = 0.0;
+  }
+  const double A = fmax(fabs(pl.pmin), fabs(pl.pmax));
+  pl.nb = count(D, A, kIMaxPanB);
+  pl.b_w = D / pl.nb;
+  *plan = pl;
+}
+
+// Node values.  FWD: vals[node][j] = sum_g Mx[g][j] exp(x_node (w_g - wref));  reduction index = genes.
+//               BWD: part[z][node][j] = sum_{n in split z} Rx[n][j] exp(psi_n y_node - m_n);  reduction index = cells.
+// Block = 8 warps = 8 nodes x 32 columns; warps stride over the reduction index, lane = column; the 8 exponentials
+// of a row are computed by lanes 0..7 and broadcast.  Cross-warp reduction in a fixed order through shared memory.
+template <bool FWD>
+__global__ void __launch_bounds__(256)
+k_interp_nodes(const InterpPlan* __restrict__ plan, const float* __restrict__ rv /*FWD: w[G]  BWD: psi[N]*/,
+               const float* __restrict__ shift /*BWD: m[N]*/, const float* __restrict__ B /*[R][J]*/, int64_t R, int J,
+               double* __restrict__ vals) {
+  __shared__ double red[8][8][32];
+  const InterpPlan pl = *plan;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int node0 = blockIdx.y * 8;
+  const int panel = node0 / kIP;
+  const int npan = FWD ? (pl.nf_neg + pl.nf_pos) : pl.nb;
+  if (panel >= npan) return;
+  double mid, half, wref = 0.0;
+  if (FWD) fwd_panel(pl, panel, mid, half, wref);
+  else bwd_panel(pl, panel, mid, half);
+  const double xq = mid + half * cheb_node((node0 % kIP) + (lane & 7));   // node handled by this lane (lanes 0..7 used)
+  const int j = blockIdx.x * 32 + lane;
+  const bool jok = j < J;
+  // reduction range of this block
+  int64_t rbeg = 0, rend = R;
+  if (!FWD) {
+    const int64_t per = (R + kISplitB - 1) / kISplitB;
+    rbeg = (int64_t)blockIdx.z * per;
+    rend = rbeg + per < R ? rbeg + per : R;
+  }
+  double acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+  // 4 rows of the reduction index per warp iteration: lane (q = lane & 7, sub = lane >> 3) evaluates the exponential
+  // of row r + sub at node q (argument in fp64, expf in fp32: ~1e-7 relative, averaged over the sum), then every lane
+  // accumulates its column in fp64
+  for (int64_t r = rbeg + (int64_t)wid * 4; r < rend; r += 32) {
+    const int64_t rr = r + (lane >> 3);
+    float e = 0.f;
+    if (rr < rend) {
+      const double v = (double)rv[rr];
+      e = FWD ? expf((float)(xq * (v - wref))) : expf((float)(v * xq - (double)shift[rr]));
+    }
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      const int64_t r2 = r + sub;
+      const double b = (jok && r2 < rend) ? (double)B[r2 * J + j] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = fma((double)__shfl_sync(CA_FULL, e, q + 8 * sub), b, acc[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) red[wid][q][lane] = acc[q];
+  __syncthreads();
+  // thread (q = wid, lane): sum over the 8 warps in order
+  double s = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][wid][lane];
+  if (jok) {
+    const int64_t nodes_total = (int64_t)(FWD ? kIMaxPanF : kIMaxPanB) * kIP;
+    const int64_t z = FWD ? 0 : blockIdx.z;
+    vals[(z * nodes_total + node0 + wid) * J + j] = s;
+  }
+}
+
+// Chebyshev coefficients per panel: c_k = (2/P) sum_p f(x_p) cos(pi k (p + 1/2) / P), c_0 halved.
+// The backward node values arrive as kISplitB partials that are summed here in a fixed order.
+__global__ void k_interp_coeffs(const InterpPlan* __restrict__ plan, const double* __restrict__ vals, int nsplit,
+                                int max_pan, int J, int fwd, double* __restrict__ coeff) {
+  const InterpPlan pl = *plan;
+  const int npan = fwd ? (pl.nf_neg + pl.nf_pos) : pl.nb;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (panel, k, j)
+  const int64_t tot = (int64_t)npan * kIP * J;
+  if (i >= tot) return;
+  const int j = (int)(i % J);
+  const int k = (int)((i / J) % kIP);
+  const int panel = (int)(i / ((int64_t)J * kIP));
+  const int64_t nodes_total = (int64_t)max_pan * kIP;
+  double c = 0.0;
+  for (int p = 0; p < kIP; ++p) {
+    double f = 0.0;
+    for (int z = 0; z < nsplit; ++z) f += vals[((int64_t)z * nodes_total + panel * kIP + p) * J + j];
+    c += f * cos(kPi * k * (p + 0.5) / kIP);
+  }
+  c *= 2.0 / kIP;
+  if (k == 0) c *= 0.5;
+  coeff[((int64_t)panel * kIP + k) * J + j] = c;
+}
+
+// Evaluation: out[i][j] = sum_k c[panel(x_i)][k][j] T_k(t_i) by Clenshaw, one warp per point, lanes over columns.
+// Persistent blocks keep the coefficients of all active panels in shared memory when they fit (the common case:
+// 2..6 panels); otherwise they are read through L2.  FWD: points = cells (x = psi), BWD: points = genes (x = w).
+constexpr int kIEvalWarps = 16;
+template <bool FWD>
+__global__ void __launch_bounds__(kIEvalWarps * 32)
+k_interp_eval(const InterpPlan* __restrict__ plan, const double* __restrict__ coeff, const float* __restrict__ xs, int64_t n,
+              int J, float* __restrict__ out, int smem_panels) {
+  extern __shared__ double csm[];
+  const InterpPlan pl = *plan;
+  const int npan = FWD ? (pl.nf_neg + pl.nf_pos) : pl.nb;
+  const bool in_smem = npan <= smem_panels;
+  const int64_t per_panel = (int64_t)kIP * J;
+  if (in_smem) {
+    for (int64_t i = threadIdx.x; i < npan * per_panel; i += blockDim.x) csm[i] = coeff[i];
+    __syncthreads();
+  }
+  const double* cbase = in_smem ? csm : coeff;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t ibeg = (int64_t)blockIdx.x * chunk;
+  const int64_t iend = ibeg + chunk < n ? ibeg + chunk : n;
+  for (int64_t i = ibeg + wid; i < iend; i += kIEvalWarps) {
+    const double x = (double)xs[i];
+    int panel;
+    double mid, half, wref;
+    if (FWD) {
+      if (x < 0.0) {
+        panel = (int)((x - pl.pmin) / pl.f_neg_w);
+        panel = panel < 0 ? 0 : (panel >= pl.nf_neg ? pl.nf_neg - 1 : panel);
+      } else {
+        panel = pl.f_pos_w > 0.0 ? (int)(x / pl.f_pos_w) : 0;
+        panel = pl.nf_neg + (panel >= pl.nf_pos ? pl.nf_pos - 1 : panel);
+      }
+      fwd_panel(pl, panel, mid, half, wref);
+    } else {
+      panel = pl.b_w > 0.0 ? (int)((x - pl.wmin) / pl.b_w) : 0;
+      panel = panel < 0 ? 0 : (panel >= pl.nb ? pl.nb - 1 : panel);
+      bwd_panel(pl, panel, mid, half);
+    }
+    const double t = half > 0.0 ? (x - mid) / half : 0.0;
+    const double t2 = 2.0 * t;
+    const double* c = cbase + (int64_t)panel * per_panel;
+    for (int j = lane; j < J; j += 32) {
+      double b1 = 0.0, b2 = 0.0;
+#pragma unroll 4
+      for (int k = kIP - 1; k >= 1; --k) {
+        const double tmp = fma(t2, b1, c[(int64_t)k * J + j] - b2);
+        b2 = b1;
+        b1 = tmp;
+      }
+      out[i * J + j] = (float)(fma(t, b1, c[j] - b2));
+    }
+  }
+}
+
+}  // namespace ca

@@ -23,7 +23,7 @@ import numpy as np
 from . import _lib
 
 _STORE = {"auto": _lib.STORE_AUTO, "f32": _lib.STORE_F32, "u16": _lib.STORE_U16, "u8": _lib.STORE_U8}
-_PATH = {"auto": _lib.PATH_AUTO, "cudacore": _lib.PATH_CUDACORE, "tensor": _lib.PATH_TENSOR}
+_PATH = {"auto": _lib.PATH_AUTO, "cudacore": _lib.PATH_CUDACORE, "tensor": _lib.PATH_TENSOR, "interp": _lib.PATH_INTERP}
 
 _SHAPES = {  # name -> lambda(session) -> (rows, cols)
     "W": lambda s: (s.G, s.K), "beta": lambda s: (s.G, s.P), "psi": lambda s: (s.N, s.K),

@@ -51,8 +51,10 @@ enum ca_y_mem    { CA_Y_HOST = 0, CA_Y_DEVICE = 1 };
  * fits, a narrower unsigned type.  AUTO picks the narrowest exact representation. */
 enum ca_y_store  { CA_STORE_AUTO = 0, CA_STORE_F32 = 1, CA_STORE_U16 = 2, CA_STORE_U8 = 3 };
 /* which contraction kernels run: AUTO = tcgen05 path when K == 1 and P == 0 (the reference's default
- * model), CUDA-core fp32 path otherwise. */
-enum ca_path     { CA_PATH_AUTO = 0, CA_PATH_CUDACORE = 1, CA_PATH_TENSOR = 2 };
+ * model), CUDA-core fp32 path otherwise.  INTERP (K == 1, P == 0 only) replaces both contractions by piecewise
+ * Chebyshev interpolation of the univariate functions they reduce to (kernels_interp.cuh); opt-in until it has
+ * been validated on hardware. */
+enum ca_path     { CA_PATH_AUTO = 0, CA_PATH_CUDACORE = 1, CA_PATH_TENSOR = 2, CA_PATH_INTERP = 3 };
 
 typedef struct ca_config {
   int64_t N;            /* cells held by this handle (this rank's shard)                       */
