@@ -50,6 +50,24 @@ def test_ca_config_layout_matches_c():
     assert out[1:] == [getattr(CaConfig, f).offset for f in fields]
 
 
+def _build_c_probe(td):
+    exe = os.path.join(td, "c_abi_probe")
+    libdir = os.path.join(ROOT, "clonealign_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c_abi_probe.c"),
+                           "-o", exe, "-L", libdir, "-lclonealign_b200", "-lm", f"-Wl,-rpath,{libdir}"])
+    return exe
+
+
+def test_plain_c_client_of_the_abi(lib):
+    """The boundary is a C ABI (plain pointers and sizes): a C program with R-layout inputs links and runs against it.
+    Without a GPU it must fail loudly inside ca_core_create; with one it must complete a train step."""
+    with tempfile.TemporaryDirectory() as td:
+        out = subprocess.run([_build_c_probe(td)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "abi=1" in out.stdout
+    assert ("create_failed" in out.stdout and "msg_len=0" not in out.stdout) or "ok elbo0=" in out.stdout
+
+
 def test_fails_loudly_without_gpu(lib, example_sce):
     """No CPU fallback: on a box without CUDA the product path must raise, not compute."""
     import torch
