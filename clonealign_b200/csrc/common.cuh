@@ -7,6 +7,10 @@
 
 #define CA_WARP 32
 #define CA_FULL 0xffffffffu
+// dynamic shared memory declaration (the CPU emulation used by tests/test_cuda_emul.py overrides it)
+#ifndef CA_DYNAMIC_SMEM
+#define CA_DYNAMIC_SMEM(T, name) extern __shared__ T name[]
+#endif
 
 namespace ca {
 

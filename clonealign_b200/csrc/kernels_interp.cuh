@@ -181,7 +181,7 @@ template <bool FWD>
 __global__ void __launch_bounds__(kIEvalWarps * 32)
 k_interp_eval(const InterpPlan* __restrict__ plan, const double* __restrict__ coeff, const float* __restrict__ xs, int64_t n,
               int J, float* __restrict__ out, int smem_panels) {
-  extern __shared__ double csm[];
+  CA_DYNAMIC_SMEM(double, csm);
   const InterpPlan pl = *plan;
   const int npan = FWD ? (pl.nf_neg + pl.nf_pos) : pl.nb;
   const bool in_smem = npan <= smem_panels;

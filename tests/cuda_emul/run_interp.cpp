@@ -1,0 +1,69 @@
+// Runs the kernels of clonealign_b200/csrc/kernels_interp.cuh on the CPU emulation (tests/cuda_emul/cuda_emul.h) in the
+// same order and with the same arguments as run_forward / run_train in core.cu, on inputs read from a binary file.
+//   usage: run_interp in.bin out.bin
+//   in : int32 N, G, J, smem_panels; float psi[N], w[G], Mx[G*J], Rx[N*J]
+//   out: int32 nf_neg, nf_pos, nb; float Zx[N*J], dMx[G*J]
+#include <cstdio>
+#include <vector>
+
+#include "../../clonealign_b200/csrc/common.cuh"
+#include "../../clonealign_b200/csrc/kernels_interp.cuh"
+
+using namespace ca;
+
+int main(int argc, char** argv) {
+  if (argc < 3) return 1;
+  FILE* f = fopen(argv[1], "rb");
+  int hdr[4];
+  if (!f || fread(hdr, 4, 4, f) != 4) return 2;
+  const int N = hdr[0], G = hdr[1], J = hdr[2], smem_panels = hdr[3];
+  std::vector<float> psi(N), w(G), Mx((size_t)G * J), Rx((size_t)N * J), shift(N);
+  if (fread(psi.data(), 4, N, f) != (size_t)N || fread(w.data(), 4, G, f) != (size_t)G ||
+      fread(Mx.data(), 4, (size_t)G * J, f) != (size_t)G * J || fread(Rx.data(), 4, (size_t)N * J, f) != (size_t)N * J)
+    return 3;
+  fclose(f);
+  float mm_w[2] = {w[0], w[0]}, mm_psi[2] = {psi[0], psi[0]};
+  for (float v : w) { mm_w[0] = fminf(mm_w[0], v); mm_w[1] = fmaxf(mm_w[1], v); }
+  for (float v : psi) { mm_psi[0] = fminf(mm_psi[0], v); mm_psi[1] = fmaxf(mm_psi[1], v); }
+  for (int n = 0; n < N; ++n) shift[n] = fmaxf(psi[n] * mm_w[0], psi[n] * mm_w[1]);   // k_shift_k1
+
+  InterpPlan plan;
+  ca_emul::launch(k_interp_plan, dim3(1), dim3(32), 0, (const float*)mm_w, (const float*)mm_psi, &plan);
+  const int npf = plan.nf_neg + plan.nf_pos;
+  std::vector<double> vals((size_t)std::max(kIMaxPanF, kISplitB * kIMaxPanB) * kIP * J, 0.0);
+  std::vector<double> coef((size_t)std::max(kIMaxPanF, kIMaxPanB) * kIP * J, 0.0);
+  std::vector<float> Zx((size_t)N * J, -1.f), dMx((size_t)G * J, -1.f);
+  const size_t eval_smem = (size_t)smem_panels * kIP * J * sizeof(double);
+
+  // forward: nodes -> coefficients -> evaluation per cell.  (core.cu launches kIMaxPanF*kIP/8 node groups; the
+  // inactive ones return at once, so only the active ones plus one extra group are emulated here.)
+  ca_emul::launch(k_interp_nodes<true>, dim3((J + 31) / 32, npf * kIP / 8 + 1), dim3(256), 0, (const InterpPlan*)&plan,
+                  (const float*)w.data(), (const float*)nullptr, (const float*)Mx.data(), (int64_t)G, J, vals.data());
+  {
+    int64_t tot = (int64_t)kIMaxPanF * kIP * J;
+    ca_emul::launch(k_interp_coeffs, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, (const InterpPlan*)&plan,
+                    (const double*)vals.data(), 1, kIMaxPanF, J, 1, coef.data());
+  }
+  ca_emul::launch(k_interp_eval<true>, dim3(3), dim3(kIEvalWarps * 32), eval_smem, (const InterpPlan*)&plan,
+                  (const double*)coef.data(), (const float*)psi.data(), (int64_t)N, J, Zx.data(), smem_panels);
+
+  // backward: nodes over w (reduction over cells, kISplitB partials) -> coefficients -> evaluation per gene
+  ca_emul::launch(k_interp_nodes<false>, dim3((J + 31) / 32, plan.nb * kIP / 8 + 1, kISplitB), dim3(256), 0,
+                  (const InterpPlan*)&plan, (const float*)psi.data(), (const float*)shift.data(), (const float*)Rx.data(),
+                  (int64_t)N, J, vals.data());
+  {
+    int64_t tot = (int64_t)kIMaxPanB * kIP * J;
+    ca_emul::launch(k_interp_coeffs, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, (const InterpPlan*)&plan,
+                    (const double*)vals.data(), kISplitB, kIMaxPanB, J, 0, coef.data());
+  }
+  ca_emul::launch(k_interp_eval<false>, dim3(2), dim3(kIEvalWarps * 32), eval_smem, (const InterpPlan*)&plan,
+                  (const double*)coef.data(), (const float*)w.data(), (int64_t)G, J, dMx.data(), smem_panels);
+
+  FILE* o = fopen(argv[2], "wb");
+  int oh[3] = {plan.nf_neg, plan.nf_pos, plan.nb};
+  fwrite(oh, 4, 3, o);
+  fwrite(Zx.data(), 4, Zx.size(), o);
+  fwrite(dMx.data(), 4, dMx.size(), o);
+  fclose(o);
+  return 0;
+}
