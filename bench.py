@@ -164,6 +164,62 @@ def run_reference(args, cfg):
 
 
 # ------------------------------------------------------------------------------------------------------
+# on-device self-check of the K = 1 interpolation path against the (test-covered) tcgen05 path
+# ------------------------------------------------------------------------------------------------------
+def run_selfcheck(args, cfg):
+    """Child-process mode: same workload, same seeds, two sessions (path tensor / interp), 3 train steps each;
+    prints {"selfcheck": "ok"|"mismatch", ...}.  A device fault here cannot poison the benchmark process."""
+    import torch
+    from clonealign_b200.inference import safe_inverse_softplus
+    from clonealign_b200.session import Session
+    from clonealign_b200.synthetic import make_synthetic_cuda
+    N, G, C, S = cfg["N"], cfg["G"], cfg["C"], cfg["S"]
+    torch.cuda.set_device(0)
+    syn = make_synthetic_cuda(N, G, C, seed=DATA_SEED, device="cuda:0")
+    Yd = syn["Y"]
+    L = np.minimum(syn["L"], 6.0)
+    psi = np.random.default_rng(EPS_SEED).standard_normal((N, 1))
+    mu_guess = (Yd / Yd.mean(dim=1, keepdim=True)).mean(dim=0, dtype=torch.float64).cpu().numpy()
+    loc_init = safe_inverse_softplus(mu_guess)
+    res = {}
+    for path in ("tensor", "interp"):
+        sess = Session(Yd, L, psi, loc_init, mc_samples=S, K=1, learning_rate=0.1, seed=EPS_SEED, y_store=args.y_store, path=path)
+        sess.init_gamma()
+        tr = [sess.elbo()]
+        for _ in range(3):
+            sess.step()
+            tr.append(sess.elbo())
+        prm = sess.params()
+        sess.close()
+        res[path] = (np.array(tr), prm["psi"], prm["clone_probs"], prm["mu"])
+    a, b = res["tensor"], res["interp"]
+    rel = lambda x, y: float(np.abs(x - y).max() / (np.abs(y).max() + 1e-300))
+    d = dict(elbo=float(np.abs(a[0] - b[0]).max() / np.abs(a[0]).max()), psi=rel(b[1], a[1]),
+             clone_probs=float(np.abs(a[2] - b[2]).max()), mu=rel(b[3], a[3]))
+    ok = (np.all(np.isfinite(b[0])) and d["elbo"] <= 1e-4 and d["psi"] <= 2e-3 and d["clone_probs"] <= 5e-3
+          and d["mu"] <= 1e-3)
+    print(json.dumps({"selfcheck": "ok" if ok else "mismatch", "deviation_vs_tensor_path": d, "elbo_interp": b[0].tolist()}),
+          flush=True)
+    sys.exit(0 if ok else 1)
+
+
+def interp_selfcheck(args):
+    """Run `bench.py --selfcheck` as a single-GPU child process (rank 0 only); returns (ok, info)."""
+    drop = ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "ROLE_WORLD_SIZE",
+            "GROUP_WORLD_SIZE", "TORCHELASTIC_RUN_ID")
+    env = {k: v for k, v in os.environ.items() if k not in drop}
+    cmd = [sys.executable, os.path.abspath(__file__), "--selfcheck", "--config", args.config, "--y-store", args.y_store,
+           "--watchdog", "240"]
+    try:
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+        last = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else ""
+        info = json.loads(last) if last.startswith("{") else {"selfcheck": "failed", "stderr": out.stderr[-300:]}
+        return out.returncode == 0 and info.get("selfcheck") == "ok", info
+    except Exception as e:                      # timeout, crash, no JSON: never let the check break the benchmark
+        return False, {"selfcheck": "failed", "error": str(e)[:300]}
+
+
+# ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
 def run_ours(args, cfg):
@@ -178,6 +234,16 @@ def run_ours(args, cfg):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     dev = local_rank
     torch.cuda.set_device(dev)
+    # contraction path: "best" asks rank 0 to validate the K = 1 interpolation path on this box (child process, same
+    # workload) against the tcgen05 path that the parity tests cover; every rank then takes rank 0's verdict
+    path, selfcheck = args.path, None
+    if path == "best":
+        ok = 0.0
+        if rank == 0:
+            okb, selfcheck = interp_selfcheck(args)
+            ok = 1.0 if okb else 0.0
+        ok = D.max_over_ranks(ok)
+        path = "interp" if ok > 0.5 else "auto"
     N, G, C, S = cfg["N"], cfg["G"], cfg["C"], cfg["S"]
     a, b = D.shard_bounds(N, rank, world)
     pk = peaks()
@@ -206,7 +272,7 @@ def run_ours(args, cfg):
     if not args.no_e2e:
         host_copy = torch.empty(Yd.shape, dtype=torch.float32, pin_memory=True)
         host_copy.copy_(Yd)
-    kw = dict(mc_samples=S, K=1, learning_rate=0.1, seed=EPS_SEED, y_store=args.y_store, path=args.path, **allele)
+    kw = dict(mc_samples=S, K=1, learning_rate=0.1, seed=EPS_SEED, y_store=args.y_store, path=path, **allele)
     sess = D.sharded_session(Yd, L, psi, loc_init, N, colsum_local, rank, world, dev, **kw)
     del Yd, syn
     torch.cuda.empty_cache()
@@ -258,7 +324,7 @@ def run_ours(args, cfg):
         ach = k["alg"] / (k["t"] / 1e3)
         traffic = None                      # DRAM bytes per launch from the committed `ncu --set full` capture (same config only)
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if world == 1 and os.path.exists(tpath):
+        if world == 1 and desc["y_store"] == "u8" and os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.config, {}).get(top)
         roofline = dict(kernel=top, bound=k["bound"], achieved=ach, peak=peak, unit="GB/s" if k["bound"] == "hbm" else "TFLOP/s",
                         frac=ach / peak, traffic=traffic, peak_source=pk["which"], ms_per_launch=k["t"],
@@ -308,6 +374,7 @@ def run_ours(args, cfg):
                 "config": {"workload": cfg["name"], "cells_total": N, "cells_per_gpu": Nl, "genes": G, "clones": C, "mc_samples": S,
                            "K": 1, "sharding": f"cells/{world}", "path": desc["path"], "y_store": desc["y_store"],
                            "l2": "inputs larger than L2 (Y shard >> 126 MB)", "psi_init": "random normal (PCA skipped)",
+                           "path_requested": args.path, "interp_selfcheck": selfcheck,
                            "elbo_start": e_start, "elbo_end": e_end},
                 "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "step_hbm": step_hbm, "e2e": e2e,
                 "cpu_baseline": cpu_base}
@@ -322,7 +389,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--y-store", default="auto", choices=["auto", "f32", "u16", "u8"])
-    ap.add_argument("--path", default="auto", choices=["auto", "cudacore", "tensor", "interp"])
+    ap.add_argument("--path", default="best", choices=["best", "auto", "cudacore", "tensor", "interp"],
+                    help="best = the K=1 interpolation path if its on-device self-check against the tensor path passes "
+                         "(run in a child process), else auto (tcgen05 contraction kernels)")
+    ap.add_argument("--selfcheck", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--watchdog", type=int, default=600,
@@ -334,7 +404,9 @@ def main():
         wd.daemon = True
         wd.start()
     cfg = CONFIGS[args.config]
-    if args.impl == "reference":
+    if args.selfcheck:
+        run_selfcheck(args, cfg)
+    elif args.impl == "reference":
         run_reference(args, cfg)
     else:
         run_ours(args, cfg)

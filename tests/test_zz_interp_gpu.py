@@ -1,0 +1,85 @@
+"""GPU parity tests of the K = 1 interpolation path (`path="interp"`, clonealign_b200/csrc/kernels_interp.cuh).
+
+The path was written after round 1's GPU budget was spent: its kernels are verified functionally on the CPU emulation
+(tests/test_cuda_emul.py) but had never run on hardware when this file was committed.  Until they have, these tests are
+`xfail(strict=False)`: a pass is reported as XPASS (evidence), a failure cannot turn the suite red, and the file sorts
+last so that a device fault here cannot disturb the tests of the default paths.  Once green on a B200: drop the marker,
+add "interp" to PATHS in test_gpu_parity.py and make it the AUTO path for K = 1, P = 0.
+"""
+import numpy as np
+import pytest
+
+from oracle import clonealign_oracle as O
+from test_gpu_parity import ELBO_RTOL, PARAM_RTOL, _case, _check_grads, _load_params, _relmax, _run_trace, _session
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="interp path not yet validated on hardware")]
+
+
+@pytest.mark.parametrize("S", [1, 3])
+def test_interp_gradients_and_elbo_match_oracle_c1(example_sce, S):
+    Y, L = example_sce
+    d, p, mu_guess, _ = _case(Y, L, K=1, seed=S)
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path="interp", seed=1) as sess:
+        assert sess.describe()["path"] == "interp"
+        _load_params(sess, p)
+        errs = _check_grads(sess, d, p, S)
+        assert errs["Z"] < 1e-5
+
+
+@pytest.mark.parametrize("N,G,C,S", [(130, 70, 5, 3), (257, 193, 2, 1), (64, 640, 7, 8), (1000, 333, 12, 8)])
+def test_interp_ragged_shapes(N, G, C, S):
+    from clonealign_b200.synthetic import make_synthetic
+    syn = make_synthetic(N, G, C, seed=N + G)
+    d, p, mu_guess, _ = _case(syn["Y"].astype(np.float64), np.minimum(syn["L"], 6.0), K=1, seed=N)
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path="interp", seed=1) as sess:
+        _load_params(sess, p)
+        _check_grads(sess, d, p, S)
+
+
+def test_interp_wide_range_uses_many_panels(example_sce):
+    """psi and W scaled up so that the exponent range needs several panels on each side."""
+    Y, L = example_sce
+    d, p, mu_guess, _ = _case(Y, L, K=1, seed=5, scale=1.0)
+    p.psi *= 2.0
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=2, K=1, path="interp", seed=1) as sess:
+        _load_params(sess, p)
+        _check_grads(sess, d, p, 2)
+
+
+def test_interp_allele(example_sce):
+    Y, L = example_sce
+    d, p, mu_guess, al = _case(Y, L, K=1, use_v=True, seed=21)
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=1, K=1, path="interp", seed=1, **al) as sess:
+        _load_params(sess, p)
+        _check_grads(sess, d, p, 1)
+
+
+@pytest.mark.parametrize("S", [1, 3])
+def test_interp_loop_matches_golden(example_sce, golden_c1, S):
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=None)
+    eps = golden_c1[f"eps_S{S}"]
+    with _session(hi["Y"], hi["L"], golden_c1["psi_init"], golden_c1["mu_guess"], mc_samples=S, K=1, path="interp",
+                  learning_rate=0.1, seed=3) as sess:
+        sess.set_eps(eps)
+        sess.init_gamma()
+        elbos = [sess.elbo()]
+        for _ in range(5):
+            sess.step()
+            elbos.append(sess.elbo())
+        prm = sess.params()
+    ref = golden_c1[f"elbos_S{S}"]
+    assert (np.abs(np.array(elbos) - ref) / np.abs(ref)).max() <= ELBO_RTOL
+    names = ["A", "B", "C"]
+    assert O.clone_assignment(prm["clone_probs"], names) == O.clone_assignment(golden_c1[f"clone_probs_S{S}"], names)
+    assert _relmax(prm["mu"], golden_c1[f"mu_S{S}"]) <= PARAM_RTOL
+    assert _relmax(prm["psi"], golden_c1[f"psi_S{S}"]) <= PARAM_RTOL
+    assert _relmax(prm["W"], golden_c1[f"W_S{S}"]) <= PARAM_RTOL
+
+
+def test_interp_same_seed_bitwise_identical(example_sce):
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
+    a, ga = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], mc_samples=2, seed=12345, path="interp")
+    b, gb = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], mc_samples=2, seed=12345, path="interp")
+    assert a.tobytes() == b.tobytes() and ga.tobytes() == gb.tobytes()
