@@ -7,9 +7,14 @@
 
 #define CA_WARP 32
 #define CA_FULL 0xffffffffu
-// dynamic shared memory declaration (the CPU emulation used by tests/test_cuda_emul.py overrides it)
+// dynamic shared memory declaration (the CPU emulation in tests/cuda_emul/ overrides it)
 #ifndef CA_DYNAMIC_SMEM
 #define CA_DYNAMIC_SMEM(T, name) extern __shared__ T name[]
+#endif
+// every kernel launch of the host code goes through this macro: CA_LAUNCH(kernel, grid, block, smem, stream)(args...)
+// (the CPU emulation of tests/cuda_emul/ overrides it to run the same launch sequence without a GPU)
+#ifndef CA_LAUNCH
+#define CA_LAUNCH(kernel, grid, block, smem, stream) kernel<<<(grid), (block), (smem), (stream)>>>
 #endif
 
 namespace ca {

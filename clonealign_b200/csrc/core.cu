@@ -22,7 +22,11 @@
 #include "kernels_expgemm.cuh"
 #include "kernels_interp.cuh"
 #include "kernels_small.cuh"
+#ifdef CA_EMULATE   // tests/cuda_emul: functional CPU emulation of the non-tensor kernels (test infrastructure only)
+#include "kernels_tc_stub.h"
+#else
 #include "kernels_tc.cuh"
+#endif
 #include "kernels_ypass.cuh"
 
 using namespace ca;
@@ -289,25 +293,25 @@ void run_ypass(ca_handle* h, cudaStream_t st) {
       LaunchScope ls(h, "ypass");
       dim3 grid(h->nCB, h->nRB);
       if (st == h->stream && !getenv("CLONEALIGN_B200_YPASS_LIGHT")) {
-        k_ypass_k1<T><<<grid, 256, 0, st>>>(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
+        CA_LAUNCH(k_ypass_k1<T>, grid, 256, 0, st)(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
       } else {
         int64_t tiles = (int64_t)h->nCB * h->nRB;
         unsigned g = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)h->num_sms);
-        k_ypass_k1_persistent<T><<<g, 256, 0, st>>>(Yp, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm, h->rowpart,
+        CA_LAUNCH(k_ypass_k1_persistent<T>, g, 256, 0, st)(Yp, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm, h->rowpart,
                                                     h->colpart);
       }
       KCHECK();
     } else {
       {
         LaunchScope ls(h, "ypass_rows");
-        k_ypass_rows_generic<T><<<(unsigned)ceil_div64(h->N, 8), 256, 0, st>>>(Yp, h->ldY, h->N, h->G, h->KP, h->Vm,
+        CA_LAUNCH(k_ypass_rows_generic<T>, (unsigned)ceil_div64(h->N, 8), 256, 0, st)(Yp, h->ldY, h->N, h->G, h->KP, h->Vm,
                                                                                  h->rowpart);
         KCHECK();
       }
       {
         LaunchScope ls(h, "ypass_cols");
         dim3 grid((h->G + 127) / 128, h->nRB);
-        k_ypass_cols_generic<T><<<grid, 128, 0, st>>>(Yp, h->ldY, h->N, h->G, h->KP, h->RB, h->U, h->colpart);
+        CA_LAUNCH(k_ypass_cols_generic<T>, grid, 128, 0, st)(Yp, h->ldY, h->N, h->G, h->KP, h->RB, h->U, h->colpart);
         KCHECK();
       }
     }
@@ -347,7 +351,7 @@ void run_forward(ca_handle* h, int mode) {
   }
   {
     LaunchScope ls(h, "alpha");
-    k_alpha<<<1, 32, 0, h->stream>>>(h->u, h->C, h->chi_raw, h->K, h->log_alpha, h->scal_elbo);
+    CA_LAUNCH(k_alpha, 1, 32, 0, h->stream)(h->u, h->C, h->chi_raw, h->K, h->log_alpha, h->scal_elbo);
     KCHECK();
   }
   {
@@ -359,40 +363,40 @@ void run_forward(ca_handle* h, int mode) {
     a.eps_out = h->eps; a.mu = h->mu; a.logmu = h->logmu; a.sig = h->sig;
     a.Mx = h->tc ? nullptr : h->Mx; a.MxT_hi = h->tc ? h->MxT_hi : nullptr; a.MxT_lo = h->tc ? h->MxT_lo : nullptr;
     a.gene_part = h->gene_part;
-    k_sample_mu<<<h->n_gene_blocks, 256, 0, h->stream>>>(a);
+    CA_LAUNCH(k_sample_mu, h->n_gene_blocks, 256, 0, h->stream)(a);
     KCHECK();
   }
   if (h->KP == 0) {
     CUDA_OK(cudaMemsetAsync(h->shift, 0, sizeof(float) * h->N, h->stream));
   } else if (h->K == 1 && h->P == 0) {
     LaunchScope ls(h, "shift", 2);
-    k_minmax<<<1, 1024, 0, h->stream>>>(h->Vm, h->G, h->mm);
+    CA_LAUNCH(k_minmax, 1, 1024, 0, h->stream)(h->Vm, h->G, h->mm);
     KCHECK();
-    k_shift_k1<<<(unsigned)ceil_div64(h->N, 256), 256, 0, h->stream>>>(h->U, h->mm, h->N, h->shift);
+    CA_LAUNCH(k_shift_k1, (unsigned)ceil_div64(h->N, 256), 256, 0, h->stream)(h->U, h->mm, h->N, h->shift);
     KCHECK();
   } else {
     LaunchScope ls(h, "shift");
-    k_shift_general<<<(unsigned)ceil_div64(h->N, 8), 256, 0, h->stream>>>(h->U, h->Vm, h->N, h->G, h->KP, h->shift);
+    CA_LAUNCH(k_shift_general, (unsigned)ceil_div64(h->N, 8), 256, 0, h->stream)(h->U, h->Vm, h->N, h->G, h->KP, h->shift);
     KCHECK();
   }
   {
     LaunchScope ls(h, "lse_fwd", h->interp ? 5 : 1);
     if (h->interp) {
       // K = 1: Zx[n][j] = F_j(psi_n) by piecewise Chebyshev interpolation (kernels_interp.cuh)
-      k_minmax<<<1, 1024, 0, h->stream>>>(h->U, (int)h->N, h->mm_psi);
-      k_interp_plan<<<1, 32, 0, h->stream>>>(h->mm, h->mm_psi, h->iplan);
+      CA_LAUNCH(k_minmax, 1, 1024, 0, h->stream)(h->U, (int)h->N, h->mm_psi);
+      CA_LAUNCH(k_interp_plan, 1, 32, 0, h->stream)(h->mm, h->mm_psi, h->iplan);
       dim3 gn((h->J + 31) / 32, kIMaxPanF * kIP / 8);
-      k_interp_nodes<true><<<gn, 256, 0, h->stream>>>(h->iplan, h->Vm, nullptr, h->Mx, h->G, h->J, h->ivals);
+      CA_LAUNCH(k_interp_nodes<true>, gn, 256, 0, h->stream)(h->iplan, h->Vm, nullptr, h->Mx, h->G, h->J, h->ivals);
       int64_t tot = (int64_t)kIMaxPanF * kIP * h->J;
-      k_interp_coeffs<<<(unsigned)ceil_div64(tot, 256), 256, 0, h->stream>>>(h->iplan, h->ivals, 1, kIMaxPanF, h->J, 1, h->icoef);
-      k_interp_eval<true><<<h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream>>>(h->iplan, h->icoef, h->U, h->N, h->J, h->Zx,
+      CA_LAUNCH(k_interp_coeffs, (unsigned)ceil_div64(tot, 256), 256, 0, h->stream)(h->iplan, h->ivals, 1, kIMaxPanF, h->J, 1, h->icoef);
+      CA_LAUNCH(k_interp_eval<true>, h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream)(h->iplan, h->icoef, h->U, h->N, h->J, h->Zx,
                                                                                   h->ieval_panels);
     } else if (h->tc) {
       tc_launch_fwd(h->tcplan, h->U, h->Vm, h->shift, h->Zx, h->stream);
     } else {
       int Jc = (mode == EPI_TRAIN) ? h->J : h->SC;   // ELBO-only passes need just Z
       dim3 grid((Jc + 63) / 64, (unsigned)ceil_div64(h->N, 64));
-      k_expgemm<true><<<grid, 256, 0, h->stream>>>(h->U, h->Vm, h->shift, h->Mx, h->Zx, h->N, h->G, Jc, h->J, h->KP);
+      CA_LAUNCH(k_expgemm<true>, grid, 256, 0, h->stream)(h->U, h->Vm, h->shift, h->Mx, h->Zx, h->N, h->G, Jc, h->J, h->KP);
     }
     KCHECK();
   }
@@ -408,9 +412,9 @@ void run_forward(ca_handle* h, int mode) {
     a.Fout = h->Fout; a.RxT = h->tc ? h->RxT : nullptr; a.shift_bwd = h->shift_bwd; a.elbo_part = h->elbo_part; a.gsum_part = h->gsum_part;
     size_t smem = epi_smem_bytes(h->SCp, h->C, h->J, h->tc);
     unsigned grid = (unsigned)h->n_epi_blocks;
-    if (mode == EPI_TRAIN) k_cell_epilogue<EPI_TRAIN><<<grid, kEpiWarps * 32, smem, h->stream>>>(a);
-    else if (mode == EPI_EVAL) k_cell_epilogue<EPI_EVAL><<<grid, kEpiWarps * 32, smem, h->stream>>>(a);
-    else k_cell_epilogue<EPI_INIT><<<grid, kEpiWarps * 32, smem, h->stream>>>(a);
+    if (mode == EPI_TRAIN) CA_LAUNCH(k_cell_epilogue<EPI_TRAIN>, grid, kEpiWarps * 32, smem, h->stream)(a);
+    else if (mode == EPI_EVAL) CA_LAUNCH(k_cell_epilogue<EPI_EVAL>, grid, kEpiWarps * 32, smem, h->stream)(a);
+    else CA_LAUNCH(k_cell_epilogue<EPI_INIT>, grid, kEpiWarps * 32, smem, h->stream)(a);
     KCHECK();
   }
 }
@@ -423,16 +427,16 @@ void run_train(ca_handle* h, bool apply) {
     if (h->interp) {
       // K = 1: dMx[g][j] = H_j(w_g); the plan of this step's forward pass is still valid (psi, W unchanged)
       dim3 gn((h->J + 31) / 32, kIMaxPanB * kIP / 8, kISplitB);
-      k_interp_nodes<false><<<gn, 256, 0, h->stream>>>(h->iplan, h->U, h->shift, h->Rx, h->N, h->J, h->ivals);
+      CA_LAUNCH(k_interp_nodes<false>, gn, 256, 0, h->stream)(h->iplan, h->U, h->shift, h->Rx, h->N, h->J, h->ivals);
       int64_t tot = (int64_t)kIMaxPanB * kIP * h->J;
-      k_interp_coeffs<<<(unsigned)ceil_div64(tot, 256), 256, 0, h->stream>>>(h->iplan, h->ivals, kISplitB, kIMaxPanB, h->J, 0, h->icoef);
-      k_interp_eval<false><<<h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream>>>(h->iplan, h->icoef, h->Vm, h->G, h->J, h->dMx,
+      CA_LAUNCH(k_interp_coeffs, (unsigned)ceil_div64(tot, 256), 256, 0, h->stream)(h->iplan, h->ivals, kISplitB, kIMaxPanB, h->J, 0, h->icoef);
+      CA_LAUNCH(k_interp_eval<false>, h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream)(h->iplan, h->icoef, h->Vm, h->G, h->J, h->dMx,
                                                                                    h->ieval_panels);
     } else if (h->tc) {
       tc_launch_bwd(h->tcplan, h->U, h->Vm, h->shift_bwd, h->dMx, h->stream);
     } else {
       dim3 grid((h->J + 63) / 64, (h->G + 63) / 64);
-      k_expgemm<false><<<grid, 256, 0, h->stream>>>(h->Vm, h->U, h->shift, h->Rx, h->dMx, h->G, h->N, h->J, h->J, h->KP);
+      CA_LAUNCH(k_expgemm<false>, grid, 256, 0, h->stream)(h->Vm, h->U, h->shift, h->Rx, h->dMx, h->G, h->N, h->J, h->J, h->KP);
     }
     KCHECK();
   }
@@ -442,9 +446,9 @@ void run_train(ca_handle* h, bool apply) {
     a.G = h->G; a.C = h->C; a.S = h->S; a.K = h->K; a.KP = h->KP; a.SCp = h->SCp; a.J = h->J; a.nsplit = h->nsplit; a.nRB = h->nRB;
     a.dMx = h->dMx; a.colpart = h->colpart; a.mu = h->mu; a.sig = h->sig; a.eps = h->eps; a.lsd = h->lsd; a.L = h->L;
     a.ar = h->ar; a.YtU = h->YtU; a.dM_out = h->dM_sum;
-    k_gene_grads_warp<<<(h->G + 7) / 8, 256, 0, h->stream>>>(a);
+    CA_LAUNCH(k_gene_grads_warp, (h->G + 7) / 8, 256, 0, h->stream)(a);
     KCHECK();
-    k_reduce_gsum<<<1, 1024, 0, h->stream>>>(h->gsum_part, h->n_epi_blocks, h->C, h->ar + (int64_t)h->G * (2 + h->KP));
+    CA_LAUNCH(k_reduce_gsum, 1, 1024, 0, h->stream)(h->gsum_part, h->n_epi_blocks, h->C, h->ar + (int64_t)h->G * (2 + h->KP));
     KCHECK();
   }
   if (h->cfg.world > 1) {
@@ -455,7 +459,7 @@ void run_train(ca_handle* h, bool apply) {
   {
     LaunchScope ls(h, "adam", apply ? 4 : 3);
     AdamHyper hy = adam_hyper(h, apply);
-    k_wsq<<<1, 1024, 0, h->stream>>>(h->Vm, h->G, h->K, h->KP, h->wsq);
+    CA_LAUNCH(k_wsq, 1, 1024, 0, h->stream)(h->Vm, h->G, h->K, h->KP, h->wsq);
     KCHECK();
     ScalarAdamArgs sa;
     sa.G = h->G; sa.C = h->C; sa.K = h->K; sa.n_total = (double)h->Ntot; sa.wsq = h->wsq;
@@ -468,13 +472,13 @@ void run_train(ca_handle* h, bool apply) {
     ga.m_loc = h->m_loc; ga.v_loc = h->v_loc; ga.m_lsd = h->m_lsd; ga.v_lsd = h->v_lsd; ga.m_V = h->m_V; ga.v_V = h->v_V;
     ga.g_loc = h->g_loc; ga.g_lsd = h->g_lsd; ga.g_V = h->g_V; ga.h = hy;
     // gene kernel reads chi_raw (old) -> must precede the scalar update
-    k_gene_adam<<<(h->G + 127) / 128, 128, 0, h->stream>>>(ga);
+    CA_LAUNCH(k_gene_adam, (h->G + 127) / 128, 128, 0, h->stream)(ga);
     KCHECK();
-    k_scalar_adam<<<1, 32, 0, h->stream>>>(sa);
+    CA_LAUNCH(k_scalar_adam, 1, 32, 0, h->stream)(sa);
     KCHECK();
     if (apply) {
       int64_t tot = h->N * h->C + h->N * h->KP;
-      k_cell_adam<<<(unsigned)ceil_div64(tot, 256), 256, 0, h->stream>>>(h->N, h->C, h->K, h->KP, h->t, h->m_t, h->v_t, h->g_t,
+      CA_LAUNCH(k_cell_adam, (unsigned)ceil_div64(tot, 256), 256, 0, h->stream)(h->N, h->C, h->K, h->KP, h->t, h->m_t, h->v_t, h->g_t,
                                                                        h->U, h->m_U, h->v_U, h->g_U, hy);
       KCHECK();
     }
@@ -489,10 +493,10 @@ void run_elbo_async(ca_handle* h) {
   h->launches_last_step = 0;
   run_forward(h, EPI_EVAL);
   LaunchScope ls(h, "elbo_reduce", 2);
-  k_reduce_partials<<<1, 1024, 0, h->stream>>>(h->elbo_part, h->n_epi_blocks, 1, h->cell_sum, h->const_sum);
+  CA_LAUNCH(k_reduce_partials, 1, 1024, 0, h->stream)(h->elbo_part, h->n_epi_blocks, 1, h->cell_sum, h->const_sum);
   KCHECK();
   if (h->cfg.world > 1) NCCL_OK(nccl().AllReduce(h->cell_sum, h->cell_sum, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
-  k_elbo_final<<<1, 256, 0, h->stream>>>(h->cell_sum, h->gene_part, h->n_gene_blocks, h->scal_elbo, h->poison, h->elbo_dev);
+  CA_LAUNCH(k_elbo_final, 1, 256, 0, h->stream)(h->cell_sum, h->gene_part, h->n_gene_blocks, h->scal_elbo, h->poison, h->elbo_dev);
   KCHECK();
 }
 
@@ -502,7 +506,7 @@ void upload_colmajor(ca_handle* h, const double* src, int64_t rows, int cols, fl
   double* tmp = nullptr;
   CUDA_OK(cudaMalloc(&tmp, sizeof(double) * rows * cols));
   CUDA_OK(cudaMemcpyAsync(tmp, src, sizeof(double) * rows * cols, cudaMemcpyHostToDevice, h->stream));
-  k_colmajor_to_rowmajor_f<<<(unsigned)ceil_div64(rows * cols, 256), 256, 0, h->stream>>>(tmp, rows, cols, dst, ld_dst, col_off);
+  CA_LAUNCH(k_colmajor_to_rowmajor_f, (unsigned)ceil_div64(rows * cols, 256), 256, 0, h->stream)(tmp, rows, cols, dst, ld_dst, col_off);
   KCHECK();
   CUDA_OK(cudaStreamSynchronize(h->stream));
   CUDA_OK(cudaFree(tmp));
@@ -543,7 +547,7 @@ void ingest_y(ca_handle* h, const Tin* Ysrc, float* Yf) {
         ld_in = N;
       }
       dim3 grid((unsigned)ceil_div64(N, 32), (gc + 31) / 32), blk(32, 8);
-      k_ingest_colmajor<Tin><<<grid, blk, 0, h->stream>>>(src, ld_in, N, g0, gc, Yf, h->ldY);
+      CA_LAUNCH(k_ingest_colmajor<Tin>, grid, blk, 0, h->stream)(src, ld_in, N, g0, gc, Yf, h->ldY);
       KCHECK();
       CUDA_OK(cudaStreamSynchronize(h->stream));
     }
@@ -564,7 +568,7 @@ void ingest_y(ca_handle* h, const Tin* Ysrc, float* Yf) {
         src = stage;
       }
       dim3 grid(std::min((G + 255) / 256, 64), (unsigned)rc);
-      k_ingest_rowmajor<Tin><<<grid, 256, 0, h->stream>>>(src, ld, rc, G, Yf + r0 * h->ldY, h->ldY);
+      CA_LAUNCH(k_ingest_rowmajor<Tin>, grid, 256, 0, h->stream)(src, ld, rc, G, Yf + r0 * h->ldY, h->ldY);
       KCHECK();
       CUDA_OK(cudaStreamSynchronize(h->stream));
     }
@@ -617,7 +621,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
 
   h->N = c.N; h->Ntot = c.N_total > 0 ? c.N_total : c.N; h->G = c.G; h->C = c.C; h->S = c.S; h->K = c.K; h->P = c.P;
   h->KP = c.K + c.P; h->SC = c.S * c.C; h->V = c.V;
-  bool tc_ok = (c.K == 1 && c.P == 0 && round_up64(h->SC, 16) <= 128);
+  bool tc_ok = kTcAvailable && (c.K == 1 && c.P == 0 && round_up64(h->SC, 16) <= 128);
   if (c.path == CA_PATH_TENSOR && !tc_ok) fail("tensor path needs K == 1, P == 0 and S*C <= 128");
   if (c.path == CA_PATH_INTERP && !(c.K == 1 && c.P == 0)) fail("interp path needs K == 1 and P == 0");
   h->interp = (c.path == CA_PATH_INTERP);
@@ -645,7 +649,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     // grid.y is limited to 65535: loop over row chunks
     for (int64_t r0 = 0; r0 < N; r0 += 65535) {
       grid.y = (unsigned)std::min<int64_t>(65535, N - r0);
-      k_scan_y<<<grid, 256, 0, h->stream>>>(Yf + r0 * h->ldY, h->ldY, grid.y, G, flags);
+      CA_LAUNCH(k_scan_y, grid, 256, 0, h->stream)(Yf + r0 * h->ldY, h->ldY, grid.y, G, flags);
       KCHECK();
     }
   }
@@ -678,11 +682,11 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   h->s = h->alloc<float>(N);
   h->colsum = h->alloc<float>(G);
   double* cst = h->alloc<double>(N);
-  k_setup_rows<float><<<(unsigned)N, 256, 0, h->stream>>>(Yf, h->ldY, N, G, C, d_logL, h->s, cst, h->Bm);
+  CA_LAUNCH(k_setup_rows<float>, (unsigned)N, 256, 0, h->stream)(Yf, h->ldY, N, G, C, d_logL, h->s, cst, h->Bm);
   KCHECK();
   {
     double* csum = h->alloc<double>(1);
-    k_reduce_partials<<<1, 1024, 0, h->stream>>>(cst, N, 1, csum, 0.0);
+    CA_LAUNCH(k_reduce_partials, 1, 1024, 0, h->stream)(cst, N, 1, csum, 0.0);
     KCHECK();
     CUDA_OK(cudaMemcpyAsync(&h->const_sum, csum, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -699,9 +703,9 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     const int RS = 64;
     double* part = h->alloc<double>((size_t)RS * G);
     dim3 grid((G + 127) / 128, RS);
-    k_colsum_part<float><<<grid, 128, 0, h->stream>>>(Yf, h->ldY, N, G, RS, part);
+    CA_LAUNCH(k_colsum_part<float>, grid, 128, 0, h->stream)(Yf, h->ldY, N, G, RS, part);
     KCHECK();
-    k_colsum_final<<<(G + 127) / 128, 128, 0, h->stream>>>(part, RS, G, h->colsum);
+    CA_LAUNCH(k_colsum_final, (G + 127) / 128, 128, 0, h->stream)(part, RS, G, h->colsum);
     KCHECK();
     CUDA_OK(cudaStreamSynchronize(h->stream));
     h->release(part);
@@ -714,10 +718,10 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     upload_colmajor(h, alt, N, V, d_alt, V, 0);
     upload_colmajor(h, cov, N, V, d_cov, V, 0);
     upload_colmajor(h, clone_allele, V, C, d_cn, C, 0);
-    k_allele<<<(unsigned)N, 128, 0, h->stream>>>(d_alt, d_cov, d_cn, N, V, C, h->vA);
+    CA_LAUNCH(k_allele, (unsigned)N, 128, 0, h->stream)(d_alt, d_cov, d_cn, N, V, C, h->vA);
     KCHECK();
     h->snv = h->alloc<float>((size_t)N * C);
-    k_softmax_rows<<<(unsigned)ceil_div64(N, 128), 128, 0, h->stream>>>(h->vA, N, C, h->snv);
+    CA_LAUNCH(k_softmax_rows, (unsigned)ceil_div64(N, 128), 128, 0, h->stream)(h->vA, N, C, h->snv);
     KCHECK();
     CUDA_OK(cudaStreamSynchronize(h->stream));
     h->release(d_alt);
@@ -732,8 +736,8 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     else Yn = h->alloc<uint8_t>((size_t)N * h->ldY, false);
     for (int64_t r0 = 0; r0 < N; r0 += 65535) {
       grid.y = (unsigned)std::min<int64_t>(65535, N - r0);
-      if (h->ystore == CA_STORE_U16) k_narrow_y<uint16_t><<<grid, 256, 0, h->stream>>>(Yf + r0 * h->ldY, h->ldY, grid.y, (uint16_t*)Yn + r0 * h->ldY);
-      else k_narrow_y<uint8_t><<<grid, 256, 0, h->stream>>>(Yf + r0 * h->ldY, h->ldY, grid.y, (uint8_t*)Yn + r0 * h->ldY);
+      if (h->ystore == CA_STORE_U16) CA_LAUNCH(k_narrow_y<uint16_t>, grid, 256, 0, h->stream)(Yf + r0 * h->ldY, h->ldY, grid.y, (uint16_t*)Yn + r0 * h->ldY);
+      else CA_LAUNCH(k_narrow_y<uint8_t>, grid, 256, 0, h->stream)(Yf + r0 * h->ldY, h->ldY, grid.y, (uint8_t*)Yn + r0 * h->ldY);
       KCHECK();
     }
     CUDA_OK(cudaStreamSynchronize(h->stream));

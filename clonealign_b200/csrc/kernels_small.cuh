@@ -293,7 +293,7 @@ constexpr int kEpiWarps = 16;
 
 template <int MODE>
 __global__ void __launch_bounds__(kEpiWarps * 32) k_cell_epilogue(EpiArgs a) {
-  extern __shared__ double sm[];
+  CA_DYNAMIC_SMEM(double, sm);
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int SC = a.S * a.C;
   // per-warp scratch: lz[SCp] | F[C] | gam[C] ; block scratch after that

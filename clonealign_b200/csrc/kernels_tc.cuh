@@ -42,6 +42,7 @@ constexpr int kTcBM = 128;                           // UMMA M
 constexpr int kTcBK = 64;                            // K elements per stage (one 128-byte swizzle row of 16-bit)
 constexpr float kLog2e = 1.4426950408889634f;
 
+constexpr bool kTcAvailable = true;   // false in the CPU-emulation stub (tests/cuda_emul/kernels_tc_stub.h)
 struct TcPlan {
   bool ok = false;
   int dev = 0, num_sms = 0;

@@ -25,3 +25,26 @@ def example_sce():
 @pytest.fixture(scope="session")
 def golden_c1():
     return dict(np.load(os.path.join(GOLDEN, "golden_c1.npz")))
+
+
+@pytest.fixture(scope="module")
+def emulated_library():
+    """Point the ctypes loader at the CPU-EMULATED build of the C-ABI (tests/cuda_emul/build.py) for one test module.
+
+    Test infrastructure: the real core.cu + every kernel except the tcgen05/TMA ones are compiled for the host against
+    a fiber-based emulation of the CUDA execution model, so host code, ABI and kernels can be checked against the oracle
+    without a GPU.  The product loader is restored afterwards (it only ever knows clonealign_b200/libclonealign_b200.so).
+    """
+    from clonealign_b200 import _lib
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cuda_emul"))
+    try:
+        import build as emul_build
+    finally:
+        sys.path.pop(0)
+    path = emul_build.build()
+    saved = (_lib.LIB_PATH, _lib._lib)
+    _lib.LIB_PATH, _lib._lib = path, None
+    try:
+        yield path
+    finally:
+        _lib.LIB_PATH, _lib._lib = saved

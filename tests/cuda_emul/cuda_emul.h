@@ -1,26 +1,47 @@
-// Minimal CPU emulation of the CUDA execution model for FUNCTIONAL tests of simple kernels (no tensor cores,
-// no TMA): one OS thread per CUDA thread, blocks run one after another, __syncthreads / warp shuffles via
-// std::barrier.  Test infrastructure only (tests/test_cuda_emul.py); it lets the index math, reductions and panel
-// logic of clonealign_b200/csrc/kernels_interp.cuh be checked without a GPU.
+// CPU emulation of the CUDA execution model and of the small part of the CUDA runtime that
+// clonealign_b200/csrc/core.cu uses.  TEST INFRASTRUCTURE ONLY (tests/test_cuda_emul.py, tests/test_emul_*.py):
+// the product (clonealign_b200/) never includes, links or loads anything from this directory; it exists so that the
+// kernels that need no tensor core / TMA (everything except kernels_tc.cuh) can be checked FUNCTIONALLY against the
+// oracle in a container without a GPU: index math, reductions, barrier placement, reads of uninitialised memory.
+// Hardware hazards (memory model, occupancy, performance) are of course not covered.
+//
+// Model: every CUDA thread of a block is a fiber (ucontext) on ONE OS thread; fibers run until they reach a
+// synchronisation point (__syncthreads, __syncwarp, warp shuffles) and are resumed once the barrier generation
+// advances.  Threads that return early count as arrived (as on hardware).  A block in which no fiber can make
+// progress aborts with a message (mismatched barriers).  Blocks of a grid are distributed over a few OS threads;
+// `__shared__` maps to `static thread_local`, which fibers of a block share because they never migrate.
+// Device memory is host memory: cudaMalloc fills it with 0xFF bytes (NaN floats) so that a kernel consuming memory
+// nobody wrote shows up as NaN in the parity tests.
 #pragma once
-#include <barrier>
+#include <ucontext.h>
+
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <thread>
+#include <tuple>
+#include <utility>
 #include <vector>
 
+// ------------------------------------------------------------------------------------------------------------------
+// vector types, qualifiers
+// ------------------------------------------------------------------------------------------------------------------
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
   unsigned x, y, z;
   dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
-struct float4 { float x, y, z, w; };
-struct uint4 { unsigned x, y, z, w; };
-struct uint2 { unsigned x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
 inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
+inline float2 make_float2(float a, float b) { return {a, b}; }
 inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return {a, b, c, d}; }
 inline uint2 make_uint2(unsigned a, unsigned b) { return {a, b}; }
 
@@ -30,52 +51,126 @@ inline uint2 make_uint2(unsigned a, unsigned b) { return {a, b}; }
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __maxnreg__(...)
+#define __shared__ static thread_local
 
 namespace ca_emul {
-struct BlockCtx {
-  std::barrier<> bar;
-  std::vector<std::unique_ptr<std::barrier<>>> wbar;   // one per warp
-  std::vector<uint64_t> wbuf;                          // 32 slots per warp
-  std::vector<unsigned char> dyn;
-  BlockCtx(int nthreads, size_t dyn_bytes) : bar(nthreads), wbuf((size_t)((nthreads + 31) / 32) * 32), dyn(dyn_bytes + 64) {
-    for (int w = 0; w < (nthreads + 31) / 32; ++w) {
-      int lanes = std::min(32, nthreads - w * 32);
-      wbar.emplace_back(new std::barrier<>(lanes));
-    }
-  }
+
+constexpr size_t kStackBytes = 256 * 1024;
+
+struct Warp {
+  int live = 0, count = 0;
+  unsigned gen = 0;
+  uint64_t slot[2][32];
 };
-inline thread_local BlockCtx* ctx = nullptr;
-inline thread_local int linear_tid = 0;
-inline void* dyn_smem() { return ctx->dyn.data(); }
+struct Fiber {
+  ucontext_t ctx;
+  char* stack = nullptr;
+  int tid = 0;
+  bool done = false;
+  int wait_kind = 0;        // 0 runnable, 1 block barrier, 2 warp barrier
+  unsigned wait_gen = 0;
+};
+struct Block {
+  int nthreads = 0, live = 0, bar_count = 0;
+  unsigned bar_gen = 0;
+  std::vector<Warp> warps;
+  std::vector<unsigned char> dyn;
+  uint64_t progress = 0;
+};
+
+inline thread_local Block* blk = nullptr;
+inline thread_local Fiber* fib = nullptr;
+inline thread_local ucontext_t sched;
+inline thread_local void (*entry)(void*) = nullptr;
+inline thread_local void* entry_arg = nullptr;
+
+inline void yield_to_scheduler() { swapcontext(&fib->ctx, &sched); }
+inline void* dyn_smem() { return blk->dyn.data(); }
+
+inline void block_barrier() {
+  Block* b = blk;
+  Fiber* f = fib;
+  const unsigned g = b->bar_gen;
+  if (++b->bar_count >= b->live) {
+    b->bar_count = 0;
+    b->bar_gen++;
+    b->progress++;
+    return;
+  }
+  f->wait_kind = 1;
+  f->wait_gen = g;
+  yield_to_scheduler();
+}
+// returns the generation the caller took part in
+inline unsigned warp_barrier() {
+  Block* b = blk;
+  Fiber* f = fib;
+  Warp& w = b->warps[f->tid >> 5];
+  const unsigned g = w.gen;
+  if (++w.count >= w.live) {
+    w.count = 0;
+    w.gen++;
+    b->progress++;
+    return g;
+  }
+  f->wait_kind = 2;
+  f->wait_gen = g;
+  yield_to_scheduler();
+  return g;
+}
+inline void thread_exit() {   // an exited thread counts as arrived at every later barrier
+  Block* b = blk;
+  Fiber* f = fib;
+  Warp& w = b->warps[f->tid >> 5];
+  f->done = true;
+  b->progress++;
+  b->live--;
+  w.live--;
+  if (b->live > 0 && b->bar_count >= b->live) { b->bar_count = 0; b->bar_gen++; }
+  if (w.live > 0 && w.count >= w.live) { w.count = 0; w.gen++; }
+}
+
 }  // namespace ca_emul
 
 inline thread_local uint3 threadIdx, blockIdx;
 inline thread_local dim3 blockDim, gridDim;
 
-inline void __syncthreads() { ca_emul::ctx->bar.arrive_and_wait(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { ca_emul::ctx->wbar[ca_emul::linear_tid / 32]->arrive_and_wait(); }
+inline void __syncthreads() { ca_emul::block_barrier(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { ca_emul::warp_barrier(); }
 
 template <typename T>
 inline T __shfl_sync(unsigned, T v, int src) {
   static_assert(sizeof(T) <= 8, "shuffle payload");
-  auto* c = ca_emul::ctx;
-  const int w = ca_emul::linear_tid / 32, lane = ca_emul::linear_tid % 32;
+  ca_emul::Warp& w = ca_emul::blk->warps[ca_emul::fib->tid >> 5];
+  const int lane = ca_emul::fib->tid & 31;
   uint64_t bits = 0;
   std::memcpy(&bits, &v, sizeof(T));
-  c->wbuf[(size_t)w * 32 + lane] = bits;
-  c->wbar[w]->arrive_and_wait();
-  uint64_t got = c->wbuf[(size_t)w * 32 + (src & 31)];
-  c->wbar[w]->arrive_and_wait();
+  // double-buffered by barrier generation: nobody can write generation g+2 before everyone has read generation g
+  const unsigned g = w.gen;
+  w.slot[g & 1][lane] = bits;
+  ca_emul::warp_barrier();
+  uint64_t got = w.slot[g & 1][src & 31];
   T out;
   std::memcpy(&out, &got, sizeof(T));
   return out;
 }
 template <typename T>
-inline T __shfl_xor_sync(unsigned m, T v, int mask) { return __shfl_sync(m, v, (ca_emul::linear_tid % 32) ^ mask); }
+inline T __shfl_xor_sync(unsigned m, T v, int mask) { return __shfl_sync(m, v, (ca_emul::fib->tid & 31) ^ mask); }
+template <typename T>
+inline T __shfl_down_sync(unsigned m, T v, int d) {
+  int lane = ca_emul::fib->tid & 31;
+  return __shfl_sync(m, v, lane + d < 32 ? lane + d : lane);
+}
+inline unsigned __ballot_sync(unsigned m, int pred) {
+  unsigned r = 0;
+  for (int l = 0; l < 32; ++l) r |= (unsigned)(__shfl_sync(m, pred ? 1 : 0, l) != 0) << l;
+  return r;
+}
 
 template <typename T> inline T __ldg(const T* p) { return *p; }
 template <typename T> inline T __ldcs(const T* p) { return *p; }
+template <typename T> inline void __stcs(T* p, T v) { *p = v; }
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 inline void sincospif(float x, float* s, float* c) { *s = sinf(3.14159265358979f * x); *c = cosf(3.14159265358979f * x); }
 inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
@@ -85,41 +180,200 @@ inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
   return r;
 }
 inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 inline float __fdividef(float a, float b) { return a / b; }
+inline float __expf(float a) { return expf(a); }
+inline float __logf(float a) { return logf(a); }
+inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 struct __half { unsigned short v; };
 struct __nv_bfloat16 { unsigned short v; };
-inline __half __float2half_rn(float) { return {0}; }
+inline __half __float2half_rn(float) { return {0}; }   // only the tensor path (not emulated) consumes halves
 inline __nv_bfloat16 __float2bfloat16_rn(float f) { unsigned u; std::memcpy(&u, &f, 4); return {(unsigned short)((u + 0x7fffu + ((u >> 16) & 1)) >> 16)}; }
 inline float __bfloat162float(__nv_bfloat16 b) { unsigned u = (unsigned)b.v << 16; float f; std::memcpy(&f, &u, 4); return f; }
 
 #define CA_DYNAMIC_SMEM(T, name) T* name = reinterpret_cast<T*>(ca_emul::dyn_smem())
 
+// ------------------------------------------------------------------------------------------------------------------
+// kernel launch
+// ------------------------------------------------------------------------------------------------------------------
 namespace ca_emul {
-// launch<<<grid, block, dyn_smem>>>: blocks sequentially, threads of a block concurrently
+
+inline void fiber_main() {
+  entry(entry_arg);
+  thread_exit();
+  setcontext(&sched);   // never returns here
+}
+
+struct StackPool {
+  std::vector<char*> all;
+  ~StackPool() { for (char* p : all) free(p); }
+  char* get(size_t i) {
+    while (all.size() <= i) all.push_back((char*)malloc(kStackBytes));
+    return all[i];
+  }
+};
+
+inline void run_block(void (*body)(void*), void* body_arg, dim3 grid, dim3 block, size_t dyn_bytes, unsigned bx, unsigned by,
+                      unsigned bz, StackPool& pool) {
+  const int nthreads = (int)(block.x * block.y * block.z);
+  Block b;
+  b.nthreads = b.live = nthreads;
+  b.warps.resize((nthreads + 31) / 32);
+  for (int w = 0; w < (int)b.warps.size(); ++w) b.warps[w].live = std::min(32, nthreads - w * 32);
+  b.dyn.assign(dyn_bytes + 64, 0xFF);
+  std::vector<Fiber> fibers(nthreads);
+  blk = &b;
+  blockIdx = {bx, by, bz};
+  blockDim = block;
+  gridDim = grid;
+  entry = body;
+  entry_arg = body_arg;
+  for (int t = 0; t < nthreads; ++t) {
+    Fiber& f = fibers[t];
+    f.tid = t;
+    f.stack = pool.get(t);
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack;
+    f.ctx.uc_stack.ss_size = kStackBytes;
+    f.ctx.uc_link = nullptr;
+    makecontext(&f.ctx, (void (*)())fiber_main, 0);
+  }
+  int remaining = nthreads;
+  while (remaining > 0) {
+    const uint64_t before = b.progress;
+    bool ran = false;
+    for (int t = 0; t < nthreads; ++t) {
+      Fiber& f = fibers[t];
+      if (f.done) continue;
+      if (f.wait_kind == 1 && b.bar_gen == f.wait_gen) continue;
+      if (f.wait_kind == 2 && b.warps[t >> 5].gen == f.wait_gen) continue;
+      f.wait_kind = 0;
+      fib = &f;
+      threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+      ran = true;
+      swapcontext(&sched, &f.ctx);
+      if (f.done) --remaining;
+    }
+    if (remaining > 0 && (!ran || b.progress == before)) {
+      fprintf(stderr, "cuda_emul: dead-lock in block (%u,%u,%u): %d threads wait at barriers that can never complete\n",
+              bx, by, bz, remaining);
+      abort();
+    }
+  }
+  blk = nullptr;
+  fib = nullptr;
+}
+
+inline int host_workers() {
+  static int n = [] {
+    const char* e = getenv("CA_EMUL_THREADS");
+    int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    return v < 1 ? 1 : (v > 16 ? 16 : v);
+  }();
+  return n;
+}
+
 template <typename K, typename... A>
 void launch(K kernel, dim3 grid, dim3 block, size_t dyn_bytes, A... args) {
-  const int nthreads = (int)(block.x * block.y * block.z);
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        BlockCtx c(nthreads, dyn_bytes);
-        std::vector<std::thread> ts;
-        ts.reserve(nthreads);
-        for (int t = 0; t < nthreads; ++t)
-          ts.emplace_back([&, t]() {
-            ctx = &c;
-            linear_tid = t;
-            threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-            blockIdx = {bx, by, bz};
-            blockDim = block;
-            gridDim = grid;
-            kernel(args...);
-            // a thread that returns early must not dead-lock the others: drop out of the block barrier
-            c.bar.arrive_and_drop();
-            c.wbar[t / 32]->arrive_and_drop();
-          });
-        for (auto& th : ts) th.join();
-      }
+  const uint64_t nblocks = (uint64_t)grid.x * grid.y * grid.z;
+  if (nblocks == 0 || block.x * block.y * block.z == 0) return;
+  struct Call {
+    K kernel;
+    std::tuple<A...> tup;
+  } call{kernel, std::make_tuple(args...)};
+  void (*body)(void*) = [](void* c) {
+    Call* k = static_cast<Call*>(c);
+    std::apply(k->kernel, k->tup);
+  };
+  std::atomic<uint64_t> next{0};
+  auto worker = [&]() {
+    StackPool pool;
+    for (;;) {
+      uint64_t i = next.fetch_add(1);
+      if (i >= nblocks) break;
+      unsigned bx = (unsigned)(i % grid.x), by = (unsigned)((i / grid.x) % grid.y), bz = (unsigned)(i / ((uint64_t)grid.x * grid.y));
+      run_block(body, &call, grid, block, dyn_bytes, bx, by, bz, pool);
+    }
+  };
+  const int nw = (int)std::min<uint64_t>(nblocks, (uint64_t)host_workers());
+  if (nw <= 1) {
+    worker();
+  } else {
+    std::vector<std::thread> ts;
+    for (int i = 0; i < nw; ++i) ts.emplace_back(worker);
+    for (auto& t : ts) t.join();
+  }
 }
+
+// CA_LAUNCH(kernel, grid, block, smem, stream)(args...) under emulation
+template <typename K>
+struct Launcher {
+  K kernel;
+  dim3 grid, block;
+  size_t smem;
+  template <typename... A>
+  void operator()(A... args) const { launch(kernel, grid, block, smem, args...); }
+};
+template <typename K>
+Launcher<K> launcher(K kernel, dim3 grid, dim3 block, size_t smem) { return {kernel, grid, block, smem}; }
+
 }  // namespace ca_emul
+
+#define CA_LAUNCH(kernel, grid, block, smem, stream) ca_emul::launcher(kernel, dim3(grid), dim3(block), (size_t)(smem))
+
+// ------------------------------------------------------------------------------------------------------------------
+// the part of the CUDA runtime API that core.cu uses (synchronous, host memory)
+// ------------------------------------------------------------------------------------------------------------------
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1 };
+typedef struct ca_emul_stream* cudaStream_t;
+struct ca_emul_event { std::chrono::steady_clock::time_point t; };
+typedef ca_emul_event* cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
+struct cudaDeviceProp { int major, minor, multiProcessorCount; };
+
+inline const char* cudaGetErrorName(cudaError_t e) { return e ? "cudaErrorEmulated" : "cudaSuccess"; }
+inline const char* cudaGetErrorString(cudaError_t e) { return e ? "emulated failure" : "no error"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
+  const char* e = getenv("CA_EMUL_SMS");
+  *p = {10, 0, e ? atoi(e) : 3};
+  return cudaSuccess;
+}
+inline cudaError_t cudaMalloc(void** p, size_t bytes) {
+  *p = aligned_alloc(256, (bytes + 255) / 256 * 256);
+  if (!*p) return cudaErrorInvalidValue;
+  memset(*p, 0xFF, bytes);
+  return cudaSuccess;
+}
+template <typename T> inline cudaError_t cudaMalloc(T** p, size_t bytes) { return cudaMalloc((void**)p, bytes); }
+inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height,
+                                     cudaMemcpyKind, cudaStream_t) {
+  for (size_t r = 0; r < height; ++r) memcpy((char*)d + r * dpitch, (const char*)s + r * spitch, width);
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)malloc(1); return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new ca_emul_event(); return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+  *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+  return cudaSuccess;
+}
+template <typename K> inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }

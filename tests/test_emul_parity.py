@@ -1,0 +1,218 @@
+"""CPU parity tests THROUGH THE C-ABI on the emulated build (tests/cuda_emul/): the same checks as
+tests/test_gpu_parity.py, for the kernels that need no tensor core (paths "cudacore" and "interp"), run in this
+container without a GPU.  What is exercised is the real core.cu (ingest, set-up, launch sequences, Adam, ABI) and the
+real kernel sources compiled for the host; what is NOT covered is the tcgen05 path and anything hardware-specific.
+The oracle is the checker, exactly as on the GPU.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import clonealign_oracle as O
+from test_gpu_parity import ELBO_RTOL, PARAM_RTOL, _case, _check_grads, _load_params, _relmax, _run_trace, _session
+
+pytestmark = pytest.mark.usefixtures("emulated_library")
+PATHS = ["cudacore", "interp"]
+
+
+def test_emulated_library_is_not_the_product(emulated_library):
+    from clonealign_b200 import _lib
+    assert "cuda_emul" in emulated_library and "cuda_emul" in _lib.LIB_PATH
+    with _session(np.ones((4, 3)), np.ones((3, 2)), np.zeros((4, 1)), np.ones(3), path="auto") as sess:
+        assert sess.describe()["path"] == "cudacore"            # tcgen05 is unavailable under emulation
+    from clonealign_b200._lib import CloneAlignLibraryError
+    with pytest.raises(CloneAlignLibraryError, match="not available under the CPU emulation|tensor path"):
+        _session(np.ones((4, 3)), np.ones((3, 2)), np.zeros((4, 1)), np.ones(3), path="tensor")
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("S", [1, 3])
+def test_gradients_and_elbo_match_oracle_c1(example_sce, path, S):
+    Y, L = example_sce
+    d, p, mu_guess, _ = _case(Y, L, K=1, seed=S)
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path=path, seed=1) as sess:
+        assert sess.describe()["path"] == path
+        _load_params(sess, p)
+        errs = _check_grads(sess, d, p, S)
+        assert errs["Z"] < 1e-5
+
+
+@pytest.mark.parametrize("K,P,use_v", [(2, 1, True), (0, 0, False), (1, 2, False), (3, 0, True)])
+def test_general_path_covariates_allele(example_sce, K, P, use_v):
+    Y, L = example_sce
+    d, p, mu_guess, al = _case(Y[:60], L, K=K, P=P, use_v=use_v, seed=K * 7 + P)
+    kw = dict(al) if use_v else {}
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=2, K=K, x=d.X, path="cudacore", seed=1, **kw) as sess:
+        if use_v:
+            assert _relmax(sess.get_array("v"), d.v) < 1e-5
+        _load_params(sess, p)
+        _check_grads(sess, d, p, 2)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("N,G,C,S", [(130, 70, 5, 3), (257, 193, 2, 1), (64, 640, 7, 8), (33, 2100, 3, 2)])
+def test_ragged_shapes(path, N, G, C, S):
+    from clonealign_b200.synthetic import make_synthetic
+    syn = make_synthetic(N, G, C, seed=N + G)
+    d, p, mu_guess, _ = _case(syn["Y"].astype(np.float64), np.minimum(syn["L"], 6.0), K=1, seed=N)
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path=path, seed=1) as sess:
+        _load_params(sess, p)
+        _check_grads(sess, d, p, S)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_wide_exponent_range(example_sce, path):
+    """psi scaled up: several interpolation panels on each side / large row shifts."""
+    Y, L = example_sce
+    d, p, mu_guess, _ = _case(Y, L, K=1, seed=5, scale=1.0)
+    p.psi *= 2.0
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=2, K=1, path=path, seed=1) as sess:
+        _load_params(sess, p)
+        _check_grads(sess, d, p, 2)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_one_sided_psi(example_sce, path):
+    """All psi >= 0 / all psi < 0: one side of the forward panel structure is empty."""
+    Y, L = example_sce
+    for sign in (+1.0, -1.0):
+        d, p, mu_guess, _ = _case(Y[:80], L, K=1, seed=9)
+        p.psi = sign * np.abs(p.psi) - sign * 1e-3
+        with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=1, K=1, path=path, seed=1) as sess:
+            _load_params(sess, p)
+            _check_grads(sess, d, p, 1)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_allele_fused(example_sce, path):
+    Y, L = example_sce
+    d, p, mu_guess, al = _case(Y, L, K=1, use_v=True, seed=21)
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=1, K=1, path=path, seed=1, **al) as sess:
+        _load_params(sess, p)
+        _check_grads(sess, d, p, 1)
+        snv = sess.params()["clone_probs_from_snv"]
+        ref = np.exp(d.v - np.logaddexp.reduce(d.v, axis=1, keepdims=True))
+        assert np.abs(snv - ref).max() < 1e-5
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("S", [1, 3])
+def test_loop_matches_golden(example_sce, golden_c1, path, S):
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=None)
+    eps = golden_c1[f"eps_S{S}"]
+    with _session(hi["Y"], hi["L"], golden_c1["psi_init"], golden_c1["mu_guess"], mc_samples=S, K=1, path=path,
+                  learning_rate=0.1, seed=3) as sess:
+        sess.set_eps(eps)
+        sess.init_gamma()
+        elbos = [sess.elbo()]
+        for _ in range(5):
+            sess.step()
+            elbos.append(sess.elbo())
+        final = [sess.elbo() for _ in range(3)]
+        prm = sess.params()
+    ref = golden_c1[f"elbos_S{S}"]
+    assert (np.abs(np.array(elbos) - ref) / np.abs(ref)).max() <= ELBO_RTOL, (elbos, ref)
+    assert abs(np.mean(final) - golden_c1[f"final_elbo_S{S}"]) <= ELBO_RTOL * abs(golden_c1[f"final_elbo_S{S}"])
+    names = ["A", "B", "C"]
+    assert O.clone_assignment(prm["clone_probs"], names) == O.clone_assignment(golden_c1[f"clone_probs_S{S}"], names)
+    assert np.abs(prm["clone_probs"] - golden_c1[f"clone_probs_S{S}"]).max() <= 2e-3
+    assert _relmax(prm["mu"], golden_c1[f"mu_S{S}"]) <= PARAM_RTOL
+    assert _relmax(prm["W"], golden_c1[f"W_S{S}"]) <= 5e-3
+    assert _relmax(prm["psi"], golden_c1[f"psi_S{S}"]) <= PARAM_RTOL
+    assert _relmax(prm["alpha"], golden_c1[f"alpha_S{S}"]) <= PARAM_RTOL
+    np.testing.assert_allclose(prm["s"], hi["s"], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_loop_with_device_rng_matches_oracle(example_sce, path):
+    """Philox draws made by the kernels fed back to the oracle: reference loop semantics (fresh draw per run)."""
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(5))
+    d = O.Data(hi["Y"], hi["L"])
+    S, draws = 2, []
+    with _session(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], mc_samples=S, K=1, seed=99, path=path) as sess:
+        def rec():
+            draws.append(sess.get_eps().astype(np.float64))
+        sess.init_gamma(); rec()
+        elbos = [sess.elbo()]; rec()
+        for _ in range(4):
+            sess.step(); rec()
+            elbos.append(sess.elbo()); rec()
+        prm = sess.params()
+    allz = np.concatenate([x.ravel() for x in draws])
+    assert abs(allz.mean()) < 0.08 and abs(allz.std() - 1.0) < 0.08
+    assert len({x.tobytes() for x in draws}) == len(draws)
+    it = iter(draws)
+    p0 = O.init_params(d.Y, d.L, hi["psi_init"], hi["mu_guess"])
+    r = O.fit(d, p0, lambda: next(it), max_iter=4, rel_tol=0.0, n_final=0)
+    assert (np.abs(np.array(elbos) - r["elbos"]) / np.abs(r["elbos"])).max() <= ELBO_RTOL
+    names = ["A", "B", "C"]
+    assert O.clone_assignment(prm["clone_probs"], names) == O.clone_assignment(r["clone_probs"], names)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_same_seed_bitwise_identical(example_sce, path):
+    """tests/testthat/test_clonealign.R:42-66 (fixed-order reductions: also independent of the host thread count)."""
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
+    a, ga = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], n=3, mc_samples=2, seed=12345, path=path)
+    b, gb = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], n=3, mc_samples=2, seed=12345, path=path)
+    c, _ = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], n=3, mc_samples=2, seed=54321, path=path)
+    assert a.tobytes() == b.tobytes() and ga.tobytes() == gb.tobytes()
+    assert a.tobytes() != c.tobytes()
+
+
+def test_storage_formats_and_input_layouts_agree(example_sce):
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
+    run = lambda y, **kw: _run_trace(y, hi["L"], hi["psi_init"], hi["mu_guess"], n=2, seed=7, **kw)[0]
+    traces = [run(hi["Y"], y_store=s) for s in ("f32", "u16", "u8")]
+    assert traces[0].tobytes() == traces[1].tobytes() == traces[2].tobytes()
+    t_f = run(np.asfortranarray(hi["Y"]), y_store="f32")                    # an R double matrix
+    t_i = run(np.asfortranarray(hi["Y"].astype(np.int32)))                  # an R integer matrix
+    t_32 = run(hi["Y"].astype(np.float32))
+    assert traces[0].tobytes() == t_f.tobytes() == t_i.tobytes() == t_32.tobytes()
+    from clonealign_b200._lib import CloneAlignLibraryError
+    with pytest.raises(CloneAlignLibraryError, match="u8"):
+        run(hi["Y"] + 0.5, y_store="u8")
+    big = hi["Y"].copy()
+    big[0, 0] = 300.0
+    with _session(big, hi["L"], hi["psi_init"], hi["mu_guess"]) as sess:
+        assert sess.describe()["y_store"] == "u16"
+    big[0, 0] = 70000.0
+    with _session(big, hi["L"], hi["psi_init"], hi["mu_guess"]) as sess:
+        assert sess.describe()["y_store"] == "f32"
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference-facing API over the emulated ABI (mirrors tests/testthat/test_clonealign.R)
+# ---------------------------------------------------------------------------------------------------
+def test_clonealign_returns_valid_object(example_sce):
+    from clonealign_b200 import clonealign
+    Y, L = example_sce
+    N, G = Y.shape
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cal = clonealign(Y, L, max_iter=5, clone_names=["A", "B", "C"], verbose=False, seed=1)
+    assert len(cal["clone"]) == N and set(cal["clone"]) <= {"A", "B", "C", "unassigned"}
+    assert cal["ml_params"]["clone_probs"].shape == (N, 3)
+    assert len(cal["retained_genes"]) == len(cal["ml_params"]["mu"]) <= G
+    assert {"clone", "convergence_info", "retained_genes", "correlations", "ml_params"} <= set(cal)
+    assert len(cal["convergence_info"]["elbo"]) == 6
+    np.testing.assert_allclose(cal["ml_params"]["clone_probs"].sum(1), 1.0, atol=1e-6)
+
+
+def test_seed_setting_works_and_na_paths(example_sce):
+    from clonealign_b200 import clonealign, inference_tflow
+    Y, L = example_sce
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = clonealign(Y, L, max_iter=3, verbose=False, seed=12345)
+        b = clonealign(Y, L, max_iter=3, verbose=False, seed=12345)
+    assert a["convergence_info"]["final_elbo"] == b["convergence_info"]["final_elbo"]
+    L0 = L.copy()
+    L0[3, 1] = 0.0
+    with pytest.raises(ValueError, match="Initial elbo is NA"):
+        inference_tflow(Y, L0, max_iter=2, verbose=False, seed=1)
