@@ -16,7 +16,8 @@ Y_COLMAJOR, Y_ROWMAJOR = 0, 1
 Y_HOST, Y_DEVICE = 0, 1
 STORE_AUTO, STORE_F32, STORE_U16, STORE_U8 = 0, 1, 2, 3
 PATH_AUTO, PATH_CUDACORE, PATH_TENSOR, PATH_INTERP = 0, 1, 2, 3
-ABI_VERSION = 1
+VAR_YPASS2, VAR_EPI2 = 1, 2
+ABI_VERSION = 2
 
 EXPORTS = (
     "ca_core_abi_version", "ca_core_device_count", "ca_core_nccl_unique_id", "ca_core_create",
@@ -33,7 +34,7 @@ class CaConfig(C.Structure):
         ("learning_rate", C.c_double), ("seed", C.c_uint64),
         ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
         ("y_dtype", C.c_int32), ("y_layout", C.c_int32), ("y_mem", C.c_int32), ("y_store", C.c_int32),
-        ("path", C.c_int32), ("y_ld", C.c_int64), ("nccl_id", C.c_void_p),
+        ("path", C.c_int32), ("y_ld", C.c_int64), ("nccl_id", C.c_void_p), ("variants", C.c_uint32),
     ]
 
 

@@ -20,6 +20,7 @@
 #include "../../include/clonealign_b200.h"
 #include "common.cuh"
 #include "kernels_expgemm.cuh"
+#include "kernels_fused.cuh"
 #include "kernels_interp.cuh"
 #include "kernels_small.cuh"
 #ifdef CA_EMULATE   // tests/cuda_emul: functional CPU emulation of the non-tensor kernels (test infrastructure only)
@@ -181,6 +182,11 @@ struct ca_handle {
   int G = 0, C = 0, S = 0, K = 0, P = 0, KP = 0, SC = 0, SCp = 0, J = 0, V = 0;
   bool tc = false;
   bool interp = false;             // K = 1 univariate-interpolation path (kernels_interp.cuh)
+  uint32_t variants = 0;           // enum ca_variant bits
+  bool epi2 = false;               // interp path: fused Clenshaw + per-cell epilogue (kernels_fused.cuh)
+  int fused_nj = 0, fused_panels = 0;
+  size_t fused_smem = 0;
+  int64_t n_cell_parts = 0;        // per-block ELBO / sum-gamma partials written by the per-cell kernel in use
   InterpPlan* iplan = nullptr;
   float* mm_psi = nullptr;
   double *ivals = nullptr, *icoef = nullptr;
@@ -212,6 +218,7 @@ struct ca_handle {
   int nCB = 1, nRB = 1, RB = 512, n_gene_blocks = 0, nsplit = 1;
   int64_t n_epi_blocks = 0;
   bool ydirty = true;
+  bool inspect = false;            // test hook (ca_core_grads): also write inspection-only arrays (Z of the fused kernel)
   TcPlan tcplan;
 
   std::vector<float> eps_queue;   // host-fed draws, S*G floats each
@@ -292,7 +299,9 @@ void run_ypass(ca_handle* h, cudaStream_t st) {
     if (h->KP == 1) {
       LaunchScope ls(h, "ypass");
       dim3 grid(h->nCB, h->nRB);
-      if (st == h->stream && !getenv("CLONEALIGN_B200_YPASS_LIGHT")) {
+      if (st == h->stream && (h->variants & CA_VAR_YPASS2)) {
+        CA_LAUNCH(k_ypass_k1_v2<T>, grid, 256, 0, st)(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
+      } else if (st == h->stream && !getenv("CLONEALIGN_B200_YPASS_LIGHT")) {
         CA_LAUNCH(k_ypass_k1<T>, grid, 256, 0, st)(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
       } else {
         int64_t tiles = (int64_t)h->nCB * h->nRB;
@@ -336,6 +345,29 @@ void stage_eps(ca_handle* h, const float** eps_in) {
   }
 }
 
+template <int MODE>
+void launch_fused_mode(ca_handle* h, const FusedArgs& a) {
+  const unsigned grid = (unsigned)h->n_cell_parts;
+  switch (h->fused_nj) {
+    case 1: { auto k = k_cell_fused<MODE, 1>; CA_LAUNCH(k, grid, kFusedWarps * 32, h->fused_smem, h->stream)(a); break; }
+    case 2: { auto k = k_cell_fused<MODE, 2>; CA_LAUNCH(k, grid, kFusedWarps * 32, h->fused_smem, h->stream)(a); break; }
+    case 3: { auto k = k_cell_fused<MODE, 3>; CA_LAUNCH(k, grid, kFusedWarps * 32, h->fused_smem, h->stream)(a); break; }
+    case 4: { auto k = k_cell_fused<MODE, 4>; CA_LAUNCH(k, grid, kFusedWarps * 32, h->fused_smem, h->stream)(a); break; }
+    default: fail("fused per-cell kernel: unsupported S*C");
+  }
+}
+void launch_fused(ca_handle* h, int mode, const FusedArgs& a) {
+  if (mode == EPI_TRAIN) launch_fused_mode<EPI_TRAIN>(h, a);
+  else if (mode == EPI_EVAL) launch_fused_mode<EPI_EVAL>(h, a);
+  else launch_fused_mode<EPI_INIT>(h, a);
+}
+template <int NJ>
+void fused_set_smem(size_t smem) {
+  CUDA_OK(cudaFuncSetAttribute(k_cell_fused<EPI_TRAIN, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_OK(cudaFuncSetAttribute(k_cell_fused<EPI_EVAL, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_OK(cudaFuncSetAttribute(k_cell_fused<EPI_INIT, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+
 void run_forward(ca_handle* h, int mode) {
   const float* eps_in;
   stage_eps(h, &eps_in);
@@ -369,18 +401,20 @@ void run_forward(ca_handle* h, int mode) {
   if (h->KP == 0) {
     CUDA_OK(cudaMemsetAsync(h->shift, 0, sizeof(float) * h->N, h->stream));
   } else if (h->K == 1 && h->P == 0) {
-    LaunchScope ls(h, "shift", 2);
+    LaunchScope ls(h, "shift", h->epi2 ? 1 : 2);
     CA_LAUNCH(k_minmax, 1, 1024, 0, h->stream)(h->Vm, h->G, h->mm);
     KCHECK();
-    CA_LAUNCH(k_shift_k1, (unsigned)ceil_div64(h->N, 256), 256, 0, h->stream)(h->U, h->mm, h->N, h->shift);
-    KCHECK();
+    if (!h->epi2) {   // EPI2 computes m_n inside the fused per-cell kernel
+      CA_LAUNCH(k_shift_k1, (unsigned)ceil_div64(h->N, 256), 256, 0, h->stream)(h->U, h->mm, h->N, h->shift);
+      KCHECK();
+    }
   } else {
     LaunchScope ls(h, "shift");
     CA_LAUNCH(k_shift_general, (unsigned)ceil_div64(h->N, 8), 256, 0, h->stream)(h->U, h->Vm, h->N, h->G, h->KP, h->shift);
     KCHECK();
   }
   {
-    LaunchScope ls(h, "lse_fwd", h->interp ? 5 : 1);
+    LaunchScope ls(h, "lse_fwd", h->interp ? (h->epi2 ? 4 : 5) : 1);
     if (h->interp) {
       // K = 1: Zx[n][j] = F_j(psi_n) by piecewise Chebyshev interpolation (kernels_interp.cuh)
       CA_LAUNCH(k_minmax, 1, 1024, 0, h->stream)(h->U, (int)h->N, h->mm_psi);
@@ -389,8 +423,9 @@ void run_forward(ca_handle* h, int mode) {
       CA_LAUNCH(k_interp_nodes<true>, gn, 256, 0, h->stream)(h->iplan, h->Vm, nullptr, h->Mx, h->G, h->J, h->ivals);
       int64_t tot = (int64_t)kIMaxPanF * kIP * h->J;
       CA_LAUNCH(k_interp_coeffs, (unsigned)ceil_div64(tot, 256), 256, 0, h->stream)(h->iplan, h->ivals, 1, kIMaxPanF, h->J, 1, h->icoef);
-      CA_LAUNCH(k_interp_eval<true>, h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream)(h->iplan, h->icoef, h->U, h->N, h->J, h->Zx,
-                                                                                  h->ieval_panels);
+      if (!h->epi2)
+        CA_LAUNCH(k_interp_eval<true>, h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream)(h->iplan, h->icoef, h->U, h->N, h->J, h->Zx,
+                                                                                    h->ieval_panels);
     } else if (h->tc) {
       tc_launch_fwd(h->tcplan, h->U, h->Vm, h->shift, h->Zx, h->stream);
     } else {
@@ -402,7 +437,18 @@ void run_forward(ca_handle* h, int mode) {
   }
   if (joined_later) CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   else if (mode != EPI_INIT) run_ypass(h, h->stream);
-  {
+  if (h->epi2) {
+    LaunchScope ls(h, mode == EPI_TRAIN ? "cell_epilogue" : (mode == EPI_EVAL ? "cell_epilogue_eval" : "gamma_init"));
+    FusedArgs a;
+    a.N = h->N; a.C = h->C; a.S = h->S; a.SC = h->SC; a.J = h->J; a.nCB = h->nCB; a.smem_panels = h->fused_panels;
+    a.plan = h->iplan; a.coeff = h->icoef; a.mm = h->mm;
+    a.U = h->U; a.Bm = h->Bm; a.vA = h->vA; a.s = h->s; a.log_alpha = h->log_alpha; a.rowpart = h->rowpart;
+    a.t = h->t; a.gT = h->g_t; a.Rx = h->Rx; a.gU = h->g_U; a.YV = h->YV; a.Fout = h->Fout; a.shift = h->shift;
+    a.Zx = h->inspect ? h->Zx : nullptr;
+    a.elbo_part = h->elbo_part; a.gsum_part = h->gsum_part;
+    launch_fused(h, mode, a);
+    KCHECK();
+  } else {
     LaunchScope ls(h, mode == EPI_TRAIN ? "cell_epilogue" : (mode == EPI_EVAL ? "cell_epilogue_eval" : "gamma_init"));
     EpiArgs a;
     a.N = h->N; a.Nld = h->Nld; a.C = h->C; a.S = h->S; a.SCp = h->SCp; a.J = h->J; a.K = h->K; a.KP = h->KP; a.nCB = h->nCB;
@@ -448,7 +494,7 @@ void run_train(ca_handle* h, bool apply) {
     a.ar = h->ar; a.YtU = h->YtU; a.dM_out = h->dM_sum;
     CA_LAUNCH(k_gene_grads_warp, (h->G + 7) / 8, 256, 0, h->stream)(a);
     KCHECK();
-    CA_LAUNCH(k_reduce_gsum, 1, 1024, 0, h->stream)(h->gsum_part, h->n_epi_blocks, h->C, h->ar + (int64_t)h->G * (2 + h->KP));
+    CA_LAUNCH(k_reduce_gsum, 1, 1024, 0, h->stream)(h->gsum_part, h->n_cell_parts, h->C, h->ar + (int64_t)h->G * (2 + h->KP));
     KCHECK();
   }
   if (h->cfg.world > 1) {
@@ -493,7 +539,7 @@ void run_elbo_async(ca_handle* h) {
   h->launches_last_step = 0;
   run_forward(h, EPI_EVAL);
   LaunchScope ls(h, "elbo_reduce", 2);
-  CA_LAUNCH(k_reduce_partials, 1, 1024, 0, h->stream)(h->elbo_part, h->n_epi_blocks, 1, h->cell_sum, h->const_sum);
+  CA_LAUNCH(k_reduce_partials, 1, 1024, 0, h->stream)(h->elbo_part, h->n_cell_parts, 1, h->cell_sum, h->const_sum);
   KCHECK();
   if (h->cfg.world > 1) NCCL_OK(nccl().AllReduce(h->cell_sum, h->cell_sum, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
   CA_LAUNCH(k_elbo_final, 1, 256, 0, h->stream)(h->cell_sum, h->gene_part, h->n_gene_blocks, h->scal_elbo, h->poison, h->elbo_dev);
@@ -625,6 +671,14 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if (c.path == CA_PATH_TENSOR && !tc_ok) fail("tensor path needs K == 1, P == 0 and S*C <= 128");
   if (c.path == CA_PATH_INTERP && !(c.K == 1 && c.P == 0)) fail("interp path needs K == 1 and P == 0");
   h->interp = (c.path == CA_PATH_INTERP);
+  h->variants = c.variants;
+  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2)) fail("unknown kernel variant bits 0x%x", c.variants);
+  if ((c.variants & CA_VAR_YPASS2) && c.K + c.P != 1) fail("variant ypass2 needs K + P == 1");
+  if (c.variants & CA_VAR_EPI2) {
+    if (!h->interp) fail("variant epi2 belongs to the interp path (path = interp)");
+    if (c.C > kFusedMaxC || c.S * c.C > 32 * kFusedMaxNJ) fail("variant epi2 needs C <= %d and S*C <= %d", kFusedMaxC, 32 * kFusedMaxNJ);
+    h->epi2 = true;
+  }
   h->tc = !h->interp && ((c.path == CA_PATH_TENSOR) || (c.path == CA_PATH_AUTO && tc_ok));
   h->SCp = h->tc ? (int)round_up64(h->SC, 16) : h->SC;
   h->J = h->SCp * (1 + h->KP);
@@ -770,9 +824,10 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   h->dM_sum = z((size_t)G * J);
   h->n_gene_blocks = (G + 255) / 256;
   h->n_epi_blocks = ceil_div64(N, kEpiWarps);
+  h->n_cell_parts = h->epi2 ? (int64_t)h->num_sms : h->n_epi_blocks;
   h->gene_part = h->alloc<double>(h->n_gene_blocks);
-  h->elbo_part = h->alloc<double>(h->n_epi_blocks);
-  h->gsum_part = h->alloc<double>((size_t)h->n_epi_blocks * C);
+  h->elbo_part = h->alloc<double>(h->n_cell_parts);
+  h->gsum_part = h->alloc<double>((size_t)h->n_cell_parts * C);
   h->scal_elbo = h->alloc<double>(1); h->cell_sum = h->alloc<double>(1); h->wsq = h->alloc<double>(std::max(K, 1));
   h->elbo_dev = h->alloc<double>(1);
   h->ar = z((size_t)G * (2 + KP) + C + 4);
@@ -819,6 +874,21 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     if (h->ieval_smem > 48 * 1024) {
       CUDA_OK(cudaFuncSetAttribute(k_interp_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ieval_smem));
       CUDA_OK(cudaFuncSetAttribute(k_interp_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ieval_smem));
+    }
+  }
+  if (h->epi2) {
+    h->fused_nj = (h->SC + 31) / 32;
+    h->fused_panels = fused_smem_panels(h->SC, C, J);
+    if (const char* e = getenv("CLONEALIGN_B200_FUSED_PANELS"))   // test hook: force the coefficients-through-L2 branch
+      h->fused_panels = std::max(0, std::min(h->fused_panels, atoi(e)));
+    h->fused_smem = fused_smem_bytes(h->SC, C, J, h->fused_panels);
+    if (h->fused_smem > 48 * 1024) {
+      switch (h->fused_nj) {
+        case 1: fused_set_smem<1>(h->fused_smem); break;
+        case 2: fused_set_smem<2>(h->fused_smem); break;
+        case 3: fused_set_smem<3>(h->fused_smem); break;
+        default: fused_set_smem<4>(h->fused_smem); break;
+      }
     }
   }
   size_t smem = epi_smem_bytes(h->SCp, C, J, h->tc);
@@ -952,7 +1022,9 @@ int ca_core_grads(ca_handle* h, char* err, size_t errlen) {
   try {
     if (!h) fail("null handle");
     CUDA_OK(cudaSetDevice(h->dev));
+    h->inspect = true;
     run_train(h, false);
+    h->inspect = false;
     CUDA_OK(cudaStreamSynchronize(h->stream));
     return 0;
   } catch (const std::exception& e) { return report(e, err, errlen); }
@@ -1120,9 +1192,9 @@ int ca_core_describe(ca_handle* h, char* json, size_t json_len) {
   snprintf(json, json_len,
            "{\"N\": %lld, \"G\": %d, \"C\": %d, \"S\": %d, \"K\": %d, \"P\": %d, \"path\": \"%s\", \"y_store\": \"%s\", "
            "\"y_bytes_per_entry\": %d, \"ldY\": %lld, \"launches_last_step\": %d, \"nsplit\": %d, \"fsplit\": %d, "
-           "\"SCp\": %d, \"J\": %d, \"world\": %d, \"rank\": %d}",
+           "\"SCp\": %d, \"J\": %d, \"world\": %d, \"rank\": %d, \"variants\": %u}",
            (long long)h->N, h->G, h->C, h->S, h->K, h->P, h->interp ? "interp" : (h->tc ? "tcgen05" : "cudacore"), st, bpe, (long long)h->ldY,
-           h->launches_last_step, h->nsplit, h->tc ? h->tcplan.fsplit : 1, h->SCp, h->J, h->cfg.world, h->cfg.rank);
+           h->launches_last_step, h->nsplit, h->tc ? h->tcplan.fsplit : 1, h->SCp, h->J, h->cfg.world, h->cfg.rank, h->variants);
   return 0;
 }
 

@@ -4,7 +4,7 @@
 //     Zx[n][j]  = sum_g Mx[g][j] exp(psi_n w_g - m(psi_n)) = F_j(psi_n)     (normaliser, R/inference-tflow.R:288-290)
 //     dMx[g][j] = sum_n Rx[n][j] exp(psi_n w_g - m_n)       = H_j(w_g)       (its reverse-mode gradient)
 // where F_j, H_j are sums of exponentials: entire functions of ONE real variable.  Piecewise Chebyshev
-// interpolation on panels whose exponent half-range is <= kAmax converges spectrally (24 nodes: ~1e-14 relative,
+// interpolation on panels whose exponent half-range is <= kAmax converges spectrally (24 nodes: ~1e-14 relative, 16 nodes: ~6e-9;
 // scripts/interp_prototype.py, tests/test_interp_model.py), so the (N x G) x (G x J) contraction is replaced by
 //     nodes:  (n_nodes x G) x (G x J)   with n_nodes ~ 50..200 instead of N = 100 000        (k_interp_nodes<FWD>)
 //     DCT  :  node values -> Chebyshev coefficients per panel                                  (k_interp_coeffs)
@@ -21,7 +21,7 @@
 
 namespace ca {
 
-constexpr int kIP = 24;            // Chebyshev nodes per panel (multiple of 8)
+constexpr int kIP = 16;            // Chebyshev nodes per panel (multiple of 8); with kIAmax = 4: ~6e-9 relative
 constexpr int kIMaxPanF = 64;      // forward panels (both signs of psi together)
 constexpr int kIMaxPanB = 64;      // backward panels over [w_min, w_max]
 constexpr int kISplitB = 16;       // fixed split of the cell reduction in the backward node kernel

@@ -186,6 +186,117 @@ k_ypass_k1_persistent(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, in
     ypass_tile<T, true>(Y, ldY, N, G, RB, U, Vm, rowpart, colpart, (int)(t % nCB), t / nCB, red);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// v2 of the KP == 1 tile: identical tiling / partial layout, arithmetic on PACKED fp32 pairs.
+// Why (profiles/r01_notes.md, ncu of round 1): with u8 counts the v1 kernel is bound by the FMA pipe, not by HBM
+// (per 8 counts: 8 PRMT on the ALU pipe, 8 FADD + 16 FFMA on the FMA pipe, one warp instruction per 2 cycles per
+// sub-partition => 0.32 ms of FMA-pipe time at c3 against a 0.31 ms HBM floor; measured 0.44 ms).  sm_100 has
+// two-wide fp32 instructions (add/fma.rn.f32x2 = __fadd2_rn / __ffma2_rn): the magic-number FADD and both FMAs go
+// through them, halving the FMA-pipe work (8 PRMT + 4 FADD2 + 8 FFMA2 per 8 counts).  Full tiles also skip the
+// per-row bounds predicates.  Sums are re-associated (even / odd columns of a thread are accumulated separately and
+// added at the end), so results differ from v1 in the last bits; they stay run-to-run deterministic.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct YLoad2;
+template <> struct YLoad2<float> {
+  static __device__ __forceinline__ void unpack(const YLoad<float>::Raw& r, float2 (&o)[4]) {
+    o[0] = make_float2(r.a.x, r.a.y); o[1] = make_float2(r.a.z, r.a.w);
+    o[2] = make_float2(r.b.x, r.b.y); o[3] = make_float2(r.b.z, r.b.w);
+  }
+};
+__device__ __forceinline__ float2 magic_pair(uint32_t x, uint32_t sel0, uint32_t sel1) {
+  const float2 m = make_float2(__uint_as_float(__byte_perm(x, 0x4B000000u, sel0)), __uint_as_float(__byte_perm(x, 0x4B000000u, sel1)));
+  return __fadd2_rn(m, make_float2(-8388608.0f, -8388608.0f));
+}
+template <> struct YLoad2<uint16_t> {
+  static __device__ __forceinline__ void unpack(const uint4& a, float2 (&o)[4]) {
+    o[0] = magic_pair(a.x, 0x7510u, 0x7532u); o[1] = magic_pair(a.y, 0x7510u, 0x7532u);
+    o[2] = magic_pair(a.z, 0x7510u, 0x7532u); o[3] = magic_pair(a.w, 0x7510u, 0x7532u);
+  }
+};
+template <> struct YLoad2<uint8_t> {
+  static __device__ __forceinline__ void unpack(const uint2& a, float2 (&o)[4]) {
+    o[0] = magic_pair(a.x, 0x7540u, 0x7541u); o[1] = magic_pair(a.x, 0x7542u, 0x7543u);
+    o[2] = magic_pair(a.y, 0x7540u, 0x7541u); o[3] = magic_pair(a.y, 0x7542u, 0x7543u);
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+k_ypass_k1_v2(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, const float* __restrict__ U,
+              const float* __restrict__ Vm, float* __restrict__ rowpart, float* __restrict__ colpart) {
+  using L = YLoad<T>;
+  constexpr int kRows = L::kRows;
+  __shared__ float red[2][8][kYMaxRows];
+  const int cb = blockIdx.x;
+  const int64_t rb = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t col0 = (int64_t)cb * kYCB + tid * 8;
+  const bool colok = col0 < ldY;
+  float2 vr[4], cacc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    vr[j] = make_float2((col0 + 2 * j < G) ? Vm[col0 + 2 * j] : 0.f, (col0 + 2 * j + 1 < G) ? Vm[col0 + 2 * j + 1] : 0.f);
+    cacc[j] = make_float2(0.f, 0.f);
+  }
+  const int64_t rbeg = rb * RB, rend = (rbeg + RB < N) ? rbeg + RB : N;
+  const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const T* yp = Y + rbeg * ldY + col0;
+  int buf = 0;
+  for (int64_t r0 = rbeg; r0 < rend; r0 += kRows, yp += (int64_t)kRows * ldY) {
+    typename L::Raw raw[kRows];
+    if (colok && r0 + kRows <= rend) {       // full tile: no per-row predicates
+#pragma unroll
+      for (int i = 0; i < kRows; ++i) raw[i] = L::ld(yp + (int64_t)i * ldY);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kRows; ++i) raw[i] = (colok && r0 + i < rend) ? L::ld(yp + (int64_t)i * ldY) : L::zero();
+    }
+    float u[kRows];   // U is allocated with 64 elements of slack, r0 is a multiple of 4: vector loads stay in bounds
+#pragma unroll
+    for (int i = 0; i < kRows; i += 4) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(U + r0 + i));
+      u[i] = t4.x; u[i + 1] = t4.y; u[i + 2] = t4.z; u[i + 3] = t4.w;
+    }
+    float rp[(kRows + 7) / 8 * 8];
+#pragma unroll
+    for (int i = 0; i < (kRows + 7) / 8 * 8; ++i) rp[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+      float2 y[4];
+      YLoad2<T>::unpack(raw[i], y);
+      const float2 u2 = make_float2(u[i], u[i]);
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc = __ffma2_rn(y[j], vr[j], acc);
+        cacc[j] = __ffma2_rn(y[j], u2, cacc[j]);
+      }
+      rp[i] = acc.x + acc.y;
+    }
+#pragma unroll
+    for (int h = 0; h < (kRows + 7) / 8; ++h) {
+      float v8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v8[i] = rp[h * 8 + i];
+      float tot = butterfly8(v8, lane);
+      if ((lane & 3) == 0) red[buf][wid][h * 8 + ridx] = tot;
+    }
+    __syncthreads();
+    if (tid < kRows && r0 + tid < rend) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) acc += red[buf][w][tid];
+      rowpart[(int64_t)cb * N + r0 + tid] = acc;
+    }
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (col0 + 2 * j < G) colpart[rb * G + col0 + 2 * j] = cacc[j].x;
+    if (col0 + 2 * j + 1 < G) colpart[rb * G + col0 + 2 * j + 1] = cacc[j].y;
+  }
+}
+
 // generic K + P (slow path, reads Y twice): rows then columns
 template <typename T>
 __global__ void k_ypass_rows_generic(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int KP,

@@ -24,6 +24,21 @@ from . import _lib
 
 _STORE = {"auto": _lib.STORE_AUTO, "f32": _lib.STORE_F32, "u16": _lib.STORE_U16, "u8": _lib.STORE_U8}
 _PATH = {"auto": _lib.PATH_AUTO, "cudacore": _lib.PATH_CUDACORE, "tensor": _lib.PATH_TENSOR, "interp": _lib.PATH_INTERP}
+_VARIANT = {"ypass2": _lib.VAR_YPASS2, "epi2": _lib.VAR_EPI2}
+
+
+def variant_mask(variants) -> int:
+    """Kernel variants (include/clonealign_b200.h, enum ca_variant): iterable / comma-separated string of names."""
+    if not variants:
+        return 0
+    if isinstance(variants, str):
+        variants = [v for v in variants.split(",") if v]
+    mask = 0
+    for v in variants:
+        if v not in _VARIANT:
+            raise ValueError(f"unknown kernel variant {v!r}; known: {sorted(_VARIANT)}")
+        mask |= _VARIANT[v]
+    return mask
 
 _SHAPES = {  # name -> lambda(session) -> (rows, cols)
     "W": lambda s: (s.G, s.K), "beta": lambda s: (s.G, s.P), "psi": lambda s: (s.N, s.K),
@@ -54,10 +69,12 @@ class Session:
 
     def __init__(self, Y, L, psi_init, loc_init, *, mc_samples=1, K=1, x=None, learning_rate=0.1, seed=0,
                  device=0, clone_allele=None, alt=None, cov=None, rank=0, world=1, nccl_id=None, n_total=None,
-                 colsum_total=None, y_store="auto", path="auto"):
+                 colsum_total=None, y_store="auto", path="auto", variants=None):
         self._h = None
         if path == "auto":   # operator override, e.g. CLONEALIGN_B200_PATH=cudacore
             path = os.environ.get("CLONEALIGN_B200_PATH", "auto")
+        if variants is None:
+            variants = os.environ.get("CLONEALIGN_B200_VARIANTS", "")
         lib = _lib.load()
         self._lib = lib
         self._err = C.create_string_buffer(1024)
@@ -132,6 +149,7 @@ class Session:
         cfg.device, cfg.rank, cfg.world = int(device), int(rank), int(world)
         cfg.y_store, cfg.path, cfg.y_ld = _STORE[y_store], _PATH[path], 0
         cfg.nccl_id = C.cast(idbuf, C.c_void_p) if idbuf is not None else None
+        cfg.variants = variant_mask(variants)
 
         self.N, self.G, self.C, self.S, self.K, self.P, self.V = N, G, Cn, int(mc_samples), K, P, V
         h = C.c_void_p()

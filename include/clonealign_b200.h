@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CA_ABI_VERSION 1
+#define CA_ABI_VERSION 2
 #if defined(__GNUC__)
 #define CA_API __attribute__((visibility("default")))
 #else
@@ -55,6 +55,12 @@ enum ca_y_store  { CA_STORE_AUTO = 0, CA_STORE_F32 = 1, CA_STORE_U16 = 2, CA_STO
  * Chebyshev interpolation of the univariate functions they reduce to (kernels_interp.cuh); opt-in until it has
  * been validated on hardware. */
 enum ca_path     { CA_PATH_AUTO = 0, CA_PATH_CUDACORE = 1, CA_PATH_TENSOR = 2, CA_PATH_INTERP = 3 };
+/* kernel variants (bit mask in ca_config.variants; 0 = the kernels measured in round 1).  Each bit swaps ONE kernel for
+ * a re-engineered version with the same inputs/outputs; they are opt-in until measured on hardware (bench.py validates
+ * them on the device against the default kernels before using them).
+ *   YPASS2: Y pass on packed fp32 pairs (add/fma.rn.f32x2), see kernels_ypass.cuh
+ *   EPI2  : (interp path) Clenshaw evaluation fused into a leaner per-cell epilogue, see kernels_fused.cuh        */
+enum ca_variant  { CA_VAR_YPASS2 = 1, CA_VAR_EPI2 = 2 };
 
 typedef struct ca_config {
   int64_t N;            /* cells held by this handle (this rank's shard)                       */
@@ -77,6 +83,7 @@ typedef struct ca_config {
   int32_t path;         /* enum ca_path                                                        */
   int64_t y_ld;         /* leading dimension of Y in elements (0 = tight)                      */
   const void* nccl_id;  /* 128-byte ncclUniqueId shared by all ranks when world > 1, else NULL */
+  uint32_t variants;    /* bit mask of enum ca_variant; 0 = default kernels                    */
 } ca_config;
 
 /* library / device discovery */

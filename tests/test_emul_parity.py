@@ -13,7 +13,9 @@ from oracle import clonealign_oracle as O
 from test_gpu_parity import ELBO_RTOL, PARAM_RTOL, _case, _check_grads, _load_params, _relmax, _run_trace, _session
 
 pytestmark = pytest.mark.usefixtures("emulated_library")
-PATHS = ["cudacore", "interp"]
+# (contraction path, kernel variants): the default kernels of both non-tensor paths and the re-engineered variants
+# (packed-fp32 Y pass, fused Clenshaw + per-cell epilogue) that bench.py validates on the device before using them
+PATHS = [("cudacore", ""), ("interp", ""), ("cudacore", "ypass2"), ("interp", "ypass2,epi2")]
 
 
 def test_emulated_library_is_not_the_product(emulated_library):
@@ -31,8 +33,8 @@ def test_emulated_library_is_not_the_product(emulated_library):
 def test_gradients_and_elbo_match_oracle_c1(example_sce, path, S):
     Y, L = example_sce
     d, p, mu_guess, _ = _case(Y, L, K=1, seed=S)
-    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path=path, seed=1) as sess:
-        assert sess.describe()["path"] == path
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path=path[0], variants=path[1], seed=1) as sess:
+        assert sess.describe()["path"] == path[0]
         _load_params(sess, p)
         errs = _check_grads(sess, d, p, S)
         assert errs["Z"] < 1e-5
@@ -51,12 +53,13 @@ def test_general_path_covariates_allele(example_sce, K, P, use_v):
 
 
 @pytest.mark.parametrize("path", PATHS)
-@pytest.mark.parametrize("N,G,C,S", [(130, 70, 5, 3), (257, 193, 2, 1), (64, 640, 7, 8), (33, 2100, 3, 2)])
+@pytest.mark.parametrize("N,G,C,S", [(130, 70, 5, 3), (257, 193, 2, 1), (64, 640, 7, 8), (33, 2100, 3, 2), (40, 50, 16, 8),
+                                     (37, 45, 32, 4), (35, 40, 11, 9)])
 def test_ragged_shapes(path, N, G, C, S):
     from clonealign_b200.synthetic import make_synthetic
     syn = make_synthetic(N, G, C, seed=N + G)
     d, p, mu_guess, _ = _case(syn["Y"].astype(np.float64), np.minimum(syn["L"], 6.0), K=1, seed=N)
-    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path=path, seed=1) as sess:
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path=path[0], variants=path[1], seed=1) as sess:
         _load_params(sess, p)
         _check_grads(sess, d, p, S)
 
@@ -67,7 +70,7 @@ def test_wide_exponent_range(example_sce, path):
     Y, L = example_sce
     d, p, mu_guess, _ = _case(Y, L, K=1, seed=5, scale=1.0)
     p.psi *= 2.0
-    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=2, K=1, path=path, seed=1) as sess:
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=2, K=1, path=path[0], variants=path[1], seed=1) as sess:
         _load_params(sess, p)
         _check_grads(sess, d, p, 2)
 
@@ -79,7 +82,7 @@ def test_one_sided_psi(example_sce, path):
     for sign in (+1.0, -1.0):
         d, p, mu_guess, _ = _case(Y[:80], L, K=1, seed=9)
         p.psi = sign * np.abs(p.psi) - sign * 1e-3
-        with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=1, K=1, path=path, seed=1) as sess:
+        with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=1, K=1, path=path[0], variants=path[1], seed=1) as sess:
             _load_params(sess, p)
             _check_grads(sess, d, p, 1)
 
@@ -88,7 +91,7 @@ def test_one_sided_psi(example_sce, path):
 def test_allele_fused(example_sce, path):
     Y, L = example_sce
     d, p, mu_guess, al = _case(Y, L, K=1, use_v=True, seed=21)
-    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=1, K=1, path=path, seed=1, **al) as sess:
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=1, K=1, path=path[0], variants=path[1], seed=1, **al) as sess:
         _load_params(sess, p)
         _check_grads(sess, d, p, 1)
         snv = sess.params()["clone_probs_from_snv"]
@@ -102,8 +105,8 @@ def test_loop_matches_golden(example_sce, golden_c1, path, S):
     Y, L = example_sce
     hi = O.host_init(Y, L, K=1, rng=None)
     eps = golden_c1[f"eps_S{S}"]
-    with _session(hi["Y"], hi["L"], golden_c1["psi_init"], golden_c1["mu_guess"], mc_samples=S, K=1, path=path,
-                  learning_rate=0.1, seed=3) as sess:
+    with _session(hi["Y"], hi["L"], golden_c1["psi_init"], golden_c1["mu_guess"], mc_samples=S, K=1, path=path[0],
+                  variants=path[1], learning_rate=0.1, seed=3) as sess:
         sess.set_eps(eps)
         sess.init_gamma()
         elbos = [sess.elbo()]
@@ -132,7 +135,7 @@ def test_loop_with_device_rng_matches_oracle(example_sce, path):
     hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(5))
     d = O.Data(hi["Y"], hi["L"])
     S, draws = 2, []
-    with _session(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], mc_samples=S, K=1, seed=99, path=path) as sess:
+    with _session(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], mc_samples=S, K=1, seed=99, path=path[0], variants=path[1]) as sess:
         def rec():
             draws.append(sess.get_eps().astype(np.float64))
         sess.init_gamma(); rec()
@@ -157,9 +160,9 @@ def test_same_seed_bitwise_identical(example_sce, path):
     """tests/testthat/test_clonealign.R:42-66 (fixed-order reductions: also independent of the host thread count)."""
     Y, L = example_sce
     hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
-    a, ga = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], n=3, mc_samples=2, seed=12345, path=path)
-    b, gb = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], n=3, mc_samples=2, seed=12345, path=path)
-    c, _ = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], n=3, mc_samples=2, seed=54321, path=path)
+    a, ga = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], n=3, mc_samples=2, seed=12345, path=path[0], variants=path[1])
+    b, gb = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], n=3, mc_samples=2, seed=12345, path=path[0], variants=path[1])
+    c, _ = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], n=3, mc_samples=2, seed=54321, path=path[0], variants=path[1])
     assert a.tobytes() == b.tobytes() and ga.tobytes() == gb.tobytes()
     assert a.tobytes() != c.tobytes()
 
@@ -184,6 +187,53 @@ def test_storage_formats_and_input_layouts_agree(example_sce):
     big[0, 0] = 70000.0
     with _session(big, hi["L"], hi["psi_init"], hi["mu_guess"]) as sess:
         assert sess.describe()["y_store"] == "f32"
+
+
+def test_fused_epilogue_coefficients_through_l2(example_sce, monkeypatch):
+    """More active panels than the shared-memory table holds: the fused kernel reads coefficients through L2."""
+    monkeypatch.setenv("CLONEALIGN_B200_FUSED_PANELS", "1")
+    Y, L = example_sce
+    d, p, mu_guess, _ = _case(Y, L, K=1, seed=5, scale=1.0)
+    p.psi *= 2.0
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=3, K=1, path="interp", variants="epi2", seed=1) as sess:
+        _load_params(sess, p)
+        _check_grads(sess, d, p, 3)
+
+
+def test_variant_validation(example_sce):
+    from clonealign_b200._lib import CloneAlignLibraryError
+    Y, L = example_sce
+    d, p, mu_guess, _ = _case(Y[:40], L, K=1, seed=1)
+    with pytest.raises(CloneAlignLibraryError, match="epi2 belongs to the interp path"):
+        _session(d.Y, d.L, p.psi, mu_guess, path="cudacore", variants="epi2")
+    from clonealign_b200.synthetic import make_synthetic
+    syn = make_synthetic(20, 30, 33, seed=3)
+    with pytest.raises(CloneAlignLibraryError, match="epi2 needs C <= 32"):
+        _session(syn["Y"].astype(np.float64) + 1.0, np.minimum(syn["L"], 6.0), np.zeros((20, 1)), np.ones(30), path="interp",
+                 variants="epi2")
+    with pytest.raises(ValueError, match="unknown kernel variant"):
+        _session(d.Y, d.L, p.psi, mu_guess, variants="nope")
+    with _session(d.Y, d.L, p.psi, mu_guess, path="interp", variants=["ypass2", "epi2"]) as sess:
+        assert sess.describe()["variants"] == 3
+
+
+def test_variants_agree_with_default_kernels(example_sce):
+    """The re-engineered kernels against the default ones on the same inputs (what bench.py's on-device self-check
+    does at full size): ELBO trace and fitted parameters after 3 steps."""
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
+    out = {}
+    for name, (path, var) in {"ref": ("cudacore", ""), "new": ("interp", "ypass2,epi2")}.items():
+        with _session(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], mc_samples=2, seed=5, path=path, variants=var) as sess:
+            sess.init_gamma()
+            tr = [sess.elbo()]
+            for _ in range(3):
+                sess.step()
+                tr.append(sess.elbo())
+            out[name] = (np.array(tr), sess.params())
+    assert (np.abs(out["ref"][0] - out["new"][0]) / np.abs(out["ref"][0])).max() < 1e-6
+    for k in ("psi", "W", "mu", "clone_probs", "alpha"):
+        assert _relmax(out["new"][1][k], out["ref"][1][k]) < 1e-4, k
 
 
 # ---------------------------------------------------------------------------------------------------
