@@ -38,7 +38,7 @@ def init_process_group(backend=None):
             torch.cuda.set_device(local_rank)
         import datetime
         # short collective timeout: a rank that dies or diverges must take the job down in minutes, not hang the box
-        dist.init_process_group(backend=backend, rank=rank, world_size=world, timeout=datetime.timedelta(seconds=300))
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, timeout=datetime.timedelta(seconds=600))
     return rank, local_rank, world
 
 

@@ -64,7 +64,8 @@ def test_plain_c_client_of_the_abi(lib):
     with tempfile.TemporaryDirectory() as td:
         out = subprocess.run([_build_c_probe(td)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "abi=1" in out.stdout
+    from clonealign_b200 import _lib as L
+    assert f"abi={L.ABI_VERSION}" in out.stdout
     assert ("create_failed" in out.stdout and "msg_len=0" not in out.stdout) or "ok elbo0=" in out.stdout
 
 
@@ -294,3 +295,39 @@ def test_sharding_algebra_gloo_world2():
                              env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "RANK_OK_0" in out.stdout and "RANK_OK_1" in out.stdout
+
+
+def test_bench_candidate_selection(monkeypatch, tmp_path):
+    """bench.py --path best: the fastest candidate that passed the on-device check wins; a candidate that failed, a
+    crashed child, or candidates slower than the tcgen05 path fall back to ("auto", "")."""
+    import argparse
+    import importlib.util
+    import json
+    import tempfile as tf
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(tf, "gettempdir", lambda: str(tmp_path))
+    args = argparse.Namespace(config="c1", y_store="auto")
+
+    def fake(lines, rc=0):
+        class R:
+            stdout = "warming up\n" + "\n".join(json.dumps(x) for x in lines) + "\n"
+            stderr = ""
+            returncode = rc
+        return lambda *a, **k: R()
+
+    rows = [{"candidate": ["tensor", ""], "ok": True, "ms_per_step": 3.3},
+            {"candidate": ["interp", ""], "ok": True, "ms_per_step": 1.4},
+            {"candidate": ["interp", "ypass2"], "ok": False, "ms_per_step": 0.9},
+            {"candidate": ["interp", "ypass2,epi2"], "ok": True, "ms_per_step": 1.1}]
+    monkeypatch.setattr(bench.subprocess, "run", fake(rows, rc=1))          # crashed after 4 verdicts: not cached
+    pick, info = bench.interp_selfcheck(args)
+    assert pick == ("interp", "ypass2,epi2") and pick in bench.CANDIDATES and len(info["candidates"]) == 4
+    monkeypatch.setattr(bench.subprocess, "run", fake(rows[:1] + [dict(rows[1], ms_per_step=5.0)]))
+    assert bench.interp_selfcheck(args)[0] == ("auto", "")                   # slower than the tensor path
+    monkeypatch.setattr(bench.subprocess, "run", fake([]))                   # (the verdict above was cached)
+    pick, info = bench.interp_selfcheck(args)
+    assert pick == ("auto", "") and "cached" in info["note"]
+    args.config = "c2"
+    assert bench.interp_selfcheck(args)[0] == ("auto", "")                   # no output at all
