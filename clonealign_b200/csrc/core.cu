@@ -419,10 +419,9 @@ void run_forward(ca_handle* h, int mode) {
       // K = 1: Zx[n][j] = F_j(psi_n) by piecewise Chebyshev interpolation (kernels_interp.cuh)
       CA_LAUNCH(k_minmax, 1, 1024, 0, h->stream)(h->U, (int)h->N, h->mm_psi);
       CA_LAUNCH(k_interp_plan, 1, 32, 0, h->stream)(h->mm, h->mm_psi, h->iplan);
-      dim3 gn((h->J + 31) / 32, kIMaxPanF * kIP / 8);
+      dim3 gn((h->J + 31) / 32, kIGroupsY, kISplitF);
       CA_LAUNCH(k_interp_nodes<true>, gn, 256, 0, h->stream)(h->iplan, h->Vm, nullptr, h->Mx, h->G, h->J, h->ivals);
-      int64_t tot = (int64_t)kIMaxPanF * kIP * h->J;
-      CA_LAUNCH(k_interp_coeffs, (unsigned)ceil_div64(tot, 256), 256, 0, h->stream)(h->iplan, h->ivals, 1, kIMaxPanF, h->J, 1, h->icoef);
+      CA_LAUNCH(k_interp_coeffs, dim3((h->J + 31) / 32, kIMaxPanF), kIP * 32, 0, h->stream)(h->iplan, h->ivals, kISplitF, kIMaxPanF, h->J, 1, h->icoef);
       if (!h->epi2)
         CA_LAUNCH(k_interp_eval<true>, h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream)(h->iplan, h->icoef, h->U, h->N, h->J, h->Zx,
                                                                                     h->ieval_panels);
@@ -472,10 +471,9 @@ void run_train(ca_handle* h, bool apply) {
     LaunchScope ls(h, "lse_bwd", h->interp ? 3 : 1);
     if (h->interp) {
       // K = 1: dMx[g][j] = H_j(w_g); the plan of this step's forward pass is still valid (psi, W unchanged)
-      dim3 gn((h->J + 31) / 32, kIMaxPanB * kIP / 8, kISplitB);
+      dim3 gn((h->J + 31) / 32, kIGroupsY, kISplitB);
       CA_LAUNCH(k_interp_nodes<false>, gn, 256, 0, h->stream)(h->iplan, h->U, h->shift, h->Rx, h->N, h->J, h->ivals);
-      int64_t tot = (int64_t)kIMaxPanB * kIP * h->J;
-      CA_LAUNCH(k_interp_coeffs, (unsigned)ceil_div64(tot, 256), 256, 0, h->stream)(h->iplan, h->ivals, kISplitB, kIMaxPanB, h->J, 0, h->icoef);
+      CA_LAUNCH(k_interp_coeffs, dim3((h->J + 31) / 32, kIMaxPanB), kIP * 32, 0, h->stream)(h->iplan, h->ivals, kISplitB, kIMaxPanB, h->J, 0, h->icoef);
       CA_LAUNCH(k_interp_eval<false>, h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream)(h->iplan, h->icoef, h->Vm, h->G, h->J, h->dMx,
                                                                                    h->ieval_panels);
     } else if (h->tc) {
@@ -865,7 +863,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if (h->interp) {
     h->iplan = h->alloc<InterpPlan>(1);
     h->mm_psi = z(2);
-    const size_t nodes_f = (size_t)kIMaxPanF * kIP, nodes_b = (size_t)kISplitB * kIMaxPanB * kIP;
+    const size_t nodes_f = (size_t)kISplitF * kIMaxPanF * kIP, nodes_b = (size_t)kISplitB * kIMaxPanB * kIP;
     h->ivals = h->alloc<double>(std::max(nodes_f, nodes_b) * J);
     h->icoef = h->alloc<double>((size_t)std::max(kIMaxPanF, kIMaxPanB) * kIP * J);
     const size_t per_panel = (size_t)kIP * J * sizeof(double);

@@ -24,7 +24,9 @@ namespace ca {
 constexpr int kIP = 16;            // Chebyshev nodes per panel (multiple of 8); with kIAmax = 4: ~6e-9 relative
 constexpr int kIMaxPanF = 64;      // forward panels (both signs of psi together)
 constexpr int kIMaxPanB = 64;      // backward panels over [w_min, w_max]
-constexpr int kISplitB = 16;       // fixed split of the cell reduction in the backward node kernel
+constexpr int kISplitF = 16;       // fixed split of the gene reduction in the forward node kernel
+constexpr int kISplitB = 64;       // fixed split of the cell reduction in the backward node kernel
+constexpr int kIGroupsY = 8;       // grid.y of the node kernels: blocks stride over the ACTIVE groups of 8 nodes
 constexpr double kIAmax = 4.0;     // exponent half-range per panel
 constexpr double kPi = 3.14159265358979323846;
 
@@ -85,10 +87,14 @@ __global__ void k_interp_plan(const float* __restrict__ mm_w, const float* __res
   *plan = pl;
 }
 
-// Node values.  FWD: vals[node][j] = sum_g Mx[g][j] exp(x_node (w_g - wref));  reduction index = genes.
-//               BWD: part[z][node][j] = sum_{n in split z} Rx[n][j] exp(psi_n y_node - m_n);  reduction index = cells.
+// Node values.  FWD: part[z][node][j] = sum_{g in split z} Mx[g][j] exp(x_node (w_g - wref));  reduction index = genes.
+//               BWD: part[z][node][j] = sum_{n in split z} Rx[n][j] exp(psi_n y_node - m_n);    reduction index = cells.
 // Block = 8 warps = 8 nodes x 32 columns; warps stride over the reduction index, lane = column; the 8 exponentials
 // of a row are computed by lanes 0..7 and broadcast.  Cross-warp reduction in a fixed order through shared memory.
+// Grid = (column blocks, kIGroupsY, reduction splits): how many panels are active is only known on the device (the
+// plan), so blocks stride over the active groups of 8 nodes instead of launching (and retiring) one block per possible
+// group; the reduction index is split over blockIdx.z (kISplitF / kISplitB partials, summed by k_interp_coeffs) so that
+// a handful of active groups still spreads over all SMs instead of running as a few long serial loops.
 template <bool FWD>
 __global__ void __launch_bounds__(256)
 k_interp_nodes(const InterpPlan* __restrict__ plan, const float* __restrict__ rv /*FWD: w[G]  BWD: psi[N]*/,
@@ -97,80 +103,87 @@ k_interp_nodes(const InterpPlan* __restrict__ plan, const float* __restrict__ rv
   __shared__ double red[8][8][32];
   const InterpPlan pl = *plan;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int node0 = blockIdx.y * 8;
-  const int panel = node0 / kIP;
   const int npan = FWD ? (pl.nf_neg + pl.nf_pos) : pl.nb;
-  if (panel >= npan) return;
-  double mid, half, wref = 0.0;
-  if (FWD) fwd_panel(pl, panel, mid, half, wref);
-  else bwd_panel(pl, panel, mid, half);
-  const double xq = mid + half * cheb_node((node0 % kIP) + (lane & 7));   // node handled by this lane (lanes 0..7 used)
+  const int ngroups = npan * (kIP / 8);
   const int j = blockIdx.x * 32 + lane;
   const bool jok = j < J;
   // reduction range of this block
-  int64_t rbeg = 0, rend = R;
-  if (!FWD) {
-    const int64_t per = (R + kISplitB - 1) / kISplitB;
-    rbeg = (int64_t)blockIdx.z * per;
-    rend = rbeg + per < R ? rbeg + per : R;
-  }
-  double acc[8];
+  const int64_t per = (R + gridDim.z - 1) / gridDim.z;
+  const int64_t rbeg = (int64_t)blockIdx.z * per;
+  const int64_t rend = rbeg + per < R ? rbeg + per : R;
+  const int64_t nodes_total = (int64_t)(FWD ? kIMaxPanF : kIMaxPanB) * kIP;
+  for (int grp = blockIdx.y; grp < ngroups; grp += gridDim.y) {
+    const int node0 = grp * 8;
+    const int panel = node0 / kIP;
+    double mid, half, wref = 0.0;
+    if (FWD) fwd_panel(pl, panel, mid, half, wref);
+    else bwd_panel(pl, panel, mid, half);
+    const double xq = mid + half * cheb_node((node0 % kIP) + (lane & 7));   // node handled by this lane (lanes 0..7 used)
+    double acc[8];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) acc[q] = 0.0;
-  // 4 rows of the reduction index per warp iteration: lane (q = lane & 7, sub = lane >> 3) evaluates the exponential
-  // of row r + sub at node q (argument in fp64, expf in fp32: ~1e-7 relative, averaged over the sum), then every lane
-  // accumulates its column in fp64
-  for (int64_t r = rbeg + (int64_t)wid * 4; r < rend; r += 32) {
-    const int64_t rr = r + (lane >> 3);
-    float e = 0.f;
-    if (rr < rend) {
-      const double v = (double)rv[rr];
-      e = FWD ? expf((float)(xq * (v - wref))) : expf((float)(v * xq - (double)shift[rr]));
+    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+    // 4 rows of the reduction index per warp iteration: lane (q = lane & 7, sub = lane >> 3) evaluates the exponential
+    // of row r + sub at node q (argument in fp64, expf in fp32: ~1e-7 relative, averaged over the sum), then every lane
+    // accumulates its column in fp64
+    for (int64_t r = rbeg + (int64_t)wid * 4; r < rend; r += 32) {
+      const int64_t rr = r + (lane >> 3);
+      float e = 0.f;
+      if (rr < rend) {
+        const double v = (double)rv[rr];
+        e = FWD ? expf((float)(xq * (v - wref))) : expf((float)(v * xq - (double)shift[rr]));
+      }
+#pragma unroll
+      for (int sub = 0; sub < 4; ++sub) {
+        const int64_t r2 = r + sub;
+        const double b = (jok && r2 < rend) ? (double)B[r2 * J + j] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = fma((double)__shfl_sync(CA_FULL, e, q + 8 * sub), b, acc[q]);
+      }
     }
 #pragma unroll
-    for (int sub = 0; sub < 4; ++sub) {
-      const int64_t r2 = r + sub;
-      const double b = (jok && r2 < rend) ? (double)B[r2 * J + j] : 0.0;
+    for (int q = 0; q < 8; ++q) red[wid][q][lane] = acc[q];
+    __syncthreads();
+    // thread (q = wid, lane): sum over the 8 warps in order
+    double s = 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = fma((double)__shfl_sync(CA_FULL, e, q + 8 * sub), b, acc[q]);
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < 8; ++q) red[wid][q][lane] = acc[q];
-  __syncthreads();
-  // thread (q = wid, lane): sum over the 8 warps in order
-  double s = 0.0;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) s += red[w][wid][lane];
-  if (jok) {
-    const int64_t nodes_total = (int64_t)(FWD ? kIMaxPanF : kIMaxPanB) * kIP;
-    const int64_t z = FWD ? 0 : blockIdx.z;
-    vals[(z * nodes_total + node0 + wid) * J + j] = s;
+    for (int w = 0; w < 8; ++w) s += red[w][wid][lane];
+    if (jok) vals[((int64_t)blockIdx.z * nodes_total + node0 + wid) * J + j] = s;
+    __syncthreads();   // red is reused by the next group
   }
 }
 
 // Chebyshev coefficients per panel: c_k = (2/P) sum_p f(x_p) cos(pi k (p + 1/2) / P), c_0 halved.
-// The backward node values arrive as kISplitB partials that are summed here in a fixed order.
-__global__ void k_interp_coeffs(const InterpPlan* __restrict__ plan, const double* __restrict__ vals, int nsplit,
-                                int max_pan, int J, int fwd, double* __restrict__ coeff) {
+// The node values arrive as `nsplit` partials that are summed here in a fixed order.
+// Block = (kIP nodes) x (32 columns) threads for one (column block, panel): thread (p, lane) sums the partials of node
+// p (coalesced over the columns), the block transposes through shared memory, then thread (k = p, lane) applies the DCT.
+__global__ void __launch_bounds__(kIP * 32)
+k_interp_coeffs(const InterpPlan* __restrict__ plan, const double* __restrict__ vals, int nsplit, int max_pan, int J,
+                int fwd, double* __restrict__ coeff) {
+  __shared__ double f[kIP][32];
+  __shared__ double ct[kIP][kIP];
   const InterpPlan pl = *plan;
   const int npan = fwd ? (pl.nf_neg + pl.nf_pos) : pl.nb;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (panel, k, j)
-  const int64_t tot = (int64_t)npan * kIP * J;
-  if (i >= tot) return;
-  const int j = (int)(i % J);
-  const int k = (int)((i / J) % kIP);
-  const int panel = (int)(i / ((int64_t)J * kIP));
+  const int panel = blockIdx.y;
+  if (panel >= npan) return;
+  const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
   const int64_t nodes_total = (int64_t)max_pan * kIP;
-  double c = 0.0;
-  for (int p = 0; p < kIP; ++p) {
-    double f = 0.0;
-    for (int z = 0; z < nsplit; ++z) f += vals[((int64_t)z * nodes_total + panel * kIP + p) * J + j];
-    c += f * cos(kPi * k * (p + 0.5) / kIP);
+  if (threadIdx.x < kIP * kIP) {
+    const int k = threadIdx.x / kIP, q = threadIdx.x % kIP;
+    ct[k][q] = cos(kPi * k * (q + 0.5) / kIP);
   }
+  double acc = 0.0;
+  if (j < J)
+    for (int z = 0; z < nsplit; ++z) acc += vals[((int64_t)z * nodes_total + panel * kIP + p) * J + j];
+  f[p][lane] = acc;
+  __syncthreads();
+  const int k = p;
+  double c = 0.0;
+#pragma unroll
+  for (int q = 0; q < kIP; ++q) c += f[q][lane] * ct[k][q];
   c *= 2.0 / kIP;
   if (k == 0) c *= 0.5;
-  coeff[((int64_t)panel * kIP + k) * J + j] = c;
+  if (j < J) coeff[((int64_t)panel * kIP + k) * J + j] = c;
 }
 
 // Evaluation: out[i][j] = sum_k c[panel(x_i)][k][j] T_k(t_i) by Clenshaw, one warp per point, lanes over columns.

@@ -30,30 +30,27 @@ int main(int argc, char** argv) {
   InterpPlan plan;
   ca_emul::launch(k_interp_plan, dim3(1), dim3(32), 0, (const float*)mm_w, (const float*)mm_psi, &plan);
   const int npf = plan.nf_neg + plan.nf_pos;
-  std::vector<double> vals((size_t)std::max(kIMaxPanF, kISplitB * kIMaxPanB) * kIP * J, 0.0);
+  std::vector<double> vals((size_t)std::max(kISplitF * kIMaxPanF, kISplitB * kIMaxPanB) * kIP * J, 0.0);
   std::vector<double> coef((size_t)std::max(kIMaxPanF, kIMaxPanB) * kIP * J, 0.0);
   std::vector<float> Zx((size_t)N * J, -1.f), dMx((size_t)G * J, -1.f);
   const size_t eval_smem = (size_t)smem_panels * kIP * J * sizeof(double);
 
-  // forward: nodes -> coefficients -> evaluation per cell.  (core.cu launches kIMaxPanF*kIP/8 node groups; the
-  // inactive ones return at once, so only the active ones plus one extra group are emulated here.)
-  ca_emul::launch(k_interp_nodes<true>, dim3((J + 31) / 32, npf * kIP / 8 + 1), dim3(256), 0, (const InterpPlan*)&plan,
+  // forward: nodes -> coefficients -> evaluation per cell (grid.y = 3 here: blocks stride over the active node groups)
+  ca_emul::launch(k_interp_nodes<true>, dim3((J + 31) / 32, 3, kISplitF), dim3(256), 0, (const InterpPlan*)&plan,
                   (const float*)w.data(), (const float*)nullptr, (const float*)Mx.data(), (int64_t)G, J, vals.data());
   {
-    int64_t tot = (int64_t)kIMaxPanF * kIP * J;
-    ca_emul::launch(k_interp_coeffs, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, (const InterpPlan*)&plan,
-                    (const double*)vals.data(), 1, kIMaxPanF, J, 1, coef.data());
+    ca_emul::launch(k_interp_coeffs, dim3((J + 31) / 32, kIMaxPanF), dim3(kIP * 32), 0, (const InterpPlan*)&plan,
+                    (const double*)vals.data(), kISplitF, kIMaxPanF, J, 1, coef.data());
   }
   ca_emul::launch(k_interp_eval<true>, dim3(3), dim3(kIEvalWarps * 32), eval_smem, (const InterpPlan*)&plan,
                   (const double*)coef.data(), (const float*)psi.data(), (int64_t)N, J, Zx.data(), smem_panels);
 
   // backward: nodes over w (reduction over cells, kISplitB partials) -> coefficients -> evaluation per gene
-  ca_emul::launch(k_interp_nodes<false>, dim3((J + 31) / 32, plan.nb * kIP / 8 + 1, kISplitB), dim3(256), 0,
+  ca_emul::launch(k_interp_nodes<false>, dim3((J + 31) / 32, 3, kISplitB), dim3(256), 0,
                   (const InterpPlan*)&plan, (const float*)psi.data(), (const float*)shift.data(), (const float*)Rx.data(),
                   (int64_t)N, J, vals.data());
   {
-    int64_t tot = (int64_t)kIMaxPanB * kIP * J;
-    ca_emul::launch(k_interp_coeffs, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, (const InterpPlan*)&plan,
+    ca_emul::launch(k_interp_coeffs, dim3((J + 31) / 32, kIMaxPanB), dim3(kIP * 32), 0, (const InterpPlan*)&plan,
                     (const double*)vals.data(), kISplitB, kIMaxPanB, J, 0, coef.data());
   }
   ca_emul::launch(k_interp_eval<false>, dim3(2), dim3(kIEvalWarps * 32), eval_smem, (const InterpPlan*)&plan,
