@@ -167,7 +167,8 @@ def run_reference(args, cfg):
 # on-device self-check of the re-engineered K = 1 kernels against the (test-covered) tcgen05 path
 # ------------------------------------------------------------------------------------------------------
 # (path, variants) candidates, most conservative first; the reference they are checked against is ("tensor", "").
-CANDIDATES = [("interp", ""), ("interp", "ypass2"), ("interp", "epi2"), ("interp", "ypass2,epi2"), ("auto", "ypass2")]
+CANDIDATES = [("interp", ""), ("interp", "ypass2"), ("interp", "epi2"), ("interp", "ypass2,epi2"), ("interp", "epi2,lean"),
+              ("interp", "ypass2,epi2,lean"), ("auto", "ypass2")]
 SELFCHECK_TOL = dict(elbo=1e-4, psi=2e-3, clone_probs=5e-3, mu=1e-3)      # north_star tolerances (ELBO 1e-4, params 1e-3)
 
 
@@ -445,7 +446,7 @@ def main():
     ap.add_argument("--path", default="best", choices=["best", "auto", "cudacore", "tensor", "interp"],
                     help="best = the fastest of the re-engineered K=1 kernel sets (CANDIDATES) that reproduces the tcgen05 "
                          "path on this device within the parity tolerances (checked in a child process), else auto")
-    ap.add_argument("--variants", default="", help="kernel variants for an explicit --path (ypass2, epi2; comma-separated)")
+    ap.add_argument("--variants", default="", help="kernel variants for an explicit --path (ypass2, epi2, lean; comma-separated)")
     ap.add_argument("--selfcheck", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

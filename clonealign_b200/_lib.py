@@ -16,7 +16,7 @@ Y_COLMAJOR, Y_ROWMAJOR = 0, 1
 Y_HOST, Y_DEVICE = 0, 1
 STORE_AUTO, STORE_F32, STORE_U16, STORE_U8 = 0, 1, 2, 3
 PATH_AUTO, PATH_CUDACORE, PATH_TENSOR, PATH_INTERP = 0, 1, 2, 3
-VAR_YPASS2, VAR_EPI2 = 1, 2
+VAR_YPASS2, VAR_EPI2, VAR_LEAN = 1, 2, 4
 ABI_VERSION = 2
 
 EXPORTS = (

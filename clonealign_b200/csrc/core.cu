@@ -184,6 +184,12 @@ struct ca_handle {
   bool interp = false;             // K = 1 univariate-interpolation path (kernels_interp.cuh)
   uint32_t variants = 0;           // enum ca_variant bits
   bool epi2 = false;               // interp path: fused Clenshaw + per-cell epilogue (kernels_fused.cuh)
+  bool lean = false;               // with epi2: k_prologue / k_gene_fused / k_adam_all
+  double* chi_cur = nullptr;
+  float* pmm_part = nullptr;
+  unsigned* ticket = nullptr;
+  int gene_panels = 0;
+  size_t gene_smem = 0;
   int fused_nj = 0, fused_panels = 0;
   size_t fused_smem = 0;
   int64_t n_cell_parts = 0;        // per-block ELBO / sum-gamma partials written by the per-cell kernel in use
@@ -381,7 +387,17 @@ void run_forward(ca_handle* h, int mode) {
     CUDA_OK(cudaEventRecord(h->ev_join, h->stream2));
     joined_later = true;
   }
-  {
+  if (h->lean) {
+    LaunchScope ls(h, "prologue");
+    PrologueArgs a;
+    a.N = h->N; a.G = h->G; a.C = h->C; a.K = h->K;
+    a.u = h->u; a.chi_raw = h->chi_raw; a.Vm = h->Vm; a.U = h->U;
+    a.log_alpha = h->log_alpha; a.mm = h->mm; a.mm_psi = h->mm_psi; a.chi_cur = h->chi_cur;
+    a.scal_elbo = h->scal_elbo; a.wsq = h->wsq; a.pmm_part = h->pmm_part; a.ticket = h->ticket; a.plan = h->iplan;
+    a.dirichlet_const = (double)h->C * lgamma(1.0 / h->C) - lgamma(1.0);
+    CA_LAUNCH(k_prologue, 2 + kProPsiBlocks, kProThreads, 0, h->stream)(a);
+    KCHECK();
+  } else {
     LaunchScope ls(h, "alpha");
     CA_LAUNCH(k_alpha, 1, 32, 0, h->stream)(h->u, h->C, h->chi_raw, h->K, h->log_alpha, h->scal_elbo);
     KCHECK();
@@ -400,6 +416,8 @@ void run_forward(ca_handle* h, int mode) {
   }
   if (h->KP == 0) {
     CUDA_OK(cudaMemsetAsync(h->shift, 0, sizeof(float) * h->N, h->stream));
+  } else if (h->lean) {
+    // W range (and sum of squares) come from k_prologue, m_n from the fused per-cell kernel
   } else if (h->K == 1 && h->P == 0) {
     LaunchScope ls(h, "shift", h->epi2 ? 1 : 2);
     CA_LAUNCH(k_minmax, 1, 1024, 0, h->stream)(h->Vm, h->G, h->mm);
@@ -414,11 +432,13 @@ void run_forward(ca_handle* h, int mode) {
     KCHECK();
   }
   {
-    LaunchScope ls(h, "lse_fwd", h->interp ? (h->epi2 ? 4 : 5) : 1);
+    LaunchScope ls(h, "lse_fwd", h->interp ? (h->lean ? 2 : (h->epi2 ? 4 : 5)) : 1);
     if (h->interp) {
       // K = 1: Zx[n][j] = F_j(psi_n) by piecewise Chebyshev interpolation (kernels_interp.cuh)
-      CA_LAUNCH(k_minmax, 1, 1024, 0, h->stream)(h->U, (int)h->N, h->mm_psi);
-      CA_LAUNCH(k_interp_plan, 1, 32, 0, h->stream)(h->mm, h->mm_psi, h->iplan);
+      if (!h->lean) {
+        CA_LAUNCH(k_minmax, 1, 1024, 0, h->stream)(h->U, (int)h->N, h->mm_psi);
+        CA_LAUNCH(k_interp_plan, 1, 32, 0, h->stream)(h->mm, h->mm_psi, h->iplan);
+      }
       dim3 gn((h->J + 31) / 32, kIGroupsY, kISplitF);
       CA_LAUNCH(k_interp_nodes<true>, gn, 256, 0, h->stream)(h->iplan, h->Vm, nullptr, h->Mx, h->G, h->J, h->ivals);
       CA_LAUNCH(k_interp_coeffs, dim3((h->J + 31) / 32, kIMaxPanF), kIP * 32, 0, h->stream)(h->iplan, h->ivals, kISplitF, kIMaxPanF, h->J, 1, h->icoef);
@@ -468,14 +488,15 @@ void run_train(ca_handle* h, bool apply) {
   h->launches_last_step = 0;
   run_forward(h, EPI_TRAIN);
   {
-    LaunchScope ls(h, "lse_bwd", h->interp ? 3 : 1);
+    LaunchScope ls(h, "lse_bwd", h->interp ? (h->lean ? 2 : 3) : 1);
     if (h->interp) {
       // K = 1: dMx[g][j] = H_j(w_g); the plan of this step's forward pass is still valid (psi, W unchanged)
       dim3 gn((h->J + 31) / 32, kIGroupsY, kISplitB);
       CA_LAUNCH(k_interp_nodes<false>, gn, 256, 0, h->stream)(h->iplan, h->U, h->shift, h->Rx, h->N, h->J, h->ivals);
       CA_LAUNCH(k_interp_coeffs, dim3((h->J + 31) / 32, kIMaxPanB), kIP * 32, 0, h->stream)(h->iplan, h->ivals, kISplitB, kIMaxPanB, h->J, 0, h->icoef);
-      CA_LAUNCH(k_interp_eval<false>, h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream)(h->iplan, h->icoef, h->Vm, h->G, h->J, h->dMx,
-                                                                                   h->ieval_panels);
+      if (!h->lean)
+        CA_LAUNCH(k_interp_eval<false>, h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream)(h->iplan, h->icoef, h->Vm, h->G, h->J, h->dMx,
+                                                                                     h->ieval_panels);
     } else if (h->tc) {
       tc_launch_bwd(h->tcplan, h->U, h->Vm, h->shift_bwd, h->dMx, h->stream);
     } else {
@@ -484,7 +505,17 @@ void run_train(ca_handle* h, bool apply) {
     }
     KCHECK();
   }
-  {
+  if (h->lean) {
+    LaunchScope ls(h, "gene_grads", 1);
+    GeneFusedArgs a;
+    a.G = h->G; a.C = h->C; a.S = h->S; a.SC = h->SC; a.J = h->J; a.nRB = h->nRB; a.smem_panels = h->gene_panels;
+    a.plan = h->iplan; a.coeff = h->icoef;
+    a.Vm = h->Vm; a.colpart = h->colpart; a.mu = h->mu; a.sig = h->sig; a.eps = h->eps; a.lsd = h->lsd; a.L = h->L;
+    a.ar = h->ar; a.YtU = h->YtU; a.dM_out = h->inspect ? h->dM_sum : nullptr;
+    a.gsum_part = h->gsum_part; a.n_parts = h->n_cell_parts;
+    CA_LAUNCH(k_gene_fused, h->num_sms + 1, kGeneWarps * 32, h->gene_smem, h->stream)(a);
+    KCHECK();
+  } else {
     LaunchScope ls(h, "gene_grads", 2);
     GeneGradArgs a;
     a.G = h->G; a.C = h->C; a.S = h->S; a.K = h->K; a.KP = h->KP; a.SCp = h->SCp; a.J = h->J; a.nsplit = h->nsplit; a.nRB = h->nRB;
@@ -501,10 +532,12 @@ void run_train(ca_handle* h, bool apply) {
     NCCL_OK(nccl().AllReduce(h->ar, h->ar, cnt, kNcclFloat32, kNcclSum, h->comm, h->stream));
   }
   {
-    LaunchScope ls(h, "adam", apply ? 4 : 3);
+    LaunchScope ls(h, "adam", h->lean ? 1 : (apply ? 4 : 3));
     AdamHyper hy = adam_hyper(h, apply);
-    CA_LAUNCH(k_wsq, 1, 1024, 0, h->stream)(h->Vm, h->G, h->K, h->KP, h->wsq);
-    KCHECK();
+    if (!h->lean) {
+      CA_LAUNCH(k_wsq, 1, 1024, 0, h->stream)(h->Vm, h->G, h->K, h->KP, h->wsq);
+      KCHECK();
+    }
     ScalarAdamArgs sa;
     sa.G = h->G; sa.C = h->C; sa.K = h->K; sa.n_total = (double)h->Ntot; sa.wsq = h->wsq;
     sa.gsum = h->ar + (int64_t)h->G * (2 + h->KP);
@@ -515,12 +548,22 @@ void run_train(ca_handle* h, bool apply) {
     ga.eps = h->eps; ga.colsum = h->colsum; ga.chi_raw = h->chi_raw; ga.loc = h->loc; ga.lsd = h->lsd; ga.Vm = h->Vm;
     ga.m_loc = h->m_loc; ga.v_loc = h->v_loc; ga.m_lsd = h->m_lsd; ga.v_lsd = h->v_lsd; ga.m_V = h->m_V; ga.v_V = h->v_V;
     ga.g_loc = h->g_loc; ga.g_lsd = h->g_lsd; ga.g_V = h->g_V; ga.h = hy;
+    if (h->lean) {
+      AdamAllArgs aa;
+      aa.ga = ga; aa.chi_cur = h->chi_cur; aa.sa = sa; aa.N = h->N; aa.C = h->C;
+      aa.t = h->t; aa.m_t = h->m_t; aa.v_t = h->v_t; aa.U = h->U; aa.m_U = h->m_U; aa.v_U = h->v_U; aa.gT = h->g_t; aa.gU = h->g_U;
+      aa.n_gene_blocks = (h->G + 255) / 256;
+      aa.n_cell_blocks = apply ? ceil_div64(h->N * h->C + h->N, 256) : 0;
+      CA_LAUNCH(k_adam_all, (unsigned)(aa.n_gene_blocks + aa.n_cell_blocks + 1), 256, 0, h->stream)(aa);
+      KCHECK();
+    } else {
     // gene kernel reads chi_raw (old) -> must precede the scalar update
     CA_LAUNCH(k_gene_adam, (h->G + 127) / 128, 128, 0, h->stream)(ga);
     KCHECK();
     CA_LAUNCH(k_scalar_adam, 1, 32, 0, h->stream)(sa);
     KCHECK();
-    if (apply) {
+    }
+    if (apply && !h->lean) {
       int64_t tot = h->N * h->C + h->N * h->KP;
       CA_LAUNCH(k_cell_adam, (unsigned)ceil_div64(tot, 256), 256, 0, h->stream)(h->N, h->C, h->K, h->KP, h->t, h->m_t, h->v_t, h->g_t,
                                                                        h->U, h->m_U, h->v_U, h->g_U, hy);
@@ -670,7 +713,9 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if (c.path == CA_PATH_INTERP && !(c.K == 1 && c.P == 0)) fail("interp path needs K == 1 and P == 0");
   h->interp = (c.path == CA_PATH_INTERP);
   h->variants = c.variants;
-  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2)) fail("unknown kernel variant bits 0x%x", c.variants);
+  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN)) fail("unknown kernel variant bits 0x%x", c.variants);
+  if ((c.variants & CA_VAR_LEAN) && !(c.variants & CA_VAR_EPI2)) fail("variant lean needs variant epi2");
+  h->lean = (c.variants & CA_VAR_LEAN) != 0;
   if ((c.variants & CA_VAR_YPASS2) && c.K + c.P != 1) fail("variant ypass2 needs K + P == 1");
   if (c.variants & CA_VAR_EPI2) {
     if (!h->interp) fail("variant epi2 belongs to the interp path (path = interp)");
@@ -873,6 +918,16 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
       CUDA_OK(cudaFuncSetAttribute(k_interp_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ieval_smem));
       CUDA_OK(cudaFuncSetAttribute(k_interp_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ieval_smem));
     }
+  }
+  if (h->lean) {
+    h->chi_cur = h->alloc<double>(std::max(K, 1));
+    h->pmm_part = h->alloc<float>(2 * kProPsiBlocks);
+    h->ticket = h->alloc<unsigned>(1);
+    h->gene_panels = gene_fused_smem_panels(J);
+    if (const char* e = getenv("CLONEALIGN_B200_FUSED_PANELS")) h->gene_panels = std::max(0, std::min(h->gene_panels, atoi(e)));
+    h->gene_smem = gene_fused_smem_bytes(J, h->gene_panels);
+    if (h->gene_smem > 48 * 1024)
+      CUDA_OK(cudaFuncSetAttribute(k_gene_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gene_smem));
   }
   if (h->epi2) {
     h->fused_nj = (h->SC + 31) / 32;

@@ -252,4 +252,292 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused(FusedArgs a)
   }
 }
 
+
+// =====================================================================================================================
+// Variant LEAN (with EPI2): fewer, fatter launches for the gene-level / scalar work that every rank of a cell-sharded
+// fit replicates and that therefore bounds strong scaling (profiles/r01_notes.md: ~0.25 ms per step independent of N).
+//   k_prologue   = k_alpha + k_minmax(W) + k_wsq + k_minmax(psi) + k_interp_plan          (5 launches -> 1)
+//   k_gene_fused = k_interp_eval<BWD> + k_gene_grads_warp + k_reduce_gsum                  (3 launches -> 1, no dMx round trip)
+//   k_adam_all   = k_gene_adam + k_scalar_adam + k_cell_adam                               (3 launches -> 1)
+// =====================================================================================================================
+constexpr int kProThreads = 512;
+constexpr int kProPsiBlocks = 30;   // psi min/max partials (blocks 2 .. 2 + kProPsiBlocks - 1)
+
+struct PrologueArgs {
+  int64_t N;
+  int G, C, K;
+  const float *u, *chi_raw, *Vm, *U;
+  float *log_alpha, *mm, *mm_psi;
+  double *scal_elbo, *wsq, *chi_cur;   // chi_cur[k] = exp(chi_raw[k]) of THIS step (read by k_adam_all)
+  float* pmm_part;       // [kProPsiBlocks][2]
+  unsigned* ticket;      // zero before the first launch; the last block resets it
+  InterpPlan* plan;
+  double dirichlet_const;   // C lgamma(1/C) - lgamma(1)   (host)
+};
+
+// roles by block: 0 = alpha / scalar priors (k_alpha), 1 = W range and sum of squares (k_minmax, k_wsq; K == 1),
+// 2.. = psi range partials; the block that arrives last combines the ranges into the panel plan (k_interp_plan).
+__global__ void __launch_bounds__(kProThreads) k_prologue(PrologueArgs a) {
+  __shared__ double dscr[32];
+  __shared__ float smin[32], smax[32];
+  __shared__ int is_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (blockIdx.x == 0) {
+    if (wid == 0) {
+      // log_softmax(alpha_unconstr) (R/inference-tflow.R:255), Dirichlet(1/C) prior on alpha + 1e-3 (:324),
+      // chi = exp(chi_raw) (:241) and its Gamma(2,1) prior (:315)
+      double mx = -1e300;
+      for (int c = lane; c < a.C; c += 32) mx = fmax(mx, (double)a.u[c]);
+      mx = warp_max(mx);
+      double z = 0.0;
+      for (int c = lane; c < a.C; c += 32) z += exp((double)a.u[c] - mx);
+      z = warp_sum(z);
+      const double lzv = mx + log(z);
+      double e = 0.0;
+      for (int c = lane; c < a.C; c += 32) {
+        const double la = (double)a.u[c] - lzv;
+        a.log_alpha[c] = (float)la;
+        e += (1.0 / a.C - 1.0) * log(exp(la) + 1e-3);
+      }
+      for (int k = lane; k < a.K; k += 32) {
+        const double ch = exp((double)a.chi_raw[k]);
+        a.chi_cur[k] = ch;
+        e += (double)a.chi_raw[k] - ch;
+      }
+      e = warp_sum(e);
+      if (lane == 0) a.scal_elbo[0] = e - a.dirichlet_const;
+    }
+  } else if (blockIdx.x == 1) {
+    float mn = 3.4e38f, mx = -3.4e38f;
+    double sq = 0.0;
+    for (int g = threadIdx.x; g < a.G; g += blockDim.x) {
+      const float v = a.Vm[g];
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
+      sq += (double)v * (double)v;
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (lane == 0) { smin[wid] = mn; smax[wid] = mx; }
+    const double tot = block_sum(sq, dscr);   // contains the barriers that also publish smin / smax
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < nw; ++i) { mn = fminf(mn, smin[i]); mx = fmaxf(mx, smax[i]); }
+      a.mm[0] = mn;
+      a.mm[1] = mx;
+      a.wsq[0] = tot;
+    }
+  } else {
+    const int pb = blockIdx.x - 2;
+    const int64_t per = (a.N + kProPsiBlocks - 1) / kProPsiBlocks;
+    const int64_t beg = (int64_t)pb * per, end = beg + per < a.N ? beg + per : a.N;
+    float mn = 3.4e38f, mx = -3.4e38f;
+    for (int64_t n = beg + threadIdx.x; n < end; n += blockDim.x) {
+      const float v = a.U[n];
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (lane == 0) { smin[wid] = mn; smax[wid] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < nw; ++i) { mn = fminf(mn, smin[i]); mx = fmaxf(mx, smax[i]); }
+      a.pmm_part[2 * pb] = mn;
+      a.pmm_part[2 * pb + 1] = mx;
+    }
+  }
+  // last block to arrive builds the plan
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    const volatile float* pp = a.pmm_part;
+    const volatile float* mw = a.mm;
+    float mn = 3.4e38f, mx = -3.4e38f;
+    for (int i = 0; i < kProPsiBlocks; ++i) { mn = fminf(mn, pp[2 * i]); mx = fmaxf(mx, pp[2 * i + 1]); }
+    a.mm_psi[0] = mn;
+    a.mm_psi[1] = mx;
+    *a.plan = interp_make_plan((double)mw[0], (double)mw[1], (double)mn, (double)mx);
+    *a.ticket = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// gene kernel: dMx[g][j] = H_j(w_g) by Clenshaw (k_interp_eval<BWD>) consumed in place by the gene-gradient reductions
+// (k_gene_grads_warp); the last block reduces the sum-gamma partials into the allreduce buffer (k_reduce_gsum).
+// One warp per gene, persistent blocks, coefficients of the active backward panels staged in shared memory.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kGeneWarps = 16;
+struct GeneFusedArgs {
+  int G, C, S, SC, J, nRB, smem_panels;
+  const InterpPlan* plan;
+  const double* coeff;       // [panel][kIP][J] backward coefficients
+  const float *Vm, *colpart, *mu, *sig, *eps, *lsd, *L;
+  float *ar, *YtU, *dM_out;  // dM_out: inspection copy [G][J] or nullptr
+  const double* gsum_part;   // [n_parts][C]
+  int64_t n_parts;
+};
+inline size_t gene_fused_smem_bytes(int J, int smem_panels) { return (size_t)smem_panels * kFusedPitch * J * sizeof(double) + 16; }
+inline int gene_fused_smem_panels(int J, size_t budget = 96 * 1024) {
+  size_t n = budget / ((size_t)kFusedPitch * J * sizeof(double));
+  return (int)(n > (size_t)kIMaxPanB ? (size_t)kIMaxPanB : n);
+}
+
+__global__ void __launch_bounds__(kGeneWarps * 32) k_gene_fused(GeneFusedArgs a) {
+  CA_DYNAMIC_SMEM(double, csm);
+  __shared__ double scratch[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (blockIdx.x == gridDim.x - 1) {   // role: sum_n gamma_nc partials -> float slots of the allreduce buffer
+    float* out = a.ar + 3 * (int64_t)a.G;
+    for (int c = 0; c < a.C; ++c) {
+      double s = 0.0;
+      for (int64_t i = threadIdx.x; i < a.n_parts; i += blockDim.x) s += a.gsum_part[i * a.C + c];
+      const double t = block_sum(s, scratch);
+      if (threadIdx.x == 0) out[c] = (float)t;
+    }
+    return;
+  }
+  const InterpPlan pl = *a.plan;
+  const int npan = pl.nb;
+  const bool in_smem = npan <= a.smem_panels;
+  const int64_t per_panel = (int64_t)kIP * a.J;
+  if (in_smem) {
+    for (int64_t i = threadIdx.x; i < npan * per_panel; i += blockDim.x) {
+      const int j = (int)(i % a.J);
+      const int64_t pk = i / a.J;
+      csm[((pk / kIP) * a.J + j) * kFusedPitch + (int)(pk % kIP)] = a.coeff[i];
+    }
+    __syncthreads();
+  }
+  const double ih = pl.b_w > 0.0 ? 2.0 / pl.b_w : 0.0;
+  const int nblk = gridDim.x - 1;
+  const int SC = a.SC;
+  for (int g = blockIdx.x * kGeneWarps + wid; g < a.G; g += nblk * kGeneWarps) {
+    const float wf = a.Vm[g];
+    const double x = (double)wf;
+    int pb = (int)((x - pl.wmin) * ih * 0.5);
+    pb = pb < 0 ? 0 : (pb >= pl.nb ? pl.nb - 1 : pb);
+    const double tt = pl.b_w > 0.0 ? (x - (pl.wmin + pb * pl.b_w)) * ih - 1.0 : 0.0;
+    const double* cpan = in_smem ? csm + (size_t)pb * a.J * kFusedPitch : a.coeff + (int64_t)pb * per_panel;
+    const float sd = expf(a.lsd[g]);
+    double aloc = 0.0, alsd = 0.0, gv = 0.0;
+    for (int j0 = 0; j0 < SC; j0 += 32) {
+      const int j = j0 + lane;
+      const bool ok = j < SC;
+      const int jc[1] = {ok ? j : SC - 1};
+      double d[1], d2[1];
+      if (in_smem) {
+        clenshaw_cols<1, true>(cpan, jc, 0, a.J, tt, d);
+        clenshaw_cols<1, true>(cpan, jc, SC, a.J, tt, d2);
+      } else {
+        clenshaw_cols<1, false>(cpan, jc, 0, a.J, tt, d);
+        clenshaw_cols<1, false>(cpan, jc, SC, a.J, tt, d2);
+      }
+      if (ok) {
+        const int s = j / a.C, c = j - s * a.C;
+        const int64_t o = (int64_t)s * a.G + g;
+        const float l = a.L[(int64_t)g * a.C + c];
+        const float df = (float)d[0], d2f = (float)d2[0];   // the unfused path rounds dMx to fp32: keep its numerics
+        if (a.dM_out) {
+          a.dM_out[(int64_t)g * a.J + j] = df;
+          a.dM_out[(int64_t)g * a.J + SC + j] = d2f;
+        }
+        const double dx = -(double)a.sig[o] * (double)l * (double)df;
+        aloc += dx;
+        alsd += dx * (double)sd * (double)a.eps[o];
+        gv -= (double)(a.mu[o] * l) * (double)d2f;
+      }
+    }
+    aloc = warp_sum(aloc);
+    alsd = warp_sum(alsd);
+    gv = warp_sum(gv);
+    double acc = 0.0;
+    for (int rb = lane; rb < a.nRB; rb += 32) acc += (double)a.colpart[(int64_t)rb * a.G + g];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      a.YtU[g] = (float)acc;
+      a.ar[2 * (int64_t)a.G + g] = (float)(acc + gv);
+      a.ar[g] = (float)aloc;
+      a.ar[a.G + g] = (float)alsd;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// optimiser: gene-level (k_gene_adam), per-cell (k_cell_adam) and scalar (k_scalar_adam) Adam updates in one launch.
+// Gene blocks read chi from chi_cur (written by k_prologue from the OLD chi_raw), so the scalar block may update
+// chi_raw concurrently.
+// ---------------------------------------------------------------------------------------------------------------------
+struct AdamAllArgs {
+  GeneAdamArgs ga;
+  const double* chi_cur;
+  ScalarAdamArgs sa;
+  int64_t N;
+  int C;
+  float *t, *m_t, *v_t, *U, *m_U, *v_U;
+  const float *gT, *gU;
+  int n_gene_blocks;
+  int64_t n_cell_blocks;
+};
+__global__ void __launch_bounds__(256) k_adam_all(AdamAllArgs a) {
+  const int64_t b = blockIdx.x;
+  if (b < a.n_gene_blocks) {
+    const GeneAdamArgs& q = a.ga;
+    const int g = (int)b * blockDim.x + threadIdx.x;
+    if (g >= q.G) return;
+    const float lsd = q.lsd[g];
+    const double sd = exp((double)lsd), cs = (double)q.colsum[g];
+    double gl = (double)q.ar[g], gs = (double)q.ar[q.G + g];
+    for (int s = 0; s < q.S; ++s) {
+      const int64_t o = (int64_t)s * q.G + g;
+      const double mu = (double)q.mu[o], sg = (double)q.sig[o];
+      const double dmu = (cs - (double)q.logmu[o]) / ((double)q.S * mu);
+      const double dx = sg * dmu + (1.0 - sg) / (double)q.S;
+      gl += dx;
+      gs += dx * sd * (double)q.eps[o];
+    }
+    gs += 1.0;
+    const float gloc = (float)gl, glsd = (float)gs;
+    q.g_loc[g] = gloc;
+    q.g_lsd[g] = glsd;
+    const float gw = (float)((double)q.ar[2 * (int64_t)q.G + g] - a.chi_cur[0] * (double)q.Vm[g]);   // K == 1, P == 0
+    q.g_V[g] = gw;
+    if (q.h.apply) {
+      adam_update(q.loc[g], q.m_loc[g], q.v_loc[g], gloc, q.h);
+      adam_update(q.lsd[g], q.m_lsd[g], q.v_lsd[g], glsd, q.h);
+      adam_update(q.Vm[g], q.m_V[g], q.v_V[g], gw, q.h);
+    }
+  } else if (b < a.n_gene_blocks + a.n_cell_blocks) {
+    if (!a.ga.h.apply) return;
+    const int64_t i = (b - a.n_gene_blocks) * blockDim.x + threadIdx.x;
+    const int64_t nt = a.N * a.C;
+    if (i < nt) adam_update(a.t[i], a.m_t[i], a.v_t[i], a.gT[i], a.ga.h);
+    else if (i - nt < a.N) adam_update(a.U[i - nt], a.m_U[i - nt], a.v_U[i - nt], a.gU[i - nt], a.ga.h);
+  } else if (threadIdx.x == 0) {
+    const ScalarAdamArgs& q = a.sa;
+    const double chi = exp((double)q.chi_raw[0]);
+    q.g_chi[0] = (float)(-0.5 * chi * q.wsq[0] + 0.5 * (double)q.G + 1.0 - chi);
+    double mx = -1e300;
+    for (int c = 0; c < q.C; ++c) mx = fmax(mx, (double)q.u[c]);
+    double z = 0.0;
+    for (int c = 0; c < q.C; ++c) z += exp((double)q.u[c] - mx);
+    double rsum = 0.0;
+    for (int c = 0; c < q.C; ++c) {
+      const double al = exp((double)q.u[c] - mx) / z;
+      rsum += al / (al + 1e-3);
+    }
+    for (int c = 0; c < q.C; ++c) {
+      const double al = exp((double)q.u[c] - mx) / z;
+      const double r = al / (al + 1e-3);
+      q.g_u[c] = (float)((double)q.gsum[c] - q.n_total * al + (1.0 / q.C - 1.0) * (r - al * rsum));
+    }
+    if (q.h.apply) {
+      adam_update(q.chi_raw[0], q.m_chi[0], q.v_chi[0], q.g_chi[0], q.h);
+      for (int c = 0; c < q.C; ++c) adam_update(q.u[c], q.m_u[c], q.v_u[c], q.g_u[c], q.h);
+    }
+  }
+}
+
 }  // namespace ca

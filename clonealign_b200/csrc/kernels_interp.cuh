@@ -58,12 +58,11 @@ __device__ __forceinline__ void bwd_panel(const InterpPlan& pl, int pb, double& 
 }
 __device__ __forceinline__ double cheb_node(int p) { return cos(kPi * (p + 0.5) / kIP); }
 
-// one thread: panel structure from the current ranges of psi and w
-__global__ void k_interp_plan(const float* __restrict__ mm_w, const float* __restrict__ mm_psi, InterpPlan* __restrict__ plan) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// panel structure from the current ranges of psi and w
+__device__ __forceinline__ InterpPlan interp_make_plan(double wmin, double wmax, double pmin, double pmax) {
   InterpPlan pl;
-  pl.wmin = (double)mm_w[0]; pl.wmax = (double)mm_w[1];
-  pl.pmin = (double)mm_psi[0]; pl.pmax = (double)mm_psi[1];
+  pl.wmin = wmin; pl.wmax = wmax;
+  pl.pmin = pmin; pl.pmax = pmax;
   const double D = pl.wmax - pl.wmin;
   auto count = [](double width, double scale, int cap) {
     int n = (int)ceil(scale * width / 2.0 / kIAmax);
@@ -84,7 +83,12 @@ __global__ void k_interp_plan(const float* __restrict__ mm_w, const float* __res
   const double A = fmax(fabs(pl.pmin), fabs(pl.pmax));
   pl.nb = count(D, A, kIMaxPanB);
   pl.b_w = D / pl.nb;
-  *plan = pl;
+  return pl;
+}
+// one thread
+__global__ void k_interp_plan(const float* __restrict__ mm_w, const float* __restrict__ mm_psi, InterpPlan* __restrict__ plan) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  *plan = interp_make_plan((double)mm_w[0], (double)mm_w[1], (double)mm_psi[0], (double)mm_psi[1]);
 }
 
 // Node values.  FWD: part[z][node][j] = sum_{g in split z} Mx[g][j] exp(x_node (w_g - wref));  reduction index = genes.

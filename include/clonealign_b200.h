@@ -59,8 +59,9 @@ enum ca_path     { CA_PATH_AUTO = 0, CA_PATH_CUDACORE = 1, CA_PATH_TENSOR = 2, C
  * a re-engineered version with the same inputs/outputs; they are opt-in until measured on hardware (bench.py validates
  * them on the device against the default kernels before using them).
  *   YPASS2: Y pass on packed fp32 pairs (add/fma.rn.f32x2), see kernels_ypass.cuh
- *   EPI2  : (interp path) Clenshaw evaluation fused into a leaner per-cell epilogue, see kernels_fused.cuh        */
-enum ca_variant  { CA_VAR_YPASS2 = 1, CA_VAR_EPI2 = 2 };
+ *   EPI2  : (interp path) Clenshaw evaluation fused into a leaner per-cell epilogue, see kernels_fused.cuh
+ *   LEAN  : (with EPI2) gene-level / scalar / optimiser work in 3 launches instead of 11, see kernels_fused.cuh    */
+enum ca_variant  { CA_VAR_YPASS2 = 1, CA_VAR_EPI2 = 2, CA_VAR_LEAN = 4 };
 
 typedef struct ca_config {
   int64_t N;            /* cells held by this handle (this rank's shard)                       */

@@ -15,7 +15,7 @@ from test_gpu_parity import ELBO_RTOL, PARAM_RTOL, _case, _check_grads, _load_pa
 pytestmark = pytest.mark.usefixtures("emulated_library")
 # (contraction path, kernel variants): the default kernels of both non-tensor paths and the re-engineered variants
 # (packed-fp32 Y pass, fused Clenshaw + per-cell epilogue) that bench.py validates on the device before using them
-PATHS = [("cudacore", ""), ("interp", ""), ("cudacore", "ypass2"), ("interp", "ypass2,epi2")]
+PATHS = [("cudacore", ""), ("interp", ""), ("cudacore", "ypass2"), ("interp", "ypass2,epi2"), ("interp", "ypass2,epi2,lean")]
 
 
 def test_emulated_library_is_not_the_product(emulated_library):
@@ -215,6 +215,8 @@ def test_variant_validation(example_sce):
         _session(d.Y, d.L, p.psi, mu_guess, variants="nope")
     with _session(d.Y, d.L, p.psi, mu_guess, path="interp", variants=["ypass2", "epi2"]) as sess:
         assert sess.describe()["variants"] == 3
+    with pytest.raises(CloneAlignLibraryError, match="lean needs variant epi2"):
+        _session(d.Y, d.L, p.psi, mu_guess, path="interp", variants="lean")
 
 
 def test_variants_agree_with_default_kernels(example_sce):
@@ -223,7 +225,7 @@ def test_variants_agree_with_default_kernels(example_sce):
     Y, L = example_sce
     hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
     out = {}
-    for name, (path, var) in {"ref": ("cudacore", ""), "new": ("interp", "ypass2,epi2")}.items():
+    for name, (path, var) in {"ref": ("cudacore", ""), "new": ("interp", "ypass2,epi2,lean")}.items():
         with _session(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], mc_samples=2, seed=5, path=path, variants=var) as sess:
             sess.init_gamma()
             tr = [sess.elbo()]
