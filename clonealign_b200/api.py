@@ -55,13 +55,16 @@ def clonealign(gene_expression_data, copy_number_data, max_iter=200, rel_tol=1e-
                learning_rate=0.1, x=None, clone_allele=None, cov=None, ref=None, fix_alpha=False, dtype="float32",
                saturate=True, saturation_threshold=6, K=None, mc_samples=1, verbose=True, initial_shrink=5,
                clone_call_probability=0.95, data_init_mu=True, clone_names=None, gene_names=None, seed=None,
-               device=0, fix_ref_bug=False, **backend):
+               device=0, fix_ref_bug=False, device_correlations=False, **backend):
     """Assign cells to clones (R/clonealign.R:184-305).
 
     gene_expression_data: cell x gene count matrix (an R user passes a SingleCellExperiment whose
     counts assay is transposed to this, :212-222).  copy_number_data: gene x clone matrix.
     `fix_ref_bug=False` keeps the reference's `ref = cov` forwarding (:271) which makes the
     alternate-allele count identically zero; pass True to forward `ref` as documented.
+    `device_correlations=True` computes the post-hoc gene/copy-number correlations (:292-294) with one pass over the Y
+    that is already resident in HBM (ca_core_correlations) instead of the host loop; the default stays the host mirror
+    until that kernel has been run on hardware (it is verified on the CPU emulation, tests/test_emul_parity.py).
     """
     Y = np.asarray(gene_expression_data)
     if Y.ndim != 2:
@@ -86,12 +89,15 @@ def clonealign(gene_expression_data, copy_number_data, max_iter=200, rel_tol=1e-
                           ref=(ref if fix_ref_bug else cov), fix_alpha=fix_alpha, dtype=dtype, saturate_=saturate,
                           saturation_threshold=saturation_threshold, K=K, mc_samples=mc_samples, verbose=verbose,
                           initial_shrink=initial_shrink, data_init_mu=data_init_mu, seed=seed, device=device,
-                          gene_names=gene_names, **backend)                             # :262-280
+                          gene_names=gene_names, correlations_with=(L, clone_call_probability) if device_correlations else None,
+                          **backend)                                                    # :262-280
+    dev_cor = res.pop("correlations", None)
     fit = CloneAlignFit(res)
     fit["clone"] = clone_assignment(res["ml_params"]["clone_probs"], clone_names, clone_call_probability)   # :283
     fit["clone_names"] = clone_names
     ridx = [gene_names.index(g) for g in res["retained_genes"]]
-    fit["correlations"] = compute_correlations(Y[:, ridx], L[ridx, :], fit["clone"], clone_names)          # :292-294
+    fit["correlations"] = dev_cor if dev_cor is not None else \
+        compute_correlations(Y[:, ridx], L[ridx, :], fit["clone"], clone_names)                            # :292-294
     cor = fit["correlations"]
     if np.any(~np.isnan(cor)) and np.nanquantile(cor, 0.25) < 0:                        # :296-300
         warnings.warn("Less than 75% of genes positively correlated with expression - assignment may have failed")

@@ -1238,6 +1238,41 @@ int ca_core_profile_step(ca_handle* h, char* names, size_t names_len, double* ms
   } catch (const std::exception& e) { return report(e, err, errlen); }
 }
 
+int ca_core_correlations(ca_handle* h, const int32_t* clone_idx, const double* L, double* out, char* err, size_t errlen) {
+  try {
+    if (!h || !clone_idx || !out) fail("bad argument");
+    CUDA_OK(cudaSetDevice(h->dev));
+    const int64_t N = h->N;
+    const int G = h->G, C = h->C;
+    if ((size_t)C * 128 * sizeof(float) > 48 * 1024) fail("too many clones for the correlation kernel");
+    int* d_z = nullptr;
+    float* d_L = nullptr;
+    double *d_part = nullptr, *d_out = nullptr;
+    const int RS = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 64));
+    CUDA_OK(cudaMalloc(&d_z, sizeof(int) * N));
+    CUDA_OK(cudaMalloc(&d_L, sizeof(float) * (size_t)G * C));
+    CUDA_OK(cudaMalloc(&d_part, sizeof(double) * (size_t)RS * G * 5));
+    CUDA_OK(cudaMalloc(&d_out, sizeof(double) * G));
+    int64_t n_assigned = 0;
+    for (int64_t n = 0; n < N; ++n) n_assigned += (clone_idx[n] >= 0 && clone_idx[n] < C) ? 1 : 0;
+    CUDA_OK(cudaMemcpyAsync(d_z, clone_idx, sizeof(int) * N, cudaMemcpyHostToDevice, h->stream));
+    if (L) upload_colmajor(h, L, G, C, d_L, C, 0);
+    else CUDA_OK(cudaMemcpyAsync(d_L, h->L, sizeof(float) * (size_t)G * C, cudaMemcpyDeviceToDevice, h->stream));
+    dispatch_y(h, [&](auto* Yp) {
+      using T = typename std::remove_const<typename std::remove_pointer<decltype(Yp)>::type>::type;
+      dim3 grid((G + 127) / 128, RS);
+      CA_LAUNCH(k_corr_part<T>, grid, 128, sizeof(float) * C * 128, h->stream)(Yp, h->ldY, N, G, C, d_z, d_L, RS, d_part);
+      KCHECK();
+    });
+    CA_LAUNCH(k_corr_final, (G + 127) / 128, 128, 0, h->stream)(d_part, RS, G, (double)n_assigned, d_out);
+    KCHECK();
+    CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(double) * G, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_z); cudaFree(d_L); cudaFree(d_part); cudaFree(d_out);
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
 int ca_core_describe(ca_handle* h, char* json, size_t json_len) {
   if (!h || !json || !json_len) return 1;
   const char* st = h->ystore == CA_STORE_F32 ? "f32" : (h->ystore == CA_STORE_U16 ? "u16" : "u8");

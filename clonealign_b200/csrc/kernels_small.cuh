@@ -127,6 +127,47 @@ __global__ void k_softmax_rows(const float* __restrict__ in, int64_t N, int C, f
 }
 
 // =============================================================================================
+// post-hoc: per-gene Pearson correlation between expression and the copy number of the assigned clone
+// (compute_correlations, R/clonealign.R:318-334; cor(x, scale(y)) == cor(x, y)).  One pass over the resident Y.
+// zidx[n] = clone index of cell n or < 0 for "unassigned" (excluded, :319-320).  Lc: G x C copy number, row-major.
+// part[rs][g][5] = sum over the assigned cells of the row slice of (y, y^2, x, x^2, x y), x = Lc[g][zidx[n]].
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(128)
+k_corr_part(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int C, const int* __restrict__ zidx,
+            const float* __restrict__ Lc, int RS, double* __restrict__ part) {
+  CA_DYNAMIC_SMEM(float, Ls);   // [C][128]
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int c = 0; c < C; ++c) Ls[c * 128 + threadIdx.x] = g < G ? Lc[(int64_t)g * C + c] : 0.f;
+  __syncthreads();
+  if (g >= G) return;
+  const int64_t rps = ceil_div64(N, RS);
+  const int64_t r0 = blockIdx.y * rps, r1 = r0 + rps < N ? r0 + rps : N;
+  double sy = 0.0, syy = 0.0, sx = 0.0, sxx = 0.0, sxy = 0.0;
+  for (int64_t r = r0; r < r1; ++r) {
+    const int z = zidx[r];
+    if (z < 0 || z >= C) continue;
+    const double y = (double)(float)Y[r * ldY + g];
+    const double x = (double)Ls[z * 128 + threadIdx.x];
+    sy += y; syy += y * y; sx += x; sxx += x * x; sxy += x * y;
+  }
+  double* o = part + ((int64_t)blockIdx.y * G + g) * 5;
+  o[0] = sy; o[1] = syy; o[2] = sx; o[3] = sxx; o[4] = sxy;
+}
+// n_assigned cells in total; NaN where x or y is constant or fewer than 2 cells are assigned (R's cor gives NA)
+__global__ void k_corr_final(const double* __restrict__ part, int RS, int G, double n_assigned, double* __restrict__ out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int r = 0; r < RS; ++r)
+    for (int q = 0; q < 5; ++q) s[q] += part[((int64_t)r * G + g) * 5 + q];
+  const double n = n_assigned;
+  const double vy = n * s[1] - s[0] * s[0], vx = n * s[3] - s[2] * s[2];
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  out[g] = (n >= 2.0 && vy > 0.0 && vx > 0.0) ? (n * s[4] - s[2] * s[0]) / sqrt(vx * vy) : nan;
+}
+
+// =============================================================================================
 // per-iteration gene-level kernels
 // =============================================================================================
 

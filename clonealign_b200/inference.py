@@ -89,7 +89,7 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
                     x=None, clone_allele=None, cov=None, ref=None, fix_alpha=False, dtype="float32",
                     saturate_=True, saturation_threshold=6, K=1, mc_samples=1, verbose=True, initial_shrink=5,
                     data_init_mu=True, seed=None, device=0, psi_init=None, y_store="auto", path="auto",
-                    gene_names=None):
+                    gene_names=None, variants=None, correlations_with=None):
     """CUDA-backed equivalent of the reference's `inference_tflow`.
 
     Y_dat: cell x gene counts; L_dat: gene x clone copy number.  Returns the reference's list as a dict:
@@ -97,6 +97,9 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
     sd_final_elbo, elbo}, retained_genes, clone_probs_from_snv (R/inference-tflow.R:475-480).
     `fix_alpha` and `initial_shrink` are accepted and ignored, as in the reference (:81,:88).
     `psi_init` (N x K) skips the PCA; it exists for callers that compute the initialisation elsewhere.
+    `correlations_with = (L_unsaturated, clone_call_probability)`: also run the caller's post-hoc
+    `compute_correlations` (R/clonealign.R:292-294,318-334) on the device while Y is still resident; the result is
+    returned under "correlations" (retained genes only).
     """
     if dtype not in ("float32", "float64"):
         raise ValueError("'arg' should be one of 'float32', 'float64'")
@@ -166,7 +169,8 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
     sess = Session(Y, L, psi_init, safe_inverse_softplus(mu_guess), mc_samples=int(mc_samples), K=K, x=x,
                    learning_rate=learning_rate, seed=op_seed, device=device,
                    clone_allele=clone_allele if use_allele else None, alt=alt, cov=cov if use_allele else None,
-                   y_store=y_store, path=path)
+                   y_store=y_store, path=path, variants=variants)
+    correlations = None
     try:
         sess.init_gamma()                                                             # :368-369
         elbo_val = sess.elbo()                                                        # :372
@@ -189,10 +193,18 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
         clone_probs_from_snv = rlist.pop("clone_probs_from_snv", None)                # :436-440
         _message(verbose, "Computing final ELBO")
         final_elbo = [sess.elbo() for _ in range(20)]                                 # :447-449
+        if correlations_with is not None:
+            L_full, call_p = correlations_with
+            cp = rlist["clone_probs"]
+            zidx = np.where(cp.max(axis=1) < call_p, -1, cp.argmax(axis=1)).astype(np.int32)   # clone_assignment, :22-29
+            correlations = sess.correlations(zidx, np.asarray(L_full, dtype=np.float64)[~zero_gene_means])
     finally:
         sess.close()                                                                  # :457
     convergence_info = {"final_elbo": float(np.mean(final_elbo)),
                         "sd_final_elbo": float(np.std(final_elbo, ddof=1)),
                         "elbo": np.array(elbos)}
-    return {"ml_params": rlist, "convergence_info": convergence_info, "retained_genes": retained_genes,
-            "clone_probs_from_snv": clone_probs_from_snv}
+    out = {"ml_params": rlist, "convergence_info": convergence_info, "retained_genes": retained_genes,
+           "clone_probs_from_snv": clone_probs_from_snv}
+    if correlations is not None:
+        out["correlations"] = correlations
+    return out

@@ -244,6 +244,17 @@ class Session:
         if v.size:
             self._chk(self._lib.ca_core_set_array(self._h, name.encode(), _ptr(v), v.size, self._err, len(self._err)))
 
+    def correlations(self, clone_idx, L=None):
+        """Per-gene Pearson correlation of expression with the assigned clone's copy number, computed on the resident Y
+        (compute_correlations, R/clonealign.R:318-334).  clone_idx: N ints, negative = unassigned; L: G x C or None."""
+        z = np.ascontiguousarray(clone_idx, dtype=np.int32)
+        if z.shape != (self.N,):
+            raise ValueError("clone_idx must have one entry per cell")
+        Lm = _f64_colmajor(L, (self.G, self.C)) if L is not None else None
+        out = np.zeros(self.G, dtype=np.float64)
+        self._chk(self._lib.ca_core_correlations(self._h, _ptr(z), _ptr(Lm), _ptr(out), self._err, len(self._err)))
+        return out
+
     # -- measurement hooks --------------------------------------------------------------------------
     def time_steps(self, n_steps: int, with_eval: bool = False) -> float:
         """Milliseconds (CUDA events on the library's stream) for n_steps train steps [+ ELBO evals]."""

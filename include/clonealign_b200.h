@@ -129,6 +129,12 @@ CA_API int ca_core_grads(ca_handle* h, char* err, size_t errlen);
 CA_API int ca_core_get_array(ca_handle* h, const char* name, double* out, int64_t n, char* err, size_t errlen);
 CA_API int ca_core_set_array(ca_handle* h, const char* name, const double* in, int64_t n, char* err, size_t errlen);
 
+/* Post-hoc per-gene Pearson correlation between expression and the copy number of each cell's assigned clone
+ * (compute_correlations, R/clonealign.R:318-334, called at :292-294) on the Y already resident in HBM.
+ * clone_idx: N clone indices (0-based), < 0 = "unassigned" (excluded).  L: G x C copy number (column-major; the
+ * reference passes the UNsaturated matrix) or NULL for the session's saturated one.  out: G values, NaN where R gives NA. */
+CA_API int ca_core_correlations(ca_handle* h, const int32_t* clone_idx, const double* L, double* out, char* err, size_t errlen);
+
 /* Measurement hooks (bench.py): run n_steps train steps (and, if with_eval != 0, one ELBO
  * evaluation after each, as the reference loop does) back to back on the handle's stream,
  * bracketed by CUDA events on that stream; *ms = elapsed milliseconds. */

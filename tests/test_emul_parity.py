@@ -268,3 +268,35 @@ def test_seed_setting_works_and_na_paths(example_sce):
     L0[3, 1] = 0.0
     with pytest.raises(ValueError, match="Initial elbo is NA"):
         inference_tflow(Y, L0, max_iter=2, verbose=False, seed=1)
+
+
+def test_device_correlations_match_host_mirror(example_sce):
+    """ca_core_correlations (post-hoc compute_correlations, R/clonealign.R:318-334) against the host mirror, with
+    unassigned cells, a constant gene (NA), an unsaturated L, and through clonealign() itself."""
+    from clonealign_b200 import clonealign, compute_correlations
+    Y, L = example_sce
+    keep = Y.sum(0) > 0
+    Y, L = Y[:, keep].copy(), L[keep].copy() * 1.7
+    Y[:, 3] = 2.0                                           # constant expression -> NA
+    rng = np.random.default_rng(4)
+    zidx = rng.integers(-1, L.shape[1], size=Y.shape[0]).astype(np.int32)
+    names = ["A", "B", "C"]
+    clones = ["unassigned" if z < 0 else names[z] for z in zidx]
+    want = compute_correlations(Y, L, clones, names)
+    for store in ("u8", "f32"):
+        with _session(Y, np.minimum(L, 6.0), np.zeros((Y.shape[0], 1)), np.ones(Y.shape[1]), y_store=store) as sess:
+            got = sess.correlations(zidx, L)
+            sat = sess.correlations(zidx)                   # NULL -> the session's saturated copy number
+        assert np.isnan(got[3]) and np.isnan(want[3])
+        ok = ~np.isnan(want)
+        assert (np.isnan(got) == np.isnan(want)).all() and np.abs(got[ok] - want[ok]).max() < 1e-9
+        want_sat = compute_correlations(Y, np.minimum(L, 6.0), clones, names)
+        oks = ~np.isnan(want_sat)
+        assert np.abs(sat[oks] - want_sat[oks]).max() < 1e-6          # the session keeps L in fp32
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = clonealign(example_sce[0], example_sce[1], max_iter=3, verbose=False, seed=5, clone_names=names,
+                       device_correlations=True)
+        b = clonealign(example_sce[0], example_sce[1], max_iter=3, verbose=False, seed=5, clone_names=names)
+    assert a["clone"] == b["clone"]
+    np.testing.assert_allclose(a["correlations"], b["correlations"], atol=1e-9, equal_nan=True)

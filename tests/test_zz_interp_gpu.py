@@ -102,3 +102,18 @@ def test_interp_same_seed_bitwise_identical(example_sce, variants):
     a, ga = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], **kw)
     b, gb = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], **kw)
     assert a.tobytes() == b.tobytes() and ga.tobytes() == gb.tobytes()
+
+
+def test_device_correlations_match_host_mirror(example_sce):
+    """ca_core_correlations on the resident Y against the host mirror of compute_correlations (R/clonealign.R:318-334)."""
+    from clonealign_b200 import compute_correlations
+    Y, L = example_sce
+    keep = Y.sum(0) > 0
+    Y, L = Y[:, keep].copy(), L[keep].copy() * 1.7
+    zidx = np.random.default_rng(4).integers(-1, L.shape[1], size=Y.shape[0]).astype(np.int32)
+    names = ["A", "B", "C"]
+    want = compute_correlations(Y, L, ["unassigned" if z < 0 else names[z] for z in zidx], names)
+    with _session(Y, np.minimum(L, 6.0), np.zeros((Y.shape[0], 1)), np.ones(Y.shape[1])) as sess:
+        got = sess.correlations(zidx, L)
+    ok = ~np.isnan(want)
+    assert (np.isnan(got) == np.isnan(want)).all() and np.abs(got[ok] - want[ok]).max() < 1e-9
