@@ -23,7 +23,7 @@ EXPORTS = (
     "ca_core_abi_version", "ca_core_device_count", "ca_core_nccl_unique_id", "ca_core_create",
     "ca_core_destroy", "ca_core_init_gamma", "ca_core_step", "ca_core_elbo", "ca_core_params",
     "ca_core_set_eps", "ca_core_get_eps", "ca_core_grads", "ca_core_get_array", "ca_core_set_array",
-    "ca_core_time_steps", "ca_core_profile_step", "ca_core_describe", "ca_core_correlations",
+    "ca_core_time_steps", "ca_core_profile_step", "ca_core_describe", "ca_core_correlations", "ca_core_pca_scores",
 )
 
 
@@ -75,6 +75,7 @@ def load():
     lib.ca_core_profile_step.argtypes = [vp, cp, sz, dp, C.c_int32, C.POINTER(C.c_int32), cp, sz]
     lib.ca_core_describe.argtypes = [vp, cp, sz]
     lib.ca_core_correlations.argtypes = [vp, vp, vp, vp, cp, sz]
+    lib.ca_core_pca_scores.argtypes = [vp, C.c_int32, C.c_double, vp, C.POINTER(C.c_int32), cp, sz]
     for n in EXPORTS:
         getattr(lib, n).restype = C.c_int
     if lib.ca_core_abi_version() != ABI_VERSION:

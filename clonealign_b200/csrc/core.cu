@@ -22,6 +22,7 @@
 #include "kernels_expgemm.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_interp.cuh"
+#include "kernels_pca.cuh"
 #include "kernels_small.cuh"
 #ifdef CA_EMULATE   // tests/cuda_emul: functional CPU emulation of the non-tensor kernels (test infrastructure only)
 #include "kernels_tc_stub.h"
@@ -1269,6 +1270,89 @@ int ca_core_correlations(ca_handle* h, const int32_t* clone_idx, const double* L
     CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(double) * G, cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
     cudaFree(d_z); cudaFree(d_L); cudaFree(d_part); cudaFree(d_out);
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_pca_scores(ca_handle* h, int32_t max_iter, double tol, double* scores, int32_t* iters_out, char* err, size_t errlen) {
+  try {
+    if (!h || !scores || max_iter < 1) fail("bad argument");
+    if (h->cfg.world != 1) fail("ca_core_pca_scores: cell-sharded sessions are not supported yet (needs the global column statistics)");
+    CUDA_OK(cudaSetDevice(h->dev));
+    const int64_t N = h->N;
+    const int G = h->G;
+    if (N < 2) fail("need at least two cells");
+    const int RS = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 64));
+    std::vector<void*> tmp;
+    auto dalloc = [&](size_t n) {
+      void* p = nullptr;
+      CUDA_OK(cudaMalloc(&p, sizeof(double) * (n ? n : 1)));
+      tmp.push_back(p);
+      return (double*)p;
+    };
+    double *part = dalloc((size_t)RS * G * 2), *mean = dalloc(G), *inv_sd = dalloc(G), *v = dalloc(G), *w = dalloc(G), *a = dalloc(G),
+           *b = dalloc(1), *t = dalloc(N), *tsum = dalloc(RS), *out2 = dalloc(2);
+    int* bad = (int*)dalloc(1);
+    CUDA_OK(cudaMemsetAsync(bad, 0, sizeof(int), h->stream));
+    int status = 0;
+    std::string msg;
+    try {
+      dispatch_y(h, [&](auto* Yp) {
+        using T = typename std::remove_const<typename std::remove_pointer<decltype(Yp)>::type>::type;
+        dim3 gridc((G + 127) / 128, RS);
+        CA_LAUNCH(k_pca_colstats<T>, gridc, 128, 0, h->stream)(Yp, h->ldY, N, G, RS, part);
+        KCHECK();
+        CA_LAUNCH(k_pca_colstats_final, (G + 127) / 128, 128, 0, h->stream)(part, RS, G, (double)N, mean, inv_sd, bad);
+        KCHECK();
+        int hbad = 0;
+        CUDA_OK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_OK(cudaStreamSynchronize(h->stream));
+        if (hbad) fail("cannot rescale a constant/zero column to unit variance");   // prcomp(..., scale = TRUE)
+        // deterministic start: v_g proportional to 1 + (g mod 7) / 7 (not orthogonal to a dominant direction in practice)
+        std::vector<double> v0(G);
+        double nn = 0.0;
+        for (int g = 0; g < G; ++g) { v0[g] = 1.0 + (double)(g % 7) / 7.0; nn += v0[g] * v0[g]; }
+        for (int g = 0; g < G; ++g) v0[g] /= sqrt(nn);
+        CUDA_OK(cudaMemcpyAsync(v, v0.data(), sizeof(double) * G, cudaMemcpyHostToDevice, h->stream));
+        CUDA_OK(cudaStreamSynchronize(h->stream));
+        int it = 0;
+        for (; it < max_iter; ++it) {
+          CA_LAUNCH(k_pca_prepare, 1, 1024, 0, h->stream)(v, mean, inv_sd, G, a, b);
+          KCHECK();
+          CA_LAUNCH(k_pca_rows<T>, (unsigned)ceil_div64(N, 8), 256, 0, h->stream)(Yp, h->ldY, N, G, a, b, t);
+          KCHECK();
+          CA_LAUNCH(k_pca_cols<T>, gridc, 128, 0, h->stream)(Yp, h->ldY, N, G, RS, t, part, tsum);
+          KCHECK();
+          CA_LAUNCH(k_pca_update, 1, 1024, 0, h->stream)(part, tsum, RS, G, mean, inv_sd, v, w, out2);
+          KCHECK();
+          double o2[2];
+          CUDA_OK(cudaMemcpyAsync(o2, out2, sizeof o2, cudaMemcpyDeviceToHost, h->stream));
+          CUDA_OK(cudaStreamSynchronize(h->stream));
+          if (o2[1] < tol) { ++it; break; }
+        }
+        if (iters_out) *iters_out = it;
+        // scores of the converged direction: t = X v
+        CA_LAUNCH(k_pca_prepare, 1, 1024, 0, h->stream)(v, mean, inv_sd, G, a, b);
+        KCHECK();
+        CA_LAUNCH(k_pca_rows<T>, (unsigned)ceil_div64(N, 8), 256, 0, h->stream)(Yp, h->ldY, N, G, a, b, t);
+        KCHECK();
+      });
+      // sign convention (prcomp's is arbitrary): the loading of largest magnitude is positive
+      std::vector<double> hv(G);
+      CUDA_OK(cudaMemcpyAsync(hv.data(), v, sizeof(double) * G, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_OK(cudaMemcpyAsync(scores, t, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_OK(cudaStreamSynchronize(h->stream));
+      int gmax = 0;
+      for (int g = 1; g < G; ++g)
+        if (fabs(hv[g]) > fabs(hv[gmax])) gmax = g;
+      if (hv[gmax] < 0.0)
+        for (int64_t n = 0; n < N; ++n) scores[n] = -scores[n];
+    } catch (const std::exception& e) {
+      status = 1;
+      msg = e.what();
+    }
+    for (void* p : tmp) cudaFree(p);
+    if (status) fail("%s", msg.c_str());
     return 0;
   } catch (const std::exception& e) { return report(e, err, errlen); }
 }

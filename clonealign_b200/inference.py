@@ -89,7 +89,7 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
                     x=None, clone_allele=None, cov=None, ref=None, fix_alpha=False, dtype="float32",
                     saturate_=True, saturation_threshold=6, K=1, mc_samples=1, verbose=True, initial_shrink=5,
                     data_init_mu=True, seed=None, device=0, psi_init=None, y_store="auto", path="auto",
-                    gene_names=None, variants=None, correlations_with=None):
+                    gene_names=None, variants=None, correlations_with=None, device_pca=False):
     """CUDA-backed equivalent of the reference's `inference_tflow`.
 
     Y_dat: cell x gene counts; L_dat: gene x clone copy number.  Returns the reference's list as a dict:
@@ -97,6 +97,9 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
     sd_final_elbo, elbo}, retained_genes, clone_probs_from_snv (R/inference-tflow.R:475-480).
     `fix_alpha` and `initial_shrink` are accepted and ignored, as in the reference (:81,:88).
     `psi_init` (N x K) skips the PCA; it exists for callers that compute the initialisation elsewhere.
+    `device_pca=True` (K == 1): the leading principal component that initialises psi (:203-205) is computed by power
+    iteration on the count matrix resident in HBM (ca_core_pca_scores) instead of a host-side SVD; scale() and the
+    N(0, 0.05^2) noise (:205-207) stay on the host and use the same RNG stream positions as the host path.
     `correlations_with = (L_unsaturated, clone_call_probability)`: also run the caller's post-hoc
     `compute_correlations` (R/clonealign.R:292-294,318-334) on the device while Y is still resident; the result is
     returned under "correlations" (retained genes only).
@@ -149,8 +152,13 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
             raise ValueError("allele inputs have inconsistent dimensions")
         alt = cov - ref                                                               # :180
 
+    pca_noise = None
     if psi_init is None:
-        psi_init = pca_init(Y, K, rng) if K > 0 else np.zeros((N, 0))                 # :204-208
+        if device_pca and K == 1:
+            pca_noise = rng.normal(0.0, 0.05, size=(N, 1))                            # :207 (same stream position)
+            psi_init = np.zeros((N, 1))                                               # replaced below, before any use
+        else:
+            psi_init = pca_init(Y, K, rng) if K > 0 else np.zeros((N, 0))             # :204-208
     s_init = np.asarray(Y, dtype=np.float64).sum(axis=1)                              # :210
     if np.any(s_init == 0):
         raise ValueError("Some cells have no counts mapping")                         # :212-214
@@ -172,6 +180,10 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
                    y_store=y_store, path=path, variants=variants)
     correlations = None
     try:
+        if pca_noise is not None:
+            pcs, _ = sess.pca_scores()                                                # :203-204 on the device
+            pcs = (pcs - pcs.mean()) / pcs.std(ddof=1)                                # scale(pcs), :205
+            sess.set_array("psi", pcs[:, None] + pca_noise)
         sess.init_gamma()                                                             # :368-369
         elbo_val = sess.elbo()                                                        # :372
         if np.isnan(elbo_val):

@@ -255,6 +255,15 @@ class Session:
         self._chk(self._lib.ca_core_correlations(self._h, _ptr(z), _ptr(Lm), _ptr(out), self._err, len(self._err)))
         return out
 
+    def pca_scores(self, max_iter=500, tol=1e-12):
+        """Scores of the leading principal component of the centred, scaled log2(Y + 1) (R/inference-tflow.R:203-204)
+        by power iteration on the resident Y.  Returns (scores[N], iterations)."""
+        out = np.zeros(self.N, dtype=np.float64)
+        it = C.c_int32(0)
+        self._chk(self._lib.ca_core_pca_scores(self._h, int(max_iter), float(tol), _ptr(out), C.byref(it), self._err,
+                                               len(self._err)))
+        return out, it.value
+
     # -- measurement hooks --------------------------------------------------------------------------
     def time_steps(self, n_steps: int, with_eval: bool = False) -> float:
         """Milliseconds (CUDA events on the library's stream) for n_steps train steps [+ ELBO evals]."""

@@ -135,6 +135,13 @@ CA_API int ca_core_set_array(ca_handle* h, const char* name, const double* in, i
  * reference passes the UNsaturated matrix) or NULL for the session's saturated one.  out: G values, NaN where R gives NA. */
 CA_API int ca_core_correlations(ca_handle* h, const int32_t* clone_idx, const double* L, double* out, char* err, size_t errlen);
 
+/* psi initialisation on the device: scores of the leading principal component of the centred, scaled log2(Y + 1)
+ * (prcomp(log2(Y_dat + 1), center = TRUE, scale = TRUE)$x[, 1], R/inference-tflow.R:203-204; K == 1) by power iteration
+ * on the resident Y.  scores: N values (sign: the loading of largest magnitude is positive); the caller applies
+ * scale() and adds its own N(0, 0.05^2) noise (:205-207) and writes the result with ca_core_set_array("psi").
+ * Stops when 1 - |<v_new, v_old>| < tol or after max_iter iterations; *iters = iterations used.  world == 1 only. */
+CA_API int ca_core_pca_scores(ca_handle* h, int32_t max_iter, double tol, double* scores, int32_t* iters, char* err, size_t errlen);
+
 /* Measurement hooks (bench.py): run n_steps train steps (and, if with_eval != 0, one ELBO
  * evaluation after each, as the reference loop does) back to back on the handle's stream,
  * bracketed by CUDA events on that stream; *ms = elapsed milliseconds. */

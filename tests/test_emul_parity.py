@@ -300,3 +300,36 @@ def test_device_correlations_match_host_mirror(example_sce):
         b = clonealign(example_sce[0], example_sce[1], max_iter=3, verbose=False, seed=5, clone_names=names)
     assert a["clone"] == b["clone"]
     np.testing.assert_allclose(a["correlations"], b["correlations"], atol=1e-9, equal_nan=True)
+
+
+def test_device_pca_matches_host_svd(example_sce):
+    """ca_core_pca_scores (power iteration on the resident Y) against prcomp's definition via a full SVD
+    (R/inference-tflow.R:203-205), for every storage format; constant columns are rejected as R's scale() does."""
+    from clonealign_b200._lib import CloneAlignLibraryError
+    from clonealign_b200.inference import inference_tflow, pca_init
+    Y, L = example_sce
+    keep = Y.sum(0) > 0
+    Y, L = Y[:, keep], L[keep]
+
+    class NoNoise:
+        def normal(self, *a, size=None, **k):
+            return np.zeros(size)
+    want = pca_init(Y, 1, NoNoise(), truncated=False)[:, 0]                 # scale(pcs), no noise
+    for store in ("u8", "f32"):
+        with _session(Y, L, np.zeros((Y.shape[0], 1)), np.ones(Y.shape[1]), y_store=store) as sess:
+            got, iters = sess.pca_scores()
+        got = (got - got.mean()) / got.std(ddof=1)
+        err = min(np.abs(got - want).max(), np.abs(got + want).max())       # sign of a principal component is arbitrary
+        assert err < 1e-5 and 1 < iters < 500, (err, iters)
+    Yc = Y.copy()
+    Yc[:, 2] = 3.0
+    with _session(Yc, L, np.zeros((Y.shape[0], 1)), np.ones(Y.shape[1])) as sess:
+        with pytest.raises(CloneAlignLibraryError, match="constant/zero column"):
+            sess.pca_scores()
+    # through the host mirror: same RNG stream positions as the host-PCA path -> same noise, same op seed
+    a = inference_tflow(Y, L, max_iter=3, verbose=False, seed=11, device_pca=True)
+    b = inference_tflow(Y, L, max_iter=3, verbose=False, seed=11)
+    ea, eb = a["convergence_info"]["elbo"], b["convergence_info"]["elbo"]
+    # W starts at 0, so the first ELBO does not see the (arbitrary) sign of the component; later iterates may differ
+    # because the additive noise does not flip with it
+    assert abs(ea[0] - eb[0]) / abs(eb[0]) < 1e-4 and np.all(np.isfinite(ea)) and ea[-1] > ea[0]

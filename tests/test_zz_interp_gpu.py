@@ -117,3 +117,20 @@ def test_device_correlations_match_host_mirror(example_sce):
         got = sess.correlations(zidx, L)
     ok = ~np.isnan(want)
     assert (np.isnan(got) == np.isnan(want)).all() and np.abs(got[ok] - want[ok]).max() < 1e-9
+
+
+def test_device_pca_matches_host_svd(example_sce):
+    """ca_core_pca_scores (power iteration on the resident Y) against a full SVD (R/inference-tflow.R:203-205)."""
+    from clonealign_b200.inference import pca_init
+    Y, L = example_sce
+    keep = Y.sum(0) > 0
+    Y, L = Y[:, keep], L[keep]
+
+    class NoNoise:
+        def normal(self, *a, size=None, **k):
+            return np.zeros(size)
+    want = pca_init(Y, 1, NoNoise(), truncated=False)[:, 0]
+    with _session(Y, L, np.zeros((Y.shape[0], 1)), np.ones(Y.shape[1])) as sess:
+        got, iters = sess.pca_scores()
+    got = (got - got.mean()) / got.std(ddof=1)
+    assert min(np.abs(got - want).max(), np.abs(got + want).max()) < 1e-5 and iters < 500
