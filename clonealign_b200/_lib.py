@@ -12,12 +12,12 @@ LIB_PATH = os.path.join(_HERE, "libclonealign_b200.so")
 
 # enums of include/clonealign_b200.h
 Y_F64, Y_F32, Y_I32 = 0, 1, 2
-Y_COLMAJOR, Y_ROWMAJOR = 0, 1
+Y_COLMAJOR, Y_ROWMAJOR, Y_CSR = 0, 1, 2
 Y_HOST, Y_DEVICE = 0, 1
 STORE_AUTO, STORE_F32, STORE_U16, STORE_U8 = 0, 1, 2, 3
 PATH_AUTO, PATH_CUDACORE, PATH_TENSOR, PATH_INTERP = 0, 1, 2, 3
 VAR_YPASS2, VAR_EPI2, VAR_LEAN = 1, 2, 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = (
     "ca_core_abi_version", "ca_core_device_count", "ca_core_nccl_unique_id", "ca_core_create",
@@ -35,6 +35,7 @@ class CaConfig(C.Structure):
         ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
         ("y_dtype", C.c_int32), ("y_layout", C.c_int32), ("y_mem", C.c_int32), ("y_store", C.c_int32),
         ("path", C.c_int32), ("y_ld", C.c_int64), ("nccl_id", C.c_void_p), ("variants", C.c_uint32),
+        ("y_indptr", C.c_void_p), ("y_indices", C.c_void_p),
     ]
 
 

@@ -136,6 +136,22 @@ __global__ void k_ingest_rowmajor(const Tin* __restrict__ in, int64_t ld_in, int
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x)
     if (r < rows) out[r * ldY + g] = (float)in[r * ld_in + g];
 }
+// compressed sparse rows -> dense: one warp per cell scatters its stored values (Yf is zero-filled beforehand).
+// idx / val hold the chunk's entries starting at offset `base`; *bad is set on an out-of-range gene index.
+template <typename Tin>
+__global__ void k_ingest_csr(const int* __restrict__ indptr, const int* __restrict__ idx, const Tin* __restrict__ val,
+                             int64_t base, int64_t r0, int64_t rows, int G, float* __restrict__ Yf, int64_t ldY,
+                             int* __restrict__ bad) {
+  const int64_t r = r0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= r0 + rows) return;
+  const int64_t a = indptr[r], b = indptr[r + 1];
+  for (int64_t k = a + lane; k < b; k += 32) {
+    const int g = idx[k - base];
+    if (g < 0 || g >= G) { atomicOr(bad, 1); continue; }
+    Yf[r * ldY + g] = (float)val[k - base];
+  }
+}
 // flags: bit0 non-integer or negative, bit1 value > 255, bit2 value > 65535
 __global__ void k_scan_y(const float* __restrict__ Y, int64_t ldY, int64_t N, int G, int* __restrict__ flags) {
   int64_t r = blockIdx.y;
@@ -616,7 +632,50 @@ void ingest_y(ca_handle* h, const Tin* Ysrc, float* Yf) {
   const int64_t N = h->N;
   const int G = h->G;
   const bool on_dev = c.y_mem == CA_Y_DEVICE;
-  if (c.y_layout == CA_Y_COLMAJOR) {
+  if (c.y_layout == CA_Y_CSR) {
+    if (on_dev) fail("CSR input must be in host memory");
+    if (!c.y_indptr || !c.y_indices) fail("CSR input needs y_indptr and y_indices");
+    const int32_t* ip = c.y_indptr;
+    if (ip[0] < 0) fail("bad CSR row offsets");
+    for (int64_t r = 0; r < N; ++r)
+      if (ip[r + 1] < ip[r]) fail("bad CSR row offsets");
+    int *d_ip = nullptr, *d_idx = nullptr, *d_bad = nullptr;
+    Tin* d_val = nullptr;
+    const int64_t cap = std::max<int64_t>(1, (int64_t)(128ll << 20) / (int64_t)(sizeof(Tin) + sizeof(int)));   // entries per chunk
+    CUDA_OK(cudaMalloc(&d_ip, sizeof(int) * (N + 1)));
+    CUDA_OK(cudaMalloc(&d_bad, sizeof(int)));
+    CUDA_OK(cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream));
+    CUDA_OK(cudaMemcpyAsync(d_ip, ip, sizeof(int) * (N + 1), cudaMemcpyHostToDevice, h->stream));
+    int64_t r0 = 0;
+    int64_t cur_cap = 0;
+    while (r0 < N) {
+      // rows [r0, r1) whose entries fit in one chunk (a single row longer than the chunk gets a chunk of its own)
+      int64_t r1 = r0 + 1;
+      while (r1 < N && (int64_t)ip[r1 + 1] - ip[r0] <= cap) ++r1;
+      const int64_t base = ip[r0], cnt = (int64_t)ip[r1] - base;
+      if (cnt > cur_cap) {
+        if (d_idx) { CUDA_OK(cudaFree(d_idx)); CUDA_OK(cudaFree(d_val)); }
+        cur_cap = std::max(cnt, cap);
+        CUDA_OK(cudaMalloc(&d_idx, sizeof(int) * cur_cap));
+        CUDA_OK(cudaMalloc(&d_val, sizeof(Tin) * cur_cap));
+      }
+      if (cnt > 0) {
+        CUDA_OK(cudaMemcpyAsync(d_idx, c.y_indices + base, sizeof(int) * cnt, cudaMemcpyHostToDevice, h->stream));
+        CUDA_OK(cudaMemcpyAsync(d_val, Ysrc + base, sizeof(Tin) * cnt, cudaMemcpyHostToDevice, h->stream));
+        CA_LAUNCH(k_ingest_csr<Tin>, (unsigned)ceil_div64(r1 - r0, 8), 256, 0, h->stream)(d_ip, d_idx, d_val, base, r0, r1 - r0, G, Yf,
+                                                                                          h->ldY, d_bad);
+        KCHECK();
+        CUDA_OK(cudaStreamSynchronize(h->stream));
+      }
+      r0 = r1;
+    }
+    int hbad = 0;
+    CUDA_OK(cudaMemcpyAsync(&hbad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_ip); cudaFree(d_bad);
+    if (d_idx) { cudaFree(d_idx); cudaFree(d_val); }
+    if (hbad) fail("CSR input has a gene index outside [0, G)");
+  } else if (c.y_layout == CA_Y_COLMAJOR) {
     int64_t ld = c.y_ld ? c.y_ld : N;
     int gchunk = (int)std::max<int64_t>(1, std::min<int64_t>(G, (int64_t)(256ll << 20) / (int64_t)(sizeof(Tin) * N)));
     Tin* stage = nullptr;
@@ -1040,6 +1099,8 @@ int ca_core_create(ca_handle** out, const ca_config* cfg, const void* Y, const d
     h->cfg = *cfg;
     build(h, Y, L, psi_init, loc_init, X, colsum_total, clone_allele, alt, cov);
     h->cfg.nccl_id = nullptr;   // never retain caller pointers
+    h->cfg.y_indptr = nullptr;
+    h->cfg.y_indices = nullptr;
     *out = h;
     return 0;
   } catch (const std::exception& e) {

@@ -112,14 +112,19 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
     rng = np.random.default_rng(seed)
     _message(verbose, "Constructing CUDA session")
 
-    Y_dat = np.asarray(Y_dat)
+    # a scipy.sparse cells x genes matrix (the transposed dgCMatrix of a SingleCellExperiment) stays compressed all the
+    # way to the device (CA_Y_CSR) instead of being densified as t(as.matrix(assay(...))) does (R/clonealign.R:217)
+    sparse = hasattr(Y_dat, "tocsr") and hasattr(Y_dat, "nnz")
+    Y_dat = Y_dat.tocsr() if sparse else np.asarray(Y_dat)
     L_dat = np.asarray(L_dat, dtype=np.float64)
     if Y_dat.ndim != 2 or L_dat.ndim != 2 or L_dat.shape[0] != Y_dat.shape[1]:
         raise ValueError("nrow(L_dat) == G is not TRUE")                              # :139 (R fails in the subset at :124)
-    zero_gene_means = Y_dat.sum(axis=0) <= gene_filter_threshold                      # :117
+    zero_gene_means = np.asarray(Y_dat.sum(axis=0)).ravel() <= gene_filter_threshold  # :117
     _message(verbose, f"Removing {int(zero_gene_means.sum())} genes with low counts")  # :120
     Y = Y_dat[:, ~zero_gene_means]
     L = L_dat[~zero_gene_means, :]
+    if sparse and psi_init is None and not (device_pca and K == 1):
+        Y, sparse = np.asarray(Y.todense()), False     # the host PCA needs the dense matrix (use device_pca=True to avoid it)
     if gene_names is not None:
         retained_genes = [g for g, z in zip(gene_names, zero_gene_means) if not z]    # :127-128
     else:
@@ -159,11 +164,15 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
             psi_init = np.zeros((N, 1))                                               # replaced below, before any use
         else:
             psi_init = pca_init(Y, K, rng) if K > 0 else np.zeros((N, 0))             # :204-208
-    s_init = np.asarray(Y, dtype=np.float64).sum(axis=1)                              # :210
+    s_init = np.asarray(Y.sum(axis=1), dtype=np.float64).ravel()                      # :210
     if np.any(s_init == 0):
         raise ValueError("Some cells have no counts mapping")                         # :212-214
     if isinstance(data_init_mu, (bool, np.bool_)):                                    # :220-235
-        if data_init_mu:
+        if data_init_mu and sparse:
+            import scipy.sparse as sp
+            inv_rowmean = sp.diags(Y.shape[1] / s_init)                               # 1 / rowMeans(Y)
+            mu_guess = np.asarray((inv_rowmean @ Y.astype(np.float64)).mean(axis=0)).ravel()
+        elif data_init_mu:
             Yd = np.asarray(Y, dtype=np.float64)
             mu_guess = (Yd / Yd.mean(axis=1, keepdims=True)).mean(axis=0)
         else:

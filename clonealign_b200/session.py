@@ -88,6 +88,20 @@ class Session:
             yptr = C.c_void_p(Y.data_ptr())
             cfg.y_dtype, cfg.y_layout, cfg.y_mem = _lib.Y_F32, _lib.Y_ROWMAJOR, _lib.Y_DEVICE
             keep.append(Y)
+        elif hasattr(Y, "tocsr") and hasattr(Y, "nnz"):                   # scipy.sparse: cells x genes, kept compressed
+            Ys = Y.tocsr()
+            Ys.sum_duplicates()
+            N, G = Ys.shape
+            if Ys.nnz >= 2 ** 31:
+                raise ValueError("sparse Y with >= 2^31 stored values is not supported (int32 offsets, as R's dgCMatrix)")
+            vals = np.ascontiguousarray(Ys.data, dtype=np.float64 if Ys.data.dtype not in (np.float32, np.int32) else Ys.data.dtype)
+            indptr = np.ascontiguousarray(Ys.indptr, dtype=np.int32)
+            indices = np.ascontiguousarray(Ys.indices, dtype=np.int32)
+            cfg.y_dtype = {np.dtype(np.float64): _lib.Y_F64, np.dtype(np.float32): _lib.Y_F32, np.dtype(np.int32): _lib.Y_I32}[vals.dtype]
+            cfg.y_layout, cfg.y_mem = _lib.Y_CSR, _lib.Y_HOST
+            cfg.y_indptr, cfg.y_indices = _ptr(indptr), _ptr(indices)
+            yptr = _ptr(vals)
+            keep += [vals, indptr, indices]
         else:
             Y = np.asarray(Y)
             if Y.ndim != 2:

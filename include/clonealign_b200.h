@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CA_ABI_VERSION 2
+#define CA_ABI_VERSION 3
 #if defined(__GNUC__)
 #define CA_API __attribute__((visibility("default")))
 #else
@@ -45,7 +45,12 @@ extern "C" {
 typedef struct ca_handle ca_handle;
 
 enum ca_y_dtype  { CA_Y_F64 = 0, CA_Y_F32 = 1, CA_Y_I32 = 2 };
-enum ca_y_layout { CA_Y_COLMAJOR = 0 /* R matrix: cell index fastest */, CA_Y_ROWMAJOR = 1 /* gene index fastest */ };
+enum ca_y_layout { CA_Y_COLMAJOR = 0 /* R matrix: cell index fastest */, CA_Y_ROWMAJOR = 1 /* gene index fastest */,
+                   /* compressed sparse rows of the cells x genes matrix == the genes x cells dgCMatrix of a
+                    * SingleCellExperiment as it is (slots @p, @i, @x): Y points at the nnz values (y_dtype),
+                    * y_indptr at the N + 1 row offsets, y_indices at the nnz gene indices (0-based, unique per cell).
+                    * Host memory only.  Avoids t(as.matrix(assay(...))) (R/clonealign.R:217), SURVEY.md 8f-2. */
+                   CA_Y_CSR = 2 };
 enum ca_y_mem    { CA_Y_HOST = 0, CA_Y_DEVICE = 1 };
 /* how Y is kept in HBM: fp32 (the reference's tensor dtype) or, when every count is an integer that
  * fits, a narrower unsigned type.  AUTO picks the narrowest exact representation. */
@@ -85,6 +90,8 @@ typedef struct ca_config {
   int64_t y_ld;         /* leading dimension of Y in elements (0 = tight)                      */
   const void* nccl_id;  /* 128-byte ncclUniqueId shared by all ranks when world > 1, else NULL */
   uint32_t variants;    /* bit mask of enum ca_variant; 0 = default kernels                    */
+  const int32_t* y_indptr;   /* CA_Y_CSR: N + 1 offsets into y_indices / Y                     */
+  const int32_t* y_indices;  /* CA_Y_CSR: gene index of every stored value                     */
 } ca_config;
 
 /* library / device discovery */

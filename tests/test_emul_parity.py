@@ -333,3 +333,33 @@ def test_device_pca_matches_host_svd(example_sce):
     # W starts at 0, so the first ELBO does not see the (arbitrary) sign of the component; later iterates may differ
     # because the additive noise does not flip with it
     assert abs(ea[0] - eb[0]) / abs(eb[0]) < 1e-4 and np.all(np.isfinite(ea)) and ea[-1] > ea[0]
+
+
+def test_sparse_input_stays_compressed(example_sce):
+    """CA_Y_CSR ingest: a scipy.sparse cells x genes matrix -- the transposed dgCMatrix of a
+    SingleCellExperiment -- gives bit-identical fits to the dense matrix, for every value type and through the host
+    mirror (with the device PCA nothing is densified on the host); malformed index arrays fail loudly."""
+    import scipy.sparse as sp
+    from clonealign_b200._lib import CloneAlignLibraryError
+    from clonealign_b200.inference import inference_tflow
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
+    run = lambda y: _run_trace(y, hi["L"], hi["psi_init"], hi["mu_guess"], n=2, seed=7)[0]
+    dense = run(hi["Y"])
+    for conv in (sp.csr_matrix, sp.csc_matrix, sp.coo_matrix, lambda y: sp.csr_matrix(y.astype(np.float32)),
+                 lambda y: sp.csr_matrix(y.astype(np.int32))):
+        assert run(conv(hi["Y"])).tobytes() == dense.tobytes()
+    bad = sp.csr_matrix(hi["Y"])
+    bad.indices = bad.indices.copy()
+    bad.indices[5] = hi["Y"].shape[1] + 3
+    bad.has_canonical_format = True                       # keep scipy from touching the broken index
+    with pytest.raises(CloneAlignLibraryError, match="gene index outside"):
+        from clonealign_b200.session import Session
+        Session(bad, hi["L"], hi["psi_init"], O.safe_inverse_softplus(hi["mu_guess"]))
+    a = inference_tflow(sp.csr_matrix(Y), L, max_iter=3, verbose=False, seed=11, device_pca=True)
+    b = inference_tflow(Y, L, max_iter=3, verbose=False, seed=11, device_pca=True)
+    assert a["convergence_info"]["elbo"].tobytes() == b["convergence_info"]["elbo"].tobytes()
+    assert a["retained_genes"] == b["retained_genes"]
+    c = inference_tflow(sp.csc_matrix(Y), L, max_iter=2, verbose=False, seed=11)        # host PCA: densified on the host
+    d = inference_tflow(Y, L, max_iter=2, verbose=False, seed=11)
+    assert c["convergence_info"]["elbo"].tobytes() == d["convergence_info"]["elbo"].tobytes()

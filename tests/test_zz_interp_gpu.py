@@ -134,3 +134,13 @@ def test_device_pca_matches_host_svd(example_sce):
         got, iters = sess.pca_scores()
     got = (got - got.mean()) / got.std(ddof=1)
     assert min(np.abs(got - want).max(), np.abs(got + want).max()) < 1e-5 and iters < 500
+
+
+def test_sparse_input_matches_dense(example_sce):
+    """CA_Y_CSR ingest: the compressed cells x genes matrix gives a bit-identical fit to the dense one."""
+    import scipy.sparse as sp
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
+    a = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], n=2, seed=7)[0]
+    b = _run_trace(sp.csr_matrix(hi["Y"]), hi["L"], hi["psi_init"], hi["mu_guess"], n=2, seed=7)[0]
+    assert a.tobytes() == b.tobytes()
