@@ -4,17 +4,42 @@
 # byte-for-byte; only the graph construction and the sess$run calls are replaced by .Call()s into src/ca_shim.c.
 # The Python mirror clonealign_b200/inference.py is the executable twin of this file and is what the tests cover.
 
+# Optional (SURVEY.md 8f; each falls back to the reference's host code when left at its default):
+#   counts_dgC  : the genes x cells dgCMatrix of the (gene-filtered) counts assay; passed to the device compressed
+#                 (ca_create_sparse) instead of Y_dat = t(as.matrix(assay(...))) (R/clonealign.R:217)
+#   device_pca  : pcs (R/inference-tflow.R:203-205) from ca_pca_scores on the resident Y; scale() and the rnorm noise
+#                 (:205-207) stay in R, so set.seed() governs the same draws (pass pcs = NULL)
+#   cor_with    : list(L = unsaturated copy number of the retained genes, p = clone_call_probability): run
+#                 compute_correlations (R/clonealign.R:292-294,318-334) on the device before the session closes
 inference_cuda_session <- function(Y_dat, L_dat, pcs, mu_guess, x, clone_allele, alt, cov,
-                                   learning_rate, K, mc_samples, max_iter, rel_tol, verbose) {
-  N <- nrow(Y_dat); G <- ncol(Y_dat); C <- ncol(L_dat)
+                                   learning_rate, K, mc_samples, max_iter, rel_tol, verbose,
+                                   counts_dgC = NULL, device_pca = FALSE, cor_with = NULL) {
+  N <- if (is.null(counts_dgC)) nrow(Y_dat) else ncol(counts_dgC)
+  G <- if (is.null(counts_dgC)) ncol(Y_dat) else nrow(counts_dgC)
+  C <- ncol(L_dat)
+  pca_noise <- NULL
+  if (device_pca && K == 1) {                              # rnorm drawn where the reference draws it (:207)
+    pca_noise <- matrix(rnorm(N, mean = 0, sd = .05), nrow = N)
+    pcs <- matrix(0, N, 1)
+  }
   P <- if (is.null(x)) 0L else ncol(x)
   V <- if (is.null(clone_allele)) 0L else nrow(clone_allele)
   if (K == 0) x <- NULL                                    # reference quirk: covariates ignored without latent dims (:279-285)
   storage.mode(L_dat) <- "double"
-  sess <- .Call("ca_create", Y_dat, L_dat, pcs, safe_inverse_softplus(mu_guess), x,
-                clone_allele, if (V > 0) t(alt) else NULL, if (V > 0) t(cov) else NULL,   # :177-180 transposes undone: ABI takes N x V
-                as.integer(mc_samples), as.integer(K), learning_rate, get_next_seed(), 0L)
+  alt_nv <- if (V > 0) t(alt) else NULL; cov_nv <- if (V > 0) t(cov) else NULL   # :177-180 transposes undone: ABI takes N x V
+  sess <- if (is.null(counts_dgC)) {
+    .Call("ca_create", Y_dat, L_dat, pcs, safe_inverse_softplus(mu_guess), x, clone_allele, alt_nv, cov_nv,
+          as.integer(mc_samples), as.integer(K), learning_rate, get_next_seed(), 0L)
+  } else {
+    .Call("ca_create_sparse", counts_dgC@Dim, counts_dgC@p, counts_dgC@i, counts_dgC@x, L_dat, pcs,
+          safe_inverse_softplus(mu_guess), x, clone_allele, alt_nv, cov_nv,
+          as.integer(mc_samples), as.integer(K), learning_rate, get_next_seed(), 0L)
+  }
   on.exit(.Call("ca_destroy", sess), add = TRUE)           # sess$close(), :457
+  if (!is.null(pca_noise)) {
+    pcs <- scale(matrix(.Call("ca_pca_scores", sess, N, 500L, 1e-12), nrow = N))   # :203-205
+    .Call("ca_set_psi", sess, pcs + pca_noise)                                     # :207
+  }
 
   .Call("ca_init_gamma", sess)                             # :368-369
   elbo_val <- .Call("ca_elbo", sess)                       # :372
@@ -31,5 +56,11 @@ inference_cuda_session <- function(Y_dat, L_dat, pcs, mu_guess, x, clone_allele,
   }
   rlist <- .Call("ca_params", sess, c(N, G, C, as.integer(K), P, V))   # :424-440
   final_elbo <- replicate(20, .Call("ca_elbo", sess))      # :447-449
-  list(rlist = rlist, elbos = elbos, final_elbo = final_elbo)
+  correlations <- NULL
+  if (!is.null(cor_with)) {                                # clone_assignment (:22-29) as 0-based indices, -1 = unassigned
+    cp <- rlist$clone_probs
+    idx <- ifelse(apply(cp, 1, max) < cor_with$p, -1L, max.col(cp, ties.method = "first") - 1L)
+    correlations <- .Call("ca_correlations", sess, as.integer(idx), cor_with$L, G)
+  }
+  list(rlist = rlist, elbos = elbos, final_elbo = final_elbo, correlations = correlations)
 }

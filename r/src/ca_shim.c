@@ -1,6 +1,7 @@
 /* .Call shim between R and libclonealign_b200.so (include/clonealign_b200.h).
  *
- * NOT COMPILED OR TESTED IN THIS REPOSITORY'S IMAGE: there is no R toolchain here (no R, no Rinternals.h).
+ * NOT LINKED OR RUN IN THIS REPOSITORY'S IMAGE: there is no R toolchain here (no R, no Rinternals.h); it is only
+ * syntax- and type-checked against stub declarations of the R API (tests/r_stub/, tests/test_host.py).
  * It is the binding a clonealign maintainer adds under src/ (plus `useDynLib(clonealign, .registration = TRUE)` in
  * NAMESPACE and `LinkingTo`-free `PKG_LIBS = -lclonealign_b200` in src/Makevars).  Every numeric operation lives in
  * the extern "C" core, which is what the Python/ctypes tests exercise with R-layout (column-major double) inputs.
@@ -71,6 +72,71 @@ SEXP ca_create(SEXP Y, SEXP L, SEXP psi_init, SEXP loc_init, SEXP X, SEXP clone_
   return ptr;
 }
 
+/* ca_create_sparse(dim, p, i, x, L, ...): the counts assay of a SingleCellExperiment as it is -- a genes x cells
+ * dgCMatrix (slots @Dim, @p, @i, @x) is the compressed-row form of the cells x genes matrix, so nothing is transposed
+ * or densified (replaces t(as.matrix(assay(...))), R/clonealign.R:217).  The gene filter must already be applied. */
+SEXP ca_create_sparse(SEXP dim, SEXP p, SEXP i, SEXP x, SEXP L, SEXP psi_init, SEXP loc_init, SEXP X, SEXP clone_allele,
+                      SEXP alt, SEXP cov, SEXP S, SEXP K, SEXP lr, SEXP seed, SEXP device) {
+  char err[ERRLEN] = {0};
+  ca_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.G = INTEGER(dim)[0];        /* dgCMatrix rows = genes */
+  cfg.N = INTEGER(dim)[1];        /* dgCMatrix columns = cells */
+  cfg.N_total = cfg.N;
+  cfg.C = Rf_ncols(L);
+  cfg.S = Rf_asInteger(S);
+  cfg.K = Rf_asInteger(K);
+  cfg.P = Rf_isNull(X) ? 0 : Rf_ncols(X);
+  cfg.V = Rf_isNull(clone_allele) ? 0 : Rf_nrows(clone_allele);
+  cfg.learning_rate = Rf_asReal(lr);
+  cfg.seed = (uint64_t)Rf_asInteger(seed);
+  cfg.device = Rf_asInteger(device);
+  cfg.world = 1;
+  cfg.y_dtype = CA_Y_F64;         /* @x is numeric */
+  cfg.y_layout = CA_Y_CSR;
+  cfg.y_mem = CA_Y_HOST;
+  cfg.y_store = CA_STORE_AUTO;
+  cfg.path = CA_PATH_AUTO;
+  cfg.y_indptr = INTEGER(p);
+  cfg.y_indices = INTEGER(i);
+  ca_handle* h = NULL;
+  int st = ca_core_create(&h, &cfg, REAL(x), REAL(L), real_or_null(psi_init), REAL(loc_init), real_or_null(X), NULL,
+                          real_or_null(clone_allele), real_or_null(alt), real_or_null(cov), err, ERRLEN);
+  if (st != 0) Rf_error("%s", err);
+  SEXP ptr = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, ca_finalizer, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+
+/* prcomp(log2(Y_dat + 1), center = TRUE, scale = TRUE)$x[, 1] (R/inference-tflow.R:203-204) on the resident Y */
+SEXP ca_pca_scores(SEXP ptr, SEXP n_cells, SEXP max_iter, SEXP tol) {
+  char err[ERRLEN] = {0};
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, Rf_asInteger(n_cells)));
+  int iters = 0;
+  int st = ca_core_pca_scores(get_handle(ptr), Rf_asInteger(max_iter), Rf_asReal(tol), REAL(out), &iters, err, ERRLEN);
+  UNPROTECT(1);
+  if (st != 0) Rf_error("%s", err);
+  return out;
+}
+
+/* psi <- scale(pcs) + rnorm noise (:205-207), written after ca_pca_scores */
+SEXP ca_set_psi(SEXP ptr, SEXP psi) {
+  char err[ERRLEN] = {0};
+  if (ca_core_set_array(get_handle(ptr), "psi", REAL(psi), (int64_t)XLENGTH(psi), err, ERRLEN)) Rf_error("%s", err);
+  return R_NilValue;
+}
+
+/* compute_correlations(Y, L, clones) (R/clonealign.R:318-334) on the resident Y; clone_idx: 0-based, -1 = unassigned */
+SEXP ca_correlations(SEXP ptr, SEXP clone_idx, SEXP L, SEXP n_genes) {
+  char err[ERRLEN] = {0};
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, Rf_asInteger(n_genes)));
+  int st = ca_core_correlations(get_handle(ptr), INTEGER(clone_idx), real_or_null(L), REAL(out), err, ERRLEN);
+  UNPROTECT(1);
+  if (st != 0) Rf_error("%s", err);
+  return out;   /* NaN where cor() gives NA */
+}
+
 SEXP ca_init_gamma(SEXP ptr) {
   char err[ERRLEN] = {0};
   if (ca_core_init_gamma(get_handle(ptr), err, ERRLEN)) Rf_error("%s", err);
@@ -136,7 +202,9 @@ static const R_CallMethodDef call_methods[] = {
     {"ca_create", (DL_FUNC)&ca_create, 13}, {"ca_init_gamma", (DL_FUNC)&ca_init_gamma, 1},
     {"ca_step", (DL_FUNC)&ca_step, 1},      {"ca_elbo", (DL_FUNC)&ca_elbo, 1},
     {"ca_params", (DL_FUNC)&ca_params, 2},  {"ca_set_eps", (DL_FUNC)&ca_set_eps, 3},
-    {"ca_destroy", (DL_FUNC)&ca_destroy, 1}, {NULL, NULL, 0}};
+    {"ca_destroy", (DL_FUNC)&ca_destroy, 1}, {"ca_create_sparse", (DL_FUNC)&ca_create_sparse, 16},
+    {"ca_pca_scores", (DL_FUNC)&ca_pca_scores, 4}, {"ca_set_psi", (DL_FUNC)&ca_set_psi, 2},
+    {"ca_correlations", (DL_FUNC)&ca_correlations, 4}, {NULL, NULL, 0}};
 
 void R_init_clonealign(DllInfo* dll) {
   R_registerRoutines(dll, NULL, call_methods, NULL, NULL);

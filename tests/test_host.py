@@ -331,3 +331,19 @@ def test_bench_candidate_selection(monkeypatch, tmp_path):
     assert pick == ("auto", "") and "cached" in info["note"]
     args.config = "c2"
     assert bench.interp_selfcheck(args)[0] == ("auto", "")                   # no output at all
+
+
+def test_r_shim_compiles_against_stub_headers():
+    """r/src/ca_shim.c (the .Call binding a clonealign maintainer adds) is type-checked against include/clonealign_b200.h
+    with stub declarations of the R API (tests/r_stub/): there is no R in this image, but argument counts / types of every
+    ca_core_* call and the registered arities must stay in step with the header."""
+    src = os.path.join(ROOT, "r", "src", "ca_shim.c")
+    out = subprocess.run(["gcc", "-std=c11", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter",
+                          "-Wno-cast-function-type", "-I", os.path.join(ROOT, "tests", "r_stub"), "-I", os.path.join(ROOT, "include"),
+                          src], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    text = open(src).read()
+    for m in re.finditer(r'\{"(ca_\w+)", \(DL_FUNC\)&(\w+), (\d+)\}', text):          # registered arity == definition
+        name, fn, n = m.group(1), m.group(2), int(m.group(3))
+        sig = re.search(r"SEXP %s\(([^)]*)\)" % fn, text).group(1)
+        assert name == fn and sig.count("SEXP") == n, (name, n, sig)
