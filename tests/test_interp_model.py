@@ -49,3 +49,32 @@ def test_one_sided_and_degenerate_ranges():
         ref = np.exp(psi[:, None] * w[None, :] - m[:, None]) @ Mx
         Z, _ = IP.forward_interp(psi, w, Mx, P=24)
         assert np.abs(Z / ref - 1.0).max() < 1e-12
+
+
+@pytest.mark.parametrize("dist", ["normal", "uniform", "spiky"])
+def test_sixteen_nodes_at_half_range_four(dist):
+    """The kernels use kIP = 16 nodes per panel with exponent half-range kIAmax = 4: worst relative error of the
+    interpolated normaliser over a panel, for gene-weight distributions from near point masses to uniform."""
+    rng = np.random.default_rng(0)
+    G, P, A, D = 5000, 16, 4.0, 2.0
+    if dist == "normal":
+        w = rng.standard_normal(G) * D / 6
+    elif dist == "uniform":
+        w = rng.uniform(-D / 2, D / 2, G)
+    else:
+        w = np.concatenate([rng.standard_normal(G - 5) * 0.01, np.array([1.0, -1.0, 0.9, -0.8, 0.7]) * D / 2])
+    M = rng.uniform(0.5, 5, G)
+    h = A / (w.max() - w.min())
+    worst = 0.0
+    for pan in range(5):
+        mid = pan * 2 * h + h
+        nodes = mid + h * np.cos(np.pi * (np.arange(P) + 0.5) / P)
+        f = np.exp(nodes[:, None] * (w - w.max())[None, :]) @ M
+        k, p = np.arange(P)[:, None], np.arange(P)[None, :]
+        c = (2.0 / P) * (f[None, :] * np.cos(np.pi * k * (p + 0.5) / P)).sum(1)
+        c[0] *= 0.5
+        xs = np.linspace(mid - h, mid + h, 101)
+        val = np.polynomial.chebyshev.chebval((xs - mid) / h, c)
+        ref = np.exp(xs[:, None] * (w - w.max())[None, :]) @ M
+        worst = max(worst, np.abs(val / ref - 1.0).max())
+    assert worst < 2e-10, worst
