@@ -423,7 +423,9 @@ def run_ours(args, cfg):
     if rank == 0:
         line = {"metric": "ELBO+grad iterations/s", "value": value, "unit": "iterations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (bf16 split tensor operands, f32 accumulate)",
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": ("f32 (f64 Chebyshev node sums / recurrences)" if desc["path"] == "interp" else
+                          "f32 (bf16 split tensor operands, f32 accumulate)" if desc["path"] == "tcgen05" else "f32"),
                 "data": "synthetic",
                 "config": {"workload": cfg["name"], "cells_total": N, "cells_per_gpu": Nl, "genes": G, "clones": C, "mc_samples": S,
                            "K": 1, "sharding": f"cells/{world}", "path": desc["path"], "variants": variants, "y_store": desc["y_store"],

@@ -368,6 +368,26 @@ void stage_eps(ca_handle* h, const float** eps_in) {
   }
 }
 
+template <bool FWD, int NC>
+void launch_interp_nodes_nc(ca_handle* h, int nsplit, const float* rv, const float* shift, const float* B, int64_t R) {
+  dim3 gn((h->J + 32 * NC - 1) / (32 * NC), kIGroupsY, nsplit);
+  auto k = k_interp_nodes<FWD, NC>;
+  CA_LAUNCH(k, gn, 256, 0, h->stream)(h->iplan, rv, shift, B, R, h->J, h->ivals);
+}
+template <bool FWD>
+void launch_interp_nodes(ca_handle* h, int nsplit, const float* rv, const float* shift, const float* B, int64_t R) {
+  switch (interp_nodes_nc(h->J)) {
+    case 1: launch_interp_nodes_nc<FWD, 1>(h, nsplit, rv, shift, B, R); break;
+    case 2: launch_interp_nodes_nc<FWD, 2>(h, nsplit, rv, shift, B, R); break;
+    case 3: launch_interp_nodes_nc<FWD, 3>(h, nsplit, rv, shift, B, R); break;
+    case 4: launch_interp_nodes_nc<FWD, 4>(h, nsplit, rv, shift, B, R); break;
+    case 5: launch_interp_nodes_nc<FWD, 5>(h, nsplit, rv, shift, B, R); break;
+    case 6: launch_interp_nodes_nc<FWD, 6>(h, nsplit, rv, shift, B, R); break;
+    case 7: launch_interp_nodes_nc<FWD, 7>(h, nsplit, rv, shift, B, R); break;
+    default: launch_interp_nodes_nc<FWD, 8>(h, nsplit, rv, shift, B, R); break;
+  }
+}
+
 template <int MODE>
 void launch_fused_mode(ca_handle* h, const FusedArgs& a) {
   const unsigned grid = (unsigned)h->n_cell_parts;
@@ -456,8 +476,7 @@ void run_forward(ca_handle* h, int mode) {
         CA_LAUNCH(k_minmax, 1, 1024, 0, h->stream)(h->U, (int)h->N, h->mm_psi);
         CA_LAUNCH(k_interp_plan, 1, 32, 0, h->stream)(h->mm, h->mm_psi, h->iplan);
       }
-      dim3 gn((h->J + 31) / 32, kIGroupsY, kISplitF);
-      CA_LAUNCH(k_interp_nodes<true>, gn, 256, 0, h->stream)(h->iplan, h->Vm, nullptr, h->Mx, h->G, h->J, h->ivals);
+      launch_interp_nodes<true>(h, kISplitF, h->Vm, nullptr, h->Mx, h->G);
       CA_LAUNCH(k_interp_coeffs, dim3((h->J + 31) / 32, kIMaxPanF), kIP * 32, 0, h->stream)(h->iplan, h->ivals, kISplitF, kIMaxPanF, h->J, 1, h->icoef);
       if (!h->epi2)
         CA_LAUNCH(k_interp_eval<true>, h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream)(h->iplan, h->icoef, h->U, h->N, h->J, h->Zx,
@@ -508,8 +527,7 @@ void run_train(ca_handle* h, bool apply) {
     LaunchScope ls(h, "lse_bwd", h->interp ? (h->lean ? 2 : 3) : 1);
     if (h->interp) {
       // K = 1: dMx[g][j] = H_j(w_g); the plan of this step's forward pass is still valid (psi, W unchanged)
-      dim3 gn((h->J + 31) / 32, kIGroupsY, kISplitB);
-      CA_LAUNCH(k_interp_nodes<false>, gn, 256, 0, h->stream)(h->iplan, h->U, h->shift, h->Rx, h->N, h->J, h->ivals);
+      launch_interp_nodes<false>(h, kISplitB, h->U, h->shift, h->Rx, h->N);
       CA_LAUNCH(k_interp_coeffs, dim3((h->J + 31) / 32, kIMaxPanB), kIP * 32, 0, h->stream)(h->iplan, h->ivals, kISplitB, kIMaxPanB, h->J, 0, h->icoef);
       if (!h->lean)
         CA_LAUNCH(k_interp_eval<false>, h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream)(h->iplan, h->icoef, h->Vm, h->G, h->J, h->dMx,

@@ -93,24 +93,26 @@ __global__ void k_interp_plan(const float* __restrict__ mm_w, const float* __res
 
 // Node values.  FWD: part[z][node][j] = sum_{g in split z} Mx[g][j] exp(x_node (w_g - wref));  reduction index = genes.
 //               BWD: part[z][node][j] = sum_{n in split z} Rx[n][j] exp(psi_n y_node - m_n);    reduction index = cells.
-// Block = 8 warps = 8 nodes x 32 columns; warps stride over the reduction index, lane = column; the 8 exponentials
-// of a row are computed by lanes 0..7 and broadcast.  Cross-warp reduction in a fixed order through shared memory.
+// Block = 8 warps, one group of 8 nodes x (32 NC) columns; warps stride over the reduction index, a lane owns NC
+// columns (j = cblock + lane + 32 c) of all 8 nodes in registers; the 8 exponentials of a row are computed by 8 lanes
+// and broadcast with shuffles, each of which now feeds NC fp64 FMAs (with NC = 1 the kernel was shuffle-bound: one
+// SHFL per DFMA).  Cross-warp reduction through shared memory in warp order (deterministic).
 // Grid = (column blocks, kIGroupsY, reduction splits): how many panels are active is only known on the device (the
 // plan), so blocks stride over the active groups of 8 nodes instead of launching (and retiring) one block per possible
 // group; the reduction index is split over blockIdx.z (kISplitF / kISplitB partials, summed by k_interp_coeffs) so that
 // a handful of active groups still spreads over all SMs instead of running as a few long serial loops.
-template <bool FWD>
+constexpr int kINodeMaxNC = 8;
+template <bool FWD, int NC>
 __global__ void __launch_bounds__(256)
 k_interp_nodes(const InterpPlan* __restrict__ plan, const float* __restrict__ rv /*FWD: w[G]  BWD: psi[N]*/,
                const float* __restrict__ shift /*BWD: m[N]*/, const float* __restrict__ B /*[R][J]*/, int64_t R, int J,
                double* __restrict__ vals) {
-  __shared__ double red[8][8][32];
+  __shared__ double red[8][32 * NC];
   const InterpPlan pl = *plan;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int npan = FWD ? (pl.nf_neg + pl.nf_pos) : pl.nb;
   const int ngroups = npan * (kIP / 8);
-  const int j = blockIdx.x * 32 + lane;
-  const bool jok = j < J;
+  const int j0 = blockIdx.x * 32 * NC + lane;
   // reduction range of this block
   const int64_t per = (R + gridDim.z - 1) / gridDim.z;
   const int64_t rbeg = (int64_t)blockIdx.z * per;
@@ -123,12 +125,14 @@ k_interp_nodes(const InterpPlan* __restrict__ plan, const float* __restrict__ rv
     if (FWD) fwd_panel(pl, panel, mid, half, wref);
     else bwd_panel(pl, panel, mid, half);
     const double xq = mid + half * cheb_node((node0 % kIP) + (lane & 7));   // node handled by this lane (lanes 0..7 used)
-    double acc[8];
+    double acc[8][NC];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[q][c] = 0.0;
     // 4 rows of the reduction index per warp iteration: lane (q = lane & 7, sub = lane >> 3) evaluates the exponential
     // of row r + sub at node q (argument in fp64, expf in fp32: ~1e-7 relative, averaged over the sum), then every lane
-    // accumulates its column in fp64
+    // accumulates its columns in fp64
     for (int64_t r = rbeg + (int64_t)wid * 4; r < rend; r += 32) {
       const int64_t rr = r + (lane >> 3);
       float e = 0.f;
@@ -139,22 +143,41 @@ k_interp_nodes(const InterpPlan* __restrict__ plan, const float* __restrict__ rv
 #pragma unroll
       for (int sub = 0; sub < 4; ++sub) {
         const int64_t r2 = r + sub;
-        const double b = (jok && r2 < rend) ? (double)B[r2 * J + j] : 0.0;
+        double b[NC];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = fma((double)__shfl_sync(CA_FULL, e, q + 8 * sub), b, acc[q]);
+        for (int c = 0; c < NC; ++c) b[c] = (r2 < rend && j0 + 32 * c < J) ? (double)B[r2 * J + j0 + 32 * c] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const double eq = (double)__shfl_sync(CA_FULL, e, q + 8 * sub);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) acc[q][c] = fma(eq, b[c], acc[q][c]);
+        }
       }
     }
+    // cross-warp sum in warp order
+    for (int w = 0; w < 8; ++w) {
+      if (wid == w) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) red[wid][q][lane] = acc[q];
-    __syncthreads();
-    // thread (q = wid, lane): sum over the 8 warps in order
-    double s = 0.0;
+        for (int q = 0; q < 8; ++q)
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w][wid][lane];
-    if (jok) vals[((int64_t)blockIdx.z * nodes_total + node0 + wid) * J + j] = s;
+          for (int c = 0; c < NC; ++c) {
+            double* slot = &red[q][c * 32 + lane];
+            *slot = (w == 0) ? acc[q][c] : *slot + acc[q][c];
+          }
+      }
+      __syncthreads();
+    }
+    // thread (node q = wid, lane): its NC columns
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int j = j0 + 32 * c;
+      if (j < J) vals[((int64_t)blockIdx.z * nodes_total + node0 + wid) * J + j] = red[wid][c * 32 + lane];
+    }
     __syncthreads();   // red is reused by the next group
   }
 }
+// host: columns per lane and grid.x for J columns
+inline int interp_nodes_nc(int J) { int nc = (J + 31) / 32; return nc > kINodeMaxNC ? kINodeMaxNC : (nc < 1 ? 1 : nc); }
 
 // Chebyshev coefficients per panel: c_k = (2/P) sum_p f(x_p) cos(pi k (p + 1/2) / P), c_0 halved.
 // The node values arrive as `nsplit` partials that are summed here in a fixed order.

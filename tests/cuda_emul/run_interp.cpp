@@ -36,7 +36,7 @@ int main(int argc, char** argv) {
   const size_t eval_smem = (size_t)smem_panels * kIP * J * sizeof(double);
 
   // forward: nodes -> coefficients -> evaluation per cell (grid.y = 3 here: blocks stride over the active node groups)
-  ca_emul::launch(k_interp_nodes<true>, dim3((J + 31) / 32, 3, kISplitF), dim3(256), 0, (const InterpPlan*)&plan,
+  ca_emul::launch(k_interp_nodes<true, 1>, dim3((J + 31) / 32, 3, kISplitF), dim3(256), 0, (const InterpPlan*)&plan,
                   (const float*)w.data(), (const float*)nullptr, (const float*)Mx.data(), (int64_t)G, J, vals.data());
   {
     ca_emul::launch(k_interp_coeffs, dim3((J + 31) / 32, kIMaxPanF), dim3(kIP * 32), 0, (const InterpPlan*)&plan,
@@ -46,7 +46,7 @@ int main(int argc, char** argv) {
                   (const double*)coef.data(), (const float*)psi.data(), (int64_t)N, J, Zx.data(), smem_panels);
 
   // backward: nodes over w (reduction over cells, kISplitB partials) -> coefficients -> evaluation per gene
-  ca_emul::launch(k_interp_nodes<false>, dim3((J + 31) / 32, 3, kISplitB), dim3(256), 0,
+  ca_emul::launch(k_interp_nodes<false, 1>, dim3((J + 31) / 32, 3, kISplitB), dim3(256), 0,
                   (const InterpPlan*)&plan, (const float*)psi.data(), (const float*)shift.data(), (const float*)Rx.data(),
                   (int64_t)N, J, vals.data());
   {
