@@ -79,6 +79,24 @@ struct NcclApi {
   const char* (*GetErrorString)(int) = nullptr;
 };
 
+#ifdef CA_EMULATE   // tests/cuda_emul: ranks are threads of one process, see nccl_emul.h
+}  // namespace
+#include "nccl_emul.h"
+namespace {
+NcclApi& nccl() {
+  static NcclApi api;
+  if (api.lib) return api;
+  api.GetUniqueId = [](void* p) { return ca_emul_nccl::GetUniqueId(p); };
+  api.CommInitRank = [](void** c, int w, Uid id, int r) { return ca_emul_nccl::CommInitRank(c, w, id, r); };
+  api.AllReduce = [](const void* s, void* d, size_t n, int t, int o, void* c, cudaStream_t st) {
+    return ca_emul_nccl::AllReduce(s, d, n, t, o, c, (void*)st);
+  };
+  api.CommDestroy = [](void* c) { return ca_emul_nccl::CommDestroy(c); };
+  api.GetErrorString = [](int e) { return ca_emul_nccl::GetErrorString(e); };
+  api.lib = (void*)&api;
+  return api;
+}
+#else
 NcclApi& nccl() {
   static NcclApi api;
   if (api.lib) return api;
@@ -100,6 +118,7 @@ NcclApi& nccl() {
   api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
   return api;
 }
+#endif
 constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;
 #define NCCL_OK(expr)                                                              \
   do {                                                                             \

@@ -363,3 +363,59 @@ def test_sparse_input_stays_compressed(example_sce):
     c = inference_tflow(sp.csc_matrix(Y), L, max_iter=2, verbose=False, seed=11)        # host PCA: densified on the host
     d = inference_tflow(Y, L, max_iter=2, verbose=False, seed=11)
     assert c["convergence_info"]["elbo"].tobytes() == d["convergence_info"]["elbo"].tobytes()
+
+
+@pytest.mark.parametrize("path", [("cudacore", ""), ("interp", "ypass2,epi2,lean")])
+@pytest.mark.parametrize("world", [2, 3])
+def test_cell_sharded_fit_matches_single_shard(example_sce, path, world):
+    """SURVEY 8e through the REAL sharded code path of core.cu: `world` ranks (threads of this process; the emulation
+    build swaps NCCL for an in-process rendezvous, tests/cuda_emul/nccl_emul.h) each hold a block of cells, sum the
+    gene-level gradient partials with one all-reduce per step, and must reproduce the single-shard fit: ELBO trace within
+    fp32 re-association, identical hard clone calls, per-cell parameters of the shards = rows of the global ones."""
+    import threading
+    from clonealign_b200 import dist as D
+    from clonealign_b200.session import Session
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
+    Yk, Lk, psi, mu_guess = hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"]
+    N = Yk.shape[0]
+    loc = O.safe_inverse_softplus(mu_guess)
+    kw = dict(mc_samples=2, K=1, seed=77, path=path[0], variants=path[1])
+
+    def trace(sess, out):
+        sess.init_gamma()
+        tr = [sess.elbo()]
+        for _ in range(3):
+            sess.step()
+            tr.append(sess.elbo())
+        out["elbo"], out["prm"] = np.array(tr), sess.params()
+        sess.close()
+
+    ref = {}
+    trace(Session(Yk, Lk, psi, loc, **kw), ref)
+    nid = Session.nccl_unique_id()
+    colsum = Yk.sum(axis=0)
+    outs, errs = [dict() for _ in range(world)], []
+
+    def rank_main(r):
+        try:
+            a, b = D.shard_bounds(N, r, world)
+            s = Session(Yk[a:b], Lk, psi[a:b], loc, rank=r, world=world, nccl_id=nid, n_total=N, colsum_total=colsum, **kw)
+            trace(s, outs[r])
+        except Exception as e:          # a dead rank would leave the others waiting in the rendezvous
+            errs.append(e)
+            raise
+    ts = [threading.Thread(target=rank_main, args=(r,), daemon=True) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=300) for t in ts]
+    assert not errs and all("elbo" in o for o in outs), errs
+    for o in outs[1:]:
+        assert o["elbo"].tobytes() == outs[0]["elbo"].tobytes()                 # every rank reports the same ELBO
+        assert o["prm"]["mu"].tobytes() == outs[0]["prm"]["mu"].tobytes()       # replicated gene-level state stays in step
+    assert (np.abs(outs[0]["elbo"] - ref["elbo"]) / np.abs(ref["elbo"])).max() < 1e-6
+    cp = np.concatenate([o["prm"]["clone_probs"] for o in outs])
+    names = ["A", "B", "C"]
+    assert O.clone_assignment(cp, names) == O.clone_assignment(ref["prm"]["clone_probs"], names)
+    assert np.abs(cp - ref["prm"]["clone_probs"]).max() < 1e-4
+    assert _relmax(np.concatenate([o["prm"]["psi"] for o in outs]), ref["prm"]["psi"]) < 1e-4
+    assert _relmax(outs[0]["prm"]["W"], ref["prm"]["W"]) < 1e-3 and _relmax(outs[0]["prm"]["alpha"], ref["prm"]["alpha"]) < 1e-4
