@@ -22,6 +22,7 @@
 #include "kernels_expgemm.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_interp.cuh"
+#include "kernels_p2p.cuh"
 #include "kernels_pca.cuh"
 #include "kernels_small.cuh"
 #ifdef CA_EMULATE   // tests/cuda_emul: functional CPU emulation of the non-tensor kernels (test infrastructure only)
@@ -269,6 +270,15 @@ struct ca_handle {
   int adam_t = 0;
 
   void* comm = nullptr;
+  // variant P2P: exchange buffer of this rank, the peers' mappings, step counter
+  bool p2p = false, p2p_ready = false;
+  float* p2p_buf = nullptr;
+  int64_t p2p_cnt = 0, p2p_cnt_pad = 0;
+  float* p2p_slots[kP2PMaxWorld] = {};
+  unsigned* p2p_flags[kP2PMaxWorld] = {};
+  void* p2p_mapped[kP2PMaxWorld] = {};
+  unsigned* p2p_ticket = nullptr;
+  unsigned p2p_step = 0;
   bool prof_on = false;
   std::vector<Prof> prof;
   int launches_last_step = 0;
@@ -580,7 +590,16 @@ void run_train(ca_handle* h, bool apply) {
     CA_LAUNCH(k_reduce_gsum, 1, 1024, 0, h->stream)(h->gsum_part, h->n_cell_parts, h->C, h->ar + (int64_t)h->G * (2 + h->KP));
     KCHECK();
   }
-  if (h->cfg.world > 1) {
+  if (h->cfg.world > 1 && h->p2p) {
+    if (!h->p2p_ready) fail("variant p2p: ca_core_p2p_connect has not been called");
+    LaunchScope ls(h, "allreduce");
+    P2PArgs a;
+    a.world = h->cfg.world; a.rank = h->cfg.rank; a.cnt = h->p2p_cnt; a.cnt_pad = h->p2p_cnt_pad; a.step = ++h->p2p_step;
+    a.src = h->ar; a.dst = h->ar; a.ticket = h->p2p_ticket;
+    for (int r = 0; r < kP2PMaxWorld; ++r) { a.slots[r] = h->p2p_slots[r]; a.flags[r] = h->p2p_flags[r]; }
+    CA_LAUNCH(k_p2p_allreduce, std::min(h->num_sms, 16), kP2PThreads, 0, h->stream)(a);
+    KCHECK();
+  } else if (h->cfg.world > 1) {
     LaunchScope ls(h, "allreduce");
     size_t cnt = (size_t)h->G * (2 + h->KP) + h->C;
     NCCL_OK(nccl().AllReduce(h->ar, h->ar, cnt, kNcclFloat32, kNcclSum, h->comm, h->stream));
@@ -765,6 +784,8 @@ void destroy(ca_handle* h) {
   cudaSetDevice(h->dev);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm) nccl().CommDestroy(h->comm);
+  for (int r = 0; r < kP2PMaxWorld; ++r)
+    if (h->p2p_mapped[r]) cudaIpcCloseMemHandle(h->p2p_mapped[r]);
   tc_plan_destroy(h->tcplan);
   for (auto& p : h->prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (void* p : h->allocs)
@@ -810,7 +831,9 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if (c.path == CA_PATH_INTERP && !(c.K == 1 && c.P == 0)) fail("interp path needs K == 1 and P == 0");
   h->interp = (c.path == CA_PATH_INTERP);
   h->variants = c.variants;
-  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN)) fail("unknown kernel variant bits 0x%x", c.variants);
+  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_P2P)) fail("unknown kernel variant bits 0x%x", c.variants);
+  if ((c.variants & CA_VAR_P2P) && c.world > kP2PMaxWorld) fail("variant p2p supports at most %d ranks", kP2PMaxWorld);
+  h->p2p = (c.variants & CA_VAR_P2P) && c.world > 1;
   if ((c.variants & CA_VAR_LEAN) && !(c.variants & CA_VAR_EPI2)) fail("variant lean needs variant epi2");
   h->lean = (c.variants & CA_VAR_LEAN) != 0;
   if ((c.variants & CA_VAR_YPASS2) && c.K + c.P != 1) fail("variant ypass2 needs K + P == 1");
@@ -1047,6 +1070,14 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     CUDA_OK(cudaFuncSetAttribute(k_cell_epilogue<EPI_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaFuncSetAttribute(k_cell_epilogue<EPI_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaFuncSetAttribute(k_cell_epilogue<EPI_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  if (h->p2p) {
+    h->p2p_cnt = (int64_t)G * (2 + KP) + C;
+    h->p2p_cnt_pad = round_up64(h->p2p_cnt, 4);
+    const size_t slot_bytes = sizeof(float) * 2 * (size_t)c.world * h->p2p_cnt_pad;
+    // one allocation (one IPC handle): slots, then the flags on their own 256-byte line
+    h->p2p_buf = (float*)h->alloc<unsigned char>(slot_bytes + 256 + sizeof(unsigned) * 2 * kP2PMaxWorld);
+    h->p2p_ticket = h->alloc<unsigned>(1);
   }
   if (c.world > 1) {
     Uid id;
@@ -1451,6 +1482,45 @@ int ca_core_pca_scores(ca_handle* h, int32_t max_iter, double tol, double* score
     }
     for (void* p : tmp) cudaFree(p);
     if (status) fail("%s", msg.c_str());
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_p2p_export(ca_handle* h, void* handle64, char* err, size_t errlen) {
+  try {
+    if (!h || !handle64) fail("bad argument");
+    if (!h->p2p) fail("ca_core_p2p_export: the session was not created with variant p2p (and world > 1)");
+    CUDA_OK(cudaSetDevice(h->dev));
+    CUDA_OK(cudaStreamSynchronize(h->stream));   // the zero-fill of the flags must have landed before a peer can signal
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t hd;
+    CUDA_OK(cudaIpcGetMemHandle(&hd, h->p2p_buf));
+    memcpy(handle64, &hd, 64);
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_p2p_connect(ca_handle* h, const void* handles, char* err, size_t errlen) {
+  try {
+    if (!h || !handles) fail("bad argument");
+    if (!h->p2p) fail("ca_core_p2p_connect: the session was not created with variant p2p (and world > 1)");
+    CUDA_OK(cudaSetDevice(h->dev));
+    const int world = h->cfg.world;
+    const size_t slot_bytes = sizeof(float) * 2 * (size_t)world * h->p2p_cnt_pad;
+    for (int r = 0; r < world; ++r) {
+      void* base = nullptr;
+      if (r == h->cfg.rank) {
+        base = h->p2p_buf;
+      } else {
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char*)handles + 64 * (size_t)r, 64);
+        CUDA_OK(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+        h->p2p_mapped[r] = base;
+      }
+      h->p2p_slots[r] = (float*)base;
+      h->p2p_flags[r] = (unsigned*)((char*)base + slot_bytes + 256);
+    }
+    h->p2p_ready = true;
     return 0;
   } catch (const std::exception& e) { return report(e, err, errlen); }
 }

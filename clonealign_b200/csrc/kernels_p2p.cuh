@@ -1,0 +1,87 @@
+// Variant P2P (world > 1): the per-step all-reduce of the gene-level gradient partials (G (2 + K + P) + C floats,
+// 240 KB at 100k x 20k x 12) as ONE kernel over NVLink peer memory instead of an ncclAllReduce launch.
+//
+// Every rank owns a device buffer that its peers map through CUDA IPC (ca_core_p2p_export / ca_core_p2p_connect):
+//     slots[2][world][cnt_pad] floats   slot (parity, r) = rank r's contribution of a step with that parity
+//     flags[2][world]          uint32   flag (parity, r) = last step whose contribution from rank r is complete
+// One launch per step on every rank (<= 16 co-resident blocks):
+//   push   : the rank's partial sums are written straight into slot (parity, rank) of EVERY rank's buffer
+//            (16-byte stores over NVLink; NVSwitch gives every pair full bandwidth, so the 8 x 240 KB leave in ~2 us);
+//   signal : when the last block has finished pushing (ticket), one system-scope fence and `flag[parity][rank] = step`
+//            on every peer;
+//   reduce : every block waits until all `world` flags of its OWN buffer carry this step, then sums its slice of the
+//            slots in RANK ORDER into the local all-reduce buffer.
+// Rank order makes the result bit-identical on every rank and independent of timing (the replicated gene-level Adam
+// state cannot drift apart).  Two parities: a fast rank can start pushing step s + 1 while a slow one still reduces
+// step s; it cannot reach s + 2 before the slow rank has signalled s + 1, i.e. finished reducing s.
+// Replaces: nothing in the reference (single process, no collective; SURVEY.md 8e adds exactly this exchange).
+#pragma once
+#include "common.cuh"
+
+#ifndef CA_SPIN_PAUSE
+#define CA_SPIN_PAUSE() __nanosleep(64)
+#endif
+
+namespace ca {
+
+constexpr int kP2PMaxWorld = 16;
+constexpr int kP2PThreads = 512;
+
+struct P2PArgs {
+  int world, rank;
+  int64_t cnt, cnt_pad;            // floats per contribution (cnt_pad: multiple of 4)
+  unsigned step;                   // 1, 2, 3, ... (flags start at 0)
+  const float* src;                // this rank's partial sums [cnt]
+  float* dst;                      // reduced result [cnt] (may alias src)
+  float* slots[kP2PMaxWorld];      // base of every rank's slots[2][world][cnt_pad] (own entry = local pointer)
+  unsigned* flags[kP2PMaxWorld];   // base of every rank's flags[2][world]
+  unsigned* ticket;                // local, zero between launches
+};
+
+__global__ void __launch_bounds__(kP2PThreads) k_p2p_allreduce(P2PArgs a) {
+  __shared__ int is_last;
+  const int par = (int)(a.step & 1u);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  // ---- push ----
+  const int64_t nvec = a.cnt_pad / 4;
+  for (int p = 0; p < a.world; ++p) {
+    const int peer = (a.rank + p) % a.world;     // stagger the targets so that the ranks do not all hit rank 0 first
+    float4* out = reinterpret_cast<float4*>(a.slots[peer] + ((int64_t)par * a.world + a.rank) * a.cnt_pad);
+    for (int64_t i = tid; i < nvec; i += nth) {
+      float4 v;
+      const int64_t e = 4 * i;
+      v.x = e < a.cnt ? a.src[e] : 0.f;
+      v.y = e + 1 < a.cnt ? a.src[e + 1] : 0.f;
+      v.z = e + 2 < a.cnt ? a.src[e + 2] : 0.f;
+      v.w = e + 3 < a.cnt ? a.src[e + 3] : 0.f;
+      out[i] = v;
+    }
+  }
+  // ---- signal (last block of this rank) ----
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (is_last && threadIdx.x < a.world) {
+    __threadfence_system();
+    volatile unsigned* f = a.flags[threadIdx.x] + par * a.world + a.rank;
+    *f = a.step;
+    if (threadIdx.x == 0) *a.ticket = 0u;
+  }
+  // ---- wait for every rank's contribution in the local buffer ----
+  if (threadIdx.x < a.world) {
+    volatile unsigned* f = a.flags[a.rank] + par * a.world + threadIdx.x;
+    while (*f != a.step) CA_SPIN_PAUSE();
+  }
+  __syncthreads();
+  __threadfence_system();
+  // ---- reduce in rank order ----
+  const float* base = a.slots[a.rank] + (int64_t)par * a.world * a.cnt_pad;
+  for (int64_t i = tid; i < a.cnt; i += nth) {
+    float s = 0.f;
+    for (int r = 0; r < a.world; ++r) s += __ldcv(base + (int64_t)r * a.cnt_pad + i);
+    a.dst[i] = s;
+  }
+}
+
+}  // namespace ca

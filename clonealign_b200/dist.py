@@ -97,5 +97,27 @@ def sharded_session(Y_local, L, psi_local, loc_init, n_total, colsum_local, rank
     if world > 1:
         mine = Session.nccl_unique_id() if rank == 0 else bytes(128)
         nccl_id = broadcast_bytes(mine, 128, src=0)
-    return Session(Y_local, L, psi_local, loc_init, device=device, rank=rank, world=world, nccl_id=nccl_id,
+    sess = Session(Y_local, L, psi_local, loc_init, device=device, rank=rank, world=world, nccl_id=nccl_id,
                    n_total=n_total, colsum_total=colsum_total, **kw)
+    if world > 1 and "p2p" in _variant_names(kw.get("variants")):
+        # variant p2p: gather the CUDA IPC handles of the exchange buffers in rank order and map the peers
+        sess.p2p_connect(allgather_bytes(sess.p2p_export(), 64))
+    return sess
+
+
+def _variant_names(v):
+    if not v:
+        return []
+    return [x for x in v.split(",") if x] if isinstance(v, str) else list(v)
+
+
+def allgather_bytes(payload: bytes, nbytes: int):
+    """Every rank contributes `nbytes` raw bytes; returns the list of all contributions in rank order."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        return [bytes(payload)]
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(_dev())
+    out = [torch.zeros(nbytes, dtype=torch.uint8, device=_dev()) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, mine)
+    return [bytes(t.cpu().numpy().tobytes()) for t in out]

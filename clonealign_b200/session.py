@@ -24,7 +24,7 @@ from . import _lib
 
 _STORE = {"auto": _lib.STORE_AUTO, "f32": _lib.STORE_F32, "u16": _lib.STORE_U16, "u8": _lib.STORE_U8}
 _PATH = {"auto": _lib.PATH_AUTO, "cudacore": _lib.PATH_CUDACORE, "tensor": _lib.PATH_TENSOR, "interp": _lib.PATH_INTERP}
-_VARIANT = {"ypass2": _lib.VAR_YPASS2, "epi2": _lib.VAR_EPI2, "lean": _lib.VAR_LEAN}
+_VARIANT = {"ypass2": _lib.VAR_YPASS2, "epi2": _lib.VAR_EPI2, "lean": _lib.VAR_LEAN, "p2p": _lib.VAR_P2P}
 
 
 def variant_mask(variants) -> int:
@@ -277,6 +277,19 @@ class Session:
         self._chk(self._lib.ca_core_pca_scores(self._h, int(max_iter), float(tol), _ptr(out), C.byref(it), self._err,
                                                len(self._err)))
         return out, it.value
+
+    # -- variant p2p: all-reduce over NVLink peer memory (kernels_p2p.cuh) ----------------------------
+    def p2p_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's exchange buffer."""
+        buf = C.create_string_buffer(64)
+        self._chk(self._lib.ca_core_p2p_export(self._h, buf, self._err, len(self._err)))
+        return buf.raw
+
+    def p2p_connect(self, handles):
+        """`handles`: the world handles from p2p_export() of every rank, in rank order (collective)."""
+        blob = b"".join(bytes(h) for h in handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        self._chk(self._lib.ca_core_p2p_connect(self._h, buf, self._err, len(self._err)))
 
     # -- measurement hooks --------------------------------------------------------------------------
     def time_steps(self, n_steps: int, with_eval: bool = False) -> float:

@@ -65,8 +65,10 @@ enum ca_path     { CA_PATH_AUTO = 0, CA_PATH_CUDACORE = 1, CA_PATH_TENSOR = 2, C
  * them on the device against the default kernels before using them).
  *   YPASS2: Y pass on packed fp32 pairs (add/fma.rn.f32x2), see kernels_ypass.cuh
  *   EPI2  : (interp path) Clenshaw evaluation fused into a leaner per-cell epilogue, see kernels_fused.cuh
- *   LEAN  : (with EPI2) gene-level / scalar / optimiser work in 3 launches instead of 11, see kernels_fused.cuh    */
-enum ca_variant  { CA_VAR_YPASS2 = 1, CA_VAR_EPI2 = 2, CA_VAR_LEAN = 4 };
+ *   LEAN  : (with EPI2) gene-level / scalar / optimiser work in 3 launches instead of 11, see kernels_fused.cuh
+ *   P2P   : (world > 1) the per-step all-reduce as one kernel over NVLink peer memory instead of ncclAllReduce; needs
+ *           ca_core_p2p_export / ca_core_p2p_connect after ca_core_create, see kernels_p2p.cuh                      */
+enum ca_variant  { CA_VAR_YPASS2 = 1, CA_VAR_EPI2 = 2, CA_VAR_LEAN = 4, CA_VAR_P2P = 8 };
 
 typedef struct ca_config {
   int64_t N;            /* cells held by this handle (this rank's shard)                       */
@@ -148,6 +150,12 @@ CA_API int ca_core_correlations(ca_handle* h, const int32_t* clone_idx, const do
  * scale() and adds its own N(0, 0.05^2) noise (:205-207) and writes the result with ca_core_set_array("psi").
  * Stops when 1 - |<v_new, v_old>| < tol or after max_iter iterations; *iters = iterations used.  world == 1 only. */
 CA_API int ca_core_pca_scores(ca_handle* h, int32_t max_iter, double tol, double* scores, int32_t* iters, char* err, size_t errlen);
+
+/* Variant P2P (world > 1): every rank exports the 64-byte CUDA IPC handle of its exchange buffer, the caller gathers
+ * the `world` handles in rank order (any transport) and hands them to every rank; from then on the per-step all-reduce of
+ * the gene-level gradient partials runs as one kernel over peer memory (kernels_p2p.cuh).  Collective calls. */
+CA_API int ca_core_p2p_export(ca_handle* h, void* handle64, char* err, size_t errlen);
+CA_API int ca_core_p2p_connect(ca_handle* h, const void* handles, char* err, size_t errlen);
 
 /* Measurement hooks (bench.py): run n_steps train steps (and, if with_eval != 0, one ELBO
  * evaluation after each, as the reference loop does) back to back on the handle's stream,

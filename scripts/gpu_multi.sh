@@ -1,5 +1,7 @@
 #!/bin/bash
-# multi-GPU bench via torchrun (NG GPUs)
+# multi-GPU bench via torchrun (NG GPUs).  EXTRA passes bench flags, e.g. the one-shot NVLink all-reduce (kernels_p2p.cuh):
+#   gpurun --gpus 2 --timeout 300 -- 'NG=2 EXTRA="--path interp --variants ypass2,epi2,lean,p2p" bash scripts/gpu_multi.sh'
+# (validate at NG=2 with a short timeout before any larger N: a peer that never signals leaves the kernel spinning)
 set -u
 NG=${NG:-2}
 mkdir -p gpurun_out

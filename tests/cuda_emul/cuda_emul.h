@@ -192,6 +192,9 @@ inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_REL
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+template <typename T> inline T __ldcv(const T* p) { return *(const volatile T*)p; }
+#define CA_SPIN_PAUSE() std::this_thread::yield()
 struct __half { unsigned short v; };
 struct __nv_bfloat16 { unsigned short v; };
 inline __half __float2half_rn(float) { return {0}; }   // only the tensor path (not emulated) consumes halves
@@ -275,7 +278,7 @@ inline int host_workers() {
   static int n = [] {
     const char* e = getenv("CA_EMUL_THREADS");
     int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
-    return v < 1 ? 1 : (v > 16 ? 16 : v);
+    return v < 4 ? 4 : (v > 16 ? 16 : v);   // >= 4: blocks of a spin-waiting kernel must be co-resident
   }();
   return n;
 }
@@ -380,3 +383,9 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
   return cudaSuccess;
 }
 template <typename K> inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
+// CUDA IPC between the "ranks" of the emulation (threads of one process): a handle is the pointer itself
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }

@@ -365,7 +365,8 @@ def test_sparse_input_stays_compressed(example_sce):
     assert c["convergence_info"]["elbo"].tobytes() == d["convergence_info"]["elbo"].tobytes()
 
 
-@pytest.mark.parametrize("path", [("cudacore", ""), ("interp", "ypass2,epi2,lean")])
+@pytest.mark.parametrize("path", [("cudacore", ""), ("interp", "ypass2,epi2,lean"), ("cudacore", "p2p"),
+                                  ("interp", "ypass2,epi2,lean,p2p")])
 @pytest.mark.parametrize("world", [2, 3])
 def test_cell_sharded_fit_matches_single_shard(example_sce, path, world):
     """SURVEY 8e through the REAL sharded code path of core.cu: `world` ranks (threads of this process; the emulation
@@ -392,7 +393,9 @@ def test_cell_sharded_fit_matches_single_shard(example_sce, path, world):
         sess.close()
 
     ref = {}
-    trace(Session(Yk, Lk, psi, loc, **kw), ref)
+    trace(Session(Yk, Lk, psi, loc, **dict(kw, variants=path[1].replace(",p2p", "").replace("p2p", ""))), ref)
+    p2p = "p2p" in path[1]
+    handles, gate = [None] * world, threading.Barrier(world)
     nid = Session.nccl_unique_id()
     colsum = Yk.sum(axis=0)
     outs, errs = [dict() for _ in range(world)], []
@@ -401,6 +404,10 @@ def test_cell_sharded_fit_matches_single_shard(example_sce, path, world):
         try:
             a, b = D.shard_bounds(N, r, world)
             s = Session(Yk[a:b], Lk, psi[a:b], loc, rank=r, world=world, nccl_id=nid, n_total=N, colsum_total=colsum, **kw)
+            if p2p:      # variant p2p: all-reduce kernel over "peer memory" (IPC handles are plain pointers here)
+                handles[r] = s.p2p_export()
+                gate.wait(timeout=120)
+                s.p2p_connect(handles)
             trace(s, outs[r])
         except Exception as e:          # a dead rank would leave the others waiting in the rendezvous
             errs.append(e)
