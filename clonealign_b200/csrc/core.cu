@@ -278,6 +278,7 @@ struct ca_handle {
   unsigned* p2p_flags[kP2PMaxWorld] = {};
   void* p2p_mapped[kP2PMaxWorld] = {};
   unsigned* p2p_ticket = nullptr;
+  int* p2p_err = nullptr;
   unsigned p2p_step = 0;
   bool prof_on = false;
   std::vector<Prof> prof;
@@ -595,7 +596,7 @@ void run_train(ca_handle* h, bool apply) {
     LaunchScope ls(h, "allreduce");
     P2PArgs a;
     a.world = h->cfg.world; a.rank = h->cfg.rank; a.cnt = h->p2p_cnt; a.cnt_pad = h->p2p_cnt_pad; a.step = ++h->p2p_step;
-    a.src = h->ar; a.dst = h->ar; a.ticket = h->p2p_ticket;
+    a.src = h->ar; a.dst = h->ar; a.ticket = h->p2p_ticket; a.error = h->p2p_err;
     for (int r = 0; r < kP2PMaxWorld; ++r) { a.slots[r] = h->p2p_slots[r]; a.flags[r] = h->p2p_flags[r]; }
     CA_LAUNCH(k_p2p_allreduce, std::min(h->num_sms, 16), kP2PThreads, 0, h->stream)(a);
     KCHECK();
@@ -1078,6 +1079,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     // one allocation (one IPC handle): slots, then the flags on their own 256-byte line
     h->p2p_buf = (float*)h->alloc<unsigned char>(slot_bytes + 256 + sizeof(unsigned) * 2 * kP2PMaxWorld);
     h->p2p_ticket = h->alloc<unsigned>(1);
+    h->p2p_err = h->alloc<int>(1);
   }
   if (c.world > 1) {
     Uid id;
@@ -1219,7 +1221,10 @@ int ca_core_elbo(ca_handle* h, double* elbo, char* err, size_t errlen) {
     CUDA_OK(cudaSetDevice(h->dev));
     run_elbo_async(h);
     CUDA_OK(cudaMemcpyAsync(elbo, h->elbo_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    int p2p_failed = 0;
+    if (h->p2p_err) CUDA_OK(cudaMemcpyAsync(&p2p_failed, h->p2p_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (p2p_failed) fail("variant p2p: the all-reduce kernel timed out waiting for a peer's contribution");
     return 0;
   } catch (const std::exception& e) { return report(e, err, errlen); }
 }

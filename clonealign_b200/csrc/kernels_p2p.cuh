@@ -36,7 +36,9 @@ struct P2PArgs {
   float* slots[kP2PMaxWorld];      // base of every rank's slots[2][world][cnt_pad] (own entry = local pointer)
   unsigned* flags[kP2PMaxWorld];   // base of every rank's flags[2][world]
   unsigned* ticket;                // local, zero between launches
+  int* error;                      // local: set to 1 when a peer's flag did not arrive within kP2PSpinCycles
 };
+constexpr long long kP2PSpinCycles = 6000000000LL;   // ~3 s of SM clock: a dead peer must not hang the GPU for ever
 
 __global__ void __launch_bounds__(kP2PThreads) k_p2p_allreduce(P2PArgs a) {
   __shared__ int is_last;
@@ -71,7 +73,14 @@ __global__ void __launch_bounds__(kP2PThreads) k_p2p_allreduce(P2PArgs a) {
   // ---- wait for every rank's contribution in the local buffer ----
   if (threadIdx.x < a.world) {
     volatile unsigned* f = a.flags[a.rank] + par * a.world + threadIdx.x;
-    while (*f != a.step) CA_SPIN_PAUSE();
+    const long long t0 = clock64();
+    while (*f != a.step) {
+      if (clock64() - t0 > kP2PSpinCycles) {
+        *a.error = 1;
+        break;
+      }
+      CA_SPIN_PAUSE();
+    }
   }
   __syncthreads();
   __threadfence_system();

@@ -195,6 +195,7 @@ inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 template <typename T> inline T __ldcv(const T* p) { return *(const volatile T*)p; }
 #define CA_SPIN_PAUSE() std::this_thread::yield()
+inline long long clock64() { return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() * 2; }
 struct __half { unsigned short v; };
 struct __nv_bfloat16 { unsigned short v; };
 inline __half __float2half_rn(float) { return {0}; }   // only the tensor path (not emulated) consumes halves
