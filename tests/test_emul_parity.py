@@ -426,3 +426,32 @@ def test_cell_sharded_fit_matches_single_shard(example_sce, path, world):
     assert np.abs(cp - ref["prm"]["clone_probs"]).max() < 1e-4
     assert _relmax(np.concatenate([o["prm"]["psi"] for o in outs]), ref["prm"]["psi"]) < 1e-4
     assert _relmax(outs[0]["prm"]["W"], ref["prm"]["W"]) < 1e-3 and _relmax(outs[0]["prm"]["alpha"], ref["prm"]["alpha"]) < 1e-4
+
+
+def test_bench_selfcheck_gate_on_the_emulation():
+    """bench.py's on-device gate (selfcheck_run / selfcheck_compare), exercised here with the CUDA-core path standing in
+    for the tcgen05 reference: every candidate kernel set passes it, a deliberately wrong run does not."""
+    import importlib.util
+    import os
+    from clonealign_b200.session import Session
+    from clonealign_b200.synthetic import make_synthetic
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    syn = make_synthetic(400, 300, 5, seed=3)
+    Y, L = syn["Y"].astype(np.float64), np.minimum(syn["L"], 6.0)
+    rng = np.random.default_rng(1)
+    psi = rng.standard_normal((400, 1))
+    loc = O.safe_inverse_softplus((Y / Y.mean(1, keepdims=True)).mean(0))
+    W0 = rng.standard_normal((300, 1)) * 0.1
+    mk = lambda path, var, **kw: (lambda: Session(Y, L, psi, loc, mc_samples=2, K=1, seed=9, path=path, variants=var, **kw))
+    ref = bench.selfcheck_run(mk("cudacore", ""), W0, timed=False)
+    for path, var in bench.CANDIDATES:
+        if path == "auto":
+            path = "cudacore"                   # no tensor cores under emulation
+        ok, d = bench.selfcheck_compare(ref, bench.selfcheck_run(mk(path, var), W0, timed=False))
+        assert ok, (path, var, d)
+    bad = bench.selfcheck_run(mk("interp", "epi2", learning_rate=0.3), W0, timed=False)     # different optimiser step
+    ok, d = bench.selfcheck_compare(ref, bad)
+    assert not ok and d["grad_psi"] < 1e-3      # same gradients, diverging trace
