@@ -454,6 +454,13 @@ void run_forward(ca_handle* h, int mode) {
     CUDA_OK(cudaEventRecord(h->ev_join, h->stream2));
     joined_later = true;
   }
+  SampleMuArgs sm;
+  sm.G = h->G; sm.C = h->C; sm.S = h->S; sm.K = h->K; sm.KP = h->KP; sm.SCp = h->SCp; sm.J = h->J; sm.Gld = h->Gld;
+  sm.loc = h->loc; sm.lsd = h->lsd; sm.Vm = h->Vm; sm.L = h->L; sm.colsum = h->colsum; sm.chi_raw = h->chi_raw;
+  sm.eps_in = eps_in; sm.seed = h->cfg.seed; sm.draw = h->draw++;
+  sm.eps_out = h->eps; sm.mu = h->mu; sm.logmu = h->logmu; sm.sig = h->sig;
+  sm.Mx = h->tc ? nullptr : h->Mx; sm.MxT_hi = h->tc ? h->MxT_hi : nullptr; sm.MxT_lo = h->tc ? h->MxT_lo : nullptr;
+  sm.gene_part = h->gene_part;
   if (h->lean) {
     LaunchScope ls(h, "prologue");
     PrologueArgs a;
@@ -462,23 +469,18 @@ void run_forward(ca_handle* h, int mode) {
     a.log_alpha = h->log_alpha; a.mm = h->mm; a.mm_psi = h->mm_psi; a.chi_cur = h->chi_cur;
     a.scal_elbo = h->scal_elbo; a.wsq = h->wsq; a.pmm_part = h->pmm_part; a.ticket = h->ticket; a.plan = h->iplan;
     a.dirichlet_const = (double)h->C * lgamma(1.0 / h->C) - lgamma(1.0);
-    CA_LAUNCH(k_prologue, 2 + kProPsiBlocks, kProThreads, 0, h->stream)(a);
+    a.mu = sm;
+    a.mu_vec4 = (h->C % 4 == 0) ? 1 : 0;
+    CA_LAUNCH(k_prologue, 2 + kProPsiBlocks + h->n_gene_blocks, kProThreads, 0, h->stream)(a);
     KCHECK();
   } else {
     LaunchScope ls(h, "alpha");
     CA_LAUNCH(k_alpha, 1, 32, 0, h->stream)(h->u, h->C, h->chi_raw, h->K, h->log_alpha, h->scal_elbo);
     KCHECK();
   }
-  {
+  if (!h->lean) {
     LaunchScope ls(h, "sample_mu");
-    SampleMuArgs a;
-    a.G = h->G; a.C = h->C; a.S = h->S; a.K = h->K; a.KP = h->KP; a.SCp = h->SCp; a.J = h->J; a.Gld = h->Gld;
-    a.loc = h->loc; a.lsd = h->lsd; a.Vm = h->Vm; a.L = h->L; a.colsum = h->colsum; a.chi_raw = h->chi_raw;
-    a.eps_in = eps_in; a.seed = h->cfg.seed; a.draw = h->draw++;
-    a.eps_out = h->eps; a.mu = h->mu; a.logmu = h->logmu; a.sig = h->sig;
-    a.Mx = h->tc ? nullptr : h->Mx; a.MxT_hi = h->tc ? h->MxT_hi : nullptr; a.MxT_lo = h->tc ? h->MxT_lo : nullptr;
-    a.gene_part = h->gene_part;
-    CA_LAUNCH(k_sample_mu, h->n_gene_blocks, 256, 0, h->stream)(a);
+    CA_LAUNCH(k_sample_mu, h->n_gene_blocks, 256, 0, h->stream)(sm);
     KCHECK();
   }
   if (h->KP == 0) {
@@ -986,7 +988,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   h->shift = z(N + 64); h->mm = z(2); h->log_alpha = z(C);
   h->YV = z((size_t)N * std::max(KP, 1)); h->YtU = z((size_t)G * std::max(KP, 1)); h->Fout = z((size_t)N * C);
   h->dM_sum = z((size_t)G * J);
-  h->n_gene_blocks = (G + 255) / 256;
+  h->n_gene_blocks = h->lean ? (G + kProThreads - 1) / kProThreads : (G + 255) / 256;
   h->n_epi_blocks = ceil_div64(N, kEpiWarps);
   h->n_cell_parts = h->epi2 ? (int64_t)h->num_sms : h->n_epi_blocks;
   h->gene_part = h->alloc<double>(h->n_gene_blocks);

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused(FusedArgs a)
 // =====================================================================================================================
 // Variant LEAN (with EPI2): fewer, fatter launches for the gene-level / scalar work that every rank of a cell-sharded
 // fit replicates and that therefore bounds strong scaling (profiles/r01_notes.md: ~0.25 ms per step independent of N).
-//   k_prologue   = k_alpha + k_minmax(W) + k_wsq + k_minmax(psi) + k_interp_plan          (5 launches -> 1)
+//   k_prologue   = k_alpha + k_minmax(W) + k_wsq + k_minmax(psi) + k_interp_plan + k_sample_mu   (6 launches -> 1)
 //   k_gene_fused = k_interp_eval<BWD> + k_gene_grads_warp + k_reduce_gsum                  (3 launches -> 1, no dMx round trip)
 //   k_adam_all   = k_gene_adam + k_scalar_adam + k_cell_adam                               (3 launches -> 1)
 // =====================================================================================================================
@@ -273,10 +273,13 @@ struct PrologueArgs {
   unsigned* ticket;      // zero before the first launch; the last block resets it
   InterpPlan* plan;
   double dirichlet_const;   // C lgamma(1/C) - lgamma(1)   (host)
+  SampleMuArgs mu;          // gene blocks (k_sample_mu): blocks 2 + kProPsiBlocks ..; gene_part has one partial per gene block
+  int mu_vec4;              // C % 4 == 0: 16-byte stores of the contraction operand
 };
 
 // roles by block: 0 = alpha / scalar priors (k_alpha), 1 = W range and sum of squares (k_minmax, k_wsq; K == 1),
-// 2.. = psi range partials; the block that arrives last combines the ranges into the panel plan (k_interp_plan).
+// 2 .. 2 + kProPsiBlocks - 1 = psi range partials, the rest = gene blocks (k_sample_mu: draws, mu, contraction operand,
+// gene-level ELBO terms); the block that arrives last combines the ranges into the panel plan (k_interp_plan).
 __global__ void __launch_bounds__(kProThreads) k_prologue(PrologueArgs a) {
   __shared__ double dscr[32];
   __shared__ float smin[32], smax[32];
@@ -326,6 +329,10 @@ __global__ void __launch_bounds__(kProThreads) k_prologue(PrologueArgs a) {
       a.mm[1] = mx;
       a.wsq[0] = tot;
     }
+  } else if (blockIdx.x >= 2 + kProPsiBlocks) {
+    const int gb = blockIdx.x - 2 - kProPsiBlocks;
+    if (a.mu_vec4) sample_mu_body<true>(a.mu, gb, dscr, a.mu.gene_part);
+    else sample_mu_body<false>(a.mu, gb, dscr, a.mu.gene_part);
   } else {
     const int pb = blockIdx.x - 2;
     const int64_t per = (a.N + kProPsiBlocks - 1) / kProPsiBlocks;

@@ -187,9 +187,12 @@ struct SampleMuArgs {
   double* gene_part;               // one partial per block
 };
 
-__global__ void __launch_bounds__(256) k_sample_mu(SampleMuArgs a) {
-  __shared__ double scratch[32];
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
+// body shared by k_sample_mu (one launch of its own) and k_prologue (variant lean: gene blocks of the fused launch).
+// VEC4 (C % 4 == 0, K = 1 layouts only): the C values a gene contributes to one sample are contiguous in Mx
+// ([g][s*C + c]), so they leave as 16-byte stores instead of C scattered 4-byte stores per (gene, sample).
+template <bool VEC4>
+__device__ __forceinline__ void sample_mu_body(const SampleMuArgs& a, int block, double* scratch, double* part_out) {
+  int g = block * blockDim.x + threadIdx.x;
   double e = 0.0;
   if (g < a.G) {
     float loc = a.loc[g], lsd = a.lsd[g], sd = expf(lsd);
@@ -210,6 +213,17 @@ __global__ void __launch_bounds__(256) k_sample_mu(SampleMuArgs a) {
       a.sig[o] = sg;
       double lsg = -(double)softplusf(-x);   // log sigmoid(x)
       e += cs * (double)lm - 0.5 * (double)lm * (double)lm - (-0.5 * (double)eps * (double)eps - (double)lsd - lsg);
+      if (VEC4) {
+        const float4* L4 = reinterpret_cast<const float4*>(a.L + (int64_t)g * a.C);
+        float4* M4 = reinterpret_cast<float4*>(a.Mx + (int64_t)g * a.J + s * a.C);
+        float4* W4 = reinterpret_cast<float4*>(a.Mx + (int64_t)g * a.J + a.SCp + s * a.C);
+        for (int c4 = 0; c4 < a.C / 4; ++c4) {
+          const float4 l = L4[c4];
+          const float4 m = make_float4(mu * l.x, mu * l.y, mu * l.z, mu * l.w);
+          M4[c4] = m;
+          W4[c4] = make_float4(vk[0] * m.x, vk[0] * m.y, vk[0] * m.z, vk[0] * m.w);
+        }
+      } else
       for (int c = 0; c < a.C; ++c) {
         float m = mu * a.L[(int64_t)g * a.C + c];
         int j = s * a.C + c;
@@ -235,7 +249,12 @@ __global__ void __launch_bounds__(256) k_sample_mu(SampleMuArgs a) {
     }
   }
   double t = block_sum(e, scratch);
-  if (threadIdx.x == 0) a.gene_part[blockIdx.x] = t;
+  if (threadIdx.x == 0) part_out[block] = t;
+}
+
+__global__ void __launch_bounds__(256) k_sample_mu(SampleMuArgs a) {
+  __shared__ double scratch[32];
+  sample_mu_body<false>(a, blockIdx.x, scratch, a.gene_part);
 }
 
 // min / max of the single latent loading column (K == 1, P == 0): gives the exact row maximum of

@@ -65,7 +65,7 @@ enum ca_path     { CA_PATH_AUTO = 0, CA_PATH_CUDACORE = 1, CA_PATH_TENSOR = 2, C
  * them on the device against the default kernels before using them).
  *   YPASS2: Y pass on packed fp32 pairs (add/fma.rn.f32x2), see kernels_ypass.cuh
  *   EPI2  : (interp path) Clenshaw evaluation fused into a leaner per-cell epilogue, see kernels_fused.cuh
- *   LEAN  : (with EPI2) gene-level / scalar / optimiser work in 3 launches instead of 11, see kernels_fused.cuh
+ *   LEAN  : (with EPI2) gene-level / scalar / optimiser work in 3 launches instead of 12, see kernels_fused.cuh
  *   P2P   : (world > 1) the per-step all-reduce as one kernel over NVLink peer memory instead of ncclAllReduce; needs
  *           ca_core_p2p_export / ca_core_p2p_connect after ca_core_create, see kernels_p2p.cuh                      */
 enum ca_variant  { CA_VAR_YPASS2 = 1, CA_VAR_EPI2 = 2, CA_VAR_LEAN = 4, CA_VAR_P2P = 8 };
