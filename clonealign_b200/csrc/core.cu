@@ -1385,6 +1385,10 @@ int ca_core_correlations(ca_handle* h, const int32_t* clone_idx, const double* L
     int* d_z = nullptr;
     float* d_L = nullptr;
     double *d_part = nullptr, *d_out = nullptr;
+    struct Guard {   // scratch is released on every exit path
+      int*& z; float*& l; double*& p; double*& o;
+      ~Guard() { cudaFree(z); cudaFree(l); cudaFree(p); cudaFree(o); }
+    } guard{d_z, d_L, d_part, d_out};
     const int RS = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 64));
     CUDA_OK(cudaMalloc(&d_z, sizeof(int) * N));
     CUDA_OK(cudaMalloc(&d_L, sizeof(float) * (size_t)G * C));
@@ -1405,7 +1409,6 @@ int ca_core_correlations(ca_handle* h, const int32_t* clone_idx, const double* L
     KCHECK();
     CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(double) * G, cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_z); cudaFree(d_L); cudaFree(d_part); cudaFree(d_out);
     return 0;
   } catch (const std::exception& e) { return report(e, err, errlen); }
 }

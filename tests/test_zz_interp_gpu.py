@@ -144,3 +144,78 @@ def test_sparse_input_matches_dense(example_sce):
     a = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], n=2, seed=7)[0]
     b = _run_trace(sp.csr_matrix(hi["Y"]), hi["L"], hi["psi_init"], hi["mu_guess"], n=2, seed=7)[0]
     assert a.tobytes() == b.tobytes()
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size properties of the new kernel sets and of the other BASELINE configurations
+# ---------------------------------------------------------------------------------------------------
+def _full_size_check(N, G, C, S, path, variants, V=0, n_sample=48, z_tol=2e-6, want_path=None):
+    """Sampled-cell parity of Z / F against float64 numpy with the device's own parameters and draws, simplex
+    constraints and an ELBO that improves, at a BASELINE.json shape (size-independent properties)."""
+    import math
+    import torch
+    from clonealign_b200.session import Session
+    from clonealign_b200.synthetic import make_synthetic_cuda
+    syn = make_synthetic_cuda(N, G, C, seed=2345234)
+    Yd = syn["Y"]
+    L = np.minimum(syn["L"], 6.0)
+    rng = np.random.default_rng(12345)
+    psi = rng.standard_normal((N, 1))
+    mu_guess = (Yd / Yd.mean(dim=1, keepdim=True)).mean(dim=0).double().cpu().numpy()
+    idx = np.sort(rng.choice(N, n_sample, replace=False))
+    Ysub = Yd[torch.tensor(idx, device=Yd.device)].double().cpu().numpy()
+    allele, vsub = {}, 0.0
+    if V:
+        cn = rng.integers(1, 4, size=(V, C)).astype(np.float64)
+        cov = rng.poisson(0.3, size=(N, V)).astype(np.float64)
+        alt = rng.binomial(cov.astype(np.int64), 0.4).astype(np.float64)
+        allele = dict(clone_allele=cn, alt=alt, cov=cov)
+        vsub = O.construct_ai_likelihood(cn, alt[idx].T, cov[idx].T)
+    sess = Session(Yd, L, psi, O.safe_inverse_softplus(mu_guess), mc_samples=S, K=1, seed=7, path=path, variants=variants, **allele)
+    del Yd, syn
+    torch.cuda.empty_cache()
+    try:
+        if want_path:
+            assert sess.describe()["path"] == want_path
+        sess.init_gamma()
+        e0 = sess.elbo()
+        for _ in range(5):
+            sess.step()
+        e1 = sess.elbo()
+        assert math.isfinite(e0) and math.isfinite(e1) and e1 > e0
+        sess.grads()
+        eps = sess.get_eps().astype(np.float64)
+        W = sess.get_array("W")[:, 0]
+        psi_d = sess.get_array("psi")[idx, 0]
+        mu = O.softplus(sess.get_array("loc")[:, 0][None] + np.exp(sess.get_array("lsd")[:, 0])[None] * eps)
+        eta = psi_d[:, None] * W[None]
+        m = eta.max(axis=1)
+        Z = np.einsum("ng,sgc->nsc", np.exp(eta - m[:, None]), mu[:, :, None] * L[None]).reshape(len(idx), -1)
+        Zdev = sess.get_array("Z")[idx]
+        assert np.abs(sess.get_array("shift")[idx, 0] - m).max() < 1e-5
+        assert np.abs(Zdev / Z - 1.0).max() < z_tol
+        s = Ysub.sum(1)
+        F = (Ysub @ np.log(L)) - s[:, None] * (np.log(Z).reshape(len(idx), S, C).mean(1) + m[:, None]) + vsub
+        assert np.abs(sess.get_array("F")[idx] - F).max() <= 2e-5 * np.abs(F).max()
+        prm = sess.params()
+        assert np.abs(prm["clone_probs"].sum(1) - 1.0).max() < 1e-6 and prm["clone_probs"].min() >= 0.0
+        assert abs(prm["alpha"].sum() - 1.0) < 1e-6
+    finally:
+        sess.close()
+
+
+@pytest.mark.parametrize("variants", ["", "ypass2,epi2,lean"])
+def test_full_size_c3_interp(variants):
+    """BASELINE config 3 (100k x 20k x 12, S = 8) on the interpolation path: Z is near-exact (fp64 node sums), unlike the
+    tcgen05 path's round-toward-zero accumulation."""
+    _full_size_check(100_000, 20_000, 12, 8, "interp", variants, want_path="interp")
+
+
+def test_full_size_c4_allele():
+    """BASELINE config 4 (50k x 10k x 8 with the allele-specific likelihood fused in), default path."""
+    _full_size_check(50_000, 10_000, 8, 1, "auto", "", V=200, z_tol=1e-4, want_path="tcgen05")
+
+
+def test_full_size_c5_one_replica():
+    """BASELINE config 5, one restart replica (200k x 20k x 16), default path."""
+    _full_size_check(200_000, 20_000, 16, 1, "auto", "", z_tol=1e-4, want_path="tcgen05")
