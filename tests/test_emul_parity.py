@@ -173,6 +173,9 @@ def test_storage_formats_and_input_layouts_agree(example_sce):
     run = lambda y, **kw: _run_trace(y, hi["L"], hi["psi_init"], hi["mu_guess"], n=2, seed=7, **kw)[0]
     traces = [run(hi["Y"], y_store=s) for s in ("f32", "u16", "u8")]
     assert traces[0].tobytes() == traces[1].tobytes() == traces[2].tobytes()
+    packed = [run(hi["Y"], y_store=s, variants="ypass2") for s in ("f32", "u16", "u8")]      # f32x2 Y pass: same exactness
+    assert packed[0].tobytes() == packed[1].tobytes() == packed[2].tobytes()
+    assert np.abs(packed[0] - traces[0]).max() <= 1e-6 * np.abs(traces[0]).max()             # re-associated sums only
     t_f = run(np.asfortranarray(hi["Y"]), y_store="f32")                    # an R double matrix
     t_i = run(np.asfortranarray(hi["Y"].astype(np.int32)))                  # an R integer matrix
     t_32 = run(hi["Y"].astype(np.float32))
@@ -455,3 +458,30 @@ def test_bench_selfcheck_gate_on_the_emulation():
     bad = bench.selfcheck_run(mk("interp", "epi2", learning_rate=0.3), W0, timed=False)     # different optimiser step
     ok, d = bench.selfcheck_compare(ref, bad)
     assert not ok and d["grad_psi"] < 1e-3      # same gradients, diverging trace
+
+
+@pytest.mark.parametrize("path", [("cudacore", "ypass2"), ("interp", "ypass2,epi2,lean")])
+def test_several_row_and_column_tiles(path):
+    """N > 2 row blocks of the Y pass (RB = 512), G > one 2048-column tile, more cells than one sweep of the persistent
+    per-cell / per-gene kernels: tile seams, partial-sum layouts and strided loops."""
+    from clonealign_b200.synthetic import make_synthetic
+    syn = make_synthetic(1100, 2300, 4, seed=8)
+    d, p, mu_guess, _ = _case(syn["Y"].astype(np.float64), np.minimum(syn["L"], 6.0), K=1, seed=2)
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=2, K=1, path=path[0], variants=path[1], seed=1) as sess:
+        _load_params(sess, p)
+        _check_grads(sess, d, p, 2)
+
+
+@pytest.mark.parametrize("path", [("interp", ""), ("interp", "ypass2,epi2,lean")])
+def test_c3_column_structure(path):
+    """C = 12 clones, S = 8 samples (J = 192 columns): the template instantiations BASELINE config 3 runs on the device
+    (6 columns per lane in the node kernels, 3 Clenshaw chains per lane in the fused per-cell kernel, 16-byte operand
+    stores), on a matrix small enough for the emulation."""
+    from clonealign_b200.synthetic import make_synthetic
+    syn = make_synthetic(700, 2600, 12, seed=12)
+    d, p, mu_guess, _ = _case(syn["Y"].astype(np.float64), np.minimum(syn["L"], 6.0), K=1, seed=4, scale=0.3)
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=8, K=1, path=path[0], variants=path[1], seed=1) as sess:
+        assert sess.describe()["J"] == 192
+        _load_params(sess, p)
+        errs = _check_grads(sess, d, p, 8)
+        assert errs["Z"] < 5e-6
