@@ -278,6 +278,9 @@ assert np.abs(r["grads"]["gamma_logits"] - ref["grads"]["gamma_logits"][a:b]).ma
 payload = bytes(range(128)) if rank == 0 else bytes(128)
 assert D.broadcast_bytes(payload, 128) == bytes(range(128))
 assert D.max_over_ranks(float(rank)) == world - 1
+# the 64-byte CUDA IPC handles of variant p2p are gathered in rank order
+got = D.allgather_bytes(bytes([rank + 1]) * 64, 64)
+assert got == [bytes([r + 1]) * 64 for r in range(world)]
 sys.stdout.write("RANK_OK_%d\n" % rank); sys.stdout.flush()
 '''
 
