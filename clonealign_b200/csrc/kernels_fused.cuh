@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused(FusedArgs a)
       tt = w_pos > 0.0 ? (x - pf * w_pos) * ih_pos - 1.0 : 0.0;
       panel = nf_neg + pf;
     }
+    // a NaN psi (diverged fit) must yield NaN results, not an out-of-range table index
+    panel = panel < 0 ? 0 : (panel >= npan ? (npan > 0 ? npan - 1 : 0) : panel);
     const double* cpan = in_smem ? csm + (size_t)panel * a.J * kFusedPitch : a.coeff + (int64_t)panel * per_panel;
     // ---- Z columns ----
     float zf[NJ];

@@ -247,6 +247,7 @@ k_interp_eval(const InterpPlan* __restrict__ plan, const double* __restrict__ co
         panel = pl.f_pos_w > 0.0 ? (int)(x / pl.f_pos_w) : 0;
         panel = pl.nf_neg + (panel >= pl.nf_pos ? pl.nf_pos - 1 : panel);
       }
+      panel = panel < 0 ? 0 : (panel >= npan ? (npan > 0 ? npan - 1 : 0) : panel);   // NaN psi: stay inside the table
       fwd_panel(pl, panel, mid, half, wref);
     } else {
       panel = pl.b_w > 0.0 ? (int)((x - pl.wmin) / pl.b_w) : 0;

@@ -485,3 +485,22 @@ def test_c3_column_structure(path):
         _load_params(sess, p)
         errs = _check_grads(sess, d, p, 8)
         assert errs["Z"] < 5e-6
+
+
+@pytest.mark.parametrize("path", [("interp", ""), ("interp", "ypass2,epi2,lean")])
+def test_nan_parameters_give_nan_not_a_fault(example_sce, path):
+    """A diverged fit (NaN in psi) must surface as a NaN ELBO, as in the reference (R/inference-tflow.R:411-412 lets NA
+    ELBOs through after the first iteration) -- not as an out-of-range panel index in the interpolation tables."""
+    Y, L = example_sce
+    d, p, mu_guess, _ = _case(Y[:64], L, K=1, seed=3)
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=1, K=1, path=path[0], variants=path[1], seed=1) as sess:
+        _load_params(sess, p)
+        bad = p.psi.copy()
+        bad[5, 0] = np.nan
+        sess.set_array("psi", bad)
+        assert np.isnan(sess.elbo())
+        sess.step()
+        assert np.isnan(sess.elbo())
+        bad[:] = np.nan
+        sess.set_array("psi", bad)
+        assert np.isnan(sess.elbo())
