@@ -105,9 +105,13 @@ def clonealign(gene_expression_data, copy_number_data, max_iter=200, rel_tol=1e-
 
 
 def run_clonealign(gene_expression_data, copy_number_data, initial_shrinks=(0, 5, 10), n_repeats=3,
-                   print_elbos=True, seed=None, devices=None, **kwargs):
+                   print_elbos=True, seed=None, devices=None, share_inputs=False, **kwargs):
     """Best-of-restarts wrapper (R/clonealign.R:35-75).  Restarts are independent fits; `devices`
-    (list of CUDA ordinals) spreads them round-robin over GPUs (replicas only, no communication)."""
+    (list of CUDA ordinals) spreads them round-robin over GPUs (replicas only, no communication).
+    `share_inputs=True`: the restarts differ only through the RNG (psi noise, op seed), so the principal components and,
+    per device, the count matrix in HBM with everything derived from it are built once and shared read-only by the
+    restarts on that device (`DeviceData`) instead of being recomputed / re-uploaded 9 times; the fits
+    are bit-identical to unshared ones.  Off by default until it has run on hardware (verified on the CPU emulation)."""
     rng = np.random.default_rng(seed)
     jobs = []
     for is_ in initial_shrinks:
@@ -116,6 +120,22 @@ def run_clonealign(gene_expression_data, copy_number_data, initial_shrinks=(0, 5
             kw = dict(kwargs)
             kw.update(initial_shrink=is_, seed=int(rng.integers(0, 2 ** 31 - 1)), device=dev)   # seeds fixed up front
             jobs.append(kw)
+    cache = None
+    if share_inputs:
+        import threading
+        cache = {"lock": threading.Lock()}
+        for kw in jobs:
+            kw["cache"] = cache
+    try:
+        return _run_restarts(gene_expression_data, copy_number_data, jobs, devices, print_elbos)
+    finally:
+        if cache is not None:
+            for k, v in list(cache.items()):
+                if isinstance(k, tuple) and k[0] == "data":
+                    v.close()
+
+
+def _run_restarts(gene_expression_data, copy_number_data, jobs, devices, print_elbos):
     if devices and len(devices) > 1:
         # replicas only: one host thread per GPU, each running its share of the restarts one after another
         # (the C-ABI calls release the GIL); results keep the serial order, so the selection below is unchanged

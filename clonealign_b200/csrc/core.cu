@@ -209,8 +209,25 @@ struct Prof {
 
 }  // namespace
 
+// Device-resident inputs of a fit that do not depend on the restart: the count matrix as stored and
+// everything derived from it once (library sizes, B = Y log L, multinomial constants, column sums, allele term).
+// Sessions created with ca_core_create_shared read them in place (read-only), so the restarts of run_clonealign
+// (R/clonealign.R:50-56) upload and preprocess Y once per device instead of once per fit.
+struct ca_data {
+  int dev = 0;
+  int64_t N = 0, ldY = 0;
+  int G = 0, C = 0, V = 0, ystore = CA_STORE_F32, poison = 0;
+  double const_sum = 0.0;
+  void* Y = nullptr;
+  float *L = nullptr, *Bm = nullptr, *vA = nullptr, *s = nullptr, *colsum = nullptr, *snv = nullptr;
+  std::vector<void*> allocs;
+  int refs = 0;
+};
+
 struct ca_handle {
   ca_config cfg{};
+  ca_data* shared = nullptr;       // inputs owned by a ca_data (ca_core_create_shared), else by this handle
+  bool data_only = false;          // ca_core_data_create: stop after the Y-derived part of build()
   int dev = 0, num_sms = 148;
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -793,6 +810,7 @@ void destroy(ca_handle* h) {
   for (auto& p : h->prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (void* p : h->allocs)
     if (p) cudaFree(p);
+  if (h->shared) h->shared->refs--;
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -808,8 +826,16 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if (c.world < 1 || c.rank < 0 || c.rank >= c.world) fail("bad rank/world");
   if (c.world > 1 && !c.nccl_id) fail("world > 1 requires cfg.nccl_id");
   if (c.world > 1 && !colsum_total) fail("world > 1 requires colsum_total (global column sums of Y)");
-  if (!Y || !L || !loc_init || (c.K > 0 && !psi_init) || (c.P > 0 && !X)) fail("missing input pointer");
-  if (c.V > 0 && (!clone_allele || !alt || !cov)) fail("V > 0 requires clone_allele, alt and cov");
+  if (!h->shared && (!Y || !L)) fail("missing input pointer");
+  if (!h->data_only && (!loc_init || (c.K > 0 && !psi_init) || (c.P > 0 && !X))) fail("missing input pointer");
+  if (!h->shared && c.V > 0 && (!clone_allele || !alt || !cov)) fail("V > 0 requires clone_allele, alt and cov");
+  if (h->shared) {
+    const ca_data* d = h->shared;
+    if (c.world != 1) fail("shared inputs are for single-shard sessions (world == 1)");
+    if (c.N != d->N || c.G != d->G || c.C != d->C || c.V != d->V || c.device != d->dev)
+      fail("session dimensions / device do not match the shared inputs (N %lld G %d C %d V %d device %d)", (long long)d->N, d->G, d->C,
+           d->V, d->dev);
+  }
   int ndev = 0;
   CUDA_OK(cudaGetDeviceCount(&ndev));
   if (c.device < 0 || c.device >= ndev) fail("CUDA device %d not available (%d devices)", c.device, ndev);
@@ -854,6 +880,12 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   const int64_t N = h->N;
   const int G = h->G, C = h->C, S = h->S, K = h->K, KP = h->KP, J = h->J;
 
+  if (h->shared) {
+    const ca_data* d = h->shared;
+    h->Y = d->Y; h->ystore = d->ystore; h->L = d->L; h->Bm = d->Bm; h->vA = d->vA; h->s = d->s; h->colsum = d->colsum;
+    h->snv = d->snv; h->const_sum = d->const_sum; h->poison = d->poison;
+    if (h->ldY != d->ldY) fail("shared inputs: leading dimension mismatch");
+  } else {
   // ---- Y -> device fp32 [N][ldY] ----
   float* Yf = h->alloc<float>((size_t)N * h->ldY);
   switch (c.y_dtype) {
@@ -963,6 +995,11 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     CUDA_OK(cudaStreamSynchronize(h->stream));
     h->release(Yf);
     h->Y = Yn;
+  }
+  }   // !shared
+  if (h->data_only) {
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return;
   }
 
   // ---- parameters (R/inference-tflow.R:240-272) ----
@@ -1171,6 +1208,65 @@ int ca_core_create(ca_handle** out, const ca_config* cfg, const void* Y, const d
     h->cfg = *cfg;
     build(h, Y, L, psi_init, loc_init, X, colsum_total, clone_allele, alt, cov);
     h->cfg.nccl_id = nullptr;   // never retain caller pointers
+    h->cfg.y_indptr = nullptr;
+    h->cfg.y_indices = nullptr;
+    *out = h;
+    return 0;
+  } catch (const std::exception& e) {
+    destroy(h);
+    return report(e, err, errlen);
+  }
+}
+
+int ca_core_data_create(ca_data** out, const ca_config* cfg, const void* Y, const double* L, const double* colsum_total,
+                        const double* clone_allele, const double* alt, const double* cov, char* err, size_t errlen) {
+  ca_handle* t = nullptr;
+  try {
+    if (!out || !cfg) fail("null argument");
+    t = new ca_handle();
+    t->cfg = *cfg;
+    t->cfg.S = std::max(1, cfg->S);
+    t->cfg.K = 0; t->cfg.P = 0; t->cfg.path = CA_PATH_CUDACORE; t->cfg.variants = 0; t->cfg.world = 1; t->cfg.rank = 0;
+    t->data_only = true;
+    build(t, Y, L, nullptr, nullptr, nullptr, colsum_total, clone_allele, alt, cov);
+    ca_data* d = new ca_data();
+    d->dev = t->dev; d->N = t->N; d->ldY = t->ldY; d->G = t->G; d->C = t->C; d->V = t->V; d->ystore = t->ystore;
+    d->poison = t->poison; d->const_sum = t->const_sum;
+    d->Y = t->Y; d->L = t->L; d->Bm = t->Bm; d->vA = t->vA; d->s = t->s; d->colsum = t->colsum; d->snv = t->snv;
+    for (void* p : t->allocs)
+      if (p) d->allocs.push_back(p);
+    t->allocs.clear();     // ownership moved
+    destroy(t);
+    *out = d;
+    return 0;
+  } catch (const std::exception& e) {
+    destroy(t);
+    return report(e, err, errlen);
+  }
+}
+
+int ca_core_data_destroy(ca_data* d, char* err, size_t errlen) {
+  try {
+    if (!d) return 0;
+    if (d->refs > 0) fail("ca_core_data_destroy: %d session(s) still use these inputs", d->refs);
+    cudaSetDevice(d->dev);
+    for (void* p : d->allocs) cudaFree(p);
+    delete d;
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_create_shared(ca_handle** out, const ca_config* cfg, ca_data* data, const double* psi_init, const double* loc_init,
+                          const double* X, char* err, size_t errlen) {
+  ca_handle* h = nullptr;
+  try {
+    if (!out || !cfg || !data) fail("null argument");
+    h = new ca_handle();
+    h->cfg = *cfg;
+    h->shared = data;
+    data->refs++;
+    build(h, nullptr, nullptr, psi_init, loc_init, X, nullptr, nullptr, nullptr, nullptr);
+    h->cfg.nccl_id = nullptr;
     h->cfg.y_indptr = nullptr;
     h->cfg.y_indices = nullptr;
     *out = h;

@@ -59,7 +59,13 @@ def _message(verbose, msg):
 
 
 def pca_init(Y, K, rng, truncated=None):
-    """psi initialisation, R/inference-tflow.R:204-208: prcomp(log2(Y+1), center, scale)$x[,1:K], scale(), + N(0,.05^2).
+    """psi initialisation, R/inference-tflow.R:204-208: prcomp(log2(Y+1), center, scale)$x[,1:K], scale(), + N(0,.05^2)."""
+    pcs = pca_scaled(Y, K, truncated)
+    return pcs + rng.normal(0.0, 0.05, size=pcs.shape)
+
+
+def pca_scaled(Y, K, truncated=None):
+    """scale(prcomp(log2(Y+1), center, scale)$x[,1:K]) (R/inference-tflow.R:204-206), without the noise of :207.
 
     The reference runs a full `prcomp` (O(N G^2)); only the K leading components are used, so large inputs go through
     a truncated Lanczos SVD (same components up to sign, which the model does not see: W starts at 0)."""
@@ -81,15 +87,14 @@ def pca_init(Y, K, rng, truncated=None):
     else:
         U, S, _ = np.linalg.svd(X, full_matrices=False)
         pcs = (U * S)[:, :K]
-    pcs = (pcs - pcs.mean(axis=0)) / pcs.std(axis=0, ddof=1)
-    return pcs + rng.normal(0.0, 0.05, size=pcs.shape)
+    return (pcs - pcs.mean(axis=0)) / pcs.std(axis=0, ddof=1)
 
 
 def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1, gene_filter_threshold=0,
                     x=None, clone_allele=None, cov=None, ref=None, fix_alpha=False, dtype="float32",
                     saturate_=True, saturation_threshold=6, K=1, mc_samples=1, verbose=True, initial_shrink=5,
                     data_init_mu=True, seed=None, device=0, psi_init=None, y_store="auto", path="auto",
-                    gene_names=None, variants=None, correlations_with=None, device_pca=False):
+                    gene_names=None, variants=None, correlations_with=None, device_pca=False, cache=None):
     """CUDA-backed equivalent of the reference's `inference_tflow`.
 
     Y_dat: cell x gene counts; L_dat: gene x clone copy number.  Returns the reference's list as a dict:
@@ -100,6 +105,10 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
     `device_pca=True` (K == 1): the leading principal component that initialises psi (:203-205) is computed by power
     iteration on the count matrix resident in HBM (ca_core_pca_scores) instead of a host-side SVD; scale() and the
     N(0, 0.05^2) noise (:205-207) stay on the host and use the same RNG stream positions as the host path.
+    `cache` (a dict owned by the caller, e.g. `run_clonealign`): restart-independent work is done once and reused by later
+    calls WITH IDENTICAL INPUTS -- the un-noised principal components, and per device the count matrix resident in HBM with
+    everything derived from it (`DeviceData`, ca_core_data_create); the RNG stream positions do not change, so a cached
+    restart is bit-identical to an uncached one.  The caller closes `cache[("data", device)]` when done.
     `correlations_with = (L_unsaturated, clone_call_probability)`: also run the caller's post-hoc
     `compute_correlations` (R/clonealign.R:292-294,318-334) on the device while Y is still resident; the result is
     returned under "correlations" (retained genes only).
@@ -162,8 +171,18 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
         if device_pca and K == 1:
             pca_noise = rng.normal(0.0, 0.05, size=(N, 1))                            # :207 (same stream position)
             psi_init = np.zeros((N, 1))                                               # replaced below, before any use
+        elif K > 0:
+            if cache is None:
+                pcs = pca_scaled(Y, K)                                                # :204-206
+            else:
+                import contextlib
+                with cache.get("lock") or contextlib.nullcontext():                   # restarts on several devices: compute once
+                    pcs = cache.get("pcs")
+                    if pcs is None:
+                        pcs = cache["pcs"] = pca_scaled(Y, K)
+            psi_init = pcs + rng.normal(0.0, 0.05, size=pcs.shape)                    # :207
         else:
-            psi_init = pca_init(Y, K, rng) if K > 0 else np.zeros((N, 0))             # :204-208
+            psi_init = np.zeros((N, 0))
     s_init = np.asarray(Y.sum(axis=1), dtype=np.float64).ravel()                      # :210
     if np.any(s_init == 0):
         raise ValueError("Some cells have no counts mapping")                         # :212-214
@@ -183,15 +202,26 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
         mu_guess = d / d.mean()
 
     op_seed = get_next_seed(rng)                                                      # :269
+    data = None
+    if cache is not None:           # restart-independent device inputs: upload + preprocess once per device
+        from .session import DeviceData
+        data = cache.get(("data", device))
+        if data is None:
+            data = cache[("data", device)] = DeviceData(Y, L, device=device, clone_allele=clone_allele if use_allele else None,
+                                                        alt=alt, cov=cov if use_allele else None, y_store=y_store)
     sess = Session(Y, L, psi_init, safe_inverse_softplus(mu_guess), mc_samples=int(mc_samples), K=K, x=x,
                    learning_rate=learning_rate, seed=op_seed, device=device,
                    clone_allele=clone_allele if use_allele else None, alt=alt, cov=cov if use_allele else None,
-                   y_store=y_store, path=path, variants=variants)
+                   y_store=y_store, path=path, variants=variants, data=data)
     correlations = None
     try:
         if pca_noise is not None:
-            pcs, _ = sess.pca_scores()                                                # :203-204 on the device
-            pcs = (pcs - pcs.mean()) / pcs.std(ddof=1)                                # scale(pcs), :205
+            pcs = cache.get("pcs_device") if cache is not None else None
+            if pcs is None:
+                pcs, _ = sess.pca_scores()                                            # :203-204 on the device
+                pcs = (pcs - pcs.mean()) / pcs.std(ddof=1)                            # scale(pcs), :205
+                if cache is not None:
+                    cache["pcs_device"] = pcs
             sess.set_array("psi", pcs[:, None] + pca_noise)
         sess.init_gamma()                                                             # :368-369
         elbo_val = sess.elbo()                                                        # :372

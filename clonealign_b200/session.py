@@ -64,12 +64,121 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def _marshal_y(Y, cfg, keep):
+    """Describe the count matrix in `cfg` (dtype / layout / memory space) and return (N, G, pointer)."""
+    if hasattr(Y, "data_ptr") and getattr(Y, "is_cuda", False):      # a CUDA tensor already in HBM
+        if Y.dim() != 2 or not Y.is_contiguous() or str(Y.dtype) != "torch.float32":
+            raise ValueError("device Y must be a contiguous 2-D float32 tensor (cells x genes)")
+        N, G = int(Y.shape[0]), int(Y.shape[1])
+        yptr = C.c_void_p(Y.data_ptr())
+        cfg.y_dtype, cfg.y_layout, cfg.y_mem = _lib.Y_F32, _lib.Y_ROWMAJOR, _lib.Y_DEVICE
+        keep.append(Y)
+    elif hasattr(Y, "tocsr") and hasattr(Y, "nnz"):                   # scipy.sparse: cells x genes, kept compressed
+        Ys = Y.tocsr()
+        Ys.sum_duplicates()
+        N, G = Ys.shape
+        if Ys.nnz >= 2 ** 31:
+            raise ValueError("sparse Y with >= 2^31 stored values is not supported (int32 offsets, as R's dgCMatrix)")
+        vals = np.ascontiguousarray(Ys.data, dtype=np.float64 if Ys.data.dtype not in (np.float32, np.int32) else Ys.data.dtype)
+        indptr = np.ascontiguousarray(Ys.indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(Ys.indices, dtype=np.int32)
+        cfg.y_dtype = {np.dtype(np.float64): _lib.Y_F64, np.dtype(np.float32): _lib.Y_F32, np.dtype(np.int32): _lib.Y_I32}[vals.dtype]
+        cfg.y_layout, cfg.y_mem = _lib.Y_CSR, _lib.Y_HOST
+        cfg.y_indptr, cfg.y_indices = _ptr(indptr), _ptr(indices)
+        yptr = _ptr(vals)
+        keep += [vals, indptr, indices]
+    else:
+        Y = np.asarray(Y)
+        if Y.ndim != 2:
+            raise ValueError("Y must be cells x genes")
+        if Y.dtype == np.float64:
+            cfg.y_dtype = _lib.Y_F64
+        elif Y.dtype == np.float32:
+            cfg.y_dtype = _lib.Y_F32
+        elif Y.dtype == np.int32:
+            cfg.y_dtype = _lib.Y_I32
+        else:
+            Y = Y.astype(np.float64)
+            cfg.y_dtype = _lib.Y_F64
+        if Y.flags.f_contiguous and not Y.flags.c_contiguous:
+            cfg.y_layout = _lib.Y_COLMAJOR                            # an R matrix
+        else:
+            Y = np.ascontiguousarray(Y)
+            cfg.y_layout = _lib.Y_ROWMAJOR
+        cfg.y_mem = _lib.Y_HOST
+        N, G = Y.shape
+        yptr = _ptr(Y)
+        keep.append(Y)
+    return N, G, yptr
+
+
+def _marshal_data(Y, L, clone_allele, alt, cov, cfg, keep):
+    """Y, L and the allele inputs -> (N, G, C, V, pointers...) with `cfg` filled in for them."""
+    N, G, yptr = _marshal_y(Y, cfg, keep)
+    Lm = _f64_colmajor(L)
+    if Lm.ndim != 2 or Lm.shape[0] != G:
+        raise ValueError("copy_number_data must have same number of genes (rows) as gene_expression_data")
+    Cn = Lm.shape[1]
+    V = 0
+    ca = al = cv = None
+    if clone_allele is not None:
+        ca = _f64_colmajor(clone_allele)
+        V = ca.shape[0]
+        if ca.shape[1] != Cn:
+            raise ValueError("clone_allele must be variants x clones")
+        al = _f64_colmajor(alt, (N, V))
+        cv = _f64_colmajor(cov, (N, V))
+    return N, G, Cn, V, yptr, Lm, ca, al, cv
+
+
+class DeviceData:
+    """Inputs of a fit that do not depend on the restart, resident on one GPU: the count matrix as stored plus everything
+    derived from it once (ca_core_data_create).  Sessions built with `Session(..., data=this)` share it read-only, so the
+    restarts of `run_clonealign` (R/clonealign.R:50-56) upload and preprocess Y once per device."""
+
+    def __init__(self, Y, L, *, device=0, clone_allele=None, alt=None, cov=None, y_store="auto"):
+        self._d = None
+        lib = _lib.load()
+        self._lib = lib
+        err = C.create_string_buffer(1024)
+        cfg = _lib.CaConfig()
+        keep = []
+        N, G, Cn, V, yptr, Lm, ca, al, cv = _marshal_data(Y, L, clone_allele, alt, cov, cfg, keep)
+        cfg.N, cfg.N_total, cfg.G, cfg.C, cfg.S, cfg.K, cfg.P, cfg.V = N, N, G, Cn, 1, 0, 0, V
+        cfg.device, cfg.rank, cfg.world = int(device), 0, 1
+        cfg.y_store, cfg.path, cfg.y_ld = _STORE[y_store], _lib.PATH_AUTO, 0
+        d = C.c_void_p()
+        _lib.check(lib.ca_core_data_create(C.byref(d), C.byref(cfg), yptr, _ptr(Lm), None, _ptr(ca), _ptr(al), _ptr(cv), err,
+                                           len(err)), err)
+        self._d = d
+        self.N, self.G, self.C, self.V, self.device = N, G, Cn, V, int(device)
+
+    def close(self):
+        if self._d is not None:
+            err = C.create_string_buffer(1024)
+            st = self._lib.ca_core_data_destroy(self._d, err, len(err))
+            _lib.check(st, err)
+            self._d = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Session:
     """One cell shard of one fit on one GPU."""
 
     def __init__(self, Y, L, psi_init, loc_init, *, mc_samples=1, K=1, x=None, learning_rate=0.1, seed=0,
                  device=0, clone_allele=None, alt=None, cov=None, rank=0, world=1, nccl_id=None, n_total=None,
-                 colsum_total=None, y_store="auto", path="auto", variants=None):
+                 colsum_total=None, y_store="auto", path="auto", variants=None, data=None):
         self._h = None
         if path == "auto":   # operator override, e.g. CLONEALIGN_B200_PATH=cudacore
             path = os.environ.get("CLONEALIGN_B200_PATH", "auto")
@@ -81,53 +190,13 @@ class Session:
 
         cfg = _lib.CaConfig()
         keep = []
-        if hasattr(Y, "data_ptr") and getattr(Y, "is_cuda", False):      # a CUDA tensor already in HBM
-            if Y.dim() != 2 or not Y.is_contiguous() or str(Y.dtype) != "torch.float32":
-                raise ValueError("device Y must be a contiguous 2-D float32 tensor (cells x genes)")
-            N, G = int(Y.shape[0]), int(Y.shape[1])
-            yptr = C.c_void_p(Y.data_ptr())
-            cfg.y_dtype, cfg.y_layout, cfg.y_mem = _lib.Y_F32, _lib.Y_ROWMAJOR, _lib.Y_DEVICE
-            keep.append(Y)
-        elif hasattr(Y, "tocsr") and hasattr(Y, "nnz"):                   # scipy.sparse: cells x genes, kept compressed
-            Ys = Y.tocsr()
-            Ys.sum_duplicates()
-            N, G = Ys.shape
-            if Ys.nnz >= 2 ** 31:
-                raise ValueError("sparse Y with >= 2^31 stored values is not supported (int32 offsets, as R's dgCMatrix)")
-            vals = np.ascontiguousarray(Ys.data, dtype=np.float64 if Ys.data.dtype not in (np.float32, np.int32) else Ys.data.dtype)
-            indptr = np.ascontiguousarray(Ys.indptr, dtype=np.int32)
-            indices = np.ascontiguousarray(Ys.indices, dtype=np.int32)
-            cfg.y_dtype = {np.dtype(np.float64): _lib.Y_F64, np.dtype(np.float32): _lib.Y_F32, np.dtype(np.int32): _lib.Y_I32}[vals.dtype]
-            cfg.y_layout, cfg.y_mem = _lib.Y_CSR, _lib.Y_HOST
-            cfg.y_indptr, cfg.y_indices = _ptr(indptr), _ptr(indices)
-            yptr = _ptr(vals)
-            keep += [vals, indptr, indices]
+        if data is not None:            # inputs already resident (DeviceData): Y / L / allele arguments are ignored
+            if data._d is None:
+                raise ValueError("DeviceData is closed")
+            N, G, Cn, V, device = data.N, data.G, data.C, data.V, data.device
+            yptr = Lm = ca = al = cv = None
         else:
-            Y = np.asarray(Y)
-            if Y.ndim != 2:
-                raise ValueError("Y must be cells x genes")
-            if Y.dtype == np.float64:
-                cfg.y_dtype = _lib.Y_F64
-            elif Y.dtype == np.float32:
-                cfg.y_dtype = _lib.Y_F32
-            elif Y.dtype == np.int32:
-                cfg.y_dtype = _lib.Y_I32
-            else:
-                Y = Y.astype(np.float64)
-                cfg.y_dtype = _lib.Y_F64
-            if Y.flags.f_contiguous and not Y.flags.c_contiguous:
-                cfg.y_layout = _lib.Y_COLMAJOR                            # an R matrix
-            else:
-                Y = np.ascontiguousarray(Y)
-                cfg.y_layout = _lib.Y_ROWMAJOR
-            cfg.y_mem = _lib.Y_HOST
-            N, G = Y.shape
-            yptr = _ptr(Y)
-            keep.append(Y)
-        Lm = _f64_colmajor(L)
-        if Lm.ndim != 2 or Lm.shape[0] != G:
-            raise ValueError("copy_number_data must have same number of genes (rows) as gene_expression_data")
-        Cn = Lm.shape[1]
+            N, G, Cn, V, yptr, Lm, ca, al, cv = _marshal_data(Y, L, clone_allele, alt, cov, cfg, keep)
         K = int(K)
         psi = _f64_colmajor(psi_init, (N, K)) if K > 0 else None
         loc = _f64_colmajor(loc_init, (G,))
@@ -141,15 +210,6 @@ class Session:
                 raise ValueError("x must have one row per cell")
             P = X.shape[1]
             X = np.asfortranarray(X)
-        V = 0
-        ca = al = cv = None
-        if clone_allele is not None:
-            ca = _f64_colmajor(clone_allele)
-            V = ca.shape[0]
-            if ca.shape[1] != Cn:
-                raise ValueError("clone_allele must be variants x clones")
-            al = _f64_colmajor(alt, (N, V))
-            cv = _f64_colmajor(cov, (N, V))
         cs = _f64_colmajor(colsum_total, (G,)) if colsum_total is not None else None
         idbuf = None
         if world > 1:
@@ -167,10 +227,15 @@ class Session:
 
         self.N, self.G, self.C, self.S, self.K, self.P, self.V = N, G, Cn, int(mc_samples), K, P, V
         h = C.c_void_p()
-        st = lib.ca_core_create(C.byref(h), C.byref(cfg), yptr, _ptr(Lm), _ptr(psi), _ptr(loc), _ptr(X), _ptr(cs),
-                                _ptr(ca), _ptr(al), _ptr(cv), self._err, len(self._err))
+        if data is not None:
+            st = lib.ca_core_create_shared(C.byref(h), C.byref(cfg), data._d, _ptr(psi), _ptr(loc), _ptr(X), self._err,
+                                           len(self._err))
+        else:
+            st = lib.ca_core_create(C.byref(h), C.byref(cfg), yptr, _ptr(Lm), _ptr(psi), _ptr(loc), _ptr(X), _ptr(cs),
+                                    _ptr(ca), _ptr(al), _ptr(cv), self._err, len(self._err))
         _lib.check(st, self._err)
         self._h = h
+        self._data = data               # keep the shared inputs alive as long as this session
         del keep
 
     # -- discovery --------------------------------------------------------------------------------

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CA_ABI_VERSION 3
+#define CA_ABI_VERSION 4
 #if defined(__GNUC__)
 #define CA_API __attribute__((visibility("default")))
 #else
@@ -43,6 +43,7 @@ extern "C" {
 #endif
 
 typedef struct ca_handle ca_handle;
+typedef struct ca_data ca_data;
 
 enum ca_y_dtype  { CA_Y_F64 = 0, CA_Y_F32 = 1, CA_Y_I32 = 2 };
 enum ca_y_layout { CA_Y_COLMAJOR = 0 /* R matrix: cell index fastest */, CA_Y_ROWMAJOR = 1 /* gene index fastest */,
@@ -112,6 +113,19 @@ CA_API int ca_core_create(ca_handle** out, const ca_config* cfg, const void* Y, 
                    const double* colsum_total, const double* clone_allele, const double* alt,
                    const double* cov, char* err, size_t errlen);
 CA_API int ca_core_destroy(ca_handle* h);
+
+/* Restarts (run_clonealign, R/clonealign.R:50-56): the inputs that do not depend on the restart -- the
+ * count matrix as stored in HBM and everything derived from it once (library sizes, B = Y log L, multinomial constants,
+ * column sums, allele term) -- can be built once per device and shared, read-only, by any number of sessions.
+ * ca_core_data_create takes the Y / L / allele arguments of ca_core_create (cfg: N, G, C, V, device, y_*; world == 1);
+ * ca_core_create_shared takes the per-fit arguments (cfg: S, K, P, seed, learning_rate, path, variants, ...).
+ * ca_core_data_destroy fails while sessions created from it are alive. */
+CA_API int ca_core_data_create(ca_data** out, const ca_config* cfg, const void* Y, const double* L,
+                        const double* colsum_total, const double* clone_allele, const double* alt, const double* cov,
+                        char* err, size_t errlen);
+CA_API int ca_core_data_destroy(ca_data* d, char* err, size_t errlen);
+CA_API int ca_core_create_shared(ca_handle** out, const ca_config* cfg, ca_data* data, const double* psi_init,
+                          const double* loc_init, const double* X, char* err, size_t errlen);
 
 /* the session operations */
 CA_API int ca_core_init_gamma(ca_handle* h, char* err, size_t errlen);

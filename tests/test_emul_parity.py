@@ -504,3 +504,45 @@ def test_nan_parameters_give_nan_not_a_fault(example_sce, path):
         bad[:] = np.nan
         sess.set_array("psi", bad)
         assert np.isnan(sess.elbo())
+
+
+def test_shared_device_inputs_for_restarts(example_sce):
+    """ca_core_data_create / ca_core_create_shared.  Sessions built on shared, read-only device inputs are
+    bit-identical to self-contained ones (also with the allele term and a non-default kernel set); run_clonealign with
+    share_inputs uploads / preprocesses / decomposes once and returns the same best fit; the inputs cannot be destroyed
+    while a session uses them."""
+    from clonealign_b200 import run_clonealign
+    from clonealign_b200._lib import CloneAlignLibraryError
+    from clonealign_b200.session import DeviceData, Session
+    Y, L = example_sce
+    d, p, mu_guess, al = _case(Y, L, K=1, use_v=True, seed=21)
+    loc = O.safe_inverse_softplus(mu_guess)
+
+    def trace(**kw):
+        with Session(d.Y, d.L, p.psi, loc, mc_samples=2, K=1, seed=5, **kw) as s:
+            s.init_gamma()
+            out = [s.elbo()]
+            for _ in range(2):
+                s.step()
+                out.append(s.elbo())
+            return np.array(out), s.params()["clone_probs"], s.params().get("clone_probs_from_snv")
+    with DeviceData(d.Y, d.L, **al) as data:
+        for kw in (dict(path="cudacore"), dict(path="interp", variants="ypass2,epi2,lean")):
+            a = trace(**kw, **al)
+            b = trace(data=data, **kw)
+            c = trace(data=data, **kw)                                   # a second session on the same inputs
+            assert a[0].tobytes() == b[0].tobytes() == c[0].tobytes() and a[1].tobytes() == b[1].tobytes()
+            assert a[2].tobytes() == b[2].tobytes()
+        s = Session(None, None, p.psi, loc, data=data)
+        with pytest.raises(CloneAlignLibraryError, match="still use these inputs"):
+            data.close()
+        s.close()
+        with pytest.raises(ValueError):                                 # wrong number of cells for these inputs
+            Session(None, None, p.psi[:10], loc, data=data)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        kw = dict(initial_shrinks=(0, 5), n_repeats=2, print_elbos=False, max_iter=3, verbose=False, seed=3)
+        f1 = run_clonealign(Y, L, share_inputs=True, **kw)
+        f2 = run_clonealign(Y, L, share_inputs=False, **kw)
+    assert f1["multirun_info"]["elbos"].tobytes() == f2["multirun_info"]["elbos"].tobytes()
+    assert f1["clone"] == f2["clone"]

@@ -219,3 +219,17 @@ def test_full_size_c4_allele():
 def test_full_size_c5_one_replica():
     """BASELINE config 5, one restart replica (200k x 20k x 16), default path."""
     _full_size_check(200_000, 20_000, 16, 1, "auto", "", z_tol=1e-4, want_path="tcgen05")
+
+
+def test_shared_device_inputs_for_restarts(example_sce):
+    """ca_core_data_create / ca_core_create_shared: restarts that share the device inputs are bit-identical."""
+    from clonealign_b200 import run_clonealign
+    import warnings
+    Y, L = example_sce
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        kw = dict(initial_shrinks=(0, 5), n_repeats=2, print_elbos=False, max_iter=3, verbose=False, seed=3)
+        f1 = run_clonealign(Y, L, share_inputs=True, **kw)
+        f2 = run_clonealign(Y, L, share_inputs=False, **kw)
+    assert f1["multirun_info"]["elbos"].tobytes() == f2["multirun_info"]["elbos"].tobytes()
+    assert f1["clone"] == f2["clone"]
