@@ -105,13 +105,16 @@ def clonealign(gene_expression_data, copy_number_data, max_iter=200, rel_tol=1e-
 
 
 def run_clonealign(gene_expression_data, copy_number_data, initial_shrinks=(0, 5, 10), n_repeats=3,
-                   print_elbos=True, seed=None, devices=None, share_inputs=False, **kwargs):
+                   print_elbos=True, seed=None, devices=None, share_inputs=False, restarts_in_flight=1, **kwargs):
     """Best-of-restarts wrapper (R/clonealign.R:35-75).  Restarts are independent fits; `devices`
     (list of CUDA ordinals) spreads them round-robin over GPUs (replicas only, no communication).
     `share_inputs=True`: the restarts differ only through the RNG (psi noise, op seed), so the principal components and,
     per device, the count matrix in HBM with everything derived from it are built once and shared read-only by the
     restarts on that device (`DeviceData`) instead of being recomputed / re-uploaded 9 times; the fits
-    are bit-identical to unshared ones.  Off by default until it has run on hardware (verified on the CPU emulation)."""
+    are bit-identical to unshared ones.  Off by default until it has run on hardware (verified on the CPU emulation).
+    `restarts_in_flight=k`: up to k restarts of one device run concurrently (one host thread and one CUDA stream each; the
+    C-ABI calls release the GIL), so the HBM-bound Y pass of one fit overlaps the issue-bound per-cell / gene kernels of
+    another; every fit stays deterministic and the selection below sees them in the serial order."""
     rng = np.random.default_rng(seed)
     jobs = []
     for is_ in initial_shrinks:
@@ -127,7 +130,7 @@ def run_clonealign(gene_expression_data, copy_number_data, initial_shrinks=(0, 5
         for kw in jobs:
             kw["cache"] = cache
     try:
-        return _run_restarts(gene_expression_data, copy_number_data, jobs, devices, print_elbos)
+        return _run_restarts(gene_expression_data, copy_number_data, jobs, devices, print_elbos, int(restarts_in_flight))
     finally:
         if cache is not None:
             for k, v in list(cache.items()):
@@ -135,8 +138,18 @@ def run_clonealign(gene_expression_data, copy_number_data, initial_shrinks=(0, 5
                     v.close()
 
 
-def _run_restarts(gene_expression_data, copy_number_data, jobs, devices, print_elbos):
-    if devices and len(devices) > 1:
+def _run_restarts(gene_expression_data, copy_number_data, jobs, devices, print_elbos, in_flight=1):
+    if in_flight > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        devs = list(dict.fromkeys(kw["device"] for kw in jobs))
+        pools = {d: ThreadPoolExecutor(max_workers=in_flight) for d in devs}       # k host threads per device
+        try:
+            futs = [pools[kw["device"]].submit(clonealign, gene_expression_data, copy_number_data, **kw) for kw in jobs]
+            fits = [f.result() for f in futs]
+        finally:
+            for p in pools.values():
+                p.shutdown(wait=True)
+    elif devices and len(devices) > 1:
         # replicas only: one host thread per GPU, each running its share of the restarts one after another
         # (the C-ABI calls release the GIL); results keep the serial order, so the selection below is unchanged
         from concurrent.futures import ThreadPoolExecutor

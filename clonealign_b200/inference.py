@@ -204,11 +204,13 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
     op_seed = get_next_seed(rng)                                                      # :269
     data = None
     if cache is not None:           # restart-independent device inputs: upload + preprocess once per device
+        import contextlib
         from .session import DeviceData
-        data = cache.get(("data", device))
-        if data is None:
-            data = cache[("data", device)] = DeviceData(Y, L, device=device, clone_allele=clone_allele if use_allele else None,
-                                                        alt=alt, cov=cov if use_allele else None, y_store=y_store)
+        with cache.get("lock") or contextlib.nullcontext():       # concurrent restarts on one device: build once
+            data = cache.get(("data", device))
+            if data is None:
+                data = cache[("data", device)] = DeviceData(Y, L, device=device, clone_allele=clone_allele if use_allele else None,
+                                                            alt=alt, cov=cov if use_allele else None, y_store=y_store)
     sess = Session(Y, L, psi_init, safe_inverse_softplus(mu_guess), mc_samples=int(mc_samples), K=K, x=x,
                    learning_rate=learning_rate, seed=op_seed, device=device,
                    clone_allele=clone_allele if use_allele else None, alt=alt, cov=cov if use_allele else None,

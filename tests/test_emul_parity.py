@@ -546,3 +546,7 @@ def test_shared_device_inputs_for_restarts(example_sce):
         f2 = run_clonealign(Y, L, share_inputs=False, **kw)
     assert f1["multirun_info"]["elbos"].tobytes() == f2["multirun_info"]["elbos"].tobytes()
     assert f1["clone"] == f2["clone"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        f3 = run_clonealign(Y, L, share_inputs=True, restarts_in_flight=3, **kw)       # concurrent restarts on one device
+    assert f3["multirun_info"]["elbos"].tobytes() == f2["multirun_info"]["elbos"].tobytes() and f3["clone"] == f2["clone"]
