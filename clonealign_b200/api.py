@@ -66,7 +66,8 @@ def clonealign(gene_expression_data, copy_number_data, max_iter=200, rel_tol=1e-
     that is already resident in HBM (ca_core_correlations) instead of the host loop; the default stays the host mirror
     until that kernel has been run on hardware (it is verified on the CPU emulation, tests/test_emul_parity.py).
     """
-    Y = np.asarray(gene_expression_data)
+    sparse = hasattr(gene_expression_data, "tocsr") and hasattr(gene_expression_data, "nnz")   # scipy.sparse, cells x genes
+    Y = gene_expression_data.tocsr() if sparse else np.asarray(gene_expression_data)
     if Y.ndim != 2:
         raise ValueError("Input gene_expression_data must be SingleCellExperiment, SummarizedExperiment, or matrix")
     N, G = Y.shape
@@ -96,8 +97,10 @@ def clonealign(gene_expression_data, copy_number_data, max_iter=200, rel_tol=1e-
     fit["clone"] = clone_assignment(res["ml_params"]["clone_probs"], clone_names, clone_call_probability)   # :283
     fit["clone_names"] = clone_names
     ridx = [gene_names.index(g) for g in res["retained_genes"]]
-    fit["correlations"] = dev_cor if dev_cor is not None else \
-        compute_correlations(Y[:, ridx], L[ridx, :], fit["clone"], clone_names)                            # :292-294
+    if dev_cor is None:
+        Yr = Y[:, ridx]
+        dev_cor = compute_correlations(np.asarray(Yr.todense()) if sparse else Yr, L[ridx, :], fit["clone"], clone_names)
+    fit["correlations"] = dev_cor                                                                           # :292-294
     cor = fit["correlations"]
     if np.any(~np.isnan(cor)) and np.nanquantile(cor, 0.25) < 0:                        # :296-300
         warnings.warn("Less than 75% of genes positively correlated with expression - assignment may have failed")

@@ -550,3 +550,22 @@ def test_shared_device_inputs_for_restarts(example_sce):
         warnings.simplefilter("ignore")
         f3 = run_clonealign(Y, L, share_inputs=True, restarts_in_flight=3, **kw)       # concurrent restarts on one device
     assert f3["multirun_info"]["elbos"].tobytes() == f2["multirun_info"]["elbos"].tobytes() and f3["clone"] == f2["clone"]
+
+
+def test_clonealign_accepts_sparse_counts(example_sce):
+    """clonealign() on the sparse counts of a SingleCellExperiment (scipy.sparse here): same fit and correlations as on
+    the dense matrix, with and without the device-side PCA / correlations."""
+    import scipy.sparse as sp
+    from clonealign_b200 import clonealign
+    Y, L = example_sce
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        kw = dict(max_iter=2, verbose=False, seed=1)
+        a = clonealign(sp.csr_matrix(Y), L, device_pca=True, device_correlations=True, **kw)
+        b = clonealign(Y, L, device_pca=True, **kw)
+        c = clonealign(sp.csc_matrix(Y), L, **kw)
+        d = clonealign(Y, L, **kw)
+    assert a["convergence_info"]["elbo"].tobytes() == b["convergence_info"]["elbo"].tobytes() and a["clone"] == b["clone"]
+    np.testing.assert_allclose(a["correlations"], b["correlations"], atol=1e-9, equal_nan=True)
+    assert c["convergence_info"]["elbo"].tobytes() == d["convergence_info"]["elbo"].tobytes()
+    np.testing.assert_allclose(c["correlations"], d["correlations"], atol=0, equal_nan=True)
