@@ -10,7 +10,7 @@ import warnings
 
 import numpy as np
 
-from .inference import clone_assignment, inference_tflow
+from .inference import clone_assignment, inference_steps, inference_tflow
 
 
 class CloneAlignFit(dict):
@@ -51,12 +51,23 @@ def compute_correlations(Y, L, clones, clone_names):
     return out
 
 
-def clonealign(gene_expression_data, copy_number_data, max_iter=200, rel_tol=1e-6, gene_filter_threshold=0,
+def clonealign(*args, **kwargs):
+    """Assign cells to clones (R/clonealign.R:184-305): arguments and return value as `clonealign_steps`, run to completion."""
+    gen = clonealign_steps(*args, **kwargs)
+    try:
+        while True:
+            next(gen)
+    except StopIteration as done:
+        return done.value
+
+
+def clonealign_steps(gene_expression_data, copy_number_data, max_iter=200, rel_tol=1e-6, gene_filter_threshold=0,
                learning_rate=0.1, x=None, clone_allele=None, cov=None, ref=None, fix_alpha=False, dtype="float32",
                saturate=True, saturation_threshold=6, K=None, mc_samples=1, verbose=True, initial_shrink=5,
                clone_call_probability=0.95, data_init_mu=True, clone_names=None, gene_names=None, seed=None,
                device=0, fix_ref_bug=False, device_correlations=False, **backend):
-    """Assign cells to clones (R/clonealign.R:184-305).
+    """Assign cells to clones (R/clonealign.R:184-305), as a generator over the synchronisation points of the fit (see
+    `inference_steps`; `run_clonealign(batch_y_pass=True)` uses them, `clonealign()` ignores them).
 
     gene_expression_data: cell x gene count matrix (an R user passes a SingleCellExperiment whose
     counts assay is transposed to this, :212-222).  copy_number_data: gene x clone matrix.
@@ -85,7 +96,7 @@ def clonealign(gene_expression_data, copy_number_data, max_iter=200, rel_tol=1e-
     if gene_names is None:
         gene_names = [f"gene_{i + 1}" for i in range(G)]
 
-    res = inference_tflow(Y, L, max_iter=max_iter, rel_tol=rel_tol, learning_rate=learning_rate,
+    res = yield from inference_steps(Y, L, max_iter=max_iter, rel_tol=rel_tol, learning_rate=learning_rate,
                           gene_filter_threshold=gene_filter_threshold, x=x, clone_allele=clone_allele, cov=cov,
                           ref=(ref if fix_ref_bug else cov), fix_alpha=fix_alpha, dtype=dtype, saturate_=saturate,
                           saturation_threshold=saturation_threshold, K=K, mc_samples=mc_samples, verbose=verbose,
@@ -108,7 +119,8 @@ def clonealign(gene_expression_data, copy_number_data, max_iter=200, rel_tol=1e-
 
 
 def run_clonealign(gene_expression_data, copy_number_data, initial_shrinks=(0, 5, 10), n_repeats=3,
-                   print_elbos=True, seed=None, devices=None, share_inputs=False, restarts_in_flight=1, **kwargs):
+                   print_elbos=True, seed=None, devices=None, share_inputs=False, restarts_in_flight=1,
+                   batch_y_pass=False, **kwargs):
     """Best-of-restarts wrapper (R/clonealign.R:35-75).  Restarts are independent fits; `devices`
     (list of CUDA ordinals) spreads them round-robin over GPUs (replicas only, no communication).
     `share_inputs=True`: the restarts differ only through the RNG (psi noise, op seed), so the principal components and,
@@ -117,7 +129,9 @@ def run_clonealign(gene_expression_data, copy_number_data, initial_shrinks=(0, 5
     are bit-identical to unshared ones.  Off by default until it has run on hardware (verified on the CPU emulation).
     `restarts_in_flight=k`: up to k restarts of one device run concurrently (one host thread and one CUDA stream each; the
     C-ABI calls release the GIL), so the HBM-bound Y pass of one fit overlaps the issue-bound per-cell / gene kernels of
-    another; every fit stays deterministic and the selection below sees them in the serial order."""
+    another; every fit stays deterministic and the selection below sees them in the serial order.
+    `batch_y_pass=True` (implies share_inputs): the restarts of a device advance in lock-step and ONE pass over the shared
+    count matrix per iteration serves all of them (ca_core_ypass_many) instead of one pass per restart and iteration."""
     rng = np.random.default_rng(seed)
     jobs = []
     for is_ in initial_shrinks:
@@ -127,13 +141,14 @@ def run_clonealign(gene_expression_data, copy_number_data, initial_shrinks=(0, 5
             kw.update(initial_shrink=is_, seed=int(rng.integers(0, 2 ** 31 - 1)), device=dev)   # seeds fixed up front
             jobs.append(kw)
     cache = None
-    if share_inputs:
+    if share_inputs or batch_y_pass:
         import threading
         cache = {"lock": threading.Lock()}
         for kw in jobs:
             kw["cache"] = cache
     try:
-        return _run_restarts(gene_expression_data, copy_number_data, jobs, devices, print_elbos, int(restarts_in_flight))
+        return _run_restarts(gene_expression_data, copy_number_data, jobs, devices, print_elbos, int(restarts_in_flight),
+                             bool(batch_y_pass))
     finally:
         if cache is not None:
             for k, v in list(cache.items()):
@@ -141,8 +156,38 @@ def run_clonealign(gene_expression_data, copy_number_data, initial_shrinks=(0, 5
                     v.close()
 
 
-def _run_restarts(gene_expression_data, copy_number_data, jobs, devices, print_elbos, in_flight=1):
-    if in_flight > 1:
+def _lockstep(gens):
+    """Advance several fits through their synchronisation points together; one batched Y pass per round."""
+    from .session import ypass_many
+    results, live = [None] * len(gens), dict(enumerate(gens))
+    while live:
+        waiting = {}
+        for i, g in list(live.items()):
+            try:
+                waiting[i] = next(g)
+            except StopIteration as done:
+                results[i] = done.value
+                del live[i]
+        if len(waiting) > 1:
+            ypass_many(list(waiting.values()))
+    return results
+
+
+def _run_restarts(gene_expression_data, copy_number_data, jobs, devices, print_elbos, in_flight=1, batch_y_pass=False):
+    if batch_y_pass:
+        from concurrent.futures import ThreadPoolExecutor
+        devs = list(dict.fromkeys(kw["device"] for kw in jobs))
+
+        def run_on(dev):
+            idx = [i for i, kw in enumerate(jobs) if kw["device"] == dev]
+            return idx, _lockstep([clonealign_steps(gene_expression_data, copy_number_data, **jobs[i]) for i in idx])
+
+        fits = [None] * len(jobs)
+        with ThreadPoolExecutor(max_workers=len(devs)) as pool:
+            for idx, res in pool.map(run_on, devs):
+                for i, r in zip(idx, res):
+                    fits[i] = r
+    elif in_flight > 1:
         from concurrent.futures import ThreadPoolExecutor
         devs = list(dict.fromkeys(kw["device"] for kw in jobs))
         pools = {d: ThreadPoolExecutor(max_workers=in_flight) for d in devs}       # k host threads per device

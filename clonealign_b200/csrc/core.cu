@@ -1631,6 +1631,56 @@ int ca_core_p2p_connect(ca_handle* h, const void* handles, char* err, size_t err
   } catch (const std::exception& e) { return report(e, err, errlen); }
 }
 
+int ca_core_ypass_many(ca_handle* const* hs, int32_t n, char* err, size_t errlen) {
+  try {
+    if (!hs || n < 1) fail("bad argument");
+    ca_handle* h0 = hs[0];
+    if (!h0) fail("null handle");
+    for (int i = 0; i < n; ++i) {
+      ca_handle* h = hs[i];
+      if (!h) fail("null handle");
+      if (h->KP != 1) fail("ca_core_ypass_many needs K + P == 1");
+      if (h->Y != h0->Y || h->dev != h0->dev || h->N != h0->N || h->G != h0->G || h->ystore != h0->ystore)
+        fail("ca_core_ypass_many: the sessions do not share one count matrix (create them with ca_core_create_shared)");
+    }
+    CUDA_OK(cudaSetDevice(h0->dev));
+    for (int g0 = 0; g0 < n; g0 += kYMultiMax) {
+      const int R = std::min(kYMultiMax, n - g0);
+      ca_handle* lead = hs[g0];
+      if (R == 1) {            // a lone fit: its own pass
+        lead->ydirty = true;
+        run_ypass(lead, lead->stream);
+        continue;
+      }
+      // the pass runs on the first session's stream: it must see the parameter updates of the others, and their next
+      // kernels must see its partial sums
+      for (int r = 1; r < R; ++r) {
+        CUDA_OK(cudaEventRecord(hs[g0 + r]->ev_fork, hs[g0 + r]->stream));
+        CUDA_OK(cudaStreamWaitEvent(lead->stream, hs[g0 + r]->ev_fork, 0));
+      }
+      YMultiArgs a;
+      for (int r = 0; r < kYMultiMax; ++r) {
+        ca_handle* h = hs[g0 + (r < R ? r : 0)];
+        a.U[r] = h->U; a.Vm[r] = h->Vm; a.rowpart[r] = h->rowpart; a.colpart[r] = h->colpart;
+      }
+      dispatch_y(lead, [&](auto* Yp) {
+        using T = typename std::remove_const<typename std::remove_pointer<decltype(Yp)>::type>::type;
+        dim3 grid(lead->nCB, lead->nRB);
+        if (R == 2) { auto k = k_ypass_k1_multi<T, 2>; CA_LAUNCH(k, grid, 256, 0, lead->stream)(Yp, lead->ldY, lead->N, lead->G, lead->RB, a); }
+        else if (R == 3) { auto k = k_ypass_k1_multi<T, 3>; CA_LAUNCH(k, grid, 256, 0, lead->stream)(Yp, lead->ldY, lead->N, lead->G, lead->RB, a); }
+        else { auto k = k_ypass_k1_multi<T, 4>; CA_LAUNCH(k, grid, 256, 0, lead->stream)(Yp, lead->ldY, lead->N, lead->G, lead->RB, a); }
+        KCHECK();
+      });
+      CUDA_OK(cudaEventRecord(lead->ev_join, lead->stream));
+      for (int r = 0; r < R; ++r) {
+        if (r > 0) CUDA_OK(cudaStreamWaitEvent(hs[g0 + r]->stream, lead->ev_join, 0));
+        hs[g0 + r]->ydirty = false;
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
 int ca_core_describe(ca_handle* h, char* json, size_t json_len) {
   if (!h || !json || !json_len) return 1;
   const char* st = h->ystore == CA_STORE_F32 ? "f32" : (h->ystore == CA_STORE_U16 ? "u16" : "u8");

@@ -297,6 +297,95 @@ k_ypass_k1_v2(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, co
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Batched Y pass for R fits that share one count matrix (restarts of run_clonealign on one device):
+// ONE stream over Y produces (Y W_r, Y^T psi_r) for every fit r -- the widening / magic-number work is shared and the
+// matrix leaves HBM once instead of R times.  Same tiling and partial layouts as k_ypass_k1_v2 (each fit's own rowpart /
+// colpart buffers, summed in the same fixed order by its consumers), 8 rows per iteration to keep R x 8 row partials
+// and R x 8 column accumulators in registers.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kYMultiMax = 4;
+struct YMultiArgs {
+  const float* U[kYMultiMax];
+  const float* Vm[kYMultiMax];
+  float* rowpart[kYMultiMax];
+  float* colpart[kYMultiMax];
+};
+
+template <typename T, int R>
+__global__ void __launch_bounds__(256, 1)
+k_ypass_k1_multi(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, YMultiArgs a) {
+  using L = YLoad<T>;
+  constexpr int kRows = 8;
+  __shared__ float red[2][8][R * kRows];
+  const int cb = blockIdx.x;
+  const int64_t rb = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t col0 = (int64_t)cb * kYCB + tid * 8;
+  const bool colok = col0 < ldY;
+  float2 vr[R][4], cacc[R][4];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      vr[r][j] = make_float2((col0 + 2 * j < G) ? a.Vm[r][col0 + 2 * j] : 0.f, (col0 + 2 * j + 1 < G) ? a.Vm[r][col0 + 2 * j + 1] : 0.f);
+      cacc[r][j] = make_float2(0.f, 0.f);
+    }
+  const int64_t rbeg = rb * RB, rend = (rbeg + RB < N) ? rbeg + RB : N;
+  const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const T* yp = Y + rbeg * ldY + col0;
+  int buf = 0;
+  for (int64_t r0 = rbeg; r0 < rend; r0 += kRows, yp += (int64_t)kRows * ldY) {
+    typename L::Raw raw[kRows];
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) raw[i] = (colok && r0 + i < rend) ? L::ld(yp + (int64_t)i * ldY) : L::zero();
+    float rp[R][kRows];
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+      float2 y[4];
+      YLoad2<T>::unpack(raw[i], y);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float u = __ldg(a.U[r] + r0 + i);     // U has 64 elements of slack: in bounds for the masked tail rows too
+        const float2 u2 = make_float2(u, u);
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc = __ffma2_rn(y[j], vr[r][j], acc);
+          cacc[r][j] = __ffma2_rn(y[j], u2, cacc[r][j]);
+        }
+        rp[r][i] = acc.x + acc.y;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float v8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v8[i] = rp[r][i];
+      const float tot = butterfly8(v8, lane);
+      if ((lane & 3) == 0) red[buf][wid][r * kRows + ridx] = tot;
+    }
+    __syncthreads();
+    if (tid < R * kRows) {
+      const int r = tid / kRows, i = tid % kRows;
+      if (r0 + i < rend) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) acc += red[buf][w][tid];
+        a.rowpart[r][(int64_t)cb * N + r0 + i] = acc;
+      }
+    }
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (col0 + 2 * j < G) a.colpart[r][rb * G + col0 + 2 * j] = cacc[r][j].x;
+      if (col0 + 2 * j + 1 < G) a.colpart[r][rb * G + col0 + 2 * j + 1] = cacc[r][j].y;
+    }
+}
+
 // generic K + P (slow path, reads Y twice): rows then columns
 template <typename T>
 __global__ void k_ypass_rows_generic(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int KP,

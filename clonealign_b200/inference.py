@@ -90,12 +90,27 @@ def pca_scaled(Y, K, truncated=None):
     return (pcs - pcs.mean(axis=0)) / pcs.std(axis=0, ddof=1)
 
 
-def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1, gene_filter_threshold=0,
+def inference_tflow(*args, **kwargs):
+    """CUDA-backed equivalent of the reference's `inference_tflow` (R/inference-tflow.R:71-481); arguments and return
+    value: see `inference_steps`, which this function simply runs to completion."""
+    gen = inference_steps(*args, **kwargs)
+    try:
+        while True:
+            next(gen)
+    except StopIteration as done:
+        return done.value
+
+
+def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1, gene_filter_threshold=0,
                     x=None, clone_allele=None, cov=None, ref=None, fix_alpha=False, dtype="float32",
                     saturate_=True, saturation_threshold=6, K=1, mc_samples=1, verbose=True, initial_shrink=5,
                     data_init_mu=True, seed=None, device=0, psi_init=None, y_store="auto", path="auto",
                     gene_names=None, variants=None, correlations_with=None, device_pca=False, cache=None):
-    """CUDA-backed equivalent of the reference's `inference_tflow`.
+    """The fit of `inference_tflow` as a generator: it yields its `Session` every time the parameters have just changed
+    and the next operation is an ELBO evaluation (after gamma-init and after every train step), i.e. exactly where one
+    batched pass over a shared count matrix can serve several restarts (`session.ypass_many`; `run_clonealign(
+    batch_y_pass=True)` advances the restarts of a device in lock-step through these points).  Ignoring the yields gives
+    the plain fit.  The generator's return value is the reference's result list:
 
     Y_dat: cell x gene counts; L_dat: gene x clone copy number.  Returns the reference's list as a dict:
     ml_params {mu, clone_probs, s, alpha [, beta] [, psi, W, chi]}, convergence_info {final_elbo,
@@ -226,6 +241,7 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
                     cache["pcs_device"] = pcs
             sess.set_array("psi", pcs[:, None] + pca_noise)
         sess.init_gamma()                                                             # :368-369
+        yield sess
         elbo_val = sess.elbo()                                                        # :372
         if np.isnan(elbo_val):
             raise ValueError("Initial elbo is NA")                                    # :374-376
@@ -234,6 +250,7 @@ def inference_tflow(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
         _message(verbose, "Optimizing ELBO")
         for _ in range(int(max_iter)):                                                # :394
             sess.step()                                                               # :401
+            yield sess
             elbo_new = sess.elbo()                                                    # :403
             elbo_diff = (elbo_new - elbo_val) / abs(elbo_val)
             elbo_diffs = elbo_diffs[1:] + [elbo_diff]

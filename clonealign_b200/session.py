@@ -173,6 +173,17 @@ class DeviceData:
             pass
 
 
+def ypass_many(sessions):
+    """One pass over the shared count matrix for several sessions built on the same `DeviceData` (ca_core_ypass_many)."""
+    sessions = list(sessions)
+    if not sessions:
+        return
+    lib = sessions[0]._lib
+    arr = (C.c_void_p * len(sessions))(*[s._h for s in sessions])
+    err = C.create_string_buffer(1024)
+    _lib.check(lib.ca_core_ypass_many(arr, len(sessions), err, len(err)), err)
+
+
 class Session:
     """One cell shard of one fit on one GPU."""
 

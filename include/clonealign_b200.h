@@ -127,6 +127,13 @@ CA_API int ca_core_data_destroy(ca_data* d, char* err, size_t errlen);
 CA_API int ca_core_create_shared(ca_handle** out, const ca_config* cfg, ca_data* data, const double* psi_init,
                           const double* loc_init, const double* X, char* err, size_t errlen);
 
+/* One pass over the shared count matrix for `n` sessions created from the same ca_data (K + P == 1): computes every
+ * session's Y W and Y^T psi partial sums together (kernels_ypass.cuh, k_ypass_k1_multi), so that their next
+ * ca_core_step / ca_core_elbo calls skip their own pass.  Call it when all of them have new parameters (after their
+ * ca_core_step calls, before their ca_core_elbo calls): the restarts of run_clonealign then read Y once per iteration
+ * instead of once per restart and iteration.  Stream-ordered with respect to every session in `hs`. */
+CA_API int ca_core_ypass_many(ca_handle* const* hs, int32_t n, char* err, size_t errlen);
+
 /* the session operations */
 CA_API int ca_core_init_gamma(ca_handle* h, char* err, size_t errlen);
 CA_API int ca_core_step(ca_handle* h, char* err, size_t errlen);

@@ -550,6 +550,13 @@ def test_shared_device_inputs_for_restarts(example_sce):
         warnings.simplefilter("ignore")
         f3 = run_clonealign(Y, L, share_inputs=True, restarts_in_flight=3, **kw)       # concurrent restarts on one device
     assert f3["multirun_info"]["elbos"].tobytes() == f2["multirun_info"]["elbos"].tobytes() and f3["clone"] == f2["clone"]
+    # lock-step restarts with one batched Y pass per iteration: same fits when every restart uses the packed Y pass
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        kv = dict(kw, path="interp", variants="ypass2,epi2,lean", max_iter=12, rel_tol=1e-3)      # fits stop at different iterations
+        f4 = run_clonealign(Y, L, batch_y_pass=True, **kv)
+        f5 = run_clonealign(Y, L, **kv)
+    assert f4["multirun_info"]["elbos"].tobytes() == f5["multirun_info"]["elbos"].tobytes() and f4["clone"] == f5["clone"]
 
 
 def test_clonealign_accepts_sparse_counts(example_sce):
@@ -569,3 +576,44 @@ def test_clonealign_accepts_sparse_counts(example_sce):
     np.testing.assert_allclose(a["correlations"], b["correlations"], atol=1e-9, equal_nan=True)
     assert c["convergence_info"]["elbo"].tobytes() == d["convergence_info"]["elbo"].tobytes()
     np.testing.assert_allclose(c["correlations"], d["correlations"], atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize("n_fits", [2, 3, 5])
+def test_batched_y_pass_for_restarts(example_sce, n_fits):
+    """ca_core_ypass_many: one stream over the shared count matrix yields every fit's (Y W, Y^T psi) partials; fits
+    stepped in lock-step with it are bit-identical to fits that each run their own (packed) Y pass."""
+    from clonealign_b200.session import DeviceData, Session, ypass_many
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
+    loc = O.safe_inverse_softplus(hi["mu_guess"])
+    rng = np.random.default_rng(3)
+    psis = [hi["psi_init"] + rng.normal(0, 0.05, size=hi["psi_init"].shape) for _ in range(n_fits)]
+    kw = dict(mc_samples=2, K=1, path="interp", variants="ypass2,epi2,lean")
+
+    def solo(i):
+        with Session(hi["Y"], hi["L"], psis[i], loc, seed=10 + i, **kw) as s:
+            s.init_gamma()
+            tr = [s.elbo()]
+            for _ in range(3):
+                s.step()
+                tr.append(s.elbo())
+            return np.array(tr), s.params()["psi"]
+    want = [solo(i) for i in range(n_fits)]
+    with DeviceData(hi["Y"], hi["L"]) as data:
+        ss = [Session(None, None, psis[i], loc, seed=10 + i, data=data, **kw) for i in range(n_fits)]
+        for s in ss:
+            s.init_gamma()
+        ypass_many(ss)
+        trs = [[s.elbo()] for s in ss]
+        for _ in range(3):
+            for s in ss:
+                s.step()                     # uses the partial sums of the batched pass, then changes the parameters
+            ypass_many(ss)                   # one read of Y for all fits
+            for s, tr in zip(ss, trs):
+                tr.append(s.elbo())
+        got = [(np.array(tr), s.params()["psi"]) for s, tr in zip(ss, trs)]
+        assert all(s.describe()["launches_last_step"] > 0 for s in ss)
+        for s in ss:
+            s.close()
+    for (a, pa), (b, pb) in zip(want, got):
+        assert a.tobytes() == b.tobytes() and pa.tobytes() == pb.tobytes()

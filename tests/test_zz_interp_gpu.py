@@ -233,3 +233,9 @@ def test_shared_device_inputs_for_restarts(example_sce):
         f2 = run_clonealign(Y, L, share_inputs=False, **kw)
     assert f1["multirun_info"]["elbos"].tobytes() == f2["multirun_info"]["elbos"].tobytes()
     assert f1["clone"] == f2["clone"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        kv = dict(kw, path="interp", variants="ypass2,epi2,lean", max_iter=12, rel_tol=1e-3)
+        f4 = run_clonealign(Y, L, batch_y_pass=True, **kv)      # lock-step restarts, one batched Y pass per iteration
+        f5 = run_clonealign(Y, L, **kv)
+    assert f4["multirun_info"]["elbos"].tobytes() == f5["multirun_info"]["elbos"].tobytes() and f4["clone"] == f5["clone"]
