@@ -350,3 +350,20 @@ def test_r_shim_compiles_against_stub_headers():
         name, fn, n = m.group(1), m.group(2), int(m.group(3))
         sig = re.search(r"SEXP %s\(([^)]*)\)" % fn, text).group(1)
         assert name == fn and sig.count("SEXP") == n, (name, n, sig)
+
+
+def test_product_has_no_emulation_or_cpu_path(lib):
+    """The CPU emulation (tests/cuda_emul/) is test infrastructure: the product package never mentions it, the product
+    build never defines CA_EMULATE, and the shipped library contains none of its symbols and links the CUDA runtime."""
+    pkg = os.path.join(ROOT, "clonealign_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "cuda_emul" not in src and "CA_EMULATE" not in src and "oracle" not in src.replace("the oracle", ""), fn
+    mk = open(os.path.join(pkg, "csrc", "Makefile")).read()
+    assert "CA_EMULATE" not in mk and "cuda_emul" not in mk
+    so = os.path.join(pkg, "libclonealign_b200.so")
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", so], text=True)
+    assert "ca_emul" not in syms
+    allsyms = subprocess.check_output(["nm", "-C", so], text=True)
+    assert "ca_emul" not in allsyms and "cudaLaunchKernel" in allsyms       # real launches, no fiber launcher
