@@ -369,7 +369,7 @@ void run_ypass(ca_handle* h, cudaStream_t st) {
     if (h->KP == 1) {
       LaunchScope ls(h, "ypass");
       dim3 grid(h->nCB, h->nRB);
-      if (st == h->stream && (h->variants & CA_VAR_YPASS2)) {
+      if (h->variants & CA_VAR_YPASS2) {
         CA_LAUNCH(k_ypass_k1_v2<T>, grid, 256, 0, st)(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
       } else if (st == h->stream && !getenv("CLONEALIGN_B200_YPASS_LIGHT")) {
         CA_LAUNCH(k_ypass_k1<T>, grid, 256, 0, st)(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
@@ -851,7 +851,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   // Measured on B200 (profiles/r01_notes.md): co-scheduling the Y stream with the forward contraction does not pay
   // yet (the register-light Y kernel is slower than the saved time), so the fork is opt-in.
-  h->overlap = getenv("CLONEALIGN_B200_OVERLAP") != nullptr;
+  h->overlap = getenv("CLONEALIGN_B200_OVERLAP") != nullptr || (c.variants & CA_VAR_OVERLAP);
 
   h->N = c.N; h->Ntot = c.N_total > 0 ? c.N_total : c.N; h->G = c.G; h->C = c.C; h->S = c.S; h->K = c.K; h->P = c.P;
   h->KP = c.K + c.P; h->SC = c.S * c.C; h->V = c.V;
@@ -860,7 +860,8 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if (c.path == CA_PATH_INTERP && !(c.K == 1 && c.P == 0)) fail("interp path needs K == 1 and P == 0");
   h->interp = (c.path == CA_PATH_INTERP);
   h->variants = c.variants;
-  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_P2P)) fail("unknown kernel variant bits 0x%x", c.variants);
+  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_P2P | CA_VAR_OVERLAP))
+    fail("unknown kernel variant bits 0x%x", c.variants);
   if ((c.variants & CA_VAR_P2P) && c.world > kP2PMaxWorld) fail("variant p2p supports at most %d ranks", kP2PMaxWorld);
   h->p2p = (c.variants & CA_VAR_P2P) && c.world > 1;
   if ((c.variants & CA_VAR_LEAN) && !(c.variants & CA_VAR_EPI2)) fail("variant lean needs variant epi2");

@@ -15,7 +15,8 @@ from test_gpu_parity import ELBO_RTOL, PARAM_RTOL, _case, _check_grads, _load_pa
 pytestmark = pytest.mark.usefixtures("emulated_library")
 # (contraction path, kernel variants): the default kernels of both non-tensor paths and the re-engineered variants
 # (packed-fp32 Y pass, fused Clenshaw + per-cell epilogue) that bench.py validates on the device before using them
-PATHS = [("cudacore", ""), ("interp", ""), ("cudacore", "ypass2"), ("interp", "ypass2,epi2"), ("interp", "ypass2,epi2,lean")]
+PATHS = [("cudacore", ""), ("interp", ""), ("cudacore", "ypass2"), ("interp", "ypass2,epi2"), ("interp", "ypass2,epi2,lean"),
+         ("interp", "ypass2,epi2,lean,overlap")]
 
 
 def test_emulated_library_is_not_the_product(emulated_library):

@@ -16,7 +16,7 @@ from test_gpu_parity import ELBO_RTOL, PARAM_RTOL, _case, _check_grads, _load_pa
 pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="interp path not yet validated on hardware")]
 
 
-VARIANTS = ["", "ypass2", "epi2", "ypass2,epi2", "ypass2,epi2,lean"]
+VARIANTS = ["", "ypass2", "epi2", "ypass2,epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap"]
 
 
 @pytest.mark.parametrize("variants", VARIANTS)
