@@ -137,6 +137,78 @@ SEXP ca_correlations(SEXP ptr, SEXP clone_idx, SEXP L, SEXP n_genes) {
   return out;   /* NaN where cor() gives NA */
 }
 
+/* ---- restarts of run_clonealign (R/clonealign.R:50-56) on shared device inputs ------------------------------------
+ * ca_data_create(Y, L, clone_allele, alt, cov, device): upload + preprocess once; ca_create_shared(data, psi_init,
+ * loc_init, X, S, K, lr, seed, dims = c(N, G, C, V)): one session per restart; ca_ypass_many(list of sessions): one pass
+ * over the shared count matrix for all of them (call between their ca_step and ca_elbo calls). */
+static void ca_data_finalizer(SEXP ptr) {
+  ca_data* d = (ca_data*)R_ExternalPtrAddr(ptr);
+  if (d) {
+    char err[ERRLEN] = {0};
+    if (ca_core_data_destroy(d, err, ERRLEN) == 0) R_ClearExternalPtr(ptr);   /* else: sessions still alive, retried later */
+  }
+}
+
+SEXP ca_data_create(SEXP Y, SEXP L, SEXP clone_allele, SEXP alt, SEXP cov, SEXP device) {
+  char err[ERRLEN] = {0};
+  SEXP dim = Rf_getAttrib(Y, R_DimSymbol);
+  ca_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.N = INTEGER(dim)[0];
+  cfg.N_total = cfg.N;
+  cfg.G = INTEGER(dim)[1];
+  cfg.C = Rf_ncols(L);
+  cfg.S = 1;
+  cfg.V = Rf_isNull(clone_allele) ? 0 : Rf_nrows(clone_allele);
+  cfg.device = Rf_asInteger(device);
+  cfg.world = 1;
+  cfg.y_dtype = (TYPEOF(Y) == INTSXP) ? CA_Y_I32 : CA_Y_F64;
+  cfg.y_layout = CA_Y_COLMAJOR;
+  cfg.y_mem = CA_Y_HOST;
+  cfg.y_store = CA_STORE_AUTO;
+  const void* yptr = (TYPEOF(Y) == INTSXP) ? (const void*)INTEGER(Y) : (const void*)REAL(Y);
+  ca_data* d = NULL;
+  if (ca_core_data_create(&d, &cfg, yptr, REAL(L), NULL, real_or_null(clone_allele), real_or_null(alt), real_or_null(cov), err,
+                          ERRLEN))
+    Rf_error("%s", err);
+  SEXP ptr = PROTECT(R_MakeExternalPtr(d, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, ca_data_finalizer, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+
+SEXP ca_create_shared(SEXP data, SEXP psi_init, SEXP loc_init, SEXP X, SEXP S, SEXP K, SEXP lr, SEXP seed, SEXP dims) {
+  char err[ERRLEN] = {0};
+  ca_data* d = (ca_data*)R_ExternalPtrAddr(data);
+  if (!d) Rf_error("clonealign CUDA inputs are closed");
+  int* dm = INTEGER(dims);   /* c(N, G, C, V, device) */
+  ca_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.N = dm[0]; cfg.N_total = dm[0]; cfg.G = dm[1]; cfg.C = dm[2]; cfg.V = dm[3]; cfg.device = dm[4];
+  cfg.S = Rf_asInteger(S);
+  cfg.K = Rf_asInteger(K);
+  cfg.P = Rf_isNull(X) ? 0 : Rf_ncols(X);
+  cfg.learning_rate = Rf_asReal(lr);
+  cfg.seed = (uint64_t)Rf_asInteger(seed);
+  cfg.world = 1;
+  cfg.path = CA_PATH_AUTO;
+  ca_handle* h = NULL;
+  if (ca_core_create_shared(&h, &cfg, d, real_or_null(psi_init), REAL(loc_init), real_or_null(X), err, ERRLEN)) Rf_error("%s", err);
+  SEXP ptr = PROTECT(R_MakeExternalPtr(h, data, R_NilValue));   /* tag = the inputs: kept alive as long as the session */
+  R_RegisterCFinalizerEx(ptr, ca_finalizer, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+
+SEXP ca_ypass_many(SEXP sessions) {   /* list of session external pointers */
+  char err[ERRLEN] = {0};
+  R_xlen_t n = XLENGTH(sessions);
+  ca_handle** hs = (ca_handle**)R_alloc((size_t)n, sizeof(ca_handle*));
+  for (R_xlen_t i = 0; i < n; ++i) hs[i] = get_handle(VECTOR_ELT(sessions, i));
+  if (ca_core_ypass_many(hs, (int32_t)n, err, ERRLEN)) Rf_error("%s", err);
+  return R_NilValue;
+}
+
 SEXP ca_init_gamma(SEXP ptr) {
   char err[ERRLEN] = {0};
   if (ca_core_init_gamma(get_handle(ptr), err, ERRLEN)) Rf_error("%s", err);
@@ -204,7 +276,8 @@ static const R_CallMethodDef call_methods[] = {
     {"ca_params", (DL_FUNC)&ca_params, 2},  {"ca_set_eps", (DL_FUNC)&ca_set_eps, 3},
     {"ca_destroy", (DL_FUNC)&ca_destroy, 1}, {"ca_create_sparse", (DL_FUNC)&ca_create_sparse, 16},
     {"ca_pca_scores", (DL_FUNC)&ca_pca_scores, 4}, {"ca_set_psi", (DL_FUNC)&ca_set_psi, 2},
-    {"ca_correlations", (DL_FUNC)&ca_correlations, 4}, {NULL, NULL, 0}};
+    {"ca_correlations", (DL_FUNC)&ca_correlations, 4}, {"ca_data_create", (DL_FUNC)&ca_data_create, 6},
+    {"ca_create_shared", (DL_FUNC)&ca_create_shared, 9}, {"ca_ypass_many", (DL_FUNC)&ca_ypass_many, 1}, {NULL, NULL, 0}};
 
 void R_init_clonealign(DllInfo* dll) {
   R_registerRoutines(dll, NULL, call_methods, NULL, NULL);

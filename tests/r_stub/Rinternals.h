@@ -31,6 +31,7 @@ SEXP Rf_mkNamed(unsigned int, const char**);
 SEXP Rf_ScalarReal(double);
 SEXP Rf_ScalarInteger(int);
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
+SEXP VECTOR_ELT(SEXP, R_xlen_t);
 SEXP Rf_protect(SEXP);
 void Rf_unprotect(int);
 #define PROTECT(s) Rf_protect(s)
