@@ -1481,16 +1481,17 @@ int ca_core_correlations(ca_handle* h, const int32_t* clone_idx, const double* L
     if ((size_t)C * 128 * sizeof(float) > 48 * 1024) fail("too many clones for the correlation kernel");
     int* d_z = nullptr;
     float* d_L = nullptr;
-    double *d_part = nullptr, *d_out = nullptr;
+    double *d_part = nullptr, *d_out = nullptr, *d_sums = nullptr;
     struct Guard {   // scratch is released on every exit path
-      int*& z; float*& l; double*& p; double*& o;
-      ~Guard() { cudaFree(z); cudaFree(l); cudaFree(p); cudaFree(o); }
-    } guard{d_z, d_L, d_part, d_out};
+      int*& z; float*& l; double*& p; double*& o; double*& s;
+      ~Guard() { cudaFree(z); cudaFree(l); cudaFree(p); cudaFree(o); cudaFree(s); }
+    } guard{d_z, d_L, d_part, d_out, d_sums};
     const int RS = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 64));
     CUDA_OK(cudaMalloc(&d_z, sizeof(int) * N));
     CUDA_OK(cudaMalloc(&d_L, sizeof(float) * (size_t)G * C));
     CUDA_OK(cudaMalloc(&d_part, sizeof(double) * (size_t)RS * G * 5));
     CUDA_OK(cudaMalloc(&d_out, sizeof(double) * G));
+    CUDA_OK(cudaMalloc(&d_sums, sizeof(double) * ((size_t)5 * G + 1)));
     int64_t n_assigned = 0;
     for (int64_t n = 0; n < N; ++n) n_assigned += (clone_idx[n] >= 0 && clone_idx[n] < C) ? 1 : 0;
     CUDA_OK(cudaMemcpyAsync(d_z, clone_idx, sizeof(int) * N, cudaMemcpyHostToDevice, h->stream));
@@ -1502,7 +1503,14 @@ int ca_core_correlations(ca_handle* h, const int32_t* clone_idx, const double* L
       CA_LAUNCH(k_corr_part<T>, grid, 128, sizeof(float) * C * 128, h->stream)(Yp, h->ldY, N, G, C, d_z, d_L, RS, d_part);
       KCHECK();
     });
-    CA_LAUNCH(k_corr_final, (G + 127) / 128, 128, 0, h->stream)(d_part, RS, G, (double)n_assigned, d_out);
+    CA_LAUNCH(k_corr_reduce, (G + 127) / 128, 128, 0, h->stream)(d_part, RS, G, d_sums);
+    KCHECK();
+    const double na = (double)n_assigned;
+    CUDA_OK(cudaMemcpyAsync(d_sums + (size_t)5 * G, &na, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));   // `na` lives on this stack frame
+    if (h->cfg.world > 1)   // collective: the sums over cells run over every shard
+      NCCL_OK(nccl().AllReduce(d_sums, d_sums, (size_t)5 * G + 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
+    CA_LAUNCH(k_corr_final, (G + 127) / 128, 128, 0, h->stream)(d_sums, G, d_out);
     KCHECK();
     CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(double) * G, cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -1513,11 +1521,11 @@ int ca_core_correlations(ca_handle* h, const int32_t* clone_idx, const double* L
 int ca_core_pca_scores(ca_handle* h, int32_t max_iter, double tol, double* scores, int32_t* iters_out, char* err, size_t errlen) {
   try {
     if (!h || !scores || max_iter < 1) fail("bad argument");
-    if (h->cfg.world != 1) fail("ca_core_pca_scores: cell-sharded sessions are not supported yet (needs the global column statistics)");
+    const bool sharded = h->cfg.world > 1;   // collective call: column statistics and X^T t are summed over the cell shards
     CUDA_OK(cudaSetDevice(h->dev));
     const int64_t N = h->N;
     const int G = h->G;
-    if (N < 2) fail("need at least two cells");
+    if (h->Ntot < 2) fail("need at least two cells");
     const int RS = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 64));
     std::vector<void*> tmp;
     auto dalloc = [&](size_t n) {
@@ -1527,7 +1535,7 @@ int ca_core_pca_scores(ca_handle* h, int32_t max_iter, double tol, double* score
       return (double*)p;
     };
     double *part = dalloc((size_t)RS * G * 2), *mean = dalloc(G), *inv_sd = dalloc(G), *v = dalloc(G), *w = dalloc(G), *a = dalloc(G),
-           *b = dalloc(1), *t = dalloc(N), *tsum = dalloc(RS), *out2 = dalloc(2);
+           *b = dalloc(1), *t = dalloc(N), *tsum = dalloc(RS), *out2 = dalloc(2), *sums = dalloc((size_t)2 * G + 2);
     int* bad = (int*)dalloc(1);
     CUDA_OK(cudaMemsetAsync(bad, 0, sizeof(int), h->stream));
     int status = 0;
@@ -1538,7 +1546,10 @@ int ca_core_pca_scores(ca_handle* h, int32_t max_iter, double tol, double* score
         dim3 gridc((G + 127) / 128, RS);
         CA_LAUNCH(k_pca_colstats<T>, gridc, 128, 0, h->stream)(Yp, h->ldY, N, G, RS, part);
         KCHECK();
-        CA_LAUNCH(k_pca_colstats_final, (G + 127) / 128, 128, 0, h->stream)(part, RS, G, (double)N, mean, inv_sd, bad);
+        CA_LAUNCH(k_pca_colstats_reduce, (G + 127) / 128, 128, 0, h->stream)(part, RS, G, sums);
+        KCHECK();
+        if (sharded) NCCL_OK(nccl().AllReduce(sums, sums, (size_t)2 * G, kNcclFloat64, kNcclSum, h->comm, h->stream));
+        CA_LAUNCH(k_pca_colstats_final, (G + 127) / 128, 128, 0, h->stream)(sums, G, (double)h->Ntot, mean, inv_sd, bad);
         KCHECK();
         int hbad = 0;
         CUDA_OK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -1559,7 +1570,10 @@ int ca_core_pca_scores(ca_handle* h, int32_t max_iter, double tol, double* score
           KCHECK();
           CA_LAUNCH(k_pca_cols<T>, gridc, 128, 0, h->stream)(Yp, h->ldY, N, G, RS, t, part, tsum);
           KCHECK();
-          CA_LAUNCH(k_pca_update, 1, 1024, 0, h->stream)(part, tsum, RS, G, mean, inv_sd, v, w, out2);
+          CA_LAUNCH(k_pca_cols_reduce, (G + 1 + 127) / 128, 128, 0, h->stream)(part, tsum, RS, G, sums);
+          KCHECK();
+          if (sharded) NCCL_OK(nccl().AllReduce(sums, sums, (size_t)G + 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
+          CA_LAUNCH(k_pca_update, 1, 1024, 0, h->stream)(sums, G, mean, inv_sd, v, w, out2);
           KCHECK();
           double o2[2];
           CUDA_OK(cudaMemcpyAsync(o2, out2, sizeof o2, cudaMemcpyDeviceToHost, h->stream));

@@ -29,9 +29,8 @@ k_pca_colstats(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RS, d
   part[((int64_t)blockIdx.y * G + g) * 2] = s1;
   part[((int64_t)blockIdx.y * G + g) * 2 + 1] = s2;
 }
-// mean, 1 / sd; *bad is set when a column is constant ("cannot rescale a constant/zero column to unit variance")
-__global__ void k_pca_colstats_final(const double* __restrict__ part, int RS, int G, double n, double* __restrict__ mean,
-                                     double* __restrict__ inv_sd, int* __restrict__ bad) {
+// sums[g] = (sum l, sum l^2) over this rank's row slices (all-reduced over the ranks of a cell-sharded fit by the host code)
+__global__ void k_pca_colstats_reduce(const double* __restrict__ part, int RS, int G, double* __restrict__ sums) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   double s1 = 0.0, s2 = 0.0;
@@ -39,6 +38,16 @@ __global__ void k_pca_colstats_final(const double* __restrict__ part, int RS, in
     s1 += part[((int64_t)r * G + g) * 2];
     s2 += part[((int64_t)r * G + g) * 2 + 1];
   }
+  sums[2 * g] = s1;
+  sums[2 * g + 1] = s2;
+}
+// mean, 1 / sd from the global sums; *bad is set when a column is constant ("cannot rescale a constant/zero column to
+// unit variance")
+__global__ void k_pca_colstats_final(const double* __restrict__ sums, int G, double n, double* __restrict__ mean,
+                                     double* __restrict__ inv_sd, int* __restrict__ bad) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const double s1 = sums[2 * g], s2 = sums[2 * g + 1];
   const double m = s1 / n;
   const double var = (s2 - n * m * m) / (n - 1.0);
   mean[g] = m;
@@ -99,19 +108,29 @@ k_pca_cols(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RS, const
   }
   part[(int64_t)blockIdx.y * G + g] = acc;
 }
-// w = X^T t, v <- w / |w|; out3 = (|w| (the singular value squared estimate), 1 - |<v_new, v_old>|, sign fix)  (one block)
-__global__ void k_pca_update(const double* __restrict__ part, const double* __restrict__ tsum_part, int RS, int G,
-                             const double* __restrict__ mean, const double* __restrict__ inv_sd, double* __restrict__ v,
-                             double* __restrict__ w, double* __restrict__ out2) {
+// qs[g] = sum_n l_ng t_n over this rank's slices, qs[G] = sum_n t_n (all-reduced over the ranks by the host code)
+__global__ void k_pca_cols_reduce(const double* __restrict__ part, const double* __restrict__ tsum_part, int RS, int G,
+                                  double* __restrict__ qs) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > G) return;
+  double q = 0.0;
+  if (g == G) {
+    for (int r = 0; r < RS; ++r) q += tsum_part[r];
+  } else {
+    for (int r = 0; r < RS; ++r) q += part[(int64_t)r * G + g];
+  }
+  qs[g] = q;
+}
+// w = X^T t = (q - mean sum(t)) / sd, v <- w / |w|; out2 = (|w|, 1 - |<v_new, v_old>|)  (one block; identical on every rank)
+__global__ void k_pca_update(const double* __restrict__ qs, int G, const double* __restrict__ mean,
+                             const double* __restrict__ inv_sd, double* __restrict__ v, double* __restrict__ w,
+                             double* __restrict__ out2) {
   __shared__ double scratch[32];
   __shared__ double sh[2];
-  double ts = 0.0;
-  for (int r = 0; r < RS; ++r) ts += tsum_part[r];
+  const double ts = qs[G];
   double nn = 0.0, dot = 0.0;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    double q = 0.0;
-    for (int r = 0; r < RS; ++r) q += part[(int64_t)r * G + g];
-    const double wg = (q - mean[g] * ts) * inv_sd[g];
+    const double wg = (qs[g] - mean[g] * ts) * inv_sd[g];
     w[g] = wg;
     nn += wg * wg;
     dot += wg * v[g];

@@ -154,14 +154,21 @@ k_corr_part(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int C, const
   double* o = part + ((int64_t)blockIdx.y * G + g) * 5;
   o[0] = sy; o[1] = syy; o[2] = sx; o[3] = sxx; o[4] = sxy;
 }
-// n_assigned cells in total; NaN where x or y is constant or fewer than 2 cells are assigned (R's cor gives NA)
-__global__ void k_corr_final(const double* __restrict__ part, int RS, int G, double n_assigned, double* __restrict__ out) {
+// sums[g][5] over this rank's row slices (all-reduced over the ranks of a cell-sharded fit by the host code)
+__global__ void k_corr_reduce(const double* __restrict__ part, int RS, int G, double* __restrict__ sums) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   for (int r = 0; r < RS; ++r)
     for (int q = 0; q < 5; ++q) s[q] += part[((int64_t)r * G + g) * 5 + q];
-  const double n = n_assigned;
+  for (int q = 0; q < 5; ++q) sums[(int64_t)g * 5 + q] = s[q];
+}
+// sums[5 G] holds the number of assigned cells; NaN where x or y is constant or fewer than 2 cells are assigned (R's cor gives NA)
+__global__ void k_corr_final(const double* __restrict__ sums, int G, double* __restrict__ out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const double* s = sums + (int64_t)g * 5;
+  const double n = sums[(int64_t)5 * G];
   const double vy = n * s[1] - s[0] * s[0], vx = n * s[3] - s[2] * s[2];
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   out[g] = (n >= 2.0 && vy > 0.0 && vx > 0.0) ? (n * s[4] - s[2] * s[0]) / sqrt(vx * vy) : nan;

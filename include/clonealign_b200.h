@@ -164,14 +164,16 @@ CA_API int ca_core_set_array(ca_handle* h, const char* name, const double* in, i
 /* Post-hoc per-gene Pearson correlation between expression and the copy number of each cell's assigned clone
  * (compute_correlations, R/clonealign.R:318-334, called at :292-294) on the Y already resident in HBM.
  * clone_idx: N clone indices (0-based), < 0 = "unassigned" (excluded).  L: G x C copy number (column-major; the
- * reference passes the UNsaturated matrix) or NULL for the session's saturated one.  out: G values, NaN where R gives NA. */
+ * reference passes the UNsaturated matrix) or NULL for the session's saturated one.  out: G values, NaN where R gives NA.
+ * With world > 1 it is a collective call (clone_idx: this rank's cells; every rank gets the same G values). */
 CA_API int ca_core_correlations(ca_handle* h, const int32_t* clone_idx, const double* L, double* out, char* err, size_t errlen);
 
 /* psi initialisation on the device: scores of the leading principal component of the centred, scaled log2(Y + 1)
  * (prcomp(log2(Y_dat + 1), center = TRUE, scale = TRUE)$x[, 1], R/inference-tflow.R:203-204; K == 1) by power iteration
  * on the resident Y.  scores: N values (sign: the loading of largest magnitude is positive); the caller applies
  * scale() and adds its own N(0, 0.05^2) noise (:205-207) and writes the result with ca_core_set_array("psi").
- * Stops when 1 - |<v_new, v_old>| < tol or after max_iter iterations; *iters = iterations used.  world == 1 only. */
+ * Stops when 1 - |<v_new, v_old>| < tol or after max_iter iterations; *iters = iterations used.  With world > 1 it is a
+ * collective call (column statistics and X^T t are all-reduced; every rank gets the scores of its own cells). */
 CA_API int ca_core_pca_scores(ca_handle* h, int32_t max_iter, double tol, double* scores, int32_t* iters, char* err, size_t errlen);
 
 /* Variant P2P (world > 1): every rank exports the 64-byte CUDA IPC handle of its exchange buffer, the caller gathers

@@ -618,3 +618,43 @@ def test_batched_y_pass_for_restarts(example_sce, n_fits):
             s.close()
     for (a, pa), (b, pb) in zip(want, got):
         assert a.tobytes() == b.tobytes() and pa.tobytes() == pb.tobytes()
+
+
+def test_device_pca_and_correlations_under_cell_sharding(example_sce):
+    """SURVEY 8f-1 / 8f-3 combined with 8e: with the cells sharded over ranks, ca_core_pca_scores and ca_core_correlations
+    are collective calls (column statistics, X^T t and the correlation sums are all-reduced) and reproduce the
+    single-shard results."""
+    import threading
+    from clonealign_b200 import compute_correlations, dist as D
+    from clonealign_b200.session import Session
+    Y, L = example_sce
+    keep = Y.sum(0) > 0
+    Y, L = Y[:, keep], L[keep]
+    N, G = Y.shape
+    loc = np.ones(G)
+    zidx = np.random.default_rng(4).integers(-1, L.shape[1], size=N).astype(np.int32)
+    with Session(Y, L, np.zeros((N, 1)), loc) as s:
+        want_pcs, _ = s.pca_scores()
+        want_cor = s.correlations(zidx, L * 1.3)
+    world, nid, colsum = 3, Session.nccl_unique_id(), Y.sum(axis=0)
+    outs, errs = [None] * world, []
+
+    def rank_main(r):
+        try:
+            a, b = D.shard_bounds(N, r, world)
+            with Session(Y[a:b], L, np.zeros((b - a, 1)), loc, rank=r, world=world, nccl_id=nid, n_total=N, colsum_total=colsum) as s:
+                outs[r] = (s.pca_scores()[0], s.correlations(zidx[a:b], L * 1.3))
+        except Exception as e:
+            errs.append(e)
+            raise
+    ts = [threading.Thread(target=rank_main, args=(r,), daemon=True) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=300) for t in ts]
+    assert not errs and all(o is not None for o in outs), errs
+    pcs = np.concatenate([o[0] for o in outs])
+    assert min(np.abs(pcs - want_pcs).max(), np.abs(pcs + want_pcs).max()) < 1e-8 * np.abs(want_pcs).max()
+    for o in outs:
+        np.testing.assert_allclose(o[1], want_cor, atol=1e-12, equal_nan=True)
+    names = ["A", "B", "C"]
+    host = compute_correlations(Y, L * 1.3, ["unassigned" if z < 0 else names[z] for z in zidx], names)
+    np.testing.assert_allclose(want_cor, host, atol=1e-9, equal_nan=True)
