@@ -579,8 +579,8 @@ def test_clonealign_accepts_sparse_counts(example_sce):
     np.testing.assert_allclose(c["correlations"], d["correlations"], atol=0, equal_nan=True)
 
 
-@pytest.mark.parametrize("n_fits", [2, 3, 5])
-def test_batched_y_pass_for_restarts(example_sce, n_fits):
+@pytest.mark.parametrize("n_fits,store", [(2, "u8"), (3, "u16"), (5, "f32")])
+def test_batched_y_pass_for_restarts(example_sce, n_fits, store):
     """ca_core_ypass_many: one stream over the shared count matrix yields every fit's (Y W, Y^T psi) partials; fits
     stepped in lock-step with it are bit-identical to fits that each run their own (packed) Y pass."""
     from clonealign_b200.session import DeviceData, Session, ypass_many
@@ -592,7 +592,7 @@ def test_batched_y_pass_for_restarts(example_sce, n_fits):
     kw = dict(mc_samples=2, K=1, path="interp", variants="ypass2,epi2,lean")
 
     def solo(i):
-        with Session(hi["Y"], hi["L"], psis[i], loc, seed=10 + i, **kw) as s:
+        with Session(hi["Y"], hi["L"], psis[i], loc, seed=10 + i, y_store=store, **kw) as s:
             s.init_gamma()
             tr = [s.elbo()]
             for _ in range(3):
@@ -600,8 +600,9 @@ def test_batched_y_pass_for_restarts(example_sce, n_fits):
                 tr.append(s.elbo())
             return np.array(tr), s.params()["psi"]
     want = [solo(i) for i in range(n_fits)]
-    with DeviceData(hi["Y"], hi["L"]) as data:
+    with DeviceData(hi["Y"], hi["L"], y_store=store) as data:
         ss = [Session(None, None, psis[i], loc, seed=10 + i, data=data, **kw) for i in range(n_fits)]
+        assert ss[0].describe()["y_store"] == store
         for s in ss:
             s.init_gamma()
         ypass_many(ss)
