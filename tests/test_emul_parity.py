@@ -659,3 +659,49 @@ def test_device_pca_and_correlations_under_cell_sharding(example_sce):
     names = ["A", "B", "C"]
     host = compute_correlations(Y, L * 1.3, ["unassigned" if z < 0 else names[z] for z in zidx], names)
     np.testing.assert_allclose(want_cor, host, atol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("path,variants", [("interp", "ypass2,epi2,lean"), ("cudacore", "")])
+def test_bench_flow_on_the_emulation(monkeypatch, capsys, path, variants):
+    """bench.py's whole `ours` arm (session, timed steps, per-kernel profile, roofline, fp32-storage measurement, e2e from
+    host buffers, JSON line) executed on the emulated library with a small workload: the contract keys are present and
+    consistent.  (Numbers are meaningless here; the point is that the code path the driver runs cannot raise.)"""
+    import argparse
+    import importlib.util
+    import json
+    import os
+    import torch
+    from clonealign_b200 import synthetic
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, pin_memory=False, **k: real_empty(*a, **k))
+
+    def fake_cuda(N, G, C, seed=2345234, device="cpu", rows=None, literal=False):
+        a, b = rows if rows is not None else (0, N)
+        syn = synthetic.make_synthetic(N, G, C, seed=seed)
+        return dict(Y=torch.from_numpy(syn["Y"][a:b].astype(np.float32)), L=syn["L"], z=syn["z"][a:b], s=syn["s"][a:b])
+    monkeypatch.setattr(synthetic, "make_synthetic_cuda", fake_cuda)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    args = argparse.Namespace(gpus=1, steps=3, warmup=1, impl="ours", config="c1", y_store="auto", path=path, variants=variants,
+                              selfcheck=False, no_e2e=False, no_cpu_baseline=True, watchdog=0)
+    cfg = dict(N=300, G=260, C=4, S=2, name="emulated mini workload")
+    bench.run_ours(args, cfg)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "gpu_launches", "roofline", "step_hbm", "e2e", "cpu_baseline"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["value"] > 0 and line["gpu_launches"] > 0
+    assert line["config"]["path"] == path and line["config"]["variants"] == variants and line["config"]["y_store"] in ("u8", "u16")
+    assert line["roofline"]["kernel"] == "ypass" and line["roofline"]["bound"] == "hbm" if path == "interp" else True
+    assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-12
+    assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["alt_fp32_storage"]["y_store"] == "f32" and line["alt_fp32_storage"]["step_hbm"]["bytes_per_step"] > line["step_hbm"]["bytes_per_step"]
+    assert np.isfinite(line["config"]["elbo_start"]) and line["config"]["elbo_end"] > line["config"]["elbo_start"]
