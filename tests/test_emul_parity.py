@@ -705,3 +705,32 @@ def test_bench_flow_on_the_emulation(monkeypatch, capsys, path, variants):
     assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["alt_fp32_storage"]["y_store"] == "f32" and line["alt_fp32_storage"]["step_hbm"]["bytes_per_step"] > line["step_hbm"]["bytes_per_step"]
     assert np.isfinite(line["config"]["elbo_start"]) and line["config"]["elbo_end"] > line["config"]["elbo_start"]
+
+
+def test_bench_selfcheck_child_on_the_emulation(monkeypatch, capsys):
+    """`bench.py --selfcheck` (the child process of the default run) end to end on the emulated library, with the
+    CUDA-core kernels standing in for the tcgen05 reference: one JSON verdict per candidate, all passing."""
+    import argparse
+    import importlib.util
+    import json
+    import os
+    import torch
+    from clonealign_b200 import _lib, session, synthetic
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setitem(session._PATH, "tensor", _lib.PATH_CUDACORE)          # no tensor cores under emulation
+
+    def fake_cuda(N, G, C, seed=2345234, device="cpu", rows=None, literal=False):
+        syn = synthetic.make_synthetic(N, G, C, seed=seed)
+        return dict(Y=torch.from_numpy(syn["Y"].astype(np.float32)), L=syn["L"], z=syn["z"], s=syn["s"])
+    monkeypatch.setattr(synthetic, "make_synthetic_cuda", fake_cuda)
+    args = argparse.Namespace(y_store="auto", config="c1")
+    with pytest.raises(SystemExit) as ex:
+        bench.run_selfcheck(args, dict(N=260, G=300, C=4, S=2, name="mini"))
+    assert ex.value.code == 0
+    rows = [json.loads(ln) for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    assert [tuple(r["candidate"]) for r in rows] == [("tensor", "")] + bench.CANDIDATES
+    assert all(r["ok"] and r["ms_per_step"] > 0 for r in rows), [r for r in rows if not r["ok"]]
