@@ -5,8 +5,9 @@
 //   * Z / Z' never round-trip through HBM (Zx [N][J] fp32 written by one kernel and read back by the next);
 //   * the Y-pass row partials are summed by nCB lanes + one shuffle tree instead of a 10-iteration loop that every
 //     lane repeated with 64-bit index math (170 instructions per cell);
-//   * the clone softmax runs in fp32 (the reference's own precision: tf$nn$softmax on float32, R/inference-tflow.R:273)
-//     with one lane per clone held in registers, instead of fp64 exp/log loops over shared memory (~310 instructions);
+//   * the clone softmax keeps one clone per lane in registers with fp32 exponentials / logarithm (the reference's own
+//     precision: tf$nn$softmax on float32, R/inference-tflow.R:273) and an fp64 normalisation (so that 1 - gamma_max keeps
+//     its digits), instead of fp64 exp/log loops over shared memory (~310 instructions);
 //   * column -> clone indices, panel constants and the coefficient table are hoisted out of the per-cell loop
 //     (persistent blocks, one warp per cell, the table of the active panels staged once per block in shared memory);
 //   * the per-cell exponent shift m_n = max(psi_n w_min, psi_n w_max) is computed here (k_shift_k1 is not launched).
@@ -196,15 +197,19 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused(FusedArgs a)
       if (cok) a.t[n * C + lane] = (float)(F - (mx + log(z)));
       continue;
     }
-    // ---- gamma = softmax(t) in fp32, one clone per lane ----
+    // ---- gamma = softmax(t), one clone per lane: exponentials in fp32, normalisation in fp64 ----
+    // d t_c = gamma_c (H_c - sum_k gamma_k H_k) cancels to (1 - gamma_A) H_A - ... for a confidently assigned cell: with
+    // gamma rounded to fp32 (1 - gamma_A) keeps no significant digits once gamma_A > 1 - 1e-6 and the logits of such
+    // cells random-walk under Adam.  exp(t_A - max) is exactly 1 and the fp64 sum keeps 1 - gamma_A = sum_{k != A} e_k / Z
+    // to the relative accuracy of the small exponentials.
     const float tv = cok ? a.t[n * C + lane] : -3.0e38f;
     const float mx = warp_max(tv);
-    const float ex = cok ? expf(tv - mx) : 0.f;
-    const float zs = warp_sum(ex);
-    const float lg = tv - (mx + logf(zs));
-    const float g = cok ? ex / zs : 0.f;
+    const double ex = cok ? (double)expf(tv - mx) : 0.0;
+    const double zs = warp_sum(ex);
+    const float lg = tv - (mx + logf((float)zs));
+    const double g = ex / zs;
     const double H = F + (double)la - (double)lg;
-    const double gh = (g == 0.f) ? 0.0 : (double)g * H;   // tf$where(gamma == 0, 0, gamma * log gamma), :333
+    const double gh = (g == 0.0) ? 0.0 : g * H;           // tf$where(gamma == 0, 0, gamma * log gamma), :333
     const double sumGH = warp_sum(gh);
     if (cok && a.Fout) a.Fout[n * C + lane] = (float)F;
     // ---- Y-linear term psi_n (YW)_n and the N(0,1) prior on psi (:318-319) ----
@@ -214,8 +219,8 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused(FusedArgs a)
     if (lane == 0 && a.YV) a.YV[n] = (float)yv;
     elbo_w += sumGH + x * yv - 0.5 * x * x - 0.5 * kLog2Pi;
     if (MODE == EPI_TRAIN) {
-      gacc += (double)g;
-      if (cok) a.gT[n * C + lane] = (g == 0.f) ? 0.f : (float)((double)g * (H - sumGH));
+      gacc += g;
+      if (cok) a.gT[n * C + lane] = (g == 0.0) ? 0.f : (float)(g * (H - sumGH));
       // R_scn = gamma_nc s_n / (S Z_scn) and d psi_n = (YW)_n - sum_sc R Z' - psi_n
       double zp[NJ];
       if (in_smem) clenshaw_cols<NJ, true>(cpan, jz, SC, a.J, tt, zp);
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused(FusedArgs a)
       double gu = 0.0;
 #pragma unroll
       for (int i = 0; i < NJ; ++i) {
-        const float gc = __shfl_sync(CA_FULL, g, cj[i]);
+        const float gc = __shfl_sync(CA_FULL, (float)g, cj[i]);
         if (jok[i]) {
           const float r = __fdividef(gc * sn_over_S, zf[i]);
           a.Rx[n * a.J + jz[i]] = r;

@@ -734,3 +734,34 @@ def test_bench_selfcheck_child_on_the_emulation(monkeypatch, capsys):
     rows = [json.loads(ln) for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
     assert [tuple(r["candidate"]) for r in rows] == [("tensor", "")] + bench.CANDIDATES
     assert all(r["ok"] and r["ms_per_step"] > 0 for r in rows), [r for r in rows if not r["ok"]]
+
+
+@pytest.mark.parametrize("path", [("interp", ""), ("interp", "ypass2,epi2,lean")])
+def test_long_loop_stays_within_north_star_tolerances(example_sce, path):
+    """40 iterations of the reference loop (train + fresh-draw ELBO) against the float64 oracle on identical draws:
+    per-iteration ELBO within 1e-4 relative, ML parameters within 1e-3 relative, hard clone assignments identical
+    (BASELINE.json north_star) -- i.e. fp32 storage, the fp32 clone softmax of the fused kernel and Adam do not drift."""
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(5))
+    d = O.Data(hi["Y"], hi["L"])
+    S, n_iter = 2, 40
+    eps = np.random.default_rng(9).standard_normal((2 + 2 * n_iter, S, d.Y.shape[1])).astype(np.float32)
+    with _session(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], mc_samples=S, K=1, path=path[0], variants=path[1], seed=3) as sess:
+        sess.set_eps(eps)
+        sess.init_gamma()
+        elbos = [sess.elbo()]
+        for _ in range(n_iter):
+            sess.step()
+            elbos.append(sess.elbo())
+        prm = sess.params()
+    it = iter(eps)
+    p0 = O.init_params(d.Y, d.L, hi["psi_init"], hi["mu_guess"])
+    r = O.fit(d, p0, lambda: next(it).astype(np.float64), max_iter=n_iter, rel_tol=0.0, n_final=0)
+    rel = np.abs(np.array(elbos) - r["elbos"]) / np.abs(r["elbos"])
+    assert rel.max() <= ELBO_RTOL, rel.max()
+    names = ["A", "B", "C"]
+    assert O.clone_assignment(prm["clone_probs"], names) == O.clone_assignment(r["clone_probs"], names)
+    assert _relmax(prm["mu"], r["mu"]) <= PARAM_RTOL
+    assert _relmax(prm["psi"], r["params"].psi) <= PARAM_RTOL
+    assert _relmax(prm["W"], r["params"].W) <= 5e-3
+    assert np.abs(prm["clone_probs"] - r["clone_probs"]).max() <= 2e-3
