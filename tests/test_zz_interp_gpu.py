@@ -239,3 +239,30 @@ def test_shared_device_inputs_for_restarts(example_sce):
         f4 = run_clonealign(Y, L, batch_y_pass=True, **kv)      # lock-step restarts, one batched Y pass per iteration
         f5 = run_clonealign(Y, L, **kv)
     assert f4["multirun_info"]["elbos"].tobytes() == f5["multirun_info"]["elbos"].tobytes() and f4["clone"] == f5["clone"]
+
+
+@pytest.mark.parametrize("path,variants", [("tensor", ""), ("cudacore", ""), ("interp", ""), ("interp", "ypass2,epi2,lean")])
+def test_long_loop_stays_within_north_star_tolerances(example_sce, path, variants):
+    """40 iterations of the reference loop against the float64 oracle on identical draws: ELBO within 1e-4, parameters
+    within 1e-3, identical hard calls (also run for the round-1 paths: informational, this file is xfail-tolerant)."""
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(5))
+    d = O.Data(hi["Y"], hi["L"])
+    S, n_iter = 2, 40
+    eps = np.random.default_rng(9).standard_normal((2 + 2 * n_iter, S, d.Y.shape[1])).astype(np.float32)
+    with _session(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], mc_samples=S, K=1, path=path, variants=variants, seed=3) as sess:
+        sess.set_eps(eps)
+        sess.init_gamma()
+        elbos = [sess.elbo()]
+        for _ in range(n_iter):
+            sess.step()
+            elbos.append(sess.elbo())
+        prm = sess.params()
+    it = iter(eps)
+    p0 = O.init_params(d.Y, d.L, hi["psi_init"], hi["mu_guess"])
+    r = O.fit(d, p0, lambda: next(it).astype(np.float64), max_iter=n_iter, rel_tol=0.0, n_final=0)
+    assert (np.abs(np.array(elbos) - r["elbos"]) / np.abs(r["elbos"])).max() <= ELBO_RTOL
+    names = ["A", "B", "C"]
+    assert O.clone_assignment(prm["clone_probs"], names) == O.clone_assignment(r["clone_probs"], names)
+    assert _relmax(prm["mu"], r["mu"]) <= PARAM_RTOL and _relmax(prm["psi"], r["params"].psi) <= PARAM_RTOL
+    assert np.abs(prm["clone_probs"] - r["clone_probs"]).max() <= 2e-3
