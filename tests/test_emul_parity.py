@@ -736,7 +736,7 @@ def test_bench_selfcheck_child_on_the_emulation(monkeypatch, capsys):
     assert all(r["ok"] and r["ms_per_step"] > 0 for r in rows), [r for r in rows if not r["ok"]]
 
 
-@pytest.mark.parametrize("path", [("interp", ""), ("interp", "ypass2,epi2,lean")])
+@pytest.mark.parametrize("path", [("cudacore", ""), ("interp", ""), ("interp", "ypass2,epi2,lean")])
 def test_long_loop_stays_within_north_star_tolerances(example_sce, path):
     """40 iterations of the reference loop (train + fresh-draw ELBO) against the float64 oracle on identical draws:
     per-iteration ELBO within 1e-4 relative, ML parameters within 1e-3 relative, hard clone assignments identical
