@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <tuple>
 #include <utility>
@@ -262,11 +263,34 @@ inline void fiber_main() {
 #endif
 }
 
+// fiber stacks are recycled across launches through a process-wide free list (a 256 KB malloc is an mmap + page
+// faults every time otherwise)
+struct StackCache {
+  std::mutex mu;
+  std::vector<char*> free_list;
+  char* take() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (!free_list.empty()) {
+        char* p = free_list.back();
+        free_list.pop_back();
+        return p;
+      }
+    }
+    return (char*)malloc(kStackBytes);
+  }
+  void give(std::vector<char*>& v) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (char* p : v) free_list.push_back(p);
+    v.clear();
+  }
+};
+inline StackCache& stack_cache() { static StackCache c; return c; }
 struct StackPool {
   std::vector<char*> all;
-  ~StackPool() { for (char* p : all) free(p); }
+  ~StackPool() { stack_cache().give(all); }
   char* get(size_t i) {
-    while (all.size() <= i) all.push_back((char*)malloc(kStackBytes));
+    while (all.size() <= i) all.push_back(stack_cache().take());
     return all[i];
   }
 };
