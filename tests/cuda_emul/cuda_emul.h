@@ -443,14 +443,50 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   *p = {10, 0, e ? atoi(e) : 3};
   return cudaSuccess;
 }
+// Device memory = host memory with a 256-byte red zone on either side (0xFF like fresh memory, checked at cudaFree: an
+// out-of-bounds WRITE near a buffer aborts with a message) and 0xFF-filled contents (reading memory nobody wrote, or the
+// red zone, shows up as NaN in the parity tests).
+namespace ca_emul {
+constexpr size_t kRedZone = 256;
+struct AllocRegistry {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> live;
+};
+inline AllocRegistry& alloc_registry() { static AllocRegistry r; return r; }
+}  // namespace ca_emul
 inline cudaError_t cudaMalloc(void** p, size_t bytes) {
-  *p = aligned_alloc(256, (bytes + 255) / 256 * 256);
-  if (!*p) return cudaErrorInvalidValue;
-  memset(*p, 0xFF, bytes);
+  const size_t body = (bytes + 255) / 256 * 256;
+  unsigned char* raw = (unsigned char*)aligned_alloc(256, body + 2 * ca_emul::kRedZone);
+  if (!raw) return cudaErrorInvalidValue;
+  memset(raw, 0xFF, ca_emul::kRedZone);
+  memset(raw + ca_emul::kRedZone, 0xFF, body);
+  memset(raw + ca_emul::kRedZone + bytes, 0xFF, body - bytes + ca_emul::kRedZone);
+  *p = raw + ca_emul::kRedZone;
+  std::lock_guard<std::mutex> lk(ca_emul::alloc_registry().mu);
+  ca_emul::alloc_registry().live.push_back({*p, bytes});
   return cudaSuccess;
 }
 template <typename T> inline cudaError_t cudaMalloc(T** p, size_t bytes) { return cudaMalloc((void**)p, bytes); }
-inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaFree(void* p) {
+  if (!p) return cudaSuccess;
+  size_t bytes = 0;
+  bool found = false;
+  {
+    std::lock_guard<std::mutex> lk(ca_emul::alloc_registry().mu);
+    auto& v = ca_emul::alloc_registry().live;
+    for (size_t i = 0; i < v.size(); ++i)
+      if (v[i].first == p) { bytes = v[i].second; v[i] = v.back(); v.pop_back(); found = true; break; }
+  }
+  if (!found) { fprintf(stderr, "cuda_emul: cudaFree of an unknown pointer %p\n", p); abort(); }
+  const size_t body = (bytes + 255) / 256 * 256;
+  unsigned char* raw = (unsigned char*)p - ca_emul::kRedZone;
+  for (size_t i = 0; i < ca_emul::kRedZone; ++i)
+    if (raw[i] != 0xFF) { fprintf(stderr, "cuda_emul: write BEFORE a %zu-byte device buffer (offset -%zu)\n", bytes, ca_emul::kRedZone - i); abort(); }
+  for (size_t i = bytes; i < body + ca_emul::kRedZone; ++i)
+    if (raw[ca_emul::kRedZone + i] != 0xFF) { fprintf(stderr, "cuda_emul: write PAST the end of a %zu-byte device buffer (offset +%zu)\n", bytes, i - bytes); abort(); }
+  free(raw);
+  return cudaSuccess;
+}
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height,
