@@ -302,7 +302,7 @@ inline void run_block(void (*body)(void*), void* body_arg, dim3 grid, dim3 block
   b.nthreads = b.live = nthreads;
   b.warps.resize((nthreads + 31) / 32);
   for (int w = 0; w < (int)b.warps.size(); ++w) b.warps[w].live = std::min(32, nthreads - w * 32);
-  b.dyn.assign(dyn_bytes + 64, 0xFF);
+  b.dyn.assign(dyn_bytes + 256, 0xFF);   // 256-byte red zone behind the dynamic shared memory, checked after the block
   std::vector<Fiber> fibers(nthreads);
   blk = &b;
   blockIdx = {bx, by, bz};
@@ -359,6 +359,12 @@ inline void run_block(void (*body)(void*), void* body_arg, dim3 grid, dim3 block
       abort();
     }
   }
+  for (size_t i = dyn_bytes; i < dyn_bytes + 256; ++i)
+    if (b.dyn[i] != 0xFF) {
+      fprintf(stderr, "cuda_emul: block (%u,%u,%u) wrote past its %zu bytes of dynamic shared memory (offset +%zu)\n", bx, by, bz,
+              dyn_bytes, i - dyn_bytes);
+      abort();
+    }
   blk = nullptr;
   fib = nullptr;
 }
