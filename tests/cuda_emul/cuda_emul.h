@@ -236,7 +236,15 @@ inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 template <typename T> inline T __ldcv(const T* p) { return *(const volatile T*)p; }
-#define CA_SPIN_PAUSE() std::this_thread::yield()
+// a spin-wait on memory written by another block / rank: let the sibling fibers of this block run (on hardware the
+// other lanes of the warp make progress independently) and give the OS thread away
+inline void ca_emul_spin_pause() {
+  ca_emul::blk->progress++;            // waiting on another OS thread is not a dead-lock of this block
+  ca_emul::fib->wait_kind = 0;
+  ca_emul::yield_to_scheduler();
+  std::this_thread::yield();
+}
+#define CA_SPIN_PAUSE() ca_emul_spin_pause()
 inline long long clock64() { return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() * 2; }
 struct __half { unsigned short v; };
 struct __nv_bfloat16 { unsigned short v; };
@@ -333,11 +341,27 @@ inline void run_block(void (*body)(void*), void* body_arg, dim3 grid, dim3 block
     makecontext(&f.ctx, (void (*)())fiber_main, 0);
 #endif
   }
+  // Scheduling order of the fibers between synchronisation points.  Correct CUDA code may not depend on it; a missing
+  // __syncthreads / __syncwarp often only shows under another order, so CA_EMUL_ORDER=reverse|random re-runs the same
+  // tests with the threads of a block visited last-to-first or in a fresh pseudo-random permutation every round.
+  static const int order_mode = [] {
+    const char* e = getenv("CA_EMUL_ORDER");
+    return !e ? 0 : (!strcmp(e, "reverse") ? 1 : (!strcmp(e, "random") ? 2 : 0));
+  }();
+  std::vector<int> order(nthreads);
+  for (int t = 0; t < nthreads; ++t) order[t] = order_mode == 1 ? nthreads - 1 - t : t;
+  uint64_t rng = 0x9E3779B97F4A7C15ull ^ ((uint64_t)bx * 1315423911u + by * 2654435761u + bz);
   int remaining = nthreads;
   while (remaining > 0) {
     const uint64_t before = b.progress;
     bool ran = false;
-    for (int t = 0; t < nthreads; ++t) {
+    if (order_mode == 2)
+      for (int i = nthreads - 1; i > 0; --i) {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        std::swap(order[i], order[(int)(rng % (uint64_t)(i + 1))]);
+      }
+    for (int oi = 0; oi < nthreads; ++oi) {
+      const int t = order[oi];
       Fiber& f = fibers[t];
       if (f.done) continue;
       if (f.wait_kind == 1 && b.bar_gen == f.wait_gen) continue;

@@ -65,3 +65,16 @@ def test_interp_kernels_match_direct_contraction(exe, sd_psi, sd_w, smem_panels,
     assert (nf_neg > 0) == bool((psi < 0).any()) and (nf_pos > 0) == bool((psi >= 0).any())
     if sd_psi == 2.0:
         assert nf_neg + nf_pos > smem_panels          # exercises the coefficients-through-L2 branch of k_interp_eval
+
+
+@pytest.mark.parametrize("order", ["reverse", "random"])
+def test_results_do_not_depend_on_thread_scheduling(order):
+    """Race check on the emulation: the threads of a block are visited last-to-first / in a fresh random permutation every
+    scheduling round (CA_EMUL_ORDER).  A kernel that is missing a __syncthreads / __syncwarp, or whose reductions are not
+    in a fixed order, fails the parity or the bitwise-determinism tests under one of these orders."""
+    import sys
+    env = dict(os.environ, CA_EMUL_ORDER=order)
+    sel = "gradients_and_elbo or same_seed or c3_column or several_row or cell_sharded or batched_y"
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_emul_parity.py"), "-x", "-q", "-k", sel,
+                          "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
