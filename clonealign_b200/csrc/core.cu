@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <stdexcept>
 #include <type_traits>
 #include <string>
@@ -221,7 +222,7 @@ struct ca_data {
   void* Y = nullptr;
   float *L = nullptr, *Bm = nullptr, *vA = nullptr, *s = nullptr, *colsum = nullptr, *snv = nullptr;
   std::vector<void*> allocs;
-  int refs = 0;
+  std::atomic<int> refs{0};   // sessions created from it (host threads of concurrent restarts create / destroy them)
 };
 
 struct ca_handle {
@@ -1249,7 +1250,7 @@ int ca_core_data_create(ca_data** out, const ca_config* cfg, const void* Y, cons
 int ca_core_data_destroy(ca_data* d, char* err, size_t errlen) {
   try {
     if (!d) return 0;
-    if (d->refs > 0) fail("ca_core_data_destroy: %d session(s) still use these inputs", d->refs);
+    if (d->refs.load() > 0) fail("ca_core_data_destroy: %d session(s) still use these inputs", d->refs.load());
     cudaSetDevice(d->dev);
     for (void* p : d->allocs) cudaFree(p);
     delete d;
