@@ -661,8 +661,8 @@ def test_device_pca_and_correlations_under_cell_sharding(example_sce):
     np.testing.assert_allclose(want_cor, host, atol=1e-9, equal_nan=True)
 
 
-@pytest.mark.parametrize("path,variants", [("interp", "ypass2,epi2,lean"), ("cudacore", "")])
-def test_bench_flow_on_the_emulation(monkeypatch, capsys, path, variants):
+@pytest.mark.parametrize("path,variants,V", [("interp", "ypass2,epi2,lean", 0), ("cudacore", "", 0), ("interp", "epi2", 25)])
+def test_bench_flow_on_the_emulation(monkeypatch, capsys, path, variants, V):
     """bench.py's whole `ours` arm (session, timed steps, per-kernel profile, roofline, fp32-storage measurement, e2e from
     host buffers, JSON line) executed on the emulated library with a small workload: the contract keys are present and
     consistent.  (Numbers are meaningless here; the point is that the code path the driver runs cannot raise.)"""
@@ -693,6 +693,8 @@ def test_bench_flow_on_the_emulation(monkeypatch, capsys, path, variants):
     args = argparse.Namespace(gpus=1, steps=3, warmup=1, impl="ours", config="c1", y_store="auto", path=path, variants=variants,
                               selfcheck=False, no_e2e=False, no_cpu_baseline=True, watchdog=0)
     cfg = dict(N=300, G=260, C=4, S=2, name="emulated mini workload")
+    if V:
+        cfg["V"] = V                         # the allele-specific configuration (BASELINE config 4 in miniature)
     bench.run_ours(args, cfg)
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
