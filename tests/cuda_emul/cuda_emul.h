@@ -397,7 +397,7 @@ inline int host_workers() {
   static int n = [] {
     const char* e = getenv("CA_EMUL_THREADS");
     int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
-    return v < 4 ? 4 : (v > 16 ? 16 : v);   // >= 4: blocks of a spin-waiting kernel must be co-resident
+    return v < 16 ? 16 : (v > 32 ? 32 : v);   // >= 16: the blocks of a spin-waiting kernel (k_p2p_allreduce, <= 16) must be co-resident
   }();
   return n;
 }
