@@ -235,7 +235,11 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
         if pca_noise is not None:
             pcs = cache.get("pcs_device") if cache is not None else None
             if pcs is None:
-                pcs, _ = sess.pca_scores()                                            # :203-204 on the device
+                pcs, n_it = sess.pca_scores(max_iter=500)                             # :203-204 on the device
+                if n_it >= 500:
+                    import warnings
+                    warnings.warn("device PCA: power iteration stopped at 500 iterations before reaching its tolerance "
+                                  "(leading components nearly degenerate); the psi initialisation is approximate")
                 pcs = (pcs - pcs.mean()) / pcs.std(ddof=1)                            # scale(pcs), :205
                 if cache is not None:
                     cache["pcs_device"] = pcs
