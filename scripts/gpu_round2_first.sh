@@ -18,6 +18,7 @@ timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytes
 echo "rc=$?"; tail -3 $O/r02_sanitizer.log
 echo "== 4. candidate table at c3 (self-check child: verdict + ms/step per candidate)"
 timeout 400 python bench.py --selfcheck --config c3 > $O/r02_candidates.jsonl 2> $O/r02_candidates.err; cat $O/r02_candidates.jsonl
+python scripts/summarize_candidates.py $O/r02_candidates.jsonl > $O/r02_candidates.md 2>/dev/null; cat $O/r02_candidates.md
 echo "== 5. default bench (picks the fastest passing candidate) + reference arm"
 timeout 600 python bench.py > $O/r02_bench.json 2> $O/r02_bench.err; tail -c 3000 $O/r02_bench.json
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $O/r02_bench_reference.json 2> $O/r02_bench_reference.err
