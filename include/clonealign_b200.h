@@ -12,6 +12,15 @@
  *   ca_core_params      sess$run(list(softplus(loc),gamma,...)) R/inference-tflow.R:424-440
  *   ca_core_destroy     sess$close()                            R/inference-tflow.R:457
  *
+ * and, for the host work on either side of the session:
+ *
+ *   ca_core_create, y_layout = CA_Y_CSR   t(as.matrix(assay(sce, "counts")))           R/clonealign.R:217
+ *   ca_core_pca_scores                    prcomp(log2(Y_dat + 1), center, scale)$x     R/inference-tflow.R:203-205
+ *   ca_core_correlations                  compute_correlations(Y, L, clones)           R/clonealign.R:292-294,318-334
+ *   ca_core_data_create / _create_shared  the per-restart repetition of the set-up in  R/clonealign.R:50-56
+ *   ca_core_ypass_many                    run_clonealign()'s loop (one Y pass for all restarts of a device)
+ *   ca_core_p2p_export / _connect         (no counterpart: the reference is single-process; SURVEY.md 8e exchange)
+ *
  * Conventions
  *   - Plain pointers and sizes only; no C++/torch types.  Every call returns 0 on success and a
  *     non-zero status with a message in `err` (NUL-terminated, truncated to errlen) otherwise.
