@@ -767,3 +767,29 @@ def test_long_loop_stays_within_north_star_tolerances(example_sce, path):
     assert _relmax(prm["psi"], r["params"].psi) <= PARAM_RTOL
     assert _relmax(prm["W"], r["params"].W) <= 5e-3
     assert np.abs(prm["clone_probs"] - r["clone_probs"]).max() <= 2e-3
+
+
+def test_random_shapes_and_variants():
+    """Seeded fuzz over (cells, genes, clones, samples, exponent range, kernel set): gradients, Z, F and the ELBO of the
+    interp path and its variants against the closed-form oracle, including tiny and degenerate shapes."""
+    from clonealign_b200.synthetic import make_synthetic
+    rng = np.random.default_rng(20261017)
+    for it in range(16):
+        small = it % 4 == 0
+        N = int(rng.integers(2, 40 if small else 700))
+        G = int(rng.integers(2, 70 if small else 3000))
+        C = int(rng.integers(1, 6 if small else 33))
+        S = max(1, min(int(rng.integers(1, 9)), 128 // C))
+        syn = make_synthetic(N, G, C, seed=int(rng.integers(1e6)))
+        Y, L = syn["Y"].astype(np.float64), np.minimum(syn["L"], 6.0)
+        Y[:, Y.sum(0) == 0] += 1.0
+        Y[Y.sum(1) == 0, 0] += 1.0
+        d, p, mu_guess, _ = _case(Y, L, K=1, seed=it, scale=float(rng.choice([0.05, 0.3, 1.0])))
+        p.psi *= float(rng.choice([0.5, 1.0, 3.0]))
+        var = str(rng.choice(["", "ypass2", "epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap"]))
+        with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path="interp", seed=1, variants=var) as sess:
+            _load_params(sess, p)
+            try:
+                _check_grads(sess, d, p, S)
+            except AssertionError as e:
+                raise AssertionError(f"N={N} G={d.Y.shape[1]} C={C} S={S} variants={var!r}: {e}") from None
