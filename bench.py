@@ -377,6 +377,11 @@ def run_ours(args, cfg):
     launches = sess.describe()["launches_last_step"] * args.steps
     e_end = sess.elbo()
 
+    # the reference's loop iteration = train step + fresh-draw ELBO evaluation (R/inference-tflow.R:401-403), device-timed
+    # the same way (reported separately; every rank runs the same count, the evaluation has a collective too)
+    n_loop = max(3, min(args.steps, 20))
+    ms_loop = D.max_over_ranks(sess.time_steps(n_loop, with_eval=True)) / n_loop
+
     # per-kernel device time (events around every launch), averaged over a few steps after the timed region
     prof = {}
     nprof = 5
@@ -476,7 +481,10 @@ def run_ours(args, cfg):
                            "l2": "inputs larger than L2 (Y shard >> 126 MB)", "psi_init": "random normal (PCA skipped)",
                            "path_requested": args.path, "selfcheck": selfcheck,
                            "elbo_start": e_start, "elbo_end": e_end},
-                "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "step_hbm": step_hbm, "alt_fp32_storage": alt_f32, "e2e": e2e,
+                "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "step_hbm": step_hbm,
+                "reference_loop_iteration": {"ms": ms_loop, "value": 1e3 / ms_loop, "unit": "iterations/s",
+                                             "what": "train step + fresh-draw ELBO evaluation, device-timed"},
+                "alt_fp32_storage": alt_f32, "e2e": e2e,
                 "cpu_baseline": cpu_base}
         print(json.dumps(line), flush=True)
 
