@@ -24,7 +24,7 @@ EXPORTS = (
     "ca_core_destroy", "ca_core_init_gamma", "ca_core_step", "ca_core_elbo", "ca_core_params",
     "ca_core_set_eps", "ca_core_get_eps", "ca_core_grads", "ca_core_get_array", "ca_core_set_array",
     "ca_core_time_steps", "ca_core_profile_step", "ca_core_describe", "ca_core_correlations", "ca_core_pca_scores", "ca_core_p2p_export", "ca_core_p2p_connect", "ca_core_data_create", "ca_core_data_destroy",
-    "ca_core_create_shared", "ca_core_ypass_many",
+    "ca_core_create_shared", "ca_core_ypass_many", "ca_core_data_stats",
 )
 
 
@@ -80,6 +80,7 @@ def load():
     lib.ca_core_data_create.argtypes = [C.POINTER(vp), C.POINTER(CaConfig), vp, vp, vp, vp, vp, vp, cp, sz]
     lib.ca_core_data_destroy.argtypes = [vp, cp, sz]
     lib.ca_core_create_shared.argtypes = [C.POINTER(vp), C.POINTER(CaConfig), vp, vp, vp, vp, cp, sz]
+    lib.ca_core_data_stats.argtypes = [vp, vp, vp, vp, cp, sz]
     lib.ca_core_ypass_many.argtypes = [C.POINTER(vp), C.c_int32, cp, sz]
     lib.ca_core_p2p_export.argtypes = [vp, vp, cp, sz]
     lib.ca_core_p2p_connect.argtypes = [vp, vp, cp, sz]

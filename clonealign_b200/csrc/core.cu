@@ -1258,6 +1258,49 @@ int ca_core_data_destroy(ca_data* d, char* err, size_t errlen) {
   } catch (const std::exception& e) { return report(e, err, errlen); }
 }
 
+int ca_core_data_stats(ca_data* d, double* rowsum, double* colsum, double* mu_guess, char* err, size_t errlen) {
+  try {
+    if (!d) fail("null argument");
+    CUDA_OK(cudaSetDevice(d->dev));
+    const int64_t N = d->N;
+    const int G = d->G;
+    const int RS = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / 64));
+    double *d_row = nullptr, *d_part = nullptr, *d_sums = nullptr;
+    struct Guard {
+      double*& a; double*& b; double*& c;
+      ~Guard() { cudaFree(a); cudaFree(b); cudaFree(c); }
+    } guard{d_row, d_part, d_sums};
+    CUDA_OK(cudaMalloc(&d_row, sizeof(double) * N));
+    CUDA_OK(cudaMalloc(&d_part, sizeof(double) * (size_t)RS * G * 2));
+    CUDA_OK(cudaMalloc(&d_sums, sizeof(double) * (size_t)G * 2));
+    cudaStream_t st = nullptr;   // the legacy default stream: the inputs are immutable and nothing else is in flight on them
+    auto run = [&](auto* Yp) {
+      using T = typename std::remove_const<typename std::remove_pointer<decltype(Yp)>::type>::type;
+      CA_LAUNCH(k_stats_rows<T>, (unsigned)ceil_div64(N, 8), 256, 0, st)(Yp, d->ldY, N, G, d_row);
+      KCHECK();
+      CA_LAUNCH(k_stats_cols<T>, dim3((G + 127) / 128, RS), 128, 0, st)(Yp, d->ldY, N, G, RS, d_row, d_part);
+      KCHECK();
+    };
+    switch (d->ystore) {
+      case CA_STORE_F32: run((const float*)d->Y); break;
+      case CA_STORE_U16: run((const uint16_t*)d->Y); break;
+      case CA_STORE_U8: run((const uint8_t*)d->Y); break;
+      default: fail("bad y_store");
+    }
+    CA_LAUNCH(k_pca_colstats_reduce, (G + 127) / 128, 128, 0, st)(d_part, RS, G, d_sums);
+    KCHECK();
+    std::vector<double> hs((size_t)2 * G);
+    CUDA_OK(cudaMemcpyAsync(hs.data(), d_sums, sizeof(double) * 2 * G, cudaMemcpyDeviceToHost, st));
+    if (rowsum) CUDA_OK(cudaMemcpyAsync(rowsum, d_row, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    for (int g = 0; g < G; ++g) {
+      if (colsum) colsum[g] = hs[2 * (size_t)g];
+      if (mu_guess) mu_guess[g] = hs[2 * (size_t)g + 1] * (double)G / (double)N;   // colMeans(Y / rowMeans(Y)), :222
+    }
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
 int ca_core_create_shared(ca_handle** out, const ca_config* cfg, ca_data* data, const double* psi_init, const double* loc_init,
                           const double* X, char* err, size_t errlen) {
   ca_handle* h = nullptr;

@@ -147,4 +147,41 @@ __global__ void k_pca_update(const double* __restrict__ qs, int G, const double*
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Host-side initial values of R/inference-tflow.R:210-222 from the resident count matrix (ca_core_data_stats):
+//   s_init = rowSums(Y) (:210), colSums(Y) (gene filter, :117), mu_guess = colMeans(Y / rowMeans(Y)) (:222)
+// One warp per cell for the row sums, then column slices for the two column quantities; fp64, fixed order.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_stats_rows(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, double* __restrict__ rowsum) {
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  double acc = 0.0;
+  for (int g = lane; g < G; g += 32) acc += (double)(float)Y[n * ldY + g];
+  acc = warp_sum(acc);
+  if (lane == 0) rowsum[n] = acc;
+}
+// part[rs][g] = (sum_n y_ng, sum_n y_ng / rowsum_n) over the row slice
+template <typename T>
+__global__ void __launch_bounds__(128)
+k_stats_cols(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RS, const double* __restrict__ rowsum,
+             double* __restrict__ part) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const int64_t rps = ceil_div64(N, RS);
+  const int64_t r0 = blockIdx.y * rps, r1 = r0 + rps < N ? r0 + rps : N;
+  double s1 = 0.0, s2 = 0.0;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float y = (float)Y[r * ldY + g];
+    if (y != 0.f) {
+      s1 += (double)y;
+      s2 += (double)y / rowsum[r];
+    }
+  }
+  part[((int64_t)blockIdx.y * G + g) * 2] = s1;
+  part[((int64_t)blockIdx.y * G + g) * 2 + 1] = s2;
+}
+
 }  // namespace ca

@@ -105,7 +105,8 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
                     x=None, clone_allele=None, cov=None, ref=None, fix_alpha=False, dtype="float32",
                     saturate_=True, saturation_threshold=6, K=1, mc_samples=1, verbose=True, initial_shrink=5,
                     data_init_mu=True, seed=None, device=0, psi_init=None, y_store="auto", path="auto",
-                    gene_names=None, variants=None, correlations_with=None, device_pca=False, cache=None):
+                    gene_names=None, variants=None, correlations_with=None, device_pca=False, cache=None,
+                    device_stats=False):
     """The fit of `inference_tflow` as a generator: it yields its `Session` every time the parameters have just changed
     and the next operation is an ELBO evaluation (after gamma-init and after every train step), i.e. exactly where one
     batched pass over a shared count matrix can serve several restarts (`session.ypass_many`; `run_clonealign(
@@ -124,6 +125,9 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
     calls WITH IDENTICAL INPUTS -- the un-noised principal components, and per device the count matrix resident in HBM with
     everything derived from it (`DeviceData`, ca_core_data_create); the RNG stream positions do not change, so a cached
     restart is bit-identical to an uncached one.  The caller closes `cache[("data", device)]` when done.
+    `device_stats=True` (needs `cache`): s_init = rowSums(Y) (:210) and mu_guess = colMeans(Y / rowMeans(Y)) (:222) come from
+    the resident matrix (ca_core_data_stats, fp64) instead of host passes over the N x G matrix; mu_guess then agrees with
+    the host value to ~1e-15 relative (different summation order), so fits are no longer bit-identical to host-initialised ones.
     `correlations_with = (L_unsaturated, clone_call_probability)`: also run the caller's post-hoc
     `compute_correlations` (R/clonealign.R:292-294,318-334) on the device while Y is still resident; the result is
     returned under "correlations" (retained genes only).
@@ -198,11 +202,32 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
             psi_init = pcs + rng.normal(0.0, 0.05, size=pcs.shape)                    # :207
         else:
             psi_init = np.zeros((N, 0))
-    s_init = np.asarray(Y.sum(axis=1), dtype=np.float64).ravel()                      # :210
+    def get_data():
+        """Restart-independent device inputs: upload + preprocess once per device (built on first use)."""
+        import contextlib
+        from .session import DeviceData
+        with cache.get("lock") or contextlib.nullcontext():       # concurrent restarts on one device: build once
+            dd = cache.get(("data", device))
+            if dd is None:
+                dd = cache[("data", device)] = DeviceData(Y, L, device=device, clone_allele=clone_allele if use_allele else None,
+                                                          alt=alt, cov=cov if use_allele else None, y_store=y_store)
+        return dd
+
+    dev_stats = None
+    if device_stats:
+        if cache is None:
+            raise ValueError("device_stats=True needs a cache (the statistics come from the shared device inputs)")
+        dev_stats = cache.get("stats")
+        if dev_stats is None:
+            dev_stats = cache["stats"] = get_data().stats()
+    s_init = dev_stats["rowsum"] if dev_stats is not None else \
+        np.asarray(Y.sum(axis=1), dtype=np.float64).ravel()                           # :210
     if np.any(s_init == 0):
         raise ValueError("Some cells have no counts mapping")                         # :212-214
     if isinstance(data_init_mu, (bool, np.bool_)):                                    # :220-235
-        if data_init_mu and sparse:
+        if data_init_mu and dev_stats is not None:
+            mu_guess = dev_stats["mu_guess"]
+        elif data_init_mu and sparse:
             import scipy.sparse as sp
             inv_rowmean = sp.diags(Y.shape[1] / s_init)                               # 1 / rowMeans(Y)
             mu_guess = np.asarray((inv_rowmean @ Y.astype(np.float64)).mean(axis=0)).ravel()
@@ -217,15 +242,7 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
         mu_guess = d / d.mean()
 
     op_seed = get_next_seed(rng)                                                      # :269
-    data = None
-    if cache is not None:           # restart-independent device inputs: upload + preprocess once per device
-        import contextlib
-        from .session import DeviceData
-        with cache.get("lock") or contextlib.nullcontext():       # concurrent restarts on one device: build once
-            data = cache.get(("data", device))
-            if data is None:
-                data = cache[("data", device)] = DeviceData(Y, L, device=device, clone_allele=clone_allele if use_allele else None,
-                                                            alt=alt, cov=cov if use_allele else None, y_store=y_store)
+    data = get_data() if cache is not None else None
     sess = Session(Y, L, psi_init, safe_inverse_softplus(mu_guess), mc_samples=int(mc_samples), K=K, x=x,
                    learning_rate=learning_rate, seed=op_seed, device=device,
                    clone_allele=clone_allele if use_allele else None, alt=alt, cov=cov if use_allele else None,

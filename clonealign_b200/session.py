@@ -154,6 +154,14 @@ class DeviceData:
         self._d = d
         self.N, self.G, self.C, self.V, self.device = N, G, Cn, V, int(device)
 
+    def stats(self):
+        """rowSums(Y), colSums(Y) and mu_guess = colMeans(Y / rowMeans(Y)) (R/inference-tflow.R:210,117,222) from the
+        resident matrix (ca_core_data_stats)."""
+        rs, cs, mg = (np.zeros(self.N), np.zeros(self.G), np.zeros(self.G))
+        err = C.create_string_buffer(1024)
+        _lib.check(self._lib.ca_core_data_stats(self._d, _ptr(rs), _ptr(cs), _ptr(mg), err, len(err)), err)
+        return {"rowsum": rs, "colsum": cs, "mu_guess": mg}
+
     def close(self):
         if self._d is not None:
             err = C.create_string_buffer(1024)

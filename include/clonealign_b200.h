@@ -17,6 +17,7 @@
  *   ca_core_create, y_layout = CA_Y_CSR   t(as.matrix(assay(sce, "counts")))           R/clonealign.R:217
  *   ca_core_pca_scores                    prcomp(log2(Y_dat + 1), center, scale)$x     R/inference-tflow.R:203-205
  *   ca_core_correlations                  compute_correlations(Y, L, clones)           R/clonealign.R:292-294,318-334
+ *   ca_core_data_stats                    rowSums / colSums / colMeans(Y / rowMeans(Y)) R/inference-tflow.R:117,210,222
  *   ca_core_data_create / _create_shared  the per-restart repetition of the set-up in  R/clonealign.R:50-56
  *   ca_core_ypass_many                    run_clonealign()'s loop (one Y pass for all restarts of a device)
  *   ca_core_p2p_export / _connect         (no counterpart: the reference is single-process; SURVEY.md 8e exchange)
@@ -135,6 +136,10 @@ CA_API int ca_core_data_create(ca_data** out, const ca_config* cfg, const void* 
                         const double* colsum_total, const double* clone_allele, const double* alt, const double* cov,
                         char* err, size_t errlen);
 CA_API int ca_core_data_destroy(ca_data* d, char* err, size_t errlen);
+/* Initial values the host code derives from Y (R/inference-tflow.R:210 s_init = rowSums(Y), :117 colSums(Y) for the gene
+ * filter, :222 mu_guess = colMeans(Y / rowMeans(Y))), computed from the resident matrix in fp64 instead of by passes over
+ * the N x G host matrix.  Any output may be NULL.  rowsum: N, colsum: G, mu_guess: G. */
+CA_API int ca_core_data_stats(ca_data* d, double* rowsum, double* colsum, double* mu_guess, char* err, size_t errlen);
 CA_API int ca_core_create_shared(ca_handle** out, const ca_config* cfg, ca_data* data, const double* psi_init,
                           const double* loc_init, const double* X, char* err, size_t errlen);
 

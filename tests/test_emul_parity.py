@@ -793,3 +793,42 @@ def test_random_shapes_and_variants():
                 _check_grads(sess, d, p, S)
             except AssertionError as e:
                 raise AssertionError(f"N={N} G={d.Y.shape[1]} C={C} S={S} variants={var!r}: {e}") from None
+
+
+def test_device_data_stats(example_sce):
+    """ca_core_data_stats: s_init, colSums and mu_guess (R/inference-tflow.R:210,117,222) from the resident matrix."""
+    import scipy.sparse as sp
+    from clonealign_b200.session import DeviceData
+    Y, L = example_sce
+    Y = Y[:, Y.sum(0) > 0]
+    L = L[: Y.shape[1]]
+    want_mu = (Y / Y.mean(axis=1, keepdims=True)).mean(axis=0)
+    for inp, store in ((Y, "u8"), (sp.csr_matrix(Y), "f32"), (Y * 300.0, "u16")):
+        with DeviceData(inp, L, y_store=store) as data:
+            st = data.stats()
+        scale = 300.0 if store == "u16" else 1.0
+        np.testing.assert_array_equal(st["rowsum"], Y.sum(1) * scale)
+        np.testing.assert_array_equal(st["colsum"], Y.sum(0) * scale)
+        np.testing.assert_allclose(st["mu_guess"], want_mu, rtol=1e-12)
+
+
+def test_fit_without_host_passes_over_the_matrix(example_sce):
+    """Sparse counts + device PCA + device statistics + device correlations + shared inputs: after the (sparse) gene filter
+    the host never touches the N x G matrix; the fit agrees with the all-host-initialised one (same RNG stream) to the
+    accuracy of the initial values."""
+    import scipy.sparse as sp
+    from clonealign_b200 import clonealign
+    Y, L = example_sce
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        kw = dict(max_iter=4, verbose=False, seed=3, clone_names=["A", "B", "C"])
+        cache = {}
+        a = clonealign(sp.csr_matrix(Y), L, device_pca=True, device_stats=True, device_correlations=True, cache=cache, **kw)
+        cache[("data", 0)].close()
+        b = clonealign(Y, L, device_pca=True, **kw)
+    ea, eb = a["convergence_info"]["elbo"], b["convergence_info"]["elbo"]
+    assert np.abs(ea - eb).max() / np.abs(eb).max() < 1e-6 and a["clone"] == b["clone"]
+    np.testing.assert_allclose(a["correlations"], b["correlations"], atol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(a["ml_params"]["s"], b["ml_params"]["s"], rtol=0, atol=0)
+    with pytest.raises(ValueError, match="device_stats=True needs a cache"):
+        clonealign(Y, L, device_stats=True, **kw)
