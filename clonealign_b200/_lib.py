@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libclonealign_b200.so")
 
 # enums of include/clonealign_b200.h
-Y_F64, Y_F32, Y_I32 = 0, 1, 2
+Y_F64, Y_F32, Y_I32, Y_U8, Y_U16 = 0, 1, 2, 3, 4
 Y_COLMAJOR, Y_ROWMAJOR, Y_CSR = 0, 1, 2
 Y_HOST, Y_DEVICE = 0, 1
 STORE_AUTO, STORE_F32, STORE_U16, STORE_U8 = 0, 1, 2, 3

@@ -894,6 +894,8 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     case CA_Y_F64: ingest_y<double>(h, (const double*)Y, Yf); break;
     case CA_Y_F32: ingest_y<float>(h, (const float*)Y, Yf); break;
     case CA_Y_I32: ingest_y<int>(h, (const int*)Y, Yf); break;
+    case CA_Y_U8: ingest_y<uint8_t>(h, (const uint8_t*)Y, Yf); break;
+    case CA_Y_U16: ingest_y<uint16_t>(h, (const uint16_t*)Y, Yf); break;
     default: fail("bad y_dtype");
   }
   // ---- narrow storage if exact ----

@@ -80,10 +80,12 @@ def _marshal_y(Y, cfg, keep):
         N, G = Ys.shape
         if Ys.nnz >= 2 ** 31:
             raise ValueError("sparse Y with >= 2^31 stored values is not supported (int32 offsets, as R's dgCMatrix)")
-        vals = np.ascontiguousarray(Ys.data, dtype=np.float64 if Ys.data.dtype not in (np.float32, np.int32) else Ys.data.dtype)
+        vals = np.ascontiguousarray(Ys.data, dtype=Ys.data.dtype if Ys.data.dtype in (np.float32, np.int32, np.uint8, np.uint16)
+                                    else np.float64)
         indptr = np.ascontiguousarray(Ys.indptr, dtype=np.int32)
         indices = np.ascontiguousarray(Ys.indices, dtype=np.int32)
-        cfg.y_dtype = {np.dtype(np.float64): _lib.Y_F64, np.dtype(np.float32): _lib.Y_F32, np.dtype(np.int32): _lib.Y_I32}[vals.dtype]
+        cfg.y_dtype = {np.dtype(np.float64): _lib.Y_F64, np.dtype(np.float32): _lib.Y_F32, np.dtype(np.int32): _lib.Y_I32,
+                       np.dtype(np.uint8): _lib.Y_U8, np.dtype(np.uint16): _lib.Y_U16}[vals.dtype]
         cfg.y_layout, cfg.y_mem = _lib.Y_CSR, _lib.Y_HOST
         cfg.y_indptr, cfg.y_indices = _ptr(indptr), _ptr(indices)
         yptr = _ptr(vals)
@@ -98,6 +100,10 @@ def _marshal_y(Y, cfg, keep):
             cfg.y_dtype = _lib.Y_F32
         elif Y.dtype == np.int32:
             cfg.y_dtype = _lib.Y_I32
+        elif Y.dtype == np.uint8:
+            cfg.y_dtype = _lib.Y_U8
+        elif Y.dtype == np.uint16:
+            cfg.y_dtype = _lib.Y_U16
         else:
             Y = Y.astype(np.float64)
             cfg.y_dtype = _lib.Y_F64

@@ -181,6 +181,9 @@ def test_storage_formats_and_input_layouts_agree(example_sce):
     t_i = run(np.asfortranarray(hi["Y"].astype(np.int32)))                  # an R integer matrix
     t_32 = run(hi["Y"].astype(np.float32))
     assert traces[0].tobytes() == t_f.tobytes() == t_i.tobytes() == t_32.tobytes()
+    import scipy.sparse as sp
+    for compact in (hi["Y"].astype(np.uint8), np.asfortranarray(hi["Y"].astype(np.uint16)), sp.csr_matrix(hi["Y"].astype(np.uint8))):
+        assert run(compact).tobytes() == traces[0].tobytes()                  # compact host counts (CA_Y_U8 / CA_Y_U16)
     from clonealign_b200._lib import CloneAlignLibraryError
     with pytest.raises(CloneAlignLibraryError, match="u8"):
         run(hi["Y"] + 0.5, y_store="u8")
@@ -692,7 +695,7 @@ def test_bench_flow_on_the_emulation(monkeypatch, capsys, path, variants, V):
         monkeypatch.delenv(k, raising=False)
     args = argparse.Namespace(gpus=1, steps=3, warmup=1, impl="ours", config="c1", y_store="auto", path=path, variants=variants,
                               selfcheck=False, no_e2e=False, no_cpu_baseline=True, watchdog=0)
-    cfg = dict(N=300, G=260, C=4, S=2, name="emulated mini workload")
+    cfg = dict(N=300, G=900 if path == "cudacore" else 260, C=4, S=2, name="emulated mini workload")   # G = 900: u8 counts
     if V:
         cfg["V"] = V                         # the allele-specific configuration (BASELINE config 4 in miniature)
     bench.run_ours(args, cfg)
@@ -705,6 +708,8 @@ def test_bench_flow_on_the_emulation(monkeypatch, capsys, path, variants, V):
     assert line["roofline"]["kernel"] == "ypass" and line["roofline"]["bound"] == "hbm" if path == "interp" else True
     assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-12
     assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    if line["config"]["y_store"] == "u8":
+        assert line["e2e_compact_host"]["value"] > 0 and line["e2e_compact_host"]["final_elbo"] == line["e2e"]["final_elbo"]
     assert line["alt_fp32_storage"]["y_store"] == "f32" and line["alt_fp32_storage"]["step_hbm"]["bytes_per_step"] > line["step_hbm"]["bytes_per_step"]
     assert np.isfinite(line["config"]["elbo_start"]) and line["config"]["elbo_end"] > line["config"]["elbo_start"]
 
