@@ -28,16 +28,23 @@ def build(verbose=False) -> str:
     for f in _sources():
         h.update(f.encode())
         h.update(open(f, "rb").read())
+    # CA_EMUL_SANITIZE=1: UBSan alignment / bounds / shift checks.  The emulated float4 / uint4 / double types carry the
+    # device's alignment, so a 16-byte vector access at an address that is only 4-byte aligned (cudaErrorMisalignedAddress
+    # on hardware, silently fine on x86) aborts with file:line.
+    sanitize = os.environ.get("CA_EMUL_SANITIZE", "") not in ("", "0")
+    h.update(b"sanitize" if sanitize else b"")
     tag = h.hexdigest()[:16]
     os.makedirs(OUT_DIR, exist_ok=True)
     out = os.path.join(OUT_DIR, f"libclonealign_emul_{tag}.so")
     if os.path.exists(out):
         return out
     for old in os.listdir(OUT_DIR):
-        if old.startswith("libclonealign_emul_"):
+        if old.startswith("libclonealign_emul_") and not sanitize:
             os.unlink(os.path.join(OUT_DIR, old))
     cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-x", "c++", "-DCA_EMULATE", "-Wno-unknown-pragmas",
            "-I", HERE, "-I", CSRC, os.path.join(CSRC, "core.cu"), "-o", out + ".tmp", "-ldl", "-pthread"]
+    if sanitize:
+        cmd[1:1] = ["-fsanitize=alignment,bounds,shift,integer-divide-by-zero,vla-bound,null", "-fno-sanitize-recover=all"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

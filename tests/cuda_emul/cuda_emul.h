@@ -402,10 +402,53 @@ inline int host_workers() {
   return n;
 }
 
+// Launch limits of the hardware (sm_100): a launch that the driver would reject with cudaErrorInvalidConfiguration /
+// cudaErrorInvalidValue aborts here with a message, so that a grid that only gets too large at full problem sizes, or
+// a kernel whose dynamic shared memory was raised past 48 KB without cudaFuncSetAttribute, is found without a device.
+struct FuncAttrRegistry {
+  std::mutex mu;
+  std::vector<std::pair<const void*, size_t>> max_dyn;   // kernel -> cudaFuncAttributeMaxDynamicSharedMemorySize
+  size_t get(const void* k) {
+    std::lock_guard<std::mutex> lk(mu);
+    size_t v = 48 * 1024;
+    for (auto& e : max_dyn)
+      if (e.first == k) v = e.second;
+    return v;
+  }
+  void set(const void* k, size_t v) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& e : max_dyn)
+      if (e.first == k) { e.second = v; return; }
+    max_dyn.push_back({k, v});
+  }
+};
+inline FuncAttrRegistry& func_attrs() { static FuncAttrRegistry r; return r; }
+constexpr size_t kMaxOptinSmem = 227 * 1024;   // per-block opt-in maximum on sm_100
+
+inline void check_launch_limits(const void* kernel, dim3 grid, dim3 block, size_t dyn_bytes) {
+  const uint64_t nthreads = (uint64_t)block.x * block.y * block.z;
+  const char* why = nullptr;
+  if (grid.x > 2147483647u || grid.y > 65535u || grid.z > 65535u) why = "grid dimension over the hardware limit (x <= 2^31-1, y/z <= 65535)";
+  else if (nthreads > 1024 || block.x > 1024 || block.y > 1024 || block.z > 64) why = "more than 1024 threads per block";
+  else if (dyn_bytes > kMaxOptinSmem) why = "dynamic shared memory over the 227 KB opt-in maximum";
+  else if (dyn_bytes > func_attrs().get(kernel)) why = "dynamic shared memory over 48 KB without a matching cudaFuncSetAttribute(MaxDynamicSharedMemorySize)";
+  if (why) {
+    fprintf(stderr, "cuda_emul: invalid launch configuration: %s [grid (%u,%u,%u) block (%u,%u,%u) smem %zu]\n", why, grid.x, grid.y,
+            grid.z, block.x, block.y, block.z, dyn_bytes);
+    abort();
+  }
+}
+
 template <typename K, typename... A>
 void launch(K kernel, dim3 grid, dim3 block, size_t dyn_bytes, A... args) {
   const uint64_t nblocks = (uint64_t)grid.x * grid.y * grid.z;
-  if (nblocks == 0 || block.x * block.y * block.z == 0) return;
+  check_launch_limits((const void*)kernel, grid, block, dyn_bytes);
+  if (nblocks == 0 || block.x * block.y * block.z == 0) {
+    // a zero-sized grid or block is cudaErrorInvalidConfiguration on hardware
+    fprintf(stderr, "cuda_emul: invalid launch configuration: empty grid or block [grid (%u,%u,%u) block (%u,%u,%u)]\n", grid.x, grid.y,
+            grid.z, block.x, block.y, block.z);
+    abort();
+  }
   struct Call {
     K kernel;
     std::tuple<A...> tup;
@@ -537,7 +580,13 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
   *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
   return cudaSuccess;
 }
-template <typename K> inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
+template <typename K> inline cudaError_t cudaFuncSetAttribute(K k, cudaFuncAttribute a, int v) {
+  if (a == cudaFuncAttributeMaxDynamicSharedMemorySize) {
+    if (v < 0 || (size_t)v > ca_emul::kMaxOptinSmem) return cudaErrorInvalidValue;
+    ca_emul::func_attrs().set((const void*)k, (size_t)v);
+  }
+  return cudaSuccess;
+}
 // CUDA IPC between the "ranks" of the emulation (threads of one process): a handle is the pointer itself
 struct cudaIpcMemHandle_t { char reserved[64]; };
 enum { cudaIpcMemLazyEnablePeerAccess = 1 };
