@@ -504,6 +504,7 @@ def run_ours(args, cfg):
                            "K": 1, "sharding": f"cells/{world}", "path": desc["path"], "variants": variants, "y_store": desc["y_store"],
                            "l2": "inputs larger than L2 (Y shard >> 126 MB)", "psi_init": "random normal (PCA skipped)",
                            "path_requested": args.path, "selfcheck": selfcheck,
+                           "fallback_after_error": os.environ.get("CLONEALIGN_B200_BENCH_FALLBACK"),
                            "elbo_start": e_start, "elbo_end": e_end},
                 "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "step_hbm": step_hbm,
                 "reference_loop_iteration": {"ms": ms_loop, "value": 1e3 / ms_loop, "unit": "iterations/s",
@@ -542,7 +543,20 @@ def main():
     elif args.impl == "reference":
         run_reference(args, cfg)
     else:
-        run_ours(args, cfg)
+        try:
+            run_ours(args, cfg)
+        except SystemExit:
+            raise
+        except BaseException as e:   # noqa: BLE001
+            # A candidate that passed the child's gate but fails in the full run must not cost the benchmark line: start
+            # over ONCE, in a fresh process (a CUDA fault poisons the context), on the kernel set the GPU parity suite covers.
+            single = int(os.environ.get("WORLD_SIZE", "1")) == 1
+            if args.path == "best" and single and not os.environ.get("CLONEALIGN_B200_BENCH_FALLBACK"):
+                sys.stderr.write(f"bench.py: run with the selected kernel set failed ({str(e)[:300]}); retrying with --path auto\n")
+                sys.stderr.flush()
+                os.environ["CLONEALIGN_B200_BENCH_FALLBACK"] = str(e)[:200] or type(e).__name__
+                os.execv(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + ["--path", "auto"])
+            raise
 
 
 if __name__ == "__main__":

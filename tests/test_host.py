@@ -336,6 +336,45 @@ def test_bench_candidate_selection(monkeypatch, tmp_path):
     assert bench.interp_selfcheck(args)[0] == ("auto", "")                   # no output at all
 
 
+def test_bench_falls_back_once_when_the_selected_kernel_set_fails(monkeypatch):
+    """A kernel set that passed the child's gate but raises in the full run restarts bench.py ONCE in a fresh process
+    with --path auto (the parity-tested kernels); the restarted process does not loop, and an explicit --path never
+    falls back."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    calls = []
+
+    def boom(args, cfg):
+        raise RuntimeError("CUDA error cudaErrorIllegalAddress at core.cu:1")
+
+    def fake_exec(exe, argv):
+        calls.append(argv)
+        raise SystemExit(77)                                   # execv does not return
+
+    monkeypatch.setattr(bench, "run_ours", boom)
+    monkeypatch.setattr(bench.os, "execv", fake_exec)
+    for k in ("WORLD_SIZE", "CLONEALIGN_B200_BENCH_FALLBACK"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--watchdog", "0"])
+    with pytest.raises(SystemExit) as ex:
+        bench.main()
+    assert ex.value.code == 77 and calls[0][-2:] == ["--path", "auto"] and "--steps" in calls[0]
+    assert "cudaErrorIllegalAddress" in os.environ["CLONEALIGN_B200_BENCH_FALLBACK"]
+    with pytest.raises(RuntimeError):                           # the restarted process: no second restart
+        bench.main()
+    monkeypatch.delenv("CLONEALIGN_B200_BENCH_FALLBACK")
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--path", "interp", "--watchdog", "0"])
+    with pytest.raises(RuntimeError):                           # an explicit path is what the caller asked for
+        bench.main()
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "2", "--watchdog", "0"])
+    with pytest.raises(RuntimeError):                           # ranks of a torchrun job cannot restart on their own
+        bench.main()
+    assert len(calls) == 1
+
+
 def test_r_shim_compiles_against_stub_headers():
     """r/src/ca_shim.c (the .Call binding a clonealign maintainer adds) is type-checked against include/clonealign_b200.h
     with stub declarations of the R API (tests/r_stub/): there is no R in this image, but argument counts / types of every
