@@ -1374,6 +1374,35 @@ int ca_core_elbo(ca_handle* h, double* elbo, char* err, size_t errlen) {
   } catch (const std::exception& e) { return report(e, err, errlen); }
 }
 
+// n evaluations of the ELBO with fresh draws, queued back to back on the stream and fetched with ONE device-to-host
+// copy (the 20 evaluations behind final_elbo / sd_final_elbo, R/inference-tflow.R:447-449, each a sess$run(elbo) with
+// its own host round trip in the reference).  Same draw sequence, same values as n calls of ca_core_elbo; the
+// parameters do not change in between, so only the first evaluation can need a Y pass.
+int ca_core_elbo_many(ca_handle* h, int32_t n, double* elbo, char* err, size_t errlen) {
+  double* d_out = nullptr;
+  try {
+    if (!h || !elbo || n < 0) fail("bad argument");
+    if (n == 0) return 0;
+    CUDA_OK(cudaSetDevice(h->dev));
+    CUDA_OK(cudaMalloc(&d_out, sizeof(double) * (size_t)n));
+    for (int i = 0; i < n; ++i) {
+      run_elbo_async(h);
+      CUDA_OK(cudaMemcpyAsync(d_out + i, h->elbo_dev, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CUDA_OK(cudaMemcpyAsync(elbo, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    int p2p_failed = 0;
+    if (h->p2p_err) CUDA_OK(cudaMemcpyAsync(&p2p_failed, h->p2p_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_out);
+    d_out = nullptr;
+    if (p2p_failed) fail("variant p2p: the all-reduce kernel timed out waiting for a peer's contribution");
+    return 0;
+  } catch (const std::exception& e) {
+    if (d_out) { cudaStreamSynchronize(h->stream); cudaFree(d_out); }
+    return report(e, err, errlen);
+  }
+}
+
 int ca_core_params(ca_handle* h, double* mu, double* clone_probs, double* s, double* alpha, double* psi, double* W,
                    double* chi, double* beta, double* clone_probs_from_snv, char* err, size_t errlen) {
   try {

@@ -283,7 +283,7 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
         rlist = sess.params()                                                         # :424-434
         clone_probs_from_snv = rlist.pop("clone_probs_from_snv", None)                # :436-440
         _message(verbose, "Computing final ELBO")
-        final_elbo = [sess.elbo() for _ in range(20)]                                 # :447-449
+        final_elbo = [float(e) for e in sess.elbo_many(20)]                           # :447-449, one host round trip
         if correlations_with is not None:
             L_full, call_p = correlations_with
             cp = rlist["clone_probs"]

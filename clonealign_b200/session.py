@@ -299,6 +299,12 @@ class Session:
         self._chk(self._lib.ca_core_elbo(self._h, C.byref(out), self._err, len(self._err)))
         return out.value
 
+    def elbo_many(self, n: int) -> np.ndarray:
+        """n fresh-draw ELBO evaluations with one host round trip (replicate(20, sess$run(elbo)), R/inference-tflow.R:447-449)."""
+        out = np.zeros(int(n), dtype=np.float64)
+        self._chk(self._lib.ca_core_elbo_many(self._h, int(n), out.ctypes.data_as(C.c_void_p), self._err, len(self._err)))
+        return out
+
     def params(self) -> dict:
         """mu, clone_probs, s, alpha [, beta] [, psi, W, chi] [, clone_probs_from_snv] (R/inference-tflow.R:424-440)."""
         N, G, Cn, K, P = self.N, self.G, self.C, self.K, self.P

@@ -9,6 +9,7 @@
  *   ca_core_init_gamma  sess$run(gamma_init) + assign           R/inference-tflow.R:338-342,368-369
  *   ca_core_step        sess$run(train)                         R/inference-tflow.R:345-346,401
  *   ca_core_elbo        sess$run(elbo)                          R/inference-tflow.R:336,372,403,448
+ *   ca_core_elbo_many   replicate(20, sess$run(elbo))           R/inference-tflow.R:447-449 (one host round trip)
  *   ca_core_params      sess$run(list(softplus(loc),gamma,...)) R/inference-tflow.R:424-440
  *   ca_core_destroy     sess$close()                            R/inference-tflow.R:457
  *
@@ -45,7 +46,7 @@
 extern "C" {
 #endif
 
-#define CA_ABI_VERSION 4
+#define CA_ABI_VERSION 5
 #if defined(__GNUC__)
 #define CA_API __attribute__((visibility("default")))
 #else
@@ -155,6 +156,10 @@ CA_API int ca_core_ypass_many(ca_handle* const* hs, int32_t n, char* err, size_t
 CA_API int ca_core_init_gamma(ca_handle* h, char* err, size_t errlen);
 CA_API int ca_core_step(ca_handle* h, char* err, size_t errlen);
 CA_API int ca_core_elbo(ca_handle* h, double* elbo, char* err, size_t errlen);
+/* n ELBO evaluations with fresh draws (the 20 behind final_elbo / sd_final_elbo, R/inference-tflow.R:447-449) queued on
+ * the stream and fetched with one device-to-host copy; elbo: n doubles, the same values n calls of ca_core_elbo give.
+ * Collective under cell sharding like ca_core_elbo (every rank passes the same n). */
+CA_API int ca_core_elbo_many(ca_handle* h, int32_t n, double* elbo, char* err, size_t errlen);
 /* any output pointer may be NULL.  mu: G, clone_probs: N x C, s: N, alpha: C, psi: N x K,
  * W: G x K, chi: K, beta: G x P, clone_probs_from_snv: N x C (only when V > 0). */
 CA_API int ca_core_params(ca_handle* h, double* mu, double* clone_probs, double* s, double* alpha,

@@ -55,7 +55,7 @@ inference_cuda_session <- function(Y_dat, L_dat, pcs, mu_guess, x, clone_allele,
     if (mean(abs(elbo_diffs)) < rel_tol) break             # :414
   }
   rlist <- .Call("ca_params", sess, c(N, G, C, as.integer(K), P, V))   # :424-440
-  final_elbo <- replicate(20, .Call("ca_elbo", sess))      # :447-449
+  final_elbo <- .Call("ca_elbo_many", sess, 20L)           # :447-449 (20 fresh-draw evaluations, one round trip)
   correlations <- NULL
   if (!is.null(cor_with)) {                                # clone_assignment (:22-29) as 0-based indices, -1 = unassigned
     cp <- rlist$clone_probs

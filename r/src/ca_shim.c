@@ -228,6 +228,20 @@ SEXP ca_elbo(SEXP ptr) {
   return Rf_ScalarReal(e);   /* NaN propagates; R keeps stop("Initial elbo is NA") */
 }
 
+/* replicate(n, sess$run(elbo)) (R/inference-tflow.R:447-449) with one device-to-host copy */
+SEXP ca_elbo_many(SEXP ptr, SEXP n) {
+  char err[ERRLEN] = {0};
+  int k = Rf_asInteger(n);
+  if (k < 0) Rf_error("ca_elbo_many: n must be >= 0");
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, k));
+  if (ca_core_elbo_many(get_handle(ptr), k, REAL(out), err, ERRLEN)) {
+    UNPROTECT(1);
+    Rf_error("%s", err);
+  }
+  UNPROTECT(1);
+  return out;
+}
+
 /* named list: mu, clone_probs, s, alpha [, beta] [, psi, W, chi] [, clone_probs_from_snv] */
 SEXP ca_params(SEXP ptr, SEXP dims) {   /* dims = c(N, G, C, K, P, V) */
   char err[ERRLEN] = {0};
@@ -277,7 +291,8 @@ static const R_CallMethodDef call_methods[] = {
     {"ca_destroy", (DL_FUNC)&ca_destroy, 1}, {"ca_create_sparse", (DL_FUNC)&ca_create_sparse, 16},
     {"ca_pca_scores", (DL_FUNC)&ca_pca_scores, 4}, {"ca_set_psi", (DL_FUNC)&ca_set_psi, 2},
     {"ca_correlations", (DL_FUNC)&ca_correlations, 4}, {"ca_data_create", (DL_FUNC)&ca_data_create, 6},
-    {"ca_create_shared", (DL_FUNC)&ca_create_shared, 9}, {"ca_ypass_many", (DL_FUNC)&ca_ypass_many, 1}, {NULL, NULL, 0}};
+    {"ca_create_shared", (DL_FUNC)&ca_create_shared, 9}, {"ca_ypass_many", (DL_FUNC)&ca_ypass_many, 1},
+    {"ca_elbo_many", (DL_FUNC)&ca_elbo_many, 2}, {NULL, NULL, 0}};
 
 void R_init_clonealign(DllInfo* dll) {
   R_registerRoutines(dll, NULL, call_methods, NULL, NULL);

@@ -157,6 +157,27 @@ def test_loop_with_device_rng_matches_oracle(example_sce, path):
 
 
 @pytest.mark.parametrize("path", PATHS)
+def test_elbo_many_equals_repeated_elbo(example_sce, path):
+    """ca_core_elbo_many (the 20 fresh-draw evaluations behind final_elbo / sd_final_elbo, R/inference-tflow.R:447-449,
+    fetched with one device-to-host copy) returns bit-for-bit what the same number of ca_core_elbo calls returns, consumes
+    the same draws, and leaves the session in the same state."""
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(2))
+
+    def run(many):
+        with _session(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], mc_samples=2, K=1, seed=31, path=path[0], variants=path[1]) as sess:
+            sess.init_gamma()
+            sess.step()
+            e = sess.elbo_many(5) if many else np.array([sess.elbo() for _ in range(5)])
+            sess.step()
+            return e, sess.elbo(), sess.elbo_many(0)
+    a, a_next, empty = run(True)
+    b, b_next, _ = run(False)
+    assert a.tobytes() == b.tobytes() and a_next == b_next and empty.size == 0
+    assert len(set(a.tolist())) == 5                                   # fresh draws: five different values
+
+
+@pytest.mark.parametrize("path", PATHS)
 def test_same_seed_bitwise_identical(example_sce, path):
     """tests/testthat/test_clonealign.R:42-66 (fixed-order reductions: also independent of the host thread count)."""
     Y, L = example_sce

@@ -32,6 +32,9 @@ class FakeSession:
         self._e += 1.0
         return self._e
 
+    def elbo_many(self, n):
+        return np.array([self.elbo() for _ in range(n)])
+
     def params(self):
         self.calls.append("params")
         N, G = self.Y.shape
