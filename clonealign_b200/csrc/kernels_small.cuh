@@ -609,52 +609,8 @@ struct GeneGradArgs {
   float* dM_out;          // [G][J] summed over splits (inspection), may be nullptr
 };
 
-// rank-local (linear in the cell sums) parts of the gene gradients -> allreduce buffer
-__global__ void __launch_bounds__(128) k_gene_grads(GeneGradArgs a) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= a.G) return;
-  const int SC = a.S * a.C;
-  float sd = expf(a.lsd[g]);
-  double aloc = 0.0, alsd = 0.0;
-  double gv[kMaxKP];
-#pragma unroll
-  for (int kp = 0; kp < kMaxKP; ++kp) gv[kp] = 0.0;
-  for (int kp = 0; kp < a.KP; ++kp) {
-    double acc = 0.0;
-    for (int rb = 0; rb < a.nRB; ++rb) acc += (double)a.colpart[((int64_t)rb * a.G + g) * a.KP + kp];
-    gv[kp] = acc;
-    a.YtU[(int64_t)g * a.KP + kp] = (float)acc;
-  }
-  for (int s = 0; s < a.S; ++s) {
-    int64_t o = (int64_t)s * a.G + g;
-    float mu = a.mu[o];
-    double dmu = 0.0;
-    for (int c = 0; c < a.C; ++c) {
-      int j = s * a.C + c;
-      float l = a.L[(int64_t)g * a.C + c];
-      double d = 0.0;
-      for (int sp = 0; sp < a.nsplit; ++sp) d += (double)a.dMx[((int64_t)sp * a.G + g) * a.J + j];
-      if (a.dM_out) a.dM_out[(int64_t)g * a.J + j] = (float)d;
-      dmu -= (double)l * d;
-      for (int kp = 0; kp < a.KP; ++kp) {
-        int jj = a.SCp * (1 + kp) + j;
-        double d2 = 0.0;
-        for (int sp = 0; sp < a.nsplit; ++sp) d2 += (double)a.dMx[((int64_t)sp * a.G + g) * a.J + jj];
-        if (a.dM_out) a.dM_out[(int64_t)g * a.J + jj] = (float)d2;
-        gv[kp] -= (double)(mu * l) * d2;
-      }
-    }
-    double dx = (double)a.sig[o] * dmu;
-    aloc += dx;
-    alsd += dx * (double)sd * (double)a.eps[o];
-  }
-  (void)SC;
-  a.ar[g] = (float)aloc;
-  a.ar[a.G + g] = (float)alsd;
-  for (int kp = 0; kp < a.KP; ++kp) a.ar[2 * (int64_t)a.G + (int64_t)g * a.KP + kp] = (float)gv[kp];
-}
-
-// Same contract as k_gene_grads, one WARP per gene: lanes stride over the J columns so every read of the
+// Rank-local (linear in the cell sums) parts of the gene gradients -> allreduce buffer.
+// One WARP per gene: lanes stride over the J columns so every read of the
 // K-split partials is a coalesced 128-byte line; the three weighted column sums are reduced with a
 // fixed-pattern warp shuffle (deterministic).
 __global__ void __launch_bounds__(256) k_gene_grads_warp(GeneGradArgs a) {
