@@ -35,11 +35,12 @@ def build(verbose=False) -> str:
     h.update(b"sanitize" if sanitize else b"")
     tag = h.hexdigest()[:16]
     os.makedirs(OUT_DIR, exist_ok=True)
-    out = os.path.join(OUT_DIR, f"libclonealign_emul_{tag}.so")
+    prefix = "libclonealign_emulsan_" if sanitize else "libclonealign_emul_"
+    out = os.path.join(OUT_DIR, f"{prefix}{tag}.so")
     if os.path.exists(out):
         return out
     for old in os.listdir(OUT_DIR):
-        if old.startswith("libclonealign_emul_") and not sanitize:
+        if old.startswith(prefix):
             os.unlink(os.path.join(OUT_DIR, old))
     cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-x", "c++", "-DCA_EMULATE", "-Wno-unknown-pragmas",
            "-I", HERE, "-I", CSRC, os.path.join(CSRC, "core.cu"), "-o", out + ".tmp", "-ldl", "-pthread"]

@@ -78,3 +78,50 @@ def test_results_do_not_depend_on_thread_scheduling(order):
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_emul_parity.py"), "-x", "-q", "-k", sel,
                           "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+
+
+def test_emulator_rejects_invalid_launch_configurations():
+    """The emulation enforces the hardware's launch limits (grid / block dimensions, dynamic shared memory above 48 KB
+    only after cudaFuncSetAttribute, 227 KB maximum): what the driver would refuse aborts with a message here."""
+    src = r'''
+#include "cuda_emul.h"
+__global__ void k(int* p) { CA_DYNAMIC_SMEM(int, s); if (threadIdx.x == 0) s[0] = 1; p[blockIdx.x] = 1; }
+int main(int argc, char** argv) {
+  int* p; cudaMalloc(&p, 1024 * sizeof(int));
+  int mode = atoi(argv[1]);
+  if (mode == 0) { CA_LAUNCH(k, 4, 64, 1024, nullptr)(p); }                                 // fine
+  if (mode == 1) { CA_LAUNCH(k, 4, 64, 64 * 1024, nullptr)(p); }                            // > 48 KB without the attribute
+  if (mode == 2) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+                   CA_LAUNCH(k, 4, 64, 64 * 1024, nullptr)(p); }                            // fine after opting in
+  if (mode == 3) { CA_LAUNCH(k, dim3(1, 70000), 64, 0, nullptr)(p); }                       // grid.y > 65535
+  if (mode == 4) { CA_LAUNCH(k, 1, 2048, 0, nullptr)(p); }                                  // > 1024 threads
+  if (mode == 5) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 300 * 1024) ? 0 : 1; }
+  if (mode == 6) { CA_LAUNCH(k, 0, 64, 0, nullptr)(p); }                                    // empty grid
+  cudaFree(p);
+  puts("ok");
+  return 0;
+}
+'''
+    with tempfile.TemporaryDirectory() as td:
+        cpp, exe_path = os.path.join(td, "t.cpp"), os.path.join(td, "t")
+        open(cpp, "w").write(src)
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I", EMUL, cpp, "-o", exe_path])
+        for mode, ok in ((0, True), (1, False), (2, True), (3, False), (4, False), (5, True), (6, False)):
+            r = subprocess.run([exe_path, str(mode)], capture_output=True, text=True, timeout=120)
+            assert (r.returncode == 0) == ok, (mode, r.returncode, r.stderr)
+            if not ok:
+                assert "invalid launch configuration" in r.stderr, (mode, r.stderr)
+
+
+def test_parity_subset_under_alignment_and_bounds_sanitizer():
+    """A slice of the emulated parity suite on a build with UBSan's alignment / bounds / shift checks
+    (CA_EMUL_SANITIZE=1): the emulated float4 / uint4 / double2 carry the device's alignment, so a vector access that
+    would raise cudaErrorMisalignedAddress on hardware (and is silently fine on x86) aborts with file:line.  Covers the
+    template instantiations of BASELINE config 3 (C = 12, S = 8: 16-byte operand stores), several row / column tiles of the
+    Y pass, and every count storage format."""
+    env = dict(os.environ, CA_EMUL_SANITIZE="1")
+    r = subprocess.run(["python", "-m", "pytest", os.path.join(ROOT, "tests", "test_emul_parity.py"), "-x", "-q", "-p", "no:cacheprovider",
+                        "-k", "c3_column_structure or several_row_and_column_tiles or storage_formats_and_input_layouts or batched_y_pass"],
+                       env=env, capture_output=True, text=True, timeout=1500, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout and "runtime error" not in r.stderr
