@@ -314,26 +314,95 @@ def test_bench_candidate_selection(monkeypatch, tmp_path):
     args = argparse.Namespace(config="c1", y_store="auto")
 
     def fake(lines, rc=0):
-        class R:
-            stdout = "warming up\n" + "\n".join(json.dumps(x) for x in lines) + "\n"
-            stderr = ""
-            returncode = rc
-        return lambda *a, **k: R()
+        """A child that prints `lines` (tensor row + candidate verdicts in CANDIDATES order, honouring --selfcheck-skip)
+        and exits with `rc` on its first start, 0 afterwards."""
+        state = {"first": True}
 
+        def run(cmd, **k):
+            skip = int(cmd[cmd.index("--selfcheck-skip") + 1])
+            cand = [x for x in lines if x["candidate"][0] != "tensor"][skip:]
+            head = [x for x in lines if x["candidate"][0] == "tensor"]
+
+            class R:
+                stdout = "warming up\n" + "\n".join(json.dumps(x) for x in head + cand) + "\n"
+                stderr = ""
+                returncode = rc if state["first"] else 0
+            state["first"] = False
+            return R
+        return run
+
+    C = bench.CANDIDATES
     rows = [{"candidate": ["tensor", ""], "ok": True, "ms_per_step": 3.3},
-            {"candidate": ["interp", ""], "ok": True, "ms_per_step": 1.4},
-            {"candidate": ["interp", "ypass2"], "ok": False, "ms_per_step": 0.9},
-            {"candidate": ["interp", "ypass2,epi2"], "ok": True, "ms_per_step": 1.1}]
-    monkeypatch.setattr(bench.subprocess, "run", fake(rows, rc=1))          # crashed after 4 verdicts: not cached
+            {"candidate": list(C[0]), "ok": True, "ms_per_step": 1.4},
+            {"candidate": list(C[1]), "ok": False, "ms_per_step": 0.9},
+            {"candidate": list(C[2]), "ok": True, "ms_per_step": 1.1}]
+    monkeypatch.setattr(bench.subprocess, "run", fake(rows, rc=1))          # died on the 4th candidate: incomplete, not cached
     pick, info = bench.interp_selfcheck(args)
-    assert pick == ("interp", "ypass2,epi2") and pick in bench.CANDIDATES and len(info["candidates"]) == 4
-    monkeypatch.setattr(bench.subprocess, "run", fake(rows[:1] + [dict(rows[1], ms_per_step=5.0)]))
-    assert bench.interp_selfcheck(args)[0] == ("auto", "")                   # slower than the tensor path
-    monkeypatch.setattr(bench.subprocess, "run", fake([]))                   # (the verdict above was cached)
+    assert pick == C[2] and len(info["candidates"]) == 5 and not info["candidates"][4]["ok"]
+    full = rows[:1] + [{"candidate": list(c), "ok": True, "ms_per_step": 5.0 + i} for i, c in enumerate(C)]
+    monkeypatch.setattr(bench.subprocess, "run", fake(full))
+    assert bench.interp_selfcheck(args)[0] == ("auto", "")                   # every candidate slower than the tensor path
+    monkeypatch.setattr(bench.subprocess, "run", fake([]))                   # (the complete verdict above was cached)
     pick, info = bench.interp_selfcheck(args)
     assert pick == ("auto", "") and "cached" in info["note"]
     args.config = "c2"
     assert bench.interp_selfcheck(args)[0] == ("auto", "")                   # no output at all
+
+
+def test_bench_selfcheck_resumes_behind_a_faulting_candidate(monkeypatch, tmp_path):
+    """A candidate that takes the CUDA context down (child exit code 3 after its verdict) or that kills / hangs the child
+    without a verdict must not keep the candidates behind it from being checked: the child is restarted behind it."""
+    import argparse
+    import importlib.util
+    import json
+    import tempfile as tf
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(tf, "gettempdir", lambda: str(tmp_path))
+    args = argparse.Namespace(config="c1", y_store="auto")
+    C = bench.CANDIDATES
+    tensor = {"candidate": ["tensor", ""], "ok": True, "ms_per_step": 3.3}
+    ok = lambda i, ms: {"candidate": list(C[i]), "ok": True, "ms_per_step": ms}
+    calls = []
+
+    def run(cmd, **kw):
+        skip = int(cmd[cmd.index("--selfcheck-skip") + 1])
+        calls.append(skip)
+
+        class R:
+            stderr = ""
+        if skip == 0:      # candidate 2 faults after its verdict was printed
+            R.stdout = "\n".join(json.dumps(x) for x in [tensor, ok(0, 1.5), ok(1, 1.4),
+                                                         {"candidate": list(C[2]), "ok": False, "error": "CUDA error cudaErrorIllegalAddress"}])
+            R.returncode = bench.SELFCHECK_RESUME_RC
+        elif skip == 3:    # candidate 4 kills the process (no verdict)
+            R.stdout = "\n".join(json.dumps(x) for x in [tensor, ok(3, 1.2)])
+            R.returncode = -11
+        else:              # the rest runs through
+            R.stdout = "\n".join(json.dumps(x) for x in [tensor] + [ok(i, 0.6 + 0.01 * i) for i in range(skip, len(C))])
+            R.returncode = 0
+        return R
+    monkeypatch.setattr(bench.subprocess, "run", run)
+    pick, info = bench.interp_selfcheck(args)
+    assert calls == [0, 3, 5]
+    rows = info["candidates"]
+    assert [tuple(r["candidate"]) for r in rows] == [("tensor", "")] + C          # one verdict per candidate, in order
+    assert not rows[3]["ok"] and "CUDA error" in rows[3]["error"] and not rows[5]["ok"] and "died" in rows[5]["error"]
+    assert pick == C[5] and "child exit -11" in info["note"]                       # fastest of the ones that passed
+    # nothing comes back at all (the tcgen05 reference itself fails): one attempt, no verdicts, default kernels
+    calls.clear()
+    args.config = "c2"
+
+    def dead(cmd, **kw):
+        calls.append(1)
+
+        class R:
+            stdout, stderr, returncode = "", "boom", 1
+        return R
+    monkeypatch.setattr(bench.subprocess, "run", dead)
+    pick, info = bench.interp_selfcheck(args)
+    assert pick == ("auto", "") and calls == [1] and "reference run did not complete" in info["note"]
 
 
 def test_bench_falls_back_once_when_the_selected_kernel_set_fails(monkeypatch):
