@@ -4,7 +4,9 @@ the kernel variants (`variants=`: packed-fp32 Y pass, fused Clenshaw + per-cell 
 They were written after round 1's GPU budget was spent: the kernels are verified against the oracle on the CPU emulation
 of the whole C-ABI (tests/test_emul_parity.py) but had never run on hardware when this file was committed.  Until they have, these tests are
 `xfail(strict=False)`: a pass is reported as XPASS (evidence), a failure cannot turn the suite red, and the file sorts
-last so that a device fault here cannot disturb the tests of the default paths.  Once green on a B200: drop the marker,
+last so that a device fault here cannot disturb the tests of the default paths.  Every test FUNCTION of this file runs in its own child pytest process (tests/conftest.py, `pytest_pyfunc_call`): a kernel that
+faults takes only its own child's CUDA context down, so the other functions still deliver their own XPASS / XFAIL verdicts.
+Once green on a B200: drop the marker,
 add "interp" to PATHS in test_gpu_parity.py and make it the AUTO path for K = 1, P = 0.
 """
 import numpy as np
