@@ -858,3 +858,18 @@ def test_fit_without_host_passes_over_the_matrix(example_sce):
     np.testing.assert_allclose(a["ml_params"]["s"], b["ml_params"]["s"], rtol=0, atol=0)
     with pytest.raises(ValueError, match="device_stats=True needs a cache"):
         clonealign(Y, L, device_stats=True, **kw)
+
+
+def test_smoke_cases_on_the_emulation(capsys, monkeypatch):
+    """__graft_entry__.smoke()'s check (one tiny fit step against the oracle) for every kernel set it reports, on the emulated
+    library; the opt-in sets run in child processes there, whose failure is reported but never fatal."""
+    import __graft_entry__ as g
+    for path, variants in (("cudacore", ""), ("interp", ""), ("interp", "ypass2,epi2,lean")):
+        g._smoke_case(path, variants)
+    out = capsys.readouterr().out
+    assert out.count(" OK") == 3 and "smoke[interp+ypass2,epi2,lean]" in out
+    # the child-process leg: the children load the PRODUCT library, which has no device here -> reported, not raised
+    monkeypatch.setattr(g, "_smoke_case", lambda path, variants="": None)      # the in-process legs (tensor cores) are not emulated
+    g.smoke()
+    out = capsys.readouterr().out
+    assert out.count("NOT OK on this device (non-fatal") == 2
