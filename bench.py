@@ -445,6 +445,9 @@ def run_ours(args, cfg):
             traffic = json.load(open(tpath)).get(args.config, {}).get(top)
         roofline = dict(kernel=top, bound=k["bound"], achieved=ach, peak=peak, unit="GB/s" if k["bound"] == "hbm" else "TFLOP/s",
                         frac=ach / peak, traffic=traffic, peak_source=pk["which"], ms_per_launch=k["t"],
+                        traffic_source=(None if traffic is None else
+                                        "profiles/r01_ncu_full_c3.md (round-1 capture of the round-1 kernel of this launch slot: "
+                                        "k_ypass_k1_persistent<u8> / k_expgemm_tc; same operands, not re-captured for the variants)"),
                         note=("algorithmic flops 2*N*G*J (J = 2*S*C: Z and Z' columns); the forward kernel ISSUES 3x that "
                               "(bf16 3-term split for fp32-grade log Z / d psi), so its tensor-pipe utilisation is ~3x frac"
                               if top == "lse_fwd" else None),
