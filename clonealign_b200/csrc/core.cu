@@ -370,7 +370,9 @@ void run_ypass(ca_handle* h, cudaStream_t st) {
     if (h->KP == 1) {
       LaunchScope ls(h, "ypass");
       dim3 grid(h->nCB, h->nRB);
-      if (h->variants & CA_VAR_YPASS2) {
+      if (h->variants & CA_VAR_YPASS3) {
+        CA_LAUNCH(k_ypass_k1_v3<T>, grid, 256, 0, st)(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
+      } else if (h->variants & CA_VAR_YPASS2) {
         CA_LAUNCH(k_ypass_k1_v2<T>, grid, 256, 0, st)(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
       } else if (st == h->stream && !getenv("CLONEALIGN_B200_YPASS_LIGHT")) {
         CA_LAUNCH(k_ypass_k1<T>, grid, 256, 0, st)(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
@@ -861,13 +863,15 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if (c.path == CA_PATH_INTERP && !(c.K == 1 && c.P == 0)) fail("interp path needs K == 1 and P == 0");
   h->interp = (c.path == CA_PATH_INTERP);
   h->variants = c.variants;
-  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_P2P | CA_VAR_OVERLAP))
+  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_P2P | CA_VAR_OVERLAP | CA_VAR_YPASS3))
     fail("unknown kernel variant bits 0x%x", c.variants);
   if ((c.variants & CA_VAR_P2P) && c.world > kP2PMaxWorld) fail("variant p2p supports at most %d ranks", kP2PMaxWorld);
   h->p2p = (c.variants & CA_VAR_P2P) && c.world > 1;
   if ((c.variants & CA_VAR_LEAN) && !(c.variants & CA_VAR_EPI2)) fail("variant lean needs variant epi2");
   h->lean = (c.variants & CA_VAR_LEAN) != 0;
   if ((c.variants & CA_VAR_YPASS2) && c.K + c.P != 1) fail("variant ypass2 needs K + P == 1");
+  if ((c.variants & CA_VAR_YPASS3) && c.K + c.P != 1) fail("variant ypass3 needs K + P == 1");
+  if ((c.variants & CA_VAR_YPASS3) && (c.variants & CA_VAR_YPASS2)) fail("variants ypass2 and ypass3 are alternatives");
   if (c.variants & CA_VAR_EPI2) {
     if (!h->interp) fail("variant epi2 belongs to the interp path (path = interp)");
     if (c.C > kFusedMaxC || c.S * c.C > 32 * kFusedMaxNJ) fail("variant epi2 needs C <= %d and S*C <= %d", kFusedMaxC, 32 * kFusedMaxNJ);
@@ -1039,7 +1043,10 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   h->elbo_dev = h->alloc<double>(1);
   h->ar = z((size_t)G * (2 + KP) + C + 4);
   if (KP == 1) {
-    h->nCB = (int)ceil_div64(h->ldY, kYCB);
+    int tile_cols = kYCB;
+    if (h->variants & CA_VAR_YPASS3)   // column tile of k_ypass_k1_v3: 256 threads x the columns a thread owns for this storage type
+      tile_cols = h->ystore == CA_STORE_U8 ? ypass3_tile_cols<uint8_t>() : (h->ystore == CA_STORE_U16 ? ypass3_tile_cols<uint16_t>() : ypass3_tile_cols<float>());
+    h->nCB = (int)ceil_div64(h->ldY, tile_cols);
     h->RB = 512;
   } else {
     h->nCB = 1;
@@ -1730,6 +1737,7 @@ int ca_core_ypass_many(ca_handle* const* hs, int32_t n, char* err, size_t errlen
       ca_handle* h = hs[i];
       if (!h) fail("null handle");
       if (h->KP != 1) fail("ca_core_ypass_many needs K + P == 1");
+      if ((h->variants & CA_VAR_YPASS3) && n > 1) fail("ca_core_ypass_many: the batched kernel uses the column tiling of ypass2 (sessions with variant ypass3 run their own pass)");
       if (h->Y != h0->Y || h->dev != h0->dev || h->N != h0->N || h->G != h0->G || h->ystore != h0->ystore)
         fail("ca_core_ypass_many: the sessions do not share one count matrix (create them with ca_core_create_shared)");
     }

@@ -298,6 +298,141 @@ k_ypass_k1_v2(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// v3 of the KP == 1 tile (variant YPASS3), from the SASS of v2 (538 warp instructions per 4096 counts for u8: 128 PRMT,
+// 128 FFMA2, 64 FADD2, 88 for the row butterfly, ~130 address / predicate / loop; issue-limited at ~0.23 ms for the
+// 2e9 counts of config 3, uncomfortably close to the 0.31 ms HBM floor):
+//   * integer counts are NOT converted: the byte (or half-word) is moved into the low bits of an otherwise zero word,
+//     which read as fp32 is the DENORMAL count * 2^-149, exactly.  NVIDIA FMA units take denormal operands at full rate
+//     and an FMA rounds once, after the exact product, so with the other operand pre-scaled by 2^100 (psi_n, w_g: one
+//     multiply per row / column, exact) every product and partial sum is the v2 value times 2^-49, in the normal range,
+//     with the same rounding (fp32 rounding is scale-invariant there); the partial sums are multiplied by 2^49 (exact)
+//     when they are stored.  Bit-identical to the widened arithmetic unless |w| or |psi| >= 2^27 (overflow) or a product
+//     is below 2^-77 (underflow); the magic-number FADD2 per pair of counts disappears;
+//   * u8: a thread owns 16 consecutive columns (one 16-byte load per row, 8 rows in flight) instead of 8, so the row
+//     butterfly, the loads of psi and the loop overhead are spread over twice the counts (CTA tile = 4096 columns).
+// Same partial-sum layouts (rowpart [nCB][N], colpart [nRB][G]) with nCB = ceil(ldY / (256 * kCols)); summation order
+// differs from v1 / v2 in the grouping of columns only.  ~340 warp instructions per 4096 u8 counts.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct Y3;
+template <> struct Y3<float> {
+  static constexpr int kCols = 8, kRows = 8;
+  static constexpr float kPre = 1.f, kPost = 1.f;
+  typedef YLoad<float>::Raw Raw;
+  static __device__ __forceinline__ Raw ld(const float* p) { return YLoad<float>::ld(p); }
+  static __device__ __forceinline__ Raw zero() { return YLoad<float>::zero(); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float2 (&o)[4]) { YLoad2<float>::unpack(r, o); }
+};
+template <> struct Y3<uint16_t> {
+  static constexpr int kCols = 8, kRows = 16;
+  static constexpr float kPre = 1.2676506002282294e30f /* 2^100 */, kPost = 562949953421312.f /* 2^49 */;
+  typedef uint4 Raw;
+  static __device__ __forceinline__ Raw ld(const uint16_t* p) { return __ldcs(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  static __device__ __forceinline__ float2 pair(uint32_t x) { return make_float2(__uint_as_float(x & 0xffffu), __uint_as_float(x >> 16)); }
+  static __device__ __forceinline__ void unpack(const Raw& a, float2 (&o)[4]) {
+    o[0] = pair(a.x); o[1] = pair(a.y); o[2] = pair(a.z); o[3] = pair(a.w);
+  }
+};
+template <> struct Y3<uint8_t> {
+  static constexpr int kCols = 16, kRows = 8;
+  static constexpr float kPre = 1.2676506002282294e30f /* 2^100 */, kPost = 562949953421312.f /* 2^49 */;
+  typedef uint4 Raw;
+  static __device__ __forceinline__ Raw ld(const uint8_t* p) { return __ldcs(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  static __device__ __forceinline__ float2 lo(uint32_t x) {
+    return make_float2(__uint_as_float(__byte_perm(x, 0u, 0x4440u)), __uint_as_float(__byte_perm(x, 0u, 0x4441u)));
+  }
+  static __device__ __forceinline__ float2 hi(uint32_t x) {
+    return make_float2(__uint_as_float(__byte_perm(x, 0u, 0x4442u)), __uint_as_float(x >> 24));
+  }
+  static __device__ __forceinline__ void unpack(const Raw& a, float2 (&o)[8]) {
+    o[0] = lo(a.x); o[1] = hi(a.x); o[2] = lo(a.y); o[3] = hi(a.y);
+    o[4] = lo(a.z); o[5] = hi(a.z); o[6] = lo(a.w); o[7] = hi(a.w);
+  }
+};
+template <typename T> constexpr int ypass3_tile_cols() { return 256 * Y3<T>::kCols; }
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+k_ypass_k1_v3(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, const float* __restrict__ U,
+              const float* __restrict__ Vm, float* __restrict__ rowpart, float* __restrict__ colpart) {
+  using L = Y3<T>;
+  constexpr int kRows = L::kRows, kCols = L::kCols, kPairs = kCols / 2;
+  __shared__ float red[2][8][kYMaxRows];
+  const int cb = blockIdx.x;
+  const int64_t rb = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t col0 = (int64_t)cb * (256 * kCols) + tid * kCols;
+  const bool colok = col0 < ldY;
+  float2 vr[kPairs], cacc[kPairs];
+#pragma unroll
+  for (int j = 0; j < kPairs; ++j) {
+    vr[j] = make_float2((col0 + 2 * j < G) ? Vm[col0 + 2 * j] * L::kPre : 0.f, (col0 + 2 * j + 1 < G) ? Vm[col0 + 2 * j + 1] * L::kPre : 0.f);
+    cacc[j] = make_float2(0.f, 0.f);
+  }
+  const int64_t rbeg = rb * RB, rend = (rbeg + RB < N) ? rbeg + RB : N;
+  const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const T* yp = Y + rbeg * ldY + col0;
+  int buf = 0;
+  for (int64_t r0 = rbeg; r0 < rend; r0 += kRows, yp += (int64_t)kRows * ldY) {
+    typename L::Raw raw[kRows];
+    if (colok && r0 + kRows <= rend) {       // full tile: no per-row predicates
+#pragma unroll
+      for (int i = 0; i < kRows; ++i) raw[i] = L::ld(yp + (int64_t)i * ldY);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kRows; ++i) raw[i] = (colok && r0 + i < rend) ? L::ld(yp + (int64_t)i * ldY) : L::zero();
+    }
+    float u[kRows];   // U is allocated with 64 elements of slack, r0 is a multiple of 4: vector loads stay in bounds
+#pragma unroll
+    for (int i = 0; i < kRows; i += 4) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(U + r0 + i));
+      u[i] = t4.x * L::kPre; u[i + 1] = t4.y * L::kPre; u[i + 2] = t4.z * L::kPre; u[i + 3] = t4.w * L::kPre;
+    }
+    float rp[(kRows + 7) / 8 * 8];
+#pragma unroll
+    for (int i = 0; i < (kRows + 7) / 8 * 8; ++i) rp[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+      float2 y[kPairs];
+      L::unpack(raw[i], y);
+      const float2 u2 = make_float2(u[i], u[i]);
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);   // two chains: the 8 pairs of a u8 row
+#pragma unroll
+      for (int j = 0; j < kPairs; j += 2) {
+        acc0 = __ffma2_rn(y[j], vr[j], acc0);
+        acc1 = __ffma2_rn(y[j + 1], vr[j + 1], acc1);
+        cacc[j] = __ffma2_rn(y[j], u2, cacc[j]);
+        cacc[j + 1] = __ffma2_rn(y[j + 1], u2, cacc[j + 1]);
+      }
+      const float2 a2 = __fadd2_rn(acc0, acc1);
+      rp[i] = a2.x + a2.y;
+    }
+#pragma unroll
+    for (int h = 0; h < (kRows + 7) / 8; ++h) {
+      float v8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v8[i] = rp[h * 8 + i];
+      float tot = butterfly8(v8, lane);
+      if ((lane & 3) == 0) red[buf][wid][h * 8 + ridx] = tot;
+    }
+    __syncthreads();
+    if (tid < kRows && r0 + tid < rend) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) acc += red[buf][w][tid];
+      rowpart[(int64_t)cb * N + r0 + tid] = acc * L::kPost;
+    }
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int j = 0; j < kPairs; ++j) {
+    if (col0 + 2 * j < G) colpart[rb * G + col0 + 2 * j] = cacc[j].x * L::kPost;
+    if (col0 + 2 * j + 1 < G) colpart[rb * G + col0 + 2 * j + 1] = cacc[j].y * L::kPost;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Batched Y pass for R fits that share one count matrix (restarts of run_clonealign on one device):
 // ONE stream over Y produces (Y W_r, Y^T psi_r) for every fit r -- the widening / magic-number work is shared and the
 // matrix leaves HBM once instead of R times.  Same tiling and partial layouts as k_ypass_k1_v2 (each fit's own rowpart /

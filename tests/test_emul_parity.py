@@ -16,7 +16,7 @@ pytestmark = pytest.mark.usefixtures("emulated_library")
 # (contraction path, kernel variants): the default kernels of both non-tensor paths and the re-engineered variants
 # (packed-fp32 Y pass, fused Clenshaw + per-cell epilogue) that bench.py validates on the device before using them
 PATHS = [("cudacore", ""), ("interp", ""), ("cudacore", "ypass2"), ("interp", "ypass2,epi2"), ("interp", "ypass2,epi2,lean"),
-         ("interp", "ypass2,epi2,lean,overlap")]
+         ("interp", "ypass2,epi2,lean,overlap"), ("cudacore", "ypass3"), ("interp", "ypass3,epi2,lean")]
 
 
 def test_emulated_library_is_not_the_product(emulated_library):
@@ -198,6 +198,12 @@ def test_storage_formats_and_input_layouts_agree(example_sce):
     packed = [run(hi["Y"], y_store=s, variants="ypass2") for s in ("f32", "u16", "u8")]      # f32x2 Y pass: same exactness
     assert packed[0].tobytes() == packed[1].tobytes() == packed[2].tobytes()
     assert np.abs(packed[0] - traces[0]).max() <= 1e-6 * np.abs(traces[0]).max()             # re-associated sums only
+    # ypass3: the stored integer is used as a denormal fp32 operand, the other operand carries the scale -> bit-identical to
+    # the arithmetic on widened counts (f32 storage runs the same tiling unscaled); u8 owns 16 columns per thread instead
+    # of 8, which only re-associates the row sums
+    y3 = [run(hi["Y"], y_store=s, variants="ypass3") for s in ("f32", "u16", "u8")]
+    assert y3[0].tobytes() == y3[1].tobytes()
+    assert np.abs(y3[2] - y3[0]).max() <= 1e-6 * np.abs(y3[0]).max() and np.abs(y3[0] - traces[0]).max() <= 1e-6 * np.abs(traces[0]).max()
     t_f = run(np.asfortranarray(hi["Y"]), y_store="f32")                    # an R double matrix
     t_i = run(np.asfortranarray(hi["Y"].astype(np.int32)))                  # an R integer matrix
     t_32 = run(hi["Y"].astype(np.float32))
@@ -245,6 +251,8 @@ def test_variant_validation(example_sce):
         assert sess.describe()["variants"] == 3
     with pytest.raises(CloneAlignLibraryError, match="lean needs variant epi2"):
         _session(d.Y, d.L, p.psi, mu_guess, path="interp", variants="lean")
+    with pytest.raises(CloneAlignLibraryError, match="ypass2 and ypass3 are alternatives"):
+        _session(d.Y, d.L, p.psi, mu_guess, variants="ypass2,ypass3")
 
 
 def test_variants_agree_with_default_kernels(example_sce):
@@ -485,12 +493,12 @@ def test_bench_selfcheck_gate_on_the_emulation():
     assert not ok and d["grad_psi"] < 1e-3      # same gradients, diverging trace
 
 
-@pytest.mark.parametrize("path", [("cudacore", "ypass2"), ("interp", "ypass2,epi2,lean")])
+@pytest.mark.parametrize("path", [("cudacore", "ypass2"), ("interp", "ypass2,epi2,lean"), ("interp", "ypass3,epi2,lean")])
 def test_several_row_and_column_tiles(path):
     """N > 2 row blocks of the Y pass (RB = 512), G > one 2048-column tile, more cells than one sweep of the persistent
     per-cell / per-gene kernels: tile seams, partial-sum layouts and strided loops."""
     from clonealign_b200.synthetic import make_synthetic
-    syn = make_synthetic(1100, 2300, 4, seed=8)
+    syn = make_synthetic(1100, 4500 if "ypass3" in path[1] else 2300, 4, seed=8)      # ypass3 / u8: 4096-column tiles
     d, p, mu_guess, _ = _case(syn["Y"].astype(np.float64), np.minimum(syn["L"], 6.0), K=1, seed=2)
     with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=2, K=1, path=path[0], variants=path[1], seed=1) as sess:
         _load_params(sess, p)
@@ -812,7 +820,7 @@ def test_random_shapes_and_variants():
         Y[Y.sum(1) == 0, 0] += 1.0
         d, p, mu_guess, _ = _case(Y, L, K=1, seed=it, scale=float(rng.choice([0.05, 0.3, 1.0])))
         p.psi *= float(rng.choice([0.5, 1.0, 3.0]))
-        var = str(rng.choice(["", "ypass2", "epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap"]))
+        var = str(rng.choice(["", "ypass2", "epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap", "ypass3", "ypass3,epi2,lean"]))
         with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path="interp", seed=1, variants=var) as sess:
             _load_params(sess, p)
             try:
@@ -872,4 +880,4 @@ def test_smoke_cases_on_the_emulation(capsys, monkeypatch):
     monkeypatch.setattr(g, "_smoke_case", lambda path, variants="": None)      # the in-process legs (tensor cores) are not emulated
     g.smoke()
     out = capsys.readouterr().out
-    assert out.count("NOT OK on this device (non-fatal") == 2
+    assert out.count("NOT OK on this device (non-fatal") == 3

@@ -18,7 +18,7 @@ from test_gpu_parity import ELBO_RTOL, PARAM_RTOL, _case, _check_grads, _load_pa
 pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="interp path not yet validated on hardware")]
 
 
-VARIANTS = ["", "ypass2", "epi2", "ypass2,epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap"]
+VARIANTS = ["", "ypass2", "epi2", "ypass2,epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap", "ypass3", "ypass3,epi2,lean"]
 
 
 @pytest.mark.parametrize("variants", VARIANTS)
@@ -33,7 +33,7 @@ def test_interp_gradients_and_elbo_match_oracle_c1(example_sce, S, variants):
         assert errs["Z"] < 1e-5
 
 
-@pytest.mark.parametrize("variants", ["", "ypass2,epi2", "ypass2,epi2,lean"])
+@pytest.mark.parametrize("variants", ["", "ypass2,epi2", "ypass2,epi2,lean", "ypass3,epi2,lean"])
 @pytest.mark.parametrize("N,G,C,S", [(130, 70, 5, 3), (257, 193, 2, 1), (64, 640, 7, 8), (1000, 333, 12, 8), (300, 4100, 32, 4)])
 def test_interp_ragged_shapes(N, G, C, S, variants):
     from clonealign_b200.synthetic import make_synthetic
@@ -44,14 +44,28 @@ def test_interp_ragged_shapes(N, G, C, S, variants):
         _check_grads(sess, d, p, S)
 
 
+@pytest.mark.parametrize("ypass", ["ypass2", "ypass3"])
 @pytest.mark.parametrize("path", ["tensor", "cudacore"])
-def test_packed_ypass_on_the_default_paths(example_sce, path):
-    """The f32x2 Y pass under the contraction kernels that round 1 validated on hardware."""
+def test_packed_ypass_on_the_default_paths(example_sce, path, ypass):
+    """The f32x2 Y passes under the contraction kernels that round 1 validated on hardware."""
     Y, L = example_sce
     d, p, mu_guess, _ = _case(Y, L, K=1, seed=2)
-    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=2, K=1, path=path, variants="ypass2", seed=1) as sess:
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=2, K=1, path=path, variants=ypass, seed=1) as sess:
         _load_params(sess, p)
         _check_grads(sess, d, p, 2)
+
+
+@pytest.mark.parametrize("path", ["tensor", "cudacore"])
+def test_ypass3_storage_formats_agree(example_sce, path):
+    """ypass3 feeds the stored integers to the packed FMA as DENORMAL fp32 operands (the other operand carries the scale):
+    bit-identical to the same tiling on fp32 storage unless the hardware flushed denormals; u8 (16 columns per thread) may
+    only differ by re-association."""
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
+    run = lambda s: _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], mc_samples=2, seed=7, path=path, variants="ypass3", y_store=s)[0]
+    f32, u16, u8 = run("f32"), run("u16"), run("u8")
+    assert np.all(np.isfinite(f32)) and f32.tobytes() == u16.tobytes()
+    assert np.abs(u8 - f32).max() <= 1e-6 * np.abs(f32).max()
 
 
 def test_interp_wide_range_uses_many_panels(example_sce):
@@ -206,7 +220,7 @@ def _full_size_check(N, G, C, S, path, variants, V=0, n_sample=48, z_tol=2e-6, w
         sess.close()
 
 
-@pytest.mark.parametrize("variants", ["", "ypass2,epi2,lean"])
+@pytest.mark.parametrize("variants", ["", "ypass2,epi2,lean", "ypass3,epi2,lean"])
 def test_full_size_c3_interp(variants):
     """BASELINE config 3 (100k x 20k x 12, S = 8) on the interpolation path: Z is near-exact (fp64 node sums), unlike the
     tcgen05 path's round-toward-zero accumulation."""
