@@ -425,6 +425,7 @@ def test_cell_sharded_fit_matches_single_shard(example_sce, path, world):
         for _ in range(3):
             sess.step()
             tr.append(sess.elbo())
+        tr += list(sess.elbo_many(2))                   # collective like elbo(): one all-reduce per evaluation
         out["elbo"], out["prm"] = np.array(tr), sess.params()
         sess.close()
 
