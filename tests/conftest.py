@@ -81,7 +81,7 @@ def _zz_run_function(path, func):
     env = dict(os.environ, CLONEALIGN_B200_ZZ_INNER="1")
     cmd = [sys.executable, "-m", "pytest", f"{path}::{func}", "-m", "gpu", "--runxfail", "-q", "-rA", "-p", "no:cacheprovider"]
     try:
-        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=420, cwd=ROOT)
         text, rc = out.stdout + "\n" + out.stderr[-2000:], out.returncode
     except subprocess.TimeoutExpired as e:
         text = (e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")) + "\nchild pytest timed out"
