@@ -402,7 +402,7 @@ def test_sparse_input_stays_compressed(example_sce):
 
 
 @pytest.mark.parametrize("path", [("cudacore", ""), ("interp", "ypass2,epi2,lean"), ("cudacore", "p2p"),
-                                  ("interp", "ypass2,epi2,lean,p2p")])
+                                  ("interp", "ypass2,epi2,lean,p2p"), ("interp", "ypass3,epi2,lean")])
 @pytest.mark.parametrize("world", [2, 3])
 def test_cell_sharded_fit_matches_single_shard(example_sce, path, world):
     """SURVEY 8e through the REAL sharded code path of core.cu: `world` ranks (threads of this process; the emulation
