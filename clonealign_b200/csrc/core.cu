@@ -1048,6 +1048,16 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
       tile_cols = h->ystore == CA_STORE_U8 ? ypass3_tile_cols<uint8_t>() : (h->ystore == CA_STORE_U16 ? ypass3_tile_cols<uint16_t>() : ypass3_tile_cols<float>());
     h->nCB = (int)ceil_div64(h->ldY, tile_cols);
     h->RB = 512;
+    if (h->variants & CA_VAR_YPASS3) {
+      // Size the row blocks so that the grid is (just under) a whole number of waves of the 2 CTAs an SM holds: with
+      // 512-row blocks config 3 gives 5 x 196 = 980 CTAs = 3.31 waves of 296, i.e. a last wave that is one third full
+      // on the kernel that bounds the step; 568-row blocks give 885 CTAs = 2.99 waves.  Small problems get enough row
+      // blocks to cover every SM.  Any multiple of 16 rows works (vector loads of psi, 8 / 16 rows in flight).
+      const int64_t slots = 2 * (int64_t)h->num_sms;
+      const int64_t waves = std::max<int64_t>(1, ceil_div64((int64_t)h->nCB * ceil_div64(N, 512), slots));
+      const int64_t nrb = std::max<int64_t>(1, waves * slots / h->nCB);
+      h->RB = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(16, round_up64(ceil_div64(N, nrb), 16)));
+    }
   } else {
     h->nCB = 1;
     h->RB = 1024;

@@ -24,7 +24,7 @@ namespace ca {
 constexpr int kIP = 16;            // Chebyshev nodes per panel (multiple of 8); with kIAmax = 4: ~6e-9 relative
 constexpr int kIMaxPanF = 64;      // forward panels (both signs of psi together)
 constexpr int kIMaxPanB = 64;      // backward panels over [w_min, w_max]
-constexpr int kISplitF = 16;       // fixed split of the gene reduction in the forward node kernel
+constexpr int kISplitF = 32;       // fixed split of the gene reduction in the forward node kernel (4 active node groups x 32 = 128 blocks)
 constexpr int kISplitB = 64;       // fixed split of the cell reduction in the backward node kernel
 constexpr int kIGroupsY = 8;       // grid.y of the node kernels: blocks stride over the ACTIVE groups of 8 nodes
 constexpr double kIAmax = 4.0;     // exponent half-range per panel
