@@ -71,10 +71,12 @@ def test_interp_kernels_match_direct_contraction(exe, sd_psi, sd_w, smem_panels,
 def test_results_do_not_depend_on_thread_scheduling(order):
     """Race check on the emulation: the threads of a block are visited last-to-first / in a fresh random permutation every
     scheduling round (CA_EMUL_ORDER).  A kernel that is missing a __syncthreads / __syncwarp, or whose reductions are not
-    in a fixed order, fails the parity or the bitwise-determinism tests under one of these orders."""
+    in a fixed order, fails the parity or the bitwise-determinism tests under one of these orders.  The two runs also report
+    1 and 148 multiprocessors (the default of the emulation is 3): the persistent kernels and the wave-fitted row blocks of
+    the Y pass size their grids and partial-sum buffers from that number."""
     import sys
-    env = dict(os.environ, CA_EMUL_ORDER=order)
-    sel = "gradients_and_elbo or same_seed or c3_column or cell_sharded"
+    env = dict(os.environ, CA_EMUL_ORDER=order, CA_EMUL_SMS="1" if order == "reverse" else "148")
+    sel = "gradients_and_elbo or same_seed or c3_column or cell_sharded or several_row"
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_emul_parity.py"), "-x", "-q", "-k", sel,
                           "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
