@@ -428,7 +428,22 @@ __global__ void __launch_bounds__(kGeneWarps * 32) k_gene_fused(GeneFusedArgs a)
   const double ih = pl.b_w > 0.0 ? 2.0 / pl.b_w : 0.0;
   const int nblk = gridDim.x - 1;
   const int SC = a.SC;
-  for (int g = blockIdx.x * kGeneWarps + wid; g < a.G; g += nblk * kGeneWarps) {
+  // Y^T psi partials of the Y pass, colpart [nRB][G]: the 16 genes a block works on in one round are consecutive, so
+  // the block sums their partials cooperatively -- thread (slice, gene) strides over the row blocks and reads 16
+  // consecutive floats per row block (whole 32-byte sectors) -- instead of every warp gathering its gene's nRB partials
+  // with a stride of G floats (one useful float per sector: 8x the traffic); slices are combined in a fixed order.
+  __shared__ double cpart[32][kGeneWarps];
+  for (int gbase = blockIdx.x * kGeneWarps; gbase < a.G; gbase += nblk * kGeneWarps) {   // block-uniform trip count
+    {
+      const int gi = threadIdx.x % kGeneWarps, sl = threadIdx.x / kGeneWarps;            // 512 threads = 32 slices x 16 genes
+      double part = 0.0;
+      if (gbase + gi < a.G)
+        for (int rb = sl; rb < a.nRB; rb += 32) part += (double)a.colpart[(int64_t)rb * a.G + gbase + gi];
+      cpart[sl][gi] = part;
+    }
+    __syncthreads();
+    const int g = gbase + wid;
+    if (g < a.G) {
     const float wf = a.Vm[g];
     const double x = (double)wf;
     int pb = (int)((x - pl.wmin) * ih * 0.5);
@@ -467,15 +482,15 @@ __global__ void __launch_bounds__(kGeneWarps * 32) k_gene_fused(GeneFusedArgs a)
     aloc = warp_sum(aloc);
     alsd = warp_sum(alsd);
     gv = warp_sum(gv);
-    double acc = 0.0;
-    for (int rb = lane; rb < a.nRB; rb += 32) acc += (double)a.colpart[(int64_t)rb * a.G + g];
-    acc = warp_sum(acc);
+    const double acc = warp_sum(cpart[lane][wid]);
     if (lane == 0) {
       a.YtU[g] = (float)acc;
       a.ar[2 * (int64_t)a.G + g] = (float)(acc + gv);
       a.ar[g] = (float)aloc;
       a.ar[a.G + g] = (float)alsd;
     }
+    }
+    __syncthreads();   // cpart is rewritten by the next round
   }
 }
 
