@@ -106,7 +106,7 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
                     saturate_=True, saturation_threshold=6, K=1, mc_samples=1, verbose=True, initial_shrink=5,
                     data_init_mu=True, seed=None, device=0, psi_init=None, y_store="auto", path="auto",
                     gene_names=None, variants=None, correlations_with=None, device_pca=False, cache=None,
-                    device_stats=False):
+                    device_stats=False, batch_final_elbo=False):
     """The fit of `inference_tflow` as a generator: it yields its `Session` every time the parameters have just changed
     and the next operation is an ELBO evaluation (after gamma-init and after every train step), i.e. exactly where one
     batched pass over a shared count matrix can serve several restarts (`session.ypass_many`; `run_clonealign(
@@ -128,6 +128,9 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
     `device_stats=True` (needs `cache`): s_init = rowSums(Y) (:210) and mu_guess = colMeans(Y / rowMeans(Y)) (:222) come from
     the resident matrix (ca_core_data_stats, fp64) instead of host passes over the N x G matrix; mu_guess then agrees with
     the host value to ~1e-15 relative (different summation order), so fits are no longer bit-identical to host-initialised ones.
+    `batch_final_elbo=True`: the 20 fresh-draw ELBO evaluations behind final_elbo / sd_final_elbo (:447-449) are queued on the
+    stream and fetched with one device-to-host copy (ca_core_elbo_many): same draws, bit-identical values; opt-in like the other
+    entry points that have not run on hardware yet.
     `correlations_with = (L_unsaturated, clone_call_probability)`: also run the caller's post-hoc
     `compute_correlations` (R/clonealign.R:292-294,318-334) on the device while Y is still resident; the result is
     returned under "correlations" (retained genes only).
@@ -283,7 +286,10 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
         rlist = sess.params()                                                         # :424-434
         clone_probs_from_snv = rlist.pop("clone_probs_from_snv", None)                # :436-440
         _message(verbose, "Computing final ELBO")
-        final_elbo = [float(e) for e in sess.elbo_many(20)]                           # :447-449, one host round trip
+        if batch_final_elbo:
+            final_elbo = [float(e) for e in sess.elbo_many(20)]                       # :447-449, one host round trip
+        else:
+            final_elbo = [sess.elbo() for _ in range(20)]                             # :447-449
         if correlations_with is not None:
             L_full, call_p = correlations_with
             cp = rlist["clone_probs"]

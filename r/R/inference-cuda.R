@@ -9,11 +9,12 @@
 #                 (ca_create_sparse) instead of Y_dat = t(as.matrix(assay(...))) (R/clonealign.R:217)
 #   device_pca  : pcs (R/inference-tflow.R:203-205) from ca_pca_scores on the resident Y; scale() and the rnorm noise
 #                 (:205-207) stay in R, so set.seed() governs the same draws (pass pcs = NULL)
+#   batch_final_elbo : the 20 evaluations behind final_elbo (:447-449) with one device-to-host copy (ca_elbo_many); same values
 #   cor_with    : list(L = unsaturated copy number of the retained genes, p = clone_call_probability): run
 #                 compute_correlations (R/clonealign.R:292-294,318-334) on the device before the session closes
 inference_cuda_session <- function(Y_dat, L_dat, pcs, mu_guess, x, clone_allele, alt, cov,
                                    learning_rate, K, mc_samples, max_iter, rel_tol, verbose,
-                                   counts_dgC = NULL, device_pca = FALSE, cor_with = NULL) {
+                                   counts_dgC = NULL, device_pca = FALSE, cor_with = NULL, batch_final_elbo = FALSE) {
   N <- if (is.null(counts_dgC)) nrow(Y_dat) else ncol(counts_dgC)
   G <- if (is.null(counts_dgC)) ncol(Y_dat) else nrow(counts_dgC)
   C <- ncol(L_dat)
@@ -55,7 +56,8 @@ inference_cuda_session <- function(Y_dat, L_dat, pcs, mu_guess, x, clone_allele,
     if (mean(abs(elbo_diffs)) < rel_tol) break             # :414
   }
   rlist <- .Call("ca_params", sess, c(N, G, C, as.integer(K), P, V))   # :424-440
-  final_elbo <- .Call("ca_elbo_many", sess, 20L)           # :447-449 (20 fresh-draw evaluations, one round trip)
+  final_elbo <- if (batch_final_elbo) .Call("ca_elbo_many", sess, 20L)   # 20 fresh-draw evaluations, one round trip
+                else replicate(20, .Call("ca_elbo", sess))               # :447-449
   correlations <- NULL
   if (!is.null(cor_with)) {                                # clone_assignment (:22-29) as 0-based indices, -1 = unassigned
     cp <- rlist$clone_probs

@@ -882,3 +882,19 @@ def test_smoke_cases_on_the_emulation(capsys, monkeypatch):
     g.smoke()
     out = capsys.readouterr().out
     assert out.count("NOT OK on this device (non-fatal") == 3
+
+
+def test_clonealign_batched_final_elbo_is_identical(example_sce):
+    """clonealign(batch_final_elbo=True): final_elbo / sd_final_elbo from ca_core_elbo_many equal the default (20 separate
+    ca_core_elbo calls) bit for bit, and nothing else of the fit changes."""
+    import warnings
+    from clonealign_b200 import clonealign
+    Y, L = example_sce
+    kw = dict(max_iter=4, verbose=False, seed=11, path="interp", variants="ypass3,epi2,lean")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = clonealign(Y, L, **kw)
+        b = clonealign(Y, L, batch_final_elbo=True, **kw)
+    ca, cb = a["convergence_info"], b["convergence_info"]
+    assert ca["final_elbo"] == cb["final_elbo"] and ca["sd_final_elbo"] == cb["sd_final_elbo"] and ca["sd_final_elbo"] > 0
+    assert ca["elbo"].tobytes() == cb["elbo"].tobytes() and a["clone"] == b["clone"]

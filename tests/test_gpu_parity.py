@@ -225,26 +225,6 @@ def test_same_seed_bitwise_identical(example_sce, path):
     assert a.tobytes() != c.tobytes()
 
 
-@pytest.mark.parametrize("path", PATHS)
-def test_elbo_many_equals_repeated_elbo(example_sce, path):
-    """The 20 fresh-draw evaluations behind final_elbo (R/inference-tflow.R:447-449) queued with one host round trip
-    (ca_core_elbo_many) are bit-for-bit the values of repeated ca_core_elbo calls and leave the same state behind."""
-    Y, L = example_sce
-    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(2))
-
-    def run(many):
-        with _session(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], mc_samples=2, K=1, seed=31, path=path) as sess:
-            sess.init_gamma()
-            sess.step()
-            e = sess.elbo_many(20) if many else np.array([sess.elbo() for _ in range(20)])
-            sess.step()
-            return e, sess.elbo()
-    a, a_next = run(True)
-    b, b_next = run(False)
-    assert a.tobytes() == b.tobytes() and a_next == b_next
-    assert len(set(a.tolist())) == 20
-
-
 def test_storage_formats_agree(example_sce):
     """u8 / u16 / f32 storage of the integer counts are exact representations: identical traces."""
     Y, L = example_sce

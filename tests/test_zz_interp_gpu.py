@@ -282,3 +282,23 @@ def test_long_loop_stays_within_north_star_tolerances(example_sce, path, variant
     assert O.clone_assignment(prm["clone_probs"], names) == O.clone_assignment(r["clone_probs"], names)
     assert _relmax(prm["mu"], r["mu"]) <= PARAM_RTOL and _relmax(prm["psi"], r["params"].psi) <= PARAM_RTOL
     assert np.abs(prm["clone_probs"] - r["clone_probs"]).max() <= 2e-3
+
+
+@pytest.mark.parametrize("path,variants", [("tensor", ""), ("cudacore", ""), ("interp", "ypass3,epi2,lean")])
+def test_elbo_many_equals_repeated_elbo(example_sce, path, variants):
+    """The 20 fresh-draw evaluations behind final_elbo (R/inference-tflow.R:447-449) queued with one host round trip
+    (ca_core_elbo_many) are bit-for-bit the values of repeated ca_core_elbo calls and leave the same state behind."""
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(2))
+
+    def run(many):
+        with _session(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], mc_samples=2, K=1, seed=31, path=path, variants=variants) as sess:
+            sess.init_gamma()
+            sess.step()
+            e = sess.elbo_many(20) if many else np.array([sess.elbo() for _ in range(20)])
+            sess.step()
+            return e, sess.elbo()
+    a, a_next = run(True)
+    b, b_next = run(False)
+    assert a.tobytes() == b.tobytes() and a_next == b_next
+    assert len(set(a.tolist())) == 20
