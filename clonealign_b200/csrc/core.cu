@@ -1051,8 +1051,9 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     if (h->variants & CA_VAR_YPASS3) {
       // Size the row blocks so that the grid is (just under) a whole number of waves of the 2 CTAs an SM holds: with
       // 512-row blocks config 3 gives 5 x 196 = 980 CTAs = 3.31 waves of 296, i.e. a last wave that is one third full
-      // on the kernel that bounds the step; 568-row blocks give 885 CTAs = 2.99 waves.  Small problems get enough row
-      // blocks to cover every SM.  Any multiple of 16 rows works (vector loads of psi, 8 / 16 rows in flight).
+      // on the kernel that bounds the step; 432-row blocks give 5 x 232 = 1160 CTAs = 3.92 waves.  Small problems get
+      // enough row blocks to cover every SM (10k x 5k: 250 CTAs instead of 40).  Any multiple of 16 rows works (vector
+      // loads of psi, 8 / 16 rows in flight).
       const int64_t slots = 2 * (int64_t)h->num_sms;
       const int64_t waves = std::max<int64_t>(1, ceil_div64((int64_t)h->nCB * ceil_div64(N, 512), slots));
       const int64_t nrb = std::max<int64_t>(1, waves * slots / h->nCB);
@@ -1796,9 +1797,11 @@ int ca_core_describe(ca_handle* h, char* json, size_t json_len) {
   snprintf(json, json_len,
            "{\"N\": %lld, \"G\": %d, \"C\": %d, \"S\": %d, \"K\": %d, \"P\": %d, \"path\": \"%s\", \"y_store\": \"%s\", "
            "\"y_bytes_per_entry\": %d, \"ldY\": %lld, \"launches_last_step\": %d, \"nsplit\": %d, \"fsplit\": %d, "
-           "\"SCp\": %d, \"J\": %d, \"world\": %d, \"rank\": %d, \"variants\": %u}",
+           "\"SCp\": %d, \"J\": %d, \"world\": %d, \"rank\": %d, \"variants\": %u, \"ypass_grid\": [%d, %d], \"ypass_rows_per_block\": %d, "
+           "\"num_sms\": %d}",
            (long long)h->N, h->G, h->C, h->S, h->K, h->P, h->interp ? "interp" : (h->tc ? "tcgen05" : "cudacore"), st, bpe, (long long)h->ldY,
-           h->launches_last_step, h->nsplit, h->tc ? h->tcplan.fsplit : 1, h->SCp, h->J, h->cfg.world, h->cfg.rank, h->variants);
+           h->launches_last_step, h->nsplit, h->tc ? h->tcplan.fsplit : 1, h->SCp, h->J, h->cfg.world, h->cfg.rank, h->variants, h->nCB, h->nRB, h->RB,
+           h->num_sms);
   return 0;
 }
 
