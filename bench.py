@@ -541,6 +541,7 @@ def run_ours(args, cfg):
                            "K": 1, "sharding": f"cells/{world}", "path": desc["path"], "variants": variants, "y_store": desc["y_store"],
                            "l2": "inputs larger than L2 (Y shard >> 126 MB)", "psi_init": "random normal (PCA skipped)",
                            "path_requested": args.path, "selfcheck": selfcheck,
+                           "ypass_grid": desc.get("ypass_grid"), "ypass_rows_per_block": desc.get("ypass_rows_per_block"),
                            "fallback_after_error": os.environ.get("CLONEALIGN_B200_BENCH_FALLBACK"),
                            "elbo_start": e_start, "elbo_end": e_end},
                 "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "step_hbm": step_hbm,
