@@ -13,7 +13,7 @@ timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -p no:cachepr
 echo "== 2. new kernels (xfail-tolerant file, run strictly here: --runxfail turns XFAIL/XPASS into real verdicts)"
 timeout 900 python -m pytest tests/test_zz_interp_gpu.py -m gpu -q --runxfail -p no:cacheprovider > $O/r02_t_new.log 2>&1; tail -15 $O/r02_t_new.log
 echo "== 3. memcheck on a small case, every variant set"
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_interp_gpu.py -m gpu -q --runxfail \
+timeout 900 compute-sanitizer --tool memcheck --target-processes all --error-exitcode 9 python -m pytest tests/test_zz_interp_gpu.py -m gpu -q --runxfail \
   -k "ragged and 130 or correlations or pca or sparse" -p no:cacheprovider > $O/r02_sanitizer.log 2>&1
 echo "rc=$?"; tail -3 $O/r02_sanitizer.log
 echo "== 4. candidate table at c3 (self-check child: verdict + ms/step per candidate)"
