@@ -170,7 +170,7 @@ def run_reference(args, cfg):
 CANDIDATES = [("interp", ""), ("interp", "ypass2"), ("interp", "epi2"), ("interp", "ypass2,epi2"), ("interp", "epi2,lean"),
               ("interp", "ypass2,epi2,lean"), ("interp", "ypass2,epi2,lean,overlap"), ("auto", "ypass2"),
               ("interp", "ypass3"), ("interp", "ypass3,epi2"), ("interp", "ypass3,epi2,lean"), ("interp", "ypass3,epi2,lean,overlap"),
-              ("auto", "ypass3")]
+              ("auto", "ypass3"), ("interp", "ypass3,epi2,lean,defer"), ("interp", "ypass3,epi2,lean,defer,overlap")]
 # Gate = what the parity tests assert at small sizes, evaluated at full size against the tcgen05 path: ELBO (1e-4, north
 # star) and every gradient AT IDENTICAL PARAMETERS AND DRAWS (4e-3 of the array's max magnitude: both sides are within 2e-3
 # of the oracle in tests/test_gpu_parity.py), then a 3-step ELBO trace and the clone calls.  Parameters after Adam steps

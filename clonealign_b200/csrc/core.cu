@@ -240,6 +240,9 @@ struct ca_handle {
   uint32_t variants = 0;           // enum ca_variant bits
   bool epi2 = false;               // interp path: fused Clenshaw + per-cell epilogue (kernels_fused.cuh)
   bool lean = false;               // with epi2: k_prologue / k_gene_fused / k_adam_all
+  bool defer = false;              // with lean: Y-linear terms added after the per-cell kernel (late join of the Y pass)
+  bool pending_join = false;       // a Y pass forked onto stream2 has not been joined yet
+  int n_yv_blocks = 0;             // ELBO partials written by k_yv_dot (behind the per-cell kernel's in elbo_part)
   double* chi_cur = nullptr;
   float* pmm_part = nullptr;
   unsigned* ticket = nullptr;
@@ -438,6 +441,16 @@ void launch_interp_nodes(ca_handle* h, int nsplit, const float* rv, const float*
   }
 }
 
+// the partial sums of the Y pass are needed from here on: wait for the pass forked onto stream2, or run it now
+void join_ypass(ca_handle* h, int mode) {
+  if (h->pending_join) {
+    CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    h->pending_join = false;
+  } else if (mode != EPI_INIT) {
+    run_ypass(h, h->stream);
+  }
+}
+
 template <int MODE>
 void launch_fused_mode(ca_handle* h, const FusedArgs& a) {
   const unsigned grid = (unsigned)h->n_cell_parts;
@@ -542,8 +555,8 @@ void run_forward(ca_handle* h, int mode) {
     }
     KCHECK();
   }
-  if (joined_later) CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-  else if (mode != EPI_INIT) run_ypass(h, h->stream);
+  h->pending_join = joined_later;
+  if (!h->defer) join_ypass(h, mode);
   if (h->epi2) {
     LaunchScope ls(h, mode == EPI_TRAIN ? "cell_epilogue" : (mode == EPI_EVAL ? "cell_epilogue_eval" : "gamma_init"));
     FusedArgs a;
@@ -553,8 +566,15 @@ void run_forward(ca_handle* h, int mode) {
     a.t = h->t; a.gT = h->g_t; a.Rx = h->Rx; a.gU = h->g_U; a.YV = h->YV; a.Fout = h->Fout; a.shift = h->shift;
     a.Zx = h->inspect ? h->Zx : nullptr;
     a.elbo_part = h->elbo_part; a.gsum_part = h->gsum_part;
+    a.defer_yv = h->defer ? 1 : 0;
     launch_fused(h, mode, a);
     KCHECK();
+    if (h->defer && mode == EPI_EVAL) {   // the ELBO needs sum_n psi_n (YW)_n now; a train step joins before k_gene_fused
+      join_ypass(h, mode);
+      LaunchScope ls2(h, "yv_dot");
+      CA_LAUNCH(k_yv_dot, h->n_yv_blocks, 256, 0, h->stream)(h->N, h->nCB, h->rowpart, h->U, h->YV, h->elbo_part + h->n_cell_parts);
+      KCHECK();
+    }
   } else {
     LaunchScope ls(h, mode == EPI_TRAIN ? "cell_epilogue" : (mode == EPI_EVAL ? "cell_epilogue_eval" : "gamma_init"));
     EpiArgs a;
@@ -592,6 +612,7 @@ void run_train(ca_handle* h, bool apply) {
     }
     KCHECK();
   }
+  if (h->defer) join_ypass(h, EPI_TRAIN);   // colpart (gene gradients) and rowpart (d psi in k_adam_all) are needed from here on
   if (h->lean) {
     LaunchScope ls(h, "gene_grads", 1);
     GeneFusedArgs a;
@@ -649,7 +670,8 @@ void run_train(ca_handle* h, bool apply) {
       aa.ga = ga; aa.chi_cur = h->chi_cur; aa.sa = sa; aa.N = h->N; aa.C = h->C;
       aa.t = h->t; aa.m_t = h->m_t; aa.v_t = h->v_t; aa.U = h->U; aa.m_U = h->m_U; aa.v_U = h->v_U; aa.gT = h->g_t; aa.gU = h->g_U;
       aa.n_gene_blocks = (h->G + 255) / 256;
-      aa.n_cell_blocks = apply ? ceil_div64(h->N * h->C + h->N, 256) : 0;
+      aa.n_cell_blocks = (apply || h->defer) ? ceil_div64(h->N * h->C + h->N, 256) : 0;
+      aa.defer_yv = h->defer ? 1 : 0; aa.nCB = h->nCB; aa.rowpart = h->rowpart; aa.YV = h->YV;
       CA_LAUNCH(k_adam_all, (unsigned)(aa.n_gene_blocks + aa.n_cell_blocks + 1), 256, 0, h->stream)(aa);
       KCHECK();
     } else {
@@ -676,7 +698,7 @@ void run_elbo_async(ca_handle* h) {
   h->launches_last_step = 0;
   run_forward(h, EPI_EVAL);
   LaunchScope ls(h, "elbo_reduce", 2);
-  CA_LAUNCH(k_reduce_partials, 1, 1024, 0, h->stream)(h->elbo_part, h->n_cell_parts, 1, h->cell_sum, h->const_sum);
+  CA_LAUNCH(k_reduce_partials, 1, 1024, 0, h->stream)(h->elbo_part, h->n_cell_parts + h->n_yv_blocks, 1, h->cell_sum, h->const_sum);
   KCHECK();
   if (h->cfg.world > 1) NCCL_OK(nccl().AllReduce(h->cell_sum, h->cell_sum, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
   CA_LAUNCH(k_elbo_final, 1, 256, 0, h->stream)(h->cell_sum, h->gene_part, h->n_gene_blocks, h->scal_elbo, h->poison, h->elbo_dev);
@@ -863,12 +885,14 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if (c.path == CA_PATH_INTERP && !(c.K == 1 && c.P == 0)) fail("interp path needs K == 1 and P == 0");
   h->interp = (c.path == CA_PATH_INTERP);
   h->variants = c.variants;
-  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_P2P | CA_VAR_OVERLAP | CA_VAR_YPASS3))
+  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_P2P | CA_VAR_OVERLAP | CA_VAR_YPASS3 | CA_VAR_DEFER))
     fail("unknown kernel variant bits 0x%x", c.variants);
   if ((c.variants & CA_VAR_P2P) && c.world > kP2PMaxWorld) fail("variant p2p supports at most %d ranks", kP2PMaxWorld);
   h->p2p = (c.variants & CA_VAR_P2P) && c.world > 1;
   if ((c.variants & CA_VAR_LEAN) && !(c.variants & CA_VAR_EPI2)) fail("variant lean needs variant epi2");
   h->lean = (c.variants & CA_VAR_LEAN) != 0;
+  if ((c.variants & CA_VAR_DEFER) && !(c.variants & CA_VAR_LEAN)) fail("variant defer needs variants epi2 and lean");
+  h->defer = (c.variants & CA_VAR_DEFER) != 0;
   if ((c.variants & CA_VAR_YPASS2) && c.K + c.P != 1) fail("variant ypass2 needs K + P == 1");
   if ((c.variants & CA_VAR_YPASS3) && c.K + c.P != 1) fail("variant ypass3 needs K + P == 1");
   if ((c.variants & CA_VAR_YPASS3) && (c.variants & CA_VAR_YPASS2)) fail("variants ypass2 and ypass3 are alternatives");
@@ -1037,7 +1061,8 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   h->n_epi_blocks = ceil_div64(N, kEpiWarps);
   h->n_cell_parts = h->epi2 ? (int64_t)h->num_sms : h->n_epi_blocks;
   h->gene_part = h->alloc<double>(h->n_gene_blocks);
-  h->elbo_part = h->alloc<double>(h->n_cell_parts);
+  h->n_yv_blocks = h->defer ? h->num_sms : 0;
+  h->elbo_part = h->alloc<double>(h->n_cell_parts + h->n_yv_blocks);
   h->gsum_part = h->alloc<double>((size_t)h->n_cell_parts * C);
   h->scal_elbo = h->alloc<double>(1); h->cell_sum = h->alloc<double>(1); h->wsq = h->alloc<double>(std::max(K, 1));
   h->elbo_dev = h->alloc<double>(1);

@@ -29,6 +29,7 @@ constexpr int kFusedPitch = kIP + 1;     // doubles per (panel, column) row of t
 struct FusedArgs {
   int64_t N;
   int C, S, SC, J, nCB, smem_panels;
+  int defer_yv;                          // variant DEFER: the Y-linear terms are added later (k_adam_all / k_yv_dot)
   const InterpPlan* plan;
   const double* coeff;                   // [panel][kIP][J]
   const float* mm;                       // (w_min, w_max)
@@ -213,10 +214,14 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused(FusedArgs a)
     const double sumGH = warp_sum(gh);
     if (cok && a.Fout) a.Fout[n * C + lane] = (float)F;
     // ---- Y-linear term psi_n (YW)_n and the N(0,1) prior on psi (:318-319) ----
+    // (variant DEFER: this kernel does not read the Y-pass partials at all, so that it can run before / next to the Y pass;
+    // psi_n (YW)_n joins the ELBO in k_yv_dot and (YW)_n joins d psi_n in k_adam_all)
     double yv = 0.0;
-    for (int cb = lane; cb < a.nCB; cb += 32) yv += (double)a.rowpart[(int64_t)cb * a.N + n];
-    yv = warp_sum(yv);
-    if (lane == 0 && a.YV) a.YV[n] = (float)yv;
+    if (!a.defer_yv) {
+      for (int cb = lane; cb < a.nCB; cb += 32) yv += (double)a.rowpart[(int64_t)cb * a.N + n];
+      yv = warp_sum(yv);
+      if (lane == 0 && a.YV) a.YV[n] = (float)yv;
+    }
     elbo_w += sumGH + x * yv - 0.5 * x * x - 0.5 * kLog2Pi;
     if (MODE == EPI_TRAIN) {
       gacc += g;
@@ -506,9 +511,13 @@ struct AdamAllArgs {
   int64_t N;
   int C;
   float *t, *m_t, *v_t, *U, *m_U, *v_U;
-  const float *gT, *gU;
+  const float* gT;
+  float* gU;                 // written back in full when the Y-linear term was deferred
   int n_gene_blocks;
   int64_t n_cell_blocks;
+  int defer_yv, nCB;         // variant DEFER: d psi_n += (YW)_n = sum_cb rowpart[cb][n] (fixed order)
+  const float* rowpart;
+  float* YV;
 };
 __global__ void __launch_bounds__(256) k_adam_all(AdamAllArgs a) {
   const int64_t b = blockIdx.x;
@@ -539,11 +548,22 @@ __global__ void __launch_bounds__(256) k_adam_all(AdamAllArgs a) {
       adam_update(q.Vm[g], q.m_V[g], q.v_V[g], gw, q.h);
     }
   } else if (b < a.n_gene_blocks + a.n_cell_blocks) {
-    if (!a.ga.h.apply) return;
     const int64_t i = (b - a.n_gene_blocks) * blockDim.x + threadIdx.x;
     const int64_t nt = a.N * a.C;
-    if (i < nt) adam_update(a.t[i], a.m_t[i], a.v_t[i], a.gT[i], a.ga.h);
-    else if (i - nt < a.N) adam_update(a.U[i - nt], a.m_U[i - nt], a.v_U[i - nt], a.gU[i - nt], a.ga.h);
+    if (i < nt) {
+      if (a.ga.h.apply) adam_update(a.t[i], a.m_t[i], a.v_t[i], a.gT[i], a.ga.h);
+    } else if (i - nt < a.N) {
+      const int64_t n = i - nt;
+      float g = a.gU[n];
+      if (a.defer_yv) {
+        double yv = 0.0;
+        for (int cb = 0; cb < a.nCB; ++cb) yv += (double)a.rowpart[(int64_t)cb * a.N + n];
+        g = (float)((double)g + yv);
+        a.gU[n] = g;
+        if (a.YV) a.YV[n] = (float)yv;
+      }
+      if (a.ga.h.apply) adam_update(a.U[n], a.m_U[n], a.v_U[n], g, a.ga.h);
+    }
   } else if (threadIdx.x == 0) {
     const ScalarAdamArgs& q = a.sa;
     const double chi = exp((double)q.chi_raw[0]);
@@ -567,6 +587,23 @@ __global__ void __launch_bounds__(256) k_adam_all(AdamAllArgs a) {
       for (int c = 0; c < q.C; ++c) adam_update(q.u[c], q.m_u[c], q.v_u[c], q.g_u[c], q.h);
     }
   }
+}
+
+// variant DEFER, ELBO evaluations: sum_n psi_n (YW)_n from the Y-pass row partials, one fixed-order partial per block
+__global__ void __launch_bounds__(256) k_yv_dot(int64_t N, int nCB, const float* __restrict__ rowpart, const float* __restrict__ U,
+                                                float* __restrict__ YV, double* __restrict__ part_out) {
+  __shared__ double scratch[32];
+  const int64_t chunk = (N + gridDim.x - 1) / gridDim.x;
+  const int64_t beg = (int64_t)blockIdx.x * chunk, end = beg + chunk < N ? beg + chunk : N;
+  double acc = 0.0;
+  for (int64_t n = beg + threadIdx.x; n < end; n += blockDim.x) {
+    double yv = 0.0;
+    for (int cb = 0; cb < nCB; ++cb) yv += (double)rowpart[(int64_t)cb * N + n];
+    if (YV) YV[n] = (float)yv;
+    acc += (double)U[n] * yv;
+  }
+  const double t = block_sum(acc, scratch);
+  if (threadIdx.x == 0) part_out[blockIdx.x] = t;
 }
 
 }  // namespace ca

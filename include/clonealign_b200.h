@@ -80,13 +80,16 @@ enum ca_path     { CA_PATH_AUTO = 0, CA_PATH_CUDACORE = 1, CA_PATH_TENSOR = 2, C
  *   YPASS3: Y pass without a conversion of the integer counts (the stored byte / half-word is used as a denormal fp32
  *           operand of the packed FMA, the other operand carries the scale) and 16 columns per thread for u8 storage;
  *           alternative to YPASS2, see kernels_ypass.cuh
+ *   DEFER : (with EPI2 + LEAN) the per-cell kernel does not read the Y-pass partials: psi_n (YW)_n joins the ELBO and (YW)_n
+ *           joins d psi_n afterwards (k_yv_dot, k_adam_all), so the Y pass is joined only before the gene-gradient kernel and,
+ *           with OVERLAP, runs next to the per-cell kernel and the backward node sums instead of before them
  *   EPI2  : (interp path) Clenshaw evaluation fused into a leaner per-cell epilogue, see kernels_fused.cuh
  *   LEAN  : (with EPI2) gene-level / scalar / optimiser work in 3 launches instead of 12, see kernels_fused.cuh
  *   P2P   : (world > 1) the per-step all-reduce as one kernel over NVLink peer memory instead of ncclAllReduce; needs
  *           ca_core_p2p_export / ca_core_p2p_connect after ca_core_create, see kernels_p2p.cuh
  *   OVERLAP: the Y pass (HBM-bound; needs only Y, psi, W) is forked onto a second stream at the start of the step and
  *           joined before the per-cell kernel, so it runs next to the small gene-level launches instead of after them */
-enum ca_variant  { CA_VAR_YPASS2 = 1, CA_VAR_EPI2 = 2, CA_VAR_LEAN = 4, CA_VAR_P2P = 8, CA_VAR_OVERLAP = 16, CA_VAR_YPASS3 = 32 };
+enum ca_variant  { CA_VAR_YPASS2 = 1, CA_VAR_EPI2 = 2, CA_VAR_LEAN = 4, CA_VAR_P2P = 8, CA_VAR_OVERLAP = 16, CA_VAR_YPASS3 = 32, CA_VAR_DEFER = 64 };
 
 typedef struct ca_config {
   int64_t N;            /* cells held by this handle (this rank's shard)                       */

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.usefixtures("emulated_library")
 # (the epi2-only and overlap sets are covered by test_random_shapes_and_variants, test_variants_agree_with_default_kernels and
 # bench.py's candidate tests: on the synchronous emulation `overlap` only changes which stream handle a launch names)
 PATHS = [("cudacore", ""), ("interp", ""), ("cudacore", "ypass2"), ("interp", "ypass2,epi2,lean"), ("cudacore", "ypass3"),
-         ("interp", "ypass3,epi2,lean")]
+         ("interp", "ypass3,epi2,lean"), ("interp", "ypass3,epi2,lean,defer")]
 
 
 def test_emulated_library_is_not_the_product(emulated_library):
@@ -253,6 +253,8 @@ def test_variant_validation(example_sce):
         assert sess.describe()["variants"] == 3
     with pytest.raises(CloneAlignLibraryError, match="lean needs variant epi2"):
         _session(d.Y, d.L, p.psi, mu_guess, path="interp", variants="lean")
+    with pytest.raises(CloneAlignLibraryError, match="defer needs variants epi2 and lean"):
+        _session(d.Y, d.L, p.psi, mu_guess, path="interp", variants="epi2,defer")
     with pytest.raises(CloneAlignLibraryError, match="ypass2 and ypass3 are alternatives"):
         _session(d.Y, d.L, p.psi, mu_guess, variants="ypass2,ypass3")
 
@@ -404,7 +406,8 @@ def test_sparse_input_stays_compressed(example_sce):
 
 
 @pytest.mark.parametrize("path", [("cudacore", ""), ("interp", "ypass2,epi2,lean"), ("cudacore", "p2p"),
-                                  ("interp", "ypass2,epi2,lean,p2p"), ("interp", "ypass3,epi2,lean")])
+                                  ("interp", "ypass2,epi2,lean,p2p"), ("interp", "ypass3,epi2,lean"),
+                                  ("interp", "ypass3,epi2,lean,defer,overlap")])
 @pytest.mark.parametrize("world", [2, 3])
 def test_cell_sharded_fit_matches_single_shard(example_sce, path, world):
     """SURVEY 8e through the REAL sharded code path of core.cu: `world` ranks (threads of this process; the emulation
@@ -823,7 +826,8 @@ def test_random_shapes_and_variants():
         Y[Y.sum(1) == 0, 0] += 1.0
         d, p, mu_guess, _ = _case(Y, L, K=1, seed=it, scale=float(rng.choice([0.05, 0.3, 1.0])))
         p.psi *= float(rng.choice([0.5, 1.0, 3.0]))
-        var = str(rng.choice(["", "ypass2", "epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap", "ypass3", "ypass3,epi2,lean"]))
+        var = str(rng.choice(["", "ypass2", "epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap", "ypass3", "ypass3,epi2,lean",
+                              "ypass2,epi2,lean,defer", "ypass3,epi2,lean,defer,overlap"]))
         with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path="interp", seed=1, variants=var) as sess:
             _load_params(sess, p)
             try:

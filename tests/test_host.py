@@ -485,6 +485,6 @@ def test_zz_gpu_file_runs_each_function_in_its_own_process():
     cmd = [sys.executable, "-m", "pytest", zz, "-m", "gpu", "-q", "-p", "no:cacheprovider", "-k", "same_seed_bitwise or full_size_c4"]
     env = {k: v for k, v in os.environ.items() if k not in ("CLONEALIGN_B200_ZZ_INNER", "CLONEALIGN_B200_TEST_EMUL")}
     r = subprocess.run(cmd, env=dict(env, CLONEALIGN_B200_TEST_EMUL="1"), capture_output=True, text=True, timeout=900, cwd=ROOT)
-    assert r.returncode == 0 and "3 xpassed" in r.stdout and "1 xfailed" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
+    assert r.returncode == 0 and "4 xpassed" in r.stdout and "1 xfailed" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    assert r.returncode == 0 and "4 xfailed" in r.stdout and "xpassed" not in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
+    assert r.returncode == 0 and "5 xfailed" in r.stdout and "xpassed" not in r.stdout, r.stdout[-1500:] + r.stderr[-500:]

@@ -18,7 +18,8 @@ from test_gpu_parity import ELBO_RTOL, PARAM_RTOL, _case, _check_grads, _load_pa
 pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="interp path not yet validated on hardware")]
 
 
-VARIANTS = ["", "ypass2", "epi2", "ypass2,epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap", "ypass3", "ypass3,epi2,lean"]
+VARIANTS = ["", "ypass2", "epi2", "ypass2,epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap", "ypass3", "ypass3,epi2,lean",
+            "ypass3,epi2,lean,defer", "ypass3,epi2,lean,defer,overlap"]
 
 
 @pytest.mark.parametrize("variants", VARIANTS)
@@ -33,7 +34,7 @@ def test_interp_gradients_and_elbo_match_oracle_c1(example_sce, S, variants):
         assert errs["Z"] < 1e-5
 
 
-@pytest.mark.parametrize("variants", ["", "ypass2,epi2", "ypass2,epi2,lean", "ypass3,epi2,lean"])
+@pytest.mark.parametrize("variants", ["", "ypass2,epi2", "ypass2,epi2,lean", "ypass3,epi2,lean", "ypass3,epi2,lean,defer,overlap"])
 @pytest.mark.parametrize("N,G,C,S", [(130, 70, 5, 3), (257, 193, 2, 1), (64, 640, 7, 8), (1000, 333, 12, 8), (300, 4100, 32, 4)])
 def test_interp_ragged_shapes(N, G, C, S, variants):
     from clonealign_b200.synthetic import make_synthetic
@@ -86,7 +87,7 @@ def test_interp_allele(example_sce):
         _check_grads(sess, d, p, 1)
 
 
-@pytest.mark.parametrize("variants", ["", "ypass2,epi2", "ypass2,epi2,lean"])
+@pytest.mark.parametrize("variants", ["", "ypass2,epi2", "ypass2,epi2,lean", "ypass3,epi2,lean,defer,overlap"])
 @pytest.mark.parametrize("S", [1, 3])
 def test_interp_loop_matches_golden(example_sce, golden_c1, S, variants):
     Y, L = example_sce
@@ -110,7 +111,7 @@ def test_interp_loop_matches_golden(example_sce, golden_c1, S, variants):
     assert _relmax(prm["W"], golden_c1[f"W_S{S}"]) <= 5e-3          # W starts at 0 (as in test_gpu_parity.py)
 
 
-@pytest.mark.parametrize("variants", ["", "ypass2,epi2", "ypass2,epi2,lean"])
+@pytest.mark.parametrize("variants", ["", "ypass2,epi2", "ypass2,epi2,lean", "ypass3,epi2,lean,defer,overlap"])
 def test_interp_same_seed_bitwise_identical(example_sce, variants):
     Y, L = example_sce
     hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
@@ -220,7 +221,7 @@ def _full_size_check(N, G, C, S, path, variants, V=0, n_sample=48, z_tol=2e-6, w
         sess.close()
 
 
-@pytest.mark.parametrize("variants", ["", "ypass2,epi2,lean", "ypass3,epi2,lean"])
+@pytest.mark.parametrize("variants", ["", "ypass2,epi2,lean", "ypass3,epi2,lean", "ypass3,epi2,lean,defer,overlap"])
 def test_full_size_c3_interp(variants):
     """BASELINE config 3 (100k x 20k x 12, S = 8) on the interpolation path: Z is near-exact (fp64 node sums), unlike the
     tcgen05 path's round-toward-zero accumulation."""
