@@ -248,7 +248,7 @@ struct ca_handle {
   unsigned* ticket = nullptr;
   int gene_panels = 0;
   size_t gene_smem = 0;
-  int fused_nj = 0, fused_panels = 0;
+  int fused_nj = 0, fused_panels = 0, fused_warps = kFusedWarps;
   size_t fused_smem = 0;
   int64_t n_cell_parts = 0;        // per-block ELBO / sum-gamma partials written by the per-cell kernel in use
   InterpPlan* iplan = nullptr;
@@ -455,10 +455,10 @@ template <int MODE>
 void launch_fused_mode(ca_handle* h, const FusedArgs& a) {
   const unsigned grid = (unsigned)h->n_cell_parts;
   switch (h->fused_nj) {
-    case 1: { auto k = k_cell_fused<MODE, 1>; CA_LAUNCH(k, grid, kFusedWarps * 32, h->fused_smem, h->stream)(a); break; }
-    case 2: { auto k = k_cell_fused<MODE, 2>; CA_LAUNCH(k, grid, kFusedWarps * 32, h->fused_smem, h->stream)(a); break; }
-    case 3: { auto k = k_cell_fused<MODE, 3>; CA_LAUNCH(k, grid, kFusedWarps * 32, h->fused_smem, h->stream)(a); break; }
-    case 4: { auto k = k_cell_fused<MODE, 4>; CA_LAUNCH(k, grid, kFusedWarps * 32, h->fused_smem, h->stream)(a); break; }
+    case 1: { auto k = k_cell_fused<MODE, 1>; CA_LAUNCH(k, grid, h->fused_warps * 32, h->fused_smem, h->stream)(a); break; }
+    case 2: { auto k = k_cell_fused<MODE, 2>; CA_LAUNCH(k, grid, h->fused_warps * 32, h->fused_smem, h->stream)(a); break; }
+    case 3: { auto k = k_cell_fused<MODE, 3>; CA_LAUNCH(k, grid, h->fused_warps * 32, h->fused_smem, h->stream)(a); break; }
+    case 4: { auto k = k_cell_fused<MODE, 4>; CA_LAUNCH(k, grid, h->fused_warps * 32, h->fused_smem, h->stream)(a); break; }
     default: fail("fused per-cell kernel: unsupported S*C");
   }
 }
@@ -480,13 +480,19 @@ void run_forward(ca_handle* h, int mode) {
   // The Y stream (HBM-bound, touches only Y, psi, W) is independent of the forward contraction (tensor / MUFU
   // bound): fork it onto a second stream so both run on the SMs at once; joined before the per-cell epilogue.
   bool joined_later = false;
-  if (mode != EPI_INIT && h->overlap && !h->prof_on && h->ydirty && h->KP > 0) {
+  const bool want_fork = mode != EPI_INIT && h->overlap && !h->prof_on && h->ydirty && h->KP > 0;
+  auto fork_ypass = [&]() {
     CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
     CUDA_OK(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
     run_ypass(h, h->stream2);
     CUDA_OK(cudaEventRecord(h->ev_join, h->stream2));
     joined_later = true;
-  }
+  };
+  // Variant DEFER forks later, right before the per-cell kernel: two Y-pass CTAs take the whole register file of an SM, so a
+  // pass started here would only push the short gene-level launches (prologue, node sums, coefficients: the head of the
+  // step's critical path) behind its first wave; started together with the per-cell kernel (half a register file per
+  // CTA) it shares every SM with it instead.
+  if (want_fork && !h->defer) fork_ypass();
   SampleMuArgs sm;
   sm.G = h->G; sm.C = h->C; sm.S = h->S; sm.K = h->K; sm.KP = h->KP; sm.SCp = h->SCp; sm.J = h->J; sm.Gld = h->Gld;
   sm.loc = h->loc; sm.lsd = h->lsd; sm.Vm = h->Vm; sm.L = h->L; sm.colsum = h->colsum; sm.chi_raw = h->chi_raw;
@@ -567,8 +573,17 @@ void run_forward(ca_handle* h, int mode) {
     a.Zx = h->inspect ? h->Zx : nullptr;
     a.elbo_part = h->elbo_part; a.gsum_part = h->gsum_part;
     a.defer_yv = h->defer ? 1 : 0;
+    // DEFER + OVERLAP: the pass may start once everything before the per-cell kernel is done (event recorded here), but
+    // it is handed to the device AFTER the per-cell kernel, whose 148 persistent CTAs should be placed first
+    if (want_fork && h->defer) CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
     launch_fused(h, mode, a);
     KCHECK();
+    if (want_fork && h->defer) {
+      CUDA_OK(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+      run_ypass(h, h->stream2);
+      CUDA_OK(cudaEventRecord(h->ev_join, h->stream2));
+      h->pending_join = true;
+    }
     if (h->defer && mode == EPI_EVAL) {   // the ELBO needs sum_n psi_n (YW)_n now; a train step joins before k_gene_fused
       join_ypass(h, mode);
       LaunchScope ls2(h, "yv_dot");
@@ -1138,10 +1153,23 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   }
   if (h->epi2) {
     h->fused_nj = (h->SC + 31) / 32;
-    h->fused_panels = fused_smem_panels(h->SC, C, J);
+    // defer + overlap: 16 warps x 64 registers = half of the register file, so that one Y-pass CTA (256 threads x 128
+    // registers, the other half) can be resident on the same SM while the per-cell kernel runs
+    h->fused_warps = (h->defer && (c.variants & CA_VAR_OVERLAP)) ? kFusedWarps / 2 : kFusedWarps;
+    if (h->fused_warps != kFusedWarps) {
+      // the Y-pass CTA must fit next to ~200 KB of shared memory: ask for the maximum shared-memory carveout, otherwise the
+      // SM would have to drain before it can be reconfigured (measured in round 1 for the contraction kernels)
+      CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v3<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v3<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v3<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v2<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v2<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v2<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
+    h->fused_panels = fused_smem_panels(h->SC, C, J, 200 * 1024, h->fused_warps);
     if (const char* e = getenv("CLONEALIGN_B200_FUSED_PANELS"))   // test hook: force the coefficients-through-L2 branch
       h->fused_panels = std::max(0, std::min(h->fused_panels, atoi(e)));
-    h->fused_smem = fused_smem_bytes(h->SC, C, J, h->fused_panels);
+    h->fused_smem = fused_smem_bytes(h->SC, C, J, h->fused_panels, h->fused_warps);
     if (h->fused_smem > 48 * 1024) {
       switch (h->fused_nj) {
         case 1: fused_set_smem<1>(h->fused_smem); break;

@@ -40,12 +40,12 @@ struct FusedArgs {
   double *elbo_part, *gsum_part;         // one partial per block
 };
 
-inline size_t fused_smem_bytes(int SC, int C, int J, int smem_panels) {
-  return ((size_t)smem_panels * kFusedPitch * J + (size_t)kFusedWarps * SC + kFusedWarps + (size_t)kFusedWarps * C) * sizeof(double) + 16;
+inline size_t fused_smem_bytes(int SC, int C, int J, int smem_panels, int warps = kFusedWarps) {
+  return ((size_t)smem_panels * kFusedPitch * J + (size_t)warps * SC + warps + (size_t)warps * C) * sizeof(double) + 16;
 }
 // how many panels of coefficients fit next to the per-warp scratch (0: read them through L2)
-inline int fused_smem_panels(int SC, int C, int J, size_t budget = 200 * 1024) {
-  const size_t fixed = fused_smem_bytes(SC, C, J, 0);
+inline int fused_smem_panels(int SC, int C, int J, size_t budget = 200 * 1024, int warps = kFusedWarps) {
+  const size_t fixed = fused_smem_bytes(SC, C, J, 0, warps);
   const size_t per_panel = (size_t)kFusedPitch * J * sizeof(double);
   if (fixed >= budget) return 0;
   size_t n = (budget - fixed) / per_panel;
@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused(FusedArgs a)
   const size_t table = (size_t)a.smem_panels * a.J * kFusedPitch;
   double* csm = sm;                                                   // [smem_panels][J][kIP + 1]
   double* lz = sm + table + (size_t)wid * SC;                         // per warp: log Z + m
-  double* blkE = sm + table + (size_t)kFusedWarps * SC;               // [warps]
-  double* blkG = blkE + kFusedWarps;                                  // [warps][C]
+  const int nwarps = blockDim.x >> 5;                                 // 32, or 16 when the block shares its SM with a Y-pass CTA
+  double* blkE = sm + table + (size_t)nwarps * SC;                    // [warps]
+  double* blkG = blkE + nwarps;                                       // [warps][C]
   // panel geometry of this step (k_interp_plan): per side the panel width and 2 / width
   int nf_neg, nf_pos;
   double pmin, w_neg, w_pos, ih_neg, ih_pos;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused(FusedArgs a)
   const int64_t chunk = (a.N + gridDim.x - 1) / gridDim.x;
   const int64_t ibeg = (int64_t)blockIdx.x * chunk;
   const int64_t iend = ibeg + chunk < a.N ? ibeg + chunk : a.N;
-  for (int64_t n = ibeg + wid; n < iend; n += kFusedWarps) {
+  for (int64_t n = ibeg + wid; n < iend; n += nwarps) {
     const float psif = a.U[n];
     const float mf = fmaxf(psif * wmin, psif * wmax);
     if (lane == 0) a.shift[n] = mf;
@@ -254,12 +255,12 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused(FusedArgs a)
   __syncthreads();
   if (threadIdx.x == 0) {
     double e = 0.0;
-    for (int w = 0; w < kFusedWarps; ++w) e += blkE[w];
+    for (int w = 0; w < nwarps; ++w) e += blkE[w];
     a.elbo_part[blockIdx.x] = e;
   }
   if (MODE == EPI_TRAIN && threadIdx.x < C) {
     double gs = 0.0;
-    for (int w = 0; w < kFusedWarps; ++w) gs += blkG[(size_t)w * C + threadIdx.x];
+    for (int w = 0; w < nwarps; ++w) gs += blkG[(size_t)w * C + threadIdx.x];
     a.gsum_part[(int64_t)blockIdx.x * C + threadIdx.x] = gs;
   }
 }
