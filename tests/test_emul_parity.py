@@ -15,10 +15,10 @@ from test_gpu_parity import ELBO_RTOL, PARAM_RTOL, _case, _check_grads, _load_pa
 pytestmark = pytest.mark.usefixtures("emulated_library")
 # (contraction path, kernel variants): the default kernels of both non-tensor paths and the re-engineered variants
 # (packed-fp32 Y pass, fused Clenshaw + per-cell epilogue) that bench.py validates on the device before using them
-# (the epi2-only and overlap sets are covered by test_random_shapes_and_variants, test_variants_agree_with_default_kernels and
+# (ypass2 on the CUDA-core path, the epi2-only and the overlap sets are covered by the storage-format test, test_random_shapes_and_variants, test_variants_agree_with_default_kernels and
 # bench.py's candidate tests: on the synchronous emulation `overlap` only changes which stream handle a launch names)
-PATHS = [("cudacore", ""), ("interp", ""), ("cudacore", "ypass2"), ("interp", "ypass2,epi2,lean"), ("cudacore", "ypass3"),
-         ("interp", "ypass3,epi2,lean"), ("interp", "ypass3,epi2,lean,defer")]
+PATHS = [("cudacore", ""), ("interp", ""), ("interp", "ypass2,epi2,lean"), ("cudacore", "ypass3"),
+         ("interp", "ypass3,epi2,lean"), ("interp", "ypass3,epi2,lean,defer,overlap")]
 
 
 def test_emulated_library_is_not_the_product(emulated_library):
