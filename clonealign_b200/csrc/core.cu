@@ -898,6 +898,17 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   bool tc_ok = kTcAvailable && (c.K == 1 && c.P == 0 && round_up64(h->SC, 16) <= 128);
   if (c.path == CA_PATH_TENSOR && !tc_ok) fail("tensor path needs K == 1, P == 0 and S*C <= 128");
   if (c.path == CA_PATH_INTERP && !(c.K == 1 && c.P == 0)) fail("interp path needs K == 1 and P == 0");
+  // path = auto: the reference's default model (K = 1, no covariates; K is forced to 1 at R/clonealign.R:226-232) runs the
+  // univariate-interpolation kernel set that round 2 validated on hardware (profiles/r02_notes.md): interp + packed Y pass
+  // on the stored integers + fused per-cell kernel + fused gene-level launches + late join of the Y pass.  Explicit
+  // variant bits of the caller are kept (ypass2 instead of ypass3, overlap, p2p).  Other shapes: tcgen05 contractions
+  // (K = 1, S*C <= 128) or the CUDA-core kernels (any K + P <= 8).
+  const bool interp_ok = c.K == 1 && c.P == 0 && c.C <= kFusedMaxC && c.S * c.C <= 32 * kFusedMaxNJ;
+  if (c.path == CA_PATH_AUTO && interp_ok) {
+    h->cfg.path = CA_PATH_INTERP;
+    if (!(h->cfg.variants & (CA_VAR_YPASS2 | CA_VAR_YPASS3))) h->cfg.variants |= CA_VAR_YPASS3;
+    h->cfg.variants |= CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_DEFER;
+  }
   h->interp = (c.path == CA_PATH_INTERP);
   h->variants = c.variants;
   if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_P2P | CA_VAR_OVERLAP | CA_VAR_YPASS3 | CA_VAR_DEFER))
@@ -1847,14 +1858,22 @@ int ca_core_describe(ca_handle* h, char* json, size_t json_len) {
   if (!h || !json || !json_len) return 1;
   const char* st = h->ystore == CA_STORE_F32 ? "f32" : (h->ystore == CA_STORE_U16 ? "u16" : "u8");
   int bpe = h->ystore == CA_STORE_F32 ? 4 : (h->ystore == CA_STORE_U16 ? 2 : 1);
+  // interp path: the panel structure of the last step (device-side data: the node work is proportional to it)
+  InterpPlan pl;
+  memset(&pl, 0, sizeof pl);
+  if (h->iplan) {
+    cudaSetDevice(h->dev);
+    cudaStreamSynchronize(h->stream);
+    cudaMemcpy(&pl, h->iplan, sizeof pl, cudaMemcpyDeviceToHost);
+  }
   snprintf(json, json_len,
            "{\"N\": %lld, \"G\": %d, \"C\": %d, \"S\": %d, \"K\": %d, \"P\": %d, \"path\": \"%s\", \"y_store\": \"%s\", "
            "\"y_bytes_per_entry\": %d, \"ldY\": %lld, \"launches_last_step\": %d, \"nsplit\": %d, \"fsplit\": %d, "
            "\"SCp\": %d, \"J\": %d, \"world\": %d, \"rank\": %d, \"variants\": %u, \"ypass_grid\": [%d, %d], \"ypass_rows_per_block\": %d, "
-           "\"num_sms\": %d}",
+           "\"num_sms\": %d, \"panels\": {\"nf_neg\": %d, \"nf_pos\": %d, \"nb\": %d, \"w_range\": [%.6g, %.6g], \"psi_range\": [%.6g, %.6g]}}",
            (long long)h->N, h->G, h->C, h->S, h->K, h->P, h->interp ? "interp" : (h->tc ? "tcgen05" : "cudacore"), st, bpe, (long long)h->ldY,
            h->launches_last_step, h->nsplit, h->tc ? h->tcplan.fsplit : 1, h->SCp, h->J, h->cfg.world, h->cfg.rank, h->variants, h->nCB, h->nRB, h->RB,
-           h->num_sms);
+           h->num_sms, pl.nf_neg, pl.nf_pos, pl.nb, pl.wmin, pl.wmax, pl.pmin, pl.pmax);
   return 0;
 }
 

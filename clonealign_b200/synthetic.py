@@ -53,34 +53,48 @@ def _fix_empty(Y):
         Y[n, n % Y.shape[1]] = 1.0
 
 
+SYN_BLOCK = 1024   # rows per independently seeded block of the CUDA generator
+
+
 def make_synthetic_cuda(N, G, C, seed=2345234, device="cuda:0", rows=None, literal=False):
     """Same model drawn on the GPU with torch (plumbing only: the 100k x 20k matrix would take minutes on
-    the host).  `rows=(a, b)` draws only that cell shard (gene-level draws are identical for every shard).
-    Returns dict(Y torch.float32 cuda (b-a, G), L numpy (G,C), z, s, colsum_hint=None)."""
+    the host).  `rows=(a, b)` draws only that cell shard.  The draw is SHARD-INVARIANT: gene-level draws are identical
+    for every shard and the counts come in blocks of SYN_BLOCK rows, each from its own generator seeded by
+    (seed, global block index), so the matrix a rank holds is exactly rows [a, b) of the matrix one GPU would draw --
+    a sharded fit and the unsharded one see the same data (1-vs-k-GPU parity runs).
+    Returns dict(Y torch.float32 cuda (b-a, G), L numpy (G,C), z, s)."""
     import torch
     p = gene_level(N, G, C, seed)
     a, b = rows if rows is not None else (0, N)
     dev = torch.device(device)
     gen = torch.Generator(device=dev)
-    gen.manual_seed(int(seed) + 7919 * a)
     t = lambda v: torch.tensor(v, dtype=torch.float32, device=dev)
     rho, mu, phi, Lp = t(p["rho"]), t(p["mu"]), t(p["phi"]), t(p["Lp"])
-    z = torch.tensor(p["z"][a:b], device=dev)
-    s = t(p["s"][a:b])
+    z_all = torch.tensor(p["z"], device=dev)
+    s_all = t(p["s"])
     Y = torch.empty((b - a, G), dtype=torch.float32, device=dev)
-    step = max(1, (1 << 27) // max(G, 1))
-    for i in range(0, b - a, step):
-        j = min(b - a, i + step)
-        r = ((1.0 - rho) * mu)[None] + (rho * mu)[None] * Lp[:, z[i:j]].T
-        m = s[i:j, None] * (r if literal else r / r.sum(dim=1, keepdim=True))
-        # Gamma(shape=phi, scale=m/phi) via standard gamma; then Poisson
-        g0 = torch._standard_gamma(phi[None].expand(j - i, G).contiguous(), generator=gen)
+    phi_b = phi[None].expand(SYN_BLOCK, G).contiguous()
+    for blk in range(a // SYN_BLOCK, (b + SYN_BLOCK - 1) // SYN_BLOCK):
+        r0 = blk * SYN_BLOCK
+        r1 = min(N, r0 + SYN_BLOCK)
+        gen.manual_seed(int(seed) * 1000003 + 7919 * (blk + 1))
+        zz = torch.zeros(SYN_BLOCK, dtype=z_all.dtype, device=dev)
+        ss = torch.ones(SYN_BLOCK, dtype=torch.float32, device=dev)
+        zz[: r1 - r0] = z_all[r0:r1]
+        ss[: r1 - r0] = s_all[r0:r1]
+        r = ((1.0 - rho) * mu)[None] + (rho * mu)[None] * Lp[:, zz].T
+        m = ss[:, None] * (r if literal else r / r.sum(dim=1, keepdim=True))
+        # Gamma(shape=phi, scale=m/phi) via standard gamma; then Poisson.  Always a full block: the draws of a row do not
+        # depend on where the shard boundaries fall.
+        g0 = torch._standard_gamma(phi_b, generator=gen)
         lam = g0 * (m / phi[None])
-        Y[i:j] = torch.poisson(lam, generator=gen)
-        del r, m, g0, lam
-    # exact shapes (see _fix_empty)
+        yb = torch.poisson(lam, generator=gen)
+        lo, hi = max(a, r0), min(b, r1)
+        Y[lo - a:hi - a] = yb[lo - r0:hi - r0]
+        del r, m, g0, lam, yb
+    # exact shapes (see _fix_empty): no empty cell (row-local rule, shard-invariant)
     rs = Y.sum(dim=1)
     bad = torch.nonzero(rs == 0).flatten().tolist()
     for n in bad:
-        Y[n, n % G] = 1.0
+        Y[n, (n + a) % G] = 1.0
     return dict(Y=Y, L=p["L"], z=p["z"][a:b], s=p["s"][a:b])

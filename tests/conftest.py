@@ -48,61 +48,3 @@ def emulated_library():
         yield path
     finally:
         _lib.LIB_PATH, _lib._lib = saved
-
-
-# ----------------------------------------------------------------------------------------------------------------------
-# Fault isolation for tests/test_zz_interp_gpu.py (kernel sets that had not run on hardware when they were committed):
-# every test FUNCTION of that file runs in its own child pytest process (all its parameter sets together), and the
-# parent only reports the child's per-case verdicts.  A kernel that faults takes the CUDA context of ITS child down;
-# the other functions still produce their own evidence (XPASS / XFAIL per case), and nothing the driver's test process
-# has loaded is disturbed.  CLONEALIGN_B200_ZZ_INNER=1 marks the child (tests run in-process there).
-# CLONEALIGN_B200_TEST_EMUL=1 (CPU-only check of this plumbing, tests/test_host.py): the child binds the emulated library.
-# ----------------------------------------------------------------------------------------------------------------------
-_ZZ_FILE = "test_zz_interp_gpu.py"
-_zz_verdicts = {}
-
-
-@pytest.fixture(scope="session", autouse=True)
-def _zz_emulated_child():
-    if os.environ.get("CLONEALIGN_B200_ZZ_INNER") == "1" and os.environ.get("CLONEALIGN_B200_TEST_EMUL") == "1":
-        from clonealign_b200 import _lib
-        sys.path.insert(0, os.path.join(ROOT, "tests", "cuda_emul"))
-        try:
-            import build as emul_build
-        finally:
-            sys.path.pop(0)
-        _lib.LIB_PATH, _lib._lib = emul_build.build(), None
-    yield
-
-
-def _zz_run_function(path, func):
-    import re
-    import subprocess
-    env = dict(os.environ, CLONEALIGN_B200_ZZ_INNER="1")
-    cmd = [sys.executable, "-m", "pytest", f"{path}::{func}", "-m", "gpu", "--runxfail", "-q", "-rA", "-p", "no:cacheprovider"]
-    try:
-        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=420, cwd=ROOT)
-        text, rc = out.stdout + "\n" + out.stderr[-2000:], out.returncode
-    except subprocess.TimeoutExpired as e:
-        text = (e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")) + "\nchild pytest timed out"
-        rc = -1
-    verdicts = {}
-    for m in re.finditer(r"^(PASSED|FAILED|ERROR)\s+\S+?::(\S+)(?:\s+-\s+(.*))?$", text, flags=re.M):
-        verdicts[m.group(2)] = (m.group(1) == "PASSED", (m.group(3) or "").strip())
-    return dict(rc=rc, verdicts=verdicts, tail=text[-1500:])
-
-
-@pytest.hookimpl(tryfirst=True)
-def pytest_pyfunc_call(pyfuncitem):
-    if os.path.basename(str(pyfuncitem.fspath)) != _ZZ_FILE or os.environ.get("CLONEALIGN_B200_ZZ_INNER") == "1":
-        return None
-    func = pyfuncitem.originalname or pyfuncitem.name
-    if func not in _zz_verdicts:
-        _zz_verdicts[func] = _zz_run_function(str(pyfuncitem.fspath), func)
-    res = _zz_verdicts[func]
-    ok, msg = res["verdicts"].get(pyfuncitem.name, (False, None))
-    if ok:
-        return True
-    if msg is None:      # the child died before reporting this case (fault, hang, collection error)
-        msg = f"no verdict from the child process (exit {res['rc']}): ...{res['tail'][-600:]}"
-    pytest.fail(f"[isolated child] {msg}", pytrace=False)

@@ -16,13 +16,9 @@ pytestmark = pytest.mark.gpu
 
 ELBO_RTOL = 1e-4
 PARAM_RTOL = 1e-3
-PATHS = ["cudacore", "tensor"]
-# The K = 1 univariate-interpolation path (kernels_interp.cuh) was written after round 1's GPU budget was spent:
-# it joins the parametrisation (and should become the default path) once `CLONEALIGN_B200_TEST_INTERP=1 pytest -m gpu`
-# is green on a B200.
-import os as _os
-if _os.environ.get("CLONEALIGN_B200_TEST_INTERP"):
-    PATHS.append("interp")
+# "auto" = what a drop-in clonealign() call runs: for K = 1, P = 0 the interpolation kernel set (interp + ypass3,epi2,lean,defer);
+# "interp" = the same contraction-free path with its unfused kernels; "tensor" / "cudacore" = the contraction kernels.
+PATHS = ["cudacore", "tensor", "interp", "auto"]
 
 
 def _session(Y, L, psi, mu_guess, **kw):
@@ -356,7 +352,7 @@ def test_full_size_properties():
     mu_guess = (Yd / rm).mean(dim=0).double().cpu().numpy()
     idx = np.sort(rng.choice(N, 48, replace=False))
     Ysub = Yd[torch.tensor(idx, device=Yd.device)].double().cpu().numpy()
-    sess = Session(Yd, L, psi, O.safe_inverse_softplus(mu_guess), mc_samples=S, K=1, seed=7)
+    sess = Session(Yd, L, psi, O.safe_inverse_softplus(mu_guess), mc_samples=S, K=1, seed=7, path="tensor")
     del Yd, syn
     torch.cuda.empty_cache()
     try:

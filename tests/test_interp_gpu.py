@@ -1,13 +1,8 @@
-"""GPU parity tests of the K = 1 interpolation path (`path="interp"`, clonealign_b200/csrc/kernels_interp.cuh) and of
-the kernel variants (`variants=`: packed-fp32 Y pass, fused Clenshaw + per-cell epilogue, kernels_fused.cuh).
-
-They were written after round 1's GPU budget was spent: the kernels are verified against the oracle on the CPU emulation
-of the whole C-ABI (tests/test_emul_parity.py) but had never run on hardware when this file was committed.  Until they have, these tests are
-`xfail(strict=False)`: a pass is reported as XPASS (evidence), a failure cannot turn the suite red, and the file sorts
-last so that a device fault here cannot disturb the tests of the default paths.  Every test FUNCTION of this file runs in its own child pytest process (tests/conftest.py, `pytest_pyfunc_call`): a kernel that
-faults takes only its own child's CUDA context down, so the other functions still deliver their own XPASS / XFAIL verdicts.
-Once green on a B200: drop the marker,
-add "interp" to PATHS in test_gpu_parity.py and make it the AUTO path for K = 1, P = 0.
+"""GPU parity tests of the K = 1 interpolation path (`path="interp"`, clonealign_b200/csrc/kernels_interp.cuh), of its kernel
+variants (`variants=`: packed-fp32 Y pass, fused Clenshaw + per-cell epilogue, fused gene-level launches) and of the section
+8f rows (device PCA, correlations, CSR ingest, shared inputs for restarts).  Since round 2 the interpolation kernel set
+(`interp` + `ypass3,epi2,lean,defer`) is what `path="auto"` resolves to for the reference's default model, so these are
+ordinary strict tests: a failure turns the suite red.
 """
 import numpy as np
 import pytest
@@ -15,7 +10,7 @@ import pytest
 from oracle import clonealign_oracle as O
 from test_gpu_parity import ELBO_RTOL, PARAM_RTOL, _case, _check_grads, _load_params, _relmax, _run_trace, _session
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="interp path not yet validated on hardware")]
+pytestmark = pytest.mark.gpu
 
 
 VARIANTS = ["", "ypass2", "epi2", "ypass2,epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap", "ypass3", "ypass3,epi2,lean",
@@ -229,13 +224,13 @@ def test_full_size_c3_interp(variants):
 
 
 def test_full_size_c4_allele():
-    """BASELINE config 4 (50k x 10k x 8 with the allele-specific likelihood fused in), default path."""
-    _full_size_check(50_000, 10_000, 8, 1, "auto", "", V=200, z_tol=1e-4, want_path="tcgen05")
+    """BASELINE config 4 (50k x 10k x 8, V = 2000 variants, allele-specific likelihood fused in), default path."""
+    _full_size_check(50_000, 10_000, 8, 1, "auto", "", V=2000, want_path="interp")
 
 
 def test_full_size_c5_one_replica():
     """BASELINE config 5, one restart replica (200k x 20k x 16), default path."""
-    _full_size_check(200_000, 20_000, 16, 1, "auto", "", z_tol=1e-4, want_path="tcgen05")
+    _full_size_check(200_000, 20_000, 16, 1, "auto", "", want_path="interp")
 
 
 def test_shared_device_inputs_for_restarts(example_sce):
