@@ -6,15 +6,20 @@
 One "step" = one `sess$run(train)` equivalent (R/inference-tflow.R:401): draw eps, forward ELBO terms, every
 gradient, TF1-Adam update of every parameter, on the synthetic workload of BASELINE.json (default c3:
 100k cells x 20k genes x 12 clones, S = 8; generator = port of inst/create_model3_synthetic.R).
-With N > 1 (torchrun, one rank per GPU) the cells are sharded and every step ends in one NCCL allreduce of the
-gene-level gradient partials: the total problem is fixed, so scaling is "strong".
+With N > 1 (torchrun, one rank per GPU) the cells are sharded and every step ends in one all-reduce of the
+gene-level gradient partials: the total problem is fixed, so scaling is "strong".  The synthetic matrix is
+shard-invariant (clonealign_b200/synthetic.py), so every N fits the SAME data: `config.parity` (ELBO before / after 20
+steps from the initial state, hash of the gathered hard clone calls) must agree across N.
 
-Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` is the same metric
-through the public API from HOST buffers (upload + reference loop + parameter download inside the timed region).
+Prints ONE JSON line (rank 0).  `value` = K / median over >= 5 timed blocks of exactly K steps (device-timed, CUDA events
+on the library's stream, barrier + synchronize on both sides of every block, max over ranks), inputs resident in HBM;
+`e2e` is the same metric through the public session API from HOST buffers (upload + set-up + reference loop with the ELBO
+fetched every iteration + parameter download inside the timed region).
 `--impl reference` times the restated reference graph (oracle, torch CPU float32, all host threads) on a bounded
 sample of the same workload.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -36,6 +41,10 @@ CONFIGS = {   # N, G, C, S
     "c5": dict(N=200_000, G=20_000, C=16, S=1, name="synthetic 200k x 20k x 16 S=1 (one restart replica)"),
 }
 DATA_SEED, EPS_SEED = 2345234, 12345
+PARITY_STEPS = 20          # config.parity: ELBO after this many steps from the initial state (same for every N)
+MIN_BLOCKS, MAX_BLOCKS = 5, 60
+MIN_TIMED_MS = 500.0       # keep timing blocks of K steps until this much device time has been measured
+LATE_STEPS = 200           # "late training" timing: after this many further steps (panel structure of a fit in progress)
 
 
 def peaks():
@@ -58,7 +67,7 @@ class ClockSampler:
 
     def __enter__(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -77,10 +86,10 @@ class ClockSampler:
         try:
             self.f.flush()
             rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+            rows = [r for r in rows if len(r) >= 9]
             sm = [float(r[1]) for r in rows]
             if sm:
-                hi = [x for x in sm if x >= 0.5 * max(sm)] or sm
-                out["sm_mhz"] = float(np.median(hi))
+                out["sm_mhz"] = float(np.median(sm))
                 out["sm_max_mhz"] = float(rows[0][2])
                 names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
                 for j, nm in enumerate(names):
@@ -111,6 +120,12 @@ def cpu_reference(cfg, steps, warmup, budget_s):
     from clonealign_b200.synthetic import make_synthetic
     from oracle import clonealign_oracle as O
     N, G, C, S = cfg["N"], cfg["G"], cfg["C"], cfg["S"]
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the baseline must use every host core it can, whatever launched it
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncpu))
     cores = torch.get_num_threads()
 
     def make(ns):
@@ -146,7 +161,7 @@ def cpu_reference(cfg, steps, warmup, budget_s):
     its = 1.0 / (t_step * N / ns)                                 # one full-workload step = N/ns sample steps
     return dict(value=its, unit="iterations/s", cores=cores, kind="port",
                 sample=f"{ns} of {N} cells x {G} genes x {C} clones S={S}; literal (S,G,C,N) TF-graph restatement, torch CPU "
-                       f"fp32 autograd + TF1 Adam; {t_step:.3f} s per sample step, scaled linearly in cells"), t_step, ns
+                       f"fp32 autograd + TF1 Adam, {cores} threads; {t_step:.3f} s per sample step, scaled linearly in cells"), t_step, ns
 
 
 def run_reference(args, cfg):
@@ -157,190 +172,82 @@ def run_reference(args, cfg):
     line = {"impl": "reference", "metric": "ELBO+grad iterations/s", "value": cb["value"], "unit": "iterations/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["name"], "note": "restated reference (oracle port), not TensorFlow: no R/TF in this image"},
+            "config": {"workload": cfg["name"], "note": "restated reference (oracle port), not TensorFlow: no R/TF in this image; "
+                       "the literal (S,G,C,N) graph does not fit in memory at this size, so a cell sample is timed and scaled"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------
-# on-device self-check of the re-engineered K = 1 kernels against the (test-covered) tcgen05 path
-# ------------------------------------------------------------------------------------------------------
-# (path, variants) candidates, most conservative first; the reference they are checked against is ("tensor", "").
-CANDIDATES = [("interp", ""), ("interp", "ypass2"), ("interp", "epi2"), ("interp", "ypass2,epi2"), ("interp", "epi2,lean"),
-              ("interp", "ypass2,epi2,lean"), ("interp", "ypass2,epi2,lean,overlap"), ("auto", "ypass2"),
-              ("interp", "ypass3"), ("interp", "ypass3,epi2"), ("interp", "ypass3,epi2,lean"), ("interp", "ypass3,epi2,lean,overlap"),
-              ("auto", "ypass3"), ("interp", "ypass3,epi2,lean,defer"), ("interp", "ypass3,epi2,lean,defer,overlap")]
-# Gate = what the parity tests assert at small sizes, evaluated at full size against the tcgen05 path: ELBO (1e-4, north
-# star) and every gradient AT IDENTICAL PARAMETERS AND DRAWS (4e-3 of the array's max magnitude: both sides are within 2e-3
-# of the oracle in tests/test_gpu_parity.py), then a 3-step ELBO trace and the clone calls.  Parameters after Adam steps
-# are deliberately NOT compared element-wise: Adam's first updates are +-lr * sign(gradient), so a coordinate whose
-# gradient is within rounding of zero legitimately lands 2 * lr apart in two correct implementations.
-SELFCHECK_RESUME_RC = 3      # child exit code: a candidate took the CUDA context down, the rest still has to be checked
-SELFCHECK_BUDGET_S = 230     # wall-clock budget of the whole check (all child processes together)
-SELFCHECK_CHILD_S = 150      # ... and of one child (a hang on one candidate must leave time to check the ones behind it)
-SELFCHECK_TOL = dict(elbo=1e-4, grad=4e-3, clone_probs_mean=1e-3, calls_agree=0.999)
-GRAD_NAMES = ("psi", "W", "loc", "lsd", "gamma_logits", "alpha_unconstr", "chi_raw")
-
-
-def selfcheck_run(make_session, W0, timed=True):
-    """One candidate: ELBO + gradients at fixed parameters and draws, a 3-step ELBO trace, clone calls, 10 timed steps."""
-    sess = make_session()
-    try:
-        sess.set_array("W", W0)
-        sess.init_gamma()
-        e0 = sess.elbo()
-        sess.grads()
-        grads = {k: sess.get_array("grad_" + k) for k in GRAD_NAMES}
-        tr = [e0]
-        for _ in range(3):
-            sess.step()
-            tr.append(sess.elbo())
-        cp = sess.params()["clone_probs"]
-        ms = None
-        if timed:
-            sess.time_steps(3)
-            ms = sess.time_steps(10) / 10.0
-        return dict(elbo=np.array(tr), grads=grads, cp=cp, ms=ms)
-    finally:
-        sess.close()
-
-
-def selfcheck_compare(ref, got):
-    d = {"elbo": float(np.abs(got["elbo"] - ref["elbo"]).max() / np.abs(ref["elbo"]).max())}
-    for k in GRAD_NAMES:
-        d["grad_" + k] = float(np.abs(got["grads"][k] - ref["grads"][k]).max() / (np.abs(ref["grads"][k]).max() + 1e-300))
-    d["clone_probs_mean"] = float(np.abs(got["cp"] - ref["cp"]).mean())
-    d["calls_agree"] = float((got["cp"].argmax(1) == ref["cp"].argmax(1)).mean())
-    ok = bool(np.all(np.isfinite(got["elbo"])) and d["elbo"] <= SELFCHECK_TOL["elbo"] and
-              all(d["grad_" + k] <= SELFCHECK_TOL["grad"] for k in GRAD_NAMES) and
-              d["clone_probs_mean"] <= SELFCHECK_TOL["clone_probs_mean"] and d["calls_agree"] >= SELFCHECK_TOL["calls_agree"])
-    return ok, d
-
-
-def run_selfcheck(args, cfg):
-    """Child-process mode: same workload, same seeds; one session per candidate, compared with the tcgen05 path, then 10
-    timed steps.  One JSON line per candidate is printed as soon as it is known, so a device fault in a later candidate
-    cannot take the earlier verdicts with it (nor poison the benchmark process)."""
-    import torch
-    from clonealign_b200.inference import safe_inverse_softplus
-    from clonealign_b200.session import Session
-    from clonealign_b200.synthetic import make_synthetic_cuda
-    N, G, C, S = cfg["N"], cfg["G"], cfg["C"], cfg["S"]
-    torch.cuda.set_device(0)
-    syn = make_synthetic_cuda(N, G, C, seed=DATA_SEED, device="cuda:0")
-    Yd = syn["Y"]
-    L = np.minimum(syn["L"], 6.0)
-    psi = np.random.default_rng(EPS_SEED).standard_normal((N, 1))
-    mu_guess = (Yd / Yd.mean(dim=1, keepdim=True)).mean(dim=0, dtype=torch.float64).cpu().numpy()
-    loc_init = safe_inverse_softplus(mu_guess)
-    W0 = np.random.default_rng(EPS_SEED + 1).standard_normal((G, 1)) * 0.1     # W = 0 would make half the terms vanish
-
-    def mk(path, variants):
-        return lambda: Session(Yd, L, psi, loc_init, mc_samples=S, K=1, learning_rate=0.1, seed=EPS_SEED, y_store=args.y_store,
-                               path=path, variants=variants)
-
-    ref = selfcheck_run(mk("tensor", ""), W0)
-    print(json.dumps({"candidate": ["tensor", ""], "ok": True, "ms_per_step": ref["ms"]}), flush=True)
-    for path, variants in CANDIDATES[getattr(args, "selfcheck_skip", 0):]:
-        try:
-            got = selfcheck_run(mk(path, variants), W0)
-            ok, d = selfcheck_compare(ref, got)
-            print(json.dumps({"candidate": [path, variants], "ok": ok, "deviation_vs_tensor_path": d, "ms_per_step": got["ms"]}),
-                  flush=True)
-        except Exception as e:                     # a failed candidate is a verdict, not a crash of the check
-            print(json.dumps({"candidate": [path, variants], "ok": False, "error": str(e)[:200]}), flush=True)
-            if "CUDA error" in str(e):             # the context is gone: the parent restarts the check behind this candidate
-                sys.exit(SELFCHECK_RESUME_RC)
-    sys.exit(0)
-
-
-def interp_selfcheck(args):
-    """Run `bench.py --selfcheck` as a single-GPU child process (rank 0 only).  Returns ((path, variants), info): the
-    fastest candidate that reproduced the tcgen05 path within tolerance, or ("auto", "") if none did."""
-    drop = ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "ROLE_WORLD_SIZE",
-            "GROUP_WORLD_SIZE", "TORCHELASTIC_RUN_ID")
-    env = {k: v for k, v in os.environ.items() if k not in drop}
-    cache = os.path.join(tempfile.gettempdir(), f"clonealign_b200_selfcheck_{args.config}_{args.y_store}.json")
-    lib = os.path.join(ROOT, "clonealign_b200", "libclonealign_b200.so")
-    stamp = os.path.getmtime(lib) if os.path.exists(lib) else 0
-    rows, note = [], None
-    try:
-        c = json.load(open(cache))
-        if c.get("stamp") == stamp:
-            rows, note = c["rows"], "cached verdicts of an earlier run on this box"
-    except Exception:
-        pass
-    if not rows:
-        # One child process checks the candidates in order.  A candidate that faults (the CUDA context dies with it) or hangs
-        # (the child's watchdog ends it) must not keep the candidates behind it from being checked: the child is restarted
-        # behind the offender until every candidate has a verdict or the time budget is spent.
-        deadline = time.time() + SELFCHECK_BUDGET_S
-        skip, notes, complete = 0, [], False
-        while skip < len(CANDIDATES):
-            left = deadline - time.time()
-            if left < 25:
-                notes.append(f"time budget spent with {len(CANDIDATES) - skip} candidate(s) unchecked")
-                break
-            cmd = [sys.executable, os.path.abspath(__file__), "--selfcheck", "--config", args.config, "--y-store", args.y_store,
-                   "--selfcheck-skip", str(skip), "--watchdog", str(int(max(20, min(left - 10, SELFCHECK_CHILD_S))))]
-            rc, stdout = None, ""
-            try:
-                out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=min(left, SELFCHECK_CHILD_S + 10))
-                rc, stdout = out.returncode, out.stdout
-                if rc not in (0, SELFCHECK_RESUME_RC):
-                    notes.append(f"child exit {rc}: {out.stderr[-200:]}")
-            except subprocess.TimeoutExpired as e:
-                stdout = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
-                notes.append("child timed out")
-            except Exception as e:                      # never let the check break the benchmark
-                notes.append(str(e)[:200])
-            got = []
-            for ln in stdout.splitlines():
-                if ln.startswith("{"):
-                    try:
-                        got.append(json.loads(ln))
-                    except ValueError:
-                        pass
-            cand = [r for r in got if r.get("candidate", [None])[0] != "tensor"]
-            if not any(r["candidate"][0] == "tensor" for r in rows):
-                rows += [r for r in got if r.get("candidate", [None])[0] == "tensor"][:1]
-            rows += cand
-            skip += len(cand)
-            if rc == 0:
-                complete = skip >= len(CANDIDATES)
-                break
-            if not any(r.get("candidate", [None])[0] == "tensor" for r in got):
-                notes.append("the tcgen05 reference run did not complete")     # nothing to compare against: give up
-                break
-            if rc != SELFCHECK_RESUME_RC and skip < len(CANDIDATES):
-                # the child died without a verdict for the candidate it was on: that candidate is the offender
-                rows.append({"candidate": list(CANDIDATES[skip]), "ok": False, "error": "child process died or hung on this candidate"})
-                skip += 1
-        note = "; ".join(notes) if notes else None
-        if rows and complete and note is None:
-            try:
-                json.dump({"stamp": stamp, "rows": rows}, open(cache, "w"))
-            except OSError:
-                pass
-    good = [r for r in rows if r.get("ok") and r.get("ms_per_step") and r["candidate"][0] != "tensor"]
-    base = next((r for r in rows if r["candidate"][0] == "tensor"), None)
-    pick = ("auto", "")
-    if good:
-        best = min(good, key=lambda r: r["ms_per_step"])
-        if base is None or not base.get("ms_per_step") or best["ms_per_step"] < base["ms_per_step"]:
-            pick = tuple(best["candidate"])
-    return pick, {"picked": list(pick), "candidates": rows, "note": note}
-
-
-# ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
+def sampled_cell_check(sess, Ysub, idx, L, S, C):
+    """fp64 numpy recomputation of the normaliser Z and the clone logits F of a few cells from the device's own parameters
+    and draws (the check of tests/test_interp_gpu.py::_full_size_check, at the benchmark's own state and size)."""
+    softplus = lambda x: np.where(x > 0, x + np.log1p(np.exp(-np.abs(x))), np.log1p(np.exp(-np.abs(x))))
+    sess.grads()
+    eps = sess.get_eps().astype(np.float64)
+    W = sess.get_array("W")[:, 0]
+    psi_d = sess.get_array("psi")[idx, 0]
+    mu = softplus(sess.get_array("loc")[:, 0][None] + np.exp(sess.get_array("lsd")[:, 0])[None] * eps)
+    eta = psi_d[:, None] * W[None]
+    m = eta.max(axis=1)
+    Z = np.einsum("ng,sgc->nsc", np.exp(eta - m[:, None]), mu[:, :, None] * L[None]).reshape(len(idx), -1)
+    Zdev = sess.get_array("Z")[idx]
+    s = Ysub.sum(1)
+    F = (Ysub @ np.log(L)) - s[:, None] * (np.log(Z).reshape(len(idx), S, C).mean(1) + m[:, None])
+    Fdev = sess.get_array("F")[idx] - (sess.get_array("v")[idx] if sess.V else 0.0)
+    return dict(cells=len(idx), z_max_rel=float(np.abs(Zdev / Z - 1.0).max()),
+                f_max_rel=float(np.abs(Fdev - F).max() / np.abs(F).max()),
+                gate="z <= 2e-6 and f <= 2e-5 (fp64 numpy from the device's own parameters and draws)",
+                ok=bool(np.abs(Zdev / Z - 1.0).max() <= 2e-6 and np.abs(Fdev - F).max() <= 2e-5 * np.abs(F).max()))
+
+
+def timed_blocks(sess, D, steps, dev):
+    """>= MIN_BLOCKS blocks of exactly `steps` train steps, each device-timed between a barrier + synchronize on both sides
+    (max over ranks), until MIN_TIMED_MS of device time has been measured; the clock sampler covers the blocks only."""
+    import torch
+    blocks = []
+    with ClockSampler(dev) as cs:
+        n_blocks = MIN_BLOCKS
+        while len(blocks) < n_blocks:
+            D.barrier()
+            torch.cuda.synchronize()
+            ms = sess.time_steps(steps)
+            torch.cuda.synchronize()
+            D.barrier()
+            blocks.append(D.max_over_ranks(ms))          # identical on every rank
+            if len(blocks) == 1:                         # same block count on all ranks: derived from a max-over-ranks value
+                n_blocks = int(min(MAX_BLOCKS, max(MIN_BLOCKS, np.ceil(MIN_TIMED_MS / max(blocks[0], 1e-3)))))
+    return blocks, cs.summary()
+
+
+def make_allele(cfg, z_all, a, b):
+    V, C, N = cfg["V"], cfg["C"], cfg["N"]
+    r2 = np.random.default_rng(DATA_SEED + 1)
+    cn = r2.integers(1, 4, size=(V, C)).astype(np.float64)
+    step = 4096                                           # row blocks with their own streams: shard-invariant
+    cov = np.empty((b - a, V))
+    alt = np.empty((b - a, V))
+    for r0 in range((a // step) * step, b, step):
+        rb = np.random.default_rng([DATA_SEED + 2, r0 // step])
+        r1 = min(N, r0 + step)
+        cv = rb.poisson(0.3, size=(step, V))[: r1 - r0].astype(np.float64)
+        z = z_all[r0:r1]
+        pr = np.where(cn[:, z].T == 2, 0.5, np.where(rb.random((step, V))[: r1 - r0] < 0.5, 0.05, 0.95))
+        al = rb.binomial(cv.astype(np.int64), pr).astype(np.float64)
+        lo, hi = max(a, r0), min(b, r1)
+        cov[lo - a:hi - a] = cv[lo - r0:hi - r0]
+        alt[lo - a:hi - a] = al[lo - r0:hi - r0]
+    return dict(clone_allele=cn, alt=alt, cov=cov)
+
+
 def run_ours(args, cfg):
     import torch
     from clonealign_b200 import dist as D
     from clonealign_b200.inference import safe_inverse_softplus
-    from clonealign_b200.synthetic import make_synthetic_cuda
+    from clonealign_b200.synthetic import gene_level, make_synthetic_cuda
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     rank, local_rank, world = D.init_process_group()
@@ -348,18 +255,10 @@ def run_ours(args, cfg):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     dev = local_rank
     torch.cuda.set_device(dev)
-    # contraction path: "best" asks rank 0 to validate the K = 1 interpolation path on this box (child process, same
-    # workload) against the tcgen05 path that the parity tests cover; every rank then takes rank 0's verdict
-    path, variants, selfcheck = args.path, args.variants, None
-    if path == "best":
-        idx = -1.0
-        if rank == 0:
-            pick, selfcheck = interp_selfcheck(args)
-            idx = float(CANDIDATES.index(pick)) if pick in CANDIDATES else -1.0
-        idx = int(D.max_over_ranks(idx))
-        path, variants = CANDIDATES[idx] if idx >= 0 else ("auto", "")
+    path, variants = args.path, args.variants
     N, G, C, S = cfg["N"], cfg["G"], cfg["C"], cfg["S"]
     a, b = D.shard_bounds(N, rank, world)
+    Nl = b - a
     pk = peaks()
 
     syn = make_synthetic_cuda(N, G, C, seed=DATA_SEED, device=f"cuda:{dev}", rows=(a, b))
@@ -372,107 +271,118 @@ def run_ours(args, cfg):
     mu_part = (Yd / rowmean).sum(dim=0, dtype=torch.float64).cpu().numpy()
     mu_guess = D.allreduce_sum(mu_part) / N                         # colMeans(Y / rowMeans(Y)), :222
     loc_init = safe_inverse_softplus(mu_guess)
-    allele = {}
-    if cfg.get("V"):
-        V = cfg["V"]
-        r2 = np.random.default_rng(DATA_SEED + 1)
-        cn = r2.integers(1, 4, size=(V, C)).astype(np.float64)
-        cov = r2.poisson(0.3, size=(N, V))[a:b].astype(np.float64)
-        z = syn["z"]
-        pr = np.where(cn[:, z].T == 2, 0.5, np.where(r2.random((b - a, V)) < 0.5, 0.05, 0.95))
-        alt = r2.binomial(cov.astype(np.int64), pr).astype(np.float64)
-        allele = dict(clone_allele=cn, alt=alt, cov=cov)
-    host_copy = None
+    allele = make_allele(cfg, gene_level(N, G, C, DATA_SEED)["z"], a, b) if cfg.get("V") else {}
+    n_chk = min(32, Nl)
+    idx = np.sort(np.random.default_rng(7).choice(Nl, n_chk, replace=False))
+    Ysub = Yd[torch.tensor(idx, device=Yd.device)].double().cpu().numpy()
+    host_f32 = host_u8 = None
+    integer_u8 = bool((Yd.max() <= 255).item())                     # synthetic counts are integers; u8 if they fit
     if not args.no_e2e:
-        host_copy = torch.empty(Yd.shape, dtype=torch.float32, pin_memory=True)
-        host_copy.copy_(Yd)
+        if integer_u8:
+            host_u8 = torch.empty(Yd.shape, dtype=torch.uint8, pin_memory=True)
+            host_u8.copy_(Yd)
+        if not integer_u8 or (world == 1 and not args.quick):
+            host_f32 = torch.empty(Yd.shape, dtype=torch.float32, pin_memory=True)
+            host_f32.copy_(Yd)
     kw = dict(mc_samples=S, K=1, learning_rate=0.1, seed=EPS_SEED, y_store=args.y_store, path=path, variants=variants, **allele)
     sess = D.sharded_session(Yd, L, psi, loc_init, N, colsum_local, rank, world, dev, **kw)
     del Yd, syn
     torch.cuda.empty_cache()
     desc = sess.describe()
 
+    # ---- parity block: the same 20 steps from the same initial state on the same data for every N ---------------------
     sess.init_gamma()
     e_start = sess.elbo()
-    sess.time_steps(max(args.warmup, 3))                            # >= 3 untimed warm-up steps
-    D.barrier()
-    torch.cuda.synchronize()
-    with ClockSampler(dev) as cs:
-        ms = sess.time_steps(args.steps)
-        # keep the sampler alive for very short timed regions.  Every step contains a collective, so the number of
-        # extra (untimed) steps MUST be identical on all ranks: derive it from the max over ranks, not the local time.
-        ms_all = D.max_over_ranks(ms)
-        if ms_all < 400:
-            sess.time_steps(max(1, int(args.steps * 400 / max(ms_all, 1e-3))))
-    clocks = cs.summary()
-    D.barrier()
-    torch.cuda.synchronize()
-    ms_max = D.max_over_ranks(ms)
-    value = args.steps / (ms_max / 1e3)
-    launches = sess.describe()["launches_last_step"] * args.steps
+    for _ in range(PARITY_STEPS):
+        sess.step()
+    e_20 = sess.elbo()
+    check = sampled_cell_check(sess, Ysub, idx, L, S, C)      # every rank: the gradient evaluation in it is a collective
+    cp = sess.params()["clone_probs"]
+    calls = np.where(cp.max(axis=1) < 0.95, -1, cp.argmax(axis=1)).astype(np.int8)      # clone_assignment, :22-29
+    calls_all = D.gather_concat(calls)
+    parity = None
+    if rank == 0:
+        parity = dict(steps=PARITY_STEPS, elbo_start=e_start, elbo_after=e_20,
+                      hard_calls_sha256=hashlib.sha256(calls_all.tobytes()).hexdigest()[:16],
+                      assigned=int((calls_all >= 0).sum()), cells=int(calls_all.size), sampled_cell_check=check)
+
+    # ---- timed region ------------------------------------------------------------------------------------------------
+    warm = max(args.warmup, 3)
+    sess.time_steps(warm)                                            # >= 3 untimed warm-up steps
+    blocks, clocks = timed_blocks(sess, D, args.steps, dev)
+    ms_med = float(np.median(blocks))
+    value = args.steps / (ms_med / 1e3)
+    d1 = sess.describe()
+    launches = d1["launches_last_step"] * args.steps
     e_end = sess.elbo()
 
     # the reference's loop iteration = train step + fresh-draw ELBO evaluation (R/inference-tflow.R:401-403), device-timed
-    # the same way (reported separately; every rank runs the same count, the evaluation has a collective too)
     n_loop = max(3, min(args.steps, 20))
     ms_loop = D.max_over_ranks(sess.time_steps(n_loop, with_eval=True)) / n_loop
 
-    # per-kernel device time (events around every launch), averaged over a few steps after the timed region
+    # per-kernel device time (events around every launch; launches serialised), averaged over a few steps
     prof = {}
     nprof = 5
     for _ in range(nprof):
         for name, t in sess.profile_step():
             prof[name] = prof.get(name, 0.0) + t / nprof
+
+    # ---- the same measurement later in the fit: the node work of the interp path follows the panel structure -----------
+    late = None
+    if not args.quick:
+        sess.time_steps(LATE_STEPS)
+        D.barrier()
+        torch.cuda.synchronize()
+        ms_late = [D.max_over_ranks(sess.time_steps(args.steps)) for _ in range(3)]
+        dl = sess.describe()
+        late = dict(after_steps=PARITY_STEPS + warm + len(blocks) * args.steps + n_loop + nprof + LATE_STEPS,
+                    ms_per_step=float(np.median(ms_late)) / args.steps, value=args.steps / (float(np.median(ms_late)) / 1e3),
+                    panels=dl.get("panels"), elbo=sess.elbo())
+
     bY = desc["y_bytes_per_entry"]
-    Nl = b - a
     ldY = desc["ldY"]
-    J, SCp = desc["J"], desc["SCp"]
     kern = {}
     if "ypass" in prof:
         kern["ypass"] = dict(bound="hbm", alg=(Nl * ldY * bY + 4 * (Nl * 2 + G * 2)) / 1e9, t=prof["ypass"])
     contraction = desc["path"] != "interp"      # the interp path has no N x G contraction to rate against the tensor peak
-    if "lse_fwd" in prof and contraction:
-        kern["lse_fwd"] = dict(bound="tensor", alg=2.0 * Nl * G * J / 1e12, t=prof["lse_fwd"])
-    if "lse_bwd" in prof and contraction:
-        kern["lse_bwd"] = dict(bound="tensor", alg=2.0 * Nl * G * J / 1e12, t=prof["lse_bwd"])
+    if contraction:
+        for nm in ("lse_fwd", "lse_bwd"):
+            if nm in prof:
+                kern[nm] = dict(bound="tensor", alg=2.0 * Nl * G * desc["J"] / 1e12, t=prof[nm])
     top = max(kern, key=lambda k: kern[k]["t"]) if kern else None
     roofline = None
     if top:
         k = kern[top]
         peak = pk["hbm"] if k["bound"] == "hbm" else pk["bf16"]
         ach = k["alg"] / (k["t"] / 1e3)
-        traffic = None                      # DRAM bytes per launch from the committed `ncu --set full` capture (same config only)
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if world == 1 and desc["y_store"] == "u8" and os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(args.config, {}).get(top)
+        traffic, tsrc = None, None              # DRAM bytes per launch of THIS kernel from the committed `ncu --set full` capture
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if world == 1 and os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            ent = tj.get(args.config, {}).get(desc["y_store"], {}).get(top)
+            if ent:
+                traffic, tsrc = ent["bytes"], f"profiles/r02_traffic.json ({ent['kernel']}, ncu --set full, same config)"
         roofline = dict(kernel=top, bound=k["bound"], achieved=ach, peak=peak, unit="GB/s" if k["bound"] == "hbm" else "TFLOP/s",
-                        frac=ach / peak, traffic=traffic, peak_source=pk["which"], ms_per_launch=k["t"],
-                        traffic_source=(None if traffic is None else
-                                        "profiles/r01_ncu_full_c3.md (round-1 capture of the round-1 kernel of this launch slot: "
-                                        "k_ypass_k1_persistent<u8> / k_expgemm_tc; same operands, not re-captured for the variants)"),
-                        note=("algorithmic flops 2*N*G*J (J = 2*S*C: Z and Z' columns); the forward kernel ISSUES 3x that "
-                              "(bf16 3-term split for fp32-grade log Z / d psi), so its tensor-pipe utilisation is ~3x frac"
-                              if top == "lse_fwd" else None),
+                        frac=ach / peak, traffic=traffic, peak_source=pk["which"], ms_per_launch=k["t"], traffic_source=tsrc,
+                        algorithmic_per_launch=k["alg"] * (1e9 if k["bound"] == "hbm" else 1e12),
                         all_kernels_ms={n: round(t, 4) for n, t in prof.items()},
                         per_kernel={n: dict(bound=v["bound"], achieved=v["alg"] / (v["t"] / 1e3),
                                             frac=v["alg"] / (v["t"] / 1e3) / (pk["hbm"] if v["bound"] == "hbm" else pk["bf16"]))
                                     for n, v in kern.items()})
     B_alg = algorithmic_bytes(Nl, G, C, S, 1, 0, bY)
-    step_hbm = dict(bytes_per_step=B_alg, achieved_gbs=B_alg / 1e9 / (ms_max / args.steps / 1e3), peak=pk["hbm"])
+    step_hbm = dict(bytes_per_step=B_alg, achieved_gbs=B_alg / 1e9 / (ms_med / args.steps / 1e3), peak=pk["hbm"])
     step_hbm["frac"] = step_hbm["achieved_gbs"] / pk["hbm"]
     sess.close()
     torch.cuda.empty_cache()
 
     # ---- the same kernel set with Y kept as fp32 (the reference's tensor dtype; SURVEY 8d "headline b_Y = 4") ----------
-    # The headline above uses the narrowest exact storage (u8: 4x fewer bytes, more iterations/s); the north star's
-    # "fraction of the HBM roofline" is quoted per byte actually streamed, so it is also measured for fp32 storage.
     alt_f32 = None
-    if world == 1 and desc["y_store"] != "f32" and host_copy is not None:
+    if world == 1 and desc["y_store"] != "f32" and host_f32 is not None:
         try:
-            s3 = D.sharded_session(host_copy.numpy(), L, psi, loc_init, N, colsum_local, rank, world, dev, **dict(kw, y_store="f32"))
+            s3 = D.sharded_session(host_f32.numpy(), L, psi, loc_init, N, colsum_local, rank, world, dev, **dict(kw, y_store="f32"))
             s3.init_gamma()
             s3.time_steps(3)
-            ms3 = s3.time_steps(10) / 10.0
+            ms3 = float(np.median([s3.time_steps(args.steps) for _ in range(3)])) / args.steps
             s3.close()
             torch.cuda.empty_cache()
             B4 = algorithmic_bytes(Nl, G, C, S, 1, 0, 4)
@@ -483,74 +393,68 @@ def run_ours(args, cfg):
             alt_f32 = {"error": str(e)[:200]}
 
     # ---- end to end through the public session API from HOST buffers -----------------------------------
-    e2e = None
-    if host_copy is not None:
+    def run_e2e(host, dtype_name):
         D.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        s2 = D.sharded_session(host_copy.numpy(), L, psi, loc_init, N, colsum_local, rank, world, dev, **kw)
+        s2 = D.sharded_session(host.numpy(), L, psi, loc_init, N, colsum_local, rank, world, dev, **kw)
+        t_up = time.perf_counter()
         s2.init_gamma()
         last = s2.elbo()
+        t_init = time.perf_counter()
         for _ in range(args.steps):                                  # the reference loop: train, then fresh-eps ELBO (D2H)
             s2.step()
             last = s2.elbo()
+        t_loop = time.perf_counter()
         prm = s2.params()
         t1 = time.perf_counter()
         s2.close()
         t_e2e = D.max_over_ranks(t1 - t0)
-        h2d = host_copy.numel() * 4 + (psi.size + loc_init.size + L.size) * 8
+        h2d = host.numel() * host.element_size() + (psi.size + loc_init.size + L.size) * 8 + \
+            sum(v.size * 8 for v in allele.values())
         d2h = 8 * (args.steps + 1) + sum(v.size for v in prm.values()) * 8
-        e2e = dict(value=args.steps / t_e2e, unit="iterations/s", h2d_bytes_per_step=h2d / args.steps,
-                   d2h_bytes_per_step=d2h / args.steps, seconds_total=t_e2e, final_elbo=last,
-                   includes="host Y upload + setup + gamma init + steps x (train + ELBO eval fetched to host) + params download")
-    # informational: the same end-to-end run when the caller already holds the counts compactly (uint8 host matrix,
-    # CA_Y_U8: 4x less to move over PCIe than the float32 matrix of the `e2e` figure above)
-    e2e_compact = None
-    if host_copy is not None and world == 1 and desc["y_store"] == "u8":
-        try:
-            host_u8 = torch.empty(host_copy.shape, dtype=torch.uint8, pin_memory=True)
-            host_u8.copy_(host_copy)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            s4 = D.sharded_session(host_u8.numpy(), L, psi, loc_init, N, colsum_local, rank, world, dev, **kw)
-            s4.init_gamma()
-            last4 = s4.elbo()
-            for _ in range(args.steps):
-                s4.step()
-                last4 = s4.elbo()
-            s4.params()
-            t1 = time.perf_counter()
-            s4.close()
-            e2e_compact = dict(value=args.steps / (t1 - t0), unit="iterations/s", seconds_total=t1 - t0, final_elbo=last4,
-                               h2d_bytes_per_step=(host_u8.numel() + (psi.size + loc_init.size + L.size) * 8) / args.steps,
-                               host_dtype="uint8")
-            del host_u8
-        except Exception as e:          # informational: never fail the bench on it
-            e2e_compact = {"error": str(e)[:200]}
+        return dict(value=args.steps / t_e2e, unit="iterations/s", h2d_bytes_per_step=h2d / args.steps,
+                    d2h_bytes_per_step=d2h / args.steps, seconds_total=t_e2e, final_elbo=last, host_dtype=dtype_name,
+                    seconds=dict(upload_and_setup=D.max_over_ranks(t_up - t0), gamma_init_and_first_elbo=D.max_over_ranks(t_init - t_up),
+                                 loop=D.max_over_ranks(t_loop - t_init), params_download=D.max_over_ranks(t1 - t_loop)),
+                    includes="host Y upload + setup (communicator included at N > 1) + gamma init + steps x (train + ELBO eval "
+                             "fetched to host) + params download")
+
+    e2e = e2e_f32 = None
+    if host_u8 is not None:
+        e2e = run_e2e(host_u8, "uint8")              # integer counts held compactly by the caller (CA_Y_U8)
+        if host_f32 is not None:
+            e2e_f32 = run_e2e(host_f32, "float32")   # informational: the reference's own host dtype
+    elif host_f32 is not None:
+        e2e = run_e2e(host_f32, "float32")
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base, _, _ = cpu_reference(cfg, 2, 1, budget_s=20.0)
 
     if rank == 0:
         line = {"metric": "ELBO+grad iterations/s", "value": value, "unit": "iterations/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+                "steps": args.steps, "warmup": warm, "ms_per_step": ms_med / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": ("f32 (f64 Chebyshev node sums / recurrences)" if desc["path"] == "interp" else
+                "dtype": ("f32 (node sums flushed to f64 every 32 terms, f64 Chebyshev recurrences)" if desc["path"] == "interp" else
                           "f32 (bf16 split tensor operands, f32 accumulate)" if desc["path"] == "tcgen05" else "f32"),
                 "data": "synthetic",
                 "config": {"workload": cfg["name"], "cells_total": N, "cells_per_gpu": Nl, "genes": G, "clones": C, "mc_samples": S,
-                           "K": 1, "sharding": f"cells/{world}", "path": desc["path"], "variants": variants, "y_store": desc["y_store"],
-                           "l2": "inputs larger than L2 (Y shard >> 126 MB)", "psi_init": "random normal (PCA skipped)",
-                           "path_requested": args.path, "selfcheck": selfcheck,
+                           "K": 1, "sharding": f"cells/{world}", "path": desc["path"], "variants_mask": desc["variants"],
+                           "path_requested": args.path, "variants_requested": variants, "y_store": desc["y_store"],
+                           "l2": "inputs larger than L2 (Y shard >> 126 MB)" if Nl * ldY * bY > 2.5e8 else
+                                 "Y shard comparable to L2: not an HBM-streaming measurement",
+                           "psi_init": "random normal (PCA skipped)", "data_generator": "shard-invariant (1024-row seeded blocks)",
                            "ypass_grid": desc.get("ypass_grid"), "ypass_rows_per_block": desc.get("ypass_rows_per_block"),
-                           "fallback_after_error": os.environ.get("CLONEALIGN_B200_BENCH_FALLBACK"),
-                           "elbo_start": e_start, "elbo_end": e_end},
+                           "timing": {"blocks": len(blocks), "steps_per_block": args.steps, "ms_blocks": [round(x, 4) for x in blocks],
+                                      "statistic": "median over blocks of the max over ranks"},
+                           "parity": parity, "elbo_start": e_start, "elbo_end": e_end, "panels": d1.get("panels")},
                 "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "step_hbm": step_hbm,
                 "reference_loop_iteration": {"ms": ms_loop, "value": 1e3 / ms_loop, "unit": "iterations/s",
                                              "what": "train step + fresh-draw ELBO evaluation, device-timed"},
-                "alt_fp32_storage": alt_f32, "e2e": e2e, "e2e_compact_host": e2e_compact,
+                "late_training": late, "alt_fp32_storage": alt_f32, "e2e": e2e, "e2e_f32_host": e2e_f32,
                 "cpu_baseline": cpu_base}
         print(json.dumps(line), flush=True)
+    D.shutdown()
 
 
 def main():
@@ -561,15 +465,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--y-store", default="auto", choices=["auto", "f32", "u16", "u8"])
-    ap.add_argument("--path", default="best", choices=["best", "auto", "cudacore", "tensor", "interp"],
-                    help="best = the fastest of the re-engineered K=1 kernel sets (CANDIDATES) that reproduces the tcgen05 "
-                         "path on this device within the parity tolerances (checked in a child process), else auto")
-    ap.add_argument("--variants", default="", help="kernel variants for an explicit --path (ypass2, epi2, lean; comma-separated)")
-    ap.add_argument("--selfcheck", action="store_true", help=argparse.SUPPRESS)
-    ap.add_argument("--selfcheck-skip", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--path", default="auto", choices=["auto", "cudacore", "tensor", "interp"],
+                    help="auto = what a drop-in clonealign() call runs (K = 1: interp + ypass3,epi2,lean,defer)")
+    ap.add_argument("--variants", default="", help="kernel variants (include/clonealign_b200.h, enum ca_variant; comma-separated)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--watchdog", type=int, default=600,
+    ap.add_argument("--quick", action="store_true", help="skip the late-training timing and the informational extras")
+    ap.add_argument("--watchdog", type=int, default=900,
                     help="abort the process after this many seconds (a hung collective must not hold the GPU box)")
     args = ap.parse_args()
     if args.watchdog > 0:
@@ -578,25 +480,10 @@ def main():
         wd.daemon = True
         wd.start()
     cfg = CONFIGS[args.config]
-    if args.selfcheck:
-        run_selfcheck(args, cfg)
-    elif args.impl == "reference":
+    if args.impl == "reference":
         run_reference(args, cfg)
     else:
-        try:
-            run_ours(args, cfg)
-        except SystemExit:
-            raise
-        except BaseException as e:   # noqa: BLE001
-            # A candidate that passed the child's gate but fails in the full run must not cost the benchmark line: start
-            # over ONCE, in a fresh process (a CUDA fault poisons the context), on the kernel set the GPU parity suite covers.
-            single = int(os.environ.get("WORLD_SIZE", "1")) == 1
-            if args.path == "best" and single and not os.environ.get("CLONEALIGN_B200_BENCH_FALLBACK"):
-                sys.stderr.write(f"bench.py: run with the selected kernel set failed ({str(e)[:300]}); retrying with --path auto\n")
-                sys.stderr.flush()
-                os.environ["CLONEALIGN_B200_BENCH_FALLBACK"] = str(e)[:200] or type(e).__name__
-                os.execv(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + ["--path", "auto"])
-            raise
+        run_ours(args, cfg)
 
 
 if __name__ == "__main__":

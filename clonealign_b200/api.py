@@ -46,7 +46,7 @@ def compute_correlations(Y, L, clones, clone_names):
     Xc = X - X.mean(axis=0)
     sy = np.sqrt((Yc * Yc).sum(axis=0))
     sx = np.sqrt((Xc * Xc).sum(axis=0))
-    ok = (sy > 0) & (sx > 0)
+    ok = (sy > 0) & (np.ptp(X, axis=0) > 0)     # a constant x is detected exactly (X - mean can leave a rounding residue)
     out[ok] = (Xc[:, ok] * Yc[:, ok]).sum(axis=0) / (sx[ok] * sy[ok])
     return out
 
@@ -104,10 +104,10 @@ def clonealign_steps(gene_expression_data, copy_number_data, max_iter=200, rel_t
                           gene_names=gene_names, correlations_with=(L, clone_call_probability) if device_correlations else None,
                           **backend)                                                    # :262-280
     dev_cor = res.pop("correlations", None)
+    ridx = np.nonzero(res.pop("retained_mask"))[0]          # positions of the retained genes (names may repeat)
     fit = CloneAlignFit(res)
     fit["clone"] = clone_assignment(res["ml_params"]["clone_probs"], clone_names, clone_call_probability)   # :283
     fit["clone_names"] = clone_names
-    ridx = [gene_names.index(g) for g in res["retained_genes"]]
     if dev_cor is None:
         Yr = Y[:, ridx]
         dev_cor = compute_correlations(np.asarray(Yr.todense()) if sparse else Yr, L[ridx, :], fit["clone"], clone_names)
@@ -133,6 +133,19 @@ def run_clonealign(gene_expression_data, copy_number_data, initial_shrinks=(0, 5
     `batch_y_pass=True` (implies share_inputs): the restarts of a device advance in lock-step and ONE pass over the shared
     count matrix per iteration serves all of them (ca_core_ypass_many) instead of one pass per restart and iteration."""
     rng = np.random.default_rng(seed)
+    if batch_y_pass:
+        # the batched pass serves fits with ONE latent dimension and no covariates, on the 8-column tiling of ypass2
+        # (core: ca_core_ypass_many); anything else runs its own pass per restart -- decided here, before any session exists
+        if kwargs.get("K") not in (None, 1) or kwargs.get("x") is not None:
+            warnings.warn("batch_y_pass needs K = 1 and no covariates: running one Y pass per restart instead")
+            batch_y_pass, share_inputs = False, True
+        else:
+            from .session import variant_mask, _VARIANT
+            names = kwargs.get("variants") or ""
+            if variant_mask(names) & _VARIANT["ypass3"]:
+                raise ValueError("batch_y_pass uses the column tiling of variant ypass2; it cannot be combined with ypass3")
+            if not (variant_mask(names) & _VARIANT["ypass2"]):
+                kwargs["variants"] = ",".join([v for v in (names.split(",") if isinstance(names, str) else list(names)) if v] + ["ypass2"])
     jobs = []
     for is_ in initial_shrinks:
         for _ in range(n_repeats):
@@ -160,16 +173,22 @@ def _lockstep(gens):
     """Advance several fits through their synchronisation points together; one batched Y pass per round."""
     from .session import ypass_many
     results, live = [None] * len(gens), dict(enumerate(gens))
-    while live:
-        waiting = {}
-        for i, g in list(live.items()):
-            try:
-                waiting[i] = next(g)
-            except StopIteration as done:
-                results[i] = done.value
-                del live[i]
-        if len(waiting) > 1:
-            ypass_many(list(waiting.values()))
+    try:
+        while live:
+            waiting = {}
+            for i, g in list(live.items()):
+                try:
+                    waiting[i] = next(g)
+                except StopIteration as done:
+                    results[i] = done.value
+                    del live[i]
+            if len(waiting) > 1:
+                ypass_many(list(waiting.values()))
+    finally:
+        # a fit that raised (e.g. "Initial elbo is NA") must not leave the others suspended with their sessions open:
+        # closing a generator runs its `finally: sess.close()`, so the shared inputs can be released by the caller
+        for g in live.values():
+            g.close()
     return results
 
 
@@ -217,7 +236,9 @@ def _run_restarts(gene_expression_data, copy_number_data, jobs, devices, print_e
         median_correlations = np.array([np.nanmedian(f["correlations"]) for f in fits])
     if print_elbos:
         print("ELBOs:  " + " ".join(str(e) for e in final_elbos))
-    best = fits[int(np.argmax(final_elbos))]
+    if np.all(np.isnan(final_elbos)):
+        raise ValueError("every restart ended with an NA final ELBO")
+    best = fits[int(np.nanargmax(final_elbos))]                 # which.max skips NA (R/clonealign.R:65)
     best["multirun_info"] = {
         "clone_prevalences_at_different_shrinks": [dict(zip(*np.unique(f["clone"], return_counts=True))) for f in fits],
         "elbos": final_elbos,

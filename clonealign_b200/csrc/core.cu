@@ -252,6 +252,8 @@ struct ca_handle {
   size_t fused_smem = 0;
   int64_t n_cell_parts = 0;        // per-block ELBO / sum-gamma partials written by the per-cell kernel in use
   InterpPlan* iplan = nullptr;
+  int n2_tj = 8, n2_ncgp = 32, n2_split_f = 1, n2_split_b = 1, n2_blocks_per_sm = kN2BlocksPerSM;   // k_interp_nodes2 launch geometry
+  size_t n2_smem = 0;
   float* mm_psi = nullptr;
   double *ivals = nullptr, *icoef = nullptr;
   size_t ieval_smem = 0;
@@ -421,24 +423,21 @@ void stage_eps(ca_handle* h, const float** eps_in) {
   }
 }
 
-template <bool FWD, int NC>
-void launch_interp_nodes_nc(ca_handle* h, int nsplit, const float* rv, const float* shift, const float* B, int64_t R) {
-  dim3 gn((h->J + 32 * NC - 1) / (32 * NC), kIGroupsY, nsplit);
-  auto k = k_interp_nodes<FWD, NC>;
-  CA_LAUNCH(k, gn, 256, 0, h->stream)(h->iplan, rv, shift, B, R, h->J, h->ivals);
-}
+// node sums + coefficients of the interp path (kernels_interp.cuh, k_interp_nodes2 / k_interp_coeffs2)
 template <bool FWD>
-void launch_interp_nodes(ca_handle* h, int nsplit, const float* rv, const float* shift, const float* B, int64_t R) {
-  switch (interp_nodes_nc(h->J)) {
-    case 1: launch_interp_nodes_nc<FWD, 1>(h, nsplit, rv, shift, B, R); break;
-    case 2: launch_interp_nodes_nc<FWD, 2>(h, nsplit, rv, shift, B, R); break;
-    case 3: launch_interp_nodes_nc<FWD, 3>(h, nsplit, rv, shift, B, R); break;
-    case 4: launch_interp_nodes_nc<FWD, 4>(h, nsplit, rv, shift, B, R); break;
-    case 5: launch_interp_nodes_nc<FWD, 5>(h, nsplit, rv, shift, B, R); break;
-    case 6: launch_interp_nodes_nc<FWD, 6>(h, nsplit, rv, shift, B, R); break;
-    case 7: launch_interp_nodes_nc<FWD, 7>(h, nsplit, rv, shift, B, R); break;
-    default: launch_interp_nodes_nc<FWD, 8>(h, nsplit, rv, shift, B, R); break;
+void launch_interp_nodes(ca_handle* h, const float* rv, const float* shift, const float* B, int64_t R) {
+  const int nsplit = FWD ? h->n2_split_f : h->n2_split_b;
+  const int max_pan = FWD ? kIMaxPanF : kIMaxPanB;
+  const unsigned grid = (unsigned)std::min<int64_t>((int64_t)max_pan * nsplit, (int64_t)h->n2_blocks_per_sm * h->num_sms);
+  if (h->n2_tj == 8) {
+    auto k = k_interp_nodes2<FWD, 8>;
+    CA_LAUNCH(k, grid, kN2Threads, h->n2_smem, h->stream)(h->iplan, rv, shift, B, R, h->J, h->n2_ncgp, nsplit, max_pan, h->ivals);
+  } else {
+    auto k = k_interp_nodes2<FWD, 6>;
+    CA_LAUNCH(k, grid, kN2Threads, h->n2_smem, h->stream)(h->iplan, rv, shift, B, R, h->J, h->n2_ncgp, nsplit, max_pan, h->ivals);
   }
+  CA_LAUNCH(k_interp_coeffs2, dim3((h->J + kC2Cols - 1) / kC2Cols, max_pan), kIP * kC2Cols * kC2Lanes, 0, h->stream)(
+      h->iplan, h->ivals, nsplit, max_pan, h->J, FWD ? 1 : 0, h->icoef);
 }
 
 // the partial sums of the Y pass are needed from here on: wait for the pass forked onto stream2, or run it now
@@ -547,8 +546,7 @@ void run_forward(ca_handle* h, int mode) {
         CA_LAUNCH(k_minmax, 1, 1024, 0, h->stream)(h->U, (int)h->N, h->mm_psi);
         CA_LAUNCH(k_interp_plan, 1, 32, 0, h->stream)(h->mm, h->mm_psi, h->iplan);
       }
-      launch_interp_nodes<true>(h, kISplitF, h->Vm, nullptr, h->Mx, h->G);
-      CA_LAUNCH(k_interp_coeffs, dim3((h->J + 31) / 32, kIMaxPanF), kIP * 32, 0, h->stream)(h->iplan, h->ivals, kISplitF, kIMaxPanF, h->J, 1, h->icoef);
+      launch_interp_nodes<true>(h, h->Vm, nullptr, h->Mx, h->G);
       if (!h->epi2)
         CA_LAUNCH(k_interp_eval<true>, h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream)(h->iplan, h->icoef, h->U, h->N, h->J, h->Zx,
                                                                                     h->ieval_panels);
@@ -614,8 +612,7 @@ void run_train(ca_handle* h, bool apply) {
     LaunchScope ls(h, "lse_bwd", h->interp ? (h->lean ? 2 : 3) : 1);
     if (h->interp) {
       // K = 1: dMx[g][j] = H_j(w_g); the plan of this step's forward pass is still valid (psi, W unchanged)
-      launch_interp_nodes<false>(h, kISplitB, h->U, h->shift, h->Rx, h->N);
-      CA_LAUNCH(k_interp_coeffs, dim3((h->J + 31) / 32, kIMaxPanB), kIP * 32, 0, h->stream)(h->iplan, h->ivals, kISplitB, kIMaxPanB, h->J, 0, h->icoef);
+      launch_interp_nodes<false>(h, h->U, h->shift, h->Rx, h->N);
       if (!h->lean)
         CA_LAUNCH(k_interp_eval<false>, h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream)(h->iplan, h->icoef, h->Vm, h->G, h->J, h->dMx,
                                                                                      h->ieval_panels);
@@ -1141,8 +1138,28 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if (h->interp) {
     h->iplan = h->alloc<InterpPlan>(1);
     h->mm_psi = z(2);
-    const size_t nodes_f = (size_t)kISplitF * kIMaxPanF * kIP, nodes_b = (size_t)kISplitB * kIMaxPanB * kIP;
-    h->ivals = h->alloc<double>(std::max(nodes_f, nodes_b) * J);
+    // node-sum kernel: columns per thread, column groups per warp, slices of the reduction index (>= 4 staged chunks per
+    // work item, at most two items per SM and panel), dynamic shared memory
+    h->n2_tj = n2_pick_tj(J);
+    h->n2_ncgp = n2_ncg_pow2(J, h->n2_tj);
+    auto n2_split = [&](int64_t R) {
+      return (int)std::max<int64_t>(1, std::min<int64_t>(2 * (int64_t)h->num_sms, ceil_div64(ceil_div64(R, kN2Chunk), 4)));
+    };
+    h->n2_split_f = n2_split(G);
+    h->n2_split_b = n2_split(N);
+    h->n2_smem = n2_smem_bytes(J, h->n2_tj);
+    h->n2_blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(kN2BlocksPerSM, (220 * 1024) / h->n2_smem));
+    if (h->n2_smem > 48 * 1024) {
+      if (h->n2_tj == 8) {
+        CUDA_OK(cudaFuncSetAttribute(k_interp_nodes2<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->n2_smem));
+        CUDA_OK(cudaFuncSetAttribute(k_interp_nodes2<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->n2_smem));
+      } else {
+        CUDA_OK(cudaFuncSetAttribute(k_interp_nodes2<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->n2_smem));
+        CUDA_OK(cudaFuncSetAttribute(k_interp_nodes2<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->n2_smem));
+      }
+    }
+    const size_t nodes_f = (size_t)h->n2_split_f * kIMaxPanF * kIP, nodes_b = (size_t)h->n2_split_b * kIMaxPanB * kIP;
+    h->ivals = h->alloc<double>(std::max(nodes_f, nodes_b) * J, false);
     h->icoef = h->alloc<double>((size_t)std::max(kIMaxPanF, kIMaxPanB) * kIP * J);
     const size_t per_panel = (size_t)kIP * J * sizeof(double);
     h->ieval_panels = (int)std::min<size_t>(16, (200 * 1024) / per_panel);
@@ -1648,9 +1665,10 @@ int ca_core_correlations(ca_handle* h, const int32_t* clone_idx, const double* L
     CUDA_OK(cudaMalloc(&d_L, sizeof(float) * (size_t)G * C));
     CUDA_OK(cudaMalloc(&d_part, sizeof(double) * (size_t)RS * G * 5));
     CUDA_OK(cudaMalloc(&d_out, sizeof(double) * G));
-    CUDA_OK(cudaMalloc(&d_sums, sizeof(double) * ((size_t)5 * G + 1)));
-    int64_t n_assigned = 0;
-    for (int64_t n = 0; n < N; ++n) n_assigned += (clone_idx[n] >= 0 && clone_idx[n] < C) ? 1 : 0;
+    CUDA_OK(cudaMalloc(&d_sums, sizeof(double) * ((size_t)5 * G + 1 + C)));
+    std::vector<double> tail(1 + (size_t)C, 0.0);      // number of assigned cells, then cells per clone (this shard)
+    for (int64_t n = 0; n < N; ++n)
+      if (clone_idx[n] >= 0 && clone_idx[n] < C) { tail[0] += 1.0; tail[1 + clone_idx[n]] += 1.0; }
     CUDA_OK(cudaMemcpyAsync(d_z, clone_idx, sizeof(int) * N, cudaMemcpyHostToDevice, h->stream));
     if (L) upload_colmajor(h, L, G, C, d_L, C, 0);
     else CUDA_OK(cudaMemcpyAsync(d_L, h->L, sizeof(float) * (size_t)G * C, cudaMemcpyDeviceToDevice, h->stream));
@@ -1662,12 +1680,11 @@ int ca_core_correlations(ca_handle* h, const int32_t* clone_idx, const double* L
     });
     CA_LAUNCH(k_corr_reduce, (G + 127) / 128, 128, 0, h->stream)(d_part, RS, G, d_sums);
     KCHECK();
-    const double na = (double)n_assigned;
-    CUDA_OK(cudaMemcpyAsync(d_sums + (size_t)5 * G, &na, sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CUDA_OK(cudaStreamSynchronize(h->stream));   // `na` lives on this stack frame
+    CUDA_OK(cudaMemcpyAsync(d_sums + (size_t)5 * G, tail.data(), sizeof(double) * tail.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));   // `tail` lives on this stack frame
     if (h->cfg.world > 1)   // collective: the sums over cells run over every shard
-      NCCL_OK(nccl().AllReduce(d_sums, d_sums, (size_t)5 * G + 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
-    CA_LAUNCH(k_corr_final, (G + 127) / 128, 128, 0, h->stream)(d_sums, G, d_out);
+      NCCL_OK(nccl().AllReduce(d_sums, d_sums, (size_t)5 * G + 1 + C, kNcclFloat64, kNcclSum, h->comm, h->stream));
+    CA_LAUNCH(k_corr_final, (G + 127) / 128, 128, 0, h->stream)(d_sums, d_L, G, C, d_out);
     KCHECK();
     CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(double) * G, cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -1863,8 +1880,8 @@ int ca_core_describe(ca_handle* h, char* json, size_t json_len) {
   memset(&pl, 0, sizeof pl);
   if (h->iplan) {
     cudaSetDevice(h->dev);
+    cudaMemcpyAsync(&pl, h->iplan, sizeof pl, cudaMemcpyDeviceToHost, h->stream);
     cudaStreamSynchronize(h->stream);
-    cudaMemcpy(&pl, h->iplan, sizeof pl, cudaMemcpyDeviceToHost);
   }
   snprintf(json, json_len,
            "{\"N\": %lld, \"G\": %d, \"C\": %d, \"S\": %d, \"K\": %d, \"P\": %d, \"path\": \"%s\", \"y_store\": \"%s\", "

@@ -6,8 +6,8 @@
 // where F_j, H_j are sums of exponentials: entire functions of ONE real variable.  Piecewise Chebyshev
 // interpolation on panels whose exponent half-range is <= kAmax converges spectrally (24 nodes: ~1e-14 relative, 16 nodes: ~6e-9;
 // scripts/interp_prototype.py, tests/test_interp_model.py), so the (N x G) x (G x J) contraction is replaced by
-//     nodes:  (n_nodes x G) x (G x J)   with n_nodes ~ 50..200 instead of N = 100 000        (k_interp_nodes<FWD>)
-//     DCT  :  node values -> Chebyshev coefficients per panel                                  (k_interp_coeffs)
+//     nodes:  (n_nodes x G) x (G x J)   with n_nodes ~ 50..200 instead of N = 100 000        (k_interp_nodes2<FWD>)
+//     DCT  :  node values -> Chebyshev coefficients per panel                                  (k_interp_coeffs2)
 //     eval :  one Clenshaw recurrence per (cell, column)                                       (k_interp_eval)
 // and symmetrically for the backward pass (nodes over w, reduction over cells, evaluation per gene).
 // Everything is fp64 (node exponentials, accumulation, recurrence); inputs/outputs keep the fp32 layouts of the
@@ -24,9 +24,6 @@ namespace ca {
 constexpr int kIP = 16;            // Chebyshev nodes per panel (multiple of 8); with kIAmax = 4: ~6e-9 relative
 constexpr int kIMaxPanF = 64;      // forward panels (both signs of psi together)
 constexpr int kIMaxPanB = 64;      // backward panels over [w_min, w_max]
-constexpr int kISplitF = 32;       // fixed split of the gene reduction in the forward node kernel (4 active node groups x 32 = 128 blocks)
-constexpr int kISplitB = 64;       // fixed split of the cell reduction in the backward node kernel
-constexpr int kIGroupsY = 8;       // grid.y of the node kernels: blocks stride over the ACTIVE groups of 8 nodes
 constexpr double kIAmax = 4.0;     // exponent half-range per panel
 constexpr double kPi = 3.14159265358979323846;
 
@@ -91,109 +88,192 @@ __global__ void k_interp_plan(const float* __restrict__ mm_w, const float* __res
   *plan = interp_make_plan((double)mm_w[0], (double)mm_w[1], (double)mm_psi[0], (double)mm_psi[1]);
 }
 
-// Node values.  FWD: part[z][node][j] = sum_{g in split z} Mx[g][j] exp(x_node (w_g - wref));  reduction index = genes.
-//               BWD: part[z][node][j] = sum_{n in split z} Rx[n][j] exp(psi_n y_node - m_n);    reduction index = cells.
-// Block = 8 warps, one group of 8 nodes x (32 NC) columns; warps stride over the reduction index, a lane owns NC
-// columns (j = cblock + lane + 32 c) of all 8 nodes in registers; the 8 exponentials of a row are computed by 8 lanes
-// and broadcast with shuffles, each of which now feeds NC fp64 FMAs (with NC = 1 the kernel was shuffle-bound: one
-// SHFL per DFMA).  Cross-warp reduction through shared memory in warp order (deterministic).
-// Grid = (column blocks, kIGroupsY, reduction splits): how many panels are active is only known on the device (the
-// plan), so blocks stride over the active groups of 8 nodes instead of launching (and retiring) one block per possible
-// group; the reduction index is split over blockIdx.z (kISplitF / kISplitB partials, summed by k_interp_coeffs) so that
-// a handful of active groups still spreads over all SMs instead of running as a few long serial loops.
-constexpr int kINodeMaxNC = 8;
-template <bool FWD, int NC>
-__global__ void __launch_bounds__(256)
-k_interp_nodes(const InterpPlan* __restrict__ plan, const float* __restrict__ rv /*FWD: w[G]  BWD: psi[N]*/,
-               const float* __restrict__ shift /*BWD: m[N]*/, const float* __restrict__ B /*[R][J]*/, int64_t R, int J,
-               double* __restrict__ vals) {
-  __shared__ double red[8][32 * NC];
+// =====================================================================================================================
+// Node sums (k_interp_nodes2 / k_interp_coeffs2).  The round-1 kernel kept 48 fp64 accumulators per lane, fed by one SHFL
+// + one F2F per 6 DFMA, 8 warps per SM, every group of 8 nodes re-reading its slice of B: 0.24 ms for 3e8 MACs at config 3,
+// issue slots 11 % busy (ncu of round 2, profiles/r02a_ncu_full_c3_start_of_round.md).  The node sums are a plain dense
+// contraction  V[node][j] = sum_r E[r][node] B[r][j]  with a generated A operand (16 nodes per panel, J <= 256 columns,
+// reduction over r = genes (FWD) or cells (BWD)), so they are tiled like one:
+//   * work item = (panel, slice of the reduction index); 128-thread blocks stride over the items (the panel count is
+//     device-side data), 3 blocks per SM;
+//   * B rows arrive in 32-row chunks by cp.async (16 bytes per request, double buffered: the next chunk is in flight
+//     while this one is consumed; a chunk of rows is ONE contiguous range of B);
+//   * the exponentials of a chunk (32 rows x 16 nodes: 4 per thread, fp64 argument, fp32 expf -- as before) go to shared
+//     memory as duplicated pairs (e, e), so that a thread's 4 nodes x TJ columns are fed by 2 + TJ/4 vector loads and
+//     updated by 2 TJ packed fma.rn.f32x2 per row: 16 FFMA2 per 4 LDS (TJ = 8);
+//   * fp32 accumulation runs over ONE chunk only (<= 32 terms), then is flushed into fp64 registers; slices are summed
+//     in fp64 in a fixed order by k_interp_coeffs2: same accuracy class as the fp64 kernel (products are exact in fp64
+//     there, rounded to fp32 here: 6e-8 relative per term, averaged over the sum), deterministic.
+// Columns beyond J (padding of the last column group) read the neighbouring row / slack and are never stored.
+// =====================================================================================================================
+constexpr int kN2Threads = 128;
+constexpr int kN2Chunk = 32;                 // rows of the reduction index per staged chunk
+constexpr int kN2EPitch = 2 * kIP + 8;       // floats per row of the (e, e) tile: 16 pairs + 8 floats of bank shift
+constexpr int kN2BlocksPerSM = 3;
+
+inline int n2_pick_tj(int J) {               // columns per thread: the choice that pads fewer columns
+  auto padded = [](int J_, int tj) { int ncg = (J_ + tj - 1) / tj, p = 1; while (p < ncg) p <<= 1; return p * tj; };
+  if (J > 6 * 32) return 8;                  // 6 x 32 lanes cover at most 192 columns (J <= 256 = 8 x 32 always fits)
+  return padded(J, 6) <= padded(J, 8) ? 6 : 8;
+}
+inline int n2_ncg_pow2(int J, int tj) { int ncg = (J + tj - 1) / tj, p = 1; while (p < ncg) p <<= 1; return p; }
+inline size_t n2_smem_bytes(int J, int tj) {
+  const size_t tile = (size_t)kN2Chunk * J + (size_t)32 * tj;          // + slack for the padded columns of the last row
+  return (2 * tile + 2 * (size_t)kN2Chunk * kN2EPitch) * sizeof(float) + kIP * sizeof(double) + 16;
+}
+
+template <bool FWD, int TJ>
+__global__ void __launch_bounds__(kN2Threads, kN2BlocksPerSM)
+k_interp_nodes2(const InterpPlan* __restrict__ plan, const float* __restrict__ rv /*FWD: w[G]  BWD: psi[N]*/,
+                const float* __restrict__ shift /*BWD: m[N]*/, const float* __restrict__ B /*[R][J]*/, int64_t R, int J,
+                int ncgp /*column groups, power of two <= 32*/, int nsplit, int max_pan, double* __restrict__ vals) {
+  CA_DYNAMIC_SMEM(float, smf);
   const InterpPlan pl = *plan;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int npan = FWD ? (pl.nf_neg + pl.nf_pos) : pl.nb;
-  const int ngroups = npan * (kIP / 8);
-  const int j0 = blockIdx.x * 32 * NC + lane;
-  // reduction range of this block
-  const int64_t per = (R + gridDim.z - 1) / gridDim.z;
-  const int64_t rbeg = (int64_t)blockIdx.z * per;
-  const int64_t rend = rbeg + per < R ? rbeg + per : R;
-  const int64_t nodes_total = (int64_t)(FWD ? kIMaxPanF : kIMaxPanB) * kIP;
-  for (int grp = blockIdx.y; grp < ngroups; grp += gridDim.y) {
-    const int node0 = grp * 8;
-    const int panel = node0 / kIP;
+  const int tid = threadIdx.x, lane = tid & 31, qg = tid >> 5;          // qg: nodes 4 qg .. 4 qg + 3 of the panel
+  const int cg = lane & (ncgp - 1), ks = lane / ncgp, nks = 32 / ncgp;   // column group / row slice of this lane
+  const size_t tile = (size_t)kN2Chunk * J + (size_t)32 * TJ;
+  float* Bs[2] = {smf, smf + tile};
+  float* Es[2] = {smf + 2 * tile, smf + 2 * tile + (size_t)kN2Chunk * kN2EPitch};
+  double* xq = reinterpret_cast<double*>(smf + 2 * tile + 2 * (size_t)kN2Chunk * kN2EPitch + 2);   // 8-byte aligned: see n2_smem_bytes
+  xq = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(xq) + 7) & ~(uintptr_t)7);
+  const int64_t per = ((R + nsplit - 1) / nsplit + 3) & ~(int64_t)3;     // rows per slice, multiple of 4 (16-byte chunk starts)
+  const bool vec16 = (J % 4) == 0;
+  const int64_t nodes_total = (int64_t)max_pan * kIP;
+  const int e_row = tid >> 2, e_q = (tid & 3) * 4;                        // exponentials: row of the chunk, first of 4 nodes
+
+  for (int item = blockIdx.x; item < npan * nsplit; item += gridDim.x) {
+    const int panel = item % npan, split = item / npan;
+    const int64_t rbeg = (int64_t)split * per;
+    const int64_t rend = rbeg + per < R ? rbeg + per : R;
     double mid, half, wref = 0.0;
     if (FWD) fwd_panel(pl, panel, mid, half, wref);
     else bwd_panel(pl, panel, mid, half);
-    const double xq = mid + half * cheb_node((node0 % kIP) + (lane & 7));   // node handled by this lane (lanes 0..7 used)
-    double acc[8][NC];
+    __syncthreads();                                   // the previous item's readers of xq / tiles are done
+    if (tid < kIP) xq[tid] = mid + half * cheb_node(tid);
+    double acc64[4][TJ];
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int c = 0; c < NC; ++c) acc[q][c] = 0.0;
-    // 4 rows of the reduction index per warp iteration: lane (q = lane & 7, sub = lane >> 3) evaluates the exponential
-    // of row r + sub at node q (argument in fp64, expf in fp32: ~1e-7 relative, averaged over the sum), then every lane
-    // accumulates its columns in fp64
-    for (int64_t r = rbeg + (int64_t)wid * 4; r < rend; r += 32) {
-      const int64_t rr = r + (lane >> 3);
-      float e = 0.f;
-      if (rr < rend) {
-        const double v = (double)rv[rr];
-        e = FWD ? expf((float)(xq * (v - wref))) : expf((float)(v * xq - (double)shift[rr]));
+      for (int j = 0; j < TJ; ++j) acc64[q][j] = 0.0;
+    const int nchunks = rend > rbeg ? (int)((rend - rbeg + kN2Chunk - 1) / kN2Chunk) : 0;
+    auto issue = [&](int k) {                           // chunk k -> Bs[k & 1]: one contiguous range of B
+      const int64_t r0 = rbeg + (int64_t)k * kN2Chunk;
+      const int rows = (int)((rend - r0) < kN2Chunk ? (rend - r0) : kN2Chunk);
+      const float* src = B + r0 * J;
+      float* dst = Bs[k & 1];
+      const int nfl = rows * J;
+      if (vec16) { for (int i = tid * 4; i < nfl; i += kN2Threads * 4) cp_async16(dst + i, src + i); }
+      else { for (int i = tid * 2; i < nfl; i += kN2Threads * 2) cp_async8(dst + i, src + i); }
+      cp_async_commit();
+    };
+    // row scalars of the chunk this thread generates exponentials for (prefetched one chunk ahead)
+    auto load_rv = [&](int k, float& v, float& sh) {
+      const int64_t r = rbeg + (int64_t)k * kN2Chunk + e_row;
+      v = r < rend ? rv[r] : 0.f;
+      sh = (!FWD && r < rend) ? shift[r] : 0.f;
+    };
+    float v_cur = 0.f, sh_cur = 0.f, v_nxt = 0.f, sh_nxt = 0.f;
+    if (nchunks > 0) { issue(0); load_rv(0, v_cur, sh_cur); }
+    __syncthreads();                                   // xq visible
+    for (int k = 0; k < nchunks; ++k) {
+      if (k + 1 < nchunks) load_rv(k + 1, v_nxt, sh_nxt);
+      {   // exponentials of chunk k: row e_row, nodes e_q .. e_q + 3, stored as (e, e) pairs
+        float* er = Es[k & 1] + (size_t)e_row * kN2EPitch + 2 * e_q;
+        float e[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double x = xq[e_q + q];
+          e[q] = FWD ? expf((float)(x * ((double)v_cur - wref))) : expf((float)((double)v_cur * x - (double)sh_cur));
+        }
+        reinterpret_cast<float4*>(er)[0] = make_float4(e[0], e[0], e[1], e[1]);
+        reinterpret_cast<float4*>(er)[1] = make_float4(e[2], e[2], e[3], e[3]);
+      }
+      cp_async_wait<0>();
+      __syncthreads();                                 // chunk k (every thread's copies) and its exponentials are visible;
+                                                       // everyone has finished consuming chunk k - 1
+      if (k + 1 < nchunks) issue(k + 1);               // overwrites the buffer chunk k - 1 was read from
+      const int64_t r0 = rbeg + (int64_t)k * kN2Chunk;
+      const int rows = (int)((rend - r0) < kN2Chunk ? (rend - r0) : kN2Chunk);
+      float2 acc[4][TJ / 2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < TJ / 2; ++j) acc[q][j] = make_float2(0.f, 0.f);
+      const float* bt = Bs[k & 1] + cg * TJ;
+      const float* et = Es[k & 1] + 8 * qg;
+#pragma unroll 2
+      for (int c = ks; c < rows; c += nks) {
+        float2 b[TJ / 2];
+        if (TJ == 8 && vec16) {                 // rows of B are 16-byte aligned: two 16-byte loads
+          const float4 b0 = *reinterpret_cast<const float4*>(bt + (size_t)c * J);
+          const float4 b1 = *reinterpret_cast<const float4*>(bt + (size_t)c * J + 4);
+          b[0] = make_float2(b0.x, b0.y); b[1] = make_float2(b0.z, b0.w);
+          b[TJ / 2 - 2] = make_float2(b1.x, b1.y); b[TJ / 2 - 1] = make_float2(b1.z, b1.w);
+        } else {                                // J is even: 8-byte alignment always holds
+#pragma unroll
+          for (int j = 0; j < TJ / 2; ++j) b[j] = *reinterpret_cast<const float2*>(bt + (size_t)c * J + 2 * j);
+        }
+        const float4 e01 = *reinterpret_cast<const float4*>(et + (size_t)c * kN2EPitch);
+        const float4 e23 = *reinterpret_cast<const float4*>(et + (size_t)c * kN2EPitch + 4);
+        const float2 ee[4] = {make_float2(e01.x, e01.y), make_float2(e01.z, e01.w), make_float2(e23.x, e23.y), make_float2(e23.z, e23.w)};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < TJ / 2; ++j) acc[q][j] = __ffma2_rn(ee[q], b[j], acc[q][j]);
       }
 #pragma unroll
-      for (int sub = 0; sub < 4; ++sub) {
-        const int64_t r2 = r + sub;
-        double b[NC];
+      for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int c = 0; c < NC; ++c) b[c] = (r2 < rend && j0 + 32 * c < J) ? (double)B[r2 * J + j0 + 32 * c] : 0.0;
+        for (int j = 0; j < TJ / 2; ++j) {
+          acc64[q][2 * j] += (double)acc[q][j].x;
+          acc64[q][2 * j + 1] += (double)acc[q][j].y;
+        }
+      v_cur = v_nxt; sh_cur = sh_nxt;
+    }
+    // row slices of a warp (ks): combined in slice order through shuffles (fixed order), then lanes with ks == 0 store
+    if (nks > 1) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const double eq = (double)__shfl_sync(CA_FULL, e, q + 8 * sub);
+      for (int q = 0; q < 4; ++q)
 #pragma unroll
-          for (int c = 0; c < NC; ++c) acc[q][c] = fma(eq, b[c], acc[q][c]);
+        for (int j = 0; j < TJ; ++j) {
+          double t = acc64[q][j];
+          for (int s2 = 1; s2 < nks; ++s2) {
+            const double o = __shfl_sync(CA_FULL, acc64[q][j], cg + s2 * ncgp);
+            t += o;
+          }
+          acc64[q][j] = t;
+        }
+    }
+    if (ks == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double* out = vals + ((int64_t)split * nodes_total + panel * kIP + 4 * qg + q) * J;
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) {
+          const int col = cg * TJ + j;
+          if (col < J) out[col] = acc64[q][j];
         }
       }
     }
-    // cross-warp sum in warp order
-    for (int w = 0; w < 8; ++w) {
-      if (wid == w) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-#pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            double* slot = &red[q][c * 32 + lane];
-            *slot = (w == 0) ? acc[q][c] : *slot + acc[q][c];
-          }
-      }
-      __syncthreads();
-    }
-    // thread (node q = wid, lane): its NC columns
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int j = j0 + 32 * c;
-      if (j < J) vals[((int64_t)blockIdx.z * nodes_total + node0 + wid) * J + j] = red[wid][c * 32 + lane];
-    }
-    __syncthreads();   // red is reused by the next group
   }
 }
-// host: columns per lane and grid.x for J columns
-inline int interp_nodes_nc(int J) { int nc = (J + 31) / 32; return nc > kINodeMaxNC ? kINodeMaxNC : (nc < 1 ? 1 : nc); }
 
-// Chebyshev coefficients per panel: c_k = (2/P) sum_p f(x_p) cos(pi k (p + 1/2) / P), c_0 halved.
-// The node values arrive as `nsplit` partials that are summed here in a fixed order.
-// Block = (kIP nodes) x (32 columns) threads for one (column block, panel): thread (p, lane) sums the partials of node
-// p (coalesced over the columns), the block transposes through shared memory, then thread (k = p, lane) applies the DCT.
-__global__ void __launch_bounds__(kIP * 32)
-k_interp_coeffs(const InterpPlan* __restrict__ plan, const double* __restrict__ vals, int nsplit, int max_pan, int J,
-                int fwd, double* __restrict__ coeff) {
-  __shared__ double f[kIP][32];
+// Coefficients from the slice partials of k_interp_nodes2: block = (8 columns, panel); thread (slice lane z, node p, column)
+// sums every 4th slice, the 4 slice lanes are combined in a fixed order through shared memory, then thread (k = p, column)
+// applies the DCT  c_k = (2/P) sum_p f(x_p) cos(pi k (p + 1/2) / P),  c_0 halved.
+constexpr int kC2Cols = 8, kC2Lanes = 4;
+__global__ void __launch_bounds__(kIP * kC2Cols * kC2Lanes)
+k_interp_coeffs2(const InterpPlan* __restrict__ plan, const double* __restrict__ vals, int nsplit, int max_pan, int J,
+                 int fwd, double* __restrict__ coeff) {
+  __shared__ double part[kC2Lanes][kIP][kC2Cols];
   __shared__ double ct[kIP][kIP];
   const InterpPlan pl = *plan;
   const int npan = fwd ? (pl.nf_neg + pl.nf_pos) : pl.nb;
   const int panel = blockIdx.y;
   if (panel >= npan) return;
-  const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
-  const int j = blockIdx.x * 32 + lane;
+  const int c8 = threadIdx.x % kC2Cols, p = (threadIdx.x / kC2Cols) % kIP, z = threadIdx.x / (kC2Cols * kIP);
+  const int j = blockIdx.x * kC2Cols + c8;
   const int64_t nodes_total = (int64_t)max_pan * kIP;
   if (threadIdx.x < kIP * kIP) {
     const int k = threadIdx.x / kIP, q = threadIdx.x % kIP;
@@ -201,16 +281,25 @@ k_interp_coeffs(const InterpPlan* __restrict__ plan, const double* __restrict__ 
   }
   double acc = 0.0;
   if (j < J)
-    for (int z = 0; z < nsplit; ++z) acc += vals[((int64_t)z * nodes_total + panel * kIP + p) * J + j];
-  f[p][lane] = acc;
+    for (int s = z; s < nsplit; s += kC2Lanes) acc += vals[((int64_t)s * nodes_total + panel * kIP + p) * J + j];
+  part[z][p][c8] = acc;
   __syncthreads();
-  const int k = p;
-  double c = 0.0;
+  if (z == 0) {
+    double f = part[0][p][c8];
 #pragma unroll
-  for (int q = 0; q < kIP; ++q) c += f[q][lane] * ct[k][q];
-  c *= 2.0 / kIP;
-  if (k == 0) c *= 0.5;
-  if (j < J) coeff[((int64_t)panel * kIP + k) * J + j] = c;
+    for (int zz = 1; zz < kC2Lanes; ++zz) f += part[zz][p][c8];
+    part[0][p][c8] = f;
+  }
+  __syncthreads();
+  if (z == 0) {
+    const int k = p;
+    double c = 0.0;
+#pragma unroll
+    for (int q = 0; q < kIP; ++q) c += part[0][q][c8] * ct[k][q];
+    c *= 2.0 / kIP;
+    if (k == 0) c *= 0.5;
+    if (j < J) coeff[((int64_t)panel * kIP + k) * J + j] = c;
+  }
 }
 
 // Evaluation: out[i][j] = sum_k c[panel(x_i)][k][j] T_k(t_i) by Clenshaw, one warp per point, lanes over columns.

@@ -163,15 +163,27 @@ __global__ void k_corr_reduce(const double* __restrict__ part, int RS, int G, do
     for (int q = 0; q < 5; ++q) s[q] += part[((int64_t)r * G + g) * 5 + q];
   for (int q = 0; q < 5; ++q) sums[(int64_t)g * 5 + q] = s[q];
 }
-// sums[5 G] holds the number of assigned cells; NaN where x or y is constant or fewer than 2 cells are assigned (R's cor gives NA)
-__global__ void k_corr_final(const double* __restrict__ sums, int G, double* __restrict__ out) {
+// sums[5 G] holds the number of assigned cells, sums[5 G + 1 + c] the number of cells assigned to clone c.  NaN where x
+// or y is constant or fewer than 2 cells are assigned (R's cor gives NA).  A constant x (the copy number of a gene is
+// the same in every clone that has cells -- common) is detected EXACTLY from L and the clone counts: the one-pass test
+// n Sxx - Sx^2 > 0 can leave a positive rounding residue for copy numbers that are not exactly representable.
+__global__ void k_corr_final(const double* __restrict__ sums, const float* __restrict__ L, int G, int C, double* __restrict__ out) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   const double* s = sums + (int64_t)g * 5;
   const double n = sums[(int64_t)5 * G];
+  const double* present = sums + (int64_t)5 * G + 1;
+  bool first = true, xconst = true;
+  float x0 = 0.f;
+  for (int c = 0; c < C; ++c) {
+    if (!(present[c] > 0.0)) continue;
+    const float l = L[(int64_t)g * C + c];
+    if (first) { x0 = l; first = false; }
+    else if (l != x0) xconst = false;
+  }
   const double vy = n * s[1] - s[0] * s[0], vx = n * s[3] - s[2] * s[2];
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  out[g] = (n >= 2.0 && vy > 0.0 && vx > 0.0) ? (n * s[4] - s[2] * s[0]) / sqrt(vx * vy) : nan;
+  out[g] = (n >= 2.0 && vy > 0.0 && vx > 0.0 && !xconst) ? (n * s[4] - s[2] * s[0]) / sqrt(vx * vy) : nan;
 }
 
 // =============================================================================================

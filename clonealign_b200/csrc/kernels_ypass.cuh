@@ -433,6 +433,139 @@ k_ypass_k1_v3(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// v4 of the KP == 1 tile (variant YPASS4), from the round-2 ncu capture of v3 (profiles/r02_notes.md): 16 warps per SM,
+// issue slots 41 % busy, the top stall is long_scoreboard -- every warp loads 8 rows into REGISTERS, waits about a
+// microsecond, then spends about as long on its ~430 instructions: the loads of the next rows are not in flight while it
+// computes (128 registers per thread leave no room to double-buffer them), and 2 CTAs take the whole register file, so
+// nothing else can share the SM with the stream.  Here the rows travel by cp.async (LDGSTS, L2 evict-first) into a
+// shared-memory ring of kRing rows per thread -- every thread copies exactly the 16-byte pieces it consumes itself, so a
+// cp.async.wait_group is all the synchronisation the data needs (no barrier, no cross-thread visibility) -- and are read
+// back one row at a time; the slot of row r - 1 is refilled (row r - 1 + kRing) while row r is processed.  Bytes in flight
+// no longer cost registers: kRing - 2 rows per thread are outstanding WHILE the thread computes (14 x 16 B against 8 x 16 B
+// that are only outstanding while it waits), and the kernel needs half the registers.  It is launched as a PERSISTENT grid
+// of 2 CTAs per SM (fixed tile assignment: deterministic) that leaves half of the register file and ~100 KB of shared
+// memory of every SM free: started first in the step on the second stream, the HBM-bound stream runs NEXT TO the
+// issue-bound kernels of the step (prologue, node sums, per-cell kernel) instead of before / after them.
+// Arithmetic, tiling (256 x kCols columns) and partial-sum layouts are those of v3: bit-identical results.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct Y4Ring { static constexpr int kRing = 16; };     // rows in the ring: 64 KB per CTA
+template <> struct Y4Ring<float> { static constexpr int kRing = 8; };         // 32-byte pieces
+template <typename T> constexpr size_t ypass4_smem_bytes() { return (size_t)Y4Ring<T>::kRing * 256 * sizeof(typename Y3<T>::Raw); }
+
+#ifdef CA_EMULATE
+__device__ __forceinline__ void y4_copy16(void* dst, const void* src, uint64_t) { memcpy(dst, src, 16); }
+__device__ __forceinline__ uint64_t y4_policy() { return 0; }
+#else
+__device__ __forceinline__ uint64_t y4_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void y4_copy16(void* dst, const void* src, uint64_t pol) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "l"(pol) : "memory");
+}
+#endif
+
+template <typename T>
+__global__ void __launch_bounds__(256, 4)
+k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, int nCB, int nRB, const float* __restrict__ U,
+              const float* __restrict__ Vm, float* __restrict__ rowpart, float* __restrict__ colpart) {
+  using L = Y3<T>;
+  using Raw = typename L::Raw;
+  constexpr int kRing = Y4Ring<T>::kRing, kCols = L::kCols, kPairs = kCols / 2;
+  constexpr int kPieces = sizeof(Raw) / 16;                      // 16-byte pieces per (thread, row): 1 (u8, u16) or 2 (f32)
+  CA_DYNAMIC_SMEM(unsigned char, ring_raw);
+  Raw* ring = reinterpret_cast<Raw*>(ring_raw) + threadIdx.x;    // [slot][thread]: this thread's column of slots
+  __shared__ float red[2][8][8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const uint64_t pol = y4_policy();
+  const int64_t ntiles = (int64_t)nCB * nRB;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int cb = (int)(tile % nCB);
+    const int64_t rb = tile / nCB;
+    const int64_t col0 = (int64_t)cb * (256 * kCols) + tid * kCols;
+    const bool colok = col0 < ldY;
+    float2 vr[kPairs], cacc[kPairs];
+#pragma unroll
+    for (int j = 0; j < kPairs; ++j) {
+      vr[j] = make_float2((col0 + 2 * j < G) ? Vm[col0 + 2 * j] * L::kPre : 0.f, (col0 + 2 * j + 1 < G) ? Vm[col0 + 2 * j + 1] * L::kPre : 0.f);
+      cacc[j] = make_float2(0.f, 0.f);
+    }
+    const int64_t rbeg = rb * RB, rend = (rbeg + RB < N) ? rbeg + RB : N;
+    const int nrows = (int)(rend - rbeg);
+    const int ngroups = (nrows + 7) / 8;
+    const T* ybase = Y + rbeg * ldY + col0;
+    // row `r` of the tile -> its slot; rows past the end of the tile (and threads past the last column) hold zeros.
+    // Exactly ONE group is committed per call, so that "all but the newest kRing - 2 groups" means "up to row r".
+    auto fill = [&](int r, int slot) {
+      Raw* dst = ring + (size_t)slot * 256;
+      if (colok && r < nrows) {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(ybase + (int64_t)r * ldY);
+#pragma unroll
+        for (int q = 0; q < kPieces; ++q) y4_copy16(reinterpret_cast<unsigned char*>(dst) + 16 * q, src + 16 * q, pol);
+      } else if (r < ngroups * 8) {
+        *dst = L::zero();
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int r = 0; r < kRing; ++r) fill(r, r);
+    int buf = 0;
+    for (int g = 0; g < ngroups; ++g) {
+      const int64_t r0 = rbeg + (int64_t)g * 8;
+      const int sbase = (g * 8) % kRing;
+      float u[8];   // U is allocated with 64 elements of slack, r0 is a multiple of 4: vector loads stay in bounds
+#pragma unroll
+      for (int i = 0; i < 8; i += 4) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(U + r0 + i));
+        u[i] = t4.x * L::kPre; u[i + 1] = t4.y * L::kPre; u[i + 2] = t4.z * L::kPre; u[i + 3] = t4.w * L::kPre;
+      }
+      float rp[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        cp_async_wait<kRing - 2>();                              // row 8 g + i has landed (this thread's own copies)
+        const Raw raw = ring[(size_t)(sbase + i) * 256];
+        // refill the slot of the PREVIOUS row (its value was consumed by the FMAs of the last iteration)
+        const int rprev = g * 8 + i - 1;
+        if (rprev >= 0) fill(rprev + kRing, (sbase + i - 1 + kRing) % kRing);
+        float2 y[kPairs];
+        L::unpack(raw, y);
+        const float2 u2 = make_float2(u[i], u[i]);
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kPairs; j += 2) {
+          acc0 = __ffma2_rn(y[j], vr[j], acc0);
+          acc1 = __ffma2_rn(y[j + 1], vr[j + 1], acc1);
+          cacc[j] = __ffma2_rn(y[j], u2, cacc[j]);
+          cacc[j + 1] = __ffma2_rn(y[j + 1], u2, cacc[j + 1]);
+        }
+        const float2 a2 = __fadd2_rn(acc0, acc1);
+        rp[i] = a2.x + a2.y;
+      }
+      const float tot = butterfly8(rp, lane);
+      if ((lane & 3) == 0) red[buf][wid][ridx] = tot;
+      __syncthreads();
+      if (tid < 8 && r0 + tid < rend) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) acc += red[buf][w][tid];
+        rowpart[(int64_t)cb * N + r0 + tid] = acc * L::kPost;
+      }
+      buf ^= 1;
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int j = 0; j < kPairs; ++j) {
+      if (col0 + 2 * j < G) colpart[rb * G + col0 + 2 * j] = cacc[j].x * L::kPost;
+      if (col0 + 2 * j + 1 < G) colpart[rb * G + col0 + 2 * j + 1] = cacc[j].y * L::kPost;
+    }
+    __syncthreads();   // `red` is reused by the next tile
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Batched Y pass for R fits that share one count matrix (restarts of run_clonealign on one device):
 // ONE stream over Y produces (Y W_r, Y^T psi_r) for every fit r -- the widening / magic-number work is shared and the
 // matrix leaves HBM once instead of R times.  Same tiling and partial layouts as k_ypass_k1_v2 (each fit's own rowpart /

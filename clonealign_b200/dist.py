@@ -121,3 +121,32 @@ def allgather_bytes(payload: bytes, nbytes: int):
     out = [torch.zeros(nbytes, dtype=torch.uint8, device=_dev()) for _ in range(dist.get_world_size())]
     dist.all_gather(out, mine)
     return [bytes(t.cpu().numpy().tobytes()) for t in out]
+
+
+def gather_concat(x):
+    """Concatenate a 1-D numpy array over the ranks in rank order (shards may differ in length); every rank gets the result."""
+    import torch
+    import torch.distributed as dist
+    x = np.ascontiguousarray(x)
+    if not dist.is_initialized():
+        return x
+    world = dist.get_world_size()
+    n = torch.tensor([x.size], dtype=torch.int64, device=_dev())
+    sizes = [torch.zeros(1, dtype=torch.int64, device=_dev()) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(sizes)
+    buf = torch.zeros(cap * x.itemsize, dtype=torch.uint8, device=_dev())
+    raw = torch.frombuffer(bytearray(x.tobytes()), dtype=torch.uint8)
+    buf[: raw.numel()] = raw.to(_dev())
+    out = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    parts = [np.frombuffer(o.cpu().numpy().tobytes()[: sizes[r] * x.itemsize], dtype=x.dtype) for r, o in enumerate(out)]
+    return np.concatenate(parts)
+
+
+def shutdown():
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()

@@ -276,6 +276,10 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
             sess.step()                                                               # :401
             yield sess
             elbo_new = sess.elbo()                                                    # :403
+            if np.isnan(elbo_new):
+                # the reference's `if(mean(abs(elbo_diffs)) < rel_tol)` (:414) stops with "missing value where TRUE/FALSE
+                # needed" once the ELBO is NA; a diverged fit must not run on to max_iter and be returned as a result
+                raise ValueError(f"ELBO is NA after iteration {len(elbos)}: missing value where TRUE/FALSE needed")
             elbo_diff = (elbo_new - elbo_val) / abs(elbo_val)
             elbo_diffs = elbo_diffs[1:] + [elbo_diff]
             elbos.append(elbo_new)
@@ -301,7 +305,7 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
                         "sd_final_elbo": float(np.std(final_elbo, ddof=1)),
                         "elbo": np.array(elbos)}
     out = {"ml_params": rlist, "convergence_info": convergence_info, "retained_genes": retained_genes,
-           "clone_probs_from_snv": clone_probs_from_snv}
+           "clone_probs_from_snv": clone_probs_from_snv, "retained_mask": ~zero_gene_means}
     if correlations is not None:
         out["correlations"] = correlations
     return out

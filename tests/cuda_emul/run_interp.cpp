@@ -30,29 +30,35 @@ int main(int argc, char** argv) {
   InterpPlan plan;
   ca_emul::launch(k_interp_plan, dim3(1), dim3(32), 0, (const float*)mm_w, (const float*)mm_psi, &plan);
   const int npf = plan.nf_neg + plan.nf_pos;
-  std::vector<double> vals((size_t)std::max(kISplitF * kIMaxPanF, kISplitB * kIMaxPanB) * kIP * J, 0.0);
+  const int tj = n2_pick_tj(J), ncgp = n2_ncg_pow2(J, tj);
+  const int split_f = 5, split_b = 7;                       // odd slice counts, ragged slices
+  std::vector<double> vals((size_t)std::max(split_f * kIMaxPanF, split_b * kIMaxPanB) * kIP * J, 0.0);
   std::vector<double> coef((size_t)std::max(kIMaxPanF, kIMaxPanB) * kIP * J, 0.0);
   std::vector<float> Zx((size_t)N * J, -1.f), dMx((size_t)G * J, -1.f);
   const size_t eval_smem = (size_t)smem_panels * kIP * J * sizeof(double);
+  const size_t n2_smem = n2_smem_bytes(J, tj);
 
-  // forward: nodes -> coefficients -> evaluation per cell (grid.y = 3 here: blocks stride over the active node groups)
-  ca_emul::launch(k_interp_nodes<true, 1>, dim3((J + 31) / 32, 3, kISplitF), dim3(256), 0, (const InterpPlan*)&plan,
-                  (const float*)w.data(), (const float*)nullptr, (const float*)Mx.data(), (int64_t)G, J, vals.data());
-  {
-    ca_emul::launch(k_interp_coeffs, dim3((J + 31) / 32, kIMaxPanF), dim3(kIP * 32), 0, (const InterpPlan*)&plan,
-                    (const double*)vals.data(), kISplitF, kIMaxPanF, J, 1, coef.data());
-  }
+  // forward: nodes -> coefficients -> evaluation per cell (3 blocks stride over the (panel, slice) work items)
+  if (tj == 8)
+    ca_emul::launch(k_interp_nodes2<true, 8>, dim3(3), dim3(kN2Threads), n2_smem, (const InterpPlan*)&plan, (const float*)w.data(),
+                    (const float*)nullptr, (const float*)Mx.data(), (int64_t)G, J, ncgp, split_f, kIMaxPanF, vals.data());
+  else
+    ca_emul::launch(k_interp_nodes2<true, 6>, dim3(3), dim3(kN2Threads), n2_smem, (const InterpPlan*)&plan, (const float*)w.data(),
+                    (const float*)nullptr, (const float*)Mx.data(), (int64_t)G, J, ncgp, split_f, kIMaxPanF, vals.data());
+  ca_emul::launch(k_interp_coeffs2, dim3((J + kC2Cols - 1) / kC2Cols, kIMaxPanF), dim3(kIP * kC2Cols * kC2Lanes), 0,
+                  (const InterpPlan*)&plan, (const double*)vals.data(), split_f, kIMaxPanF, J, 1, coef.data());
   ca_emul::launch(k_interp_eval<true>, dim3(3), dim3(kIEvalWarps * 32), eval_smem, (const InterpPlan*)&plan,
                   (const double*)coef.data(), (const float*)psi.data(), (int64_t)N, J, Zx.data(), smem_panels);
 
-  // backward: nodes over w (reduction over cells, kISplitB partials) -> coefficients -> evaluation per gene
-  ca_emul::launch(k_interp_nodes<false, 1>, dim3((J + 31) / 32, 3, kISplitB), dim3(256), 0,
-                  (const InterpPlan*)&plan, (const float*)psi.data(), (const float*)shift.data(), (const float*)Rx.data(),
-                  (int64_t)N, J, vals.data());
-  {
-    ca_emul::launch(k_interp_coeffs, dim3((J + 31) / 32, kIMaxPanB), dim3(kIP * 32), 0, (const InterpPlan*)&plan,
-                    (const double*)vals.data(), kISplitB, kIMaxPanB, J, 0, coef.data());
-  }
+  // backward: nodes over w (reduction over cells) -> coefficients -> evaluation per gene
+  if (tj == 8)
+    ca_emul::launch(k_interp_nodes2<false, 8>, dim3(4), dim3(kN2Threads), n2_smem, (const InterpPlan*)&plan, (const float*)psi.data(),
+                    (const float*)shift.data(), (const float*)Rx.data(), (int64_t)N, J, ncgp, split_b, kIMaxPanB, vals.data());
+  else
+    ca_emul::launch(k_interp_nodes2<false, 6>, dim3(4), dim3(kN2Threads), n2_smem, (const InterpPlan*)&plan, (const float*)psi.data(),
+                    (const float*)shift.data(), (const float*)Rx.data(), (int64_t)N, J, ncgp, split_b, kIMaxPanB, vals.data());
+  ca_emul::launch(k_interp_coeffs2, dim3((J + kC2Cols - 1) / kC2Cols, kIMaxPanB), dim3(kIP * kC2Cols * kC2Lanes), 0,
+                  (const InterpPlan*)&plan, (const double*)vals.data(), split_b, kIMaxPanB, J, 0, coef.data());
   ca_emul::launch(k_interp_eval<false>, dim3(2), dim3(kIEvalWarps * 32), eval_smem, (const InterpPlan*)&plan,
                   (const double*)coef.data(), (const float*)w.data(), (int64_t)G, J, dMx.data(), smem_panels);
 

@@ -18,7 +18,7 @@ EMUL = os.path.join(ROOT, "tests", "cuda_emul")
 def exe():
     td = tempfile.mkdtemp()
     out = os.path.join(td, "run_interp")
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I", EMUL, os.path.join(EMUL, "run_interp.cpp"), "-o", out])
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-DCA_EMULATE", "-I", EMUL, os.path.join(EMUL, "run_interp.cpp"), "-o", out])
     return out
 
 
@@ -108,7 +108,7 @@ int main(int argc, char** argv) {
     with tempfile.TemporaryDirectory() as td:
         cpp, exe_path = os.path.join(td, "t.cpp"), os.path.join(td, "t")
         open(cpp, "w").write(src)
-        subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I", EMUL, cpp, "-o", exe_path])
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-DCA_EMULATE", "-I", EMUL, cpp, "-o", exe_path])
         for mode, ok in ((0, True), (1, False), (2, True), (3, False), (4, False), (5, True), (6, False)):
             r = subprocess.run([exe_path, str(mode)], capture_output=True, text=True, timeout=120)
             assert (r.returncode == 0) == ok, (mode, r.returncode, r.stderr)

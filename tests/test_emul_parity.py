@@ -18,13 +18,16 @@ pytestmark = pytest.mark.usefixtures("emulated_library")
 # (ypass2 on the CUDA-core path, the epi2-only and the overlap sets are covered by the storage-format test, test_random_shapes_and_variants, test_variants_agree_with_default_kernels and
 # bench.py's candidate tests: on the synchronous emulation `overlap` only changes which stream handle a launch names)
 PATHS = [("cudacore", ""), ("interp", ""), ("interp", "ypass2,epi2,lean"), ("cudacore", "ypass3"),
-         ("interp", "ypass3,epi2,lean"), ("interp", "ypass3,epi2,lean,defer,overlap")]
+         ("interp", "ypass3,epi2,lean"), ("interp", "ypass3,epi2,lean,defer,overlap"), ("auto", "")]
 
 
 def test_emulated_library_is_not_the_product(emulated_library):
     from clonealign_b200 import _lib
     assert "cuda_emul" in emulated_library and "cuda_emul" in _lib.LIB_PATH
     with _session(np.ones((4, 3)), np.ones((3, 2)), np.zeros((4, 1)), np.ones(3), path="auto") as sess:
+        d = sess.describe()                                     # the default model runs the interpolation kernel set
+        assert d["path"] == "interp" and d["variants"] == 2 | 4 | 32 | 64
+    with _session(np.ones((4, 3)), np.ones((3, 2)), np.zeros((4, 2)), np.ones(3), K=2, path="auto") as sess:
         assert sess.describe()["path"] == "cudacore"            # tcgen05 is unavailable under emulation
     from clonealign_b200._lib import CloneAlignLibraryError
     with pytest.raises(CloneAlignLibraryError, match="not available under the CPU emulation|tensor path"):
@@ -37,7 +40,7 @@ def test_gradients_and_elbo_match_oracle_c1(example_sce, path, S):
     Y, L = example_sce
     d, p, mu_guess, _ = _case(Y, L, K=1, seed=S)
     with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path=path[0], variants=path[1], seed=1) as sess:
-        assert sess.describe()["path"] == path[0]
+        assert sess.describe()["path"] == ("interp" if path[0] == "auto" else path[0])
         _load_params(sess, p)
         errs = _check_grads(sess, d, p, S)
         assert errs["Z"] < 1e-5
@@ -195,24 +198,28 @@ def test_storage_formats_and_input_layouts_agree(example_sce):
     Y, L = example_sce
     hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
     run = lambda y, **kw: _run_trace(y, hi["L"], hi["psi_init"], hi["mu_guess"], n=2, seed=7, **kw)[0]
-    traces = [run(hi["Y"], y_store=s) for s in ("f32", "u16", "u8")]
+    # the contraction-kernel paths widen the counts and use the 8-column tiling for every storage type: bit-identical
+    traces = [run(hi["Y"], y_store=s, path="cudacore") for s in ("f32", "u16", "u8")]
     assert traces[0].tobytes() == traces[1].tobytes() == traces[2].tobytes()
-    packed = [run(hi["Y"], y_store=s, variants="ypass2") for s in ("f32", "u16", "u8")]      # f32x2 Y pass: same exactness
+    packed = [run(hi["Y"], y_store=s, path="cudacore", variants="ypass2") for s in ("f32", "u16", "u8")]   # f32x2 Y pass: same exactness
     assert packed[0].tobytes() == packed[1].tobytes() == packed[2].tobytes()
     assert np.abs(packed[0] - traces[0]).max() <= 1e-6 * np.abs(traces[0]).max()             # re-associated sums only
     # ypass3: the stored integer is used as a denormal fp32 operand, the other operand carries the scale -> bit-identical to
     # the arithmetic on widened counts (f32 storage runs the same tiling unscaled); u8 owns 16 columns per thread instead
     # of 8, which only re-associates the row sums
-    y3 = [run(hi["Y"], y_store=s, variants="ypass3") for s in ("f32", "u16", "u8")]
+    y3 = [run(hi["Y"], y_store=s, path="cudacore", variants="ypass3") for s in ("f32", "u16", "u8")]
     assert y3[0].tobytes() == y3[1].tobytes()
     assert np.abs(y3[2] - y3[0]).max() <= 1e-6 * np.abs(y3[0]).max() and np.abs(y3[0] - traces[0]).max() <= 1e-6 * np.abs(traces[0]).max()
+    # the default kernel set (path = auto: interp + ypass3): same statement
+    d3 = [run(hi["Y"], y_store=s) for s in ("f32", "u16", "u8")]
+    assert np.all(np.isfinite(d3[0])) and d3[0].tobytes() == d3[1].tobytes() and np.abs(d3[2] - d3[0]).max() <= 1e-6 * np.abs(d3[0]).max()
     t_f = run(np.asfortranarray(hi["Y"]), y_store="f32")                    # an R double matrix
-    t_i = run(np.asfortranarray(hi["Y"].astype(np.int32)))                  # an R integer matrix
+    t_i = run(np.asfortranarray(hi["Y"].astype(np.int32)))                  # an R integer matrix (stored u8)
     t_32 = run(hi["Y"].astype(np.float32))
-    assert traces[0].tobytes() == t_f.tobytes() == t_i.tobytes() == t_32.tobytes()
+    assert d3[0].tobytes() == t_f.tobytes() and d3[2].tobytes() == t_i.tobytes() == t_32.tobytes()
     import scipy.sparse as sp
     for compact in (hi["Y"].astype(np.uint8), np.asfortranarray(hi["Y"].astype(np.uint16)), sp.csr_matrix(hi["Y"].astype(np.uint8))):
-        assert run(compact).tobytes() == traces[0].tobytes()                  # compact host counts (CA_Y_U8 / CA_Y_U16)
+        assert run(compact).tobytes() == d3[2].tobytes()                      # compact host counts (CA_Y_U8 / CA_Y_U16)
     from clonealign_b200._lib import CloneAlignLibraryError
     with pytest.raises(CloneAlignLibraryError, match="u8"):
         run(hi["Y"] + 0.5, y_store="u8")
@@ -470,35 +477,6 @@ def test_cell_sharded_fit_matches_single_shard(example_sce, path, world):
     assert _relmax(outs[0]["prm"]["W"], ref["prm"]["W"]) < 1e-3 and _relmax(outs[0]["prm"]["alpha"], ref["prm"]["alpha"]) < 1e-4
 
 
-def test_bench_selfcheck_gate_on_the_emulation():
-    """bench.py's on-device gate (selfcheck_run / selfcheck_compare), exercised here with the CUDA-core path standing in
-    for the tcgen05 reference: every candidate kernel set passes it, a deliberately wrong run does not."""
-    import importlib.util
-    import os
-    from clonealign_b200.session import Session
-    from clonealign_b200.synthetic import make_synthetic
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
-    bench = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(bench)
-    syn = make_synthetic(400, 300, 5, seed=3)
-    Y, L = syn["Y"].astype(np.float64), np.minimum(syn["L"], 6.0)
-    rng = np.random.default_rng(1)
-    psi = rng.standard_normal((400, 1))
-    loc = O.safe_inverse_softplus((Y / Y.mean(1, keepdims=True)).mean(0))
-    W0 = rng.standard_normal((300, 1)) * 0.1
-    mk = lambda path, var, **kw: (lambda: Session(Y, L, psi, loc, mc_samples=2, K=1, seed=9, path=path, variants=var, **kw))
-    ref = bench.selfcheck_run(mk("cudacore", ""), W0, timed=False)
-    for path, var in bench.CANDIDATES:
-        if path == "auto":
-            path = "cudacore"                   # no tensor cores under emulation
-        ok, d = bench.selfcheck_compare(ref, bench.selfcheck_run(mk(path, var), W0, timed=False))
-        assert ok, (path, var, d)
-    bad = bench.selfcheck_run(mk("interp", "epi2", learning_rate=0.3), W0, timed=False)     # different optimiser step
-    ok, d = bench.selfcheck_compare(ref, bad)
-    assert not ok and d["grad_psi"] < 1e-3      # same gradients, diverging trace
-
-
 @pytest.mark.parametrize("path", [("cudacore", "ypass2"), ("interp", "ypass2,epi2,lean"), ("interp", "ypass3,epi2,lean")])
 def test_several_row_and_column_tiles(path):
     """N > 2 row blocks of the Y pass (RB = 512), G > one 2048-column tile, more cells than one sweep of the persistent
@@ -699,11 +677,12 @@ def test_device_pca_and_correlations_under_cell_sharding(example_sce):
     np.testing.assert_allclose(want_cor, host, atol=1e-9, equal_nan=True)
 
 
-@pytest.mark.parametrize("path,variants,V", [("interp", "ypass2,epi2,lean", 0), ("cudacore", "", 0), ("interp", "epi2", 25)])
+@pytest.mark.parametrize("path,variants,V", [("auto", "", 0), ("cudacore", "", 0), ("interp", "epi2", 25)])
 def test_bench_flow_on_the_emulation(monkeypatch, capsys, path, variants, V):
-    """bench.py's whole `ours` arm (session, timed steps, per-kernel profile, roofline, fp32-storage measurement, e2e from
-    host buffers, JSON line) executed on the emulated library with a small workload: the contract keys are present and
-    consistent.  (Numbers are meaningless here; the point is that the code path the driver runs cannot raise.)"""
+    """bench.py's whole `ours` arm (session, parity block with the sampled-cell fp64 check, timed blocks, per-kernel profile,
+    roofline, late-training timing, fp32-storage measurement, e2e from host buffers, JSON line) executed on the emulated
+    library with a small workload: the contract keys are present and consistent.  (Numbers are meaningless here; the point
+    is that the code path the driver runs cannot raise.)"""
     import argparse
     import importlib.util
     import json
@@ -720,6 +699,9 @@ def test_bench_flow_on_the_emulation(monkeypatch, capsys, path, variants, V):
     monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
     real_empty = torch.empty
     monkeypatch.setattr(torch, "empty", lambda *a, pin_memory=False, **k: real_empty(*a, **k))
+    monkeypatch.setattr(bench, "MIN_TIMED_MS", 0.0)
+    monkeypatch.setattr(bench, "LATE_STEPS", 4)
+    monkeypatch.setattr(bench, "PARITY_STEPS", 3)
 
     def fake_cuda(N, G, C, seed=2345234, device="cpu", rows=None, literal=False):
         a, b = rows if rows is not None else (0, N)
@@ -729,7 +711,7 @@ def test_bench_flow_on_the_emulation(monkeypatch, capsys, path, variants, V):
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
     args = argparse.Namespace(gpus=1, steps=3, warmup=1, impl="ours", config="c1", y_store="auto", path=path, variants=variants,
-                              selfcheck=False, no_e2e=False, no_cpu_baseline=True, watchdog=0)
+                              no_e2e=False, no_cpu_baseline=True, watchdog=0, quick=False)
     cfg = dict(N=300, G=900 if path == "cudacore" else 260, C=4, S=2, name="emulated mini workload")   # G = 900: u8 counts
     if V:
         cfg["V"] = V                         # the allele-specific configuration (BASELINE config 4 in miniature)
@@ -738,44 +720,23 @@ def test_bench_flow_on_the_emulation(monkeypatch, capsys, path, variants, V):
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "clocks", "gpu_launches", "roofline", "step_hbm", "e2e", "cpu_baseline"):
         assert key in line, key
-    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["value"] > 0 and line["gpu_launches"] > 0
-    assert line["config"]["path"] == path and line["config"]["variants"] == variants and line["config"]["y_store"] in ("u8", "u16")
-    assert line["roofline"]["kernel"] == "ypass" and line["roofline"]["bound"] == "hbm" if path == "interp" else True
+    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["warmup"] == 3 and line["value"] > 0 and line["gpu_launches"] > 0
+    want = "interp" if path == "auto" else path
+    assert line["config"]["path"] == want and line["config"]["y_store"] in ("u8", "u16")
+    assert line["config"]["timing"]["blocks"] >= 5 and len(line["config"]["timing"]["ms_blocks"]) == line["config"]["timing"]["blocks"]
+    par = line["config"]["parity"]
+    assert par["steps"] == 3 and np.isfinite(par["elbo_start"]) and par["elbo_after"] > par["elbo_start"] and len(par["hard_calls_sha256"]) == 16
+    assert par["sampled_cell_check"]["ok"], par["sampled_cell_check"]
+    assert line["roofline"]["kernel"] == "ypass" and line["roofline"]["bound"] == "hbm" if want == "interp" else True
     assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-12
     assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(line["e2e"]["seconds"]) == {"upload_and_setup", "gamma_init_and_first_elbo", "loop", "params_download"}
     if line["config"]["y_store"] == "u8":
-        assert line["e2e_compact_host"]["value"] > 0 and line["e2e_compact_host"]["final_elbo"] == line["e2e"]["final_elbo"]
+        assert line["e2e"]["host_dtype"] == "uint8" and line["e2e_f32_host"]["final_elbo"] == line["e2e"]["final_elbo"]
     assert line["alt_fp32_storage"]["y_store"] == "f32" and line["alt_fp32_storage"]["step_hbm"]["bytes_per_step"] > line["step_hbm"]["bytes_per_step"]
-    assert np.isfinite(line["config"]["elbo_start"]) and line["config"]["elbo_end"] > line["config"]["elbo_start"]
-
-
-def test_bench_selfcheck_child_on_the_emulation(monkeypatch, capsys):
-    """`bench.py --selfcheck` (the child process of the default run) end to end on the emulated library, with the
-    CUDA-core kernels standing in for the tcgen05 reference: one JSON verdict per candidate, all passing."""
-    import argparse
-    import importlib.util
-    import json
-    import os
-    import torch
-    from clonealign_b200 import _lib, session, synthetic
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
-    bench = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(bench)
-    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
-    monkeypatch.setitem(session._PATH, "tensor", _lib.PATH_CUDACORE)          # no tensor cores under emulation
-
-    def fake_cuda(N, G, C, seed=2345234, device="cpu", rows=None, literal=False):
-        syn = synthetic.make_synthetic(N, G, C, seed=seed)
-        return dict(Y=torch.from_numpy(syn["Y"].astype(np.float32)), L=syn["L"], z=syn["z"], s=syn["s"])
-    monkeypatch.setattr(synthetic, "make_synthetic_cuda", fake_cuda)
-    args = argparse.Namespace(y_store="auto", config="c1")
-    with pytest.raises(SystemExit) as ex:
-        bench.run_selfcheck(args, dict(N=260, G=300, C=4, S=2, name="mini"))
-    assert ex.value.code == 0
-    rows = [json.loads(ln) for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
-    assert [tuple(r["candidate"]) for r in rows] == [("tensor", "")] + bench.CANDIDATES
-    assert all(r["ok"] and r["ms_per_step"] > 0 for r in rows), [r for r in rows if not r["ok"]]
+    assert line["late_training"]["ms_per_step"] > 0 and line["late_training"]["elbo"] > par["elbo_start"]
+    if want == "interp":
+        assert line["config"]["panels"]["nb"] >= 1 and line["late_training"]["panels"]["nb"] >= 1
 
 
 @pytest.mark.parametrize("path", [("cudacore", ""), ("interp", ""), ("interp", "ypass2,epi2,lean")])

@@ -172,6 +172,24 @@ def test_synthetic_generator():
     assert 0.5 < np.corrcoef(rs, a["s"])[0, 1]            # s_n is the library size in the benchmark variant
 
 
+def test_device_generator_is_shard_invariant():
+    """make_synthetic_cuda draws the counts in 1024-row blocks with their own seeded generators: the rows a rank draws are
+    exactly the rows of the matrix one device would draw, wherever the shard boundaries fall (run on the torch CPU
+    generator here; the bench's 1-vs-2/4/8-GPU parity block relies on it)."""
+    from clonealign_b200 import dist as D
+    from clonealign_b200.synthetic import make_synthetic_cuda
+    N, G, C = 2500, 64, 4
+    full = make_synthetic_cuda(N, G, C, seed=5, device="cpu")
+    assert tuple(full["Y"].shape) == (N, G) and float(full["Y"].sum(dim=1).min()) > 0
+    for world in (2, 3, 8):
+        parts = [make_synthetic_cuda(N, G, C, seed=5, device="cpu", rows=D.shard_bounds(N, r, world)) for r in range(world)]
+        import torch
+        assert torch.equal(torch.cat([p["Y"] for p in parts]), full["Y"])
+        assert np.array_equal(np.concatenate([p["z"] for p in parts]), full["z"])
+    other = make_synthetic_cuda(N, G, C, seed=6, device="cpu")
+    assert not np.array_equal(other["Y"].numpy(), full["Y"].numpy())
+
+
 def test_run_clonealign_spreads_restarts_over_devices(monkeypatch):
     """run_clonealign (R/clonealign.R:35-75): restarts pinned round-robin to `devices`, run from one host thread per
     GPU, results kept in the serial order and the max-ELBO fit returned.  The fit itself is faked (no GPU here)."""
@@ -298,150 +316,6 @@ def test_sharding_algebra_gloo_world2():
                              env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "RANK_OK_0" in out.stdout and "RANK_OK_1" in out.stdout
-
-
-def test_bench_candidate_selection(monkeypatch, tmp_path):
-    """bench.py --path best: the fastest candidate that passed the on-device check wins; a candidate that failed, a
-    crashed child, or candidates slower than the tcgen05 path fall back to ("auto", "")."""
-    import argparse
-    import importlib.util
-    import json
-    import tempfile as tf
-    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
-    bench = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(bench)
-    monkeypatch.setattr(tf, "gettempdir", lambda: str(tmp_path))
-    args = argparse.Namespace(config="c1", y_store="auto")
-
-    def fake(lines, rc=0):
-        """A child that prints `lines` (tensor row + candidate verdicts in CANDIDATES order, honouring --selfcheck-skip)
-        and exits with `rc` on its first start, 0 afterwards."""
-        state = {"first": True}
-
-        def run(cmd, **k):
-            skip = int(cmd[cmd.index("--selfcheck-skip") + 1])
-            cand = [x for x in lines if x["candidate"][0] != "tensor"][skip:]
-            head = [x for x in lines if x["candidate"][0] == "tensor"]
-
-            class R:
-                stdout = "warming up\n" + "\n".join(json.dumps(x) for x in head + cand) + "\n"
-                stderr = ""
-                returncode = rc if state["first"] else 0
-            state["first"] = False
-            return R
-        return run
-
-    C = bench.CANDIDATES
-    rows = [{"candidate": ["tensor", ""], "ok": True, "ms_per_step": 3.3},
-            {"candidate": list(C[0]), "ok": True, "ms_per_step": 1.4},
-            {"candidate": list(C[1]), "ok": False, "ms_per_step": 0.9},
-            {"candidate": list(C[2]), "ok": True, "ms_per_step": 1.1}]
-    monkeypatch.setattr(bench.subprocess, "run", fake(rows, rc=1))          # died on the 4th candidate: incomplete, not cached
-    pick, info = bench.interp_selfcheck(args)
-    assert pick == C[2] and len(info["candidates"]) == 5 and not info["candidates"][4]["ok"]
-    full = rows[:1] + [{"candidate": list(c), "ok": True, "ms_per_step": 5.0 + i} for i, c in enumerate(C)]
-    monkeypatch.setattr(bench.subprocess, "run", fake(full))
-    assert bench.interp_selfcheck(args)[0] == ("auto", "")                   # every candidate slower than the tensor path
-    monkeypatch.setattr(bench.subprocess, "run", fake([]))                   # (the complete verdict above was cached)
-    pick, info = bench.interp_selfcheck(args)
-    assert pick == ("auto", "") and "cached" in info["note"]
-    args.config = "c2"
-    assert bench.interp_selfcheck(args)[0] == ("auto", "")                   # no output at all
-
-
-def test_bench_selfcheck_resumes_behind_a_faulting_candidate(monkeypatch, tmp_path):
-    """A candidate that takes the CUDA context down (child exit code 3 after its verdict) or that kills / hangs the child
-    without a verdict must not keep the candidates behind it from being checked: the child is restarted behind it."""
-    import argparse
-    import importlib.util
-    import json
-    import tempfile as tf
-    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
-    bench = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(bench)
-    monkeypatch.setattr(tf, "gettempdir", lambda: str(tmp_path))
-    args = argparse.Namespace(config="c1", y_store="auto")
-    C = bench.CANDIDATES
-    tensor = {"candidate": ["tensor", ""], "ok": True, "ms_per_step": 3.3}
-    ok = lambda i, ms: {"candidate": list(C[i]), "ok": True, "ms_per_step": ms}
-    calls = []
-
-    def run(cmd, **kw):
-        skip = int(cmd[cmd.index("--selfcheck-skip") + 1])
-        calls.append(skip)
-
-        class R:
-            stderr = ""
-        if skip == 0:      # candidate 2 faults after its verdict was printed
-            R.stdout = "\n".join(json.dumps(x) for x in [tensor, ok(0, 1.5), ok(1, 1.4),
-                                                         {"candidate": list(C[2]), "ok": False, "error": "CUDA error cudaErrorIllegalAddress"}])
-            R.returncode = bench.SELFCHECK_RESUME_RC
-        elif skip == 3:    # candidate 4 kills the process (no verdict)
-            R.stdout = "\n".join(json.dumps(x) for x in [tensor, ok(3, 1.2)])
-            R.returncode = -11
-        else:              # the rest runs through
-            R.stdout = "\n".join(json.dumps(x) for x in [tensor] + [ok(i, 0.6 + 0.01 * i) for i in range(skip, len(C))])
-            R.returncode = 0
-        return R
-    monkeypatch.setattr(bench.subprocess, "run", run)
-    pick, info = bench.interp_selfcheck(args)
-    assert calls == [0, 3, 5]
-    rows = info["candidates"]
-    assert [tuple(r["candidate"]) for r in rows] == [("tensor", "")] + C          # one verdict per candidate, in order
-    assert not rows[3]["ok"] and "CUDA error" in rows[3]["error"] and not rows[5]["ok"] and "died" in rows[5]["error"]
-    assert pick == C[5] and "child exit -11" in info["note"]                       # fastest of the ones that passed
-    # nothing comes back at all (the tcgen05 reference itself fails): one attempt, no verdicts, default kernels
-    calls.clear()
-    args.config = "c2"
-
-    def dead(cmd, **kw):
-        calls.append(1)
-
-        class R:
-            stdout, stderr, returncode = "", "boom", 1
-        return R
-    monkeypatch.setattr(bench.subprocess, "run", dead)
-    pick, info = bench.interp_selfcheck(args)
-    assert pick == ("auto", "") and calls == [1] and "reference run did not complete" in info["note"]
-
-
-def test_bench_falls_back_once_when_the_selected_kernel_set_fails(monkeypatch):
-    """A kernel set that passed the child's gate but raises in the full run restarts bench.py ONCE in a fresh process
-    with --path auto (the parity-tested kernels); the restarted process does not loop, and an explicit --path never
-    falls back."""
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
-    bench = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(bench)
-    calls = []
-
-    def boom(args, cfg):
-        raise RuntimeError("CUDA error cudaErrorIllegalAddress at core.cu:1")
-
-    def fake_exec(exe, argv):
-        calls.append(argv)
-        raise SystemExit(77)                                   # execv does not return
-
-    monkeypatch.setattr(bench, "run_ours", boom)
-    monkeypatch.setattr(bench.os, "execv", fake_exec)
-    for k in ("WORLD_SIZE", "CLONEALIGN_B200_BENCH_FALLBACK"):
-        monkeypatch.delenv(k, raising=False)
-    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--watchdog", "0"])
-    with pytest.raises(SystemExit) as ex:
-        bench.main()
-    assert ex.value.code == 77 and calls[0][-2:] == ["--path", "auto"] and "--steps" in calls[0]
-    assert "cudaErrorIllegalAddress" in os.environ["CLONEALIGN_B200_BENCH_FALLBACK"]
-    with pytest.raises(RuntimeError):                           # the restarted process: no second restart
-        bench.main()
-    monkeypatch.delenv("CLONEALIGN_B200_BENCH_FALLBACK")
-    monkeypatch.setattr(sys, "argv", ["bench.py", "--path", "interp", "--watchdog", "0"])
-    with pytest.raises(RuntimeError):                           # an explicit path is what the caller asked for
-        bench.main()
-    monkeypatch.setenv("WORLD_SIZE", "2")
-    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "2", "--watchdog", "0"])
-    with pytest.raises(RuntimeError):                           # ranks of a torchrun job cannot restart on their own
-        bench.main()
-    assert len(calls) == 1
 
 
 def test_r_shim_compiles_against_stub_headers():
