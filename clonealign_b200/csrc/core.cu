@@ -241,6 +241,7 @@ struct ca_handle {
   bool epi2 = false;               // interp path: fused Clenshaw + per-cell epilogue (kernels_fused.cuh)
   bool lean = false;               // with epi2: k_prologue / k_gene_fused / k_adam_all
   bool defer = false;              // with lean: Y-linear terms added after the per-cell kernel (late join of the Y pass)
+  bool cosched = false;            // with defer + ypass4: the Y pass starts first in the step, next to everything up to the gene kernel
   bool pending_join = false;       // a Y pass forked onto stream2 has not been joined yet
   int n_yv_blocks = 0;             // ELBO partials written by k_yv_dot (behind the per-cell kernel's in elbo_part)
   double* chi_cur = nullptr;
@@ -375,7 +376,12 @@ void run_ypass(ca_handle* h, cudaStream_t st) {
     if (h->KP == 1) {
       LaunchScope ls(h, "ypass");
       dim3 grid(h->nCB, h->nRB);
-      if (h->variants & CA_VAR_YPASS3) {
+      if (h->variants & CA_VAR_YPASS4) {
+        const int64_t tiles = (int64_t)h->nCB * h->nRB;
+        const unsigned g4 = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)h->num_sms);
+        CA_LAUNCH(k_ypass_k1_v4<T>, g4, 256, ypass4_smem_bytes<T>(), st)(Yp, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm,
+                                                                          h->rowpart, h->colpart);
+      } else if (h->variants & CA_VAR_YPASS3) {
         CA_LAUNCH(k_ypass_k1_v3<T>, grid, 256, 0, st)(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
       } else if (h->variants & CA_VAR_YPASS2) {
         CA_LAUNCH(k_ypass_k1_v2<T>, grid, 256, 0, st)(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
@@ -479,7 +485,7 @@ void run_forward(ca_handle* h, int mode) {
   // The Y stream (HBM-bound, touches only Y, psi, W) is independent of the forward contraction (tensor / MUFU
   // bound): fork it onto a second stream so both run on the SMs at once; joined before the per-cell epilogue.
   bool joined_later = false;
-  const bool want_fork = mode != EPI_INIT && h->overlap && !h->prof_on && h->ydirty && h->KP > 0;
+  const bool want_fork = mode != EPI_INIT && (h->overlap || h->cosched) && !h->prof_on && h->ydirty && h->KP > 0;
   auto fork_ypass = [&]() {
     CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
     CUDA_OK(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
@@ -491,7 +497,7 @@ void run_forward(ca_handle* h, int mode) {
   // pass started here would only push the short gene-level launches (prologue, node sums, coefficients: the head of the
   // step's critical path) behind its first wave; started together with the per-cell kernel (half a register file per
   // CTA) it shares every SM with it instead.
-  if (want_fork && !h->defer) fork_ypass();
+  if (want_fork && (!h->defer || h->cosched)) fork_ypass();   // cosched: the persistent 2-CTA-per-SM pass goes first, everything else fits next to it
   SampleMuArgs sm;
   sm.G = h->G; sm.C = h->C; sm.S = h->S; sm.K = h->K; sm.KP = h->KP; sm.SCp = h->SCp; sm.J = h->J; sm.Gld = h->Gld;
   sm.loc = h->loc; sm.lsd = h->lsd; sm.Vm = h->Vm; sm.L = h->L; sm.colsum = h->colsum; sm.chi_raw = h->chi_raw;
@@ -573,10 +579,10 @@ void run_forward(ca_handle* h, int mode) {
     a.defer_yv = h->defer ? 1 : 0;
     // DEFER + OVERLAP: the pass may start once everything before the per-cell kernel is done (event recorded here), but
     // it is handed to the device AFTER the per-cell kernel, whose 148 persistent CTAs should be placed first
-    if (want_fork && h->defer) CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
+    if (want_fork && h->defer && !h->cosched) CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
     launch_fused(h, mode, a);
     KCHECK();
-    if (want_fork && h->defer) {
+    if (want_fork && h->defer && !h->cosched) {
       CUDA_OK(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
       run_ypass(h, h->stream2);
       CUDA_OK(cudaEventRecord(h->ev_join, h->stream2));
@@ -903,12 +909,12 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   const bool interp_ok = c.K == 1 && c.P == 0 && c.C <= kFusedMaxC && c.S * c.C <= 32 * kFusedMaxNJ;
   if (c.path == CA_PATH_AUTO && interp_ok) {
     h->cfg.path = CA_PATH_INTERP;
-    if (!(h->cfg.variants & (CA_VAR_YPASS2 | CA_VAR_YPASS3))) h->cfg.variants |= CA_VAR_YPASS3;
+    if (!(h->cfg.variants & (CA_VAR_YPASS2 | CA_VAR_YPASS3 | CA_VAR_YPASS4))) h->cfg.variants |= CA_VAR_YPASS3;
     h->cfg.variants |= CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_DEFER;
   }
   h->interp = (c.path == CA_PATH_INTERP);
   h->variants = c.variants;
-  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_P2P | CA_VAR_OVERLAP | CA_VAR_YPASS3 | CA_VAR_DEFER))
+  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_P2P | CA_VAR_OVERLAP | CA_VAR_YPASS3 | CA_VAR_DEFER | CA_VAR_YPASS4 | CA_VAR_COSCHED))
     fail("unknown kernel variant bits 0x%x", c.variants);
   if ((c.variants & CA_VAR_P2P) && c.world > kP2PMaxWorld) fail("variant p2p supports at most %d ranks", kP2PMaxWorld);
   h->p2p = (c.variants & CA_VAR_P2P) && c.world > 1;
@@ -919,6 +925,11 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if ((c.variants & CA_VAR_YPASS2) && c.K + c.P != 1) fail("variant ypass2 needs K + P == 1");
   if ((c.variants & CA_VAR_YPASS3) && c.K + c.P != 1) fail("variant ypass3 needs K + P == 1");
   if ((c.variants & CA_VAR_YPASS3) && (c.variants & CA_VAR_YPASS2)) fail("variants ypass2 and ypass3 are alternatives");
+  if ((c.variants & CA_VAR_YPASS4) && c.K + c.P != 1) fail("variant ypass4 needs K + P == 1");
+  if ((c.variants & CA_VAR_YPASS4) && (c.variants & (CA_VAR_YPASS2 | CA_VAR_YPASS3))) fail("variants ypass2, ypass3 and ypass4 are alternatives");
+  if ((c.variants & CA_VAR_COSCHED) && !((c.variants & CA_VAR_DEFER) && (c.variants & CA_VAR_YPASS4)))
+    fail("variant cosched needs variants defer and ypass4");
+  h->cosched = (c.variants & CA_VAR_COSCHED) != 0;
   if (c.variants & CA_VAR_EPI2) {
     if (!h->interp) fail("variant epi2 belongs to the interp path (path = interp)");
     if (c.C > kFusedMaxC || c.S * c.C > 32 * kFusedMaxNJ) fail("variant epi2 needs C <= %d and S*C <= %d", kFusedMaxC, 32 * kFusedMaxNJ);
@@ -1092,11 +1103,11 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   h->ar = z((size_t)G * (2 + KP) + C + 4);
   if (KP == 1) {
     int tile_cols = kYCB;
-    if (h->variants & CA_VAR_YPASS3)   // column tile of k_ypass_k1_v3: 256 threads x the columns a thread owns for this storage type
+    if (h->variants & (CA_VAR_YPASS3 | CA_VAR_YPASS4))   // column tile of k_ypass_k1_v3 / v4: 256 threads x the columns a thread owns for this storage type
       tile_cols = h->ystore == CA_STORE_U8 ? ypass3_tile_cols<uint8_t>() : (h->ystore == CA_STORE_U16 ? ypass3_tile_cols<uint16_t>() : ypass3_tile_cols<float>());
     h->nCB = (int)ceil_div64(h->ldY, tile_cols);
     h->RB = 512;
-    if (h->variants & CA_VAR_YPASS3) {
+    if (h->variants & (CA_VAR_YPASS3 | CA_VAR_YPASS4)) {
       // Size the row blocks so that the grid is (just under) a whole number of waves of the 2 CTAs an SM holds: with
       // 512-row blocks config 3 gives 5 x 196 = 980 CTAs = 3.31 waves of 296, i.e. a last wave that is one third full
       // on the kernel that bounds the step; 432-row blocks give 5 x 232 = 1160 CTAs = 3.92 waves.  Small problems get
@@ -1169,6 +1180,11 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
       CUDA_OK(cudaFuncSetAttribute(k_interp_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ieval_smem));
     }
   }
+  if (h->variants & CA_VAR_YPASS4) {
+    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v4<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ypass4_smem_bytes<float>()));
+    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v4<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ypass4_smem_bytes<uint16_t>()));
+    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v4<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ypass4_smem_bytes<uint8_t>()));
+  }
   if (h->lean) {
     h->chi_cur = h->alloc<double>(std::max(K, 1));
     h->pmm_part = h->alloc<float>(2 * kProPsiBlocks);
@@ -1183,7 +1199,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     h->fused_nj = (h->SC + 31) / 32;
     // defer + overlap: 16 warps x 64 registers = half of the register file, so that one Y-pass CTA (256 threads x 128
     // registers, the other half) can be resident on the same SM while the per-cell kernel runs
-    h->fused_warps = (h->defer && (c.variants & CA_VAR_OVERLAP)) ? kFusedWarps / 2 : kFusedWarps;
+    h->fused_warps = (h->defer && (c.variants & (CA_VAR_OVERLAP | CA_VAR_COSCHED))) ? kFusedWarps / 2 : kFusedWarps;
     if (h->fused_warps != kFusedWarps) {
       // the Y-pass CTA must fit next to ~200 KB of shared memory: ask for the maximum shared-memory carveout, otherwise the
       // SM would have to drain before it can be reconfigured (measured in round 1 for the contraction kernels)
@@ -1194,7 +1210,9 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
       CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v2<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v2<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
-    h->fused_panels = fused_smem_panels(h->SC, C, J, 200 * 1024, h->fused_warps);
+    // cosched: two persistent Y-pass CTAs (64 KB rings) stay resident on every SM; the per-cell CTA gets what is left
+    const size_t fused_budget = h->cosched ? 92 * 1024 : 200 * 1024;
+    h->fused_panels = fused_smem_panels(h->SC, C, J, fused_budget, h->fused_warps);
     if (const char* e = getenv("CLONEALIGN_B200_FUSED_PANELS"))   // test hook: force the coefficients-through-L2 branch
       h->fused_panels = std::max(0, std::min(h->fused_panels, atoi(e)));
     h->fused_smem = fused_smem_bytes(h->SC, C, J, h->fused_panels, h->fused_warps);

@@ -88,8 +88,14 @@ enum ca_path     { CA_PATH_AUTO = 0, CA_PATH_CUDACORE = 1, CA_PATH_TENSOR = 2, C
  *   P2P   : (world > 1) the per-step all-reduce as one kernel over NVLink peer memory instead of ncclAllReduce; needs
  *           ca_core_p2p_export / ca_core_p2p_connect after ca_core_create, see kernels_p2p.cuh
  *   OVERLAP: the Y pass (HBM-bound; needs only Y, psi, W) is forked onto a second stream at the start of the step and
- *           joined before the per-cell kernel, so it runs next to the small gene-level launches instead of after them */
-enum ca_variant  { CA_VAR_YPASS2 = 1, CA_VAR_EPI2 = 2, CA_VAR_LEAN = 4, CA_VAR_P2P = 8, CA_VAR_OVERLAP = 16, CA_VAR_YPASS3 = 32, CA_VAR_DEFER = 64 };
+ *           joined before the per-cell kernel, so it runs next to the small gene-level launches instead of after them
+ *   YPASS4: the arithmetic and tiling of YPASS3 with the rows staged through a per-thread shared-memory ring by cp.async
+ *           (bytes in flight while the thread computes, half the registers), launched as a persistent grid of 2 CTAs per SM
+ *   COSCHED: (with DEFER + YPASS4) the Y pass is started FIRST in the step on the second stream and joined before the
+ *           gene-gradient kernel; the per-cell kernel runs with 16 warps so that both fit on every SM: the HBM-bound stream
+ *           runs next to the issue-bound kernels of the whole step */
+enum ca_variant  { CA_VAR_YPASS2 = 1, CA_VAR_EPI2 = 2, CA_VAR_LEAN = 4, CA_VAR_P2P = 8, CA_VAR_OVERLAP = 16, CA_VAR_YPASS3 = 32, CA_VAR_DEFER = 64,
+                   CA_VAR_YPASS4 = 128, CA_VAR_COSCHED = 256 };
 
 typedef struct ca_config {
   int64_t N;            /* cells held by this handle (this rank's shard)                       */

@@ -18,7 +18,8 @@ pytestmark = pytest.mark.usefixtures("emulated_library")
 # (ypass2 on the CUDA-core path, the epi2-only and the overlap sets are covered by the storage-format test, test_random_shapes_and_variants, test_variants_agree_with_default_kernels and
 # bench.py's candidate tests: on the synchronous emulation `overlap` only changes which stream handle a launch names)
 PATHS = [("cudacore", ""), ("interp", ""), ("interp", "ypass2,epi2,lean"), ("cudacore", "ypass3"),
-         ("interp", "ypass3,epi2,lean"), ("interp", "ypass3,epi2,lean,defer,overlap"), ("auto", "")]
+         ("interp", "ypass3,epi2,lean"), ("interp", "ypass3,epi2,lean,defer,overlap"), ("auto", ""),
+         ("interp", "ypass4,epi2,lean,defer,cosched"), ("cudacore", "ypass4")]
 
 
 def test_emulated_library_is_not_the_product(emulated_library):
@@ -477,7 +478,8 @@ def test_cell_sharded_fit_matches_single_shard(example_sce, path, world):
     assert _relmax(outs[0]["prm"]["W"], ref["prm"]["W"]) < 1e-3 and _relmax(outs[0]["prm"]["alpha"], ref["prm"]["alpha"]) < 1e-4
 
 
-@pytest.mark.parametrize("path", [("cudacore", "ypass2"), ("interp", "ypass2,epi2,lean"), ("interp", "ypass3,epi2,lean")])
+@pytest.mark.parametrize("path", [("cudacore", "ypass2"), ("interp", "ypass2,epi2,lean"), ("interp", "ypass3,epi2,lean"),
+                                  ("interp", "ypass4,epi2,lean,defer,cosched")])
 def test_several_row_and_column_tiles(path):
     """N > 2 row blocks of the Y pass (RB = 512), G > one 2048-column tile, more cells than one sweep of the persistent
     per-cell / per-gene kernels: tile seams, partial-sum layouts and strided loops."""

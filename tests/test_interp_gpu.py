@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 
 VARIANTS = ["", "ypass2", "epi2", "ypass2,epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap", "ypass3", "ypass3,epi2,lean",
-            "ypass3,epi2,lean,defer", "ypass3,epi2,lean,defer,overlap"]
+            "ypass3,epi2,lean,defer", "ypass3,epi2,lean,defer,overlap", "ypass4", "ypass4,epi2,lean,defer", "ypass4,epi2,lean,defer,cosched"]
 
 
 @pytest.mark.parametrize("variants", VARIANTS)
@@ -29,7 +29,8 @@ def test_interp_gradients_and_elbo_match_oracle_c1(example_sce, S, variants):
         assert errs["Z"] < 1e-5
 
 
-@pytest.mark.parametrize("variants", ["", "ypass2,epi2", "ypass2,epi2,lean", "ypass3,epi2,lean", "ypass3,epi2,lean,defer,overlap"])
+@pytest.mark.parametrize("variants", ["", "ypass2,epi2", "ypass2,epi2,lean", "ypass3,epi2,lean", "ypass3,epi2,lean,defer,overlap",
+                                      "ypass4,epi2,lean,defer,cosched"])
 @pytest.mark.parametrize("N,G,C,S", [(130, 70, 5, 3), (257, 193, 2, 1), (64, 640, 7, 8), (1000, 333, 12, 8), (300, 4100, 32, 4)])
 def test_interp_ragged_shapes(N, G, C, S, variants):
     from clonealign_b200.synthetic import make_synthetic
@@ -62,6 +63,17 @@ def test_ypass3_storage_formats_agree(example_sce, path):
     f32, u16, u8 = run("f32"), run("u16"), run("u8")
     assert np.all(np.isfinite(f32)) and f32.tobytes() == u16.tobytes()
     assert np.abs(u8 - f32).max() <= 1e-6 * np.abs(f32).max()
+
+
+@pytest.mark.parametrize("store", ["f32", "u16", "u8"])
+def test_ypass4_is_bit_identical_to_ypass3(example_sce, store):
+    """ypass4 = the arithmetic and tiling of ypass3 with the rows staged through a shared-memory ring by cp.async and a
+    persistent grid: the same partial sums in the same order, so whole traces agree bit for bit (also co-scheduled)."""
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
+    run = lambda v: _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], mc_samples=2, seed=7, path="interp", variants=v, y_store=store)[0]
+    a, b, c = run("ypass3,epi2,lean,defer"), run("ypass4,epi2,lean,defer"), run("ypass4,epi2,lean,defer,cosched")
+    assert np.all(np.isfinite(a)) and a.tobytes() == b.tobytes() == c.tobytes()
 
 
 def test_interp_wide_range_uses_many_panels(example_sce):
@@ -216,7 +228,8 @@ def _full_size_check(N, G, C, S, path, variants, V=0, n_sample=48, z_tol=2e-6, w
         sess.close()
 
 
-@pytest.mark.parametrize("variants", ["", "ypass2,epi2,lean", "ypass3,epi2,lean", "ypass3,epi2,lean,defer,overlap"])
+@pytest.mark.parametrize("variants", ["", "ypass2,epi2,lean", "ypass3,epi2,lean", "ypass3,epi2,lean,defer,overlap",
+                                      "ypass4,epi2,lean,defer,cosched"])
 def test_full_size_c3_interp(variants):
     """BASELINE config 3 (100k x 20k x 12, S = 8) on the interpolation path: Z is near-exact (fp64 node sums), unlike the
     tcgen05 path's round-toward-zero accumulation."""
