@@ -1091,7 +1091,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   h->shift = z(N + 64); h->mm = z(2); h->log_alpha = z(C);
   h->YV = z((size_t)N * std::max(KP, 1)); h->YtU = z((size_t)G * std::max(KP, 1)); h->Fout = z((size_t)N * C);
   h->dM_sum = z((size_t)G * J);
-  h->n_gene_blocks = h->lean ? (G + kProThreads - 1) / kProThreads : (G + 255) / 256;
+  h->n_gene_blocks = (int)ceil_div64((int64_t)G * S, h->lean ? kProThreads : 256);   // one thread per (sample, gene) pair
   h->n_epi_blocks = ceil_div64(N, kEpiWarps);
   h->n_cell_parts = h->epi2 ? (int64_t)h->num_sms : h->n_epi_blocks;
   h->gene_part = h->alloc<double>(h->n_gene_blocks);

@@ -207,19 +207,23 @@ struct SampleMuArgs {
 };
 
 // body shared by k_sample_mu (one launch of its own) and k_prologue (variant lean: gene blocks of the fused launch).
+// One thread per (sample, gene) pair, gene index fastest: the [S][G] arrays are written coalesced and S x G threads (160 000
+// at config 3) fill the machine -- one thread per gene looping over its S samples left 40 blocks on 148 SMs and took
+// 36 us, all of it replicated on every rank of a cell-sharded fit (ncu of round 2, profiles/r02_notes.md).
 // VEC4 (C % 4 == 0, K = 1 layouts only): the C values a gene contributes to one sample are contiguous in Mx
 // ([g][s*C + c]), so they leave as 16-byte stores instead of C scattered 4-byte stores per (gene, sample).
 template <bool VEC4>
 __device__ __forceinline__ void sample_mu_body(const SampleMuArgs& a, int block, double* scratch, double* part_out) {
-  int g = block * blockDim.x + threadIdx.x;
+  const int64_t idx = (int64_t)block * blockDim.x + threadIdx.x;
+  const int s = (int)(idx / a.G), g = (int)(idx - (int64_t)s * a.G);
   double e = 0.0;
-  if (g < a.G) {
+  if (s < a.S) {
     float loc = a.loc[g], lsd = a.lsd[g], sd = expf(lsd);
     double cs = (double)a.colsum[g];
     float vk[kMaxKP];
 #pragma unroll
     for (int kp = 0; kp < kMaxKP; ++kp) vk[kp] = kp < a.KP ? a.Vm[(int64_t)g * a.KP + kp] : 0.f;
-    for (int s = 0; s < a.S; ++s) {
+    {
       float eps = a.eps_in ? a.eps_in[(int64_t)s * a.G + g] : normal_draw(a.seed, a.draw, (uint32_t)s, (uint32_t)g);
       float x = loc + sd * eps;
       float mu = softplusf(x);
@@ -262,10 +266,11 @@ __device__ __forceinline__ void sample_mu_body(const SampleMuArgs& a, int block,
       }
     }
     e /= (double)a.S;
-    for (int k = 0; k < a.K; ++k) {   // Normal(0, chi^-1/2) prior on W, R/inference-tflow.R:312-313
-      double cr = (double)a.chi_raw[k], w = (double)vk[k];
-      e += -0.5 * exp(cr) * w * w + 0.5 * cr - 0.5 * kLog2Pi;
-    }
+    if (s == 0)
+      for (int k = 0; k < a.K; ++k) {   // Normal(0, chi^-1/2) prior on W, R/inference-tflow.R:312-313 (once per gene)
+        double cr = (double)a.chi_raw[k], w = (double)vk[k];
+        e += -0.5 * exp(cr) * w * w + 0.5 * cr - 0.5 * kLog2Pi;
+      }
   }
   double t = block_sum(e, scratch);
   if (threadIdx.x == 0) part_out[block] = t;

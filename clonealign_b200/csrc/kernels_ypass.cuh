@@ -437,7 +437,7 @@ k_ypass_k1_v3(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, co
 // issue slots 41 % busy, the top stall is long_scoreboard -- every warp loads 8 rows into REGISTERS, waits about a
 // microsecond, then spends about as long on its ~430 instructions: the loads of the next rows are not in flight while it
 // computes (128 registers per thread leave no room to double-buffer them), and 2 CTAs take the whole register file, so
-// nothing else can share the SM with the stream.  Here the rows travel by cp.async (LDGSTS, L2 evict-first) into a
+// nothing else can share the SM with the stream.  Here the rows travel by cp.async (LDGSTS, L1 bypassed) into a
 // shared-memory ring of kRing rows per thread -- every thread copies exactly the 16-byte pieces it consumes itself, so a
 // cp.async.wait_group is all the synchronisation the data needs (no barrier, no cross-thread visibility) -- and are read
 // back one row at a time; the slot of row r - 1 is refilled (row r - 1 + kRing) while row r is processed.  Bytes in flight
@@ -452,20 +452,10 @@ template <typename T> struct Y4Ring { static constexpr int kRing = 16; };     //
 template <> struct Y4Ring<float> { static constexpr int kRing = 8; };         // 32-byte pieces
 template <typename T> constexpr size_t ypass4_smem_bytes() { return (size_t)Y4Ring<T>::kRing * 256 * sizeof(typename Y3<T>::Raw); }
 
-#ifdef CA_EMULATE
-__device__ __forceinline__ void y4_copy16(void* dst, const void* src, uint64_t) { memcpy(dst, src, 16); }
+// (An L2 evict-first cache hint on the copies -- createpolicy + cp.async...L2::cache_hint -- assembled but trapped with
+// cudaErrorIllegalInstruction on the B200 of round 2; the plain .cg form, which bypasses L1, is used.)
+__device__ __forceinline__ void y4_copy16(void* dst, const void* src, uint64_t) { cp_async16(dst, src); }
 __device__ __forceinline__ uint64_t y4_policy() { return 0; }
-#else
-__device__ __forceinline__ uint64_t y4_policy() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void y4_copy16(void* dst, const void* src, uint64_t pol) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "l"(pol) : "memory");
-}
-#endif
 
 template <typename T>
 __global__ void __launch_bounds__(256, 4)
