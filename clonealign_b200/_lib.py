@@ -17,14 +17,16 @@ Y_HOST, Y_DEVICE = 0, 1
 STORE_AUTO, STORE_F32, STORE_U16, STORE_U8 = 0, 1, 2, 3
 PATH_AUTO, PATH_CUDACORE, PATH_TENSOR, PATH_INTERP = 0, 1, 2, 3
 VAR_YPASS2, VAR_EPI2, VAR_LEAN, VAR_P2P, VAR_OVERLAP, VAR_YPASS3, VAR_DEFER, VAR_YPASS4, VAR_COSCHED = 1, 2, 4, 8, 16, 32, 64, 128, 256
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 EXPORTS = (
     "ca_core_abi_version", "ca_core_device_count", "ca_core_nccl_unique_id", "ca_core_create",
     "ca_core_destroy", "ca_core_init_gamma", "ca_core_step", "ca_core_elbo", "ca_core_params",
     "ca_core_set_eps", "ca_core_get_eps", "ca_core_grads", "ca_core_get_array", "ca_core_set_array",
     "ca_core_time_steps", "ca_core_profile_step", "ca_core_describe", "ca_core_correlations", "ca_core_pca_scores", "ca_core_p2p_export", "ca_core_p2p_connect", "ca_core_data_create", "ca_core_data_destroy",
-    "ca_core_create_shared", "ca_core_ypass_many", "ca_core_data_stats", "ca_core_elbo_many",
+    "ca_core_create_shared", "ca_core_ypass_many", "ca_core_data_stats", "ca_core_elbo_many", "ca_core_shutdown",
+    "ca_core_multi_create", "ca_core_multi_destroy", "ca_core_multi_init_gamma", "ca_core_multi_step", "ca_core_multi_elbo",
+    "ca_core_multi_elbo_many", "ca_core_multi_params", "ca_core_multi_time_steps", "ca_core_multi_shard", "ca_core_multi_size",
 )
 
 
@@ -86,6 +88,17 @@ def load():
     lib.ca_core_p2p_export.argtypes = [vp, vp, cp, sz]
     lib.ca_core_p2p_connect.argtypes = [vp, vp, cp, sz]
     lib.ca_core_pca_scores.argtypes = [vp, C.c_int32, C.c_double, vp, C.POINTER(C.c_int32), cp, sz]
+    lib.ca_core_shutdown.argtypes = []
+    lib.ca_core_multi_create.argtypes = [C.POINTER(vp), C.POINTER(CaConfig), vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, cp, sz]
+    lib.ca_core_multi_destroy.argtypes = [vp]
+    lib.ca_core_multi_init_gamma.argtypes = [vp, cp, sz]
+    lib.ca_core_multi_step.argtypes = [vp, cp, sz]
+    lib.ca_core_multi_elbo.argtypes = [vp, dp, cp, sz]
+    lib.ca_core_multi_elbo_many.argtypes = [vp, C.c_int32, vp, cp, sz]
+    lib.ca_core_multi_params.argtypes = [vp] + [vp] * 9 + [cp, sz]
+    lib.ca_core_multi_time_steps.argtypes = [vp, C.c_int32, C.c_int32, dp, cp, sz]
+    lib.ca_core_multi_shard.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.ca_core_multi_size.argtypes = [vp]
     for n in EXPORTS:
         getattr(lib, n).restype = C.c_int
     if lib.ca_core_abi_version() != ABI_VERSION:

@@ -12,6 +12,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <stdexcept>
 #include <type_traits>
 #include <string>
@@ -128,6 +131,35 @@ constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;
     if (_r != 0) fail("NCCL error %d at %s:%d: %s", _r, __FILE__, __LINE__, nccl().GetErrorString(_r)); \
   } while (0)
 
+// Communicators are expensive to build (ncclCommInitRank: 0.3 - 1 s with 8 ranks) and a process usually runs several
+// sessions of the same shape one after another (restarts, the set-up of a benchmark and its end-to-end run), so a
+// released communicator is kept per (world, rank, device) and handed to the next session of that shape; every rank
+// of a job creates and releases its sessions in the same order, so all ranks hit (or miss) the cache together.
+// ca_core_shutdown() destroys what is parked.
+struct CommKey {
+  int world, rank, dev;
+  bool operator<(const CommKey& o) const { return std::tie(world, rank, dev) < std::tie(o.world, o.rank, o.dev); }
+};
+std::mutex& comm_mu() { static std::mutex m; return m; }
+std::map<CommKey, std::vector<void*>>& comm_pool() { static std::map<CommKey, std::vector<void*>> p; return p; }
+void* comm_acquire(int world, int rank, int dev, const void* id128) {
+  {
+    std::lock_guard<std::mutex> lk(comm_mu());
+    auto& v = comm_pool()[CommKey{world, rank, dev}];
+    if (!v.empty()) { void* c = v.back(); v.pop_back(); return c; }
+  }
+  Uid id;
+  memcpy(&id, id128, sizeof id);
+  void* c = nullptr;
+  NCCL_OK(nccl().CommInitRank(&c, world, id, rank));
+  return c;
+}
+void comm_release(int world, int rank, int dev, void* c) {
+  if (!c) return;
+  std::lock_guard<std::mutex> lk(comm_mu());
+  comm_pool()[CommKey{world, rank, dev}].push_back(c);
+}
+
 // ------------------------------------------------------------------------------------------------
 // conversion kernels (ingest)
 // ------------------------------------------------------------------------------------------------
@@ -241,6 +273,7 @@ struct ca_handle {
   bool epi2 = false;               // interp path: fused Clenshaw + per-cell epilogue (kernels_fused.cuh)
   bool lean = false;               // with epi2: k_prologue / k_gene_fused / k_adam_all
   bool defer = false;              // with lean: Y-linear terms added after the per-cell kernel (late join of the Y pass)
+  int y4_minb = 4;                 // k_ypass_k1_v4 register budget: sized for 4 (64 registers) or 3 (80) CTAs per SM
   bool cosched = false;            // with defer + ypass4: the Y pass starts first in the step, next to everything up to the gene kernel
   bool pending_join = false;       // a Y pass forked onto stream2 has not been joined yet
   int n_yv_blocks = 0;             // ELBO partials written by k_yv_dot (behind the per-cell kernel's in elbo_part)
@@ -379,8 +412,13 @@ void run_ypass(ca_handle* h, cudaStream_t st) {
       if (h->variants & CA_VAR_YPASS4) {
         const int64_t tiles = (int64_t)h->nCB * h->nRB;
         const unsigned g4 = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)h->num_sms);
-        CA_LAUNCH(k_ypass_k1_v4<T>, g4, 256, ypass4_smem_bytes<T>(), st)(Yp, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm,
-                                                                          h->rowpart, h->colpart);
+        if (h->y4_minb == 3) {
+          auto k = k_ypass_k1_v4<T, 3>;
+          CA_LAUNCH(k, g4, 256, ypass4_smem_bytes<T>(), st)(Yp, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm, h->rowpart, h->colpart);
+        } else {
+          auto k = k_ypass_k1_v4<T, 4>;
+          CA_LAUNCH(k, g4, 256, ypass4_smem_bytes<T>(), st)(Yp, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm, h->rowpart, h->colpart);
+        }
       } else if (h->variants & CA_VAR_YPASS3) {
         CA_LAUNCH(k_ypass_k1_v3<T>, grid, 256, 0, st)(Yp, h->ldY, h->N, h->G, h->RB, h->U, h->Vm, h->rowpart, h->colpart);
       } else if (h->variants & CA_VAR_YPASS2) {
@@ -442,7 +480,7 @@ void launch_interp_nodes(ca_handle* h, const float* rv, const float* shift, cons
     auto k = k_interp_nodes2<FWD, 6>;
     CA_LAUNCH(k, grid, kN2Threads, h->n2_smem, h->stream)(h->iplan, rv, shift, B, R, h->J, h->n2_ncgp, nsplit, max_pan, h->ivals);
   }
-  CA_LAUNCH(k_interp_coeffs2, dim3((h->J + kC2Cols - 1) / kC2Cols, max_pan), kIP * kC2Cols * kC2Lanes, 0, h->stream)(
+  CA_LAUNCH(k_interp_coeffs2, dim3((h->J + kC2Cols - 1) / kC2Cols, kC2PanelsY), kIP * kC2Cols * kC2Lanes, 0, h->stream)(
       h->iplan, h->ivals, nsplit, max_pan, h->J, FWD ? 1 : 0, h->icoef);
 }
 
@@ -846,7 +884,7 @@ void destroy(ca_handle* h) {
   if (!h) return;
   cudaSetDevice(h->dev);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  if (h->comm) nccl().CommDestroy(h->comm);
+  if (h->comm) comm_release(h->cfg.world, h->cfg.rank, h->dev, h->comm);   // parked for the next session of this shape
   for (int r = 0; r < kP2PMaxWorld; ++r)
     if (h->p2p_mapped[r]) cudaIpcCloseMemHandle(h->p2p_mapped[r]);
   tc_plan_destroy(h->tcplan);
@@ -868,7 +906,6 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if (c.K + c.P > kMaxKP) fail("K + P = %d exceeds the supported maximum of %d", c.K + c.P, kMaxKP);
   if (c.world < 1 || c.rank < 0 || c.rank >= c.world) fail("bad rank/world");
   if (c.world > 1 && !c.nccl_id) fail("world > 1 requires cfg.nccl_id");
-  if (c.world > 1 && !colsum_total) fail("world > 1 requires colsum_total (global column sums of Y)");
   if (!h->shared && (!Y || !L)) fail("missing input pointer");
   if (!h->data_only && (!loc_init || (c.K > 0 && !psi_init) || (c.P > 0 && !X))) fail("missing input pointer");
   if (!h->shared && c.V > 0 && (!clone_allele || !alt || !cov)) fail("V > 0 requires clone_allele, alt and cov");
@@ -892,6 +929,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  if (c.world > 1) h->comm = comm_acquire(c.world, c.rank, h->dev, c.nccl_id);   // collective (first session of this shape)
   // Measured on B200 (profiles/r01_notes.md): co-scheduling the Y stream with the forward contraction does not pay
   // yet (the register-light Y kernel is slower than the saved time), so the fork is opt-in.
   h->overlap = getenv("CLONEALIGN_B200_OVERLAP") != nullptr || (c.variants & CA_VAR_OVERLAP);
@@ -1018,15 +1056,24 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     CUDA_OK(cudaMemcpyAsync(h->colsum, cs.data(), sizeof(float) * G, cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
   } else {
+    // colSums(Y) (R/inference-tflow.R:117) over this shard in fp64; under cell sharding the shards' sums are added
+    // with one all-reduce (collective: every rank passes colsum_total == NULL or none does)
     const int RS = 64;
     double* part = h->alloc<double>((size_t)RS * G);
+    double* tot = h->alloc<double>(G);
     dim3 grid((G + 127) / 128, RS);
     CA_LAUNCH(k_colsum_part<float>, grid, 128, 0, h->stream)(Yf, h->ldY, N, G, RS, part);
     KCHECK();
-    CA_LAUNCH(k_colsum_final, (G + 127) / 128, 128, 0, h->stream)(part, RS, G, h->colsum);
+    CA_LAUNCH(k_colsum_final, (G + 127) / 128, 128, 0, h->stream)(part, RS, G, h->colsum, tot);
     KCHECK();
+    if (c.world > 1) {
+      NCCL_OK(nccl().AllReduce(tot, tot, (size_t)G, kNcclFloat64, kNcclSum, h->comm, h->stream));
+      CA_LAUNCH(k_colsum_final, (G + 127) / 128, 128, 0, h->stream)(tot, 1, G, h->colsum, nullptr);
+      KCHECK();
+    }
     CUDA_OK(cudaStreamSynchronize(h->stream));
     h->release(part);
+    h->release(tot);
   }
   if (c.V > 0) {
     int V = c.V;
@@ -1181,9 +1228,11 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     }
   }
   if (h->variants & CA_VAR_YPASS4) {
-    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v4<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ypass4_smem_bytes<float>()));
-    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v4<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ypass4_smem_bytes<uint16_t>()));
-    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v4<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ypass4_smem_bytes<uint8_t>()));
+    if (const char* e = getenv("CLONEALIGN_B200_Y4_MINB")) h->y4_minb = atoi(e) == 3 ? 3 : 4;
+    auto set4 = [&](auto kern, size_t bytes) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); };
+    set4(k_ypass_k1_v4<float, 3>, ypass4_smem_bytes<float>()); set4(k_ypass_k1_v4<float, 4>, ypass4_smem_bytes<float>());
+    set4(k_ypass_k1_v4<uint16_t, 3>, ypass4_smem_bytes<uint16_t>()); set4(k_ypass_k1_v4<uint16_t, 4>, ypass4_smem_bytes<uint16_t>());
+    set4(k_ypass_k1_v4<uint8_t, 3>, ypass4_smem_bytes<uint8_t>()); set4(k_ypass_k1_v4<uint8_t, 4>, ypass4_smem_bytes<uint8_t>());
   }
   if (h->lean) {
     h->chi_cur = h->alloc<double>(std::max(K, 1));
@@ -1200,6 +1249,8 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     // defer + overlap: 16 warps x 64 registers = half of the register file, so that one Y-pass CTA (256 threads x 128
     // registers, the other half) can be resident on the same SM while the per-cell kernel runs
     h->fused_warps = (h->defer && (c.variants & (CA_VAR_OVERLAP | CA_VAR_COSCHED))) ? kFusedWarps / 2 : kFusedWarps;
+    if (h->cosched && h->y4_minb == 3) h->fused_warps = 12;     // 2 x 256 x 80 registers for the stream leave 24 K of the 64 K
+    if (const char* e = getenv("CLONEALIGN_B200_FUSED_WARPS")) h->fused_warps = std::max(1, std::min(kFusedWarps, atoi(e)));
     if (h->fused_warps != kFusedWarps) {
       // the Y-pass CTA must fit next to ~200 KB of shared memory: ask for the maximum shared-memory carveout, otherwise the
       // SM would have to drain before it can be reconfigured (measured in round 1 for the contraction kernels)
@@ -1240,11 +1291,6 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     h->p2p_buf = (float*)h->alloc<unsigned char>(slot_bytes + 256 + sizeof(unsigned) * 2 * kP2PMaxWorld);
     h->p2p_ticket = h->alloc<unsigned>(1);
     h->p2p_err = h->alloc<int>(1);
-  }
-  if (c.world > 1) {
-    Uid id;
-    memcpy(&id, c.nccl_id, sizeof id);
-    NCCL_OK(nccl().CommInitRank(&h->comm, c.world, id, c.rank));
   }
   CUDA_OK(cudaStreamSynchronize(h->stream));
 }
@@ -1301,6 +1347,17 @@ bool lookup(ca_handle* h, const std::string& n, ArrayRef& r) {
 extern "C" {
 
 int ca_core_abi_version(void) { return CA_ABI_VERSION; }
+
+int ca_core_shutdown(void) {
+  std::lock_guard<std::mutex> lk(comm_mu());
+  for (auto& kv : comm_pool())
+    for (void* c : kv.second) {
+      cudaSetDevice(kv.first.dev);
+      nccl().CommDestroy(c);
+    }
+  comm_pool().clear();
+  return 0;
+}
 
 int ca_core_device_count(int* count, char* err, size_t errlen) {
   try {

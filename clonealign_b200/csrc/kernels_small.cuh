@@ -69,12 +69,14 @@ __global__ void k_colsum_part(const T* __restrict__ Y, int64_t ldY, int64_t N, i
   for (int64_t r = r0; r < r1; ++r) a += (double)(float)Y[r * ldY + g];
   part[(int64_t)rs * G + g] = a;
 }
-__global__ void k_colsum_final(const double* __restrict__ part, int RS, int G, float* __restrict__ colsum) {
+__global__ void k_colsum_final(const double* __restrict__ part, int RS, int G, float* __restrict__ colsum,
+                               double* __restrict__ colsum_d /* optional fp64 copy (summed over shards by the caller) */) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   double a = 0.0;
   for (int r = 0; r < RS; ++r) a += part[(int64_t)r * G + g];
   colsum[g] = (float)a;
+  if (colsum_d) colsum_d[g] = a;
 }
 
 // allele-specific (beta-binomial) cell x clone log-likelihood, R/allele-specific.R:17-58.

@@ -433,50 +433,78 @@ k_ypass_k1_v3(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// v4 of the KP == 1 tile (variant YPASS4), from the round-2 ncu capture of v3 (profiles/r02_notes.md): 16 warps per SM,
-// issue slots 41 % busy, the top stall is long_scoreboard -- every warp loads 8 rows into REGISTERS, waits about a
-// microsecond, then spends about as long on its ~430 instructions: the loads of the next rows are not in flight while it
-// computes (128 registers per thread leave no room to double-buffer them), and 2 CTAs take the whole register file, so
-// nothing else can share the SM with the stream.  Here the rows travel by cp.async (LDGSTS, L1 bypassed) into a
-// shared-memory ring of kRing rows per thread -- every thread copies exactly the 16-byte pieces it consumes itself, so a
-// cp.async.wait_group is all the synchronisation the data needs (no barrier, no cross-thread visibility) -- and are read
-// back one row at a time; the slot of row r - 1 is refilled (row r - 1 + kRing) while row r is processed.  Bytes in flight
-// no longer cost registers: kRing - 2 rows per thread are outstanding WHILE the thread computes (14 x 16 B against 8 x 16 B
-// that are only outstanding while it waits), and the kernel needs half the registers.  It is launched as a PERSISTENT grid
-// of 2 CTAs per SM (fixed tile assignment: deterministic) that leaves half of the register file and ~100 KB of shared
-// memory of every SM free: started first in the step on the second stream, the HBM-bound stream runs NEXT TO the
-// issue-bound kernels of the step (prologue, node sums, per-cell kernel) instead of before / after them.
+// v4 of the KP == 1 tile (variant YPASS4), from the round-2 ncu captures (profiles/r02_notes.md).  v3: 16 warps per SM,
+// issue slots 41 % busy, top stall long_scoreboard -- every warp loads 8 rows into REGISTERS, waits about a microsecond,
+// then spends about as long on its ~430 instructions: nothing is in flight while it computes (128 registers per thread
+// leave no room to double-buffer), and 2 CTAs take the whole register file, so nothing can share the SM with the stream.
+// A first ring of per-thread cp.async copies (LDGSTS) removed the stall but cost +57 % instructions (address arithmetic,
+// one commit / wait and three compiler-inserted dummy LDS per 16-byte copy): issue-bound at the same speed.
+// Here the rows travel by BULK copies (cp.async.bulk, the TMA engine): the 32 lanes of a warp own 32 x 16 = 512
+// consecutive bytes of a row, so ONE lane issues one 512-byte copy per (warp, row) into the warp's own shared-memory ring
+// (16 rows = 4 stages of 4 rows, one mbarrier per stage counting bytes); every lane then reads its 16-byte piece with one
+// LDS.128.  A stage is re-armed and refilled as soon as it has been consumed.  Bytes in flight cost neither registers nor
+// issue slots: 12 rows per warp are outstanding WHILE it computes, the kernel needs half the registers, and it is
+// launched as a PERSISTENT grid of 2 CTAs per SM (fixed tile assignment: deterministic) that leaves half of the register
+// file and ~100 KB of shared memory of every SM free: started first in the step on the second stream (variant COSCHED),
+// the HBM-bound stream runs NEXT TO the issue-bound kernels of the step instead of before / after them.
 // Arithmetic, tiling (256 x kCols columns) and partial-sum layouts are those of v3: bit-identical results.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T> struct Y4Ring { static constexpr int kRing = 16; };     // rows in the ring: 64 KB per CTA
-template <> struct Y4Ring<float> { static constexpr int kRing = 8; };         // 32-byte pieces
-template <typename T> constexpr size_t ypass4_smem_bytes() { return (size_t)Y4Ring<T>::kRing * 256 * sizeof(typename Y3<T>::Raw); }
+constexpr int kY4StageRows = 4;
+template <typename T> struct Y4Ring { static constexpr int kStages = 4; };    // 16 rows x 512 B per warp: 64 KB per CTA
+template <> struct Y4Ring<float> { static constexpr int kStages = 2; };       // 1024-byte rows
+template <typename T> constexpr size_t ypass4_smem_bytes() {
+  return (size_t)Y4Ring<T>::kStages * kY4StageRows * 256 * sizeof(typename Y3<T>::Raw) + 8 * 8 * Y4Ring<T>::kStages + 16;
+}
 
-// (An L2 evict-first cache hint on the copies -- createpolicy + cp.async...L2::cache_hint -- assembled but trapped with
-// cudaErrorIllegalInstruction on the B200 of round 2; the plain .cg form, which bypasses L1, is used.)
-__device__ __forceinline__ void y4_copy16(void* dst, const void* src, uint64_t) { cp_async16(dst, src); }
-__device__ __forceinline__ uint64_t y4_policy() { return 0; }
+#ifdef CA_EMULATE   // functional stand-ins: the issuing lane copies synchronously, a wait is a warp barrier
+__device__ __forceinline__ void y4_bar_init(uint64_t*, int) {}
+__device__ __forceinline__ void y4_arm(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void y4_bulk(void* dst, const void* src, uint32_t bytes, uint64_t*) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void y4_wait(uint64_t*, uint32_t) { __syncwarp(); }
+__device__ __forceinline__ void y4_fence_init() {}
+__device__ __forceinline__ void y4_fence_proxy() {}
+#else
+__device__ __forceinline__ void y4_bar_init(uint64_t* bar, int count) { ptx::mbar_init(ptx::smem_u32(bar), (uint32_t)count); }
+__device__ __forceinline__ void y4_arm(uint64_t* bar, uint32_t bytes) { ptx::mbar_expect_tx(ptx::smem_u32(bar), bytes); }
+__device__ __forceinline__ void y4_bulk(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  ptx::bulk_load_1d(ptx::smem_u32(dst), src, bytes, ptx::smem_u32(bar));
+}
+__device__ __forceinline__ void y4_wait(uint64_t* bar, uint32_t parity) { ptx::mbar_wait(ptx::smem_u32(bar), parity); }
+__device__ __forceinline__ void y4_fence_init() { ptx::fence_barrier_init(); }
+__device__ __forceinline__ void y4_fence_proxy() { ptx::fence_proxy_async_smem(); }
+#endif
 
-template <typename T>
-__global__ void __launch_bounds__(256, 4)
+// MINB = CTAs per SM the register allocation is sized for: 4 -> 64 registers (a few spills in the row loop), 3 -> 80
+template <typename T, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, int nCB, int nRB, const float* __restrict__ U,
               const float* __restrict__ Vm, float* __restrict__ rowpart, float* __restrict__ colpart) {
   using L = Y3<T>;
   using Raw = typename L::Raw;
-  constexpr int kRing = Y4Ring<T>::kRing, kCols = L::kCols, kPairs = kCols / 2;
-  constexpr int kPieces = sizeof(Raw) / 16;                      // 16-byte pieces per (thread, row): 1 (u8, u16) or 2 (f32)
+  constexpr int kStages = Y4Ring<T>::kStages, kSR = kY4StageRows, kCols = L::kCols, kPairs = kCols / 2;
+  constexpr uint32_t kRowBytes = 32 * sizeof(Raw);               // one row of the warp's column strip
   CA_DYNAMIC_SMEM(unsigned char, ring_raw);
-  Raw* ring = reinterpret_cast<Raw*>(ring_raw) + threadIdx.x;    // [slot][thread]: this thread's column of slots
-  __shared__ float red[2][8][8];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  Raw* wring = reinterpret_cast<Raw*>(ring_raw) + (size_t)wid * kStages * kSR * 32;        // this warp's ring [slot][lane]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_raw + (size_t)kStages * kSR * 256 * sizeof(Raw)) + wid * kStages;
+  __shared__ float red[2][8][8];
   const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-  const uint64_t pol = y4_policy();
+  // the ring starts zeroed: lanes past the last stored column never receive data and must read zeros, not stale bits
+  for (int i = lane; i < kStages * kSR * 32; i += 32) wring[i] = L::zero();
+  if (lane == 0)
+    for (int st = 0; st < kStages; ++st) y4_bar_init(bars + st, 1);
+  y4_fence_init();
+  __syncthreads();
+  uint32_t sc = 0;                                               // stages issued == consumed so far by this warp (all tiles)
   const int64_t ntiles = (int64_t)nCB * nRB;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int cb = (int)(tile % nCB);
     const int64_t rb = tile / nCB;
-    const int64_t col0 = (int64_t)cb * (256 * kCols) + tid * kCols;
-    const bool colok = col0 < ldY;
+    const int64_t wcol0 = (int64_t)cb * (256 * kCols) + (int64_t)wid * 32 * kCols;         // first column of the warp's strip
+    const int64_t col0 = wcol0 + lane * kCols;
+    // bytes of a row that exist for this warp (the stored row ends at ldY; ldY and the strip start are multiples of 16 bytes)
+    const int64_t avail = (ldY - wcol0) * (int64_t)sizeof(T);
+    const uint32_t wbytes = avail <= 0 ? 0u : (avail < (int64_t)kRowBytes ? (uint32_t)avail : kRowBytes);
     float2 vr[kPairs], cacc[kPairs];
 #pragma unroll
     for (int j = 0; j < kPairs; ++j) {
@@ -485,27 +513,26 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
     }
     const int64_t rbeg = rb * RB, rend = (rbeg + RB < N) ? rbeg + RB : N;
     const int nrows = (int)(rend - rbeg);
+    const int nst = (nrows + kSR - 1) / kSR;                     // stages of this tile
     const int ngroups = (nrows + 7) / 8;
-    const T* ybase = Y + rbeg * ldY + col0;
-    // row `r` of the tile -> its slot; rows past the end of the tile (and threads past the last column) hold zeros.
-    // Exactly ONE group is committed per call, so that "all but the newest kRing - 2 groups" means "up to row r".
-    auto fill = [&](int r, int slot) {
-      Raw* dst = ring + (size_t)slot * 256;
-      if (colok && r < nrows) {
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(ybase + (int64_t)r * ldY);
-#pragma unroll
-        for (int q = 0; q < kPieces; ++q) y4_copy16(reinterpret_cast<unsigned char*>(dst) + 16 * q, src + 16 * q, pol);
-      } else if (r < ngroups * 8) {
-        *dst = L::zero();
-      }
-      cp_async_commit();
+    const T* ybase = Y + rbeg * ldY + wcol0;
+    // stage `t` of the tile (rows 4 t ..) -> ring stage (sc0 + t) % kStages; issued by lane 0 only
+    const uint32_t sc0 = sc;
+    auto issue = [&](int t) {
+      if (t >= nst || wbytes == 0u) return;
+      const uint32_t st = (sc0 + (uint32_t)t) % kStages;
+      const int r0 = t * kSR;
+      const int nv = nrows - r0 < kSR ? nrows - r0 : kSR;
+      y4_arm(bars + st, (uint32_t)nv * wbytes);
+      for (int i = 0; i < nv; ++i)
+        y4_bulk(wring + ((size_t)st * kSR + i) * 32, ybase + (int64_t)(r0 + i) * ldY, wbytes, bars + st);
     };
-#pragma unroll
-    for (int r = 0; r < kRing; ++r) fill(r, r);
+    if (lane == 0)
+      for (int t = 0; t < kStages; ++t) issue(t);
+    __syncwarp();
     int buf = 0;
     for (int g = 0; g < ngroups; ++g) {
       const int64_t r0 = rbeg + (int64_t)g * 8;
-      const int sbase = (g * 8) % kRing;
       float u[8];   // U is allocated with 64 elements of slack, r0 is a multiple of 4: vector loads stay in bounds
 #pragma unroll
       for (int i = 0; i < 8; i += 4) {
@@ -514,25 +541,45 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
       }
       float rp[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        cp_async_wait<kRing - 2>();                              // row 8 g + i has landed (this thread's own copies)
-        const Raw raw = ring[(size_t)(sbase + i) * 256];
-        // refill the slot of the PREVIOUS row (its value was consumed by the FMAs of the last iteration)
-        const int rprev = g * 8 + i - 1;
-        if (rprev >= 0) fill(rprev + kRing, (sbase + i - 1 + kRing) % kRing);
-        float2 y[kPairs];
-        L::unpack(raw, y);
-        const float2 u2 = make_float2(u[i], u[i]);
-        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+      for (int hh = 0; hh < 2; ++hh) {
+        const int t = 2 * g + hh;                                // stage of the tile
+        if (t < nst) {
+          const uint32_t scur = sc0 + (uint32_t)t, st = scur % kStages;
+          if (wbytes != 0u) y4_wait(bars + st, (scur / kStages) & 1u);
+          const Raw* src = wring + (size_t)st * kSR * 32 + lane;
+          const int nv = nrows - t * kSR;                         // valid rows of this stage (>= 1)
+          if (nv < kSR) {
+            // last stage of the tile: its trailing rows were not copied and hold stale ring contents.  Every lane zeroes
+            // its own pieces (it reads them back itself below); the proxy fence orders these generic stores before the
+            // bulk copy that refills the stage later.
+            for (int i = nv; i < kSR; ++i) wring[((size_t)st * kSR + i) * 32 + lane] = L::zero();
+            y4_fence_proxy();
+          }
 #pragma unroll
-        for (int j = 0; j < kPairs; j += 2) {
-          acc0 = __ffma2_rn(y[j], vr[j], acc0);
-          acc1 = __ffma2_rn(y[j + 1], vr[j + 1], acc1);
-          cacc[j] = __ffma2_rn(y[j], u2, cacc[j]);
-          cacc[j + 1] = __ffma2_rn(y[j + 1], u2, cacc[j + 1]);
+          for (int i = 0; i < kSR; ++i) {
+            const Raw raw = src[(size_t)i * 32];
+            float2 y[kPairs];
+            L::unpack(raw, y);
+            const float2 u2 = make_float2(u[hh * kSR + i], u[hh * kSR + i]);
+            float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < kPairs; j += 2) {
+              acc0 = __ffma2_rn(y[j], vr[j], acc0);
+              acc1 = __ffma2_rn(y[j + 1], vr[j + 1], acc1);
+              cacc[j] = __ffma2_rn(y[j], u2, cacc[j]);
+              cacc[j + 1] = __ffma2_rn(y[j + 1], u2, cacc[j + 1]);
+            }
+            const float2 a2 = __fadd2_rn(acc0, acc1);
+            rp[hh * kSR + i] = a2.x + a2.y;
+          }
+          // every lane has issued the FMAs that consume its pieces of this stage (in-order issue: their LDS have returned),
+          // so the stage can be re-armed and refilled at once: kStages - 1 stages stay in flight while the warp computes
+          __syncwarp();
+          if (lane == 0) issue(t + kStages);
+        } else {
+#pragma unroll
+          for (int i = 0; i < kSR; ++i) rp[hh * kSR + i] = 0.f;
         }
-        const float2 a2 = __fadd2_rn(acc0, acc1);
-        rp[i] = a2.x + a2.y;
       }
       const float tot = butterfly8(rp, lane);
       if ((lane & 3) == 0) red[buf][wid][ridx] = tot;
@@ -545,13 +592,13 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
       }
       buf ^= 1;
     }
-    cp_async_wait<0>();
+    sc = sc0 + (uint32_t)nst;
 #pragma unroll
     for (int j = 0; j < kPairs; ++j) {
       if (col0 + 2 * j < G) colpart[rb * G + col0 + 2 * j] = cacc[j].x * L::kPost;
       if (col0 + 2 * j + 1 < G) colpart[rb * G + col0 + 2 * j + 1] = cacc[j].y * L::kPost;
     }
-    __syncthreads();   // `red` is reused by the next tile
+    __syncthreads();   // `red` is reused by the next tile; every warp has consumed every stage it issued
   }
 }
 

@@ -427,3 +427,133 @@ class Session:
             self.close()
         except Exception:
             pass
+
+
+class MultiSession:
+    """One fit with its cells sharded over several GPUs of THIS process (ca_core_multi_*): what an R user gets with
+    `options(clonealign.gpus = ...)` -- the R interpreter is single-threaded, so the library owns one worker thread per
+    device and builds the communicator itself.  Same lifecycle and results as `Session`; `params()` covers all cells.
+    Y must be a host array (numpy, any layout / supported dtype) or a scipy.sparse matrix."""
+
+    def __init__(self, Y, L, psi_init, loc_init, *, devices, mc_samples=1, K=1, x=None, learning_rate=0.1, seed=0,
+                 clone_allele=None, alt=None, cov=None, y_store="auto", path="auto", variants=None):
+        self._m = None
+        if path == "auto":
+            path = os.environ.get("CLONEALIGN_B200_PATH", "auto")
+        if variants is None:
+            variants = os.environ.get("CLONEALIGN_B200_VARIANTS", "")
+        lib = _lib.load()
+        self._lib = lib
+        self._err = C.create_string_buffer(1024)
+        cfg = _lib.CaConfig()
+        keep = []
+        N, G, Cn, V, yptr, Lm, ca, al, cv = _marshal_data(Y, L, clone_allele, alt, cov, cfg, keep)
+        if cfg.y_mem != _lib.Y_HOST:
+            raise ValueError("MultiSession needs Y in host memory")
+        K = int(K)
+        psi = _f64_colmajor(psi_init, (N, K)) if K > 0 else None
+        loc = _f64_colmajor(loc_init, (G,))
+        X, P = None, 0
+        if x is not None:
+            X = np.asarray(x, dtype=np.float64)
+            if X.ndim == 1:
+                X = X[:, None]
+            if X.shape[0] != N:
+                raise ValueError("x must have one row per cell")
+            P = X.shape[1]
+            X = np.asfortranarray(X)
+        devs = [int(d) for d in devices]
+        if not devs:
+            raise ValueError("devices must name at least one GPU")
+        cfg.N, cfg.N_total = N, N
+        cfg.G, cfg.C, cfg.S, cfg.K, cfg.P, cfg.V = G, Cn, int(mc_samples), K, P, V
+        cfg.learning_rate, cfg.seed = float(learning_rate), int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.device, cfg.rank, cfg.world = devs[0], 0, 1
+        cfg.y_store, cfg.path, cfg.y_ld = _STORE[y_store], _PATH[path], 0
+        cfg.variants = variant_mask(variants)
+        darr = (C.c_int32 * len(devs))(*devs)
+        m = C.c_void_p()
+        _lib.check(lib.ca_core_multi_create(C.byref(m), C.byref(cfg), darr, len(devs), yptr, _ptr(Lm), _ptr(psi), _ptr(loc), _ptr(X),
+                                            _ptr(ca), _ptr(al), _ptr(cv), self._err, len(self._err)), self._err)
+        self._m = m
+        self.N, self.G, self.C, self.S, self.K, self.P, self.V = N, G, Cn, int(mc_samples), K, P, V
+        self.devices = devs
+        del keep
+
+    def _chk(self, st):
+        _lib.check(st, self._err)
+
+    def init_gamma(self):
+        self._chk(self._lib.ca_core_multi_init_gamma(self._m, self._err, len(self._err)))
+
+    def step(self):
+        self._chk(self._lib.ca_core_multi_step(self._m, self._err, len(self._err)))
+
+    def elbo(self) -> float:
+        out = C.c_double(0.0)
+        self._chk(self._lib.ca_core_multi_elbo(self._m, C.byref(out), self._err, len(self._err)))
+        return out.value
+
+    def elbo_many(self, n: int) -> np.ndarray:
+        out = np.zeros(int(n), dtype=np.float64)
+        self._chk(self._lib.ca_core_multi_elbo_many(self._m, int(n), out.ctypes.data_as(C.c_void_p), self._err, len(self._err)))
+        return out
+
+    def params(self) -> dict:
+        N, G, Cn, K, P = self.N, self.G, self.C, self.K, self.P
+        f = lambda *shape: np.zeros(shape, dtype=np.float64, order="F")
+        mu, cp, s, alpha = f(G), f(N, Cn), f(N), f(Cn)
+        psi = f(N, K) if K > 0 else None
+        W = f(G, K) if K > 0 else None
+        chi = f(K) if K > 0 else None
+        beta = f(G, P) if P > 0 else None
+        snv = f(N, Cn) if self.V > 0 else None
+        self._chk(self._lib.ca_core_multi_params(self._m, _ptr(mu), _ptr(cp), _ptr(s), _ptr(alpha), _ptr(psi), _ptr(W),
+                                                 _ptr(chi), _ptr(beta), _ptr(snv), self._err, len(self._err)))
+        out = {"mu": mu, "clone_probs": cp, "s": s, "alpha": alpha}
+        if P > 0:
+            out["beta"] = beta
+        if K > 0:
+            out.update(psi=psi, W=W, chi=chi)
+        if snv is not None:
+            out["clone_probs_from_snv"] = snv
+        return out
+
+    def time_steps(self, n_steps: int, with_eval: bool = False) -> float:
+        ms = C.c_double(0.0)
+        self._chk(self._lib.ca_core_multi_time_steps(self._m, int(n_steps), int(bool(with_eval)), C.byref(ms), self._err,
+                                                     len(self._err)))
+        return ms.value
+
+    def describe(self) -> dict:
+        """describe() of shard 0 plus the shard layout."""
+        h, a, b = C.c_void_p(), C.c_int64(0), C.c_int64(0)
+        rows = []
+        d0 = None
+        for i in range(len(self.devices)):
+            self._lib.ca_core_multi_shard(self._m, i, C.byref(h), C.byref(a), C.byref(b))
+            rows.append((a.value, b.value))
+            if i == 0:
+                buf = C.create_string_buffer(1024)
+                self._lib.ca_core_describe(h, buf, len(buf))
+                d0 = json.loads(buf.value.decode())
+        d0["shards"] = rows
+        d0["devices"] = list(self.devices)
+        return d0
+
+    def close(self):
+        if self._m is not None:
+            self._lib.ca_core_multi_destroy(self._m)
+            self._m = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

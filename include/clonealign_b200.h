@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define CA_ABI_VERSION 5
+#define CA_ABI_VERSION 6
 #if defined(__GNUC__)
 #define CA_API __attribute__((visibility("default")))
 #else
@@ -132,7 +132,10 @@ CA_API int ca_core_nccl_unique_id(void* out128, char* err, size_t errlen);
 /* Build the device state.  Y: N x G counts as described by cfg.  L: G x C copy number (already
  * saturated, R/clonealign.R:394-397).  psi_init: N x K.  loc_init: G values of
  * safe_inverse_softplus(mu_guess) (R/inference-tflow.R:262).  X: N x P or NULL.
- * colsum_total: G global column sums of Y over ALL ranks, or NULL when world == 1.
+ * colsum_total: G global column sums of Y over ALL ranks, or NULL: the library then sums the shards' column sums itself
+ * (one all-reduce during set-up; with world > 1 every rank must pass NULL or every rank a value).
+ * With world > 1 the call is collective; the NCCL communicator of a (world, rank, device) is built once per process and
+ * re-used by later sessions of the same shape (released by ca_core_shutdown).
  * Allele inputs (V > 0): clone_allele V x C, alt and cov N x V (R/allele-specific.R:17-48). */
 CA_API int ca_core_create(ca_handle** out, const ca_config* cfg, const void* Y, const double* L,
                    const double* psi_init, const double* loc_init, const double* X,
@@ -224,6 +227,34 @@ CA_API int ca_core_profile_step(ca_handle* h, char* names, size_t names_len, dou
                          char* err, size_t errlen);
 /* static facts for the roofline: bytes of Y as stored, kernels per step, path in use ... as a JSON string */
 CA_API int ca_core_describe(ca_handle* h, char* json, size_t json_len);
+
+/* destroys the NCCL communicators parked by destroyed sessions (optional; process exit does the same) */
+CA_API int ca_core_shutdown(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * ONE fit, cells sharded over several GPUs, driven from ONE host thread (the R interpreter is single-threaded; SURVEY.md
+ * section 8b "Threading", 8e): the library owns one worker thread per device (they never touch R), builds the
+ * communicator itself and mirrors the session lifecycle of R/inference-tflow.R:351-457 over all shards.  Rows of Y,
+ * psi_init, X, alt and cov are split into contiguous, balanced blocks (the first N %% n devices get one more cell);
+ * per-cell state never leaves its GPU, gene-level gradients are summed once per step (one all-reduce per train step).
+ * cfg->N is the TOTAL number of cells; cfg->rank / world / nccl_id / device / N_total are ignored; Y must be in HOST
+ * memory (any ca_y_layout / ca_y_dtype).  Results equal the torchrun path (one process per GPU) bit for bit.
+ * ca_core_multi_params fills the arrays of ca_core_params for ALL cells.  ca_core_multi_shard lends shard i (for the
+ * test / measurement hooks of a single shard; collective calls on it must be issued for every shard). */
+typedef struct ca_multi ca_multi;
+CA_API int ca_core_multi_create(ca_multi** out, const ca_config* cfg, const int32_t* devices, int32_t n_devices, const void* Y,
+                         const double* L, const double* psi_init, const double* loc_init, const double* X,
+                         const double* clone_allele, const double* alt, const double* cov, char* err, size_t errlen);
+CA_API int ca_core_multi_destroy(ca_multi* m);
+CA_API int ca_core_multi_init_gamma(ca_multi* m, char* err, size_t errlen);
+CA_API int ca_core_multi_step(ca_multi* m, char* err, size_t errlen);
+CA_API int ca_core_multi_elbo(ca_multi* m, double* elbo, char* err, size_t errlen);
+CA_API int ca_core_multi_elbo_many(ca_multi* m, int32_t n, double* elbo, char* err, size_t errlen);
+CA_API int ca_core_multi_params(ca_multi* m, double* mu, double* clone_probs, double* s, double* alpha, double* psi,
+                         double* W, double* chi, double* beta, double* clone_probs_from_snv, char* err, size_t errlen);
+CA_API int ca_core_multi_time_steps(ca_multi* m, int32_t n_steps, int32_t with_eval, double* ms, char* err, size_t errlen);
+CA_API int ca_core_multi_shard(ca_multi* m, int32_t i, ca_handle** out, int64_t* row_begin, int64_t* row_end);
+CA_API int ca_core_multi_size(ca_multi* m);
 
 #ifdef __cplusplus
 }

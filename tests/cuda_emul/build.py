@@ -43,7 +43,7 @@ def build(verbose=False) -> str:
         if old.startswith(prefix):
             os.unlink(os.path.join(OUT_DIR, old))
     cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-x", "c++", "-DCA_EMULATE", "-Wno-unknown-pragmas",
-           "-I", HERE, "-I", CSRC, os.path.join(CSRC, "core.cu"), "-o", out + ".tmp", "-ldl", "-pthread"]
+           "-I", HERE, "-I", CSRC, os.path.join(CSRC, "core.cu"), os.path.join(CSRC, "multi.cu"), "-o", out + ".tmp", "-ldl", "-pthread"]
     if sanitize:
         cmd[1:1] = ["-fsanitize=alignment,bounds,shift,integer-divide-by-zero,vla-bound,null", "-fno-sanitize-recover=all"]
     if verbose:

@@ -45,7 +45,7 @@ int main(int argc, char** argv) {
   else
     ca_emul::launch(k_interp_nodes2<true, 6>, dim3(3), dim3(kN2Threads), n2_smem, (const InterpPlan*)&plan, (const float*)w.data(),
                     (const float*)nullptr, (const float*)Mx.data(), (int64_t)G, J, ncgp, split_f, kIMaxPanF, vals.data());
-  ca_emul::launch(k_interp_coeffs2, dim3((J + kC2Cols - 1) / kC2Cols, kIMaxPanF), dim3(kIP * kC2Cols * kC2Lanes), 0,
+  ca_emul::launch(k_interp_coeffs2, dim3((J + kC2Cols - 1) / kC2Cols, 3), dim3(kIP * kC2Cols * kC2Lanes), 0,
                   (const InterpPlan*)&plan, (const double*)vals.data(), split_f, kIMaxPanF, J, 1, coef.data());
   ca_emul::launch(k_interp_eval<true>, dim3(3), dim3(kIEvalWarps * 32), eval_smem, (const InterpPlan*)&plan,
                   (const double*)coef.data(), (const float*)psi.data(), (int64_t)N, J, Zx.data(), smem_panels);
@@ -57,7 +57,7 @@ int main(int argc, char** argv) {
   else
     ca_emul::launch(k_interp_nodes2<false, 6>, dim3(4), dim3(kN2Threads), n2_smem, (const InterpPlan*)&plan, (const float*)psi.data(),
                     (const float*)shift.data(), (const float*)Rx.data(), (int64_t)N, J, ncgp, split_b, kIMaxPanB, vals.data());
-  ca_emul::launch(k_interp_coeffs2, dim3((J + kC2Cols - 1) / kC2Cols, kIMaxPanB), dim3(kIP * kC2Cols * kC2Lanes), 0,
+  ca_emul::launch(k_interp_coeffs2, dim3((J + kC2Cols - 1) / kC2Cols, 2), dim3(kIP * kC2Cols * kC2Lanes), 0,
                   (const InterpPlan*)&plan, (const double*)vals.data(), split_b, kIMaxPanB, J, 0, coef.data());
   ca_emul::launch(k_interp_eval<false>, dim3(2), dim3(kIEvalWarps * 32), eval_smem, (const InterpPlan*)&plan,
                   (const double*)coef.data(), (const float*)w.data(), (int64_t)G, J, dMx.data(), smem_panels);

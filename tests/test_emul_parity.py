@@ -478,6 +478,67 @@ def test_cell_sharded_fit_matches_single_shard(example_sce, path, world):
     assert _relmax(outs[0]["prm"]["W"], ref["prm"]["W"]) < 1e-3 and _relmax(outs[0]["prm"]["alpha"], ref["prm"]["alpha"]) < 1e-4
 
 
+@pytest.mark.parametrize("layout", ["rowmajor_u8", "colmajor_f64", "csr"])
+@pytest.mark.parametrize("world", [1, 3])
+def test_single_process_multi_gpu_equals_one_rank_per_process(example_sce, world, layout):
+    """ca_core_multi_* (one host thread drives all shards: what the R boundary needs) against the path the
+    torchrun launch takes (one caller per shard, here Python threads): the same per-shard calls in the same order, so ELBO
+    traces and parameters agree BIT FOR BIT; every input layout R can hand over is split by rows inside the library."""
+    import threading
+    import scipy.sparse as sp
+    from clonealign_b200 import dist as D
+    from clonealign_b200.session import MultiSession, Session
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
+    Yk, Lk, psi, mu_guess = hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"]
+    N = Yk.shape[0]
+    loc = O.safe_inverse_softplus(mu_guess)
+    rng = np.random.default_rng(3)
+    V = 7
+    cn = rng.integers(1, 4, size=(V, Lk.shape[1])).astype(float)
+    cov = rng.poisson(0.7, size=(N, V)).astype(float)
+    alt = rng.binomial(cov.astype(int), 0.4).astype(float)
+    kw = dict(mc_samples=2, K=1, seed=77, clone_allele=cn)
+    Yin = {"rowmajor_u8": Yk.astype(np.uint8), "colmajor_f64": np.asfortranarray(Yk), "csr": sp.csr_matrix(Yk)}[layout]
+
+    def trace(sess):
+        sess.init_gamma()
+        tr = [sess.elbo()]
+        for _ in range(3):
+            sess.step()
+            tr.append(sess.elbo())
+        tr += list(sess.elbo_many(2))
+        return np.array(tr), sess.params()
+
+    with MultiSession(Yin, Lk, psi, loc, devices=[0] * world, alt=alt, cov=cov, **kw) as ms:
+        d = ms.describe()
+        assert d["path"] == "interp" and d["world"] == world and d["shards"] == [D.shard_bounds(N, r, world) for r in range(world)]
+        e_multi, p_multi = trace(ms)
+        assert ms.time_steps(1) >= 0.0
+    outs, errs = [None] * world, []
+    nid = Session.nccl_unique_id()
+
+    def rank_main(r):
+        try:
+            a, b = D.shard_bounds(N, r, world)
+            s = Session(Yk[a:b], Lk, psi[a:b], loc, rank=r, world=world, nccl_id=nid if world > 1 else None, n_total=N,
+                        alt=alt[a:b], cov=cov[a:b], **kw)      # colsum_total = None: summed by the library (collective)
+            outs[r] = trace(s)
+            s.close()
+        except Exception as e:
+            errs.append(e)
+            raise
+    ts = [threading.Thread(target=rank_main, args=(r,), daemon=True) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=300) for t in ts]
+    assert not errs and all(o is not None for o in outs), errs
+    assert e_multi.tobytes() == outs[0][0].tobytes()
+    for k in ("clone_probs", "psi", "s", "clone_probs_from_snv"):
+        assert p_multi[k].tobytes() == np.concatenate([o[1][k] for o in outs]).tobytes(), k
+    for k in ("mu", "W", "alpha", "chi"):
+        assert p_multi[k].tobytes() == outs[0][1][k].tobytes(), k
+
+
 @pytest.mark.parametrize("path", [("cudacore", "ypass2"), ("interp", "ypass2,epi2,lean"), ("interp", "ypass3,epi2,lean"),
                                   ("interp", "ypass4,epi2,lean,defer,cosched")])
 def test_several_row_and_column_tiles(path):
