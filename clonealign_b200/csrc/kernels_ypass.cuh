@@ -437,30 +437,30 @@ k_ypass_k1_v3(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, co
 // issue slots 41 % busy, top stall long_scoreboard -- every warp loads 8 rows into REGISTERS, waits about a microsecond,
 // then spends about as long on its ~430 instructions: nothing is in flight while it computes (128 registers per thread
 // leave no room to double-buffer), and 2 CTAs take the whole register file, so nothing can share the SM with the stream.
-// A first ring of per-thread cp.async copies (LDGSTS) removed the stall but cost +57 % instructions (address arithmetic,
-// one commit / wait and three compiler-inserted dummy LDS per 16-byte copy): issue-bound at the same speed.
-// Here the rows travel by BULK copies (cp.async.bulk, the TMA engine): the 32 lanes of a warp own 32 x 16 = 512
-// consecutive bytes of a row, so ONE lane issues one 512-byte copy per (warp, row) into the warp's own shared-memory ring
-// (16 rows = 4 stages of 4 rows, one mbarrier per stage counting bytes); every lane then reads its 16-byte piece with one
-// LDS.128.  A stage is re-armed and refilled as soon as it has been consumed.  Bytes in flight cost neither registers nor
-// issue slots: 12 rows per warp are outstanding WHILE it computes, the kernel needs half the registers, and it is
-// launched as a PERSISTENT grid of 2 CTAs per SM (fixed tile assignment: deterministic) that leaves half of the register
-// file and ~100 KB of shared memory of every SM free: started first in the step on the second stream (variant COSCHED),
-// the HBM-bound stream runs NEXT TO the issue-bound kernels of the step instead of before / after them.
+// Two staging schemes were measured and dropped: per-thread cp.async (LDGSTS) copies removed the stall but cost +57 %
+// instructions (address arithmetic, a commit / wait and three compiler-inserted dummy LDS per 16-byte copy): issue-bound
+// at the same speed; 512-byte bulk copies per (warp, row) ran at 3.4 TB/s -- the TMA engine serves about one request
+// per 46 cycles per SM, so small requests starve it.
+// Here a row of the CTA's column tile (256 threads x 16 bytes = 4 KB contiguous) is ONE bulk copy (cp.async.bulk, the TMA
+// engine) into a shared-memory ring of 16 rows (4 stages of 4 rows, one mbarrier per stage counting bytes), issued by one
+// thread; every thread reads its 16-byte piece of a row with one LDS.128.  The block barrier the row sums need every 8
+// rows doubles as the "stage is free" signal: right after it one thread re-arms and refills the two stages just consumed,
+// so the next 8 rows are in flight WHILE the CTA computes.  Bytes in flight cost neither registers nor issue slots, the
+// kernel needs half the registers, and it is launched as a PERSISTENT grid of 2 CTAs per SM (fixed tile assignment:
+// deterministic) that leaves half of the register file and ~100 KB of shared memory of every SM free: started first in
+// the step on the second stream (variant COSCHED), the HBM-bound stream runs NEXT TO the issue-bound kernels of the step.
 // Arithmetic, tiling (256 x kCols columns) and partial-sum layouts are those of v3: bit-identical results.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kY4StageRows = 4;
-template <typename T> struct Y4Ring { static constexpr int kStages = 4; };    // 16 rows x 512 B per warp: 64 KB per CTA
-template <> struct Y4Ring<float> { static constexpr int kStages = 2; };       // 1024-byte rows
+constexpr int kY4StageRows = 4, kY4Stages = 4;
 template <typename T> constexpr size_t ypass4_smem_bytes() {
-  return (size_t)Y4Ring<T>::kStages * kY4StageRows * 256 * sizeof(typename Y3<T>::Raw) + 8 * 8 * Y4Ring<T>::kStages + 16;
+  return (size_t)kY4Stages * kY4StageRows * 256 * sizeof(typename Y3<T>::Raw) + 8 * kY4Stages + 16;
 }
 
-#ifdef CA_EMULATE   // functional stand-ins: the issuing lane copies synchronously, a wait is a warp barrier
+#ifdef CA_EMULATE   // functional stand-ins: the issuing thread copies synchronously (block barriers order it, see below)
 __device__ __forceinline__ void y4_bar_init(uint64_t*, int) {}
 __device__ __forceinline__ void y4_arm(uint64_t*, uint32_t) {}
 __device__ __forceinline__ void y4_bulk(void* dst, const void* src, uint32_t bytes, uint64_t*) { memcpy(dst, src, bytes); }
-__device__ __forceinline__ void y4_wait(uint64_t*, uint32_t) { __syncwarp(); }
+__device__ __forceinline__ void y4_wait(uint64_t*, uint32_t) {}
 __device__ __forceinline__ void y4_fence_init() {}
 __device__ __forceinline__ void y4_fence_proxy() {}
 #else
@@ -474,37 +474,38 @@ __device__ __forceinline__ void y4_fence_init() { ptx::fence_barrier_init(); }
 __device__ __forceinline__ void y4_fence_proxy() { ptx::fence_proxy_async_smem(); }
 #endif
 
-// MINB = CTAs per SM the register allocation is sized for: 4 -> 64 registers (a few spills in the row loop), 3 -> 80
+// MINB = CTAs per SM the register allocation is sized for: 4 -> 64 registers, 3 -> 80
 template <typename T, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, int nCB, int nRB, const float* __restrict__ U,
               const float* __restrict__ Vm, float* __restrict__ rowpart, float* __restrict__ colpart) {
   using L = Y3<T>;
   using Raw = typename L::Raw;
-  constexpr int kStages = Y4Ring<T>::kStages, kSR = kY4StageRows, kCols = L::kCols, kPairs = kCols / 2;
-  constexpr uint32_t kRowBytes = 32 * sizeof(Raw);               // one row of the warp's column strip
+  constexpr int kSR = kY4StageRows, kCols = L::kCols, kPairs = kCols / 2;
+  constexpr uint32_t kRowBytes = 256 * sizeof(Raw);              // one row of the CTA's column tile
   CA_DYNAMIC_SMEM(unsigned char, ring_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  Raw* wring = reinterpret_cast<Raw*>(ring_raw) + (size_t)wid * kStages * kSR * 32;        // this warp's ring [slot][lane]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_raw + (size_t)kStages * kSR * 256 * sizeof(Raw)) + wid * kStages;
+  Raw* ring = reinterpret_cast<Raw*>(ring_raw);                  // [stage][row][thread]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_raw + (size_t)kY4Stages * kSR * kRowBytes);
   __shared__ float red[2][8][8];
   const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-  // the ring starts zeroed: lanes past the last stored column never receive data and must read zeros, not stale bits
-  for (int i = lane; i < kStages * kSR * 32; i += 32) wring[i] = L::zero();
-  if (lane == 0)
-    for (int st = 0; st < kStages; ++st) y4_bar_init(bars + st, 1);
+  // the ring starts zeroed: threads past the last stored column never receive data and must not read NaN patterns
+  for (int i = tid; i < kY4Stages * kSR * 256; i += 256) ring[i] = L::zero();
+  if (tid == 0)
+    for (int st = 0; st < kY4Stages; ++st) y4_bar_init(bars + st, 1);
   y4_fence_init();
+  y4_fence_proxy();                                              // the zero fill (generic stores) before any bulk copy
   __syncthreads();
-  uint32_t sc = 0;                                               // stages issued == consumed so far by this warp (all tiles)
+  uint32_t gg = 0;                                               // groups of 8 rows consumed so far by this CTA (all tiles)
   const int64_t ntiles = (int64_t)nCB * nRB;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int cb = (int)(tile % nCB);
     const int64_t rb = tile / nCB;
-    const int64_t wcol0 = (int64_t)cb * (256 * kCols) + (int64_t)wid * 32 * kCols;         // first column of the warp's strip
-    const int64_t col0 = wcol0 + lane * kCols;
-    // bytes of a row that exist for this warp (the stored row ends at ldY; ldY and the strip start are multiples of 16 bytes)
-    const int64_t avail = (ldY - wcol0) * (int64_t)sizeof(T);
-    const uint32_t wbytes = avail <= 0 ? 0u : (avail < (int64_t)kRowBytes ? (uint32_t)avail : kRowBytes);
+    const int64_t tcol0 = (int64_t)cb * (256 * kCols);           // first column of the CTA's tile
+    const int64_t col0 = tcol0 + tid * kCols;
+    // bytes of a row that exist for this tile (the stored row ends at ldY; ldY * sizeof(T) and the tile start are multiples of 16)
+    const int64_t avail = (ldY - tcol0) * (int64_t)sizeof(T);
+    const uint32_t tbytes = avail < (int64_t)kRowBytes ? (uint32_t)avail : kRowBytes;
     float2 vr[kPairs], cacc[kPairs];
 #pragma unroll
     for (int j = 0; j < kPairs; ++j) {
@@ -513,26 +514,31 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
     }
     const int64_t rbeg = rb * RB, rend = (rbeg + RB < N) ? rbeg + RB : N;
     const int nrows = (int)(rend - rbeg);
-    const int nst = (nrows + kSR - 1) / kSR;                     // stages of this tile
     const int ngroups = (nrows + 7) / 8;
-    const T* ybase = Y + rbeg * ldY + wcol0;
-    // stage `t` of the tile (rows 4 t ..) -> ring stage (sc0 + t) % kStages; issued by lane 0 only
-    const uint32_t sc0 = sc;
-    auto issue = [&](int t) {
-      if (t >= nst || wbytes == 0u) return;
-      const uint32_t st = (sc0 + (uint32_t)t) % kStages;
-      const int r0 = t * kSR;
-      const int nv = nrows - r0 < kSR ? nrows - r0 : kSR;
-      y4_arm(bars + st, (uint32_t)nv * wbytes);
-      for (int i = 0; i < nv; ++i)
-        y4_bulk(wring + ((size_t)st * kSR + i) * 32, ybase + (int64_t)(r0 + i) * ldY, wbytes, bars + st);
+    const T* ybase = Y + rbeg * ldY + tcol0;
+    const uint32_t gg0 = gg;
+    // group `g` of the tile (rows 8 g ..) -> stages 2 ((gg0 + g) & 1) and + 1; issued by thread 0 only
+    auto issue = [&](int g) {
+      if (g >= ngroups) return;
+      const uint32_t s0 = 2u * ((gg0 + (uint32_t)g) & 1u);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int r0 = g * 8 + hh * kSR;
+        const int nv = nrows - r0 < kSR ? nrows - r0 : kSR;
+        if (nv <= 0) break;
+        y4_arm(bars + s0 + hh, (uint32_t)nv * tbytes);
+        for (int i = 0; i < nv; ++i)
+          y4_bulk(ring + ((size_t)(s0 + hh) * kSR + i) * 256, ybase + (int64_t)(r0 + i) * ldY, tbytes, bars + s0 + hh);
+      }
     };
-    if (lane == 0)
-      for (int t = 0; t < kStages; ++t) issue(t);
-    __syncwarp();
+    if (tid == 0) { issue(0); issue(1); }
+#ifdef CA_EMULATE
+    __syncthreads();                                             // the synchronous stand-in copies must precede the readers
+#endif
     int buf = 0;
     for (int g = 0; g < ngroups; ++g) {
       const int64_t r0 = rbeg + (int64_t)g * 8;
+      const uint32_t gcur = gg0 + (uint32_t)g, s0 = 2u * (gcur & 1u), par = (gcur >> 1) & 1u;
       float u[8];   // U is allocated with 64 elements of slack, r0 is a multiple of 4: vector loads stay in bounds
 #pragma unroll
       for (int i = 0; i < 8; i += 4) {
@@ -542,22 +548,20 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
       float rp[8];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        const int t = 2 * g + hh;                                // stage of the tile
-        if (t < nst) {
-          const uint32_t scur = sc0 + (uint32_t)t, st = scur % kStages;
-          if (wbytes != 0u) y4_wait(bars + st, (scur / kStages) & 1u);
-          const Raw* src = wring + (size_t)st * kSR * 32 + lane;
-          const int nv = nrows - t * kSR;                         // valid rows of this stage (>= 1)
+        const int nv = nrows - (g * 8 + hh * kSR);               // valid rows of this stage
+        if (nv > 0) {
+          y4_wait(bars + s0 + hh, par);
+          Raw* src = ring + (size_t)(s0 + hh) * kSR * 256 + tid;
           if (nv < kSR) {
-            // last stage of the tile: its trailing rows were not copied and hold stale ring contents.  Every lane zeroes
-            // its own pieces (it reads them back itself below); the proxy fence orders these generic stores before the
-            // bulk copy that refills the stage later.
-            for (int i = nv; i < kSR; ++i) wring[((size_t)st * kSR + i) * 32 + lane] = L::zero();
+            // last stage of the tile: its trailing rows were not copied and hold stale ring contents.  Every thread
+            // zeroes its own pieces (it reads them back itself below); the proxy fence orders these generic stores
+            // before the bulk copy that refills the stage later.
+            for (int i = nv; i < kSR; ++i) src[(size_t)i * 256] = L::zero();
             y4_fence_proxy();
           }
 #pragma unroll
           for (int i = 0; i < kSR; ++i) {
-            const Raw raw = src[(size_t)i * 32];
+            const Raw raw = src[(size_t)i * 256];
             float2 y[kPairs];
             L::unpack(raw, y);
             const float2 u2 = make_float2(u[hh * kSR + i], u[hh * kSR + i]);
@@ -572,10 +576,6 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
             const float2 a2 = __fadd2_rn(acc0, acc1);
             rp[hh * kSR + i] = a2.x + a2.y;
           }
-          // every lane has issued the FMAs that consume its pieces of this stage (in-order issue: their LDS have returned),
-          // so the stage can be re-armed and refilled at once: kStages - 1 stages stay in flight while the warp computes
-          __syncwarp();
-          if (lane == 0) issue(t + kStages);
         } else {
 #pragma unroll
           for (int i = 0; i < kSR; ++i) rp[hh * kSR + i] = 0.f;
@@ -584,6 +584,9 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
       const float tot = butterfly8(rp, lane);
       if ((lane & 3) == 0) red[buf][wid][ridx] = tot;
       __syncthreads();
+      // every thread has issued the FMAs that consume its pieces of this group (in-order issue: their LDS have returned)
+      // and passed the barrier: the two stages are free and are refilled with the group after next
+      if (tid == 0) issue(g + 2);
       if (tid < 8 && r0 + tid < rend) {
         float acc = 0.f;
 #pragma unroll
@@ -592,13 +595,13 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
       }
       buf ^= 1;
     }
-    sc = sc0 + (uint32_t)nst;
+    gg = gg0 + (uint32_t)ngroups;
 #pragma unroll
     for (int j = 0; j < kPairs; ++j) {
       if (col0 + 2 * j < G) colpart[rb * G + col0 + 2 * j] = cacc[j].x * L::kPost;
       if (col0 + 2 * j + 1 < G) colpart[rb * G + col0 + 2 * j + 1] = cacc[j].y * L::kPost;
     }
-    __syncthreads();   // `red` is reused by the next tile; every warp has consumed every stage it issued
+    __syncthreads();   // `red` is reused by the next tile; every stage this CTA issued has been consumed
   }
 }
 

@@ -106,7 +106,7 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
                     saturate_=True, saturation_threshold=6, K=1, mc_samples=1, verbose=True, initial_shrink=5,
                     data_init_mu=True, seed=None, device=0, psi_init=None, y_store="auto", path="auto",
                     gene_names=None, variants=None, correlations_with=None, device_pca=False, cache=None,
-                    device_stats=False, batch_final_elbo=False):
+                    device_stats=False, batch_final_elbo=False, devices=None):
     """The fit of `inference_tflow` as a generator: it yields its `Session` every time the parameters have just changed
     and the next operation is an ELBO evaluation (after gamma-init and after every train step), i.e. exactly where one
     batched pass over a shared count matrix can serve several restarts (`session.ypass_many`; `run_clonealign(
@@ -131,6 +131,9 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
     `batch_final_elbo=True`: the 20 fresh-draw ELBO evaluations behind final_elbo / sd_final_elbo (:447-449) are queued on the
     stream and fetched with one device-to-host copy (ca_core_elbo_many): same draws, bit-identical values; opt-in like the other
     entry points that have not run on hardware yet.
+    `devices=[0, 1, ...]` (the R twin: `options(clonealign.gpus = ...)`): the cells of THIS fit are sharded over several GPUs of
+    this process (`MultiSession`, ca_core_multi_*: one worker thread per device inside the library, one all-reduce of the
+    gene-level gradients per step); dense or sparse host input; not combined with the device-side extras above.
     `correlations_with = (L_unsaturated, clone_call_probability)`: also run the caller's post-hoc
     `compute_correlations` (R/clonealign.R:292-294,318-334) on the device while Y is still resident; the result is
     returned under "correlations" (retained genes only).
@@ -245,11 +248,24 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
         mu_guess = d / d.mean()
 
     op_seed = get_next_seed(rng)                                                      # :269
+    multi = devices is not None and len(list(devices)) > 1
+    if multi and (device_pca or device_stats or cache is not None or correlations_with is not None):
+        raise ValueError("devices=[...] (one fit over several GPUs) cannot be combined with device_pca, device_stats, "
+                         "shared restart inputs or device correlations")
     data = get_data() if cache is not None else None
-    sess = Session(Y, L, psi_init, safe_inverse_softplus(mu_guess), mc_samples=int(mc_samples), K=K, x=x,
-                   learning_rate=learning_rate, seed=op_seed, device=device,
-                   clone_allele=clone_allele if use_allele else None, alt=alt, cov=cov if use_allele else None,
-                   y_store=y_store, path=path, variants=variants, data=data)
+    if multi:
+        from .session import MultiSession
+        sess = MultiSession(Y, L, psi_init, safe_inverse_softplus(mu_guess), devices=list(devices), mc_samples=int(mc_samples),
+                            K=K, x=x, learning_rate=learning_rate, seed=op_seed,
+                            clone_allele=clone_allele if use_allele else None, alt=alt, cov=cov if use_allele else None,
+                            y_store=y_store, path=path, variants=variants)
+    else:
+        if devices is not None and len(list(devices)) == 1:
+            device = list(devices)[0]
+        sess = Session(Y, L, psi_init, safe_inverse_softplus(mu_guess), mc_samples=int(mc_samples), K=K, x=x,
+                       learning_rate=learning_rate, seed=op_seed, device=device,
+                       clone_allele=clone_allele if use_allele else None, alt=alt, cov=cov if use_allele else None,
+                       y_store=y_store, path=path, variants=variants, data=data)
     correlations = None
     try:
         if pca_noise is not None:

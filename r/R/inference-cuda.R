@@ -28,36 +28,46 @@ inference_cuda_session <- function(Y_dat, L_dat, pcs, mu_guess, x, clone_allele,
   if (K == 0) x <- NULL                                    # reference quirk: covariates ignored without latent dims (:279-285)
   storage.mode(L_dat) <- "double"
   alt_nv <- if (V > 0) t(alt) else NULL; cov_nv <- if (V > 0) t(cov) else NULL   # :177-180 transposes undone: ABI takes N x V
-  sess <- if (is.null(counts_dgC)) {
+  # options(clonealign.gpus = c(0, 1, ...)): shard the cells of this fit over several GPUs (SURVEY.md 8e).  R stays
+  # single-threaded: the library owns one worker thread per device (ca_core_multi_*); same calls, same results.
+  gpus <- as.integer(getOption("clonealign.gpus", 0L))
+  multi <- length(gpus) > 1
+  if (multi && (!is.null(counts_dgC) || device_pca || !is.null(cor_with)))
+    stop("options(clonealign.gpus) with several devices supports dense input without the device-side extras")
+  cc <- function(name, ...) .Call(if (multi) sub("^ca_", "ca_multi_", name) else name, ...)
+  sess <- if (multi) {
+    .Call("ca_multi_create", Y_dat, L_dat, pcs, safe_inverse_softplus(mu_guess), x, clone_allele, alt_nv, cov_nv,
+          as.integer(mc_samples), as.integer(K), learning_rate, get_next_seed(), gpus)
+  } else if (is.null(counts_dgC)) {
     .Call("ca_create", Y_dat, L_dat, pcs, safe_inverse_softplus(mu_guess), x, clone_allele, alt_nv, cov_nv,
-          as.integer(mc_samples), as.integer(K), learning_rate, get_next_seed(), 0L)
+          as.integer(mc_samples), as.integer(K), learning_rate, get_next_seed(), gpus[1])
   } else {
     .Call("ca_create_sparse", counts_dgC@Dim, counts_dgC@p, counts_dgC@i, counts_dgC@x, L_dat, pcs,
           safe_inverse_softplus(mu_guess), x, clone_allele, alt_nv, cov_nv,
-          as.integer(mc_samples), as.integer(K), learning_rate, get_next_seed(), 0L)
+          as.integer(mc_samples), as.integer(K), learning_rate, get_next_seed(), gpus[1])
   }
-  on.exit(.Call("ca_destroy", sess), add = TRUE)           # sess$close(), :457
+  on.exit(cc("ca_destroy", sess), add = TRUE)              # sess$close(), :457
   if (!is.null(pca_noise)) {
     pcs <- scale(matrix(.Call("ca_pca_scores", sess, N, 500L, 1e-12), nrow = N))   # :203-205
     .Call("ca_set_psi", sess, pcs + pca_noise)                                     # :207
   }
 
-  .Call("ca_init_gamma", sess)                             # :368-369
-  elbo_val <- .Call("ca_elbo", sess)                       # :372
+  cc("ca_init_gamma", sess)                                # :368-369
+  elbo_val <- cc("ca_elbo", sess)                          # :372
   if (is.na(elbo_val)) stop("Initial elbo is NA")          # :374-376
 
   elbo_diffs <- rep(1e3, 10); elbos <- elbo_val            # :379-380
   for (i in seq_len(max_iter)) {                           # :394
-    .Call("ca_step", sess)                                 # :401
-    elbo_new <- .Call("ca_elbo", sess)                     # :403
+    cc("ca_step", sess)                                    # :401
+    elbo_new <- cc("ca_elbo", sess)                        # :403
     elbo_diff <- (elbo_new - elbo_val) / abs(elbo_val)
     elbo_diffs <- c(elbo_diffs[-1], elbo_diff)
     elbos <- c(elbos, elbo_new); elbo_val <- elbo_new
     if (mean(abs(elbo_diffs)) < rel_tol) break             # :414
   }
-  rlist <- .Call("ca_params", sess, c(N, G, C, as.integer(K), P, V))   # :424-440
-  final_elbo <- if (batch_final_elbo) .Call("ca_elbo_many", sess, 20L)   # 20 fresh-draw evaluations, one round trip
-                else replicate(20, .Call("ca_elbo", sess))               # :447-449
+  rlist <- cc("ca_params", sess, c(N, G, C, as.integer(K), P, V))      # :424-440
+  final_elbo <- if (batch_final_elbo) cc("ca_elbo_many", sess, 20L)      # 20 fresh-draw evaluations, one round trip
+                else replicate(20, cc("ca_elbo", sess))                  # :447-449
   correlations <- NULL
   if (!is.null(cor_with)) {                                # clone_assignment (:22-29) as 0-based indices, -1 = unassigned
     cp <- rlist$clone_probs

@@ -284,7 +284,118 @@ SEXP ca_destroy(SEXP ptr) {
   return R_NilValue;
 }
 
+/* ---- one fit over several GPUs from the (single-threaded) R interpreter: options(clonealign.gpus = c(0, 1, ...)) ----
+ * ca_core_multi_* shards the cells inside the library (one worker thread per device, none of them touches R) and mirrors
+ * the same session lifecycle; ca_multi_create takes the arguments of ca_create with `devices` (integer vector) last. */
+static void ca_multi_finalizer(SEXP ptr) {
+  ca_multi* m = (ca_multi*)R_ExternalPtrAddr(ptr);
+  if (m) {
+    ca_core_multi_destroy(m);
+    R_ClearExternalPtr(ptr);
+  }
+}
+static ca_multi* get_multi(SEXP ptr) {
+  ca_multi* m = (ca_multi*)R_ExternalPtrAddr(ptr);
+  if (!m) Rf_error("clonealign CUDA session is closed");
+  return m;
+}
+SEXP ca_multi_create(SEXP Y, SEXP L, SEXP psi_init, SEXP loc_init, SEXP X, SEXP clone_allele, SEXP alt, SEXP cov,
+                     SEXP S, SEXP K, SEXP lr, SEXP seed, SEXP devices) {
+  char err[ERRLEN] = {0};
+  SEXP dim = Rf_getAttrib(Y, R_DimSymbol);
+  ca_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.N = INTEGER(dim)[0];
+  cfg.N_total = cfg.N;
+  cfg.G = INTEGER(dim)[1];
+  cfg.C = Rf_ncols(L);
+  cfg.S = Rf_asInteger(S);
+  cfg.K = Rf_asInteger(K);
+  cfg.P = Rf_isNull(X) ? 0 : Rf_ncols(X);
+  cfg.V = Rf_isNull(clone_allele) ? 0 : Rf_nrows(clone_allele);
+  cfg.learning_rate = Rf_asReal(lr);
+  cfg.seed = (uint64_t)Rf_asInteger(seed);
+  cfg.world = 1;
+  cfg.y_dtype = (TYPEOF(Y) == INTSXP) ? CA_Y_I32 : CA_Y_F64;
+  cfg.y_layout = CA_Y_COLMAJOR;
+  cfg.y_mem = CA_Y_HOST;
+  cfg.y_store = CA_STORE_AUTO;
+  cfg.path = CA_PATH_AUTO;
+  const void* yptr = (TYPEOF(Y) == INTSXP) ? (const void*)INTEGER(Y) : (const void*)REAL(Y);
+  ca_multi* m = NULL;
+  int st = ca_core_multi_create(&m, &cfg, INTEGER(devices), (int32_t)XLENGTH(devices), yptr, REAL(L), real_or_null(psi_init),
+                                REAL(loc_init), real_or_null(X), real_or_null(clone_allele), real_or_null(alt), real_or_null(cov),
+                                err, ERRLEN);
+  if (st != 0) Rf_error("%s", err);
+  SEXP ptr = PROTECT(R_MakeExternalPtr(m, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, ca_multi_finalizer, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+SEXP ca_multi_init_gamma(SEXP ptr) {
+  char err[ERRLEN] = {0};
+  if (ca_core_multi_init_gamma(get_multi(ptr), err, ERRLEN)) Rf_error("%s", err);
+  return R_NilValue;
+}
+SEXP ca_multi_step(SEXP ptr) {
+  char err[ERRLEN] = {0};
+  if (ca_core_multi_step(get_multi(ptr), err, ERRLEN)) Rf_error("%s", err);
+  return R_NilValue;
+}
+SEXP ca_multi_elbo(SEXP ptr) {
+  char err[ERRLEN] = {0};
+  double e = NA_REAL;
+  if (ca_core_multi_elbo(get_multi(ptr), &e, err, ERRLEN)) Rf_error("%s", err);
+  return Rf_ScalarReal(e);
+}
+SEXP ca_multi_elbo_many(SEXP ptr, SEXP n) {
+  char err[ERRLEN] = {0};
+  int k = Rf_asInteger(n);
+  if (k < 0) Rf_error("ca_multi_elbo_many: n must be >= 0");
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, k));
+  if (ca_core_multi_elbo_many(get_multi(ptr), k, REAL(out), err, ERRLEN)) {
+    UNPROTECT(1);
+    Rf_error("%s", err);
+  }
+  UNPROTECT(1);
+  return out;
+}
+SEXP ca_multi_params(SEXP ptr, SEXP dims) {   /* dims = c(N, G, C, K, P, V); N = all cells */
+  char err[ERRLEN] = {0};
+  int* d = INTEGER(dims);
+  int N = d[0], G = d[1], C = d[2], K = d[3], P = d[4], V = d[5];
+  int np = 0;
+  SEXP mu = PROTECT(Rf_allocVector(REALSXP, G)); np++;
+  SEXP cp = PROTECT(Rf_allocMatrix(REALSXP, N, C)); np++;
+  SEXP s = PROTECT(Rf_allocVector(REALSXP, N)); np++;
+  SEXP alpha = PROTECT(Rf_allocVector(REALSXP, C)); np++;
+  SEXP psi = PROTECT(K > 0 ? Rf_allocMatrix(REALSXP, N, K) : R_NilValue); np++;
+  SEXP W = PROTECT(K > 0 ? Rf_allocMatrix(REALSXP, G, K) : R_NilValue); np++;
+  SEXP chi = PROTECT(K > 0 ? Rf_allocVector(REALSXP, K) : R_NilValue); np++;
+  SEXP beta = PROTECT(P > 0 ? Rf_allocMatrix(REALSXP, G, P) : R_NilValue); np++;
+  SEXP snv = PROTECT(V > 0 ? Rf_allocMatrix(REALSXP, N, C) : R_NilValue); np++;
+  int st = ca_core_multi_params(get_multi(ptr), REAL(mu), REAL(cp), REAL(s), REAL(alpha), K > 0 ? REAL(psi) : NULL,
+                                K > 0 ? REAL(W) : NULL, K > 0 ? REAL(chi) : NULL, P > 0 ? REAL(beta) : NULL,
+                                V > 0 ? REAL(snv) : NULL, err, ERRLEN);
+  if (st != 0) { UNPROTECT(np); Rf_error("%s", err); }
+  const char* names[] = {"mu", "clone_probs", "s", "alpha", "psi", "W", "chi", "beta", "clone_probs_from_snv", ""};
+  SEXP out = PROTECT(Rf_mkNamed(VECSXP, names)); np++;
+  SET_VECTOR_ELT(out, 0, mu); SET_VECTOR_ELT(out, 1, cp); SET_VECTOR_ELT(out, 2, s); SET_VECTOR_ELT(out, 3, alpha);
+  SET_VECTOR_ELT(out, 4, psi); SET_VECTOR_ELT(out, 5, W); SET_VECTOR_ELT(out, 6, chi); SET_VECTOR_ELT(out, 7, beta);
+  SET_VECTOR_ELT(out, 8, snv);
+  UNPROTECT(np);
+  return out;
+}
+SEXP ca_multi_destroy(SEXP ptr) {
+  ca_multi_finalizer(ptr);
+  return R_NilValue;
+}
+
 static const R_CallMethodDef call_methods[] = {
+    {"ca_multi_create", (DL_FUNC)&ca_multi_create, 13}, {"ca_multi_init_gamma", (DL_FUNC)&ca_multi_init_gamma, 1},
+    {"ca_multi_step", (DL_FUNC)&ca_multi_step, 1}, {"ca_multi_elbo", (DL_FUNC)&ca_multi_elbo, 1},
+    {"ca_multi_elbo_many", (DL_FUNC)&ca_multi_elbo_many, 2}, {"ca_multi_params", (DL_FUNC)&ca_multi_params, 2},
+    {"ca_multi_destroy", (DL_FUNC)&ca_multi_destroy, 1},
     {"ca_create", (DL_FUNC)&ca_create, 13}, {"ca_init_gamma", (DL_FUNC)&ca_init_gamma, 1},
     {"ca_step", (DL_FUNC)&ca_step, 1},      {"ca_elbo", (DL_FUNC)&ca_elbo, 1},
     {"ca_params", (DL_FUNC)&ca_params, 2},  {"ca_set_eps", (DL_FUNC)&ca_set_eps, 3},

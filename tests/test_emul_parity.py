@@ -302,6 +302,13 @@ def test_clonealign_returns_valid_object(example_sce):
     assert {"clone", "convergence_info", "retained_genes", "correlations", "ml_params"} <= set(cal)
     assert len(cal["convergence_info"]["elbo"]) == 6
     np.testing.assert_allclose(cal["ml_params"]["clone_probs"].sum(1), 1.0, atol=1e-6)
+    # the same call with the cells of the fit sharded over "two GPUs" of this process (options(clonealign.gpus) in R)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        two = clonealign(Y, L, max_iter=5, clone_names=["A", "B", "C"], verbose=False, seed=1, devices=[0, 0])
+    assert two["clone"] == cal["clone"]
+    assert np.abs(two["convergence_info"]["elbo"] / cal["convergence_info"]["elbo"] - 1.0).max() < 1e-6
+    assert np.abs(two["ml_params"]["clone_probs"] - cal["ml_params"]["clone_probs"]).max() < 1e-4
 
 
 def test_seed_setting_works_and_na_paths(example_sce):
