@@ -142,8 +142,8 @@ def run_clonealign(gene_expression_data, copy_number_data, initial_shrinks=(0, 5
         else:
             from .session import variant_mask, _VARIANT
             names = kwargs.get("variants") or ""
-            if variant_mask(names) & _VARIANT["ypass3"]:
-                raise ValueError("batch_y_pass uses the column tiling of variant ypass2; it cannot be combined with ypass3")
+            if variant_mask(names) & (_VARIANT["ypass3"] | _VARIANT["ypass4"]):
+                raise ValueError("batch_y_pass uses the column tiling of variant ypass2; it cannot be combined with ypass3 / ypass4")
             if not (variant_mask(names) & _VARIANT["ypass2"]):
                 kwargs["variants"] = ",".join([v for v in (names.split(",") if isinstance(names, str) else list(names)) if v] + ["ypass2"])
     jobs = []

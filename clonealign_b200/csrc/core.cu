@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -326,6 +327,9 @@ struct ca_handle {
   uint64_t draw = 0;
   int adam_t = 0;
 
+  StepState* dstate = nullptr;     // device-side counters (draw, adam_t, lr_t, p2p_step): constant launch arguments
+  cudaGraphExec_t g_train[2] = {nullptr, nullptr}, g_eval[2] = {nullptr, nullptr};   // replayable step / evaluation, by ydirty
+  bool use_graph = false;
   void* comm = nullptr;
   // variant P2P: exchange buffer of this rank, the peers' mappings, step counter
   bool p2p = false, p2p_ready = false;
@@ -411,7 +415,9 @@ void run_ypass(ca_handle* h, cudaStream_t st) {
       dim3 grid(h->nCB, h->nRB);
       if (h->variants & CA_VAR_YPASS4) {
         const int64_t tiles = (int64_t)h->nCB * h->nRB;
-        const unsigned g4 = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)h->num_sms);
+        // persistent grid: 2 CTAs per SM (64 KB rings); fp32 storage has 128 KB rings: one per SM
+        const int per_sm = std::is_same<T, float>::value ? 1 : 2;
+        const unsigned g4 = (unsigned)std::min<int64_t>(tiles, per_sm * (int64_t)h->num_sms);
         if (h->y4_minb == 3) {
           auto k = k_ypass_k1_v4<T, 3>;
           CA_LAUNCH(k, g4, 256, ypass4_smem_bytes<T>(), st)(Yp, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm, h->rowpart, h->colpart);
@@ -551,6 +557,7 @@ void run_forward(ca_handle* h, int mode) {
     a.log_alpha = h->log_alpha; a.mm = h->mm; a.mm_psi = h->mm_psi; a.chi_cur = h->chi_cur;
     a.scal_elbo = h->scal_elbo; a.wsq = h->wsq; a.pmm_part = h->pmm_part; a.ticket = h->ticket; a.plan = h->iplan;
     a.dirichlet_const = (double)h->C * lgamma(1.0 / h->C) - lgamma(1.0);
+    a.state = h->dstate; a.lr = h->cfg.learning_rate;
     a.mu = sm;
     a.mu_vec4 = (h->C % 4 == 0) ? 1 : 0;
     CA_LAUNCH(k_prologue, 2 + kProPsiBlocks + h->n_gene_blocks, kProThreads, 0, h->stream)(a);
@@ -694,7 +701,7 @@ void run_train(ca_handle* h, bool apply) {
     if (!h->p2p_ready) fail("variant p2p: ca_core_p2p_connect has not been called");
     LaunchScope ls(h, "allreduce");
     P2PArgs a;
-    a.world = h->cfg.world; a.rank = h->cfg.rank; a.cnt = h->p2p_cnt; a.cnt_pad = h->p2p_cnt_pad; a.step = ++h->p2p_step;
+    a.world = h->cfg.world; a.rank = h->cfg.rank; a.cnt = h->p2p_cnt; a.cnt_pad = h->p2p_cnt_pad; a.step_ctr = &h->dstate->p2p_step;
     a.src = h->ar; a.dst = h->ar; a.ticket = h->p2p_ticket; a.error = h->p2p_err;
     for (int r = 0; r < kP2PMaxWorld; ++r) { a.slots[r] = h->p2p_slots[r]; a.flags[r] = h->p2p_flags[r]; }
     CA_LAUNCH(k_p2p_allreduce, std::min(h->num_sms, 16), kP2PThreads, 0, h->stream)(a);
@@ -728,6 +735,7 @@ void run_train(ca_handle* h, bool apply) {
       aa.n_gene_blocks = (h->G + 255) / 256;
       aa.n_cell_blocks = (apply || h->defer) ? ceil_div64(h->N * h->C + h->N, 256) : 0;
       aa.defer_yv = h->defer ? 1 : 0; aa.nCB = h->nCB; aa.rowpart = h->rowpart; aa.YV = h->YV;
+      aa.state = h->dstate;
       CA_LAUNCH(k_adam_all, (unsigned)(aa.n_gene_blocks + aa.n_cell_blocks + 1), 256, 0, h->stream)(aa);
       KCHECK();
     } else {
@@ -759,6 +767,65 @@ void run_elbo_async(ca_handle* h) {
   if (h->cfg.world > 1) NCCL_OK(nccl().AllReduce(h->cell_sum, h->cell_sum, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
   CA_LAUNCH(k_elbo_final, 1, 256, 0, h->stream)(h->cell_sum, h->gene_part, h->n_gene_blocks, h->scal_elbo, h->poison, h->elbo_dev);
   KCHECK();
+}
+
+// ---- CUDA-graph replay of the train step / the ELBO evaluation --------------------------------------
+// The fused (lean) kernel set keeps everything that changes from step to step in device memory (StepState), so the
+// launches of a step have constant arguments: the sequence is captured once per (kind, "Y pass needed") and replayed with
+// one cudaGraphLaunch -- 7-9 launches, the fork / join of the Y-pass stream and the all-reduce of a sharded fit included.
+// Not used with host-fed draws (test hook), per-kernel profiling or inspection copies; CLONEALIGN_B200_NO_GRAPH=1 disables it.
+bool graph_ok(ca_handle* h) {
+#ifdef CA_EMULATE
+  return false;
+#else
+  return h->use_graph && h->lean && !h->prof_on && !h->inspect && h->eps_queue.empty();
+#endif
+}
+#ifndef CA_EMULATE
+template <typename F>
+void capture_or_replay(ca_handle* h, cudaGraphExec_t& exec, F&& body, const std::function<void()>& host_effects) {
+  if (!exec) {
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      body();                                  // also applies the host-side bookkeeping once
+    } catch (...) {
+      cudaStreamEndCapture(h->stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    CUDA_OK(cudaStreamEndCapture(h->stream, &graph));
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CUDA_OK(e);
+  } else {
+    host_effects();
+  }
+  CUDA_OK(cudaGraphLaunch(exec, h->stream));
+}
+#endif
+void train_step(ca_handle* h) {
+#ifndef CA_EMULATE
+  if (graph_ok(h)) {
+    const int key = h->ydirty ? 1 : 0;
+    const int n_launch = h->launches_last_step;
+    capture_or_replay(h, h->g_train[key], [&] { run_train(h, true); },
+                      [&] { h->draw++; h->adam_t++; h->ydirty = true; h->pending_join = false; (void)n_launch; });
+    return;
+  }
+#endif
+  run_train(h, true);
+}
+void eval_step(ca_handle* h) {
+#ifndef CA_EMULATE
+  if (graph_ok(h)) {
+    const int key = h->ydirty ? 1 : 0;
+    capture_or_replay(h, h->g_eval[key], [&] { run_elbo_async(h); },
+                      [&] { h->draw++; if (h->KP > 0) h->ydirty = false; h->pending_join = false; });
+    return;
+  }
+#endif
+  run_elbo_async(h);
 }
 
 // ---- host <-> device helpers ---------------------------------------------------------------------
@@ -887,6 +954,10 @@ void destroy(ca_handle* h) {
   if (h->comm) comm_release(h->cfg.world, h->cfg.rank, h->dev, h->comm);   // parked for the next session of this shape
   for (int r = 0; r < kP2PMaxWorld; ++r)
     if (h->p2p_mapped[r]) cudaIpcCloseMemHandle(h->p2p_mapped[r]);
+#ifndef CA_EMULATE
+  for (auto* g : {&h->g_train[0], &h->g_train[1], &h->g_eval[0], &h->g_eval[1]})
+    if (*g) { cudaGraphExecDestroy(*g); *g = nullptr; }
+#endif
   tc_plan_destroy(h->tcplan);
   for (auto& p : h->prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (void* p : h->allocs)
@@ -933,6 +1004,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   // Measured on B200 (profiles/r01_notes.md): co-scheduling the Y stream with the forward contraction does not pay
   // yet (the register-light Y kernel is slower than the saved time), so the fork is opt-in.
   h->overlap = getenv("CLONEALIGN_B200_OVERLAP") != nullptr || (c.variants & CA_VAR_OVERLAP);
+  h->use_graph = getenv("CLONEALIGN_B200_NO_GRAPH") == nullptr;
 
   h->N = c.N; h->Ntot = c.N_total > 0 ? c.N_total : c.N; h->G = c.G; h->C = c.C; h->S = c.S; h->K = c.K; h->P = c.P;
   h->KP = c.K + c.P; h->SC = c.S * c.C; h->V = c.V;
@@ -940,15 +1012,16 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if (c.path == CA_PATH_TENSOR && !tc_ok) fail("tensor path needs K == 1, P == 0 and S*C <= 128");
   if (c.path == CA_PATH_INTERP && !(c.K == 1 && c.P == 0)) fail("interp path needs K == 1 and P == 0");
   // path = auto: the reference's default model (K = 1, no covariates; K is forced to 1 at R/clonealign.R:226-232) runs the
-  // univariate-interpolation kernel set that round 2 validated on hardware (profiles/r02_notes.md): interp + packed Y pass
-  // on the stored integers + fused per-cell kernel + fused gene-level launches + late join of the Y pass.  Explicit
-  // variant bits of the caller are kept (ypass2 instead of ypass3, overlap, p2p).  Other shapes: tcgen05 contractions
+  // univariate-interpolation kernel set that round 2 validated on hardware (profiles/r02_notes.md): interp + bulk-copy Y
+  // pass on the stored integers, co-scheduled with the rest of the step + fused per-cell kernel + fused gene-level
+  // launches + late join of the Y pass.  Explicit variant bits of the caller are kept (ypass2 / ypass3, overlap, p2p).  Other shapes: tcgen05 contractions
   // (K = 1, S*C <= 128) or the CUDA-core kernels (any K + P <= 8).
   const bool interp_ok = c.K == 1 && c.P == 0 && c.C <= kFusedMaxC && c.S * c.C <= 32 * kFusedMaxNJ;
   if (c.path == CA_PATH_AUTO && interp_ok) {
     h->cfg.path = CA_PATH_INTERP;
-    if (!(h->cfg.variants & (CA_VAR_YPASS2 | CA_VAR_YPASS3 | CA_VAR_YPASS4))) h->cfg.variants |= CA_VAR_YPASS3;
+    if (!(h->cfg.variants & (CA_VAR_YPASS2 | CA_VAR_YPASS3 | CA_VAR_YPASS4))) h->cfg.variants |= CA_VAR_YPASS4;
     h->cfg.variants |= CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_DEFER;
+    if (h->cfg.variants & CA_VAR_YPASS4) h->cfg.variants |= CA_VAR_COSCHED;
   }
   h->interp = (c.path == CA_PATH_INTERP);
   h->variants = c.variants;
@@ -1116,6 +1189,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   }
 
   // ---- parameters (R/inference-tflow.R:240-272) ----
+  h->dstate = h->alloc<StepState>(1);
   auto z = [&](size_t n) { return h->alloc<float>(n); };
   h->U = z((size_t)N * KP + 64); h->m_U = z((size_t)N * KP); h->v_U = z((size_t)N * KP); h->g_U = z((size_t)N * KP);
   h->Vm = z((size_t)G * KP + 64); h->m_V = z((size_t)G * KP); h->v_V = z((size_t)G * KP); h->g_V = z((size_t)G * KP);
@@ -1517,7 +1591,7 @@ int ca_core_step(ca_handle* h, char* err, size_t errlen) {
   try {
     if (!h) fail("null handle");
     CUDA_OK(cudaSetDevice(h->dev));
-    run_train(h, true);
+    train_step(h);
     return 0;   // asynchronous: the next call on this handle is stream-ordered behind it
   } catch (const std::exception& e) { return report(e, err, errlen); }
 }
@@ -1538,7 +1612,7 @@ int ca_core_elbo(ca_handle* h, double* elbo, char* err, size_t errlen) {
   try {
     if (!h || !elbo) fail("null argument");
     CUDA_OK(cudaSetDevice(h->dev));
-    run_elbo_async(h);
+    eval_step(h);
     CUDA_OK(cudaMemcpyAsync(elbo, h->elbo_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     int p2p_failed = 0;
     if (h->p2p_err) CUDA_OK(cudaMemcpyAsync(&p2p_failed, h->p2p_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -1560,7 +1634,7 @@ int ca_core_elbo_many(ca_handle* h, int32_t n, double* elbo, char* err, size_t e
     CUDA_OK(cudaSetDevice(h->dev));
     CUDA_OK(cudaMalloc(&d_out, sizeof(double) * (size_t)n));
     for (int i = 0; i < n; ++i) {
-      run_elbo_async(h);
+      eval_step(h);
       CUDA_OK(cudaMemcpyAsync(d_out + i, h->elbo_dev, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     }
     CUDA_OK(cudaMemcpyAsync(elbo, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
@@ -1679,8 +1753,8 @@ int ca_core_time_steps(ca_handle* h, int32_t n_steps, int32_t with_eval, double*
     CUDA_OK(cudaStreamSynchronize(h->stream));
     CUDA_OK(cudaEventRecord(a, h->stream));
     for (int i = 0; i < n_steps; ++i) {
-      run_train(h, true);
-      if (with_eval) run_elbo_async(h);
+      train_step(h);
+      if (with_eval) eval_step(h);
     }
     CUDA_OK(cudaEventRecord(b, h->stream));
     CUDA_OK(cudaEventSynchronize(b));
@@ -1895,6 +1969,43 @@ int ca_core_p2p_connect(ca_handle* h, const void* handles, char* err, size_t err
   } catch (const std::exception& e) { return report(e, err, errlen); }
 }
 
+// variant p2p inside ONE process (ca_core_multi_*): the peers' exchange buffers are ordinary device pointers (CUDA IPC
+// handles cannot be opened by the process that exported them); peer access is enabled on demand.
+int ca_core_p2p_base(ca_handle* h, void** base, char* err, size_t errlen) {
+  try {
+    if (!h || !base) fail("bad argument");
+    if (!h->p2p) fail("ca_core_p2p_base: the session was not created with variant p2p (and world > 1)");
+    CUDA_OK(cudaSetDevice(h->dev));
+    CUDA_OK(cudaStreamSynchronize(h->stream));   // the zero-fill of the flags must have landed before a peer can signal
+    *base = h->p2p_buf;
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
+int ca_core_p2p_connect_ptrs(ca_handle* h, void* const* bases, const int32_t* devices, char* err, size_t errlen) {
+  try {
+    if (!h || !bases || !devices) fail("bad argument");
+    if (!h->p2p) fail("ca_core_p2p_connect_ptrs: the session was not created with variant p2p (and world > 1)");
+    CUDA_OK(cudaSetDevice(h->dev));
+    const int world = h->cfg.world;
+    const size_t slot_bytes = sizeof(float) * 2 * (size_t)world * h->p2p_cnt_pad;
+    for (int r = 0; r < world; ++r) {
+      if (r != h->cfg.rank && devices[r] != h->dev) {
+        int can = 0;
+        CUDA_OK(cudaDeviceCanAccessPeer(&can, h->dev, devices[r]));
+        if (!can) fail("variant p2p: device %d cannot access device %d", h->dev, devices[r]);
+        cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_OK(e);
+        cudaGetLastError();
+      }
+      h->p2p_slots[r] = (float*)bases[r];
+      h->p2p_flags[r] = (unsigned*)((char*)bases[r] + slot_bytes + 256);
+    }
+    h->p2p_ready = true;
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
 int ca_core_ypass_many(ca_handle* const* hs, int32_t n, char* err, size_t errlen) {
   try {
     if (!hs || n < 1) fail("bad argument");
@@ -1904,7 +2015,7 @@ int ca_core_ypass_many(ca_handle* const* hs, int32_t n, char* err, size_t errlen
       ca_handle* h = hs[i];
       if (!h) fail("null handle");
       if (h->KP != 1) fail("ca_core_ypass_many needs K + P == 1");
-      if ((h->variants & CA_VAR_YPASS3) && n > 1) fail("ca_core_ypass_many: the batched kernel uses the column tiling of ypass2 (sessions with variant ypass3 run their own pass)");
+      if ((h->variants & (CA_VAR_YPASS3 | CA_VAR_YPASS4)) && n > 1) fail("ca_core_ypass_many: the batched kernel uses the column tiling of ypass2 (sessions with variant ypass3 / ypass4 run their own pass)");
       if (h->Y != h0->Y || h->dev != h0->dev || h->N != h0->N || h->G != h0->G || h->ystore != h0->ystore)
         fail("ca_core_ypass_many: the sessions do not share one count matrix (create them with ca_core_create_shared)");
     }

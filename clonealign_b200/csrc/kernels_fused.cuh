@@ -286,6 +286,8 @@ struct PrologueArgs {
   unsigned* ticket;      // zero before the first launch; the last block resets it
   InterpPlan* plan;
   double dirichlet_const;   // C lgamma(1/C) - lgamma(1)   (host)
+  StepState* state;         // draw counter read by every gene block, advanced (with lr_t of this step) by the last block
+  double lr;                // learning rate
   SampleMuArgs mu;          // gene blocks (k_sample_mu): blocks 2 + kProPsiBlocks ..; gene_part has one partial per gene block
   int mu_vec4;              // C % 4 == 0: 16-byte stores of the contraction operand
 };
@@ -298,6 +300,7 @@ __global__ void __launch_bounds__(kProThreads) k_prologue(PrologueArgs a) {
   __shared__ float smin[32], smax[32];
   __shared__ int is_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const unsigned long long draw = a.state->draw;   // every block reads it before it arrives at the ticket below
   if (blockIdx.x == 0) {
     if (wid == 0) {
       // log_softmax(alpha_unconstr) (R/inference-tflow.R:255), Dirichlet(1/C) prior on alpha + 1e-3 (:324),
@@ -344,8 +347,10 @@ __global__ void __launch_bounds__(kProThreads) k_prologue(PrologueArgs a) {
     }
   } else if (blockIdx.x >= 2 + kProPsiBlocks) {
     const int gb = blockIdx.x - 2 - kProPsiBlocks;
-    if (a.mu_vec4) sample_mu_body<true>(a.mu, gb, dscr, a.mu.gene_part);
-    else sample_mu_body<false>(a.mu, gb, dscr, a.mu.gene_part);
+    SampleMuArgs m = a.mu;
+    m.draw = draw;
+    if (a.mu_vec4) sample_mu_body<true>(m, gb, dscr, m.gene_part);
+    else sample_mu_body<false>(m, gb, dscr, m.gene_part);
   } else {
     const int pb = blockIdx.x - 2;
     const int64_t per = (a.N + kProPsiBlocks - 1) / kProPsiBlocks;
@@ -381,6 +386,10 @@ __global__ void __launch_bounds__(kProThreads) k_prologue(PrologueArgs a) {
     a.mm_psi[1] = mx;
     *a.plan = interp_make_plan((double)mw[0], (double)mw[1], (double)mn, (double)mx);
     *a.ticket = 0u;
+    // this forward pass has consumed draw `draw`; the optimiser step that may follow is step adam_t + 1
+    a.state->draw = draw + 1ull;
+    const double t = (double)(a.state->adam_t + 1);
+    a.state->lr_t = (float)(a.lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
   }
 }
 
@@ -442,9 +451,25 @@ __global__ void __launch_bounds__(kGeneWarps * 32) k_gene_fused(GeneFusedArgs a)
   for (int gbase = blockIdx.x * kGeneWarps; gbase < a.G; gbase += nblk * kGeneWarps) {   // block-uniform trip count
     {
       const int gi = threadIdx.x % kGeneWarps, sl = threadIdx.x / kGeneWarps;            // 512 threads = 32 slices x 16 genes
+      // 8 loads in flight per thread, summed in row-block order: a serial chain paid one DRAM latency per row block and
+      // round (ncu of round 2: long_scoreboard 10 of 22 stall cycles per issue, 82 us for the whole kernel)
       double part = 0.0;
-      if (gbase + gi < a.G)
-        for (int rb = sl; rb < a.nRB; rb += 32) part += (double)a.colpart[(int64_t)rb * a.G + gbase + gi];
+      if (gbase + gi < a.G) {
+        const float* cp = a.colpart + gbase + gi;
+        int rb = sl;
+        for (; rb + 7 * 32 < a.nRB; rb += 8 * 32) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = cp[(int64_t)(rb + 32 * u) * a.G];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) part += (double)v[u];
+        }
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (rb + 32 * u < a.nRB) ? cp[(int64_t)(rb + 32 * u) * a.G] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) part += (double)v[u];
+      }
       cpart[sl][gi] = part;
     }
     __syncthreads();
@@ -519,9 +544,11 @@ struct AdamAllArgs {
   int defer_yv, nCB;         // variant DEFER: d psi_n += (YW)_n = sum_cb rowpart[cb][n] (fixed order)
   const float* rowpart;
   float* YV;
+  StepState* state;          // lr_t of this step (k_prologue); the scalar block advances adam_t
 };
 __global__ void __launch_bounds__(256) k_adam_all(AdamAllArgs a) {
   const int64_t b = blockIdx.x;
+  a.ga.h.lr_t = a.sa.h.lr_t = a.state->lr_t;   // nobody writes lr_t while this kernel runs
   if (b < a.n_gene_blocks) {
     const GeneAdamArgs& q = a.ga;
     const int g = (int)b * blockDim.x + threadIdx.x;
@@ -586,6 +613,7 @@ __global__ void __launch_bounds__(256) k_adam_all(AdamAllArgs a) {
     if (q.h.apply) {
       adam_update(q.chi_raw[0], q.m_chi[0], q.v_chi[0], q.g_chi[0], q.h);
       for (int c = 0; c < q.C; ++c) adam_update(q.u[c], q.m_u[c], q.v_u[c], q.g_u[c], q.h);
+      a.state->adam_t += 1;                     // read only by the next k_prologue (stream order)
     }
   }
 }

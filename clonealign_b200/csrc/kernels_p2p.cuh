@@ -30,7 +30,7 @@ constexpr int kP2PThreads = 512;
 struct P2PArgs {
   int world, rank;
   int64_t cnt, cnt_pad;            // floats per contribution (cnt_pad: multiple of 4)
-  unsigned step;                   // 1, 2, 3, ... (flags start at 0)
+  unsigned* step_ctr;              // device counter of finished exchanges: this launch is exchange *step_ctr + 1 (flags start at 0)
   const float* src;                // this rank's partial sums [cnt]
   float* dst;                      // reduced result [cnt] (may alias src)
   float* slots[kP2PMaxWorld];      // base of every rank's slots[2][world][cnt_pad] (own entry = local pointer)
@@ -42,7 +42,8 @@ constexpr long long kP2PSpinCycles = 6000000000LL;   // ~3 s of SM clock: a dead
 
 __global__ void __launch_bounds__(kP2PThreads) k_p2p_allreduce(P2PArgs a) {
   __shared__ int is_last;
-  const int par = (int)(a.step & 1u);
+  const unsigned step = *a.step_ctr + 1u;      // every block reads it before it arrives at the ticket
+  const int par = (int)(step & 1u);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   // ---- push ----
   const int64_t nvec = a.cnt_pad / 4;
@@ -67,14 +68,14 @@ __global__ void __launch_bounds__(kP2PThreads) k_p2p_allreduce(P2PArgs a) {
   if (is_last && threadIdx.x < a.world) {
     __threadfence_system();
     volatile unsigned* f = a.flags[threadIdx.x] + par * a.world + a.rank;
-    *f = a.step;
-    if (threadIdx.x == 0) *a.ticket = 0u;
+    *f = step;
+    if (threadIdx.x == 0) { *a.ticket = 0u; *a.step_ctr = step; }
   }
   // ---- wait for every rank's contribution in the local buffer ----
   if (threadIdx.x < a.world) {
     volatile unsigned* f = a.flags[a.rank] + par * a.world + threadIdx.x;
     const long long t0 = clock64();
-    while (*f != a.step) {
+    while (*f != step) {
       if (clock64() - t0 > kP2PSpinCycles) {
         *a.error = 1;
         break;

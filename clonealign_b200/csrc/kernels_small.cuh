@@ -683,6 +683,18 @@ struct AdamHyper {
   float lr_t, b1, b2, eps;
   int apply;   // 0: gradients only
 };
+// Per-session counters that change from step to step, kept in DEVICE memory for the fused (lean) kernel set so that the
+// launches of a train step / ELBO evaluation have constant arguments and can be replayed as a CUDA graph:
+// draw = index of the next N(0,1) draw (advanced by every forward pass, k_prologue), adam_t = optimiser steps taken
+// (advanced by k_adam_all), lr_t = lr sqrt(1 - b2^t) / (1 - b1^t) of the step in flight (TF1 Adam; set by
+// k_prologue), p2p_step = exchanges done by the peer-memory all-reduce kernel.
+struct StepState {
+  unsigned long long draw;
+  int adam_t;
+  float lr_t;
+  unsigned p2p_step;
+  int pad;
+};
 __device__ __forceinline__ void adam_update(float& th, float& m, float& v, float g_elbo, const AdamHyper& h) {
   // TF1 AdamOptimizer on loss = -ELBO: epsilon outside the bias correction
   float g = -g_elbo;

@@ -176,6 +176,13 @@ int ca_core_multi_create(ca_multi** out, const ca_config* cfg, const int32_t* de
                           clone_allele, cfg->V > 0 ? al.data() : nullptr, cfg->V > 0 ? cv.data() : nullptr, e, el);
   }, err, errlen);
   if (st) { destroy_multi(m); return st; }
+  if (n_devices > 1 && (cfg->variants & CA_VAR_P2P)) {
+    // variant p2p: every shard learns the exchange buffers of its peers (plain device pointers within one process)
+    std::vector<void*> bases(n_devices, nullptr);
+    int s2 = m->run_all([&](int i, char* e, size_t el) { return ca_core_p2p_base(m->h[i], &bases[i], e, el); }, err, errlen);
+    if (!s2) s2 = m->run_all([&](int i, char* e, size_t el) { return ca_core_p2p_connect_ptrs(m->h[i], bases.data(), devices, e, el); }, err, errlen);
+    if (s2) { destroy_multi(m); return s2; }
+  }
   *out = m;
   return 0;
 }

@@ -216,6 +216,9 @@ CA_API int ca_core_pca_scores(ca_handle* h, int32_t max_iter, double tol, double
  * the gene-level gradient partials runs as one kernel over peer memory (kernels_p2p.cuh).  Collective calls. */
 CA_API int ca_core_p2p_export(ca_handle* h, void* handle64, char* err, size_t errlen);
 CA_API int ca_core_p2p_connect(ca_handle* h, const void* handles, char* err, size_t errlen);
+/* the same inside one process (ca_core_multi_* does this itself): the exchange buffers as plain device pointers */
+CA_API int ca_core_p2p_base(ca_handle* h, void** base, char* err, size_t errlen);
+CA_API int ca_core_p2p_connect_ptrs(ca_handle* h, void* const* bases, const int32_t* devices, char* err, size_t errlen);
 
 /* Measurement hooks (bench.py): run n_steps train steps (and, if with_eval != 0, one ELBO
  * evaluation after each, as the reference loop does) back to back on the handle's stream,

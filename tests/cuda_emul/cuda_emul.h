@@ -497,10 +497,11 @@ Launcher<K> launcher(K kernel, dim3 grid, dim3 block, size_t smem) { return {ker
 // the part of the CUDA runtime API that core.cu uses (synchronous, host memory)
 // ------------------------------------------------------------------------------------------------------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorPeerAccessAlreadyEnabled = 704 };
 typedef struct ca_emul_stream* cudaStream_t;
 struct ca_emul_event { std::chrono::steady_clock::time_point t; };
 typedef ca_emul_event* cudaEvent_t;
+typedef void* cudaGraphExec_t;   // graphs are never built under emulation (core.cu: graph_ok)
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
@@ -511,6 +512,8 @@ inline const char* cudaGetErrorString(cudaError_t e) { return e ? "emulated fail
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }
+inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   const char* e = getenv("CA_EMUL_SMS");
   *p = {10, 0, e ? atoi(e) : 3};

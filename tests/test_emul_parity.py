@@ -27,7 +27,7 @@ def test_emulated_library_is_not_the_product(emulated_library):
     assert "cuda_emul" in emulated_library and "cuda_emul" in _lib.LIB_PATH
     with _session(np.ones((4, 3)), np.ones((3, 2)), np.zeros((4, 1)), np.ones(3), path="auto") as sess:
         d = sess.describe()                                     # the default model runs the interpolation kernel set
-        assert d["path"] == "interp" and d["variants"] == 2 | 4 | 32 | 64
+        assert d["path"] == "interp" and d["variants"] == 2 | 4 | 64 | 128 | 256
     with _session(np.ones((4, 3)), np.ones((3, 2)), np.zeros((4, 2)), np.ones(3), K=2, path="auto") as sess:
         assert sess.describe()["path"] == "cudacore"            # tcgen05 is unavailable under emulation
     from clonealign_b200._lib import CloneAlignLibraryError
@@ -422,7 +422,7 @@ def test_sparse_input_stays_compressed(example_sce):
 
 @pytest.mark.parametrize("path", [("cudacore", ""), ("interp", "ypass2,epi2,lean"), ("cudacore", "p2p"),
                                   ("interp", "ypass2,epi2,lean,p2p"), ("interp", "ypass3,epi2,lean"),
-                                  ("interp", "ypass3,epi2,lean,defer,overlap")])
+                                  ("interp", "ypass3,epi2,lean,defer,overlap"), ("auto", ""), ("auto", "p2p")])
 @pytest.mark.parametrize("world", [2, 3])
 def test_cell_sharded_fit_matches_single_shard(example_sce, path, world):
     """SURVEY 8e through the REAL sharded code path of core.cu: `world` ranks (threads of this process; the emulation
@@ -507,6 +507,17 @@ def test_single_process_multi_gpu_equals_one_rank_per_process(example_sce, world
     alt = rng.binomial(cov.astype(int), 0.4).astype(float)
     kw = dict(mc_samples=2, K=1, seed=77, clone_allele=cn)
     Yin = {"rowmajor_u8": Yk.astype(np.uint8), "colmajor_f64": np.asfortranarray(Yk), "csr": sp.csr_matrix(Yk)}[layout]
+    if world > 1 and layout == "csr":
+        # variant p2p inside one process: the exchange buffers are wired up by ca_core_multi_create itself; the rank-ordered
+        # reduction of the kernel gives the same bits as the (emulated, rank-ordered) NCCL all-reduce
+        with MultiSession(Yin, Lk, psi, loc, devices=[0] * world, alt=alt, cov=cov, variants="p2p", **kw) as ms:
+            e_p2p, p_p2p = None, None
+            ms.init_gamma()
+            e_p2p = [ms.elbo()]
+            for _ in range(3):
+                ms.step()
+                e_p2p.append(ms.elbo())
+            p_p2p = ms.params()
 
     def trace(sess):
         sess.init_gamma()
@@ -540,6 +551,8 @@ def test_single_process_multi_gpu_equals_one_rank_per_process(example_sce, world
     [t.join(timeout=300) for t in ts]
     assert not errs and all(o is not None for o in outs), errs
     assert e_multi.tobytes() == outs[0][0].tobytes()
+    if world > 1 and layout == "csr":
+        assert np.array(e_p2p).tobytes() == e_multi[:4].tobytes()
     for k in ("clone_probs", "psi", "s", "clone_probs_from_snv"):
         assert p_multi[k].tobytes() == np.concatenate([o[1][k] for o in outs]).tobytes(), k
     for k in ("mu", "W", "alpha", "chi"):
@@ -552,7 +565,7 @@ def test_several_row_and_column_tiles(path):
     """N > 2 row blocks of the Y pass (RB = 512), G > one 2048-column tile, more cells than one sweep of the persistent
     per-cell / per-gene kernels: tile seams, partial-sum layouts and strided loops."""
     from clonealign_b200.synthetic import make_synthetic
-    syn = make_synthetic(1100, 4500 if "ypass3" in path[1] else 2300, 4, seed=8)      # ypass3 / u8: 4096-column tiles
+    syn = make_synthetic(1100, 4500 if ("ypass3" in path[1] or "ypass4" in path[1]) else 2300, 4, seed=8)      # ypass3 / u8: 4096-column tiles
     d, p, mu_guess, _ = _case(syn["Y"].astype(np.float64), np.minimum(syn["L"], 6.0), K=1, seed=2)
     with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=2, K=1, path=path[0], variants=path[1], seed=1) as sess:
         _load_params(sess, p)
@@ -858,7 +871,7 @@ def test_random_shapes_and_variants():
         d, p, mu_guess, _ = _case(Y, L, K=1, seed=it, scale=float(rng.choice([0.05, 0.3, 1.0])))
         p.psi *= float(rng.choice([0.5, 1.0, 3.0]))
         var = str(rng.choice(["", "ypass2", "epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap", "ypass3", "ypass3,epi2,lean",
-                              "ypass2,epi2,lean,defer", "ypass3,epi2,lean,defer,overlap"]))
+                              "ypass2,epi2,lean,defer", "ypass3,epi2,lean,defer,overlap", "ypass4", "ypass4,epi2,lean,defer,cosched"]))
         with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path="interp", seed=1, variants=var) as sess:
             _load_params(sess, p)
             try:

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 ELBO_RTOL = 1e-4
 PARAM_RTOL = 1e-3
-# "auto" = what a drop-in clonealign() call runs: for K = 1, P = 0 the interpolation kernel set (interp + ypass3,epi2,lean,defer);
+# "auto" = what a drop-in clonealign() call runs: for K = 1, P = 0 the interpolation kernel set (interp + ypass4,epi2,lean,defer,cosched);
 # "interp" = the same contraction-free path with its unfused kernels; "tensor" / "cudacore" = the contraction kernels.
 PATHS = ["cudacore", "tensor", "interp", "auto"]
 
