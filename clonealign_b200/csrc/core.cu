@@ -684,7 +684,12 @@ void run_train(ca_handle* h, bool apply) {
     a.Vm = h->Vm; a.colpart = h->colpart; a.mu = h->mu; a.sig = h->sig; a.eps = h->eps; a.lsd = h->lsd; a.L = h->L;
     a.ar = h->ar; a.YtU = h->YtU; a.dM_out = h->inspect ? h->dM_sum : nullptr;
     a.gsum_part = h->gsum_part; a.n_parts = h->n_cell_parts;
-    CA_LAUNCH(k_gene_fused, h->num_sms + 1, kGeneWarps * 32, h->gene_smem, h->stream)(a);
+    switch ((h->SC + 31) / 32) {
+      case 1: { auto k = k_gene_fused<1>; CA_LAUNCH(k, h->num_sms + 1, kGeneWarps * 32, h->gene_smem, h->stream)(a); break; }
+      case 2: { auto k = k_gene_fused<2>; CA_LAUNCH(k, h->num_sms + 1, kGeneWarps * 32, h->gene_smem, h->stream)(a); break; }
+      case 3: { auto k = k_gene_fused<3>; CA_LAUNCH(k, h->num_sms + 1, kGeneWarps * 32, h->gene_smem, h->stream)(a); break; }
+      default: { auto k = k_gene_fused<4>; CA_LAUNCH(k, h->num_sms + 1, kGeneWarps * 32, h->gene_smem, h->stream)(a); break; }
+    }
     KCHECK();
   } else {
     LaunchScope ls(h, "gene_grads", 2);
@@ -1316,7 +1321,12 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     if (const char* e = getenv("CLONEALIGN_B200_FUSED_PANELS")) h->gene_panels = std::max(0, std::min(h->gene_panels, atoi(e)));
     h->gene_smem = gene_fused_smem_bytes(J, h->gene_panels);
     if (h->gene_smem > 48 * 1024)
-      CUDA_OK(cudaFuncSetAttribute(k_gene_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gene_smem));
+    {
+      CUDA_OK(cudaFuncSetAttribute(k_gene_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gene_smem));
+      CUDA_OK(cudaFuncSetAttribute(k_gene_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gene_smem));
+      CUDA_OK(cudaFuncSetAttribute(k_gene_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gene_smem));
+      CUDA_OK(cudaFuncSetAttribute(k_gene_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gene_smem));
+    }
   }
   if (h->epi2) {
     h->fused_nj = (h->SC + 31) / 32;

@@ -414,6 +414,12 @@ inline int gene_fused_smem_panels(int J, size_t budget = 96 * 1024) {
   return (int)(n > (size_t)kIMaxPanB ? (size_t)kIMaxPanB : n);
 }
 
+// Latency structure (ncu of round 2: 75 us at 26 % issue, stall samples spread over the Clenshaw chains, the loads of a
+// gene's inputs issued behind them and the gather of the column partials): per gene a lane now owns NJ columns (template,
+// as in k_cell_fused), loads sigma / L / eps / mu of its columns BEFORE the recurrences, and runs the 2 NJ Clenshaw chains
+// (dM and dM') of all its columns interleaved; the column partials of the NEXT round of 16 genes are fetched while this
+// round computes.
+template <int NJ>
 __global__ void __launch_bounds__(kGeneWarps * 32) k_gene_fused(GeneFusedArgs a) {
   CA_DYNAMIC_SMEM(double, csm);
   __shared__ double scratch[32];
@@ -432,94 +438,104 @@ __global__ void __launch_bounds__(kGeneWarps * 32) k_gene_fused(GeneFusedArgs a)
   const int npan = pl.nb;
   const bool in_smem = npan <= a.smem_panels;
   const int64_t per_panel = (int64_t)kIP * a.J;
+  const double ih = pl.b_w > 0.0 ? 2.0 / pl.b_w : 0.0;
+  const int nblk = gridDim.x - 1;
+  const int SC = a.SC;
+  // Y^T psi partials of the Y pass, colpart [nRB][G]: the 16 genes a block works on in one round are consecutive, so
+  // the block sums their partials cooperatively -- thread (slice, gene) strides over the row blocks and reads 16
+  // consecutive floats per row block (whole 32-byte sectors); slices are combined in a fixed order.  kGMaxPer loads per
+  // thread are in flight at once (up to 32 x kGMaxPer row blocks; more are summed by a serial tail).
+  constexpr int kGMaxPer = 8;
+  __shared__ double cpart[32][kGeneWarps];
+  const int gi = threadIdx.x % kGeneWarps, sl = threadIdx.x / kGeneWarps;            // 512 threads = 32 slices x 16 genes
+  auto fetch = [&](int gbase, float (&v)[kGMaxPer]) {
+    const bool ok = gbase + gi < a.G;
+    const float* cp = a.colpart + gbase + gi;
+#pragma unroll
+    for (int u = 0; u < kGMaxPer; ++u) v[u] = (ok && sl + 32 * u < a.nRB) ? cp[(int64_t)(sl + 32 * u) * a.G] : 0.f;
+  };
+  // cell-independent per-lane constants: columns j = lane + 32 i, their (sample, clone)
+  int jz[NJ], sj[NJ], cj[NJ];
+  bool jok[NJ];
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    const int j = lane + 32 * i;
+    jok[i] = j < SC;
+    jz[i] = jok[i] ? j : SC - 1;
+    sj[i] = jz[i] / a.C;
+    cj[i] = jz[i] - sj[i] * a.C;
+  }
+  float vcur[kGMaxPer];
+  fetch(blockIdx.x * kGeneWarps, vcur);
   if (in_smem) {
     for (int64_t i = threadIdx.x; i < npan * per_panel; i += blockDim.x) {
       const int j = (int)(i % a.J);
       const int64_t pk = i / a.J;
       csm[((pk / kIP) * a.J + j) * kFusedPitch + (int)(pk % kIP)] = a.coeff[i];
     }
-    __syncthreads();
   }
-  const double ih = pl.b_w > 0.0 ? 2.0 / pl.b_w : 0.0;
-  const int nblk = gridDim.x - 1;
-  const int SC = a.SC;
-  // Y^T psi partials of the Y pass, colpart [nRB][G]: the 16 genes a block works on in one round are consecutive, so
-  // the block sums their partials cooperatively -- thread (slice, gene) strides over the row blocks and reads 16
-  // consecutive floats per row block (whole 32-byte sectors) -- instead of every warp gathering its gene's nRB partials
-  // with a stride of G floats (one useful float per sector: 8x the traffic); slices are combined in a fixed order.
-  __shared__ double cpart[32][kGeneWarps];
   for (int gbase = blockIdx.x * kGeneWarps; gbase < a.G; gbase += nblk * kGeneWarps) {   // block-uniform trip count
     {
-      const int gi = threadIdx.x % kGeneWarps, sl = threadIdx.x / kGeneWarps;            // 512 threads = 32 slices x 16 genes
-      // 8 loads in flight per thread, summed in row-block order: a serial chain paid one DRAM latency per row block and
-      // round (ncu of round 2: long_scoreboard 10 of 22 stall cycles per issue, 82 us for the whole kernel)
       double part = 0.0;
-      if (gbase + gi < a.G) {
-        const float* cp = a.colpart + gbase + gi;
-        int rb = sl;
-        for (; rb + 7 * 32 < a.nRB; rb += 8 * 32) {
-          float v[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = cp[(int64_t)(rb + 32 * u) * a.G];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) part += (double)v[u];
-        }
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = (rb + 32 * u < a.nRB) ? cp[(int64_t)(rb + 32 * u) * a.G] : 0.f;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) part += (double)v[u];
-      }
+      for (int u = 0; u < kGMaxPer; ++u) part += (double)vcur[u];
+      if (gbase + gi < a.G)
+        for (int rb = sl + 32 * kGMaxPer; rb < a.nRB; rb += 32) part += (double)a.colpart[(int64_t)rb * a.G + gbase + gi];
       cpart[sl][gi] = part;
     }
-    __syncthreads();
+    __syncthreads();                                    // also publishes the staged coefficient table (first round)
+    fetch(gbase + nblk * kGeneWarps, vcur);             // next round's partials travel while this round computes
     const int g = gbase + wid;
     if (g < a.G) {
-    const float wf = a.Vm[g];
-    const double x = (double)wf;
-    int pb = (int)((x - pl.wmin) * ih * 0.5);
-    pb = pb < 0 ? 0 : (pb >= pl.nb ? pl.nb - 1 : pb);
-    const double tt = pl.b_w > 0.0 ? (x - (pl.wmin + pb * pl.b_w)) * ih - 1.0 : 0.0;
-    const double* cpan = in_smem ? csm + (size_t)pb * a.J * kFusedPitch : a.coeff + (int64_t)pb * per_panel;
-    const float sd = expf(a.lsd[g]);
-    double aloc = 0.0, alsd = 0.0, gv = 0.0;
-    for (int j0 = 0; j0 < SC; j0 += 32) {
-      const int j = j0 + lane;
-      const bool ok = j < SC;
-      const int jc[1] = {ok ? j : SC - 1};
-      double d[1], d2[1];
+      const float wf = a.Vm[g];
+      const float lsdf = a.lsd[g];
+      // inputs of this lane's columns, requested before the recurrences
+      float sg[NJ], lc[NJ], ep[NJ], mu[NJ];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        const int64_t o = (int64_t)sj[i] * a.G + g;
+        sg[i] = a.sig[o]; ep[i] = a.eps[o]; mu[i] = a.mu[o];
+        lc[i] = a.L[(int64_t)g * a.C + cj[i]];
+      }
+      const double x = (double)wf;
+      int pb = (int)((x - pl.wmin) * ih * 0.5);
+      pb = pb < 0 ? 0 : (pb >= pl.nb ? pl.nb - 1 : pb);
+      const double tt = pl.b_w > 0.0 ? (x - (pl.wmin + pb * pl.b_w)) * ih - 1.0 : 0.0;
+      const double* cpan = in_smem ? csm + (size_t)pb * a.J * kFusedPitch : a.coeff + (int64_t)pb * per_panel;
+      double d[NJ], d2[NJ];
       if (in_smem) {
-        clenshaw_cols<1, true>(cpan, jc, 0, a.J, tt, d);
-        clenshaw_cols<1, true>(cpan, jc, SC, a.J, tt, d2);
+        clenshaw_cols<NJ, true>(cpan, jz, 0, a.J, tt, d);
+        clenshaw_cols<NJ, true>(cpan, jz, SC, a.J, tt, d2);
       } else {
-        clenshaw_cols<1, false>(cpan, jc, 0, a.J, tt, d);
-        clenshaw_cols<1, false>(cpan, jc, SC, a.J, tt, d2);
+        clenshaw_cols<NJ, false>(cpan, jz, 0, a.J, tt, d);
+        clenshaw_cols<NJ, false>(cpan, jz, SC, a.J, tt, d2);
       }
-      if (ok) {
-        const int s = j / a.C, c = j - s * a.C;
-        const int64_t o = (int64_t)s * a.G + g;
-        const float l = a.L[(int64_t)g * a.C + c];
-        const float df = (float)d[0], d2f = (float)d2[0];   // the unfused path rounds dMx to fp32: keep its numerics
-        if (a.dM_out) {
-          a.dM_out[(int64_t)g * a.J + j] = df;
-          a.dM_out[(int64_t)g * a.J + SC + j] = d2f;
+      const float sd = expf(lsdf);
+      double aloc = 0.0, alsd = 0.0, gv = 0.0;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) {
+        if (jok[i]) {
+          const float df = (float)d[i], d2f = (float)d2[i];   // the unfused path rounds dMx to fp32: keep its numerics
+          if (a.dM_out) {
+            a.dM_out[(int64_t)g * a.J + jz[i]] = df;
+            a.dM_out[(int64_t)g * a.J + SC + jz[i]] = d2f;
+          }
+          const double dx = -(double)sg[i] * (double)lc[i] * (double)df;
+          aloc += dx;
+          alsd += dx * (double)sd * (double)ep[i];
+          gv -= (double)(mu[i] * lc[i]) * (double)d2f;
         }
-        const double dx = -(double)a.sig[o] * (double)l * (double)df;
-        aloc += dx;
-        alsd += dx * (double)sd * (double)a.eps[o];
-        gv -= (double)(a.mu[o] * l) * (double)d2f;
       }
-    }
-    aloc = warp_sum(aloc);
-    alsd = warp_sum(alsd);
-    gv = warp_sum(gv);
-    const double acc = warp_sum(cpart[lane][wid]);
-    if (lane == 0) {
-      a.YtU[g] = (float)acc;
-      a.ar[2 * (int64_t)a.G + g] = (float)(acc + gv);
-      a.ar[g] = (float)aloc;
-      a.ar[a.G + g] = (float)alsd;
-    }
+      aloc = warp_sum(aloc);
+      alsd = warp_sum(alsd);
+      gv = warp_sum(gv);
+      const double acc = warp_sum(cpart[lane][wid]);
+      if (lane == 0) {
+        a.YtU[g] = (float)acc;
+        a.ar[2 * (int64_t)a.G + g] = (float)(acc + gv);
+        a.ar[g] = (float)aloc;
+        a.ar[a.G + g] = (float)alsd;
+      }
     }
     __syncthreads();   // cpart is rewritten by the next round
   }

@@ -496,7 +496,7 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
   y4_fence_init();
   y4_fence_proxy();                                              // the zero fill (generic stores) before any bulk copy
   __syncthreads();
-  uint32_t gg = 0;                                               // groups of 8 rows consumed so far by this CTA (all tiles)
+  uint32_t ph = 0;                                               // bit st: parity the next wait on stage st has to see
   const int64_t ntiles = (int64_t)nCB * nRB;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int cb = (int)(tile % nCB);
@@ -516,29 +516,28 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
     const int nrows = (int)(rend - rbeg);
     const int ngroups = (nrows + 7) / 8;
     const T* ybase = Y + rbeg * ldY + tcol0;
-    const uint32_t gg0 = gg;
-    // group `g` of the tile (rows 8 g ..) -> stages 2 ((gg0 + g) & 1) and + 1; issued by thread 0 only
-    auto issue = [&](int g) {
+    // group `g` of the tile (rows 8 g ..) lives in stages S0, S0 + 1 with S0 = 2 (g & 1): even groups in stages 0 / 1, odd
+    // groups in 2 / 3 (the loop below is unrolled by two, so stage addresses are compile-time offsets); thread 0 issues.
+    auto issue = [&](auto s0c, int g) {
+      constexpr int S0 = decltype(s0c)::value;
       if (g >= ngroups) return;
-      const uint32_t s0 = 2u * ((gg0 + (uint32_t)g) & 1u);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int r0 = g * 8 + hh * kSR;
         const int nv = nrows - r0 < kSR ? nrows - r0 : kSR;
         if (nv <= 0) break;
-        y4_arm(bars + s0 + hh, (uint32_t)nv * tbytes);
+        y4_arm(bars + S0 + hh, (uint32_t)nv * tbytes);
         for (int i = 0; i < nv; ++i)
-          y4_bulk(ring + ((size_t)(s0 + hh) * kSR + i) * 256, ybase + (int64_t)(r0 + i) * ldY, tbytes, bars + s0 + hh);
+          y4_bulk(ring + ((size_t)(S0 + hh) * kSR + i) * 256, ybase + (int64_t)(r0 + i) * ldY, tbytes, bars + S0 + hh);
       }
     };
-    if (tid == 0) { issue(0); issue(1); }
+    if (tid == 0) { issue(std::integral_constant<int, 0>{}, 0); issue(std::integral_constant<int, 2>{}, 1); }
 #ifdef CA_EMULATE
     __syncthreads();                                             // the synchronous stand-in copies must precede the readers
 #endif
-    int buf = 0;
-    for (int g = 0; g < ngroups; ++g) {
+    auto group = [&](auto s0c, int g) {
+      constexpr int S0 = decltype(s0c)::value;
       const int64_t r0 = rbeg + (int64_t)g * 8;
-      const uint32_t gcur = gg0 + (uint32_t)g, s0 = 2u * (gcur & 1u), par = (gcur >> 1) & 1u;
       float u[8];   // U is allocated with 64 elements of slack, r0 is a multiple of 4: vector loads stay in bounds
 #pragma unroll
       for (int i = 0; i < 8; i += 4) {
@@ -550,8 +549,9 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
       for (int hh = 0; hh < 2; ++hh) {
         const int nv = nrows - (g * 8 + hh * kSR);               // valid rows of this stage
         if (nv > 0) {
-          y4_wait(bars + s0 + hh, par);
-          Raw* src = ring + (size_t)(s0 + hh) * kSR * 256 + tid;
+          y4_wait(bars + S0 + hh, (ph >> (S0 + hh)) & 1u);
+          ph ^= 1u << (S0 + hh);
+          Raw* src = ring + (size_t)(S0 + hh) * kSR * 256 + tid;
           if (nv < kSR) {
             // last stage of the tile: its trailing rows were not copied and hold stale ring contents.  Every thread
             // zeroes its own pieces (it reads them back itself below); the proxy fence orders these generic stores
@@ -582,20 +582,23 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
         }
       }
       const float tot = butterfly8(rp, lane);
+      const int buf = S0 >> 1;                                   // even / odd groups alternate between the two exchange buffers
       if ((lane & 3) == 0) red[buf][wid][ridx] = tot;
       __syncthreads();
       // every thread has issued the FMAs that consume its pieces of this group (in-order issue: their LDS have returned)
       // and passed the barrier: the two stages are free and are refilled with the group after next
-      if (tid == 0) issue(g + 2);
+      if (tid == 0) issue(s0c, g + 2);
       if (tid < 8 && r0 + tid < rend) {
         float acc = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) acc += red[buf][w][tid];
         rowpart[(int64_t)cb * N + r0 + tid] = acc * L::kPost;
       }
-      buf ^= 1;
+    };
+    for (int g = 0; g < ngroups; g += 2) {
+      group(std::integral_constant<int, 0>{}, g);
+      if (g + 1 < ngroups) group(std::integral_constant<int, 2>{}, g + 1);
     }
-    gg = gg0 + (uint32_t)ngroups;
 #pragma unroll
     for (int j = 0; j < kPairs; ++j) {
       if (col0 + 2 * j < G) colpart[rb * G + col0 + 2 * j] = cacc[j].x * L::kPost;
