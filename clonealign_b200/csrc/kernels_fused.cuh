@@ -52,6 +52,20 @@ inline int fused_smem_panels(int SC, int C, int J, size_t budget = 200 * 1024, i
   return (int)(n > (size_t)kIMaxPanF ? (size_t)kIMaxPanF : n);
 }
 
+// log of a positive fp32 value as a double: exponent and mantissa are split, the mantissa m in [0.707, 1.414) goes through
+// the hardware lg2 (__logf: absolute error <= 2^-21.4 on [0.5, 2]) and the exponent is added in fp64.  The absolute error
+// (3.6e-7) does not grow with |log z|, unlike logf's 1 ulp of the result (9.5e-7 at log z ~ 10) -- log Z is multiplied by
+// the library size before the clone softmax -- and it costs ~9 instructions instead of ~30 (ncu of round 2: logf was 98
+// of the 1090 warp instructions per cell).  Zero, denormal, infinite and NaN arguments take the library path.
+__device__ __forceinline__ double log_pos_f32(float z) {
+  if (!(z >= 1.17549435e-38f && z <= 3.4e38f)) return (double)logf(z);
+  const int bits = __float_as_int(z);
+  int e = ((bits >> 23) & 0xff) - 127;
+  float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+  if (m > 1.41421356f) { m *= 0.5f; e += 1; }
+  return (double)__logf(m) + (double)e * 0.69314718055994530942;
+}
+
 // One Clenshaw pass over NJ columns per lane.  SMEM: table staged as [panel][j][kIP + 1] -- a chain reads consecutive
 // doubles at compile-time offsets from its per-lane base (no address arithmetic in the recurrence; the odd row pitch
 // keeps the 64-bit reads of a half-warp on distinct banks).  Otherwise: coefficients through L2 in their [k][J] layout.
@@ -178,7 +192,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused(FusedArgs a)
 #pragma unroll
       for (int i = 0; i < NJ; ++i) {
         zf[i] = (float)z[i];
-        if (jok[i]) lz[jz[i]] = (double)logf(zf[i]) + m;
+        if (jok[i]) lz[jz[i]] = log_pos_f32(zf[i]) + m;
         if (a.Zx && jok[i]) a.Zx[n * a.J + jz[i]] = zf[i];
       }
     }
@@ -592,12 +606,29 @@ __global__ void __launch_bounds__(256) k_adam_all(AdamAllArgs a) {
       adam_update(q.Vm[g], q.m_V[g], q.v_V[g], gw, q.h);
     }
   } else if (b < a.n_gene_blocks + a.n_cell_blocks) {
+    // cell blocks: thread i < nt4 updates 4 consecutive gamma logits (16-byte loads / stores: a quarter of the threads,
+    // 4x the bytes in flight per thread -- the kernel is latency-bound), the threads behind them one psi each
     const int64_t i = (b - a.n_gene_blocks) * blockDim.x + threadIdx.x;
-    const int64_t nt = a.N * a.C;
-    if (i < nt) {
-      if (a.ga.h.apply) adam_update(a.t[i], a.m_t[i], a.v_t[i], a.gT[i], a.ga.h);
-    } else if (i - nt < a.N) {
-      const int64_t n = i - nt;
+    const int64_t nt = a.N * a.C, nt4 = (nt + 3) / 4;
+    if (i < nt4) {
+      if (a.ga.h.apply) {
+        const int64_t e0 = 4 * i;
+        if (e0 + 4 <= nt) {
+          float4 t4 = reinterpret_cast<float4*>(a.t)[i], m4 = reinterpret_cast<float4*>(a.m_t)[i], v4 = reinterpret_cast<float4*>(a.v_t)[i];
+          const float4 g4 = reinterpret_cast<const float4*>(a.gT)[i];
+          adam_update(t4.x, m4.x, v4.x, g4.x, a.ga.h);
+          adam_update(t4.y, m4.y, v4.y, g4.y, a.ga.h);
+          adam_update(t4.z, m4.z, v4.z, g4.z, a.ga.h);
+          adam_update(t4.w, m4.w, v4.w, g4.w, a.ga.h);
+          reinterpret_cast<float4*>(a.t)[i] = t4;
+          reinterpret_cast<float4*>(a.m_t)[i] = m4;
+          reinterpret_cast<float4*>(a.v_t)[i] = v4;
+        } else {
+          for (int64_t e = e0; e < nt; ++e) adam_update(a.t[e], a.m_t[e], a.v_t[e], a.gT[e], a.ga.h);
+        }
+      }
+    } else if (i - nt4 < a.N) {
+      const int64_t n = i - nt4;
       float g = a.gU[n];
       if (a.defer_yv) {
         double yv = 0.0;
