@@ -27,7 +27,7 @@ EXPORTS = (
     "ca_core_create_shared", "ca_core_ypass_many", "ca_core_data_stats", "ca_core_elbo_many", "ca_core_shutdown",
     "ca_core_multi_create", "ca_core_multi_destroy", "ca_core_multi_init_gamma", "ca_core_multi_step", "ca_core_multi_elbo",
     "ca_core_multi_elbo_many", "ca_core_multi_params", "ca_core_multi_time_steps", "ca_core_multi_shard", "ca_core_multi_size",
-    "ca_core_p2p_base", "ca_core_p2p_connect_ptrs",
+    "ca_core_p2p_base", "ca_core_p2p_connect_ptrs", "ca_core_data_masked_rowsums",
 )
 
 
@@ -85,6 +85,7 @@ def load():
     lib.ca_core_data_destroy.argtypes = [vp, cp, sz]
     lib.ca_core_create_shared.argtypes = [C.POINTER(vp), C.POINTER(CaConfig), vp, vp, vp, vp, cp, sz]
     lib.ca_core_data_stats.argtypes = [vp, vp, vp, vp, cp, sz]
+    lib.ca_core_data_masked_rowsums.argtypes = [vp, vp, vp, cp, sz]
     lib.ca_core_ypass_many.argtypes = [C.POINTER(vp), C.c_int32, cp, sz]
     lib.ca_core_p2p_export.argtypes = [vp, vp, cp, sz]
     lib.ca_core_p2p_connect.argtypes = [vp, vp, cp, sz]

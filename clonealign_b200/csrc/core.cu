@@ -1562,6 +1562,41 @@ int ca_core_data_stats(ca_data* d, double* rowsum, double* colsum, double* mu_gu
   } catch (const std::exception& e) { return report(e, err, errlen); }
 }
 
+// rowSums(Y[, keep]) over the resident matrix: the cell filter of preprocess_for_clonealign (R/preprocess.R:138-139), which
+// counts only the genes that survived the gene filters.  gene_keep: G bytes, non-zero = gene retained.
+int ca_core_data_masked_rowsums(ca_data* d, const uint8_t* gene_keep, double* rowsum, char* err, size_t errlen) {
+  try {
+    if (!d || !gene_keep || !rowsum) fail("null argument");
+    CUDA_OK(cudaSetDevice(d->dev));
+    const int64_t N = d->N;
+    const int G = d->G;
+    double* d_row = nullptr;
+    unsigned char* d_keep = nullptr;
+    struct Guard {
+      double*& a; unsigned char*& b;
+      ~Guard() { cudaFree(a); cudaFree(b); }
+    } guard{d_row, d_keep};
+    CUDA_OK(cudaMalloc(&d_row, sizeof(double) * N));
+    CUDA_OK(cudaMalloc(&d_keep, (size_t)G));
+    cudaStream_t st = nullptr;
+    CUDA_OK(cudaMemcpyAsync(d_keep, gene_keep, (size_t)G, cudaMemcpyHostToDevice, st));
+    auto run = [&](auto* Yp) {
+      using T = typename std::remove_const<typename std::remove_pointer<decltype(Yp)>::type>::type;
+      CA_LAUNCH(k_stats_rows_masked<T>, (unsigned)ceil_div64(N, 8), 256, 0, st)(Yp, d->ldY, N, G, d_keep, d_row);
+      KCHECK();
+    };
+    switch (d->ystore) {
+      case CA_STORE_F32: run((const float*)d->Y); break;
+      case CA_STORE_U16: run((const uint16_t*)d->Y); break;
+      case CA_STORE_U8: run((const uint8_t*)d->Y); break;
+      default: fail("bad y_store");
+    }
+    CUDA_OK(cudaMemcpyAsync(rowsum, d_row, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+  } catch (const std::exception& e) { return report(e, err, errlen); }
+}
+
 int ca_core_create_shared(ca_handle** out, const ca_config* cfg, ca_data* data, const double* psi_init, const double* loc_init,
                           const double* X, char* err, size_t errlen) {
   ca_handle* h = nullptr;

@@ -163,6 +163,21 @@ k_stats_rows(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, double* __r
   acc = warp_sum(acc);
   if (lane == 0) rowsum[n] = acc;
 }
+// rowSums(Y[, keep]) (R/preprocess.R:138): the cell filter of preprocess_for_clonealign counts only the genes that survived
+// the gene filters; keep[g] != 0 marks them
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_stats_rows_masked(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, const unsigned char* __restrict__ keep,
+                    double* __restrict__ rowsum) {
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  double acc = 0.0;
+  for (int g = lane; g < G; g += 32)
+    if (keep[g]) acc += (double)(float)Y[n * ldY + g];
+  acc = warp_sum(acc);
+  if (lane == 0) rowsum[n] = acc;
+}
 // part[rs][g] = (sum_n y_ng, sum_n y_ng / rowsum_n) over the row slice
 template <typename T>
 __global__ void __launch_bounds__(128)

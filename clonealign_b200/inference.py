@@ -155,8 +155,11 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
         raise ValueError("nrow(L_dat) == G is not TRUE")                              # :139 (R fails in the subset at :124)
     zero_gene_means = np.asarray(Y_dat.sum(axis=0)).ravel() <= gene_filter_threshold  # :117
     _message(verbose, f"Removing {int(zero_gene_means.sum())} genes with low counts")  # :120
-    Y = Y_dat[:, ~zero_gene_means]
-    L = L_dat[~zero_gene_means, :]
+    if zero_gene_means.any():
+        Y = Y_dat[:, ~zero_gene_means]
+        L = L_dat[~zero_gene_means, :]
+    else:                       # nothing to drop: no copy of the N x G matrix (16 GB of doubles at 100k x 20k)
+        Y, L = Y_dat, L_dat
     if sparse and psi_init is None and not (device_pca and K == 1):
         Y, sparse = np.asarray(Y.todense()), False     # the host PCA needs the dense matrix (use device_pca=True to avoid it)
     if gene_names is not None:

@@ -169,6 +169,17 @@ class DeviceData:
         _lib.check(self._lib.ca_core_data_stats(self._d, _ptr(rs), _ptr(cs), _ptr(mg), err, len(err)), err)
         return {"rowsum": rs, "colsum": cs, "mu_guess": mg}
 
+    def masked_rowsums(self, gene_keep):
+        """rowSums(Y[, keep]) from the resident matrix (ca_core_data_masked_rowsums): the cell filter of
+        preprocess_for_clonealign (R/preprocess.R:138-139)."""
+        k = np.ascontiguousarray(np.asarray(gene_keep).astype(bool), dtype=np.uint8)
+        if k.shape != (self.G,):
+            raise ValueError("gene_keep must have one entry per gene")
+        rs = np.zeros(self.N)
+        err = C.create_string_buffer(1024)
+        _lib.check(self._lib.ca_core_data_masked_rowsums(self._d, _ptr(k), _ptr(rs), err, len(err)), err)
+        return rs
+
     def close(self):
         if self._d is not None:
             err = C.create_string_buffer(1024)

@@ -157,6 +157,10 @@ CA_API int ca_core_data_destroy(ca_data* d, char* err, size_t errlen);
  * filter, :222 mu_guess = colMeans(Y / rowMeans(Y))), computed from the resident matrix in fp64 instead of by passes over
  * the N x G host matrix.  Any output may be NULL.  rowsum: N, colsum: G, mu_guess: G. */
 CA_API int ca_core_data_stats(ca_data* d, double* rowsum, double* colsum, double* mu_guess, char* err, size_t errlen);
+/* rowSums(Y[, keep]) over the resident matrix: the cell filter of preprocess_for_clonealign (R/preprocess.R:138-139) counts
+ * only the genes that survived its gene filters (:114-135, which need colSums(Y) from ca_core_data_stats and the copy-number
+ * matrix only).  gene_keep: G bytes (non-zero = retained); rowsum: N doubles.  SURVEY.md 8f-2. */
+CA_API int ca_core_data_masked_rowsums(ca_data* d, const uint8_t* gene_keep, double* rowsum, char* err, size_t errlen);
 CA_API int ca_core_create_shared(ca_handle** out, const ca_config* cfg, ca_data* data, const double* psi_init,
                           const double* loc_init, const double* X, char* err, size_t errlen);
 

@@ -311,3 +311,27 @@ def test_elbo_many_equals_repeated_elbo(example_sce, path, variants):
     b, b_next = run(False)
     assert a.tobytes() == b.tobytes() and a_next == b_next
     assert len(set(a.tolist())) == 20
+
+
+def test_device_preprocess_matches_host_mirror(example_sce):
+    """preprocess_for_clonealign (R/preprocess.R:93-147) with its two passes over the matrix as device reductions
+    (ca_core_data_stats, ca_core_data_masked_rowsums): same retained genes / cells and matrices as the host
+    mirror, on the bundled data (vignette: 6 cells x 67 genes) and on a sparse synthetic matrix."""
+    import scipy.sparse as sp
+    from clonealign_b200.preprocess import preprocess_for_clonealign
+    from clonealign_b200.synthetic import make_synthetic
+    Y, L = example_sce
+    cases = [(Y, L, {}), (Y.astype(np.uint8), L, dict(min_counts_per_cell=60, nmads=3))]
+    syn = make_synthetic(400, 300, 5, seed=4)
+    Ls = syn["L"].copy()
+    Ls[::7] = 2.0                      # genes with the same copy number in every clone
+    Ls[5] = 9.0                        # above max_copy_number
+    cases.append((sp.csr_matrix(syn["Y"]), Ls, dict(min_counts_per_gene=150, min_counts_per_cell=2500)))
+    for Yc, Lc, kw in cases:
+        host = preprocess_for_clonealign(Yc.toarray() if sp.issparse(Yc) else Yc, Lc, **kw)
+        dev = preprocess_for_clonealign(Yc, Lc, device=0, **kw)
+        assert np.array_equal(dev["retained_genes"], host["retained_genes"]) and np.array_equal(dev["retained_cells"], host["retained_cells"])
+        got = dev["gene_expression_data"]
+        got = got.toarray() if sp.issparse(got) else np.asarray(got)
+        assert np.array_equal(got, host["gene_expression_data"]) and np.array_equal(dev["copy_number_data"], host["copy_number_data"])
+        assert 0 < len(host["retained_genes"]) < Yc.shape[1] and 0 < len(host["retained_cells"]) < Yc.shape[0]
