@@ -1219,6 +1219,8 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   h->YV = z((size_t)N * std::max(KP, 1)); h->YtU = z((size_t)G * std::max(KP, 1)); h->Fout = z((size_t)N * C);
   h->dM_sum = z((size_t)G * J);
   h->n_gene_blocks = (int)ceil_div64((int64_t)G * S, h->lean ? kProThreads : 256);   // one thread per (sample, gene) pair
+  // fused prologue: two 512-thread blocks fit an SM; 32 of the slots go to its scalar / range blocks, the gene blocks stride
+  if (h->lean) h->n_gene_blocks = std::min(h->n_gene_blocks, std::max(1, 2 * h->num_sms - 2 - kProPsiBlocks));
   h->n_epi_blocks = ceil_div64(N, kEpiWarps);
   h->n_cell_parts = h->epi2 ? (int64_t)h->num_sms : h->n_epi_blocks;
   h->gene_part = h->alloc<double>(h->n_gene_blocks);

@@ -363,8 +363,9 @@ __global__ void __launch_bounds__(kProThreads) k_prologue(PrologueArgs a) {
     const int gb = blockIdx.x - 2 - kProPsiBlocks;
     SampleMuArgs m = a.mu;
     m.draw = draw;
-    if (a.mu_vec4) sample_mu_body<true>(m, gb, dscr, m.gene_part);
-    else sample_mu_body<false>(m, gb, dscr, m.gene_part);
+    const int ngb = (int)gridDim.x - 2 - kProPsiBlocks;
+    if (a.mu_vec4) sample_mu_body<true>(m, gb, ngb, dscr, m.gene_part);
+    else sample_mu_body<false>(m, gb, ngb, dscr, m.gene_part);
   } else {
     const int pb = blockIdx.x - 2;
     const int64_t per = (a.N + kProPsiBlocks - 1) / kProPsiBlocks;

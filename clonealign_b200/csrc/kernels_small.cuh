@@ -214,12 +214,14 @@ struct SampleMuArgs {
 // 36 us, all of it replicated on every rank of a cell-sharded fit (ncu of round 2, profiles/r02_notes.md).
 // VEC4 (C % 4 == 0, K = 1 layouts only): the C values a gene contributes to one sample are contiguous in Mx
 // ([g][s*C + c]), so they leave as 16-byte stores instead of C scattered 4-byte stores per (gene, sample).
+// `nblocks` blocks stride over the pairs (a whole number of resident blocks per SM: no half-empty second wave).
 template <bool VEC4>
-__device__ __forceinline__ void sample_mu_body(const SampleMuArgs& a, int block, double* scratch, double* part_out) {
-  const int64_t idx = (int64_t)block * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void sample_mu_body(const SampleMuArgs& a, int block, int nblocks, double* scratch, double* part_out) {
+  double etot = 0.0;
+  for (int64_t idx = (int64_t)block * blockDim.x + threadIdx.x; idx < (int64_t)a.S * a.G; idx += (int64_t)nblocks * blockDim.x) {
   const int s = (int)(idx / a.G), g = (int)(idx - (int64_t)s * a.G);
   double e = 0.0;
-  if (s < a.S) {
+  {
     float loc = a.loc[g], lsd = a.lsd[g], sd = expf(lsd);
     double cs = (double)a.colsum[g];
     float vk[kMaxKP];
@@ -274,13 +276,15 @@ __device__ __forceinline__ void sample_mu_body(const SampleMuArgs& a, int block,
         e += -0.5 * exp(cr) * w * w + 0.5 * cr - 0.5 * kLog2Pi;
       }
   }
-  double t = block_sum(e, scratch);
+  etot += e;
+  }
+  double t = block_sum(etot, scratch);
   if (threadIdx.x == 0) part_out[block] = t;
 }
 
 __global__ void __launch_bounds__(256) k_sample_mu(SampleMuArgs a) {
   __shared__ double scratch[32];
-  sample_mu_body<false>(a, blockIdx.x, scratch, a.gene_part);
+  sample_mu_body<false>(a, blockIdx.x, gridDim.x, scratch, a.gene_part);
 }
 
 // min / max of the single latent loading column (K == 1, P == 0): gives the exact row maximum of
