@@ -457,6 +457,53 @@ def run_ours(args, cfg):
     D.shutdown()
 
 
+# ------------------------------------------------------------------------------------------------------
+# BASELINE config 5: run_clonealign restarts spread over the GPUs of one process (R/clonealign.R:50-56)
+# ------------------------------------------------------------------------------------------------------
+def run_restarts(args, cfg):
+    """`--restarts R`: R independent fits of the workload through run_clonealign(devices=..., share_inputs=True), as
+    replicas (one Y pass per fit and iteration) and with the batched Y pass (one pass over the shared matrix serves up to 4
+    fits): restarts/s and fit-iterations/s, wall clock from HOST buffers (upload per device included)."""
+    import torch
+    from clonealign_b200 import run_clonealign
+    from clonealign_b200.synthetic import make_synthetic_cuda
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    ndev = max(1, min(args.gpus, torch.cuda.device_count()))
+    N, G, C, S = cfg["N"], cfg["G"], cfg["C"], cfg["S"]
+    syn = make_synthetic_cuda(N, G, C, seed=DATA_SEED, device="cuda:0")
+    Y = syn["Y"].to(torch.uint8).cpu().numpy()                      # the caller holds integer counts compactly
+    L = np.minimum(syn["L"], 6.0)
+    del syn
+    torch.cuda.empty_cache()
+    psi = np.random.default_rng(EPS_SEED).standard_normal((N, 1))
+    R, iters = int(args.restarts), int(args.steps)
+    per = max(1, R // 4)
+    kw = dict(initial_shrinks=tuple(range(R // per)), n_repeats=per, print_elbos=False, seed=EPS_SEED, devices=list(range(ndev)),
+              max_iter=iters, rel_tol=0.0, verbose=False, psi_init=psi, mc_samples=S, device_stats=True, batch_final_elbo=True,
+              device_correlations=True)
+    out = {}
+    import warnings
+    for label, extra in (("replicas", dict(share_inputs=True)), ("batched_y_pass", dict(share_inputs=True, batch_y_pass=True))):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t0 = time.perf_counter()
+            fit = run_clonealign(Y, L, **kw, **extra)
+            dt = time.perf_counter() - t0
+        n_fit = len(fit["multirun_info"]["elbos"])
+        out[label] = dict(seconds=dt, restarts=n_fit, restarts_per_s=n_fit / dt, fit_iterations_per_s=n_fit * iters / dt,
+                          best_final_elbo=float(np.nanmax(fit["multirun_info"]["elbos"])),
+                          y_bytes_streamed_per_fit_iteration=(2.0 if label == "replicas" else 2.0 / min(4, -(-n_fit // ndev))) * N * G)
+    line = {"metric": "run_clonealign restarts/s", "value": out["batched_y_pass"]["restarts_per_s"], "unit": "restarts/s",
+            "n_gpus": ndev, "steps": iters, "warmup": 0, "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None,
+            "data": "synthetic", "dtype": "f32",
+            "config": {"workload": cfg["name"], "restarts": R, "iterations_per_fit": iters, "final_elbo_evaluations": 20,
+                       "note": "wall clock through run_clonealign from host uint8 counts: upload once per device, shared device "
+                               "inputs, device statistics / correlations; each iteration = train step + fresh-draw ELBO evaluation"},
+            "modes": out}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -471,6 +518,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the late-training timing and the informational extras")
+    ap.add_argument("--restarts", type=int, default=0,
+                    help="BASELINE config 5 mode: this many run_clonealign restarts spread over --gpus devices of ONE process")
     ap.add_argument("--watchdog", type=int, default=900,
                     help="abort the process after this many seconds (a hung collective must not hold the GPU box)")
     args = ap.parse_args()
@@ -482,6 +531,8 @@ def main():
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
         run_reference(args, cfg)
+    elif args.restarts > 0:
+        run_restarts(args, cfg)
     else:
         run_ours(args, cfg)
 

@@ -153,7 +153,12 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
     L_dat = np.asarray(L_dat, dtype=np.float64)
     if Y_dat.ndim != 2 or L_dat.ndim != 2 or L_dat.shape[0] != Y_dat.shape[1]:
         raise ValueError("nrow(L_dat) == G is not TRUE")                              # :139 (R fails in the subset at :124)
-    zero_gene_means = np.asarray(Y_dat.sum(axis=0)).ravel() <= gene_filter_threshold  # :117
+    if cache is not None and cache.get("gene_filter") is not None:                    # restarts share identical inputs
+        zero_gene_means = cache["gene_filter"]
+    else:
+        zero_gene_means = np.asarray(Y_dat.sum(axis=0)).ravel() <= gene_filter_threshold  # :117
+        if cache is not None:
+            cache["gene_filter"] = zero_gene_means
     _message(verbose, f"Removing {int(zero_gene_means.sum())} genes with low counts")  # :120
     if zero_gene_means.any():
         Y = Y_dat[:, ~zero_gene_means]

@@ -972,3 +972,34 @@ def test_device_preprocess_matches_host_mirror(example_sce):
         got = got.toarray() if sp.issparse(got) else np.asarray(got)
         assert np.array_equal(got, host["gene_expression_data"]) and np.array_equal(dev["copy_number_data"], host["copy_number_data"])
         assert 0 < len(host["retained_genes"]) < Yc.shape[1] and 0 < len(host["retained_cells"]) < Yc.shape[0]
+
+
+def test_bench_restart_mode_on_the_emulation(monkeypatch, capsys):
+    """bench.py --restarts (BASELINE config 5: run_clonealign restarts over the devices of one process, replicas and batched
+    Y pass) on the emulated library with a miniature workload: the line is produced and both modes fit the same restarts."""
+    import argparse
+    import importlib.util
+    import json
+    import os
+    import torch
+    from clonealign_b200 import synthetic
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+
+    def fake_cuda(N, G, C, seed=2345234, device="cpu", rows=None, literal=False):
+        syn = synthetic.make_synthetic(N, G, C, seed=seed)
+        return dict(Y=torch.from_numpy(syn["Y"].astype(np.float32)), L=syn["L"], z=syn["z"], s=syn["s"])
+    monkeypatch.setattr(synthetic, "make_synthetic_cuda", fake_cuda)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    args = argparse.Namespace(gpus=1, steps=3, restarts=4)
+    bench.run_restarts(args, dict(N=150, G=900, C=3, S=1, name="emulated mini restarts"))
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["unit"] == "restarts/s" and line["value"] > 0 and line["config"]["restarts"] == 4
+    m = line["modes"]
+    assert m["replicas"]["restarts"] == m["batched_y_pass"]["restarts"] == 4
+    assert abs(m["replicas"]["best_final_elbo"] / m["batched_y_pass"]["best_final_elbo"] - 1.0) < 1e-5
+    assert m["batched_y_pass"]["y_bytes_streamed_per_fit_iteration"] * 4 == m["replicas"]["y_bytes_streamed_per_fit_iteration"]
