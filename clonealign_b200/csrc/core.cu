@@ -685,11 +685,12 @@ void run_train(ca_handle* h, bool apply) {
     a.Vm = h->Vm; a.colpart = h->colpart; a.mu = h->mu; a.sig = h->sig; a.eps = h->eps; a.lsd = h->lsd; a.L = h->L;
     a.ar = h->ar; a.YtU = h->YtU; a.dM_out = h->inspect ? h->dM_sum : nullptr;
     a.gsum_part = h->gsum_part; a.n_parts = h->n_cell_parts;
+    // two 512-thread blocks per SM (64 registers, <= 78 KB of coefficients each): 32 warps keep the fp64 recurrences fed
     switch ((h->SC + 31) / 32) {
-      case 1: { auto k = k_gene_fused<1>; CA_LAUNCH(k, h->num_sms + 1, kGeneWarps * 32, h->gene_smem, h->stream)(a); break; }
-      case 2: { auto k = k_gene_fused<2>; CA_LAUNCH(k, h->num_sms + 1, kGeneWarps * 32, h->gene_smem, h->stream)(a); break; }
-      case 3: { auto k = k_gene_fused<3>; CA_LAUNCH(k, h->num_sms + 1, kGeneWarps * 32, h->gene_smem, h->stream)(a); break; }
-      default: { auto k = k_gene_fused<4>; CA_LAUNCH(k, h->num_sms + 1, kGeneWarps * 32, h->gene_smem, h->stream)(a); break; }
+      case 1: { auto k = k_gene_fused<1>; CA_LAUNCH(k, 2 * h->num_sms + 1, kGeneWarps * 32, h->gene_smem, h->stream)(a); break; }
+      case 2: { auto k = k_gene_fused<2>; CA_LAUNCH(k, 2 * h->num_sms + 1, kGeneWarps * 32, h->gene_smem, h->stream)(a); break; }
+      case 3: { auto k = k_gene_fused<3>; CA_LAUNCH(k, 2 * h->num_sms + 1, kGeneWarps * 32, h->gene_smem, h->stream)(a); break; }
+      default: { auto k = k_gene_fused<4>; CA_LAUNCH(k, 2 * h->num_sms + 1, kGeneWarps * 32, h->gene_smem, h->stream)(a); break; }
     }
     KCHECK();
   } else {

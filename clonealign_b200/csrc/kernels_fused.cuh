@@ -435,7 +435,7 @@ inline int gene_fused_smem_panels(int J, size_t budget = 96 * 1024) {
 // (dM and dM') of all its columns interleaved; the column partials of the NEXT round of 16 genes are fetched while this
 // round computes.
 template <int NJ>
-__global__ void __launch_bounds__(kGeneWarps * 32) k_gene_fused(GeneFusedArgs a) {
+__global__ void __launch_bounds__(kGeneWarps * 32, 2) k_gene_fused(GeneFusedArgs a) {
   CA_DYNAMIC_SMEM(double, csm);
   __shared__ double scratch[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
