@@ -153,12 +153,14 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
     L_dat = np.asarray(L_dat, dtype=np.float64)
     if Y_dat.ndim != 2 or L_dat.ndim != 2 or L_dat.shape[0] != Y_dat.shape[1]:
         raise ValueError("nrow(L_dat) == G is not TRUE")                              # :139 (R fails in the subset at :124)
-    if cache is not None and cache.get("gene_filter") is not None:                    # restarts share identical inputs
-        zero_gene_means = cache["gene_filter"]
+    if cache is not None:                                                             # restarts share identical inputs:
+        import contextlib                                                             # one pass over the matrix, not one per fit
+        with cache.get("lock") or contextlib.nullcontext():
+            zero_gene_means = cache.get("gene_filter")
+            if zero_gene_means is None:
+                zero_gene_means = cache["gene_filter"] = np.asarray(Y_dat.sum(axis=0)).ravel() <= gene_filter_threshold
     else:
         zero_gene_means = np.asarray(Y_dat.sum(axis=0)).ravel() <= gene_filter_threshold  # :117
-        if cache is not None:
-            cache["gene_filter"] = zero_gene_means
     _message(verbose, f"Removing {int(zero_gene_means.sum())} genes with low counts")  # :120
     if zero_gene_means.any():
         Y = Y_dat[:, ~zero_gene_means]
@@ -220,7 +222,12 @@ def inference_steps(Y_dat, L_dat, max_iter=100, rel_tol=1e-5, learning_rate=0.1,
         """Restart-independent device inputs: upload + preprocess once per device (built on first use)."""
         import contextlib
         from .session import DeviceData
-        with cache.get("lock") or contextlib.nullcontext():       # concurrent restarts on one device: build once
+        # concurrent restarts on one device build the inputs once; different devices upload concurrently (a lock per device,
+        # the shared lock only guards the dictionary)
+        import threading
+        with cache.get("lock") or contextlib.nullcontext():
+            dev_lock = cache.setdefault(("lock", device), threading.Lock())
+        with dev_lock:
             dd = cache.get(("data", device))
             if dd is None:
                 dd = cache[("data", device)] = DeviceData(Y, L, device=device, clone_allele=clone_allele if use_allele else None,
