@@ -711,7 +711,7 @@ void run_train(ca_handle* h, bool apply) {
     a.world = h->cfg.world; a.rank = h->cfg.rank; a.cnt = h->p2p_cnt; a.cnt_pad = h->p2p_cnt_pad; a.step_ctr = &h->dstate->p2p_step;
     a.src = h->ar; a.dst = h->ar; a.ticket = h->p2p_ticket; a.error = h->p2p_err;
     for (int r = 0; r < kP2PMaxWorld; ++r) { a.slots[r] = h->p2p_slots[r]; a.flags[r] = h->p2p_flags[r]; }
-    CA_LAUNCH(k_p2p_allreduce, std::min(h->num_sms, 16), kP2PThreads, 0, h->stream)(a);
+    CA_LAUNCH(k_p2p_allreduce, std::min(h->num_sms, 64), kP2PThreads, 0, h->stream)(a);
     KCHECK();
   } else if (h->cfg.world > 1) {
     LaunchScope ls(h, "allreduce");
@@ -1280,11 +1280,11 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     h->iplan = h->alloc<InterpPlan>(1);
     h->mm_psi = z(2);
     // node-sum kernel: columns per thread, column groups per warp, slices of the reduction index (>= 4 staged chunks per
-    // work item, at most two items per SM and panel), dynamic shared memory
+    // work item, at most three items per SM and panel: with one active panel every resident block still has work), dynamic shared memory
     h->n2_tj = n2_pick_tj(J);
     h->n2_ncgp = n2_ncg_pow2(J, h->n2_tj);
     auto n2_split = [&](int64_t R) {
-      return (int)std::max<int64_t>(1, std::min<int64_t>(2 * (int64_t)h->num_sms, ceil_div64(ceil_div64(R, kN2Chunk), 4)));
+      return (int)std::max<int64_t>(1, std::min<int64_t>(kN2BlocksPerSM * (int64_t)h->num_sms, ceil_div64(ceil_div64(R, kN2Chunk), 4)));
     };
     h->n2_split_f = n2_split(G);
     h->n2_split_b = n2_split(N);

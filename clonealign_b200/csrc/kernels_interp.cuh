@@ -22,8 +22,8 @@
 namespace ca {
 
 constexpr int kIP = 16;            // Chebyshev nodes per panel (multiple of 8); with kIAmax = 4: ~6e-9 relative
-constexpr int kIMaxPanF = 64;      // forward panels (both signs of psi together)
-constexpr int kIMaxPanB = 64;      // backward panels over [w_min, w_max]
+constexpr int kIMaxPanF = 32;      // forward panels (both signs of psi together): exponent range 16 x 8 = 128 per side
+constexpr int kIMaxPanB = 32;      // backward panels over [w_min, w_max]
 constexpr double kIAmax = 4.0;     // exponent half-range per panel
 constexpr double kPi = 3.14159265358979323846;
 
@@ -202,7 +202,7 @@ k_interp_nodes2(const InterpPlan* __restrict__ plan, const float* __restrict__ r
         for (int j = 0; j < TJ / 2; ++j) acc[q][j] = make_float2(0.f, 0.f);
       const float* bt = Bs[k & 1] + cg * TJ;
       const float* et = Es[k & 1] + 8 * qg;
-#pragma unroll 2
+#pragma unroll 4
       for (int c = ks; c < rows; c += nks) {
         float2 b[TJ / 2];
         if (TJ == 8 && vec16) {                 // rows of B are 16-byte aligned: two 16-byte loads

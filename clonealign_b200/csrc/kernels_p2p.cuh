@@ -4,7 +4,7 @@
 // Every rank owns a device buffer that its peers map through CUDA IPC (ca_core_p2p_export / ca_core_p2p_connect):
 //     slots[2][world][cnt_pad] floats   slot (parity, r) = rank r's contribution of a step with that parity
 //     flags[2][world]          uint32   flag (parity, r) = last step whose contribution from rank r is complete
-// One launch per step on every rank (<= 16 co-resident blocks):
+// One launch per step on every rank (<= 64 co-resident blocks: nothing else of the step runs next to it):
 //   push   : the rank's partial sums are written straight into slot (parity, rank) of EVERY rank's buffer
 //            (16-byte stores over NVLink; NVSwitch gives every pair full bandwidth, so the 8 x 240 KB leave in ~2 us);
 //   signal : when the last block has finished pushing (ticket), one system-scope fence and `flag[parity][rank] = step`
@@ -86,11 +86,26 @@ __global__ void __launch_bounds__(kP2PThreads) k_p2p_allreduce(P2PArgs a) {
   __syncthreads();
   __threadfence_system();
   // ---- reduce in rank order ----
+  // 16 bytes per thread and rank, ALL ranks' loads in flight before the first add (the first version summed rank after rank
+  // through one dependent load chain per output: ~8 load latencies per element and 7 elements per thread at 8 ranks)
   const float* base = a.slots[a.rank] + (int64_t)par * a.world * a.cnt_pad;
-  for (int64_t i = tid; i < a.cnt; i += nth) {
-    float s = 0.f;
-    for (int r = 0; r < a.world; ++r) s += __ldcv(base + (int64_t)r * a.cnt_pad + i);
-    a.dst[i] = s;
+  for (int64_t i = tid; i < nvec; i += nth) {
+    float4 v[kP2PMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kP2PMaxWorld; ++r)
+      if (r < a.world) v[r] = __ldcv(reinterpret_cast<const float4*>(base + (int64_t)r * a.cnt_pad) + i);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < kP2PMaxWorld; ++r)
+      if (r < a.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+    const int64_t e = 4 * i;
+    if (e + 3 < a.cnt) {
+      reinterpret_cast<float4*>(a.dst)[i] = s;        // dst (the all-reduce buffer) is 16-byte aligned
+    } else {
+      if (e < a.cnt) a.dst[e] = s.x;
+      if (e + 1 < a.cnt) a.dst[e + 1] = s.y;
+      if (e + 2 < a.cnt) a.dst[e + 2] = s.z;
+    }
   }
 }
 

@@ -237,7 +237,7 @@ inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_R
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-template <typename T> inline T __ldcv(const T* p) { return *(const volatile T*)p; }
+template <typename T> inline T __ldcv(const T* p) { T v; std::memcpy(&v, (const void*)p, sizeof(T)); return v; }
 // a spin-wait on memory written by another block / rank: let the sibling fibers of this block run (on hardware the
 // other lanes of the warp make progress independently) and give the OS thread away
 inline void ca_emul_spin_pause() {
@@ -399,7 +399,8 @@ inline int host_workers() {
   static int n = [] {
     const char* e = getenv("CA_EMUL_THREADS");
     int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
-    return v < 16 ? 16 : (v > 32 ? 32 : v);   // >= 16: the blocks of a spin-waiting kernel (k_p2p_allreduce, <= 16) must be co-resident
+    (void)v;
+    return 64;   // the blocks of a spin-waiting kernel (k_p2p_allreduce, <= 64) must be co-resident, whatever the host has
   }();
   return n;
 }
