@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <string.h>
+#include "platform.cuh"
 
 #define CA_WARP 32
 #define CA_FULL 0xffffffffu
@@ -97,28 +98,6 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
     for (int i = 0; i < nw; ++i) r += scratch[i];
   return r;
 }
-
-// ---------------------------------------------------------------------------------------------
-// asynchronous global -> shared copies (cp.async / LDGSTS): bytes in flight without registers.
-// The CPU emulation of tests/cuda_emul/ copies synchronously (commit / wait are no-ops there).
-// ---------------------------------------------------------------------------------------------
-#ifdef CA_EMULATE
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) { memcpy(smem_dst, gmem_src, 16); }
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) { memcpy(smem_dst, gmem_src, 8); }
-__device__ __forceinline__ void cp_async_commit() {}
-template <int N> __device__ __forceinline__ void cp_async_wait() {}
-#else
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-#endif
 
 __device__ __forceinline__ float softplusf(float x) {
   return x > 0.f ? x + log1pf(expf(-x)) : log1pf(expf(x));

@@ -456,23 +456,7 @@ template <typename T> constexpr size_t ypass4_smem_bytes() {
   return (size_t)kY4Stages * kY4StageRows * 256 * sizeof(typename Y3<T>::Raw) + 8 * kY4Stages + 16;
 }
 
-#ifdef CA_EMULATE   // functional stand-ins: the issuing thread copies synchronously (block barriers order it, see below)
-__device__ __forceinline__ void y4_bar_init(uint64_t*, int) {}
-__device__ __forceinline__ void y4_arm(uint64_t*, uint32_t) {}
-__device__ __forceinline__ void y4_bulk(void* dst, const void* src, uint32_t bytes, uint64_t*) { memcpy(dst, src, bytes); }
-__device__ __forceinline__ void y4_wait(uint64_t*, uint32_t) {}
-__device__ __forceinline__ void y4_fence_init() {}
-__device__ __forceinline__ void y4_fence_proxy() {}
-#else
-__device__ __forceinline__ void y4_bar_init(uint64_t* bar, int count) { ptx::mbar_init(ptx::smem_u32(bar), (uint32_t)count); }
-__device__ __forceinline__ void y4_arm(uint64_t* bar, uint32_t bytes) { ptx::mbar_expect_tx(ptx::smem_u32(bar), bytes); }
-__device__ __forceinline__ void y4_bulk(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  ptx::bulk_load_1d(ptx::smem_u32(dst), src, bytes, ptx::smem_u32(bar));
-}
-__device__ __forceinline__ void y4_wait(uint64_t* bar, uint32_t parity) { ptx::mbar_wait(ptx::smem_u32(bar), parity); }
-__device__ __forceinline__ void y4_fence_init() { ptx::fence_barrier_init(); }
-__device__ __forceinline__ void y4_fence_proxy() { ptx::fence_proxy_async_smem(); }
-#endif
+// (bar_init / bar_arm / bar_wait / bulk_copy / fence_*: platform.cuh)
 
 // MINB = CTAs per SM the register allocation is sized for: 4 -> 64 registers, 3 -> 80
 template <typename T, int MINB>
@@ -492,9 +476,9 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
   // the ring starts zeroed: threads past the last stored column never receive data and must not read NaN patterns
   for (int i = tid; i < kY4Stages * kSR * 256; i += 256) ring[i] = L::zero();
   if (tid == 0)
-    for (int st = 0; st < kY4Stages; ++st) y4_bar_init(bars + st, 1);
-  y4_fence_init();
-  y4_fence_proxy();                                              // the zero fill (generic stores) before any bulk copy
+    for (int st = 0; st < kY4Stages; ++st) bar_init(bars + st, 1);
+  fence_bar_init();
+  fence_proxy_async();                                              // the zero fill (generic stores) before any bulk copy
   __syncthreads();
   uint32_t ph = 0;                                               // bit st: parity the next wait on stage st has to see
   const int64_t ntiles = (int64_t)nCB * nRB;
@@ -526,15 +510,13 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
         const int r0 = g * 8 + hh * kSR;
         const int nv = nrows - r0 < kSR ? nrows - r0 : kSR;
         if (nv <= 0) break;
-        y4_arm(bars + S0 + hh, (uint32_t)nv * tbytes);
+        bar_arm(bars + S0 + hh, (uint32_t)nv * tbytes);
         for (int i = 0; i < nv; ++i)
-          y4_bulk(ring + ((size_t)(S0 + hh) * kSR + i) * 256, ybase + (int64_t)(r0 + i) * ldY, tbytes, bars + S0 + hh);
+          bulk_copy(ring + ((size_t)(S0 + hh) * kSR + i) * 256, ybase + (int64_t)(r0 + i) * ldY, tbytes, bars + S0 + hh);
       }
     };
     if (tid == 0) { issue(std::integral_constant<int, 0>{}, 0); issue(std::integral_constant<int, 2>{}, 1); }
-#ifdef CA_EMULATE
-    __syncthreads();                                             // the synchronous stand-in copies must precede the readers
-#endif
+    CA_SYNC_AFTER_SYNCHRONOUS_COPY();                            // nothing on the device (see platform.cuh)
     auto group = [&](auto s0c, int g) {
       constexpr int S0 = decltype(s0c)::value;
       const int64_t r0 = rbeg + (int64_t)g * 8;
@@ -549,7 +531,7 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
       for (int hh = 0; hh < 2; ++hh) {
         const int nv = nrows - (g * 8 + hh * kSR);               // valid rows of this stage
         if (nv > 0) {
-          y4_wait(bars + S0 + hh, (ph >> (S0 + hh)) & 1u);
+          bar_wait(bars + S0 + hh, (ph >> (S0 + hh)) & 1u);
           ph ^= 1u << (S0 + hh);
           Raw* src = ring + (size_t)(S0 + hh) * kSR * 256 + tid;
           if (nv < kSR) {
@@ -557,7 +539,7 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
             // zeroes its own pieces (it reads them back itself below); the proxy fence orders these generic stores
             // before the bulk copy that refills the stage later.
             for (int i = nv; i < kSR; ++i) src[(size_t)i * 256] = L::zero();
-            y4_fence_proxy();
+            fence_proxy_async();
           }
 #pragma unroll
           for (int i = 0; i < kSR; ++i) {

@@ -17,8 +17,8 @@ OUT_DIR = os.path.join(HERE, "_build")
 
 
 def _sources():
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
-    files += [os.path.join(HERE, f) for f in sorted(os.listdir(HERE)) if f.endswith(".h")]
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".inl"))]
+    files += [os.path.join(HERE, f) for f in sorted(os.listdir(HERE)) if f.endswith((".h", ".inl"))]
     files.append(os.path.join(ROOT, "include", "clonealign_b200.h"))
     return files
 

@@ -504,7 +504,16 @@ enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorPeerAccessAlreadyEna
 typedef struct ca_emul_stream* cudaStream_t;
 struct ca_emul_event { std::chrono::steady_clock::time_point t; };
 typedef ca_emul_event* cudaEvent_t;
-typedef void* cudaGraphExec_t;   // graphs are never built under emulation (core.cu: graph_ok)
+// CUDA graphs are never built under emulation (platform_emul.h: kGraphsAvailable == false); the calls only have to compile
+typedef void* cudaGraphExec_t;
+typedef void* cudaGraph_t;
+enum cudaStreamCaptureMode { cudaStreamCaptureModeThreadLocal = 1 };
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorInvalidValue; }
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t*) { return cudaErrorInvalidValue; }
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, unsigned long long) { return cudaErrorInvalidValue; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorInvalidValue; }
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
