@@ -187,3 +187,42 @@ def test_seed_controls_all_host_randomness():
     c = (FakeSession.last.psi_init.copy(), FakeSession.last.kw["seed"])
     assert np.array_equal(a[0], b[0]) and a[1] == b[1]
     assert not np.array_equal(a[0], c[0]) and a[1] != c[1]
+
+
+def test_diverged_fit_stops_and_na_restarts_are_not_selected(monkeypatch):
+    """The reference's `if(mean(abs(elbo_diffs)) < rel_tol)` (R/inference-tflow.R:414) errors once the ELBO is NA, and
+    `which.max` (R/clonealign.R:65) skips NA: a diverged fit must neither run on to max_iter nor be returned as the best."""
+    rng = np.random.default_rng(0)
+    Y = rng.poisson(2.0, size=(30, 12)).astype(float) + 1.0
+    L = rng.integers(1, 4, size=(12, 3)).astype(float)
+    FakeSession.script = [-100.0, -90.0, float("nan"), -80.0]
+    with pytest.raises(ValueError, match="ELBO is NA after iteration 2"):
+        inference.inference_tflow(Y, L, max_iter=50, verbose=False, seed=1)
+    assert FakeSession.last.calls[-1] == "close" and FakeSession.last.calls.count("step") == 2
+    # best-of-restarts: NA final ELBOs are skipped, all-NA is an error
+    fits = iter([{"convergence_info": {"final_elbo": float("nan")}, "correlations": np.zeros(3), "clone": ["A"]},
+                 {"convergence_info": {"final_elbo": -5.0}, "correlations": np.zeros(3), "clone": ["B"]},
+                 {"convergence_info": {"final_elbo": -7.0}, "correlations": np.zeros(3), "clone": ["C"]}])
+    monkeypatch.setattr(api, "clonealign", lambda *a, **k: next(fits))
+    best = api.run_clonealign(Y, L, initial_shrinks=(0,), n_repeats=3, print_elbos=False, seed=2)
+    assert best["clone"] == ["B"] and np.isnan(best["multirun_info"]["elbos"][0])
+    allnan = iter([{"convergence_info": {"final_elbo": float("nan")}, "correlations": np.zeros(3), "clone": ["A"]}] * 2)
+    monkeypatch.setattr(api, "clonealign", lambda *a, **k: next(allnan))
+    with pytest.raises(ValueError, match="every restart ended with an NA final ELBO"):
+        api.run_clonealign(Y, L, initial_shrinks=(0,), n_repeats=2, print_elbos=False, seed=2)
+
+
+def test_duplicate_gene_names_keep_their_own_columns():
+    """The post-hoc correlations use the POSITIONS of the retained genes (the mask of the gene filter), so repeated gene
+    names cannot alias each other's columns (they did through a name -> first-index lookup)."""
+    rng = np.random.default_rng(3)
+    Y = rng.poisson(3.0, size=(40, 6)).astype(float) + 1.0
+    Y[:, 2] = 0.0                                   # filtered out
+    L = rng.integers(1, 5, size=(6, 3)).astype(float)
+    names = ["g", "g", "x", "g", "h", "h"]
+    fit = api.clonealign(Y, L, max_iter=3, verbose=False, seed=1, gene_names=names, clone_names=["A", "B", "C"])
+    assert fit["retained_genes"] == ["g", "g", "g", "h", "h"] and len(fit["correlations"]) == 5
+    keep = [0, 1, 3, 4, 5]
+    want = api.compute_correlations(Y[:, keep], L[keep], fit["clone"], ["A", "B", "C"])
+    np.testing.assert_array_equal(np.isnan(fit["correlations"]), np.isnan(want))
+    np.testing.assert_allclose(np.nan_to_num(fit["correlations"]), np.nan_to_num(want))
