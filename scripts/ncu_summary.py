@@ -13,6 +13,9 @@ METRICS = [
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU %"),
+    ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64 %"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma %"),
+    ("smsp__inst_executed.sum", "warp instr"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps %"),
     ("launch__registers_per_thread", "regs"),
