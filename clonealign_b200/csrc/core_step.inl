@@ -261,8 +261,6 @@ void run_forward(ca_handle* h, int mode) {
     a.U = h->U; a.Bm = h->Bm; a.vA = h->vA; a.s = h->s; a.log_alpha = h->log_alpha; a.rowpart = h->rowpart;
     a.t = h->t; a.gT = h->g_t; a.Rx = h->Rx; a.gU = h->g_U; a.YV = h->YV; a.shift = h->shift;
     a.Fout = h->inspect ? h->Fout : nullptr;     // inspection copies (ca_core_grads): not written by the timed path
-    a.apply_t = (mode == EPI_TRAIN && h->lean && h->apply_now) ? 1 : 0;
-    a.m_t = h->m_t; a.v_t = h->v_t; a.state = h->dstate;
     a.Zx = h->inspect ? h->Zx : nullptr;
     a.elbo_part = h->elbo_part; a.gsum_part = h->gsum_part;
     a.defer_yv = h->defer ? 1 : 0;
@@ -302,7 +300,6 @@ void run_forward(ca_handle* h, int mode) {
 
 void run_train(ca_handle* h, bool apply) {
   h->launches_last_step = 0;
-  h->apply_now = apply;
   run_forward(h, EPI_TRAIN);
   {
     LaunchScope ls(h, "lse_bwd", h->interp ? (h->lean ? 2 : 3) : 1);
@@ -384,8 +381,7 @@ void run_train(ca_handle* h, bool apply) {
       aa.ga = ga; aa.chi_cur = h->chi_cur; aa.sa = sa; aa.N = h->N; aa.C = h->C;
       aa.t = h->t; aa.m_t = h->m_t; aa.v_t = h->v_t; aa.U = h->U; aa.m_U = h->m_U; aa.v_U = h->v_U; aa.gT = h->g_t; aa.gU = h->g_U;
       aa.n_gene_blocks = (h->G + 255) / 256;
-      aa.t_done = apply ? 1 : 0;                 // k_cell_fused updated the gamma logits of this step itself
-      aa.n_cell_blocks = (apply || h->defer) ? ceil_div64((aa.t_done ? 0 : ceil_div64(h->N * h->C, 4)) + h->N, 256) : 0;
+      aa.n_cell_blocks = (apply || h->defer) ? ceil_div64(ceil_div64(h->N * h->C, 4) + h->N, 256) : 0;
       aa.defer_yv = h->defer ? 1 : 0; aa.nCB = h->nCB; aa.rowpart = h->rowpart; aa.YV = h->YV;
       aa.state = h->dstate;
       CA_LAUNCH(k_adam_all, (unsigned)(aa.n_gene_blocks + aa.n_cell_blocks + 1), 256, 0, h->stream)(aa);

@@ -38,12 +38,6 @@ struct FusedArgs {
   float *gT, *Rx, *gU, *YV, *Fout, *shift;
   float* Zx;                             // optional inspection copy of (Z | Z') [N][J], nullptr in the timed path
   double *elbo_part, *gsum_part;         // one partial per block
-  // TRAIN mode with apply_t != 0: the TF1-Adam update of the gamma logits happens HERE, by the lane that has just computed
-  // the gradient (d t depends on nothing outside this cell), instead of writing g_t for k_adam_all to read back:
-  // 1.2 M of the 1.3 M elements that kernel used to update at config 3.  lr_t of the step comes from StepState (k_prologue).
-  int apply_t;
-  float *m_t, *v_t;
-  const StepState* state;
 };
 
 inline size_t fused_smem_bytes(int SC, int C, int J, int smem_panels, int warps = kFusedWarps) {
@@ -162,7 +156,6 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused(FusedArgs a)
   const float la = cok ? a.log_alpha[lane] : 0.f;
   const float wmin = a.mm[0], wmax = a.mm[1];
   const double invS = 1.0 / (double)a.S;
-  const float lr_t = (MODE == EPI_TRAIN && a.apply_t) ? a.state->lr_t : 0.f;
 
   double elbo_w = 0.0, gacc = 0.0;
   const int64_t chunk = (a.N + gridDim.x - 1) / gridDim.x;
@@ -247,17 +240,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused(FusedArgs a)
     elbo_w += sumGH + x * yv - 0.5 * x * x - 0.5 * kLog2Pi;
     if (MODE == EPI_TRAIN) {
       gacc += g;
-      if (cok) {
-        const float gt = (g == 0.0) ? 0.f : (float)(g * (H - sumGH));
-        if (a.apply_t) {
-          const int64_t o = n * C + lane;
-          float tnew = tv, mm_ = a.m_t[o], vv_ = a.v_t[o];
-          adam_update_tf1(tnew, mm_, vv_, gt, lr_t);
-          a.t[o] = tnew; a.m_t[o] = mm_; a.v_t[o] = vv_;
-        } else {
-          a.gT[n * C + lane] = gt;
-        }
-      }
+      if (cok) a.gT[n * C + lane] = (g == 0.0) ? 0.f : (float)(g * (H - sumGH));
       // R_scn = gamma_nc s_n / (S Z_scn) and d psi_n = (YW)_n - sum_sc R Z' - psi_n
       double zp[NJ];
       if (in_smem) clenshaw_cols<NJ, true>(cpan, jz, SC, a.J, tt, zp);
@@ -593,7 +576,6 @@ struct AdamAllArgs {
   const float* rowpart;
   float* YV;
   StepState* state;          // lr_t of this step (k_prologue); the scalar block advances adam_t
-  int t_done;                // the gamma logits were already updated by k_cell_fused: the cell blocks only hold psi
 };
 __global__ void __launch_bounds__(256) k_adam_all(AdamAllArgs a) {
   const int64_t b = blockIdx.x;
@@ -628,7 +610,7 @@ __global__ void __launch_bounds__(256) k_adam_all(AdamAllArgs a) {
     // cell blocks: thread i < nt4 updates 4 consecutive gamma logits (16-byte loads / stores: a quarter of the threads,
     // 4x the bytes in flight per thread -- the kernel is latency-bound), the threads behind them one psi each
     const int64_t i = (b - a.n_gene_blocks) * blockDim.x + threadIdx.x;
-    const int64_t nt = a.N * a.C, nt4 = a.t_done ? 0 : (nt + 3) / 4;
+    const int64_t nt = a.N * a.C, nt4 = (nt + 3) / 4;
     if (i < nt4) {
       if (a.ga.h.apply) {
         const int64_t e0 = 4 * i;
