@@ -327,6 +327,18 @@ def run_ours(args, cfg):
         for name, t in sess.profile_step():
             prof[name] = prof.get(name, 0.0) + t / nprof
 
+    # the step as it runs (Y pass co-scheduled on its own stream): start offset and duration of every launch, last of 3 steps
+    timeline = None
+    os.environ["CLONEALIGN_B200_PROF_OVERLAP"] = "1"
+    try:
+        for _ in range(3):
+            pl = sess.profile_step()
+        t0 = {n[3:]: t for n, t in pl if n.startswith("t0:")}
+        if t0:
+            timeline = {n: [round(t0.get(n, 0.0), 4), round(t, 4)] for n, t in pl if not n.startswith("t0:")}
+    finally:
+        del os.environ["CLONEALIGN_B200_PROF_OVERLAP"]
+
     # ---- the same measurement later in the fit: the node work of the interp path follows the panel structure -----------
     late = None
     if not args.quick:
@@ -366,6 +378,7 @@ def run_ours(args, cfg):
                         frac=ach / peak, traffic=traffic, peak_source=pk["which"], ms_per_launch=k["t"], traffic_source=tsrc,
                         algorithmic_per_launch=k["alg"] * (1e9 if k["bound"] == "hbm" else 1e12),
                         all_kernels_ms={n: round(t, 4) for n, t in prof.items()},
+                        timeline_ms=timeline,    # {launch: [start offset, duration]} of one step with the Y pass co-scheduled
                         per_kernel={n: dict(bound=v["bound"], achieved=v["alg"] / (v["t"] / 1e3),
                                             frac=v["alg"] / (v["t"] / 1e3) / (pk["hbm"] if v["bound"] == "hbm" else pk["bf16"]))
                                     for n, v in kern.items()})

@@ -25,6 +25,7 @@
 #include "../../include/clonealign_b200.h"
 #include "common.cuh"
 #include "kernels_expgemm.cuh"
+#include "kernels_cell.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_interp.cuh"
 #include "kernels_p2p.cuh"
@@ -434,10 +435,12 @@ int ca_core_profile_step(ca_handle* h, char* names, size_t names_len, double* ms
     CUDA_OK(cudaSetDevice(h->dev));
     for (auto& p : h->prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     h->prof.clear();
+    h->prof_overlap = getenv("CLONEALIGN_B200_PROF_OVERLAP") != nullptr;
     h->prof_on = true;
     run_train(h, true);
     h->prof_on = false;
     CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream2));
     std::string all;
     int k = 0;
     for (auto& p : h->prof) {
@@ -447,6 +450,16 @@ int ca_core_profile_step(ca_handle* h, char* names, size_t names_len, double* ms
       ms[k++] = (double)f;
       if (!all.empty()) all += ";";
       all += p.name;
+    }
+    if (h->prof_overlap && !h->prof.empty()) {   // timeline: start of every launch relative to the first event of the step
+      cudaEvent_t t0 = h->prof[0].a;
+      for (auto& p : h->prof) {
+        float f = 0.f;
+        if (cudaEventElapsedTime(&f, t0, p.a) != cudaSuccess) { cudaGetLastError(); f = 0.f; }   // (the forked Y pass may start first)
+        if (k >= cap) break;
+        ms[k++] = (double)f;
+        all += ";t0:" + p.name;
+      }
     }
     *n_k = k;
     strncpy(names, all.c_str(), names_len - 1);

@@ -194,10 +194,11 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     if (!(h->cfg.variants & (CA_VAR_YPASS2 | CA_VAR_YPASS3 | CA_VAR_YPASS4))) h->cfg.variants |= CA_VAR_YPASS4;
     h->cfg.variants |= CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_DEFER;
     if (h->cfg.variants & CA_VAR_YPASS4) h->cfg.variants |= CA_VAR_COSCHED;
+    if (c.S <= kCell2MaxS && !getenv("CLONEALIGN_B200_NO_CELL2")) h->cfg.variants |= CA_VAR_CELL2;
   }
   h->interp = (c.path == CA_PATH_INTERP);
   h->variants = c.variants;
-  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_P2P | CA_VAR_OVERLAP | CA_VAR_YPASS3 | CA_VAR_DEFER | CA_VAR_YPASS4 | CA_VAR_COSCHED))
+  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_P2P | CA_VAR_OVERLAP | CA_VAR_YPASS3 | CA_VAR_DEFER | CA_VAR_YPASS4 | CA_VAR_COSCHED | CA_VAR_CELL2))
     fail("unknown kernel variant bits 0x%x", c.variants);
   if ((c.variants & CA_VAR_P2P) && c.world > kP2PMaxWorld) fail("variant p2p supports at most %d ranks", kP2PMaxWorld);
   h->p2p = (c.variants & CA_VAR_P2P) && c.world > 1;
@@ -213,6 +214,8 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if ((c.variants & CA_VAR_COSCHED) && !((c.variants & CA_VAR_DEFER) && (c.variants & CA_VAR_YPASS4)))
     fail("variant cosched needs variants defer and ypass4");
   h->cosched = (c.variants & CA_VAR_COSCHED) != 0;
+  if ((c.variants & CA_VAR_CELL2) && !(c.variants & CA_VAR_DEFER)) fail("variant cell2 needs variants epi2, lean and defer");
+  h->cell2 = (c.variants & CA_VAR_CELL2) != 0 && c.S <= kCell2MaxS;   // more samples than a lane keeps in registers: k_cell_fused
   if (c.variants & CA_VAR_EPI2) {
     if (!h->interp) fail("variant epi2 belongs to the interp path (path = interp)");
     if (c.C > kFusedMaxC || c.S * c.C > 32 * kFusedMaxNJ) fail("variant epi2 needs C <= %d and S*C <= %d", kFusedMaxC, 32 * kFusedMaxNJ);
@@ -470,6 +473,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     const size_t nodes_f = (size_t)h->n2_split_f * kIMaxPanF * kIP, nodes_b = (size_t)h->n2_split_b * kIMaxPanB * kIP;
     h->ivals = h->alloc<double>(std::max(nodes_f, nodes_b) * J, false);
     h->icoef = h->alloc<double>((size_t)std::max(kIMaxPanF, kIMaxPanB) * kIP * J);
+    if (h->cell2) h->icoef2 = h->alloc<double>((size_t)std::max(kIMaxPanF, kIMaxPanB) * kIP * J);
     const size_t per_panel = (size_t)kIP * J * sizeof(double);
     h->ieval_panels = (int)std::min<size_t>(16, (200 * 1024) / per_panel);
     h->ieval_smem = (size_t)h->ieval_panels * per_panel;
@@ -531,6 +535,25 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
         default: fused_set_smem<4>(h->fused_smem); break;
       }
     }
+  }
+  if (h->cell2) {
+    h->cell2_wc = cell2_pick_wc(C);
+    h->cell2_sb = cell2_pick_sb(S);
+    const size_t budget = h->cosched ? 92 * 1024 : 200 * 1024;
+    h->cell2_panels = cell2_smem_panels(h->cell2_wc, h->cell2_sb, C, budget, h->fused_warps);
+    if (h->cell2_panels < 1) fail("variant cell2: the coefficient table of one panel (%zu bytes) does not fit into shared memory", cell2_panel_bytes(h->cell2_wc, h->cell2_sb));
+    if (const char* e = getenv("CLONEALIGN_B200_FUSED_PANELS")) h->cell2_panels = std::max(1, std::min(h->cell2_panels, atoi(e)));   // test hook: several rounds
+    h->cell2_smem = cell2_smem_bytes(h->cell2_wc, h->cell2_sb, C, h->cell2_panels, h->fused_warps);
+    h->gene2_panels = gene2_smem_panels(h->cell2_wc, h->cell2_sb, 96 * 1024);   // two 512-thread blocks per SM
+    if (const char* e = getenv("CLONEALIGN_B200_FUSED_PANELS")) h->gene2_panels = std::max(1, std::min(h->gene2_panels, atoi(e)));
+    h->gene2_smem = gene2_smem_bytes(h->cell2_wc, h->cell2_sb, h->gene2_panels);
+    cell2_dispatch(h->cell2_wc, h->cell2_sb, [&](auto wc, auto sb) {
+      constexpr int WC = decltype(wc)::value, SB = decltype(sb)::value;
+      CUDA_OK(cudaFuncSetAttribute(k_gene_fused2<WC, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gene2_smem));
+      CUDA_OK(cudaFuncSetAttribute(k_cell_fused2<EPI_TRAIN, WC, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cell2_smem));
+      CUDA_OK(cudaFuncSetAttribute(k_cell_fused2<EPI_EVAL, WC, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cell2_smem));
+      CUDA_OK(cudaFuncSetAttribute(k_cell_fused2<EPI_INIT, WC, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cell2_smem));
+    });
   }
   size_t smem = epi_smem_bytes(h->SCp, C, J, h->tc);
   if (smem > 48 * 1024) {

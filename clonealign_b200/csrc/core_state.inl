@@ -42,6 +42,12 @@ struct ca_handle {
   size_t gene_smem = 0;
   int fused_nj = 0, fused_panels = 0, fused_warps = kFusedWarps;
   size_t fused_smem = 0;
+  bool cell2 = false;              // with epi2 + lean + defer, S <= 8: k_cell_fused2 (kernels_cell.cuh) is the per-cell kernel
+  int cell2_wc = 16, cell2_sb = 8, cell2_panels = 0;
+  size_t cell2_smem = 0;
+  double* icoef2 = nullptr;        // monomial coefficient pairs [panel][kIP / 2][J][2] (k_interp_coeffs2)
+  int gene2_panels = 0;            // k_gene_fused2: panels staged at a time, dynamic shared memory
+  size_t gene2_smem = 0;
   int64_t n_cell_parts = 0;        // per-block ELBO / sum-gamma partials written by the per-cell kernel in use
   InterpPlan* iplan = nullptr;
   int n2_tj = 8, n2_ncgp = 32, n2_split_f = 1, n2_split_b = 1, n2_blocks_per_sm = kN2BlocksPerSM;   // k_interp_nodes2 launch geometry
@@ -99,6 +105,7 @@ struct ca_handle {
   int* p2p_err = nullptr;
   unsigned p2p_step = 0;
   bool prof_on = false;
+  bool prof_overlap = false;       // CLONEALIGN_B200_PROF_OVERLAP=1: profile the step as it runs (Y pass on its own stream), with start offsets
   std::vector<Prof> prof;
   int launches_last_step = 0;
 

@@ -6,20 +6,21 @@ struct LaunchScope {
   ca_handle* h;
   bool on;
   size_t idx = 0;
-  LaunchScope(ca_handle* h_, const char* name, int n_kernels = 1) : h(h_), on(h_->prof_on) {
+  cudaStream_t st;
+  LaunchScope(ca_handle* h_, const char* name, int n_kernels = 1, cudaStream_t st_ = nullptr) : h(h_), on(h_->prof_on), st(st_ ? st_ : h_->stream) {
     h->launches_last_step += n_kernels;
     if (on) {
       Prof p;
       p.name = name;
       CUDA_OK(cudaEventCreate(&p.a));
       CUDA_OK(cudaEventCreate(&p.b));
-      CUDA_OK(cudaEventRecord(p.a, h->stream));
+      CUDA_OK(cudaEventRecord(p.a, st));
       h->prof.push_back(p);
       idx = h->prof.size() - 1;
     }
   }
   ~LaunchScope() {
-    if (on) cudaEventRecord(h->prof[idx].b, h->stream);
+    if (on) cudaEventRecord(h->prof[idx].b, st);
   }
 };
 #define KCHECK() CUDA_OK(cudaGetLastError())
@@ -52,7 +53,7 @@ void run_ypass(ca_handle* h, cudaStream_t st) {
   dispatch_y(h, [&](auto* Yp) {
     using T = typename std::remove_const<typename std::remove_pointer<decltype(Yp)>::type>::type;
     if (h->KP == 1) {
-      LaunchScope ls(h, "ypass");
+      LaunchScope ls(h, "ypass", 1, st);
       dim3 grid(h->nCB, h->nRB);
       if (h->variants & CA_VAR_YPASS4) {
         const int64_t tiles = (int64_t)h->nCB * h->nRB;
@@ -128,7 +129,7 @@ void launch_interp_nodes(ca_handle* h, const float* rv, const float* shift, cons
     CA_LAUNCH(k, grid, kN2Threads, h->n2_smem, h->stream)(h->iplan, rv, shift, B, R, h->J, h->n2_ncgp, nsplit, max_pan, h->ivals);
   }
   CA_LAUNCH(k_interp_coeffs2, dim3((h->J + kC2Cols - 1) / kC2Cols, kC2PanelsY), kIP * kC2Cols * kC2Lanes, 0, h->stream)(
-      h->iplan, h->ivals, nsplit, max_pan, h->J, FWD ? 1 : 0, h->icoef);
+      h->iplan, h->ivals, nsplit, max_pan, h->J, FWD ? 1 : 0, h->icoef, h->cell2 ? h->icoef2 : nullptr);
 }
 
 // the partial sums of the Y pass are needed from here on: wait for the pass forked onto stream2, or run it now
@@ -164,13 +165,44 @@ void fused_set_smem(size_t smem) {
   CUDA_OK(cudaFuncSetAttribute(k_cell_fused<EPI_INIT, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 }
 
+// (lanes per cell, samples in registers) -> compile-time constants of k_cell_fused2
+template <typename F>
+void cell2_dispatch(int wc, int sb, F&& f) {
+  auto with_sb = [&](auto wcc) {
+    switch (sb) {
+      case 1: f(wcc, std::integral_constant<int, 1>{}); break;
+      case 2: f(wcc, std::integral_constant<int, 2>{}); break;
+      case 4: f(wcc, std::integral_constant<int, 4>{}); break;
+      case 8: f(wcc, std::integral_constant<int, 8>{}); break;
+      default: fail("per-cell kernel: unsupported sample count");
+    }
+  };
+  switch (wc) {
+    case 4: with_sb(std::integral_constant<int, 4>{}); break;
+    case 8: with_sb(std::integral_constant<int, 8>{}); break;
+    case 16: with_sb(std::integral_constant<int, 16>{}); break;
+    case 32: with_sb(std::integral_constant<int, 32>{}); break;
+    default: fail("per-cell kernel: unsupported clone count");
+  }
+}
+void launch_cell2(ca_handle* h, int mode, const Cell2Args& a) {
+  const unsigned grid = (unsigned)h->n_cell_parts, block = (unsigned)h->fused_warps * 32;
+  cell2_dispatch(h->cell2_wc, h->cell2_sb, [&](auto wc, auto sb) {
+    constexpr int WC = decltype(wc)::value, SB = decltype(sb)::value;
+    if (mode == EPI_TRAIN) { auto k = k_cell_fused2<EPI_TRAIN, WC, SB>; CA_LAUNCH(k, grid, block, h->cell2_smem, h->stream)(a); }
+    else if (mode == EPI_EVAL) { auto k = k_cell_fused2<EPI_EVAL, WC, SB>; CA_LAUNCH(k, grid, block, h->cell2_smem, h->stream)(a); }
+    else { auto k = k_cell_fused2<EPI_INIT, WC, SB>; CA_LAUNCH(k, grid, block, h->cell2_smem, h->stream)(a); }
+  });
+}
+
 void run_forward(ca_handle* h, int mode) {
   const float* eps_in;
   stage_eps(h, &eps_in);
   // The Y stream (HBM-bound, touches only Y, psi, W) is independent of the forward contraction (tensor / MUFU
   // bound): fork it onto a second stream so both run on the SMs at once; joined before the per-cell epilogue.
   bool joined_later = false;
-  const bool want_fork = mode != EPI_INIT && (h->overlap || h->cosched) && !h->prof_on && h->ydirty && h->KP > 0;
+  // (per-kernel profiling serialises the step: no fork -- unless the co-scheduled timeline itself is asked for, ca_core_profile_step)
+  const bool want_fork = mode != EPI_INIT && (h->overlap || h->cosched) && (!h->prof_on || h->prof_overlap) && h->ydirty && h->KP > 0;
   auto fork_ypass = [&]() {
     CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
     CUDA_OK(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
@@ -267,6 +299,15 @@ void run_forward(ca_handle* h, int mode) {
     // DEFER + OVERLAP: the pass may start once everything before the per-cell kernel is done (event recorded here), but
     // it is handed to the device AFTER the per-cell kernel, whose 148 persistent CTAs should be placed first
     if (want_fork && h->defer && !h->cosched) CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
+    if (h->cell2) {
+      Cell2Args b;
+      b.N = a.N; b.C = a.C; b.S = a.S; b.SC = a.SC; b.J = a.J; b.smem_panels = h->cell2_panels;
+      b.plan = a.plan; b.coef2 = reinterpret_cast<const double2*>(h->icoef2); b.mm = a.mm;
+      b.U = a.U; b.Bm = a.Bm; b.vA = a.vA; b.s = a.s; b.log_alpha = a.log_alpha;
+      b.t = a.t; b.gT = a.gT; b.Rx = a.Rx; b.gU = a.gU; b.Fout = a.Fout; b.shift = a.shift; b.Zx = a.Zx;
+      b.elbo_part = a.elbo_part; b.gsum_part = a.gsum_part;
+      launch_cell2(h, mode, b);
+    } else
     launch_fused(h, mode, a);
     KCHECK();
     if (want_fork && h->defer && !h->cosched) {
@@ -317,6 +358,31 @@ void run_train(ca_handle* h, bool apply) {
     }
     KCHECK();
   }
+  if (h->cell2) {
+    // CELL2 set: the gene kernel does not read the Y-pass partials -- it runs before the join, next to the Y pass; the
+    // column partials are added to the w-gradient slots by a short launch behind the join
+    {
+      LaunchScope ls(h, "gene_grads", 1);
+      Gene2Args a;
+      a.G = h->G; a.C = h->C; a.S = h->S; a.SC = h->SC; a.J = h->J; a.smem_panels = h->gene2_panels;
+      a.plan = h->iplan; a.coef2 = reinterpret_cast<const double2*>(h->icoef2);
+      a.Vm = h->Vm; a.mu = h->mu; a.sig = h->sig; a.eps = h->eps; a.lsd = h->lsd; a.L = h->L;
+      a.ar = h->ar; a.dM_out = h->inspect ? h->dM_sum : nullptr;
+      a.gsum_part = h->gsum_part; a.n_parts = h->n_cell_parts;
+      cell2_dispatch(h->cell2_wc, h->cell2_sb, [&](auto wc, auto sb) {
+        auto k = k_gene_fused2<decltype(wc)::value, decltype(sb)::value>;
+        CA_LAUNCH(k, 2 * h->num_sms + 1, kGene2Warps * 32, h->gene2_smem, h->stream)(a);
+      });
+      KCHECK();
+    }
+    join_ypass(h, EPI_TRAIN);                // colpart and rowpart (d psi in k_adam_all) are needed from here on
+    {
+      LaunchScope ls(h, "colpart_add", 1);
+      CA_LAUNCH(k_colpart_add, (h->G + kColAddGenes - 1) / kColAddGenes, kColAddGenes * kColAddSlices, 0, h->stream)(
+          h->G, h->nRB, h->colpart, h->ar + 2 * (int64_t)h->G, h->YtU);
+      KCHECK();
+    }
+  } else {
   if (h->defer) join_ypass(h, EPI_TRAIN);   // colpart (gene gradients) and rowpart (d psi in k_adam_all) are needed from here on
   if (h->lean) {
     LaunchScope ls(h, "gene_grads", 1);
@@ -345,6 +411,7 @@ void run_train(ca_handle* h, bool apply) {
     CA_LAUNCH(k_reduce_gsum, 1, 1024, 0, h->stream)(h->gsum_part, h->n_cell_parts, h->C, h->ar + (int64_t)h->G * (2 + h->KP));
     KCHECK();
   }
+  }   // !cell2
   if (h->cfg.world > 1 && h->p2p) {
     if (!h->p2p_ready) fail("variant p2p: ca_core_p2p_connect has not been called");
     LaunchScope ls(h, "allreduce");

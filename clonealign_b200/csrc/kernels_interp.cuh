@@ -55,6 +55,23 @@ __device__ __forceinline__ void bwd_panel(const InterpPlan& pl, int pb, double& 
 }
 __device__ __forceinline__ double cheb_node(int p) { return cos(kPi * (p + 0.5) / kIP); }
 
+// Chebyshev -> monomial basis of the panel variable t: T_k(t) = sum_m kT2M.v[k][m] t^m (integers up to 2^14 * 3.3, exact in
+// fp64; T_{k+1} = 2 t T_k - T_{k-1}).  The per-cell and per-gene kernels evaluate the interpolants by Horner's rule (one
+// DFMA per coefficient instead of Clenshaw's DADD + DFMA).  Conditioning: the panels keep the exponent half-range <= kIAmax,
+// the interpolated sums of exponentials have monomial coefficients bounded by sum_k A^k / k! = e^A times their maximum,
+// against values >= e^-2A of it: evaluation error <= e^(3A) 1.1e-16 ~ 2e-11 relative at the worst point of a worst-case
+// panel, below the 6e-9 of the interpolation itself (tests/test_interp_model.py).
+struct ChebToMono { double v[kIP][kIP]; };
+constexpr ChebToMono make_cheb_to_mono() {
+  ChebToMono t{};
+  t.v[0][0] = 1.0;
+  t.v[1][1] = 1.0;
+  for (int k = 2; k < kIP; ++k)
+    for (int m = 0; m <= k; ++m) t.v[k][m] = (m > 0 ? 2.0 * t.v[k - 1][m - 1] : 0.0) - t.v[k - 2][m];
+  return t;
+}
+static __device__ const ChebToMono kT2M = make_cheb_to_mono();   // global memory: indexed per thread (staged to shared memory by its users)
+
 // panel structure from the current ranges of psi and w
 __device__ __forceinline__ InterpPlan interp_make_plan(double wmin, double wmax, double pmin, double pmax) {
   InterpPlan pl;
@@ -267,8 +284,10 @@ k_interp_nodes2(const InterpPlan* __restrict__ plan, const float* __restrict__ r
 constexpr int kC2Cols = 4, kC2Lanes = 8, kC2PanelsY = 8;
 __global__ void __launch_bounds__(kIP * kC2Cols * kC2Lanes)
 k_interp_coeffs2(const InterpPlan* __restrict__ plan, const double* __restrict__ vals, int nsplit, int max_pan, int J,
-                 int fwd, double* __restrict__ coeff) {
+                 int fwd, double* __restrict__ coeff, double* __restrict__ coef2 /*monomial pairs [panel][kIP/2][J][2] or nullptr*/) {
   __shared__ double part[kC2Lanes][kIP][kC2Cols];
+  __shared__ double cheb[kIP][kC2Cols];
+  __shared__ double t2m[kIP][kIP];
   __shared__ double ct[kIP][kIP];
   const InterpPlan pl = *plan;
   const int npan = fwd ? (pl.nf_neg + pl.nf_pos) : pl.nb;
@@ -278,6 +297,7 @@ k_interp_coeffs2(const InterpPlan* __restrict__ plan, const double* __restrict__
   if (threadIdx.x < kIP * kIP) {
     const int k = threadIdx.x / kIP, q = threadIdx.x % kIP;
     ct[k][q] = cos(kPi * k * (q + 0.5) / kIP);
+    t2m[k][q] = kT2M.v[k][q];
   }
   for (int panel = blockIdx.y; panel < npan; panel += gridDim.y) {     // grid.y = kC2PanelsY: blocks stride over the active panels
   double acc = 0.0;
@@ -311,8 +331,118 @@ k_interp_coeffs2(const InterpPlan* __restrict__ plan, const double* __restrict__
     c *= 2.0 / kIP;
     if (k == 0) c *= 0.5;
     if (j < J) coeff[((int64_t)panel * kIP + k) * J + j] = c;
+    cheb[k][c4] = c;
   }
   __syncthreads();   // part is rewritten for the next panel
+  if (coef2 && z == 0 && j < J) {   // monomial coefficient a_m, m = p: smallest Chebyshev terms first
+    const int mo = p;
+    double am = 0.0;
+#pragma unroll
+    for (int k = kIP - 1; k >= 0; --k) am += t2m[k][mo] * cheb[k][c4];   // entries with k < m are zero
+    coef2[(((int64_t)panel * (kIP / 2) + (mo >> 1)) * J + j) * 2 + (mo & 1)] = am;
+  }
+  }
+}
+
+// k_interp_coeffs3: the same result as k_interp_coeffs2 with every block busy.  ncu of round 2 (config 3, backward pass):
+// 22 us for 10.9 MB of slice partials -- with one or two active panels only 48 - 96 of the 384 blocks had work, and each of
+// their threads walked 55 slices that lie 786 KB apart.  Here the slices are split over grid.y = kC3Groups blocks per
+// column group as well: a thread has at most 8 loads, all in flight at once; the block combines its slice lanes through
+// shared memory and publishes one partial per (panel, node, column); the block of a column group that arrives LAST (ticket)
+// adds the kC3Groups partials in group order and applies the DCT and the monomial conversion.  Fixed summation order:
+// slices s = 64 i + 8 z + gy -> over i per thread, over z per block, over gy by the last block.
+constexpr int kC3Groups = 8;
+__global__ void __launch_bounds__(kIP * kC2Cols * kC2Lanes)
+k_interp_coeffs3(const InterpPlan* __restrict__ plan, const double* __restrict__ vals, int nsplit, int max_pan, int J, int fwd,
+                 double* __restrict__ partial2 /*[kC3Groups][max_pan][kIP][J]*/, unsigned* __restrict__ tickets /*[grid.x], zero*/,
+                 double* __restrict__ coeff, double* __restrict__ coef2) {
+  __shared__ double part[kC2Lanes][kIP][kC2Cols];
+  __shared__ double cheb[kIP][kC2Cols];
+  __shared__ double t2m[kIP][kIP];
+  __shared__ double ct[kIP][kIP];
+  __shared__ int is_last;
+  const InterpPlan pl = *plan;
+  const int npan = fwd ? (pl.nf_neg + pl.nf_pos) : pl.nb;
+  const int c4 = threadIdx.x % kC2Cols, p = (threadIdx.x / kC2Cols) % kIP, z = threadIdx.x / (kC2Cols * kIP);
+  const int j = blockIdx.x * kC2Cols + c4;
+  const int gy = blockIdx.y;
+  const int64_t nodes_total = (int64_t)max_pan * kIP;
+  if (threadIdx.x < kIP * kIP) {
+    const int k = threadIdx.x / kIP, q = threadIdx.x % kIP;
+    ct[k][q] = cos(kPi * k * (q + 0.5) / kIP);
+    t2m[k][q] = kT2M.v[k][q];
+  }
+  constexpr int kStep = kC3Groups * kC2Lanes;                       // slices between two loads of a thread
+  for (int panel = 0; panel < npan; ++panel) {
+    double acc = 0.0;
+    if (j < J) {
+      const double* base = vals + ((int64_t)panel * kIP + p) * J + j;
+      const int64_t stride = nodes_total * J;                       // doubles between consecutive slices
+      int s = z * kC3Groups + gy;
+      for (; s + 7 * kStep < nsplit; s += 8 * kStep) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = base[(int64_t)(s + u * kStep) * stride];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+      }
+      {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (s + u * kStep < nsplit) ? base[(int64_t)(s + u * kStep) * stride] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+      }
+    }
+    part[z][p][c4] = acc;
+    __syncthreads();
+    if (z == 0 && j < J) {
+      double f = part[0][p][c4];
+#pragma unroll
+      for (int zz = 1; zz < kC2Lanes; ++zz) f += part[zz][p][c4];
+      partial2[(((int64_t)gy * max_pan + panel) * kIP + p) * J + j] = f;
+    }
+    __syncthreads();   // part is rewritten for the next panel
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(tickets + blockIdx.x, 1u) == gridDim.y - 1) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;                   // ready for the next launch (stream order)
+  for (int panel = 0; panel < npan; ++panel) {
+    if (z == 0) {
+      double f = 0.0;
+      if (j < J) {
+        double v[kC3Groups];
+#pragma unroll
+        for (int g = 0; g < kC3Groups; ++g) v[g] = __ldcv(partial2 + (((int64_t)g * max_pan + panel) * kIP + p) * J + j);
+#pragma unroll
+        for (int g = 0; g < kC3Groups; ++g) f += v[g];
+      }
+      part[0][p][c4] = f;
+    }
+    __syncthreads();
+    if (z == 0) {
+      const int k = p;
+      double c = 0.0;
+#pragma unroll
+      for (int q = 0; q < kIP; ++q) c += part[0][q][c4] * ct[k][q];
+      c *= 2.0 / kIP;
+      if (k == 0) c *= 0.5;
+      if (j < J) coeff[((int64_t)panel * kIP + k) * J + j] = c;
+      cheb[k][c4] = c;
+    }
+    __syncthreads();
+    if (coef2 && z == 0 && j < J) {   // monomial coefficient a_m, m = p: smallest Chebyshev terms first
+      const int mo = p;
+      double am = 0.0;
+#pragma unroll
+      for (int k = kIP - 1; k >= 0; --k) am += t2m[k][mo] * cheb[k][c4];   // entries with k < m are zero
+      coef2[(((int64_t)panel * (kIP / 2) + (mo >> 1)) * J + j) * 2 + (mo & 1)] = am;
+    }
+    __syncthreads();
   }
 }
 

@@ -93,9 +93,11 @@ enum ca_path     { CA_PATH_AUTO = 0, CA_PATH_CUDACORE = 1, CA_PATH_TENSOR = 2, C
  *           (bytes in flight while the thread computes, half the registers), launched as a persistent grid of 2 CTAs per SM
  *   COSCHED: (with DEFER + YPASS4) the Y pass is started FIRST in the step on the second stream and joined before the
  *           gene-gradient kernel; the per-cell kernel runs with 16 warps so that both fit on every SM: the HBM-bound stream
- *           runs next to the issue-bound kernels of the whole step */
+ *           runs next to the issue-bound kernels of the whole step
+ *   CELL2 : (with EPI2 + LEAN + DEFER; takes effect for S <= 8) per-cell kernel with lane = (cell, clone) and Horner evaluation of the
+ *           interpolants in the monomial basis, see kernels_cell.cuh; part of the default set */
 enum ca_variant  { CA_VAR_YPASS2 = 1, CA_VAR_EPI2 = 2, CA_VAR_LEAN = 4, CA_VAR_P2P = 8, CA_VAR_OVERLAP = 16, CA_VAR_YPASS3 = 32, CA_VAR_DEFER = 64,
-                   CA_VAR_YPASS4 = 128, CA_VAR_COSCHED = 256 };
+                   CA_VAR_YPASS4 = 128, CA_VAR_COSCHED = 256, CA_VAR_CELL2 = 512 };
 
 typedef struct ca_config {
   int64_t N;            /* cells held by this handle (this rank's shard)                       */

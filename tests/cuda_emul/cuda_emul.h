@@ -41,6 +41,8 @@ struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(8) float2 { float x, y; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct alignas(8) uint2 { unsigned x, y; };
+struct alignas(16) double2 { double x, y; };
+inline double2 make_double2(double a, double b) { return {a, b}; }
 inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
 inline float2 make_float2(float a, float b) { return {a, b}; }
 inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return {a, b, c, d}; }
@@ -209,6 +211,7 @@ inline unsigned __ballot_sync(unsigned m, int pred) {
   for (int l = 0; l < 32; ++l) r |= (unsigned)(__shfl_sync(m, pred ? 1 : 0, l) != 0) << l;
   return r;
 }
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 
 template <typename T> inline T __ldg(const T* p) { return *p; }
 template <typename T> inline T __ldcs(const T* p) { return *p; }
@@ -224,6 +227,9 @@ inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
 inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+inline int __double2hiint(double d) { long long v; std::memcpy(&v, &d, 8); return (int)(v >> 32); }
+inline int __double2loint(double d) { long long v; std::memcpy(&v, &d, 8); return (int)(v & 0xffffffffll); }
+inline double __hiloint2double(int hi, int lo) { long long v = ((long long)hi << 32) | (unsigned)lo; double d; std::memcpy(&d, &v, 8); return d; }
 inline float __fdividef(float a, float b) { return a / b; }
 inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return {fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
 inline float2 __fadd2_rn(float2 a, float2 b) { return {a.x + b.x, a.y + b.y}; }

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.usefixtures("emulated_library")
 # bench.py's candidate tests: on the synchronous emulation `overlap` only changes which stream handle a launch names)
 PATHS = [("cudacore", ""), ("interp", ""), ("interp", "ypass2,epi2,lean"), ("cudacore", "ypass3"),
          ("interp", "ypass3,epi2,lean"), ("interp", "ypass3,epi2,lean,defer,overlap"), ("auto", ""),
-         ("interp", "ypass4,epi2,lean,defer,cosched"), ("cudacore", "ypass4")]
+         ("interp", "ypass4,epi2,lean,defer,cosched"), ("cudacore", "ypass4"), ("interp", "ypass3,epi2,lean,defer,cell2")]
 
 
 def test_emulated_library_is_not_the_product(emulated_library):
@@ -27,7 +27,7 @@ def test_emulated_library_is_not_the_product(emulated_library):
     assert "cuda_emul" in emulated_library and "cuda_emul" in _lib.LIB_PATH
     with _session(np.ones((4, 3)), np.ones((3, 2)), np.zeros((4, 1)), np.ones(3), path="auto") as sess:
         d = sess.describe()                                     # the default model runs the interpolation kernel set
-        assert d["path"] == "interp" and d["variants"] == 2 | 4 | 64 | 128 | 256
+        assert d["path"] == "interp" and d["variants"] == 2 | 4 | 64 | 128 | 256 | 512
     with _session(np.ones((4, 3)), np.ones((3, 2)), np.zeros((4, 2)), np.ones(3), K=2, path="auto") as sess:
         assert sess.describe()["path"] == "cudacore"            # tcgen05 is unavailable under emulation
     from clonealign_b200._lib import CloneAlignLibraryError
@@ -871,7 +871,8 @@ def test_random_shapes_and_variants():
         d, p, mu_guess, _ = _case(Y, L, K=1, seed=it, scale=float(rng.choice([0.05, 0.3, 1.0])))
         p.psi *= float(rng.choice([0.5, 1.0, 3.0]))
         var = str(rng.choice(["", "ypass2", "epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap", "ypass3", "ypass3,epi2,lean",
-                              "ypass2,epi2,lean,defer", "ypass3,epi2,lean,defer,overlap", "ypass4", "ypass4,epi2,lean,defer,cosched"]))
+                              "ypass2,epi2,lean,defer", "ypass3,epi2,lean,defer,overlap", "ypass4", "ypass4,epi2,lean,defer,cosched",
+                              "ypass4,epi2,lean,defer,cosched,cell2", "ypass2,epi2,lean,defer,cell2"]))
         with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path="interp", seed=1, variants=var) as sess:
             _load_params(sess, p)
             try:
