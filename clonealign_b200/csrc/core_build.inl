@@ -415,7 +415,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
       // row blocks halve the column partials the gene kernel has to gather (and the pipeline refills at tile starts).
       const int64_t slots = 2 * (int64_t)h->num_sms;
       int64_t waves = std::max<int64_t>(1, ceil_div64((int64_t)h->nCB * ceil_div64(N, 512), slots));
-      if (h->variants & CA_VAR_YPASS4) waves = std::min<int64_t>(waves, 2);
+      if (h->variants & CA_VAR_YPASS4) waves = std::min<int64_t>(waves, h->cell2 ? 1 : 2);   // cell2: half the column partials to add behind the join
       const int64_t nrb = std::max<int64_t>(1, waves * slots / h->nCB);
       h->RB = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(16, round_up64(ceil_div64(N, nrb), 16)));
     }
@@ -473,7 +473,11 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     const size_t nodes_f = (size_t)h->n2_split_f * kIMaxPanF * kIP, nodes_b = (size_t)h->n2_split_b * kIMaxPanB * kIP;
     h->ivals = h->alloc<double>(std::max(nodes_f, nodes_b) * J, false);
     h->icoef = h->alloc<double>((size_t)std::max(kIMaxPanF, kIMaxPanB) * kIP * J);
-    if (h->cell2) h->icoef2 = h->alloc<double>((size_t)std::max(kIMaxPanF, kIMaxPanB) * kIP * J);
+    if (h->cell2) {
+      h->icoef2 = h->alloc<double>((size_t)std::max(kIMaxPanF, kIMaxPanB) * kIP * J);
+      h->ipart2 = h->alloc<double>((size_t)kC3Groups * std::max(kIMaxPanF, kIMaxPanB) * kIP * J, false);
+      h->itickets = h->alloc<unsigned>((size_t)(J + kC2Cols - 1) / kC2Cols);
+    }
     const size_t per_panel = (size_t)kIP * J * sizeof(double);
     h->ieval_panels = (int)std::min<size_t>(16, (200 * 1024) / per_panel);
     h->ieval_smem = (size_t)h->ieval_panels * per_panel;

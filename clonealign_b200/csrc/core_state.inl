@@ -46,6 +46,8 @@ struct ca_handle {
   int cell2_wc = 16, cell2_sb = 8, cell2_panels = 0;
   size_t cell2_smem = 0;
   double* icoef2 = nullptr;        // monomial coefficient pairs [panel][kIP / 2][J][2] (k_interp_coeffs2)
+  double* ipart2 = nullptr;        // k_interp_coeffs3: one partial per (slice group, panel, node, column)
+  unsigned* itickets = nullptr;    // ... and one arrival counter per column group
   int gene2_panels = 0;            // k_gene_fused2: panels staged at a time, dynamic shared memory
   size_t gene2_smem = 0;
   int64_t n_cell_parts = 0;        // per-block ELBO / sum-gamma partials written by the per-cell kernel in use

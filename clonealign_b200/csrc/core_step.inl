@@ -128,8 +128,12 @@ void launch_interp_nodes(ca_handle* h, const float* rv, const float* shift, cons
     auto k = k_interp_nodes2<FWD, 6>;
     CA_LAUNCH(k, grid, kN2Threads, h->n2_smem, h->stream)(h->iplan, rv, shift, B, R, h->J, h->n2_ncgp, nsplit, max_pan, h->ivals);
   }
+  if (h->cell2)   // CELL2 set: slices split over grid.y as well, the last block of a column group finishes (k_interp_coeffs3)
+    CA_LAUNCH(k_interp_coeffs3, dim3((h->J + kC2Cols - 1) / kC2Cols, kC3Groups), kIP * kC2Cols * kC2Lanes, 0, h->stream)(
+        h->iplan, h->ivals, nsplit, max_pan, h->J, FWD ? 1 : 0, h->ipart2, h->itickets, h->icoef, h->icoef2);
+  else
   CA_LAUNCH(k_interp_coeffs2, dim3((h->J + kC2Cols - 1) / kC2Cols, kC2PanelsY), kIP * kC2Cols * kC2Lanes, 0, h->stream)(
-      h->iplan, h->ivals, nsplit, max_pan, h->J, FWD ? 1 : 0, h->icoef, h->cell2 ? h->icoef2 : nullptr);
+      h->iplan, h->ivals, nsplit, max_pan, h->J, FWD ? 1 : 0, h->icoef, nullptr);
 }
 
 // the partial sums of the Y pass are needed from here on: wait for the pass forked onto stream2, or run it now
@@ -376,7 +380,7 @@ void run_train(ca_handle* h, bool apply) {
       KCHECK();
     }
     join_ypass(h, EPI_TRAIN);                // colpart and rowpart (d psi in k_adam_all) are needed from here on
-    {
+    if (h->cfg.world > 1) {                  // (an unsharded fit adds the column partials inside k_adam_all)
       LaunchScope ls(h, "colpart_add", 1);
       CA_LAUNCH(k_colpart_add, (h->G + kColAddGenes - 1) / kColAddGenes, kColAddGenes * kColAddSlices, 0, h->stream)(
           h->G, h->nRB, h->colpart, h->ar + 2 * (int64_t)h->G, h->YtU);
@@ -451,6 +455,8 @@ void run_train(ca_handle* h, bool apply) {
       aa.n_cell_blocks = (apply || h->defer) ? ceil_div64(ceil_div64(h->N * h->C, 4) + h->N, 256) : 0;
       aa.defer_yv = h->defer ? 1 : 0; aa.nCB = h->nCB; aa.rowpart = h->rowpart; aa.YV = h->YV;
       aa.state = h->dstate;
+      const bool adam_adds_colpart = h->cell2 && h->cfg.world == 1;
+      aa.colpart = adam_adds_colpart ? h->colpart : nullptr; aa.nRB = h->nRB; aa.YtU = h->YtU;
       CA_LAUNCH(k_adam_all, (unsigned)(aa.n_gene_blocks + aa.n_cell_blocks + 1), 256, 0, h->stream)(aa);
       KCHECK();
     } else {

@@ -576,6 +576,11 @@ struct AdamAllArgs {
   const float* rowpart;
   float* YV;
   StepState* state;          // lr_t of this step (k_prologue); the scalar block advances adam_t
+  // CELL2 set, unsharded fit: the gene kernel ran in front of the Y-pass join, (Y^T psi)_g = sum_rb colpart[rb][g] is added here
+  // (a sharded fit adds it before the all-reduce: k_colpart_add); nullptr otherwise
+  const float* colpart;
+  int nRB;
+  float* YtU;
 };
 __global__ void __launch_bounds__(256) k_adam_all(AdamAllArgs a) {
   const int64_t b = blockIdx.x;
@@ -599,7 +604,21 @@ __global__ void __launch_bounds__(256) k_adam_all(AdamAllArgs a) {
     const float gloc = (float)gl, glsd = (float)gs;
     q.g_loc[g] = gloc;
     q.g_lsd[g] = glsd;
-    const float gw = (float)((double)q.ar[2 * (int64_t)q.G + g] - a.chi_cur[0] * (double)q.Vm[g]);   // K == 1, P == 0
+    double ytu = 0.0;
+    if (a.colpart) {   // fixed order: 8 partials in flight, row blocks ascending
+      const float* cp = a.colpart + g;
+      int rb = 0;
+      for (; rb + 8 <= a.nRB; rb += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = cp[(int64_t)(rb + u) * q.G];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) ytu += (double)v[u];
+      }
+      for (; rb < a.nRB; ++rb) ytu += (double)cp[(int64_t)rb * q.G];
+      a.YtU[g] = (float)ytu;
+    }
+    const float gw = (float)((double)q.ar[2 * (int64_t)q.G + g] + ytu - a.chi_cur[0] * (double)q.Vm[g]);   // K == 1, P == 0
     q.g_V[g] = gw;
     if (q.h.apply) {
       adam_update(q.loc[g], q.m_loc[g], q.v_loc[g], gloc, q.h);

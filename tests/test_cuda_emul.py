@@ -34,7 +34,9 @@ def _run(exe, psi, w, Mx, Rx, smem_panels):
         raw = open(fout, "rb").read()
     hdr = np.frombuffer(raw[:12], dtype=np.int32)
     body = np.frombuffer(raw[12:], dtype=np.float32)
-    return hdr, body[:N * J].reshape(N, J).astype(np.float64), body[N * J:].reshape(G, J).astype(np.float64)
+    Z, dM = body[:N * J].reshape(N, J), body[N * J:(N + G) * J].reshape(G, J)
+    Zh, dMh = body[(N + G) * J:(2 * N + G) * J].reshape(N, J), body[(2 * N + G) * J:].reshape(G, J)
+    return hdr, Z.astype(np.float64), dM.astype(np.float64), Zh.astype(np.float64), dMh.astype(np.float64)
 
 
 @pytest.mark.parametrize("sd_psi,sd_w,smem_panels,sign", [(1.0, 0.4, 16, 0), (2.0, 1.5, 2, 0), (1.0, 0.0, 16, 0),
@@ -50,7 +52,7 @@ def test_interp_kernels_match_direct_contraction(exe, sd_psi, sd_w, smem_panels,
     Mx[:, J // 2:] *= w[:, None]
     Rx = rng.uniform(0.0, 1.0, size=(N, J)).astype(np.float32)
     Rx[:, J // 2:] *= psi[:, None]
-    hdr, Z, dM = _run(exe, psi, w, Mx, Rx, smem_panels)
+    hdr, Z, dM, Zh, dMh = _run(exe, psi, w, Mx, Rx, smem_panels)
     p, ww = psi.astype(np.float64), w.astype(np.float64)
     m = np.maximum(p * ww.max(), p * ww.min())
     E = np.exp(p[:, None] * ww[None, :] - m[:, None])
@@ -61,6 +63,12 @@ def test_interp_kernels_match_direct_contraction(exe, sd_psi, sd_w, smem_panels,
     zscale = np.abs(Z_ref[:, :h]).max(axis=1, keepdims=True) * max(np.abs(ww).max(), 1e-30)
     assert (np.abs(Z - Z_ref)[:, h:] / zscale).max() < 5e-6
     assert (np.abs(dM - dM_ref) / np.abs(dM_ref).max(axis=0, keepdims=True).clip(1e-30)).max() < 5e-6
+    # the monomial tables (Horner: what the per-cell / per-gene kernels of the cell2 set evaluate), the backward one through the
+    # ticketed two-level reduction of k_interp_coeffs3: same interpolants as the Chebyshev tables
+    assert np.abs(Zh[:, :h] / Z_ref[:, :h] - 1.0).max() < 5e-6
+    assert (np.abs(Zh - Z_ref)[:, h:] / zscale).max() < 5e-6
+    assert (np.abs(dMh - dM_ref) / np.abs(dM_ref).max(axis=0, keepdims=True).clip(1e-30)).max() < 5e-6
+    assert np.abs(Zh - Z).max() <= 2e-6 * np.abs(Z).max() and np.abs(dMh - dM).max() <= 2e-6 * np.abs(dM).max()
     nf_neg, nf_pos, nb = hdr
     assert (nf_neg > 0) == bool((psi < 0).any()) and (nf_pos > 0) == bool((psi >= 0).any())
     if sd_psi == 2.0:
