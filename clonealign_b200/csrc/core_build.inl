@@ -452,14 +452,15 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     h->mm_psi = z(2);
     // node-sum kernel: columns per thread, column groups per warp, slices of the reduction index (>= 4 staged chunks per
     // work item, at most three items per SM and panel: with one active panel every resident block still has work), dynamic shared memory
-    h->n2_tj = n2_pick_tj(J);
-    h->n2_ncgp = n2_ncg_pow2(J, h->n2_tj);
+    h->Jn = h->cell2 ? (int)round_up64(h->SC, 2) : J;   // even: 8-byte row starts (cp.async, float2 reads of the node kernel)
+    h->n2_tj = n2_pick_tj(h->Jn);
+    h->n2_ncgp = n2_ncg_pow2(h->Jn, h->n2_tj);
     auto n2_split = [&](int64_t R) {
       return (int)std::max<int64_t>(1, std::min<int64_t>(kN2BlocksPerSM * (int64_t)h->num_sms, ceil_div64(ceil_div64(R, kN2Chunk), 4)));
     };
     h->n2_split_f = n2_split(G);
     h->n2_split_b = n2_split(N);
-    h->n2_smem = n2_smem_bytes(J, h->n2_tj);
+    h->n2_smem = n2_smem_bytes(h->Jn, h->n2_tj);
     h->n2_blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(kN2BlocksPerSM, (220 * 1024) / h->n2_smem));
     if (h->n2_smem > 48 * 1024) {
       if (h->n2_tj == 8) {
@@ -607,7 +608,7 @@ bool lookup(ca_handle* h, const std::string& n, ArrayRef& r) {
   if (n == "grad_gamma_logits") return set(h->g_t, N, C, C, 0, false);
   if (n == "Z") return set(h->Zx, N, SC, J, 0, false);
   if (n == "Zx") return set(h->Zx, N, J, J, 0, false);
-  if (n == "R" && h->Rx) return set(h->Rx, N, SC, J, 0, false);
+  if (n == "R" && h->Rx) return set(h->Rx, N, SC, h->cell2 ? h->Jn : J, 0, false);
   if (n == "dM") return set(h->dM_sum, G, SC, J, 0, false);
   if (n == "dMx") return set(h->dM_sum, G, J, J, 0, false);
   if (n == "F") return set(h->Fout, N, C, C, 0, false);

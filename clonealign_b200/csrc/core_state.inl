@@ -42,6 +42,7 @@ struct ca_handle {
   size_t gene_smem = 0;
   int fused_nj = 0, fused_panels = 0, fused_warps = kFusedWarps;
   size_t fused_smem = 0;
+  int Jn = 0;                      // columns of the node sums: J, or S*C for the CELL2 set (derivative columns from the interpolants)
   bool cell2 = false;              // with epi2 + lean + defer, S <= 8: k_cell_fused2 (kernels_cell.cuh) is the per-cell kernel
   int cell2_wc = 16, cell2_sb = 8, cell2_panels = 0;
   size_t cell2_smem = 0;

@@ -120,20 +120,21 @@ template <bool FWD>
 void launch_interp_nodes(ca_handle* h, const float* rv, const float* shift, const float* B, int64_t R) {
   const int nsplit = FWD ? h->n2_split_f : h->n2_split_b;
   const int max_pan = FWD ? kIMaxPanF : kIMaxPanB;
+  const int Jn = h->Jn;   // node-sum columns = row pitch of B (CELL2 set: the S*C normaliser columns only)
   const unsigned grid = (unsigned)std::min<int64_t>((int64_t)max_pan * nsplit, (int64_t)h->n2_blocks_per_sm * h->num_sms);
   if (h->n2_tj == 8) {
     auto k = k_interp_nodes2<FWD, 8>;
-    CA_LAUNCH(k, grid, kN2Threads, h->n2_smem, h->stream)(h->iplan, rv, shift, B, R, h->J, h->n2_ncgp, nsplit, max_pan, h->ivals);
+    CA_LAUNCH(k, grid, kN2Threads, h->n2_smem, h->stream)(h->iplan, rv, shift, B, R, Jn, h->n2_ncgp, nsplit, max_pan, h->ivals);
   } else {
     auto k = k_interp_nodes2<FWD, 6>;
-    CA_LAUNCH(k, grid, kN2Threads, h->n2_smem, h->stream)(h->iplan, rv, shift, B, R, h->J, h->n2_ncgp, nsplit, max_pan, h->ivals);
+    CA_LAUNCH(k, grid, kN2Threads, h->n2_smem, h->stream)(h->iplan, rv, shift, B, R, Jn, h->n2_ncgp, nsplit, max_pan, h->ivals);
   }
   if (h->cell2)   // CELL2 set: slices split over grid.y as well, the last block of a column group finishes (k_interp_coeffs3)
-    CA_LAUNCH(k_interp_coeffs3, dim3((h->J + kC2Cols - 1) / kC2Cols, kC3Groups), kIP * kC2Cols * kC2Lanes, 0, h->stream)(
-        h->iplan, h->ivals, nsplit, max_pan, h->J, FWD ? 1 : 0, h->ipart2, h->itickets, h->icoef, h->icoef2);
+    CA_LAUNCH(k_interp_coeffs3, dim3((Jn + kC2Cols - 1) / kC2Cols, kC3Groups), kIP * kC2Cols * kC2Lanes, 0, h->stream)(
+        h->iplan, h->ivals, nsplit, max_pan, Jn, FWD ? 1 : 0, h->ipart2, h->itickets, h->icoef, h->icoef2);
   else
-  CA_LAUNCH(k_interp_coeffs2, dim3((h->J + kC2Cols - 1) / kC2Cols, kC2PanelsY), kIP * kC2Cols * kC2Lanes, 0, h->stream)(
-      h->iplan, h->ivals, nsplit, max_pan, h->J, FWD ? 1 : 0, h->icoef, nullptr);
+  CA_LAUNCH(k_interp_coeffs2, dim3((Jn + kC2Cols - 1) / kC2Cols, kC2PanelsY), kIP * kC2Cols * kC2Lanes, 0, h->stream)(
+      h->iplan, h->ivals, nsplit, max_pan, Jn, FWD ? 1 : 0, h->icoef, nullptr);
 }
 
 // the partial sums of the Y pass are needed from here on: wait for the pass forked onto stream2, or run it now
@@ -225,7 +226,7 @@ void run_forward(ca_handle* h, int mode) {
   sm.eps_in = eps_in; sm.seed = h->cfg.seed; sm.draw = h->draw++;
   sm.eps_out = h->eps; sm.mu = h->mu; sm.logmu = h->logmu; sm.sig = h->sig;
   sm.Mx = h->tc ? nullptr : h->Mx; sm.MxT_hi = h->tc ? h->MxT_hi : nullptr; sm.MxT_lo = h->tc ? h->MxT_lo : nullptr;
-  sm.gene_part = h->gene_part;
+  sm.gene_part = h->gene_part; sm.no_w_half = h->cell2 ? 1 : 0; sm.Jm = h->Jn;
   if (h->lean) {
     LaunchScope ls(h, "prologue");
     PrologueArgs a;
@@ -237,6 +238,7 @@ void run_forward(ca_handle* h, int mode) {
     a.state = h->dstate; a.lr = h->cfg.learning_rate;
     a.mu = sm;
     a.mu_vec4 = (h->C % 4 == 0) ? 1 : 0;
+    a.wide_panels = h->cell2 ? 1 : 0;
     CA_LAUNCH(k_prologue, 2 + kProPsiBlocks + h->n_gene_blocks, kProThreads, 0, h->stream)(a);
     KCHECK();
   } else {
@@ -305,7 +307,7 @@ void run_forward(ca_handle* h, int mode) {
     if (want_fork && h->defer && !h->cosched) CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
     if (h->cell2) {
       Cell2Args b;
-      b.N = a.N; b.C = a.C; b.S = a.S; b.SC = a.SC; b.J = a.J; b.smem_panels = h->cell2_panels;
+      b.N = a.N; b.C = a.C; b.S = a.S; b.SC = a.SC; b.J = a.J; b.Jn = h->Jn; b.smem_panels = h->cell2_panels;
       b.plan = a.plan; b.coef2 = reinterpret_cast<const double2*>(h->icoef2); b.mm = a.mm;
       b.U = a.U; b.Bm = a.Bm; b.vA = a.vA; b.s = a.s; b.log_alpha = a.log_alpha;
       b.t = a.t; b.gT = a.gT; b.Rx = a.Rx; b.gU = a.gU; b.Fout = a.Fout; b.shift = a.shift; b.Zx = a.Zx;
@@ -368,7 +370,7 @@ void run_train(ca_handle* h, bool apply) {
     {
       LaunchScope ls(h, "gene_grads", 1);
       Gene2Args a;
-      a.G = h->G; a.C = h->C; a.S = h->S; a.SC = h->SC; a.J = h->J; a.smem_panels = h->gene2_panels;
+      a.G = h->G; a.C = h->C; a.S = h->S; a.SC = h->SC; a.J = h->J; a.Jn = h->Jn; a.smem_panels = h->gene2_panels;
       a.plan = h->iplan; a.coef2 = reinterpret_cast<const double2*>(h->icoef2);
       a.Vm = h->Vm; a.mu = h->mu; a.sig = h->sig; a.eps = h->eps; a.lsd = h->lsd; a.L = h->L;
       a.ar = h->ar; a.dM_out = h->inspect ? h->dM_sum : nullptr;

@@ -30,9 +30,9 @@ constexpr int kCell2MaxS = 8;            // samples a lane keeps in registers
 
 struct Cell2Args {
   int64_t N;
-  int C, S, SC, J, smem_panels;
+  int C, S, SC, J, Jn, smem_panels;      // Jn: S*C rounded up to even = row pitch of Rx and of the coefficient table
   const InterpPlan* plan;
-  const double2* coef2;                  // monomial pairs [panel][kIP / 2][J] (k_interp_coeffs2)
+  const double2* coef2;                  // monomial pairs of the S*C normaliser columns [panel][kIP / 2][Jn] (k_interp_coeffs3)
   const float* mm;                       // (w_min, w_max)
   const float *U, *Bm, *vA, *s, *log_alpha;
   float* t;                              // gamma_logits (written in INIT mode)
@@ -41,7 +41,7 @@ struct Cell2Args {
   double *elbo_part, *gsum_part;         // one partial per block
 };
 
-inline size_t cell2_panel_bytes(int WC, int SB) { return (size_t)(kIP / 2) * 2 * SB * WC * sizeof(double2); }
+inline size_t cell2_panel_bytes(int WC, int SB) { return (size_t)(kIP / 2) * SB * WC * sizeof(double2); }
 inline size_t cell2_smem_bytes(int WC, int SB, int C, int smem_panels, int warps) {
   return (size_t)smem_panels * cell2_panel_bytes(WC, SB) + ((size_t)warps + (size_t)warps * C) * sizeof(double) + 16;
 }
@@ -84,10 +84,11 @@ __device__ __forceinline__ T group_max(T v) {
   return v;
 }
 
-// Horner evaluation of SBB samples' interpolants (Z, and Z' when DERIV) of one clone from the staged coefficient pairs
-// (a_2k, a_2k+1), table [pair][Z | Z'][SB][WC]: every offset is a compile-time constant.  Samples beyond S repeat the last one.
+// Horner evaluation of SBB samples' interpolants of one clone -- value p and, when DERIV, derivative dp / dt in the same pass
+// (dp <- dp t + p; p <- p t + a_m: every coefficient is loaded once and feeds both recurrences) -- from the staged coefficient
+// pairs (a_2k, a_2k+1), table [pair][SB][WC]: every offset is a compile-time constant.  Samples beyond S repeat the last one.
 template <bool DERIV, int WC, int SB, int SBB>
-__device__ __forceinline__ void cell2_horner(const double2* __restrict__ tb, double tt, int s0, int S, double (&p)[SBB], double (&q)[SBB]) {
+__device__ __forceinline__ void cell2_horner(const double2* __restrict__ tb, double tt, int s0, int S, double (&p)[SBB], double (&dp)[SBB]) {
   constexpr int KP = kIP / 2;
   int so[SBB];
 #pragma unroll
@@ -96,13 +97,15 @@ __device__ __forceinline__ void cell2_horner(const double2* __restrict__ tb, dou
   for (int kp = KP - 1; kp >= 0; --kp) {
 #pragma unroll
     for (int i = 0; i < SBB; ++i) {
-      const double2 cz = tb[kp * 2 * SB * WC + so[i]];
-      if (kp == KP - 1) p[i] = fma(cz.y, tt, cz.x);
-      else { p[i] = fma(p[i], tt, cz.y); p[i] = fma(p[i], tt, cz.x); }
-      if (DERIV) {
-        const double2 cd = tb[(kp * 2 + 1) * SB * WC + so[i]];
-        if (kp == KP - 1) q[i] = fma(cd.y, tt, cd.x);
-        else { q[i] = fma(q[i], tt, cd.y); q[i] = fma(q[i], tt, cd.x); }
+      const double2 cz = tb[kp * SB * WC + so[i]];
+      if (kp == KP - 1) {
+        if (DERIV) dp[i] = cz.y;                                  // p = a_15 -> dp = a_15, p = a_15 t + a_14
+        p[i] = fma(cz.y, tt, cz.x);
+      } else {
+        if (DERIV) dp[i] = fma(dp[i], tt, p[i]);
+        p[i] = fma(p[i], tt, cz.y);
+        if (DERIV) dp[i] = fma(dp[i], tt, p[i]);
+        p[i] = fma(p[i], tt, cz.x);
       }
     }
   }
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused2(Cell2Args a
   constexpr int CPW = 32 / WC;                  // cells per warp
   constexpr int SBB = SB < 4 ? SB : 4;          // samples per Horner batch (2 SBB independent chains per lane)
   constexpr int KP = kIP / 2;                   // coefficient pairs
-  constexpr int kPanelStride = KP * 2 * SB * WC;   // double2 per staged panel
+  constexpr int kPanelStride = KP * SB * WC;       // double2 per staged panel
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int sub = lane / WC, cl = lane % WC;
   const int C = a.C, S = a.S, SC = a.SC, J = a.J;
@@ -165,15 +168,14 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused2(Cell2Args a
   const int cap = a.smem_panels;
   for (int p0 = 0; p0 < (npan > 0 ? npan : 1); p0 += cap) {
   if (p0 > 0) __syncthreads();                  // every warp is done with the previous subset
-  {   // [panel][pair][J] -> [panel][pair][Z | Z'][sample][lane of the cell]
-    const int per = KP * 2 * SC;                // pairs per panel that exist
+  {   // [panel][pair][S*C] -> [panel][pair][sample][lane of the cell]
+    const int per = KP * SC;                    // pairs per panel that exist
     const int np = npan - p0 < cap ? npan - p0 : cap;
     for (int i = threadIdx.x; i < np * per; i += blockDim.x) {
       const int pan = i / per, r = i - pan * per;
-      const int kp = r / (2 * SC), jj = r - kp * 2 * SC;          // jj = half * SC + s * C + c
-      const int half = jj / SC, sc = jj - half * SC;
+      const int kp = r / SC, sc = r - kp * SC;                    // sc = s * C + c
       const int s = sc / C, cc = sc - s * C;
-      sm2[(size_t)pan * kPanelStride + ((kp * 2 + half) * SB + s) * WC + cc] = a.coef2[((int64_t)(p0 + pan) * KP + kp) * J + jj];
+      sm2[(size_t)pan * kPanelStride + (kp * SB + s) * WC + cc] = a.coef2[((int64_t)(p0 + pan) * KP + kp) * a.Jn + sc];
     }
     __syncthreads();
   }
@@ -189,17 +191,17 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused2(Cell2Args a
     const double x = (double)psif, m = (double)mf;
     // ---- panel and panel variable: tt = (x - lo) * 2 / width - 1 ----
     int panel;
-    double tt;
+    double tt, ih, wref;                         // Z' = (2 / width) dp/dt + w_ref p: the shift m = psi w_ref is linear on a side
     if (x < 0.0) {
       int pf = (int)((x - pmin) * ih_neg * 0.5);
       pf = pf < 0 ? 0 : (pf >= nf_neg ? nf_neg - 1 : pf);
       tt = (x - (pmin + pf * w_neg)) * ih_neg - 1.0;
-      panel = pf;
+      panel = pf; ih = ih_neg; wref = (double)wmin;
     } else {
       int pf = (int)(x * ih_pos * 0.5);
       pf = pf >= nf_pos ? nf_pos - 1 : pf;
       tt = w_pos > 0.0 ? (x - pf * w_pos) * ih_pos - 1.0 : 0.0;
-      panel = nf_neg + pf;
+      panel = nf_neg + pf; ih = ih_pos; wref = (double)wmax;
     }
     // a NaN psi (diverged fit) must yield NaN results, not an out-of-range table index
     panel = panel < 0 ? 0 : (panel >= npan ? (npan > 0 ? npan - 1 : 0) : panel);
@@ -213,8 +215,8 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused2(Cell2Args a
 #pragma unroll
     for (int s0 = 0; s0 < SB; s0 += SBB) {
       if (s0 < S) {                              // warp-uniform
-        double p[SBB], q[SBB];
-        cell2_horner<MODE == EPI_TRAIN, WC, SB, SBB>(tb, tt, s0, S, p, q);
+        double p[SBB], dp[SBB];
+        cell2_horner<MODE == EPI_TRAIN, WC, SB, SBB>(tb, tt, s0, S, p, dp);
         double pr = 1.0;
 #pragma unroll
         for (int i = 0; i < SBB; ++i) {
@@ -222,13 +224,12 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused2(Cell2Args a
             pr *= p[i];
             const float zf = (float)p[i];
             if (MODE == EPI_TRAIN) {
-              rz[s0 + i] = __fdividef(1.f, zf);
-              u = fma((double)rz[s0 + i], q[i], u);
+              const double q = fma(ih, dp[i], wref * p[i]);        // Z'_s
+              rz[s0 + i] = rcp_approx(zf);
+              u = fma((double)rz[s0 + i], q, u);
+              if (a.Zx && act) a.Zx[n * J + SC + (s0 + i) * C + c] = (float)q;
             }
-            if (a.Zx && act) {
-              a.Zx[n * J + (s0 + i) * C + c] = zf;
-              if (MODE == EPI_TRAIN) a.Zx[n * J + SC + (s0 + i) * C + c] = (float)q[i];
-            }
+            if (a.Zx && act) a.Zx[n * J + (s0 + i) * C + c] = zf;
           }
         }
         L += log_pos_f64(pr);
@@ -249,8 +250,8 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused2(Cell2Args a
     const float mx = group_max<WC>(tv);
     const double ex = cok ? (double)expf(tv - mx) : 0.0;
     const double zs = group_sum<WC>(ex);            // in [1, C]
-    const float lg = tv - (mx + logf((float)zs));
-    double rcp = (double)__fdividef(1.f, (float)zs);
+    const float lg = tv - (mx + __logf((float)zs));      // zs in [1, C]: absolute error < 1e-6
+    double rcp = (double)rcp_approx((float)zs);
     rcp = rcp * fma(-zs, rcp, 2.0);
     rcp = rcp * fma(-zs, rcp, 2.0);
     const double g = ex * rcp;
@@ -267,14 +268,10 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused2(Cell2Args a
       }
       // R_scn = gamma_nc s_n / (S Z_scn) and d psi_n = (YW)_n - sum_sc R Z' - psi_n
       const float gs = (float)(g * sn * invS);
-      float* rx = a.Rx + n * J + c;
+      float* rx = a.Rx + n * a.Jn + c;              // [N][Jn]: the psi-scaled copy of R is not needed (k_gene_fused2)
 #pragma unroll
       for (int s = 0; s < SB; ++s) {
-        if (s < S && act) {
-          const float r = gs * rz[s];
-          rx[s * C] = r;
-          rx[SC + s * C] = psif * r;
-        }
+        if (s < S && act) { *rx = gs * rz[s]; rx += C; }
       }
       const double gu = group_sum<WC>(cok ? (double)gs * u : 0.0);
       if (cl == 0 && nok) a.gU[n] = (float)(-gu - x);
@@ -322,9 +319,9 @@ namespace ca {
 // Reference graph nodes: R/inference-tflow.R:288-296 (reverse mode of the log-normaliser), 345-346.
 // =====================================================================================================================
 struct Gene2Args {
-  int G, C, S, SC, J, smem_panels;
+  int G, C, S, SC, J, Jn, smem_panels;
   const InterpPlan* plan;
-  const double2* coef2;      // backward monomial pairs [panel][kIP / 2][J]
+  const double2* coef2;      // backward monomial pairs of the S*C columns [panel][kIP / 2][SC]
   const float *Vm, *mu, *sig, *eps, *lsd, *L;
   float *ar, *dM_out;        // dM_out: inspection copy [G][J] or nullptr
   const double* gsum_part;   // [n_parts][C]
@@ -344,7 +341,7 @@ __global__ void __launch_bounds__(kGene2Warps * 32, 2) k_gene_fused2(Gene2Args a
   constexpr int GPW = 32 / WC;                  // genes per warp
   constexpr int SBB = SB < 4 ? SB : 4;
   constexpr int KP = kIP / 2;
-  constexpr int kPanelStride = KP * 2 * SB * WC;
+  constexpr int kPanelStride = KP * SB * WC;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int sub = lane / WC, cl = lane % WC;
   const int C = a.C, S = a.S, SC = a.SC, J = a.J, G = a.G;
@@ -369,14 +366,13 @@ __global__ void __launch_bounds__(kGene2Warps * 32, 2) k_gene_fused2(Gene2Args a
   for (int p0 = 0; p0 < (npan > 0 ? npan : 1); p0 += cap) {
     if (p0 > 0) __syncthreads();
     {
-      const int per = KP * 2 * SC;
+      const int per = KP * SC;
       const int np = npan - p0 < cap ? npan - p0 : cap;
       for (int i = threadIdx.x; i < np * per; i += blockDim.x) {
         const int pan = i / per, r = i - pan * per;
-        const int kp = r / (2 * SC), jj = r - kp * 2 * SC;
-        const int half = jj / SC, sc = jj - half * SC;
+        const int kp = r / SC, sc = r - kp * SC;
         const int s = sc / C, cc = sc - s * C;
-        sm2[(size_t)pan * kPanelStride + ((kp * 2 + half) * SB + s) * WC + cc] = a.coef2[((int64_t)(p0 + pan) * KP + kp) * J + jj];
+        sm2[(size_t)pan * kPanelStride + (kp * SB + s) * WC + cc] = a.coef2[((int64_t)(p0 + pan) * KP + kp) * a.Jn + sc];
       }
       __syncthreads();
     }
@@ -406,12 +402,13 @@ __global__ void __launch_bounds__(kGene2Warps * 32, 2) k_gene_fused2(Gene2Args a
             const int64_t o = (int64_t)(s0 + i < S ? s0 + i : S - 1) * G + g;
             sg[i] = a.sig[o]; ep[i] = a.eps[o]; mu[i] = a.mu[o];
           }
-          double d[SBB], d2[SBB];
-          cell2_horner<true, WC, SB, SBB>(tb, tt, s0, S, d, d2);
+          double d[SBB], dd[SBB];
+          cell2_horner<true, WC, SB, SBB>(tb, tt, s0, S, d, dd);
 #pragma unroll
           for (int i = 0; i < SBB; ++i) {
             if (s0 + i < S) {
-              const float df = (float)d[i], d2f = (float)d2[i];   // the unfused path rounds dMx to fp32: keep its numerics
+              // dM' = sum_n psi_n R exp(psi_n w - m_n) = d(dM)/dw: the derivative of the interpolant (the shifts m_n do not depend on w)
+              const float df = (float)d[i], d2f = (float)(ih * dd[i]);   // the unfused path rounds dMx to fp32: keep its numerics
               if (a.dM_out && act) {
                 a.dM_out[(int64_t)g * J + (s0 + i) * C + c] = df;
                 a.dM_out[(int64_t)g * J + SC + (s0 + i) * C + c] = d2f;

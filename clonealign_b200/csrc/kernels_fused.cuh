@@ -304,6 +304,7 @@ struct PrologueArgs {
   double lr;                // learning rate
   SampleMuArgs mu;          // gene blocks (k_sample_mu): blocks 2 + kProPsiBlocks ..; gene_part has one partial per gene block
   int mu_vec4;              // C % 4 == 0: 16-byte stores of the contraction operand
+  int wide_panels;          // CELL2 set: interp_make_plan(..., wide = true)
 };
 
 // roles by block: 0 = alpha / scalar priors (k_alpha), 1 = W range and sum of squares (k_minmax, k_wsq; K == 1),
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(kProThreads) k_prologue(PrologueArgs a) {
     for (int i = 0; i < kProPsiBlocks; ++i) { mn = fminf(mn, pp[2 * i]); mx = fmaxf(mx, pp[2 * i + 1]); }
     a.mm_psi[0] = mn;
     a.mm_psi[1] = mx;
-    *a.plan = interp_make_plan((double)mw[0], (double)mw[1], (double)mn, (double)mx);
+    *a.plan = interp_make_plan((double)mw[0], (double)mw[1], (double)mn, (double)mx, a.wide_panels != 0);
     *a.ticket = 0u;
     // this forward pass has consumed draw `draw`; the optimiser step that may follow is step adam_t + 1
     a.state->draw = draw + 1ull;

@@ -73,7 +73,13 @@ constexpr ChebToMono make_cheb_to_mono() {
 static __device__ const ChebToMono kT2M = make_cheb_to_mono();   // global memory: indexed per thread (staged to shared memory by its users)
 
 // panel structure from the current ranges of psi and w
-__device__ __forceinline__ InterpPlan interp_make_plan(double wmin, double wmax, double pmin, double pmax) {
+// `wide` (CELL2 set): the derivative columns Z' = dZ/dpsi + w_ref Z and dM' = d(dM)/dw are taken from the DERIVATIVE of the
+// interpolants instead of being interpolated themselves (half the node sums, half the tables).  Differentiating amplifies the
+// fp32-class noise of the node values (~2e-8 relative) by ~n^2 / (panel half-width), so a single panel that would be narrower
+// than an exponent half-range of kIAmin = 2 is widened to it (it then reaches beyond the data: harmless, the function is entire):
+// |d/dx| error <= ~1e-6 of (scale x value) for every range of psi and W, including W = 0 and psi = 0 at the start of a fit.
+constexpr double kIAmin = 2.0;
+__device__ __forceinline__ InterpPlan interp_make_plan(double wmin, double wmax, double pmin, double pmax, bool wide = false) {
   InterpPlan pl;
   pl.wmin = wmin; pl.wmax = wmax;
   pl.pmin = pmin; pl.pmax = pmax;
@@ -97,6 +103,12 @@ __device__ __forceinline__ InterpPlan interp_make_plan(double wmin, double wmax,
   const double A = fmax(fabs(pl.pmin), fabs(pl.pmax));
   pl.nb = count(D, A, kIMaxPanB);
   pl.b_w = D / pl.nb;
+  if (wide) {
+    const double wf = fmin(2.0 * kIAmin / fmax(D, 1e-30), 1e3), wb = fmin(2.0 * kIAmin / fmax(A, 1e-30), 1e3);
+    if (pl.nf_neg == 1 && pl.f_neg_w < wf) { pl.f_neg_w = wf; pl.pmin = -wf; }     // panel [-wf, 0)
+    if (pl.nf_pos == 1 && pl.f_pos_w < wf) pl.f_pos_w = wf;                         // panel [0, wf]
+    if (pl.nb == 1 && pl.b_w < wb) pl.b_w = wb;                                     // panel [wmin, wmin + wb]
+  }
   return pl;
 }
 // one thread
@@ -126,7 +138,7 @@ __global__ void k_interp_plan(const float* __restrict__ mm_w, const float* __res
 constexpr int kN2Threads = 128;
 constexpr int kN2Chunk = 32;                 // rows of the reduction index per staged chunk
 constexpr int kN2EPitch = 2 * kIP + 8;       // floats per row of the (e, e) tile: 16 pairs + 8 floats of bank shift
-constexpr int kN2BlocksPerSM = 3;
+constexpr int kN2BlocksPerSM = 4;                // 128 registers: two blocks fit next to the two persistent Y-pass CTAs of an SM
 
 inline int n2_pick_tj(int J) {               // columns per thread: the choice that pads fewer columns
   auto padded = [](int J_, int tj) { int ncg = (J_ + tj - 1) / tj, p = 1; while (p < ncg) p <<= 1; return p * tj; };

@@ -206,6 +206,8 @@ struct SampleMuArgs {
   float* Mx;                       // [G][J] fp32 (CUDA-core path) or nullptr
   __nv_bfloat16 *MxT_hi, *MxT_lo;  // [J][Gld] bf16 hi / lo split (tensor path) or nullptr
   double* gene_part;               // one partial per block
+  int no_w_half;                   // CELL2 set: Mx holds only the S*C normaliser columns (no w-scaled copy), row pitch Jm
+  int Jm;                          // = S*C rounded up to even: 8-byte row starts for the staged copies of the node kernel
 };
 
 // body shared by k_sample_mu (one launch of its own) and k_prologue (variant lean: gene blocks of the fused launch).
@@ -242,19 +244,22 @@ __device__ __forceinline__ void sample_mu_body(const SampleMuArgs& a, int block,
       e += cs * (double)lm - 0.5 * (double)lm * (double)lm - (-0.5 * (double)eps * (double)eps - (double)lsd - lsg);
       if (VEC4) {
         const float4* L4 = reinterpret_cast<const float4*>(a.L + (int64_t)g * a.C);
-        float4* M4 = reinterpret_cast<float4*>(a.Mx + (int64_t)g * a.J + s * a.C);
-        float4* W4 = reinterpret_cast<float4*>(a.Mx + (int64_t)g * a.J + a.SCp + s * a.C);
+        const int pitch = a.no_w_half ? a.Jm : a.J;
+        float4* M4 = reinterpret_cast<float4*>(a.Mx + (int64_t)g * pitch + s * a.C);
+        float4* W4 = reinterpret_cast<float4*>(a.Mx + (int64_t)g * pitch + a.SCp + s * a.C);
         for (int c4 = 0; c4 < a.C / 4; ++c4) {
           const float4 l = L4[c4];
           const float4 m = make_float4(mu * l.x, mu * l.y, mu * l.z, mu * l.w);
           M4[c4] = m;
-          W4[c4] = make_float4(vk[0] * m.x, vk[0] * m.y, vk[0] * m.z, vk[0] * m.w);
+          if (!a.no_w_half) W4[c4] = make_float4(vk[0] * m.x, vk[0] * m.y, vk[0] * m.z, vk[0] * m.w);
         }
       } else
       for (int c = 0; c < a.C; ++c) {
         float m = mu * a.L[(int64_t)g * a.C + c];
         int j = s * a.C + c;
-        if (a.Mx) {
+        if (a.Mx && a.no_w_half) {
+          a.Mx[(int64_t)g * a.Jm + j] = m;
+        } else if (a.Mx) {
           a.Mx[(int64_t)g * a.J + j] = m;
           for (int kp = 0; kp < a.KP; ++kp) a.Mx[(int64_t)g * a.J + a.SCp * (1 + kp) + j] = vk[kp] * m;
         }

@@ -63,6 +63,13 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src,
 }
 }  // namespace ptx
 
+// hardware reciprocal (MUFU.RCP, 1 ulp; flushes denormals): for positive normal arguments
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // the same, on generic pointers (what the Y pass uses)
 __device__ __forceinline__ void bar_init(uint64_t* bar, int count) { ptx::mbar_init(ptx::smem_u32(bar), (uint32_t)count); }
 __device__ __forceinline__ void bar_arm(uint64_t* bar, uint32_t bytes) { ptx::mbar_expect_tx(ptx::smem_u32(bar), bytes); }

@@ -3,6 +3,9 @@
 // Copies are synchronous: a cp.async / bulk copy is a memcpy by the issuing thread, commit / wait / mbarrier waits are
 // no-ops, and CA_SYNC_AFTER_SYNCHRONOUS_COPY() is the block barrier that orders a one-thread copy before its readers.
 #pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #define CA_TC_HEADER "kernels_tc_stub.h"
@@ -11,14 +14,23 @@
 
 namespace ca {
 constexpr bool kGraphsAvailable = false;
-inline void cp_async16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
-inline void cp_async8(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 8); }
+// the hardware faults on a copy whose addresses are not multiples of its size (cudaErrorMisalignedAddress): so does the emulation
+inline void ca_emul_check_aligned(const void* a, const void* b, unsigned n, const char* what) {
+  if (((uintptr_t)a | (uintptr_t)b) % n) { fprintf(stderr, "cuda_emul: misaligned %s (%p <- %p)\n", what, a, b); abort(); }
+}
+inline void cp_async16(void* smem_dst, const void* gmem_src) { ca_emul_check_aligned(smem_dst, gmem_src, 16, "cp.async 16"); std::memcpy(smem_dst, gmem_src, 16); }
+inline void cp_async8(void* smem_dst, const void* gmem_src) { ca_emul_check_aligned(smem_dst, gmem_src, 8, "cp.async 8"); std::memcpy(smem_dst, gmem_src, 8); }
+inline float rcp_approx(float x) { return 1.0f / x; }
 inline void cp_async_commit() {}
 template <int N> inline void cp_async_wait() {}
 inline void bar_init(uint64_t*, int) {}
 inline void bar_arm(uint64_t*, uint32_t) {}
 inline void bar_wait(uint64_t*, uint32_t) {}
-inline void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t*) { std::memcpy(dst, src, bytes); }
+inline void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t*) {
+  ca_emul_check_aligned(dst, src, 16, "bulk copy");
+  if (bytes % 16) { fprintf(stderr, "cuda_emul: bulk copy of %u bytes\n", bytes); abort(); }
+  std::memcpy(dst, src, bytes);
+}
 inline void fence_bar_init() {}
 inline void fence_proxy_async() {}
 }  // namespace ca
