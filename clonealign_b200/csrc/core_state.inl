@@ -85,6 +85,8 @@ struct ca_handle {
   int nCB = 1, nRB = 1, RB = 512, n_gene_blocks = 0, nsplit = 1;
   int64_t n_epi_blocks = 0;
   bool ydirty = true;
+  bool t_done = false;             // the per-cell kernel of the step in flight has updated the gamma logits itself
+  bool apply_now = false;          // the train step in flight applies its updates (false: ca_core_grads)
   bool inspect = false;            // test hook (ca_core_grads): also write inspection-only arrays (Z of the fused kernel)
   TcPlan tcplan;
 

@@ -312,6 +312,9 @@ void run_forward(ca_handle* h, int mode) {
       b.U = a.U; b.Bm = a.Bm; b.vA = a.vA; b.s = a.s; b.log_alpha = a.log_alpha;
       b.t = a.t; b.gT = a.gT; b.Rx = a.Rx; b.gU = a.gU; b.Fout = a.Fout; b.shift = a.shift; b.Zx = a.Zx;
       b.elbo_part = a.elbo_part; b.gsum_part = a.gsum_part;
+      b.apply_t = (mode == EPI_TRAIN && h->apply_now && !getenv("CLONEALIGN_B200_NO_CELL_ADAM")) ? 1 : 0;
+      b.m_t = h->m_t; b.v_t = h->v_t; b.state = h->dstate;
+      h->t_done = b.apply_t != 0;
       launch_cell2(h, mode, b);
     } else
     launch_fused(h, mode, a);
@@ -347,6 +350,8 @@ void run_forward(ca_handle* h, int mode) {
 
 void run_train(ca_handle* h, bool apply) {
   h->launches_last_step = 0;
+  h->apply_now = apply;
+  h->t_done = false;
   run_forward(h, EPI_TRAIN);
   {
     LaunchScope ls(h, "lse_bwd", h->interp ? (h->lean ? 2 : 3) : 1);
@@ -454,7 +459,8 @@ void run_train(ca_handle* h, bool apply) {
       aa.ga = ga; aa.chi_cur = h->chi_cur; aa.sa = sa; aa.N = h->N; aa.C = h->C;
       aa.t = h->t; aa.m_t = h->m_t; aa.v_t = h->v_t; aa.U = h->U; aa.m_U = h->m_U; aa.v_U = h->v_U; aa.gT = h->g_t; aa.gU = h->g_U;
       aa.n_gene_blocks = (h->G + 255) / 256;
-      aa.n_cell_blocks = (apply || h->defer) ? ceil_div64(ceil_div64(h->N * h->C, 4) + h->N, 256) : 0;
+      aa.t_done = h->t_done ? 1 : 0;
+      aa.n_cell_blocks = (apply || h->defer) ? ceil_div64((aa.t_done ? 0 : ceil_div64(h->N * h->C, 4)) + h->N, 256) : 0;
       aa.defer_yv = h->defer ? 1 : 0; aa.nCB = h->nCB; aa.rowpart = h->rowpart; aa.YV = h->YV;
       aa.state = h->dstate;
       const bool adam_adds_colpart = h->cell2 && h->cfg.world == 1;

@@ -39,6 +39,14 @@ struct Cell2Args {
   float *gT, *Rx, *gU, *Fout, *shift;
   float* Zx;                             // optional inspection copy of (Z | Z') [N][J], nullptr in the timed path
   double *elbo_part, *gsum_part;         // one partial per block
+  // TRAIN mode with apply_t != 0: the TF1-Adam update of the gamma logits happens HERE, by the lane that has just computed the
+  // gradient (d t depends on nothing outside this cell), instead of writing g_t for k_adam_all to read back: 1.2 M of the 1.3 M
+  // elements that kernel updates at config 3, off the critical tail behind the Y-pass join.  The per-cell kernel is bound by
+  // shared-memory latency, not by issue slots (ncu of round 2), so the update is close to free here (it was not in k_cell_fused).
+  // lr_t of the step comes from StepState (k_prologue).
+  int apply_t;
+  float *m_t, *v_t;
+  const StepState* state;
 };
 
 inline size_t cell2_panel_bytes(int WC, int SB) { return (size_t)(kIP / 2) * SB * WC * sizeof(double2); }
@@ -138,6 +146,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused2(Cell2Args a
   const float la = a.log_alpha[c];
   const float wmin = a.mm[0], wmax = a.mm[1];
   const double invS = 1.0 / (double)S;
+  const float lr_t = (MODE == EPI_TRAIN && a.apply_t) ? a.state->lr_t : 0.f;
 
   double elbo_w = 0.0, gacc = 0.0;
   const int64_t chunk = (a.N + gridDim.x - 1) / gridDim.x;
@@ -264,7 +273,15 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_cell_fused2(Cell2Args a
     if (MODE == EPI_TRAIN) {
       if (act) {
         gacc += g;
-        a.gT[n * C + c] = (g == 0.0) ? 0.f : (float)(g * (H - sumGH));
+        const float gt = (g == 0.0) ? 0.f : (float)(g * (H - sumGH));
+        if (a.apply_t) {
+          const int64_t o = n * C + c;
+          float tnew = tv_in, mm_ = a.m_t[o], vv_ = a.v_t[o];
+          adam_update_tf1(tnew, mm_, vv_, gt, lr_t);
+          a.t[o] = tnew; a.m_t[o] = mm_; a.v_t[o] = vv_;
+        } else {
+          a.gT[n * C + c] = gt;
+        }
       }
       // R_scn = gamma_nc s_n / (S Z_scn) and d psi_n = (YW)_n - sum_sc R Z' - psi_n
       const float gs = (float)(g * sn * invS);

@@ -582,6 +582,7 @@ struct AdamAllArgs {
   const float* colpart;
   int nRB;
   float* YtU;
+  int t_done;                // the gamma logits were already updated by k_cell_fused2: the cell blocks only hold psi
 };
 __global__ void __launch_bounds__(256) k_adam_all(AdamAllArgs a) {
   const int64_t b = blockIdx.x;
@@ -630,7 +631,7 @@ __global__ void __launch_bounds__(256) k_adam_all(AdamAllArgs a) {
     // cell blocks: thread i < nt4 updates 4 consecutive gamma logits (16-byte loads / stores: a quarter of the threads,
     // 4x the bytes in flight per thread -- the kernel is latency-bound), the threads behind them one psi each
     const int64_t i = (b - a.n_gene_blocks) * blockDim.x + threadIdx.x;
-    const int64_t nt = a.N * a.C, nt4 = (nt + 3) / 4;
+    const int64_t nt = a.N * a.C, nt4 = a.t_done ? 0 : (nt + 3) / 4;
     if (i < nt4) {
       if (a.ga.h.apply) {
         const int64_t e0 = 4 * i;

@@ -712,6 +712,15 @@ __device__ __forceinline__ void adam_update(float& th, float& m, float& v, float
   th = th - h.lr_t * m / (sqrtf(v) + h.eps);
 }
 
+// the same update with the optimiser's constants as literals (b1 = 0.9, b2 = 0.999, eps = 1e-8: tf$train$AdamOptimizer
+// defaults, R/inference-tflow.R:345): bit-identical to adam_update with those values, three registers fewer in the caller
+__device__ __forceinline__ void adam_update_tf1(float& th, float& m, float& v, float g_elbo, float lr_t) {
+  float g = -g_elbo;
+  m = m + (1.f - 0.9f) * (g - m);
+  v = v + (1.f - 0.999f) * (g * g - v);
+  th = th - lr_t * m / (sqrtf(v) + 1e-8f);
+}
+
 struct GeneAdamArgs {
   int G, S, K, KP;
   const float* ar;   // after allreduce

@@ -83,7 +83,7 @@ enum ca_path     { CA_PATH_AUTO = 0, CA_PATH_CUDACORE = 1, CA_PATH_TENSOR = 2, C
  *   DEFER : (with EPI2 + LEAN) the per-cell kernel does not read the Y-pass partials: psi_n (YW)_n joins the ELBO and (YW)_n
  *           joins d psi_n afterwards (k_yv_dot, k_adam_all), so the Y pass is joined only before the gene-gradient kernel and,
  *           with OVERLAP, runs next to the per-cell kernel and the backward node sums instead of before them
- *   EPI2  : (interp path) Clenshaw evaluation fused into a leaner per-cell epilogue, see kernels_fused.cuh
+ *   EPI2  : (interp path) evaluation of the interpolants fused into a leaner per-cell epilogue, see kernels_fused.cuh
  *   LEAN  : (with EPI2) gene-level / scalar / optimiser work in 3 launches instead of 12, see kernels_fused.cuh
  *   P2P   : (world > 1) the per-step all-reduce as one kernel over NVLink peer memory instead of ncclAllReduce; needs
  *           ca_core_p2p_export / ca_core_p2p_connect after ca_core_create, see kernels_p2p.cuh
@@ -94,8 +94,10 @@ enum ca_path     { CA_PATH_AUTO = 0, CA_PATH_CUDACORE = 1, CA_PATH_TENSOR = 2, C
  *   COSCHED: (with DEFER + YPASS4) the Y pass is started FIRST in the step on the second stream and joined before the
  *           gene-gradient kernel; the per-cell kernel runs with 16 warps so that both fit on every SM: the HBM-bound stream
  *           runs next to the issue-bound kernels of the whole step
- *   CELL2 : (with EPI2 + LEAN + DEFER; takes effect for S <= 8) per-cell kernel with lane = (cell, clone) and Horner evaluation of the
- *           interpolants in the monomial basis, see kernels_cell.cuh; part of the default set */
+ *   CELL2 : (with EPI2 + LEAN + DEFER; takes effect for S <= 8) second-generation per-cell / per-gene kernels, see kernels_cell.cuh:
+ *           lane = (cell, clone) resp. (gene, clone), Horner evaluation of the interpolants in the monomial basis, the w-weighted
+ *           columns taken from the derivative of the interpolants (node sums over the S*C normaliser columns only), the gene kernel
+ *           in front of the Y-pass join, the gamma-logit Adam update inside the per-cell kernel; part of the default set */
 enum ca_variant  { CA_VAR_YPASS2 = 1, CA_VAR_EPI2 = 2, CA_VAR_LEAN = 4, CA_VAR_P2P = 8, CA_VAR_OVERLAP = 16, CA_VAR_YPASS3 = 32, CA_VAR_DEFER = 64,
                    CA_VAR_YPASS4 = 128, CA_VAR_COSCHED = 256, CA_VAR_CELL2 = 512 };
 

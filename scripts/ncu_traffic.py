@@ -13,7 +13,7 @@ import sys
 
 LABELS = [("k_ypass", "ypass"), ("k_cell_fused", "cell_epilogue"), ("k_prologue", "prologue"), ("k_gene_fused", "gene_grads"),
           ("k_adam_all", "adam"), ("k_interp_nodes2<1", "lse_fwd_nodes"), ("k_interp_nodes2<0", "lse_bwd_nodes"),
-          ("k_interp_coeffs2", "coeffs")]
+          ("k_interp_coeffs", "coeffs"), ("k_colpart_add", "colpart_add")]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 

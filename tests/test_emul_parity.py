@@ -17,8 +17,8 @@ pytestmark = pytest.mark.usefixtures("emulated_library")
 # (packed-fp32 Y pass, fused Clenshaw + per-cell epilogue) that bench.py validates on the device before using them
 # (ypass2 on the CUDA-core path, the epi2-only and the overlap sets are covered by the storage-format test, test_random_shapes_and_variants, test_variants_agree_with_default_kernels and
 # bench.py's candidate tests: on the synchronous emulation `overlap` only changes which stream handle a launch names)
-PATHS = [("cudacore", ""), ("interp", ""), ("interp", "ypass2,epi2,lean"), ("cudacore", "ypass3"),
-         ("interp", "ypass3,epi2,lean"), ("interp", "ypass3,epi2,lean,defer,overlap"), ("auto", ""),
+PATHS = [("cudacore", ""), ("interp", ""), ("interp", "ypass2,epi2,lean"),
+         ("interp", "ypass3,epi2,lean,defer,overlap"), ("auto", ""),
          ("interp", "ypass4,epi2,lean,defer,cosched"), ("cudacore", "ypass4"), ("interp", "ypass3,epi2,lean,defer,cell2")]
 
 
@@ -242,6 +242,21 @@ def test_fused_epilogue_coefficients_through_l2(example_sce, monkeypatch):
     with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=3, K=1, path="interp", variants="epi2", seed=1) as sess:
         _load_params(sess, p)
         _check_grads(sess, d, p, 3)
+
+
+@pytest.mark.parametrize("panels", ["1", "2"])
+def test_cell2_panels_staged_in_rounds(example_sce, monkeypatch, panels):
+    """CELL2 set with more active panels than the shared-memory tables of the per-cell / per-gene kernels hold: the blocks
+    walk their cells (genes) once per subset of panels, every cell is worked on in the round that holds its panel."""
+    monkeypatch.setenv("CLONEALIGN_B200_FUSED_PANELS", panels)
+    Y, L = example_sce
+    d, p, mu_guess, _ = _case(Y, L, K=1, seed=5, scale=1.0)
+    p.psi *= 2.0
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=3, K=1, path="auto", seed=1) as sess:
+        _load_params(sess, p)
+        _check_grads(sess, d, p, 3)
+        pan = sess.describe()["panels"]
+        assert sess.describe()["variants"] & 512 and pan["nf_neg"] + pan["nf_pos"] > 2 and pan["nb"] > 2
 
 
 def test_variant_validation(example_sce):
