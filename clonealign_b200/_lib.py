@@ -16,7 +16,7 @@ Y_COLMAJOR, Y_ROWMAJOR, Y_CSR = 0, 1, 2
 Y_HOST, Y_DEVICE = 0, 1
 STORE_AUTO, STORE_F32, STORE_U16, STORE_U8 = 0, 1, 2, 3
 PATH_AUTO, PATH_CUDACORE, PATH_TENSOR, PATH_INTERP = 0, 1, 2, 3
-VAR_YPASS2, VAR_EPI2, VAR_LEAN, VAR_P2P, VAR_OVERLAP, VAR_YPASS3, VAR_DEFER, VAR_YPASS4, VAR_COSCHED, VAR_CELL2 = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
+VAR_YPASS2, VAR_EPI2, VAR_LEAN, VAR_P2P, VAR_OVERLAP, VAR_YPASS3, VAR_DEFER, VAR_YPASS4, VAR_COSCHED, VAR_CELL2, VAR_YPASS5 = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024
 ABI_VERSION = 6
 
 EXPORTS = (

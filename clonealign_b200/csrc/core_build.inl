@@ -198,7 +198,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   }
   h->interp = (c.path == CA_PATH_INTERP);
   h->variants = c.variants;
-  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_P2P | CA_VAR_OVERLAP | CA_VAR_YPASS3 | CA_VAR_DEFER | CA_VAR_YPASS4 | CA_VAR_COSCHED | CA_VAR_CELL2))
+  if (c.variants & ~(uint32_t)(CA_VAR_YPASS2 | CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_P2P | CA_VAR_OVERLAP | CA_VAR_YPASS3 | CA_VAR_DEFER | CA_VAR_YPASS4 | CA_VAR_COSCHED | CA_VAR_CELL2 | CA_VAR_YPASS5))
     fail("unknown kernel variant bits 0x%x", c.variants);
   if ((c.variants & CA_VAR_P2P) && c.world > kP2PMaxWorld) fail("variant p2p supports at most %d ranks", kP2PMaxWorld);
   h->p2p = (c.variants & CA_VAR_P2P) && c.world > 1;
@@ -399,10 +399,12 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   h->scal_elbo = h->alloc<double>(1); h->cell_sum = h->alloc<double>(1); h->wsq = h->alloc<double>(std::max(K, 1));
   h->elbo_dev = h->alloc<double>(1);
   h->ar = z((size_t)G * (2 + KP) + C + 4);
+  h->ypass5 = kImmaAvailable && (h->variants & CA_VAR_YPASS5) && (h->variants & CA_VAR_YPASS4) && h->ystore == CA_STORE_U8 && KP == 1;
   if (KP == 1) {
     int tile_cols = kYCB;
     if (h->variants & (CA_VAR_YPASS3 | CA_VAR_YPASS4))   // column tile of k_ypass_k1_v3 / v4: 256 threads x the columns a thread owns for this storage type
       tile_cols = h->ystore == CA_STORE_U8 ? ypass3_tile_cols<uint8_t>() : (h->ystore == CA_STORE_U16 ? ypass3_tile_cols<uint16_t>() : ypass3_tile_cols<float>());
+    if (h->ypass5) tile_cols = kY5Cols;
     h->nCB = (int)ceil_div64(h->ldY, tile_cols);
     h->RB = 512;
     if (h->variants & (CA_VAR_YPASS3 | CA_VAR_YPASS4)) {
@@ -418,6 +420,14 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
       if (h->variants & CA_VAR_YPASS4) waves = std::min<int64_t>(waves, h->cell2 ? 1 : 2);   // cell2: half the column partials to add behind the join
       const int64_t nrb = std::max<int64_t>(1, waves * slots / h->nCB);
       h->RB = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(16, round_up64(ceil_div64(N, nrb), 16)));
+    }
+    if (h->ypass5) {
+      // one persistent CTA per SM; a whole number of waves of (kY5Cols columns x RB rows) tiles, RB a multiple of the 32-row stage
+      // and at most kY5MaxRows (the psi digits of a tile live in shared memory)
+      const int64_t slots = h->num_sms;
+      const int64_t waves = std::max<int64_t>(1, ceil_div64((int64_t)h->nCB * ceil_div64(N, kY5MaxRows), slots));
+      const int64_t nrb = std::max<int64_t>(1, waves * slots / h->nCB);
+      h->RB = (int)std::min<int64_t>(kY5MaxRows, std::max<int64_t>(kY5StageRows, round_up64(ceil_div64(N, nrb), kY5StageRows)));
     }
   } else {
     h->nCB = 1;
@@ -487,6 +497,13 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
       CUDA_OK(cudaFuncSetAttribute(k_interp_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ieval_smem));
     }
   }
+  if (h->ypass5) {
+    if (const char* e = getenv("CLONEALIGN_B200_Y5_WARPS")) h->y5_warps = atoi(e) == 8 ? 8 : 16;
+    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v5<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ypass5_smem_bytes()));
+    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v5<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v5<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ypass5_smem_bytes()));
+    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v5<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  }
   if (h->variants & CA_VAR_YPASS4) {
     if (const char* e = getenv("CLONEALIGN_B200_Y4_MINB")) h->y4_minb = atoi(e) == 3 ? 3 : 4;
     auto set4 = [&](auto kern, size_t bytes) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); };
@@ -544,12 +561,12 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if (h->cell2) {
     h->cell2_wc = cell2_pick_wc(C);
     h->cell2_sb = cell2_pick_sb(S);
-    const size_t budget = h->cosched ? 92 * 1024 : 200 * 1024;
+    const size_t budget = h->cosched ? (h->ypass5 ? 56 * 1024 : 92 * 1024) : 200 * 1024;
     h->cell2_panels = cell2_smem_panels(h->cell2_wc, h->cell2_sb, C, budget, h->fused_warps);
     if (h->cell2_panels < 1) fail("variant cell2: the coefficient table of one panel (%zu bytes) does not fit into shared memory", cell2_panel_bytes(h->cell2_wc, h->cell2_sb));
     if (const char* e = getenv("CLONEALIGN_B200_FUSED_PANELS")) h->cell2_panels = std::max(1, std::min(h->cell2_panels, atoi(e)));   // test hook: several rounds
     h->cell2_smem = cell2_smem_bytes(h->cell2_wc, h->cell2_sb, C, h->cell2_panels, h->fused_warps);
-    h->gene2_panels = gene2_smem_panels(h->cell2_wc, h->cell2_sb, 96 * 1024);   // two 512-thread blocks per SM
+    h->gene2_panels = std::max(1, gene2_smem_panels(h->cell2_wc, h->cell2_sb, (h->cosched && h->ypass5) ? 56 * 1024 : 96 * 1024));   // two 512-thread blocks per SM (one next to the Y pass)
     if (const char* e = getenv("CLONEALIGN_B200_FUSED_PANELS")) h->gene2_panels = std::max(1, std::min(h->gene2_panels, atoi(e)));
     h->gene2_smem = gene2_smem_bytes(h->cell2_wc, h->cell2_sb, h->gene2_panels);
     cell2_dispatch(h->cell2_wc, h->cell2_sb, [&](auto wc, auto sb) {

@@ -55,7 +55,16 @@ void run_ypass(ca_handle* h, cudaStream_t st) {
     if (h->KP == 1) {
       LaunchScope ls(h, "ypass", 1, st);
       dim3 grid(h->nCB, h->nRB);
-      if (h->variants & CA_VAR_YPASS4) {
+      if (h->ypass5 && std::is_same<T, uint8_t>::value) {
+        const int64_t tiles = (int64_t)h->nCB * h->nRB;
+        const unsigned g5 = (unsigned)std::min<int64_t>(tiles, (int64_t)h->num_sms);
+        if (h->y5_warps == 8)
+          CA_LAUNCH(k_ypass_k1_v5<8>, g5, 256, ypass5_smem_bytes(), st)((const uint8_t*)(const void*)Yp, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm,
+                                                                       h->rowpart, h->colpart);
+        else
+          CA_LAUNCH(k_ypass_k1_v5<16>, g5, 512, ypass5_smem_bytes(), st)((const uint8_t*)(const void*)Yp, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm,
+                                                                        h->rowpart, h->colpart);
+      } else if (h->variants & CA_VAR_YPASS4) {
         const int64_t tiles = (int64_t)h->nCB * h->nRB;
         // persistent grid: 2 CTAs per SM (64 KB rings); fp32 storage has 128 KB rings: one per SM
         const int per_sm = std::is_same<T, float>::value ? 1 : 2;

@@ -591,6 +591,234 @@ k_ypass_k1_v4(const T* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, in
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// k_ypass_k1_v5 (variant YPASS5, u8 storage): the two products of the Y pass on the INTEGER tensor pipe.
+// The co-scheduled timeline of round 2 (profiles/r02_notes.md section 3b) shows the step bound by instruction issue, and the
+// Y pass owns 74 % of the step's warp instructions: byte-wise arithmetic on the FMA pipe costs one PRMT and half a packed FMA
+// per count and product.  Both products are exact integer contractions once the fp32 operand is written in base-128 digits:
+//     w_g   = 2^e_w   sum_d D_d(g) 2^(-6 - 7 d),   psi_n = 2^e_psi sum_d P_d(n) 2^(-6 - 7 d),   D_d, P_d in [-64, 64], d = 0 .. 3
+// (four digits: absolute error 2^-28 of the tile's power-of-two scale -- finer than an fp32 ulp of the largest operand and
+// than the rounding of an fp32 accumulation chain; the digit recursion y -> rint(y), 128 (y - rint(y)) is exact in fp32), so
+//     (Y W)_n     = 2^e_w   sum_d 2^(-6 - 7 d) [ sum_g y_ng D_d(g) ]      mma.sync m16n8k32: A = Y tile (u8), B = W digits (s8)
+//     (Y^T psi)_g = 2^e_psi sum_d 2^(-6 - 7 d) [ sum_n y_ng P_d(n) ]      A = Y tile TRANSPOSED (ldmatrix.trans + 4 PRMT per
+//                                                                        512 counts regroup bytes by gene), B = psi digits
+// with s32 accumulation (bounds: 255 * 64 * 256 columns resp. * 4 096 rows < 2^27).  Per 512 counts a warp issues ~10
+// instructions instead of ~55, the results do not depend on the order of accumulation at all, and the FMA / ALU pipes stay
+// free for the kernels that run next to the pass.  One persistent CTA per SM (8 warps, <= 128 registers, 161 KB): the other
+// half of the register file and 66 KB of shared memory are left to the per-cell kernel and the gene-level launches.
+//   tile    = kY5Cols (2 048) columns x RB rows (multiple of 32, <= kY5MaxRows); warp w owns columns [256 w, 256 w + 256)
+//   ring    = 2 stages x 32 rows x (2 048 + 16) bytes: a row is one bulk copy (TMA engine); the 16-byte skew puts the 8 rows
+//             of an ldmatrix tile on distinct banks; one mbarrier per stage, the block barrier behind a stage's row sums frees it
+//   stage   = 2 x 8 (ldmatrix + mma) for the row sums of its 32 rows, 16 x (ldmatrix.trans + 4 PRMT + mma) for the column sums
+// Rows of a stage beyond the tile have psi digits 0 (stale ring contents times 0), columns beyond G have W digits 0.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kY5Cols = 2048, kY5StageRows = 32, kY5Stages = 2, kY5Pitch = kY5Cols + 16, kY5MaxRows = 2048;
+inline size_t ypass5_smem_bytes() {
+  return (size_t)kY5Stages * kY5StageRows * kY5Pitch + (size_t)(kY5MaxRows / 32) * 128 + 8 * kY5Stages + 16;
+}
+// power of two >= |v| (v finite): exponent arithmetic only
+__device__ __forceinline__ float y5_pow2_ceil(float amax) {
+  if (!(amax > 0.f)) return 1.f;
+  int e = ((__float_as_int(amax) >> 23) & 0xff) + 1;            // 2^(e - 127) > amax
+  e = e > 254 ? 254 : e;
+  return __int_as_float(e << 23);
+}
+// digit d (0 .. 3) of x in [-1, 1]: y_0 = 64 x, D = rint(y), y <- 128 (y - D)
+__device__ __forceinline__ int y5_digit(float x, int d) {
+  float y = x * 64.f;
+  float D = rintf(y);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < d) { y = (y - D) * 128.f; D = rintf(y); }
+  }
+  return (int)D;
+}
+// NW warps per CTA (8: 128 registers each, 16: 64 -- twice the warps to hide the ldmatrix -> mma latency next to other kernels)
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 2)
+k_ypass_k1_v5(const uint8_t* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, int nCB, int nRB, const float* __restrict__ U,
+              const float* __restrict__ Vm, float* __restrict__ rowpart, float* __restrict__ colpart) {
+  CA_DYNAMIC_SMEM(unsigned char, ring5);
+  unsigned char* ring = ring5;                                                                   // [stage][row][kY5Pitch]
+  uint2* psd = reinterpret_cast<uint2*>(ring5 + (size_t)kY5Stages * kY5StageRows * kY5Pitch);      // [32-row block][digit][t]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring5 + (size_t)kY5Stages * kY5StageRows * kY5Pitch + (size_t)(kY5MaxRows / 32) * 128);
+  constexpr int kY5WarpCols = kY5Cols / NW, kY5KB = kY5WarpCols / 32, kY5GB = kY5WarpCols / 16, kThreads = NW * 32;
+  __shared__ double red[2][NW][kY5StageRows];
+  __shared__ float sred[NW];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;                           // fragment coordinates (groupID, threadID_in_group)
+  for (int i = tid; i < kY5Stages * kY5StageRows * kY5Pitch / 16; i += kThreads) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0)
+    for (int st = 0; st < kY5Stages; ++st) bar_init(bars + st, 1);
+  fence_bar_init();
+  fence_proxy_async();
+  __syncthreads();
+  uint32_t ph = 0;
+  const int64_t ntiles = (int64_t)nCB * nRB;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int cb = (int)(tile % nCB);
+    const int64_t rb = tile / nCB;
+    const int64_t tcol0 = (int64_t)cb * kY5Cols;
+    const int64_t avail = ldY - tcol0;
+    const uint32_t tbytes = avail < (int64_t)kY5Cols ? (uint32_t)avail : (uint32_t)kY5Cols;
+    const int64_t rbeg = rb * RB, rend = (rbeg + RB < N) ? rbeg + RB : N;
+    const int nrows = (int)(rend - rbeg);
+    const int nstages = (nrows + kY5StageRows - 1) / kY5StageRows;
+    const uint8_t* ybase = Y + rbeg * ldY + tcol0;
+    // stage group sg -> ring stage sg % kY5Stages; issued by the 32 lanes of warp 0, one row each (a single issuing thread
+    // is a bottleneck of its own: ~80 cycles per bulk copy, measured)
+    auto issue = [&](int sg) {
+      if (sg >= nstages) return;
+      const int st = sg % kY5Stages;
+      const int r0 = sg * kY5StageRows;
+      const int nv = nrows - r0 < kY5StageRows ? nrows - r0 : kY5StageRows;
+      if (lane == 0) bar_arm(bars + st, (uint32_t)nv * tbytes);
+      __syncwarp();
+      if (lane < nv) bulk_copy(ring + ((size_t)st * kY5StageRows + lane) * kY5Pitch, ybase + (int64_t)(r0 + lane) * ldY, tbytes, bars + st);
+    };
+    if (wid == 0)
+      for (int sg = 0; sg < kY5Stages; ++sg) issue(sg);
+    CA_SYNC_AFTER_SYNCHRONOUS_COPY();
+    // ---- per-tile operands (computed while the first stages travel): scales, W digit fragments, psi digit table ----
+    float wm = 0.f, pm = 0.f;
+    // (a NaN / infinite operand turns the maximum into +inf: fmaxf alone would drop a NaN)
+    const float kInf = __int_as_float(0x7f800000);
+    for (int c = tid; c < kY5Cols; c += kThreads) {
+      const int64_t col = tcol0 + c;
+      if (col < G) { const float v = fabsf(Vm[col]); wm = (v <= 3.0e38f) ? fmaxf(wm, v) : kInf; }
+    }
+    for (int r = tid; r < nrows; r += kThreads) { const float v = fabsf(U[rbeg + r]); pm = (v <= 3.0e38f) ? fmaxf(pm, v) : kInf; }
+    wm = warp_max(wm); pm = warp_max(pm);
+    __syncthreads();                                                 // sred / psd of the previous tile are no longer read
+    if (lane == 0) sred[wid] = wm;
+    __syncthreads();
+    wm = sred[0];
+#pragma unroll
+    for (int i = 1; i < NW; ++i) wm = fmaxf(wm, sred[i]);
+    __syncthreads();
+    if (lane == 0) sred[wid] = pm;
+    __syncthreads();
+    pm = sred[0];
+#pragma unroll
+    for (int i = 1; i < NW; ++i) pm = fmaxf(pm, sred[i]);
+    const float sw = y5_pow2_ceil(wm), sp = y5_pow2_ceil(pm);        // NaN operands: scale 1, digits of NaN are garbage -> results
+    const float isw = 1.f / sw, isp = 1.f / sp;                      // are flagged below
+    const bool bad = !(wm <= 3.0e38f) || !(pm <= 3.0e38f);           // NaN / inf in W or psi: the partials of the tile are NaN
+    // W digits of this warp's 256 columns as B fragments: bw[kb][0] = digit g of columns 32 kb + 4 t .. + 3, [1]: + 16
+    uint32_t bw[kY5KB][2];
+#pragma unroll
+    for (int kb = 0; kb < kY5KB; ++kb) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk = 0u;
+        if (g < 4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int64_t col = tcol0 + wid * kY5WarpCols + kb * 32 + h * 16 + t * 4 + j;
+            const int D = col < G ? y5_digit(Vm[col] * isw, g) : 0;
+            pk |= ((uint32_t)D & 0xffu) << (8 * j);
+          }
+        }
+        bw[kb][h] = pk;
+      }
+    }
+    // psi digits of the tile's rows, laid out as the B fragments of the column-sum products: block k (32 rows), digit d, lane
+    // coordinate t: word 0 = digit d of rows (2 t, 2 t + 1, 8 + 2 t, 9 + 2 t), word 1 = rows (16 + 2 t, 17 + 2 t, 24 + 2 t, 25 + 2 t)
+    for (int it = tid; it < nstages * 16; it += kThreads) {
+      const int k = it >> 4, d = (it >> 2) & 3, tt = it & 3;
+      uint32_t w2[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = k * 32 + h * 16 + (j >> 1) * 8 + 2 * tt + (j & 1);
+          const int D = r < nrows ? y5_digit(U[rbeg + r] * isp, d) : 0;
+          pk |= ((uint32_t)D & 0xffu) << (8 * j);
+        }
+        w2[h] = pk;
+      }
+      psd[it] = make_uint2(w2[0], w2[1]);
+    }
+    __syncthreads();
+    int cacc[kY5GB][4];                                            // column sums: blocks of 16 genes x (digit columns)
+#pragma unroll
+    for (int gb = 0; gb < kY5GB; ++gb)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cacc[gb][i] = 0;
+    for (int sg = 0; sg < nstages; ++sg) {
+      const int st = sg % kY5Stages;
+      bar_wait(bars + st, (ph >> st) & 1u);
+      ph ^= 1u << st;
+      const unsigned char* sbase = ring + (size_t)st * kY5StageRows * kY5Pitch + wid * kY5WarpCols;
+      // ---- row sums: 2 halves of 16 rows x 8 blocks of 32 columns ----
+      int racc[2][4];
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) racc[rh][i] = 0;
+        const unsigned char* ap = sbase + (size_t)(rh * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kY5Pitch + 16 * (lane >> 4);
+#pragma unroll
+        for (int kb = 0; kb < kY5KB; ++kb) {
+          uint32_t a[4];
+          ldmatrix_x4(a, ap + kb * 32);
+          mma_u8s8(racc[rh], a, bw[kb][0], bw[kb][1]);
+        }
+      }
+      // ---- column sums: 16 blocks of 16 genes x the 32 rows of the stage ----
+      const uint2 pb = (g < 4) ? psd[sg * 16 + g * 4 + t] : make_uint2(0u, 0u);
+      const unsigned char* tp = sbase + (size_t)lane * kY5Pitch;
+#pragma unroll
+      for (int gb = 0; gb < kY5GB; ++gb) {
+        uint32_t r[4], a[4];
+        ldmatrix_x4_trans(r, tp + gb * 16);
+        a[0] = __byte_perm(r[0], r[1], 0x6420u);                   // gene 2 g   : rows (2 t, 2 t + 1, 8 + 2 t, 9 + 2 t)
+        a[1] = __byte_perm(r[0], r[1], 0x7531u);                   // gene 2 g + 1
+        a[2] = __byte_perm(r[2], r[3], 0x6420u);                   // rows (16 + 2 t, ...)
+        a[3] = __byte_perm(r[2], r[3], 0x7531u);
+        mma_u8s8(cacc[gb], a, pb.x, pb.y);
+      }
+      // ---- row sums of the stage: digits -> value, lanes t = 0 (digits 0, 1) + t = 1 (digits 2, 3), then over the warps ----
+      const int buf = sg & 1;
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        const double s0 = t == 0 ? 0.015625 : (t == 1 ? 9.5367431640625e-07 : 0.0);                 // 2^-6, 2^-20
+        const double s1 = t == 0 ? 0.0001220703125 : (t == 1 ? 7.450580596923828e-09 : 0.0);       // 2^-13, 2^-27
+        double lo = (double)racc[rh][0] * s0 + (double)racc[rh][1] * s1;                           // row g
+        double hi = (double)racc[rh][2] * s0 + (double)racc[rh][3] * s1;                           // row g + 8
+        lo += __shfl_xor_sync(CA_FULL, lo, 1);
+        hi += __shfl_xor_sync(CA_FULL, hi, 1);
+        if (t == 0) { red[buf][wid][rh * 16 + g] = lo; red[buf][wid][rh * 16 + g + 8] = hi; }
+      }
+      __syncthreads();
+      // every warp has consumed the stage (its ldmatrix results are in registers): refill it with the stage after next
+      if (wid == 0) issue(sg + kY5Stages);
+      if (tid < kY5StageRows && sg * kY5StageRows + tid < nrows) {
+        double acc = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) acc += red[buf][w][tid];
+        rowpart[(int64_t)cb * N + rbeg + sg * kY5StageRows + tid] = bad ? __int_as_float(0x7fc00000) : (float)(acc * (double)sw);
+      }
+    }
+    // ---- column sums of the tile: digits -> value (lanes t = 0, 1), gene 2 g and 2 g + 1 of every block ----
+#pragma unroll
+    for (int gb = 0; gb < kY5GB; ++gb) {
+      const double s0 = t == 0 ? 0.015625 : (t == 1 ? 9.5367431640625e-07 : 0.0);
+      const double s1 = t == 0 ? 0.0001220703125 : (t == 1 ? 7.450580596923828e-09 : 0.0);
+      double ev = (double)cacc[gb][0] * s0 + (double)cacc[gb][1] * s1;                             // gene 16 gb + 2 g
+      double od = (double)cacc[gb][2] * s0 + (double)cacc[gb][3] * s1;                             // gene 16 gb + 2 g + 1
+      ev += __shfl_xor_sync(CA_FULL, ev, 1);
+      od += __shfl_xor_sync(CA_FULL, od, 1);
+      if (t == 0) {
+        const int64_t col = tcol0 + wid * kY5WarpCols + gb * 16 + 2 * g;
+        if (col < G) colpart[rb * G + col] = bad ? __int_as_float(0x7fc00000) : (float)(ev * (double)sp);
+        if (col + 1 < G) colpart[rb * G + col + 1] = bad ? __int_as_float(0x7fc00000) : (float)(od * (double)sp);
+      }
+    }
+    __syncthreads();                                                 // red / psd / sred are reused by the next tile
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Batched Y pass for R fits that share one count matrix (restarts of run_clonealign on one device):
 // ONE stream over Y produces (Y W_r, Y^T psi_r) for every fit r -- the widening / magic-number work is shared and the
 // matrix leaves HBM once instead of R times.  Same tiling and partial layouts as k_ypass_k1_v2 (each fit's own rowpart /

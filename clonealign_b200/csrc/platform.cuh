@@ -70,6 +70,23 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
+// ---- warp-level matrix primitives of the integer Y pass (k_ypass_k1_v5): ldmatrix + mma.sync m16n8k32 u8 x s8 -> s32 ---------
+constexpr bool kImmaAvailable = true;
+// four 8 x 8 tiles of 16-bit elements; lane l supplies the address of row (l % 8) of tile (l / 8) (16 bytes, 16-byte aligned)
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(ptx::smem_u32(smem_row)) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(ptx::smem_u32(smem_row)) : "memory");
+}
+// C (16 x 8, s32) += A (16 x 32, u8, row-major fragment) * B (32 x 8, s8, column-major fragment)
+__device__ __forceinline__ void mma_u8s8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // the same, on generic pointers (what the Y pass uses)
 __device__ __forceinline__ void bar_init(uint64_t* bar, int count) { ptx::mbar_init(ptx::smem_u32(bar), (uint32_t)count); }
 __device__ __forceinline__ void bar_arm(uint64_t* bar, uint32_t bytes) { ptx::mbar_expect_tx(ptx::smem_u32(bar), bytes); }

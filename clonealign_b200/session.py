@@ -26,7 +26,7 @@ _STORE = {"auto": _lib.STORE_AUTO, "f32": _lib.STORE_F32, "u16": _lib.STORE_U16,
 _PATH = {"auto": _lib.PATH_AUTO, "cudacore": _lib.PATH_CUDACORE, "tensor": _lib.PATH_TENSOR, "interp": _lib.PATH_INTERP}
 _VARIANT = {"ypass2": _lib.VAR_YPASS2, "epi2": _lib.VAR_EPI2, "lean": _lib.VAR_LEAN, "p2p": _lib.VAR_P2P,
             "overlap": _lib.VAR_OVERLAP, "ypass3": _lib.VAR_YPASS3, "defer": _lib.VAR_DEFER, "ypass4": _lib.VAR_YPASS4,
-            "cosched": _lib.VAR_COSCHED, "cell2": _lib.VAR_CELL2}
+            "cosched": _lib.VAR_COSCHED, "cell2": _lib.VAR_CELL2, "ypass5": _lib.VAR_YPASS5}
 
 
 def variant_mask(variants) -> int:

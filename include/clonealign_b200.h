@@ -97,9 +97,11 @@ enum ca_path     { CA_PATH_AUTO = 0, CA_PATH_CUDACORE = 1, CA_PATH_TENSOR = 2, C
  *   CELL2 : (with EPI2 + LEAN + DEFER; takes effect for S <= 8) second-generation per-cell / per-gene kernels, see kernels_cell.cuh:
  *           lane = (cell, clone) resp. (gene, clone), Horner evaluation of the interpolants in the monomial basis, the w-weighted
  *           columns taken from the derivative of the interpolants (node sums over the S*C normaliser columns only), the gene kernel
- *           in front of the Y-pass join, the gamma-logit Adam update inside the per-cell kernel; part of the default set */
+ *           in front of the Y-pass join, the gamma-logit Adam update inside the per-cell kernel; part of the default set
+ *   YPASS5: (takes effect with YPASS4 and counts stored as u8) the two products of the Y pass as exact integer contractions on
+ *           the tensor pipe (mma.sync u8 x s8 on base-128 digits of W and psi), one persistent CTA per SM, see kernels_ypass.cuh */
 enum ca_variant  { CA_VAR_YPASS2 = 1, CA_VAR_EPI2 = 2, CA_VAR_LEAN = 4, CA_VAR_P2P = 8, CA_VAR_OVERLAP = 16, CA_VAR_YPASS3 = 32, CA_VAR_DEFER = 64,
-                   CA_VAR_YPASS4 = 128, CA_VAR_COSCHED = 256, CA_VAR_CELL2 = 512 };
+                   CA_VAR_YPASS4 = 128, CA_VAR_COSCHED = 256, CA_VAR_CELL2 = 512, CA_VAR_YPASS5 = 1024 };
 
 typedef struct ca_config {
   int64_t N;            /* cells held by this handle (this rank's shard)                       */

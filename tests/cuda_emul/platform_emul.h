@@ -21,6 +21,12 @@ inline void ca_emul_check_aligned(const void* a, const void* b, unsigned n, cons
 inline void cp_async16(void* smem_dst, const void* gmem_src) { ca_emul_check_aligned(smem_dst, gmem_src, 16, "cp.async 16"); std::memcpy(smem_dst, gmem_src, 16); }
 inline void cp_async8(void* smem_dst, const void* gmem_src) { ca_emul_check_aligned(smem_dst, gmem_src, 8, "cp.async 8"); std::memcpy(smem_dst, gmem_src, 8); }
 inline float rcp_approx(float x) { return 1.0f / x; }
+// the integer Y pass (ldmatrix + mma.sync) is not emulated: the host code never selects it when kImmaAvailable is false
+constexpr bool kImmaAvailable = false;
+inline void ca_emul_no_imma() { fprintf(stderr, "cuda_emul: ldmatrix / mma.sync are not emulated\n"); abort(); }
+inline void ldmatrix_x4(uint32_t (&)[4], const void*) { ca_emul_no_imma(); }
+inline void ldmatrix_x4_trans(uint32_t (&)[4], const void*) { ca_emul_no_imma(); }
+inline void mma_u8s8(int (&)[4], const uint32_t (&)[4], uint32_t, uint32_t) { ca_emul_no_imma(); }
 inline void cp_async_commit() {}
 template <int N> inline void cp_async_wait() {}
 inline void bar_init(uint64_t*, int) {}

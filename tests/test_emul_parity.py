@@ -602,7 +602,7 @@ def test_c3_column_structure(path):
         assert errs["Z"] < 5e-6
 
 
-@pytest.mark.parametrize("path", [("interp", ""), ("interp", "ypass2,epi2,lean")])
+@pytest.mark.parametrize("path", [("interp", ""), ("interp", "ypass2,epi2,lean"), ("auto", "")])
 def test_nan_parameters_give_nan_not_a_fault(example_sce, path):
     """A diverged fit (NaN in psi) must surface as a NaN ELBO, as in the reference (R/inference-tflow.R:411-412 lets NA
     ELBOs through after the first iteration) -- not as an out-of-range panel index in the interpolation tables."""

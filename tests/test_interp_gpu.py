@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 VARIANTS = ["", "ypass2", "epi2", "ypass2,epi2", "ypass2,epi2,lean", "ypass2,epi2,lean,overlap", "ypass3", "ypass3,epi2,lean",
             "ypass3,epi2,lean,defer", "ypass3,epi2,lean,defer,overlap", "ypass4", "ypass4,epi2,lean,defer", "ypass4,epi2,lean,defer,cosched",
-            "ypass4,epi2,lean,defer,cosched,cell2", "ypass2,epi2,lean,defer,cell2"]
+            "ypass4,epi2,lean,defer,cosched,cell2", "ypass2,epi2,lean,defer,cell2", "ypass4,epi2,lean,defer,cosched,cell2,ypass5"]
 
 
 @pytest.mark.parametrize("variants", VARIANTS)
@@ -31,7 +31,8 @@ def test_interp_gradients_and_elbo_match_oracle_c1(example_sce, S, variants):
 
 
 @pytest.mark.parametrize("variants", ["", "ypass2,epi2", "ypass2,epi2,lean", "ypass3,epi2,lean", "ypass3,epi2,lean,defer,overlap",
-                                      "ypass4,epi2,lean,defer,cosched", "ypass4,epi2,lean,defer,cosched,cell2"])
+                                      "ypass4,epi2,lean,defer,cosched", "ypass4,epi2,lean,defer,cosched,cell2",
+                                      "ypass4,epi2,lean,defer,cosched,cell2,ypass5"])
 @pytest.mark.parametrize("N,G,C,S", [(130, 70, 5, 3), (257, 193, 2, 1), (64, 640, 7, 8), (1000, 333, 12, 8), (300, 4100, 32, 4)])
 def test_interp_ragged_shapes(N, G, C, S, variants):
     from clonealign_b200.synthetic import make_synthetic
@@ -230,7 +231,8 @@ def _full_size_check(N, G, C, S, path, variants, V=0, n_sample=48, z_tol=2e-6, w
 
 
 @pytest.mark.parametrize("variants", ["", "ypass2,epi2,lean", "ypass3,epi2,lean", "ypass3,epi2,lean,defer,overlap",
-                                      "ypass4,epi2,lean,defer,cosched", "ypass4,epi2,lean,defer,cosched,cell2"])
+                                      "ypass4,epi2,lean,defer,cosched", "ypass4,epi2,lean,defer,cosched,cell2",
+                                      "ypass4,epi2,lean,defer,cosched,cell2,ypass5"])
 def test_full_size_c3_interp(variants):
     """BASELINE config 3 (100k x 20k x 12, S = 8) on the interpolation path: Z is near-exact (fp64 node sums), unlike the
     tcgen05 path's round-toward-zero accumulation."""
