@@ -325,15 +325,16 @@ int ca_core_params(ca_handle* h, double* mu, double* clone_probs, double* s, dou
       download_colmajor(h, h->loc, G, 1, 1, 0, tmp.data());
       for (int g = 0; g < G; ++g) { double x = tmp[g]; mu[g] = x > 0 ? x + log1p(exp(-x)) : log1p(exp(x)); }
     }
-    if (clone_probs) {   // softmax(gamma_logits), :273,424
+    if (clone_probs) {   // softmax(gamma_logits), :273,424 -- on the device (2.4 M host exp() calls took longer than the whole fit loop of the e2e bench)
+      if (!h->cp_scratch) h->cp_scratch = h->alloc<double>((size_t)N * C, false);   // kept for the session (no allocation / free per call)
+      double* d_cp = h->cp_scratch;
+      CA_LAUNCH(k_softmax_rows_f64, (unsigned)ceil_div64(N, 128), 128, 0, h->stream)(h->t, N, C, d_cp);
+      KCHECK();
       std::vector<double> tmp((size_t)N * C);
-      download_colmajor(h, h->t, N, C, C, 0, tmp.data());
-      for (int64_t n = 0; n < N; ++n) {
-        double mx = -1e300, z = 0;
-        for (int c = 0; c < C; ++c) mx = std::max(mx, tmp[(size_t)c * N + n]);
-        for (int c = 0; c < C; ++c) z += exp(tmp[(size_t)c * N + n] - mx);
-        for (int c = 0; c < C; ++c) clone_probs[(size_t)c * N + n] = exp(tmp[(size_t)c * N + n] - mx) / z;
-      }
+      CUDA_OK(cudaMemcpyAsync(tmp.data(), d_cp, sizeof(double) * (size_t)N * C, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_OK(cudaStreamSynchronize(h->stream));
+      for (int c = 0; c < C; ++c)
+        for (int64_t n = 0; n < N; ++n) clone_probs[(size_t)c * N + n] = tmp[(size_t)n * C + c];
     }
     if (s) download_colmajor(h, h->s, N, 1, 1, 0, s);
     if (alpha) {   // exp(log_softmax(alpha_unconstr))

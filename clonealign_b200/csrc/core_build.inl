@@ -236,8 +236,21 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     h->snv = d->snv; h->const_sum = d->const_sum; h->poison = d->poison;
     if (h->ldY != d->ldY) fail("shared inputs: leading dimension mismatch");
   } else {
+  // Row-major u8 counts that are to be stored as u8 go straight into their final array: one 2-D copy, no fp32 staging matrix
+  // (4 x the bytes, an 8 GB allocation at config 3), no widening / scan / narrowing passes; the set-up reductions read the bytes.
+  const bool compact_u8 = c.y_dtype == CA_Y_U8 && c.y_layout == CA_Y_ROWMAJOR && (c.y_store == CA_STORE_AUTO || c.y_store == CA_STORE_U8);
+  uint8_t* Yc = nullptr;
+  float* Yf = nullptr;
+  if (compact_u8) {
+    Yc = h->alloc<uint8_t>((size_t)N * h->ldY, h->ldY != G);          // (the padding columns must read as zero)
+    const int64_t ld = c.y_ld ? c.y_ld : G;
+    CUDA_OK(cudaMemcpy2DAsync(Yc, (size_t)h->ldY, Y, (size_t)ld, (size_t)G, (size_t)N,
+                              c.y_mem == CA_Y_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    h->ystore = CA_STORE_U8;
+    h->Y = Yc;
+  } else {
   // ---- Y -> device fp32 [N][ldY] ----
-  float* Yf = h->alloc<float>((size_t)N * h->ldY);
+  Yf = h->alloc<float>((size_t)N * h->ldY);
   switch (c.y_dtype) {
     case CA_Y_F64: ingest_y<double>(h, (const double*)Y, Yf); break;
     case CA_Y_F32: ingest_y<float>(h, (const float*)Y, Yf); break;
@@ -266,6 +279,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if (want == CA_STORE_U16 && (hflags & 5)) fail("y_store = u16 requested but Y has non-integer, negative or > 65535 entries");
   h->ystore = want;
   h->Y = Yf;
+  }   // !compact_u8
 
   // ---- small inputs ----
   h->L = h->alloc<float>((size_t)G * C);
@@ -286,7 +300,8 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   h->s = h->alloc<float>(N);
   h->colsum = h->alloc<float>(G);
   double* cst = h->alloc<double>(N);
-  CA_LAUNCH(k_setup_rows<float>, (unsigned)N, 256, 0, h->stream)(Yf, h->ldY, N, G, C, d_logL, h->s, cst, h->Bm);
+  if (compact_u8) CA_LAUNCH(k_setup_rows<uint8_t>, (unsigned)N, 256, 0, h->stream)(Yc, h->ldY, N, G, C, d_logL, h->s, cst, h->Bm);
+  else CA_LAUNCH(k_setup_rows<float>, (unsigned)N, 256, 0, h->stream)(Yf, h->ldY, N, G, C, d_logL, h->s, cst, h->Bm);
   KCHECK();
   {
     double* csum = h->alloc<double>(1);
@@ -310,7 +325,8 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     double* part = h->alloc<double>((size_t)RS * G);
     double* tot = h->alloc<double>(G);
     dim3 grid((G + 127) / 128, RS);
-    CA_LAUNCH(k_colsum_part<float>, grid, 128, 0, h->stream)(Yf, h->ldY, N, G, RS, part);
+    if (compact_u8) CA_LAUNCH(k_colsum_part<uint8_t>, grid, 128, 0, h->stream)(Yc, h->ldY, N, G, RS, part);
+    else CA_LAUNCH(k_colsum_part<float>, grid, 128, 0, h->stream)(Yf, h->ldY, N, G, RS, part);
     KCHECK();
     CA_LAUNCH(k_colsum_final, (G + 127) / 128, 128, 0, h->stream)(part, RS, G, h->colsum, tot);
     KCHECK();
@@ -342,7 +358,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     h->release(d_cn);
   }
   // narrow Y after the setup passes that read it as fp32
-  if (h->ystore != CA_STORE_F32) {
+  if (!compact_u8 && h->ystore != CA_STORE_F32) {
     dim3 grid(std::min<int64_t>((h->ldY + 255) / 256, 64), 1);
     void* Yn = nullptr;
     if (h->ystore == CA_STORE_U16) Yn = h->alloc<uint16_t>((size_t)N * h->ldY, false);

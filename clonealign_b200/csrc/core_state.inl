@@ -88,6 +88,7 @@ struct ca_handle {
   int64_t n_epi_blocks = 0;
   bool ydirty = true;
   bool t_done = false;             // the per-cell kernel of the step in flight has updated the gamma logits itself
+  double* cp_scratch = nullptr;    // ca_core_params: clone_probs [N][C] in fp64 before the download
   bool apply_now = false;          // the train step in flight applies its updates (false: ca_core_grads)
   bool inspect = false;            // test hook (ca_core_grads): also write inspection-only arrays (Z of the fused kernel)
   TcPlan tcplan;

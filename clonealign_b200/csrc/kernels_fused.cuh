@@ -591,36 +591,57 @@ __global__ void __launch_bounds__(256) k_adam_all(AdamAllArgs a) {
     const GeneAdamArgs& q = a.ga;
     const int g = (int)b * blockDim.x + threadIdx.x;
     if (g >= q.G) return;
+    // This launch is all that is left behind the Y-pass join and it is a chain of dependent loads (ncu of round 2: 21 us for
+    // 1.3e6 instructions): everything a gene needs is requested up front -- the first column partials, then the samples in
+    // batches of 8 -- instead of one round trip per sample and per 8 partials.
+    float cpv[8];
+    if (a.colpart) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cpv[u] = u < a.nRB ? a.colpart[(int64_t)u * q.G + g] : 0.f;
+    }
     const float lsd = q.lsd[g];
+    const float ar0 = q.ar[g], ar1 = q.ar[q.G + g], ar2 = q.ar[2 * (int64_t)q.G + g], wg = q.Vm[g];
     const double sd = exp((double)lsd), cs = (double)q.colsum[g];
-    double gl = (double)q.ar[g], gs = (double)q.ar[q.G + g];
-    for (int s = 0; s < q.S; ++s) {
-      const int64_t o = (int64_t)s * q.G + g;
-      const double mu = (double)q.mu[o], sg = (double)q.sig[o];
-      const double dmu = (cs - (double)q.logmu[o]) / ((double)q.S * mu);
-      const double dx = sg * dmu + (1.0 - sg) / (double)q.S;
-      gl += dx;
-      gs += dx * sd * (double)q.eps[o];
+    double gl = (double)ar0, gs = (double)ar1;
+    for (int s0 = 0; s0 < q.S; s0 += 8) {
+      float mu8[8], sg8[8], lm8[8], ep8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t o = (int64_t)(s0 + i < q.S ? s0 + i : q.S - 1) * q.G + g;
+        mu8[i] = q.mu[o]; sg8[i] = q.sig[o]; lm8[i] = q.logmu[o]; ep8[i] = q.eps[o];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (s0 + i < q.S) {
+          const double mu = (double)mu8[i], sg = (double)sg8[i];
+          const double dmu = (cs - (double)lm8[i]) / ((double)q.S * mu);
+          const double dx = sg * dmu + (1.0 - sg) / (double)q.S;
+          gl += dx;
+          gs += dx * sd * (double)ep8[i];
+        }
+      }
     }
     gs += 1.0;
     const float gloc = (float)gl, glsd = (float)gs;
     q.g_loc[g] = gloc;
     q.g_lsd[g] = glsd;
     double ytu = 0.0;
-    if (a.colpart) {   // fixed order: 8 partials in flight, row blocks ascending
+    if (a.colpart) {   // fixed order: row blocks ascending, 16 partials in flight
       const float* cp = a.colpart + g;
-      int rb = 0;
-      for (; rb + 8 <= a.nRB; rb += 8) {
-        float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = cp[(int64_t)(rb + u) * q.G];
+      for (int u = 0; u < 8; ++u) ytu += (double)cpv[u];
+      int rb = 8;
+      for (; rb + 16 <= a.nRB; rb += 16) {
+        float v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) ytu += (double)v[u];
+        for (int u = 0; u < 16; ++u) v[u] = cp[(int64_t)(rb + u) * q.G];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) ytu += (double)v[u];
       }
       for (; rb < a.nRB; ++rb) ytu += (double)cp[(int64_t)rb * q.G];
       a.YtU[g] = (float)ytu;
     }
-    const float gw = (float)((double)q.ar[2 * (int64_t)q.G + g] + ytu - a.chi_cur[0] * (double)q.Vm[g]);   // K == 1, P == 0
+    const float gw = (float)((double)ar2 + ytu - a.chi_cur[0] * (double)wg);   // K == 1, P == 0
     q.g_V[g] = gw;
     if (q.h.apply) {
       adam_update(q.loc[g], q.m_loc[g], q.v_loc[g], gloc, q.h);

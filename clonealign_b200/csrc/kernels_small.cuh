@@ -128,6 +128,17 @@ __global__ void k_softmax_rows(const float* __restrict__ in, int64_t N, int C, f
   for (int c = 0; c < C; ++c) out[n * C + c] = (float)(exp((double)in[n * C + c] - mx) / z);
 }
 
+// clone_probs = softmax(gamma_logits) (R/inference-tflow.R:273,424) in fp64 from the fp32 logits, [N][C] row-major
+__global__ void k_softmax_rows_f64(const float* __restrict__ in, int64_t N, int C, double* __restrict__ out) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double mx = -1e300;
+  for (int c = 0; c < C; ++c) mx = fmax(mx, (double)in[n * C + c]);
+  double z = 0.0;
+  for (int c = 0; c < C; ++c) z += exp((double)in[n * C + c] - mx);
+  for (int c = 0; c < C; ++c) out[n * C + c] = exp((double)in[n * C + c] - mx) / z;
+}
+
 // =============================================================================================
 // post-hoc: per-gene Pearson correlation between expression and the copy number of the assigned clone
 // (compute_correlations, R/clonealign.R:318-334; cor(x, scale(y)) == cor(x, y)).  One pass over the resident Y.
