@@ -1,6 +1,6 @@
-// Variant CELL2 of the interp path (with EPI2 + LEAN + DEFER, S <= 8): the per-cell kernel re-laid-out from the round-2 ncu
-// source counters of k_cell_fused (kernels_fused.cuh): 1 110 warp instructions per cell at config 3, of which only 276
-// were the Clenshaw recurrences -- the rest was the lane = column mapping paying for itself: 38 shuffles, a shared-memory
+// Variant CELL2 of the interp path (with EPI2 + LEAN + DEFER, S <= 8): the per-cell and per-gene kernels re-laid-out from the
+// round-2 ncu source counters of k_cell_fused (kernels_fused.cuh): 1 110 warp instructions per cell at config 3, of which only
+// 276 were the Clenshaw recurrences -- the rest was the lane = column mapping paying for itself: 38 shuffles, a shared-memory
 // round trip of log Z to regroup (sample, clone) columns by clone, 12 of 32 lanes active in the clone softmax, an IEEE fp64
 // division, two library logarithms, 117 IMAD of address arithmetic.
 //
@@ -8,16 +8,22 @@
 //     owns ALL S samples of its clone.  sum_s log Z_scn, gamma_nc, R_scn and sum_s R Z' are then in-lane; the only
 //     cross-lane steps are the clone softmax and two sums over the WC lanes of a cell (log2 WC shuffle levels each).
 //   * the interpolants are evaluated in the MONOMIAL basis of the panel variable (Horner: one DFMA per coefficient instead
-//     of DADD + DFMA for Clenshaw; k_interp_coeffs2 converts the Chebyshev coefficients, kernels_interp.cuh), coefficients
+//     of DADD + DFMA for Clenshaw; k_interp_coeffs3 converts the Chebyshev coefficients, kernels_interp.cuh), coefficients
 //     staged as (a_2k, a_2k+1) pairs: one 16-byte shared-memory load per two Horner steps, at compile-time offsets from
-//     one per-lane base (table padded to [panel][pair][Z | Z'][SB samples][WC lanes]).
+//     one per-lane base (table padded to [panel][pair][SB samples][WC lanes]).
+//   * the w-weighted column Z'_sc = sum_g w_g M e^(psi w_g - m) is NOT interpolated: with m = psi w_ref linear on a side,
+//     Z' = dZ/dpsi + w_ref Z, and dZ/dpsi is the derivative of the interpolant, carried in the same Horner pass (each
+//     coefficient is loaded once and feeds p and dp/dt).  Half the node sums, half the table, half the shared-memory
+//     traffic of the kernel (which was bound by it: 4 wavefronts per 16-byte load of a warp); the same holds for
+//     dM' = d(dM)/dw in the gene kernel.  Accuracy: interp_make_plan(..., wide) in kernels_interp.cuh.
 //   * sum_s log Z_s = log prod_s Z_s: one split-exponent logarithm per 4 samples on the fp64 product instead of one per
 //     sample (absolute error 3.6e-7 per logarithm, see log_pos_f32 in kernels_fused.cuh).
-//   * gamma = e / sum e through a Newton-refined reciprocal (2 DFMA + 2 DMUL, relative error < 1e-15) instead of the
-//     IEEE division subroutine; exponentials in fp32, normalisation in fp64 as before (1 - gamma_max keeps its digits).
-//   * the per-cell inputs of the NEXT group of cells are requested before this group's recurrences start.
-// Outputs and their layouts are those of k_cell_fused (Rx [N][J], gT, gU without the Y-linear term, shift, per-block
-// partial sums in a fixed order), so the backward node kernel, the gene kernel and the optimiser are shared.
+//   * gamma = e / sum e through a Newton-refined hardware reciprocal (2 DFMA + 2 DMUL, relative error < 1e-15) instead of
+//     the IEEE division subroutine; exponentials in fp32, normalisation in fp64 as before (1 - gamma_max keeps its digits).
+//   * the per-cell inputs of the NEXT group of cells are requested before this group's recurrences start; the TF1-Adam
+//     update of the gamma logits is applied by the lane that computed the gradient.
+// Outputs: Rx [N][Jn] (Jn = S*C rounded up to even: R only), gT or the updated logits, gU without the Y-linear term, shift,
+// per-block partial sums in a fixed order; the backward node kernel and the optimiser are shared with the other kernel sets.
 // Math: SURVEY.md App. A.2/A.3; reference graph nodes R/inference-tflow.R:272-273,288-308,318-319,332-340.
 #pragma once
 #include "common.cuh"
