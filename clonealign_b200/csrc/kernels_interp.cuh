@@ -53,7 +53,29 @@ __device__ __forceinline__ void bwd_panel(const InterpPlan& pl, int pb, double& 
   half = 0.5 * pl.b_w;
   mid = pl.wmin + pb * pl.b_w + half;
 }
-__device__ __forceinline__ double cheb_node(int p) { return cos(kPi * (p + 0.5) / kIP); }
+// Chebyshev nodes cos(pi (p + 1/2) / 16) and the DCT matrix cos(pi k (q + 1/2) / 16) as correctly rounded literals (generated with
+// Python's math.cos; kIP == 16): the launches that need them are latency-bound, a double-precision cos() per thread at their start
+// is microseconds on the step's critical path
+static_assert(kIP == 16, "regenerate kChebNodeTable / kDctTable for another node count");
+static __device__ const double kChebNodeTable[kIP] = {0.9951847266721969, 0.9569403357322088, 0.881921264348355, 0.773010453362737, 0.6343932841636455, 0.4713967368259978, 0.29028467725446233, 0.09801714032956077, -0.09801714032956065, -0.29028467725446216, -0.4713967368259977, -0.6343932841636454, -0.773010453362737, -0.8819212643483549, -0.9569403357322088, -0.9951847266721968};
+static __device__ const double kDctTable[kIP][kIP] = {
+  {1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0},
+  {0.9951847266721969, 0.9569403357322088, 0.881921264348355, 0.773010453362737, 0.6343932841636455, 0.4713967368259978, 0.29028467725446233, 0.09801714032956077, -0.09801714032956065, -0.29028467725446216, -0.4713967368259977, -0.6343932841636454, -0.773010453362737, -0.8819212643483549, -0.9569403357322088, -0.9951847266721968},
+  {0.9807852804032304, 0.8314696123025452, 0.5555702330196023, 0.19509032201612833, -0.1950903220161282, -0.555570233019602, -0.8314696123025453, -0.9807852804032304, -0.9807852804032304, -0.8314696123025455, -0.5555702330196022, -0.19509032201612866, 0.1950903220161283, 0.5555702330196018, 0.8314696123025452, 0.9807852804032303},
+  {0.9569403357322088, 0.6343932841636455, 0.09801714032956077, -0.4713967368259977, -0.8819212643483549, -0.9951847266721969, -0.7730104533627371, -0.29028467725446244, 0.29028467725446205, 0.7730104533627367, 0.9951847266721969, 0.881921264348355, 0.471396736825998, -0.09801714032955997, -0.6343932841636448, -0.9569403357322085},
+  {0.9238795325112867, 0.38268343236508984, -0.3826834323650897, -0.9238795325112867, -0.9238795325112868, -0.38268343236509034, 0.38268343236509, 0.9238795325112865, 0.9238795325112867, 0.38268343236509045, -0.3826834323650899, -0.9238795325112864, -0.9238795325112867, -0.38268343236509056, 0.3826834323650898, 0.9238795325112864},
+  {0.881921264348355, 0.09801714032956077, -0.773010453362737, -0.9569403357322089, -0.29028467725446244, 0.6343932841636456, 0.9951847266721969, 0.471396736825998, -0.4713967368259975, -0.9951847266721969, -0.6343932841636454, 0.29028467725446266, 0.9569403357322085, 0.7730104533627377, -0.09801714032955972, -0.8819212643483547},
+  {0.8314696123025452, -0.1950903220161282, -0.9807852804032304, -0.5555702330196022, 0.5555702330196018, 0.9807852804032304, 0.19509032201612878, -0.8314696123025451, -0.8314696123025456, 0.1950903220161272, 0.9807852804032304, 0.5555702330196025, -0.5555702330196015, -0.9807852804032307, -0.19509032201613, 0.831469612302544},
+  {0.773010453362737, -0.4713967368259977, -0.9569403357322089, 0.09801714032956009, 0.9951847266721969, 0.29028467725446255, -0.8819212643483548, -0.6343932841636454, 0.6343932841636447, 0.8819212643483553, -0.29028467725446255, -0.9951847266721969, -0.0980171403295627, 0.9569403357322089, 0.4713967368259984, -0.7730104533627357},
+  {0.7071067811865476, -0.7071067811865475, -0.7071067811865477, 0.7071067811865474, 0.7071067811865477, -0.7071067811865467, -0.7071067811865471, 0.7071067811865466, 0.7071067811865472, -0.7071067811865465, -0.7071067811865474, 0.7071067811865464, 0.7071067811865475, -0.7071067811865464, -0.7071067811865476, 0.7071067811865462},
+  {0.6343932841636455, -0.8819212643483549, -0.29028467725446244, 0.9951847266721969, -0.09801714032955997, -0.9569403357322087, 0.47139673682599736, 0.7730104533627377, -0.773010453362737, -0.4713967368259983, 0.9569403357322089, 0.09801714032956282, -0.995184726672197, 0.2902846772544622, 0.8819212643483563, -0.6343932841636443},
+  {0.5555702330196023, -0.9807852804032304, 0.1950903220161283, 0.8314696123025455, -0.8314696123025451, -0.19509032201612803, 0.9807852804032307, -0.5555702330196015, -0.5555702330196026, 0.9807852804032304, -0.19509032201612858, -0.8314696123025449, 0.8314696123025438, 0.19509032201613036, -0.9807852804032308, 0.5555702330196011},
+  {0.4713967368259978, -0.9951847266721969, 0.6343932841636449, 0.2902846772544634, -0.9569403357322093, 0.7730104533627359, 0.09801714032956259, -0.8819212643483562, 0.8819212643483538, -0.0980171403295577, -0.773010453362739, 0.9569403357322078, -0.2902846772544587, -0.6343932841636487, 0.9951847266721965, -0.4713967368259935},
+  {0.38268343236508984, -0.9238795325112868, 0.9238795325112865, -0.3826834323650899, -0.38268343236509056, 0.9238795325112867, -0.9238795325112864, 0.38268343236508956, 0.3826834323650909, -0.9238795325112876, 0.9238795325112868, -0.3826834323650892, -0.3826834323650912, 0.9238795325112877, -0.9238795325112854, 0.38268343236508556},
+  {0.29028467725446233, -0.7730104533627369, 0.9951847266721968, -0.8819212643483556, 0.47139673682599736, 0.09801714032955905, -0.6343932841636456, 0.9569403357322084, -0.9569403357322089, 0.634393284163647, -0.09801714032956099, -0.47139673682599564, 0.8819212643483547, -0.9951847266721968, 0.7730104533627398, -0.29028467725446505},
+  {0.19509032201612833, -0.5555702330196022, 0.8314696123025455, -0.9807852804032307, 0.9807852804032304, -0.831469612302545, 0.5555702330196015, -0.19509032201612858, -0.19509032201613025, 0.5555702330196028, -0.831469612302545, 0.9807852804032309, -0.9807852804032297, 0.8314696123025456, -0.5555702330196007, 0.19509032201612425},
+  {0.09801714032956077, -0.2902846772544633, 0.471396736825998, -0.6343932841636467, 0.7730104533627377, -0.8819212643483562, 0.9569403357322094, -0.995184726672197, 0.9951847266721965, -0.9569403357322078, 0.8819212643483536, -0.7730104533627331, 0.6343932841636439, -0.47139673682599326, 0.2902846772544547, -0.09801714032955673}};
+__device__ __forceinline__ double cheb_node(int p) { return kChebNodeTable[p]; }
 
 // Chebyshev -> monomial basis of the panel variable t: T_k(t) = sum_m kT2M.v[k][m] t^m (integers up to 2^14 * 3.3, exact in
 // fp64; T_{k+1} = 2 t T_k - T_{k-1}).  The per-cell and per-gene kernels evaluate the interpolants by Horner's rule (one
@@ -308,7 +330,7 @@ k_interp_coeffs2(const InterpPlan* __restrict__ plan, const double* __restrict__
   const int64_t nodes_total = (int64_t)max_pan * kIP;
   if (threadIdx.x < kIP * kIP) {
     const int k = threadIdx.x / kIP, q = threadIdx.x % kIP;
-    ct[k][q] = cos(kPi * k * (q + 0.5) / kIP);
+    ct[k][q] = kDctTable[k][q];
     t2m[k][q] = kT2M.v[k][q];
   }
   for (int panel = blockIdx.y; panel < npan; panel += gridDim.y) {     // grid.y = kC2PanelsY: blocks stride over the active panels
@@ -381,7 +403,7 @@ k_interp_coeffs3(const InterpPlan* __restrict__ plan, const double* __restrict__
   const int64_t nodes_total = (int64_t)max_pan * kIP;
   if (threadIdx.x < kIP * kIP) {
     const int k = threadIdx.x / kIP, q = threadIdx.x % kIP;
-    ct[k][q] = cos(kPi * k * (q + 0.5) / kIP);
+    ct[k][q] = kDctTable[k][q];
     t2m[k][q] = kT2M.v[k][q];
   }
   constexpr int kStep = kC3Groups * kC2Lanes;                       // slices between two loads of a thread

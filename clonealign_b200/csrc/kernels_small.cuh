@@ -231,27 +231,38 @@ struct SampleMuArgs {
 template <bool VEC4>
 __device__ __forceinline__ void sample_mu_body(const SampleMuArgs& a, int block, int nblocks, double* scratch, double* part_out) {
   double etot = 0.0;
+  const double invS = 1.0 / (double)a.S;
   for (int64_t idx = (int64_t)block * blockDim.x + threadIdx.x; idx < (int64_t)a.S * a.G; idx += (int64_t)nblocks * blockDim.x) {
   const int s = (int)(idx / a.G), g = (int)(idx - (int64_t)s * a.G);
   double e = 0.0;
   {
     float loc = a.loc[g], lsd = a.lsd[g], sd = expf(lsd);
     double cs = (double)a.colsum[g];
+    // the weights of the gene: all K + P of them scale the contraction operand; without its w-scaled copy (CELL2 set) only
+    // the K of them that enter the prior are read, and only by the thread of sample 0
     float vk[kMaxKP];
+    if (a.no_w_half) {
 #pragma unroll
-    for (int kp = 0; kp < kMaxKP; ++kp) vk[kp] = kp < a.KP ? a.Vm[(int64_t)g * a.KP + kp] : 0.f;
+      for (int kp = 0; kp < kMaxKP; ++kp) vk[kp] = (s == 0 && kp < a.K) ? a.Vm[(int64_t)g * a.KP + kp] : 0.f;
+    } else {
+#pragma unroll
+      for (int kp = 0; kp < kMaxKP; ++kp) vk[kp] = kp < a.KP ? a.Vm[(int64_t)g * a.KP + kp] : 0.f;
+    }
     {
       float eps = a.eps_in ? a.eps_in[(int64_t)s * a.G + g] : normal_draw(a.seed, a.draw, (uint32_t)s, (uint32_t)g);
       float x = loc + sd * eps;
-      float mu = softplusf(x);
+      // softplus(x) = max(x, 0) + log1p(e^-|x|) and softplus(-x) = max(-x, 0) + the same logarithm: one expf / log1pf for
+      // both (bit-identical to two softplusf calls); sigmoid(x) from the same exponential
+      const float ex = expf(-fabsf(x)), l1 = log1pf(ex);
+      float mu = fmaxf(x, 0.f) + l1;
       float lm = logf(mu);
-      float sg = sigmoidf_(x);
+      float sg = x >= 0.f ? 1.0f / (1.0f + ex) : ex / (1.0f + ex);
       int64_t o = (int64_t)s * a.G + g;
       a.eps_out[o] = eps;
       a.mu[o] = mu;
       a.logmu[o] = lm;
       a.sig[o] = sg;
-      double lsg = -(double)softplusf(-x);   // log sigmoid(x)
+      double lsg = -(double)(fmaxf(-x, 0.f) + l1);   // log sigmoid(x) = -softplus(-x)
       e += cs * (double)lm - 0.5 * (double)lm * (double)lm - (-0.5 * (double)eps * (double)eps - (double)lsd - lsg);
       if (VEC4) {
         const float4* L4 = reinterpret_cast<const float4*>(a.L + (int64_t)g * a.C);
@@ -285,7 +296,7 @@ __device__ __forceinline__ void sample_mu_body(const SampleMuArgs& a, int block,
         }
       }
     }
-    e /= (double)a.S;
+    e *= invS;
     if (s == 0)
       for (int k = 0; k < a.K; ++k) {   // Normal(0, chi^-1/2) prior on W, R/inference-tflow.R:312-313 (once per gene)
         double cr = (double)a.chi_raw[k], w = (double)vk[k];
