@@ -8,7 +8,7 @@ import re
 import subprocess
 import sys
 
-COLS = ["UTCHMMA", "LDTM", "UTMALDG", "UBLKCP", "LDGSTS", "SYNCS", "FFMA2", "FADD2", "DFMA", "DADD", "MUFU", "PRMT", "SHFL", "LDS", "STS", "BAR"]
+COLS = ["UTCHMMA", "LDTM", "UTMALDG", "UBLKCP", "LDGSTS", "SYNCS", "IMMA", "LDSM", "FFMA2", "FADD2", "DFMA", "DADD", "MUFU", "PRMT", "SHFL", "LDS", "STS", "BAR"]
 
 
 def main():
@@ -30,7 +30,7 @@ def main():
             tot[op] += 1
     print(f"# SASS instruction mnemonics per kernel of `{lib.split('/')[-1]}`\n")
     print("`cuobjdump -sass`, static counts per function (not executed counts).  `UTCHMMA` = tcgen05.mma, `LDTM` = tcgen05.ld, `UTMALDG` = TMA tensor load,")
-    print("`UBLKCP` = cp.async.bulk (TMA engine, 1-D), `LDGSTS` = cp.async, `SYNCS` = mbarrier ops, `FFMA2` / `FADD2` = packed fp32 pairs.\n")
+    print("`UBLKCP` = cp.async.bulk (TMA engine, 1-D), `LDGSTS` = cp.async, `SYNCS` = mbarrier ops, `IMMA` = mma.sync u8 x s8, `LDSM` = ldmatrix, `FFMA2` / `FADD2` = packed fp32 pairs.\n")
     print("| kernel | instr | " + " | ".join(COLS) + " |")
     print("|---|---:|" + "---:|" * len(COLS))
     for name, c in per.items():
