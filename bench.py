@@ -321,11 +321,15 @@ def run_ours(args, cfg):
     ms_loop = D.max_over_ranks(sess.time_steps(n_loop, with_eval=True)) / n_loop
 
     # per-kernel device time (events around every launch; launches serialised), averaged over a few steps
-    prof = {}
+    # (a launch is averaged over the steps that contain it: the first profiled step follows an ELBO evaluation, whose Y pass is still
+    # valid, and issues none -- dividing by the number of steps under-reported the Y pass by a fifth until the end of round 2)
+    prof_sum, prof_cnt = {}, {}
     nprof = 5
     for _ in range(nprof):
         for name, t in sess.profile_step():
-            prof[name] = prof.get(name, 0.0) + t / nprof
+            prof_sum[name] = prof_sum.get(name, 0.0) + t
+            prof_cnt[name] = prof_cnt.get(name, 0) + 1
+    prof = {n: prof_sum[n] / prof_cnt[n] for n in prof_sum}
 
     # the step as it runs (Y pass co-scheduled on its own stream): start offset and duration of every launch, last of 3 steps
     timeline = None
@@ -338,6 +342,34 @@ def run_ours(args, cfg):
             timeline = {n: [round(t0.get(n, 0.0), 4), round(t, 4)] for n, t in pl if not n.startswith("t0:")}
     finally:
         del os.environ["CLONEALIGN_B200_PROF_OVERLAP"]
+
+    # timing ablation (CA_BENCH_ABLATE=1; results of these steps are invalid, they are the last thing the session does): duration
+    # of the Y pass next to each of the other launches alone -- which of them holds it up, and by how much
+    ablation = None
+    if os.environ.get("CA_BENCH_ABLATE"):
+        ablation = {}
+        for _ in range(3):
+            pl = sess.profile_step()
+        ablation["serial_before"] = {n: round(t, 4) for n, t in pl}
+        os.environ["CLONEALIGN_B200_PROF_OVERLAP"] = "1"
+        try:
+            for label, mask in (("all", 0), ("none", 63), ("prologue", 63 - 1), ("lse_fwd", 63 - 2), ("cell", 63 - 4), ("lse_bwd", 63 - 8),
+                                ("gene", 63 - 16), ("adam", 63 - 32), ("cell+lse_bwd", 63 - 12)):
+                os.environ["CLONEALIGN_B200_DBG_SKIP"] = str(mask)
+                for _ in range(3):
+                    pl = sess.profile_step()
+                t0 = {n[3:]: t for n, t in pl if n.startswith("t0:")}
+                ablation[label] = {n: [round(t0.get(n, 0.0), 4), round(t, 4)] for n, t in pl if not n.startswith("t0:")}
+        finally:
+            os.environ.pop("CLONEALIGN_B200_DBG_SKIP", None)
+            del os.environ["CLONEALIGN_B200_PROF_OVERLAP"]
+        for label, mask in (("serial_all", 0), ("serial_none", 63), ("serial_all_again", 0)):      # the same launches one after the other
+            os.environ["CLONEALIGN_B200_DBG_SKIP"] = str(mask)
+            for _ in range(3):
+                pl = sess.profile_step()
+            ablation[label] = {n: round(t, 4) for n, t in pl}
+        os.environ.pop("CLONEALIGN_B200_DBG_SKIP", None)
+        print(json.dumps({"ablation_ms": ablation}), file=sys.stderr, flush=True)
 
     # ---- the same measurement later in the fit: the node work of the interp path follows the panel structure -----------
     late = None

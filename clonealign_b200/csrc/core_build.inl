@@ -420,7 +420,8 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     int tile_cols = kYCB;
     if (h->variants & (CA_VAR_YPASS3 | CA_VAR_YPASS4))   // column tile of k_ypass_k1_v3 / v4: 256 threads x the columns a thread owns for this storage type
       tile_cols = h->ystore == CA_STORE_U8 ? ypass3_tile_cols<uint8_t>() : (h->ystore == CA_STORE_U16 ? ypass3_tile_cols<uint16_t>() : ypass3_tile_cols<float>());
-    if (h->ypass5) tile_cols = kY5Cols;
+    h->y5_spec = h->ypass5 && getenv("CLONEALIGN_B200_Y5_SPEC") != nullptr;
+    if (h->ypass5) tile_cols = h->y5_spec ? kY6Cols : kY5Cols;
     h->nCB = (int)ceil_div64(h->ldY, tile_cols);
     h->RB = 512;
     if (h->variants & (CA_VAR_YPASS3 | CA_VAR_YPASS4)) {
@@ -514,7 +515,9 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     }
   }
   if (h->ypass5) {
-    if (const char* e = getenv("CLONEALIGN_B200_Y5_WARPS")) h->y5_warps = atoi(e) == 8 ? 8 : 16;
+    if (const char* e = getenv("CLONEALIGN_B200_Y5_WARPS")) h->y5_warps = atoi(e) == 16 ? 16 : 8;
+    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ypass6_smem_bytes()));
+    CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v6, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v5<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ypass5_smem_bytes()));
     CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v5<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v5<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ypass5_smem_bytes()));
@@ -577,12 +580,12 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   if (h->cell2) {
     h->cell2_wc = cell2_pick_wc(C);
     h->cell2_sb = cell2_pick_sb(S);
-    const size_t budget = h->cosched ? (h->ypass5 ? 56 * 1024 : 92 * 1024) : 200 * 1024;
+    const size_t budget = h->cosched ? (h->ypass5 ? (h->y5_spec ? 48 * 1024 : 56 * 1024) : 92 * 1024) : 200 * 1024;
     h->cell2_panels = cell2_smem_panels(h->cell2_wc, h->cell2_sb, C, budget, h->fused_warps);
     if (h->cell2_panels < 1) fail("variant cell2: the coefficient table of one panel (%zu bytes) does not fit into shared memory", cell2_panel_bytes(h->cell2_wc, h->cell2_sb));
     if (const char* e = getenv("CLONEALIGN_B200_FUSED_PANELS")) h->cell2_panels = std::max(1, std::min(h->cell2_panels, atoi(e)));   // test hook: several rounds
     h->cell2_smem = cell2_smem_bytes(h->cell2_wc, h->cell2_sb, C, h->cell2_panels, h->fused_warps);
-    h->gene2_panels = std::max(1, gene2_smem_panels(h->cell2_wc, h->cell2_sb, (h->cosched && h->ypass5) ? 56 * 1024 : 96 * 1024));   // two 512-thread blocks per SM (one next to the Y pass)
+    h->gene2_panels = std::max(1, gene2_smem_panels(h->cell2_wc, h->cell2_sb, (h->cosched && h->ypass5) ? 48 * 1024 : 96 * 1024));   // two 512-thread blocks per SM (one next to the Y pass)
     if (const char* e = getenv("CLONEALIGN_B200_FUSED_PANELS")) h->gene2_panels = std::max(1, std::min(h->gene2_panels, atoi(e)));
     h->gene2_smem = gene2_smem_bytes(h->cell2_wc, h->cell2_sb, h->gene2_panels);
     cell2_dispatch(h->cell2_wc, h->cell2_sb, [&](auto wc, auto sb) {

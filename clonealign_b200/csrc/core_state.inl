@@ -32,7 +32,8 @@ struct ca_handle {
   bool lean = false;               // with epi2: k_prologue / k_gene_fused / k_adam_all
   bool defer = false;              // with lean: Y-linear terms added after the per-cell kernel (late join of the Y pass)
   int y4_minb = 4;                 // k_ypass_k1_v4 register budget: sized for 4 (64 registers) or 3 (80) CTAs per SM
-  int y5_warps = 16;               // warps of a k_ypass_k1_v5 CTA (8 x 128 registers or 16 x 64)
+  bool y5_spec = false;            // k_ypass_k1_v6: the same arithmetic, stages handed over through mbarriers (producer warp + 8 consumer warps)
+  int y5_warps = 8;                // warps of a k_ypass_k1_v5 CTA (8 x 128 registers or 16 x 64)
   bool ypass5 = false;             // with ypass4, counts stored as u8: integer tensor-pipe Y pass (k_ypass_k1_v5), one persistent CTA per SM
   bool cosched = false;            // with defer + ypass4: the Y pass starts first in the step, next to everything up to the gene kernel
   bool pending_join = false;       // a Y pass forked onto stream2 has not been joined yet

@@ -24,6 +24,10 @@ struct LaunchScope {
   }
 };
 #define KCHECK() CUDA_OK(cudaGetLastError())
+// timing ablation (results INVALID): CLONEALIGN_B200_DBG_SKIP = bit mask of launches of the default train step that are not issued
+// (1 prologue, 2 forward node sums + coefficients, 4 per-cell kernel, 8 backward node sums + coefficients, 16 gene kernel, 32 optimiser);
+// read at every non-replayed step: ca_core_profile_step shows what the Y pass costs next to each of the others (bench.py: CA_BENCH_ABLATE)
+inline unsigned dbg_skip() { const char* e = getenv("CLONEALIGN_B200_DBG_SKIP"); return e ? (unsigned)atoi(e) : 0u; }
 
 template <typename F>
 void dispatch_y(ca_handle* h, F&& f) {
@@ -58,7 +62,10 @@ void run_ypass(ca_handle* h, cudaStream_t st) {
       if (h->ypass5 && std::is_same<T, uint8_t>::value) {
         const int64_t tiles = (int64_t)h->nCB * h->nRB;
         const unsigned g5 = (unsigned)std::min<int64_t>(tiles, (int64_t)h->num_sms);
-        if (h->y5_warps == 8)
+        if (h->y5_spec)
+          CA_LAUNCH(k_ypass_k1_v6, g5, kY6Threads, ypass6_smem_bytes(), st)((const uint8_t*)(const void*)Yp, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm,
+                                                                           h->rowpart, h->colpart);
+        else if (h->y5_warps == 8)
           CA_LAUNCH(k_ypass_k1_v5<8>, g5, 256, ypass5_smem_bytes(), st)((const uint8_t*)(const void*)Yp, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm,
                                                                        h->rowpart, h->colpart);
         else
@@ -248,7 +255,7 @@ void run_forward(ca_handle* h, int mode) {
     a.mu = sm;
     a.mu_vec4 = (h->C % 4 == 0) ? 1 : 0;
     a.wide_panels = h->cell2 ? 1 : 0;
-    CA_LAUNCH(k_prologue, 2 + kProPsiBlocks + h->n_gene_blocks, kProThreads, 0, h->stream)(a);
+    if (!(dbg_skip() & 1u)) CA_LAUNCH(k_prologue, 2 + kProPsiBlocks + h->n_gene_blocks, kProThreads, 0, h->stream)(a);
     KCHECK();
   } else {
     LaunchScope ls(h, "alpha");
@@ -285,7 +292,7 @@ void run_forward(ca_handle* h, int mode) {
         CA_LAUNCH(k_minmax, 1, 1024, 0, h->stream)(h->U, (int)h->N, h->mm_psi);
         CA_LAUNCH(k_interp_plan, 1, 32, 0, h->stream)(h->mm, h->mm_psi, h->iplan);
       }
-      launch_interp_nodes<true>(h, h->Vm, nullptr, h->Mx, h->G);
+      if (!(dbg_skip() & 2u)) launch_interp_nodes<true>(h, h->Vm, nullptr, h->Mx, h->G);
       if (!h->epi2)
         CA_LAUNCH(k_interp_eval<true>, h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream)(h->iplan, h->icoef, h->U, h->N, h->J, h->Zx,
                                                                                     h->ieval_panels);
@@ -324,7 +331,7 @@ void run_forward(ca_handle* h, int mode) {
       b.apply_t = (mode == EPI_TRAIN && h->apply_now && !getenv("CLONEALIGN_B200_NO_CELL_ADAM")) ? 1 : 0;
       b.m_t = h->m_t; b.v_t = h->v_t; b.state = h->dstate;
       h->t_done = b.apply_t != 0;
-      launch_cell2(h, mode, b);
+      if (!(dbg_skip() & 4u)) launch_cell2(h, mode, b);
     } else
     launch_fused(h, mode, a);
     KCHECK();
@@ -366,7 +373,7 @@ void run_train(ca_handle* h, bool apply) {
     LaunchScope ls(h, "lse_bwd", h->interp ? (h->lean ? 2 : 3) : 1);
     if (h->interp) {
       // K = 1: dMx[g][j] = H_j(w_g); the plan of this step's forward pass is still valid (psi, W unchanged)
-      launch_interp_nodes<false>(h, h->U, h->shift, h->Rx, h->N);
+      if (!(dbg_skip() & 8u)) launch_interp_nodes<false>(h, h->U, h->shift, h->Rx, h->N);
       if (!h->lean)
         CA_LAUNCH(k_interp_eval<false>, h->num_sms, kIEvalWarps * 32, h->ieval_smem, h->stream)(h->iplan, h->icoef, h->Vm, h->G, h->J, h->dMx,
                                                                                      h->ieval_panels);
@@ -391,7 +398,7 @@ void run_train(ca_handle* h, bool apply) {
       a.gsum_part = h->gsum_part; a.n_parts = h->n_cell_parts;
       cell2_dispatch(h->cell2_wc, h->cell2_sb, [&](auto wc, auto sb) {
         auto k = k_gene_fused2<decltype(wc)::value, decltype(sb)::value>;
-        CA_LAUNCH(k, 2 * h->num_sms + 1, kGene2Warps * 32, h->gene2_smem, h->stream)(a);
+        if (!(dbg_skip() & 16u)) CA_LAUNCH(k, 2 * h->num_sms + 1, kGene2Warps * 32, h->gene2_smem, h->stream)(a);
       });
       KCHECK();
     }
@@ -474,7 +481,7 @@ void run_train(ca_handle* h, bool apply) {
       aa.state = h->dstate;
       const bool adam_adds_colpart = h->cell2 && h->cfg.world == 1;
       aa.colpart = adam_adds_colpart ? h->colpart : nullptr; aa.nRB = h->nRB; aa.YtU = h->YtU;
-      CA_LAUNCH(k_adam_all, (unsigned)(aa.n_gene_blocks + aa.n_cell_blocks + 1), 256, 0, h->stream)(aa);
+      if (!(dbg_skip() & 32u)) CA_LAUNCH(k_adam_all, (unsigned)(aa.n_gene_blocks + aa.n_cell_blocks + 1), 256, 0, h->stream)(aa);
       KCHECK();
     } else {
     // gene kernel reads chi_raw (old) -> must precede the scalar update

@@ -819,6 +819,218 @@ k_ypass_k1_v5(const uint8_t* __restrict__ Y, int64_t ldY, int64_t N, int G, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// k_ypass_k1_v6: the arithmetic of k_ypass_k1_v5 without a block barrier per stage (CLONEALIGN_B200_Y5_SPEC=1).
+// v5 next to the other kernels of the step is held up as much as the FMA-pipe pass (profiles/r02_notes.md section 3c): its 8 warps
+// meet at a block barrier after every 32-row stage, so the slowest warp -- delayed by whatever else the schedulers issue -- sets the
+// pace of the CTA.  Here the stages are handed over through mbarriers only:
+//   * warps 0 .. 5 (consumers): wait for full[stage] -> row-sum and column-sum products of their 256 columns -> integer digit sums
+//     of the 32 rows added into shared memory with red.shared.add.s32 (integer: order-independent) -> arrive on empty[stage];
+//   * warp 6 (producer): waits for empty[stage] (6 arrivals), turns the stage's digit sums into the row partials (lane = row),
+//     zeroes them, re-arms full[stage] and issues the 32 bulk copies of the stage after next.
+// Block barriers remain at tile boundaries only (the per-tile scales and digit tables are built by all threads).  Tiles are 1 536 columns
+// wide in a ring of THREE stages (two travel while one is consumed; two stages of 1 792 columns left the pass 24 % above the time of its
+// bytes): 6 consumer warps + the producer, at most 2 warps per scheduler (a ninth warp takes a third register slice on one scheduler and
+// pushes the co-scheduled 16-warp kernels off the SM: measured, the step serialised).  W digit fragments live in shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kY6Consumers = 6, kY6Threads = 32 * (kY6Consumers + 1), kY6Cols = kY6Consumers * 256, kY6Pitch = kY6Cols + 16, kY6Stages = 3;   // 1 536-column tiles
+inline size_t ypass6_smem_bytes() {
+  return (size_t)kY6Stages * kY5StageRows * kY6Pitch + (size_t)(kY5MaxRows / 32) * 128 + (size_t)kY6Consumers * 8 * 32 * 8 +
+         (size_t)kY6Stages * kY5StageRows * 16 + 8 * 2 * kY6Stages + 16;
+}
+__global__ void __launch_bounds__(kY6Threads, 2)
+k_ypass_k1_v6(const uint8_t* __restrict__ Y, int64_t ldY, int64_t N, int G, int RB, int nCB, int nRB, const float* __restrict__ U,
+              const float* __restrict__ Vm, float* __restrict__ rowpart, float* __restrict__ colpart) {
+  CA_DYNAMIC_SMEM(unsigned char, ring6);
+  constexpr int kWarpCols = 256, kKB = 8, kGB = 16;
+  unsigned char* ring = ring6;                                                                   // [stage][row][kY6Pitch]
+  unsigned char* p0 = ring6 + (size_t)kY6Stages * kY5StageRows * kY6Pitch;
+  uint2* psd = reinterpret_cast<uint2*>(p0);                                                      // [32-row block][digit][t]
+  uint2* bws = reinterpret_cast<uint2*>(p0 + (size_t)(kY5MaxRows / 32) * 128);                    // [warp][kb][lane]: W digit fragments
+  int* rsum = reinterpret_cast<int*>(p0 + (size_t)(kY5MaxRows / 32) * 128 + (size_t)kY6Consumers * 8 * 32 * 8);   // [stage][row][digit]
+  uint64_t* full = reinterpret_cast<uint64_t*>(rsum + kY6Stages * kY5StageRows * 4);
+  uint64_t* empty = full + kY6Stages;
+  __shared__ float sred[8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool producer = wid == kY6Consumers;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < kY6Stages * kY5StageRows * kY6Pitch / 16; i += kY6Threads) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < kY6Stages * kY5StageRows * 4; i += kY6Threads) rsum[i] = 0;
+  if (tid == 0)
+    for (int st = 0; st < kY6Stages; ++st) { bar_init(full + st, 1); bar_init(empty + st, kY6Consumers); }
+  fence_bar_init();
+  fence_proxy_async();
+  __syncthreads();
+  uint32_t j0 = 0;                                                   // stages handed over so far (all tiles): stage j lives in slot j % kY6Stages
+  const int64_t ntiles = (int64_t)nCB * nRB;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int cb = (int)(tile % nCB);
+    const int64_t rb = tile / nCB;
+    const int64_t tcol0 = (int64_t)cb * kY6Cols;
+    const int64_t avail = ldY - tcol0;
+    const uint32_t tbytes = avail < (int64_t)kY6Cols ? (uint32_t)avail : (uint32_t)kY6Cols;
+    const int64_t rbeg = rb * RB, rend = (rbeg + RB < N) ? rbeg + RB : N;
+    const int nrows = (int)(rend - rbeg);
+    const int nstages = (nrows + kY5StageRows - 1) / kY5StageRows;
+    const uint8_t* ybase = Y + rbeg * ldY + tcol0;
+    auto issue = [&](int sg) {                                       // producer warp: stage sg of this tile -> slot (j0 + sg) % kY6Stages
+      if (sg >= nstages) return;
+      const int st = (int)((j0 + (uint32_t)sg) % kY6Stages);
+      const int r0 = sg * kY5StageRows;
+      const int nv = nrows - r0 < kY5StageRows ? nrows - r0 : kY5StageRows;
+      if (lane == 0) bar_arm(full + st, (uint32_t)nv * tbytes);
+      __syncwarp();
+      if (lane < nv) bulk_copy(ring + ((size_t)st * kY5StageRows + lane) * kY6Pitch, ybase + (int64_t)(r0 + lane) * ldY, tbytes, full + st);
+    };
+    if (producer)                                                    // (the slots were released when the previous tile was finalised)
+      for (int sg = 0; sg < kY6Stages; ++sg) issue(sg);
+    CA_SYNC_AFTER_SYNCHRONOUS_COPY();
+    // ---- per-tile operands: scales, W digit fragments, psi digit table (all threads) ----
+    const float kInf = __int_as_float(0x7f800000);
+    float wm = 0.f, pm = 0.f;
+    for (int c = tid; c < kY6Cols; c += kY6Threads) {
+      const int64_t col = tcol0 + c;
+      if (col < G) { const float v = fabsf(Vm[col]); wm = (v <= 3.0e38f) ? fmaxf(wm, v) : kInf; }
+    }
+    for (int r = tid; r < nrows; r += kY6Threads) { const float v = fabsf(U[rbeg + r]); pm = (v <= 3.0e38f) ? fmaxf(pm, v) : kInf; }
+    wm = warp_max(wm); pm = warp_max(pm);
+    if (lane == 0) sred[wid] = wm;
+    __syncthreads();
+    wm = sred[0];
+#pragma unroll
+    for (int i = 1; i < kY6Consumers + 1; ++i) wm = fmaxf(wm, sred[i]);
+    __syncthreads();
+    if (lane == 0) sred[wid] = pm;
+    __syncthreads();
+    pm = sred[0];
+#pragma unroll
+    for (int i = 1; i < kY6Consumers + 1; ++i) pm = fmaxf(pm, sred[i]);
+    const float sw = y5_pow2_ceil(wm), sp = y5_pow2_ceil(pm);
+    const float isw = 1.f / sw, isp = 1.f / sp;
+    const bool bad = !(wm <= 3.0e38f) || !(pm <= 3.0e38f);
+    if (!producer) {
+#pragma unroll
+      for (int kb = 0; kb < kKB; ++kb) {
+        uint32_t w2[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t pk = 0u;
+          if (g < 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int64_t col = tcol0 + wid * kWarpCols + kb * 32 + h * 16 + t * 4 + j;
+              const int D = col < G ? y5_digit(Vm[col] * isw, g) : 0;
+              pk |= ((uint32_t)D & 0xffu) << (8 * j);
+            }
+          }
+          w2[h] = pk;
+        }
+        bws[(wid * kKB + kb) * 32 + lane] = make_uint2(w2[0], w2[1]);
+      }
+    }
+    for (int it = tid; it < nstages * 16; it += kY6Threads) {
+      const int k = it >> 4, d = (it >> 2) & 3, tt = it & 3;
+      uint32_t w2[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = k * 32 + h * 16 + (j >> 1) * 8 + 2 * tt + (j & 1);
+          const int D = r < nrows ? y5_digit(U[rbeg + r] * isp, d) : 0;
+          pk |= ((uint32_t)D & 0xffu) << (8 * j);
+        }
+        w2[h] = pk;
+      }
+      psd[it] = make_uint2(w2[0], w2[1]);
+    }
+    __syncthreads();
+    if (producer) {
+      // ---- producer: finalise the row sums of every stage behind its consumers, then refill the slot ----
+      for (int sg = 0; sg < nstages; ++sg) {
+        const uint32_t j = j0 + (uint32_t)sg;
+        const int st = (int)(j % kY6Stages);
+        bar_wait(empty + st, (j / kY6Stages) & 1u);
+        int4 d4 = reinterpret_cast<int4*>(rsum)[st * kY5StageRows + lane];
+        reinterpret_cast<int4*>(rsum)[st * kY5StageRows + lane] = make_int4(0, 0, 0, 0);
+        const double v = (double)d4.x * 0.015625 + (double)d4.y * 0.0001220703125 + (double)d4.z * 9.5367431640625e-07 +
+                         (double)d4.w * 7.450580596923828e-09;
+        if (sg * kY5StageRows + lane < nrows)
+          rowpart[(int64_t)cb * N + rbeg + sg * kY5StageRows + lane] = bad ? __int_as_float(0x7fc00000) : (float)(v * (double)sw);
+        __syncwarp();
+        issue(sg + kY6Stages);
+      }
+    } else {
+      int cacc[kGB][4];
+#pragma unroll
+      for (int gb = 0; gb < kGB; ++gb)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cacc[gb][i] = 0;
+      for (int sg = 0; sg < nstages; ++sg) {
+        const uint32_t j = j0 + (uint32_t)sg;
+        const int st = (int)(j % kY6Stages);
+        bar_wait(full + st, (j / kY6Stages) & 1u);
+        const unsigned char* sbase = ring + (size_t)st * kY5StageRows * kY6Pitch + wid * kWarpCols;
+        int racc[2][4];
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) racc[rh][i] = 0;
+          const unsigned char* ap = sbase + (size_t)(rh * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kY6Pitch + 16 * (lane >> 4);
+#pragma unroll
+          for (int kb = 0; kb < kKB; ++kb) {
+            uint32_t a[4];
+            ldmatrix_x4(a, ap + kb * 32);
+            const uint2 b = bws[(wid * kKB + kb) * 32 + lane];
+            mma_u8s8(racc[rh], a, b.x, b.y);
+          }
+        }
+        const uint2 pb = (g < 4) ? psd[sg * 16 + g * 4 + t] : make_uint2(0u, 0u);
+        const unsigned char* tp = sbase + (size_t)lane * kY6Pitch;
+#pragma unroll
+        for (int gb = 0; gb < kGB; ++gb) {
+          uint32_t r[4], a[4];
+          ldmatrix_x4_trans(r, tp + gb * 16);
+          a[0] = __byte_perm(r[0], r[1], 0x6420u);
+          a[1] = __byte_perm(r[0], r[1], 0x7531u);
+          a[2] = __byte_perm(r[2], r[3], 0x6420u);
+          a[3] = __byte_perm(r[2], r[3], 0x7531u);
+          mma_u8s8(cacc[gb], a, pb.x, pb.y);
+        }
+        // digit sums of the stage's rows: lanes t = 0 hold digits (0, 1), t = 1 digits (2, 3); integer adds commute
+        if (t < 2) {
+          int* rs = rsum + st * kY5StageRows * 4 + 2 * t;
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            atomicAdd(rs + (rh * 16 + g) * 4, racc[rh][0]);
+            atomicAdd(rs + (rh * 16 + g) * 4 + 1, racc[rh][1]);
+            atomicAdd(rs + (rh * 16 + g + 8) * 4, racc[rh][2]);
+            atomicAdd(rs + (rh * 16 + g + 8) * 4 + 1, racc[rh][3]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) bar_arrive(empty + st);
+      }
+#pragma unroll
+      for (int gb = 0; gb < kGB; ++gb) {
+        const double s0 = t == 0 ? 0.015625 : (t == 1 ? 9.5367431640625e-07 : 0.0);
+        const double s1 = t == 0 ? 0.0001220703125 : (t == 1 ? 7.450580596923828e-09 : 0.0);
+        double ev = (double)cacc[gb][0] * s0 + (double)cacc[gb][1] * s1;
+        double od = (double)cacc[gb][2] * s0 + (double)cacc[gb][3] * s1;
+        ev += __shfl_xor_sync(CA_FULL, ev, 1);
+        od += __shfl_xor_sync(CA_FULL, od, 1);
+        if (t == 0) {
+          const int64_t col = tcol0 + wid * kWarpCols + gb * 16 + 2 * g;
+          if (col < G) colpart[rb * G + col] = bad ? __int_as_float(0x7fc00000) : (float)(ev * (double)sp);
+          if (col + 1 < G) colpart[rb * G + col + 1] = bad ? __int_as_float(0x7fc00000) : (float)(od * (double)sp);
+        }
+      }
+    }
+    j0 += (uint32_t)nstages;
+    __syncthreads();                                                 // the tile is finalised: slots, sred, psd, bws are reused
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Batched Y pass for R fits that share one count matrix (restarts of run_clonealign on one device):
 // ONE stream over Y produces (Y W_r, Y^T psi_r) for every fit r -- the widening / magic-number work is shared and the
 // matrix leaves HBM once instead of R times.  Same tiling and partial layouts as k_ypass_k1_v2 (each fit's own rowpart /

@@ -91,6 +91,7 @@ __device__ __forceinline__ void mma_u8s8(int (&c)[4], const uint32_t (&a)[4], ui
 __device__ __forceinline__ void bar_init(uint64_t* bar, int count) { ptx::mbar_init(ptx::smem_u32(bar), (uint32_t)count); }
 __device__ __forceinline__ void bar_arm(uint64_t* bar, uint32_t bytes) { ptx::mbar_expect_tx(ptx::smem_u32(bar), bytes); }
 __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) { ptx::mbar_wait(ptx::smem_u32(bar), parity); }
+__device__ __forceinline__ void bar_arrive(uint64_t* bar) { ptx::mbar_arrive(ptx::smem_u32(bar)); }
 __device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   ptx::bulk_load_1d(ptx::smem_u32(dst), src, bytes, ptx::smem_u32(bar));
 }

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2, call W (one GPU): ypass5 with 16 / 8 warps per CTA, ncu of the pass.
+# Round 2, call W (one GPU): ypass5: block-barrier pass (k_ypass_k1_v5) against the mbarrier-only producer / consumer pass (k_ypass_k1_v6).
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
@@ -8,16 +8,14 @@ summ() { python - "$1" <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-    print(round(d["value"],1), round(d["ms_per_step"],4), d["roofline"]["all_kernels_ms"], d["config"]["parity"]["elbo_after"], d["config"]["parity"]["hard_calls_sha256"], "timeline", d["roofline"].get("timeline_ms"))
+    print(round(d["value"],1), round(d["ms_per_step"],4), d["roofline"]["all_kernels_ms"], d["config"]["parity"]["elbo_start"], d["config"]["parity"]["elbo_after"], d["config"]["parity"]["hard_calls_sha256"], "timeline", d["roofline"].get("timeline_ms"))
 except Exception as e:
     print("no line:", e)
 PY
 }
-for w in 16 8; do
-echo "== ypass5, $w warps per Y-pass CTA"
-CLONEALIGN_B200_Y5_WARPS=$w timeout 300 python bench.py --steps 30 --warmup 5 --quick --no-e2e --no-cpu-baseline --variants ypass5 > $O/r2w_bench_y$w.json 2> $O/r2w_bench_y$w.err; summ $O/r2w_bench_y$w.json; tail -3 $O/r2w_bench_y$w.err
-done
-echo "== ncu of the default step with ypass5 (16 warps)"
-CLONEALIGN_B200_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ypass -s 20 -c 2 -o $O/r2w_prof -f \
-  python bench.py --steps 2 --warmup 3 --quick --no-e2e --no-cpu-baseline --variants ypass5 > $O/r2w_ncu_full.log 2>&1
-tail -2 $O/r2w_ncu_full.log | cut -c1-200
+echo "== small-shape parity with the producer / consumer pass"
+CLONEALIGN_B200_Y5_SPEC=1 CLONEALIGN_B200_VARIANTS=ypass5 timeout 120 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider -k "auto" > $O/r2w_tests.log 2>&1; echo "rc=$?"; tail -3 $O/r2w_tests.log | cut -c1-300
+echo "== ypass5, producer / consumer (v6)"
+CLONEALIGN_B200_Y5_SPEC=1 timeout 120 python bench.py --steps 30 --warmup 5 --quick --no-e2e --no-cpu-baseline --variants ypass5 > $O/r2w_bench_v6.json 2> $O/r2w_bench_v6.err; summ $O/r2w_bench_v6.json; tail -3 $O/r2w_bench_v6.err
+echo "== ypass5, block barrier (v5, 8 warps)"
+timeout 120 python bench.py --steps 30 --warmup 5 --quick --no-e2e --no-cpu-baseline --variants ypass5 > $O/r2w_bench_v5.json 2> $O/r2w_bench_v5.err; summ $O/r2w_bench_v5.json; tail -3 $O/r2w_bench_v5.err

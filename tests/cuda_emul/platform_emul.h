@@ -32,6 +32,7 @@ template <int N> inline void cp_async_wait() {}
 inline void bar_init(uint64_t*, int) {}
 inline void bar_arm(uint64_t*, uint32_t) {}
 inline void bar_wait(uint64_t*, uint32_t) {}
+inline void bar_arrive(uint64_t*) {}
 inline void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t*) {
   ca_emul_check_aligned(dst, src, 16, "bulk copy");
   if (bytes % 16) { fprintf(stderr, "cuda_emul: bulk copy of %u bytes\n", bytes); abort(); }
