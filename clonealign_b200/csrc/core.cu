@@ -33,6 +33,7 @@
 #include "kernels_small.cuh"
 #include CA_TC_HEADER   // platform.cuh: kernels_tc.cuh
 #include "kernels_ypass.cuh"
+#include CA_Y7_HEADER   // platform.cuh: kernels_ypass_tma.cuh
 
 using namespace ca;
 

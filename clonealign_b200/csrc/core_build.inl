@@ -421,6 +421,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     if (h->variants & (CA_VAR_YPASS3 | CA_VAR_YPASS4))   // column tile of k_ypass_k1_v3 / v4: 256 threads x the columns a thread owns for this storage type
       tile_cols = h->ystore == CA_STORE_U8 ? ypass3_tile_cols<uint8_t>() : (h->ystore == CA_STORE_U16 ? ypass3_tile_cols<uint16_t>() : ypass3_tile_cols<float>());
     h->y5_spec = h->ypass5 && getenv("CLONEALIGN_B200_Y5_SPEC") != nullptr;
+    h->y7 = h->y5_spec && kY7Available && atoi(getenv("CLONEALIGN_B200_Y5_SPEC")) == 2;
     if (h->ypass5) tile_cols = h->y5_spec ? kY6Cols : kY5Cols;
     h->nCB = (int)ceil_div64(h->ldY, tile_cols);
     h->RB = 512;
@@ -516,6 +517,10 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
   }
   if (h->ypass5) {
     if (const char* e = getenv("CLONEALIGN_B200_Y5_WARPS")) h->y5_warps = atoi(e) == 16 ? 16 : 8;
+    if (h->y7) {
+      y7_plan_create(h->y7plan, h->Y, N, h->ldY);
+      CUDA_OK(y7_set_attributes());
+    }
     CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ypass6_smem_bytes()));
     CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v6, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v5<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ypass5_smem_bytes()));

@@ -13,6 +13,7 @@
 #else
 
 #define CA_TC_HEADER "kernels_tc.cuh"                 // tcgen05 / TMEM / TMA contraction kernels
+#define CA_Y7_HEADER "kernels_ypass_tma.cuh"          // integer Y pass on 2-D tensor copies (needs the tensor-map types of the header above)
 #define CA_NCCL_PROVIDER "nccl_dlopen.inl"            // NCCL resolved with dlopen at first multi-GPU use
 #define CA_SYNC_AFTER_SYNCHRONOUS_COPY() ((void)0)     // bulk copies are asynchronous here: completion is an mbarrier phase
 

@@ -9,6 +9,7 @@
 #include <cstring>
 
 #define CA_TC_HEADER "kernels_tc_stub.h"
+#define CA_Y7_HEADER "kernels_ypass_tma_stub.h"
 #define CA_NCCL_PROVIDER "nccl_emul_provider.inl"
 #define CA_SYNC_AFTER_SYNCHRONOUS_COPY() __syncthreads()
 
