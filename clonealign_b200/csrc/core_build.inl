@@ -195,6 +195,12 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     h->cfg.variants |= CA_VAR_EPI2 | CA_VAR_LEAN | CA_VAR_DEFER;
     if (h->cfg.variants & CA_VAR_YPASS4) h->cfg.variants |= CA_VAR_COSCHED;
     if (c.S <= kCell2MaxS && !getenv("CLONEALIGN_B200_NO_CELL2")) h->cfg.variants |= CA_VAR_CELL2;
+    // stored bytes + cell2 + co-scheduling: the integer tensor-pipe Y pass on 2-D tensor copies (k_ypass_k1_v7) where the matrix is large
+    // enough to keep one persistent CTA per SM busy (CLONEALIGN_B200_Y7 = 0 / 1 overrides the size rule)
+    if (kY7Available && (h->cfg.variants & CA_VAR_YPASS4) && (h->cfg.variants & CA_VAR_CELL2) && y7_wanted((int64_t)c.N * c.G)) {
+      h->cfg.variants |= CA_VAR_YPASS5;
+      h->y7_auto = true;
+    }
   }
   h->interp = (c.path == CA_PATH_INTERP);
   h->variants = c.variants;
@@ -420,8 +426,8 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     int tile_cols = kYCB;
     if (h->variants & (CA_VAR_YPASS3 | CA_VAR_YPASS4))   // column tile of k_ypass_k1_v3 / v4: 256 threads x the columns a thread owns for this storage type
       tile_cols = h->ystore == CA_STORE_U8 ? ypass3_tile_cols<uint8_t>() : (h->ystore == CA_STORE_U16 ? ypass3_tile_cols<uint16_t>() : ypass3_tile_cols<float>());
-    h->y5_spec = h->ypass5 && getenv("CLONEALIGN_B200_Y5_SPEC") != nullptr;
-    h->y7 = h->y5_spec && kY7Available && atoi(getenv("CLONEALIGN_B200_Y5_SPEC")) == 2;
+    h->y5_spec = h->ypass5 && (h->y7_auto || getenv("CLONEALIGN_B200_Y5_SPEC") != nullptr);
+    h->y7 = h->y5_spec && kY7Available && (h->y7_auto || atoi(getenv("CLONEALIGN_B200_Y5_SPEC")) == 2);
     if (h->ypass5) tile_cols = h->y5_spec ? kY6Cols : kY5Cols;
     h->nCB = (int)ceil_div64(h->ldY, tile_cols);
     h->RB = 512;
@@ -446,6 +452,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
       const int64_t waves = std::max<int64_t>(1, ceil_div64((int64_t)h->nCB * ceil_div64(N, kY5MaxRows), slots));
       const int64_t nrb = std::max<int64_t>(1, waves * slots / h->nCB);
       h->RB = (int)std::min<int64_t>(kY5MaxRows, std::max<int64_t>(kY5StageRows, round_up64(ceil_div64(N, nrb), kY5StageRows)));
+      if (h->y7) y7_plan_tiles(h->y7plan, N, h->ldY, h->num_sms, h->RB);   // per-CTA tile lists
     }
   } else {
     h->nCB = 1;
@@ -519,6 +526,12 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     if (const char* e = getenv("CLONEALIGN_B200_Y5_WARPS")) h->y5_warps = atoi(e) == 16 ? 16 : 8;
     if (h->y7) {
       y7_plan_create(h->y7plan, h->Y, N, h->ldY);
+      int* dt = h->alloc<int>(h->y7plan.tiles.size());
+      int* dof = h->alloc<int>(h->y7plan.offs.size());
+      CUDA_OK(cudaMemcpyAsync(dt, h->y7plan.tiles.data(), sizeof(int) * h->y7plan.tiles.size(), cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(cudaMemcpyAsync(dof, h->y7plan.offs.data(), sizeof(int) * h->y7plan.offs.size(), cudaMemcpyHostToDevice, h->stream));
+      CUDA_OK(cudaStreamSynchronize(h->stream));
+      h->y7plan.d_tiles = dt; h->y7plan.d_offs = dof;
       CUDA_OK(y7_set_attributes());
     }
     CUDA_OK(cudaFuncSetAttribute(k_ypass_k1_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ypass6_smem_bytes()));

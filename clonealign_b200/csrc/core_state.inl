@@ -34,6 +34,7 @@ struct ca_handle {
   int y4_minb = 4;                 // k_ypass_k1_v4 register budget: sized for 4 (64 registers) or 3 (80) CTAs per SM
   bool y7 = false;                 // CLONEALIGN_B200_Y5_SPEC=2: k_ypass_k1_v7 (stages as 2-D tensor copies); 6 consumers, 1 536-column tiles
   Y7Plan y7plan;
+  bool y7_auto = false;            // chosen by path = auto (core_build.inl)
   bool y5_spec = false;            // k_ypass_k1_v6: the same arithmetic, stages handed over through mbarriers (producer warp + 8 consumer warps)
   int y5_warps = 8;                // warps of a k_ypass_k1_v5 CTA (8 x 128 registers or 16 x 64)
   bool ypass5 = false;             // with ypass4, counts stored as u8: integer tensor-pipe Y pass (k_ypass_k1_v5), one persistent CTA per SM

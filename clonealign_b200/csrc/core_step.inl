@@ -63,7 +63,7 @@ void run_ypass(ca_handle* h, cudaStream_t st) {
         const int64_t tiles = (int64_t)h->nCB * h->nRB;
         const unsigned g5 = (unsigned)std::min<int64_t>(tiles, (int64_t)h->num_sms);
         if (h->y7) {
-          y7_launch(h->y7plan, g5, st, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm, h->rowpart, h->colpart);
+          y7_launch(h->y7plan, (unsigned)h->num_sms, st, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm, h->rowpart, h->colpart);
         } else if (h->y5_spec)
           CA_LAUNCH(k_ypass_k1_v6, g5, kY6Threads, ypass6_smem_bytes(), st)((const uint8_t*)(const void*)Yp, h->ldY, h->N, h->G, h->RB, h->nCB, h->nRB, h->U, h->Vm,
                                                                            h->rowpart, h->colpart);

@@ -18,6 +18,13 @@ struct CaError : std::runtime_error {
   throw CaError(buf);
 }
 
+// path = auto picks the tensor-copy integer Y pass from this many stored elements per rank on (see profiles/r02_notes.md section 3c)
+constexpr int64_t kY7MinElements = (int64_t)1 << 25;
+inline bool y7_wanted(int64_t elements) {
+  if (const char* e = getenv("CLONEALIGN_B200_Y7")) return atoi(e) != 0;
+  return elements >= kY7MinElements;
+}
+
 #define CUDA_OK(expr)                                                                         \
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \

@@ -14,8 +14,8 @@ except Exception as e:
 PY
 }
 echo "== small-shape parity with the tensor-copy pass"
-CLONEALIGN_B200_Y5_SPEC=2 CLONEALIGN_B200_VARIANTS=ypass5 timeout 150 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider -k "auto" > $O/r2ab_tests.log 2>&1; echo "rc=$?"; tail -3 $O/r2ab_tests.log | cut -c1-300
+CLONEALIGN_B200_Y5_SPEC=2 CLONEALIGN_B200_VARIANTS=ypass5 timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_interp_gpu.py -m gpu -q -x -p no:cacheprovider -k "auto or ypass5" > $O/r2ab_tests.log 2>&1; echo "rc=$?"; tail -3 $O/r2ab_tests.log | cut -c1-300
 echo "== ypass5, tensor copies (v7)"
 CLONEALIGN_B200_Y5_SPEC=2 timeout 120 python bench.py --steps 30 --warmup 5 --quick --no-e2e --no-cpu-baseline --variants ypass5 > $O/r2ab_bench_v7.json 2> $O/r2ab_bench_v7.err; summ $O/r2ab_bench_v7.json; tail -3 $O/r2ab_bench_v7.err
-echo "== default (v4)"
-timeout 120 python bench.py --steps 30 --warmup 5 --quick --no-e2e --no-cpu-baseline > $O/r2ab_bench_v4.json 2> $O/r2ab_bench_v4.err; summ $O/r2ab_bench_v4.json; tail -3 $O/r2ab_bench_v4.err
+echo "== ypass5, tensor copies (v7), strided tile walk"
+CLONEALIGN_B200_Y7_PLAIN=1 CLONEALIGN_B200_Y5_SPEC=2 timeout 120 python bench.py --steps 30 --warmup 5 --quick --no-e2e --no-cpu-baseline --variants ypass5 > $O/r2ab_bench_v7p.json 2> $O/r2ab_bench_v7p.err; summ $O/r2ab_bench_v7p.json; tail -3 $O/r2ab_bench_v7p.err
