@@ -480,7 +480,9 @@ def run_ours(args, cfg):
         line = {"metric": "ELBO+grad iterations/s", "value": value, "unit": "iterations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": warm, "ms_per_step": ms_med / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": ("f32 (node sums flushed to f64 every 32 terms, f64 polynomial recurrences per cell and per gene)" if desc["path"] == "interp" else
+                "dtype": (("f32 (Y-pass products as exact u8 x s8 -> s32 digit contractions of 28-bit fixed-point W and psi, node sums flushed to f64 every 32 terms, "
+                           "f64 polynomial recurrences per cell and per gene)" if desc["variants"] & 1024 else
+                           "f32 (node sums flushed to f64 every 32 terms, f64 polynomial recurrences per cell and per gene)") if desc["path"] == "interp" else
                           "f32 (bf16 split tensor operands, f32 accumulate)" if desc["path"] == "tcgen05" else "f32"),
                 "data": "synthetic",
                 "config": {"workload": cfg["name"], "cells_total": N, "cells_per_gpu": Nl, "genes": G, "clones": C, "mc_samples": S,

@@ -99,7 +99,9 @@ enum ca_path     { CA_PATH_AUTO = 0, CA_PATH_CUDACORE = 1, CA_PATH_TENSOR = 2, C
  *           columns taken from the derivative of the interpolants (node sums over the S*C normaliser columns only), the gene kernel
  *           in front of the Y-pass join, the gamma-logit Adam update inside the per-cell kernel; part of the default set
  *   YPASS5: (takes effect with YPASS4 and counts stored as u8) the two products of the Y pass as exact integer contractions on
- *           the tensor pipe (mma.sync u8 x s8 on base-128 digits of W and psi), one persistent CTA per SM, see kernels_ypass.cuh */
+ *           the tensor pipe (mma.sync u8 x s8 on base-128 digits of W and psi), one persistent CTA per SM, see kernels_ypass.cuh.
+ *           path = auto adds it, on its tensor-copy kernel (k_ypass_k1_v7, kernels_ypass_tma.cuh), for u8 matrices of >= 2^25 counts
+ *           per rank; passed explicitly it selects the row-copy kernels k_ypass_k1_v5 / v6 (A/B partners) */
 enum ca_variant  { CA_VAR_YPASS2 = 1, CA_VAR_EPI2 = 2, CA_VAR_LEAN = 4, CA_VAR_P2P = 8, CA_VAR_OVERLAP = 16, CA_VAR_YPASS3 = 32, CA_VAR_DEFER = 64,
                    CA_VAR_YPASS4 = 128, CA_VAR_COSCHED = 256, CA_VAR_CELL2 = 512, CA_VAR_YPASS5 = 1024 };
 

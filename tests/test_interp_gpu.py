@@ -43,6 +43,32 @@ def test_interp_ragged_shapes(N, G, C, S, variants):
         _check_grads(sess, d, p, S)
 
 
+@pytest.mark.parametrize("N,G,C,S", [(130, 70, 5, 3), (257, 193, 2, 1), (64, 640, 7, 8), (1000, 333, 12, 8), (300, 4100, 32, 4),
+                                     (33, 1537, 3, 2), (2049, 1536, 4, 1), (31, 3200, 6, 8)])
+def test_tensor_copy_integer_ypass_ragged_shapes(monkeypatch, N, G, C, S):
+    """k_ypass_k1_v7 (kernels_ypass_tma.cuh: what `path="auto"` runs on u8 matrices of benchmark size) forced on at small and ragged
+    shapes: partial row stages, one box / partial boxes / an uneven deal of boxes over column blocks, fewer tiles than SMs."""
+    from clonealign_b200.synthetic import make_synthetic
+    monkeypatch.setenv("CLONEALIGN_B200_Y7", "1")
+    syn = make_synthetic(N, G, C, seed=N + G)
+    d, p, mu_guess, _ = _case(np.minimum(syn["Y"], 255).astype(np.float64), np.minimum(syn["L"], 6.0), K=1, seed=N)
+    with _session(d.Y, d.L, p.psi, mu_guess, mc_samples=S, K=1, path="auto", seed=1) as sess:
+        desc = sess.describe()
+        assert desc["path"] == "interp" and desc["y_store"] == "u8" and desc["variants"] & 1024
+        _load_params(sess, p)
+        _check_grads(sess, d, p, S)
+
+
+def test_tensor_copy_integer_ypass_same_seed_bitwise_identical(monkeypatch, example_sce):
+    monkeypatch.setenv("CLONEALIGN_B200_Y7", "1")
+    Y, L = example_sce
+    hi = O.host_init(Y, L, K=1, rng=np.random.default_rng(0))
+    kw = dict(mc_samples=2, seed=12345, path="auto")
+    a, ga = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], **kw)
+    b, gb = _run_trace(hi["Y"], hi["L"], hi["psi_init"], hi["mu_guess"], **kw)
+    assert a.tobytes() == b.tobytes() and ga.tobytes() == gb.tobytes()
+
+
 @pytest.mark.parametrize("ypass", ["ypass2", "ypass3"])
 @pytest.mark.parametrize("path", ["tensor", "cudacore"])
 def test_packed_ypass_on_the_default_paths(example_sce, path, ypass):
