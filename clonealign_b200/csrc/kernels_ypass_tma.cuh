@@ -87,7 +87,7 @@ k_ypass_k1_v7(const __grid_constant__ CUtensorMap tmY, int64_t ldY, int64_t N, i
   int* rsum = reinterpret_cast<int*>(p0 + (size_t)(kY5MaxRows / 32) * 128 + (size_t)kY6Consumers * 8 * 32 * 8);   // [stage][row][digit]
   uint64_t* full = reinterpret_cast<uint64_t*>(rsum + kY6Stages * kY5StageRows * 4);
   uint64_t* empty = full + kY6Stages;
-  __shared__ float sred[8];
+  __shared__ float sred[16];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool producer = wid == kY6Consumers;
   const int g = lane >> 2, t = lane & 3;
@@ -149,38 +149,29 @@ k_ypass_k1_v7(const __grid_constant__ CUtensorMap tmY, int64_t ldY, int64_t N, i
     }
     for (int r = tid; r < nrows; r += kY6Threads) { const float v = fabsf(U[rbeg + r]); pm = (v <= 3.0e38f) ? fmaxf(pm, v) : kInf; }
     wm = warp_max(wm); pm = warp_max(pm);
-    if (lane == 0) sred[wid] = wm;
+    if (lane == 0) { sred[wid] = wm; sred[8 + wid] = pm; }           // (read again only behind the barriers below)
     __syncthreads();
-    wm = sred[0];
+    wm = sred[0]; pm = sred[8];
 #pragma unroll
-    for (int i = 1; i < kY6Consumers + 1; ++i) wm = fmaxf(wm, sred[i]);
-    __syncthreads();
-    if (lane == 0) sred[wid] = pm;
-    __syncthreads();
-    pm = sred[0];
-#pragma unroll
-    for (int i = 1; i < kY6Consumers + 1; ++i) pm = fmaxf(pm, sred[i]);
+    for (int i = 1; i < kY6Consumers + 1; ++i) { wm = fmaxf(wm, sred[i]); pm = fmaxf(pm, sred[8 + i]); }
     const float sw = y5_pow2_ceil(wm), sp = y5_pow2_ceil(pm);
     const float isw = 1.f / sw, isp = 1.f / sp;
     const bool bad = !(wm <= 3.0e38f) || !(pm <= 3.0e38f);
     if (!producer) {
+      // W digit fragments [warp][kb][lane (g < 4)] = (columns 32 kb + 4 t .. + 3, the same + 16) of digit g: lanes g < 4 fill the first
+      // word of their own entry, lanes g >= 4 the second word of lane - 16's (entries of lanes g >= 4 are never read: those operands are 0)
+      const int dg = g & 3, h = g >> 2;
+      uint32_t* bw32 = reinterpret_cast<uint32_t*>(bws);
 #pragma unroll
       for (int kb = 0; kb < kKB; ++kb) {
-        uint32_t w2[2];
+        uint32_t pk = 0u;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t pk = 0u;
-          if (g < 4) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int64_t col = tcol0 + wid * kWarpCols + kb * 32 + h * 16 + t * 4 + j;
-              const int D = col < cend ? y5_digit(Vm[col] * isw, g) : 0;
-              pk |= ((uint32_t)D & 0xffu) << (8 * j);
-            }
-          }
-          w2[h] = pk;
+        for (int j = 0; j < 4; ++j) {
+          const int64_t col = tcol0 + wid * kWarpCols + kb * 32 + h * 16 + t * 4 + j;
+          const int D = col < cend ? y5_digit(Vm[col] * isw, dg) : 0;
+          pk |= ((uint32_t)D & 0xffu) << (8 * j);
         }
-        bws[(wid * kKB + kb) * 32 + lane] = make_uint2(w2[0], w2[1]);
+        bw32[((wid * kKB + kb) * 32 + dg * 4 + t) * 2 + h] = pk;
       }
     }
     for (int it = tid; it < nstages * 16; it += kY6Threads) {
@@ -260,7 +251,7 @@ k_ypass_k1_v7(const __grid_constant__ CUtensorMap tmY, int64_t ldY, int64_t N, i
         for (int I = 0; I < kKB; ++I) {                              // the next batch's loads are in flight while this one multiplies
           if (I + 1 < kKB) load_batch(f[(I + 1) & 1], sb, I + 1);
           uint32_t (&c)[4][4] = f[I & 1];
-          const uint2 bw = bwp[I * 32];
+          const uint2 bw = (g < 4) ? bwp[I * 32] : make_uint2(0u, 0u);
           y7_mma_u8s8(racc[0], c[0], bw.x, bw.y);
           y7_mma_u8s8(racc[1], c[1], bw.x, bw.y);
           y7_mma_s8u8_half(cacc[2 * I], a10, a12, c[2][0], c[2][1]);
