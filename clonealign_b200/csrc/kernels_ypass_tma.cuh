@@ -55,6 +55,14 @@ inline void y7_plan_create(Y7Plan& p, const void* Y, int64_t N, int64_t ldY) {
   p.ok = true;
 }
 
+// all four base-128 digits of x in [-1, 1] from one pass of y5_digit's recursion (the same roundings: identical digits)
+__device__ __forceinline__ void y7_digits4(float x, int (&D)[4]) {
+  float y = x * 64.f;
+  float d = rintf(y);
+  D[0] = (int)d;
+#pragma unroll
+  for (int i = 1; i < 4; ++i) { y = (y - d) * 128.f; d = rintf(y); D[i] = (int)d; }
+}
 // ldmatrix on shared-space addresses; products without `volatile` (pure functions of their operands: the compiler orders them by data flow)
 __device__ __forceinline__ void y7_ldsm(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
@@ -158,37 +166,40 @@ k_ypass_k1_v7(const __grid_constant__ CUtensorMap tmY, int64_t ldY, int64_t N, i
     const float isw = 1.f / sw, isp = 1.f / sp;
     const bool bad = !(wm <= 3.0e38f) || !(pm <= 3.0e38f);
     if (!producer) {
-      // W digit fragments [warp][kb][lane (g < 4)] = (columns 32 kb + 4 t .. + 3, the same + 16) of digit g: lanes g < 4 fill the first
-      // word of their own entry, lanes g >= 4 the second word of lane - 16's (entries of lanes g >= 4 are never read: those operands are 0)
-      const int dg = g & 3, h = g >> 2;
+      // W digit fragments [warp][kb][lane (g < 4)] = (columns 32 kb + 4 t .. + 3, the same + 16) of digit g; entries of lanes g >= 4 are
+      // never read (those operands are 0).  A lane takes 4 columns of two k-blocks and writes their word in all four digits' entries.
+      const int wt = lane & 3, wh = (lane >> 2) & 1, kq = lane >> 3;
       uint32_t* bw32 = reinterpret_cast<uint32_t*>(bws);
 #pragma unroll
-      for (int kb = 0; kb < kKB; ++kb) {
-        uint32_t pk = 0u;
+      for (int i = 0; i < 2; ++i) {
+        const int kb = 2 * kq + i;
+        uint32_t pk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int64_t col = tcol0 + wid * kWarpCols + kb * 32 + h * 16 + t * 4 + j;
-          const int D = col < cend ? y5_digit(Vm[col] * isw, dg) : 0;
-          pk |= ((uint32_t)D & 0xffu) << (8 * j);
+          const int64_t col = tcol0 + wid * kWarpCols + kb * 32 + wh * 16 + wt * 4 + j;
+          int D[4] = {0, 0, 0, 0};
+          if (col < cend) y7_digits4(Vm[col] * isw, D);
+#pragma unroll
+          for (int d = 0; d < 4; ++d) pk[d] |= ((uint32_t)D[d] & 0xffu) << (8 * j);
         }
-        bw32[((wid * kKB + kb) * 32 + dg * 4 + t) * 2 + h] = pk;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) bw32[((wid * kKB + kb) * 32 + d * 4 + wt) * 2 + wh] = pk[d];
       }
     }
-    for (int it = tid; it < nstages * 16; it += kY6Threads) {
-      const int k = it >> 4, d = (it >> 2) & 3, tt = it & 3;
-      uint32_t w2[2];
+    // psi digit table [32-row block k][digit d][tt] = (rows 2 tt, 2 tt + 1, 8 + 2 tt, 9 + 2 tt | the same + 16) of the block: an item is
+    // two adjacent rows, written as a 16-bit half in all four digits' entries
+    {
+      unsigned short* psd16 = reinterpret_cast<unsigned short*>(psd);
+      for (int it = tid; it < nstages * 16; it += kY6Threads) {
+        const int k = it >> 4, h = (it >> 3) & 1, jp = (it >> 2) & 1, tt = it & 3;
+        const int r0 = k * 32 + h * 16 + jp * 8 + 2 * tt;
+        int D0[4] = {0, 0, 0, 0}, D1[4] = {0, 0, 0, 0};
+        if (r0 < nrows) y7_digits4(U[rbeg + r0] * isp, D0);
+        if (r0 + 1 < nrows) y7_digits4(U[rbeg + r0 + 1] * isp, D1);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t pk = 0u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = k * 32 + h * 16 + (j >> 1) * 8 + 2 * tt + (j & 1);
-          const int D = r < nrows ? y5_digit(U[rbeg + r] * isp, d) : 0;
-          pk |= ((uint32_t)D & 0xffu) << (8 * j);
-        }
-        w2[h] = pk;
+        for (int d = 0; d < 4; ++d)
+          psd16[((k * 16 + d * 4 + tt) * 2 + h) * 2 + jp] = (unsigned short)(((uint32_t)D0[d] & 0xffu) | (((uint32_t)D1[d] & 0xffu) << 8));
       }
-      psd[it] = make_uint2(w2[0], w2[1]);
     }
     __syncthreads();
     if (producer) {
