@@ -465,13 +465,24 @@ def run_ours(args, cfg):
                     includes="host Y upload + setup (communicator included at N > 1) + gamma init + steps x (train + ELBO eval "
                              "fetched to host) + params download")
 
+    def run_e2e_median(host, dtype_name, reps=3):
+        """One untimed warm-up fit (the first session of a process pays one-off allocation / page-mapping costs that vary from 0.07 to
+        0.44 s between boxes), then the median of `reps` complete fits, each from the host buffer to the downloaded parameters."""
+        first = run_e2e(host, dtype_name)
+        runs = sorted((run_e2e(host, dtype_name) for _ in range(reps)), key=lambda r: r["seconds_total"])
+        med = runs[len(runs) // 2]
+        med["first_fit_seconds_total"] = first["seconds_total"]
+        med["fits_timed"] = reps
+        med["seconds_total_all"] = [r["seconds_total"] for r in runs]
+        return med
+
     e2e = e2e_f32 = None
     if host_u8 is not None:
-        e2e = run_e2e(host_u8, "uint8")              # integer counts held compactly by the caller (CA_Y_U8)
+        e2e = run_e2e_median(host_u8, "uint8")       # integer counts held compactly by the caller (CA_Y_U8)
         if host_f32 is not None:
             e2e_f32 = run_e2e(host_f32, "float32")   # informational: the reference's own host dtype
     elif host_f32 is not None:
-        e2e = run_e2e(host_f32, "float32")
+        e2e = run_e2e_median(host_f32, "float32")
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base, _, _ = cpu_reference(cfg, 2, 1, budget_s=20.0)

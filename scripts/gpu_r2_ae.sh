@@ -28,3 +28,7 @@ CLONEALIGN_B200_NO_GRAPH=1 timeout 500 ncu --metrics gpu__time_duration.sum --cl
 CLONEALIGN_B200_NO_GRAPH=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ -s 150 -c 11 -o $O/r2ae_prof -f \
   python bench.py --steps 2 --warmup 3 --quick --no-e2e --no-cpu-baseline > $O/r2ae_ncu_full.log 2>&1
 tail -2 $O/r2ae_ncu_full.log | cut -c1-200
+echo "== 5. the other configurations (quick lines)"
+for c in c2 c4 c5; do
+  timeout 200 python bench.py --config $c --steps 30 --warmup 5 --quick --no-e2e --no-cpu-baseline > $O/r2ae_$c.json 2> $O/r2ae_$c.err; summ $O/r2ae_$c.json 2>/dev/null | cut -c1-200
+done
