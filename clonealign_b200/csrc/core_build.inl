@@ -197,7 +197,7 @@ void build(ca_handle* h, const void* Y, const double* L, const double* psi_init,
     if (c.S <= kCell2MaxS && !getenv("CLONEALIGN_B200_NO_CELL2")) h->cfg.variants |= CA_VAR_CELL2;
     // stored bytes + cell2 + co-scheduling: the integer tensor-pipe Y pass on 2-D tensor copies (k_ypass_k1_v7) where the matrix is large
     // enough to keep one persistent CTA per SM busy (CLONEALIGN_B200_Y7 = 0 / 1 overrides the size rule)
-    if (kY7Available && (h->cfg.variants & CA_VAR_YPASS4) && (h->cfg.variants & CA_VAR_CELL2) && y7_wanted((int64_t)c.N * c.G)) {
+    if (kY7Available && (h->cfg.variants & CA_VAR_YPASS4) && (h->cfg.variants & CA_VAR_CELL2) && c.N > 0 && y7_wanted((int64_t)c.N * c.G)) {
       h->cfg.variants |= CA_VAR_YPASS5;
       h->y7_auto = true;
     }
