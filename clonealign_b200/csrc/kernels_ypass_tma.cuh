@@ -1,9 +1,19 @@
-// k_ypass_k1_v7: k_ypass_k1_v6 (integer tensor-pipe Y pass, stages handed over through mbarriers by a producer warp) with the stages
-// loaded as 2-D TENSOR copies: one (32 rows x 128 columns) box of 4 KB per request, 12 requests per stage instead of 32 row copies of
-// 1.5 KB -- the row-copy versions of the three-stage ring were bound by the copy issue rate (profiles/r02_notes.md section 3c) --, written
-// with the 128-byte swizzle (ldmatrix reads 8 rows x 16 bytes of a box from 8 distinct bank groups without the 16-byte row skew), rows and
-// columns outside the matrix zero-filled by the copy engine.  Everything else is k_ypass_k1_v6.  Real build only (tensor maps come from the
-// driver entry point that kernels_tc.cuh resolves); the emulated build substitutes tests/cuda_emul/kernels_ypass_tma_stub.h.
+// k_ypass_k1_v7: the Y pass of the K = 1 step (row sums YW and column sums Y^T psi from ONE stream over the stored u8 counts) as exact
+// integer contractions on the tensor pipe, fed by 2-D TENSOR copies.  What `path = auto` runs on u8 matrices of benchmark size
+// (core_build.inl; profiles/r02_notes.md section 3d has the measurements behind every choice below).
+//   * W and psi are cut into four base-128 s8 digits of a power-of-two tile scale (k_ypass_k1_v5 in kernels_ypass.cuh introduced the
+//     arithmetic); products are mma.sync.m16n8k32 on u8 x s8 / s8 x u8 with s32 accumulators, digits recombined in fp64 in a fixed order:
+//     the results do not depend on the order of accumulation or on which CTA ran a tile.
+//   * One persistent CTA per SM: a producer warp and six consumer warps (128 registers: fits next to the 16 x 64-register kernels of the
+//     co-scheduled step).  A stage is 32 rows x up to 12 boxes of 128 columns, one cp.async.bulk.tensor request of 4 KB per box (12 requests
+//     instead of the 32 row copies that bound the row-copy versions by their issue rate), written with the 128-byte swizzle so that
+//     ldmatrix reads 8 rows x 16 bytes of a box from 8 distinct bank groups; rows outside the matrix are zero-filled by the copy engine.
+//     Three stages, handed over through full / empty mbarriers only; the producer walks the stages of all the CTA's tiles as one stream.
+//   * Row sums: A = the staged tile (ldmatrix), B = W digit fragments.  Column sums: B = the staged tile through ldmatrix.trans AS IT IS
+//     (two rows of a column pair per register), A = psi digits with the other column parity's slots zeroed -- no byte transpose.
+//   * The boxes of a row are dealt evenly over the column blocks; tiles are walked in storage order from per-CTA lists.
+// Real build only (tensor maps come from the driver entry point that kernels_tc.cuh resolves); the emulated build substitutes
+// tests/cuda_emul/kernels_ypass_tma_stub.h and never selects the kernel.
 #pragma once
 #include <vector>
 #include "kernels_ypass.cuh"
